@@ -1,0 +1,256 @@
+"""TEST INFRASTRUCTURE - CPU oracle of the reference model graphs.
+
+Restates, with torch CPU ops and the helpers in oracle/tf_ops.py, the numeric
+path of
+  full        reference models/model_full.py:208-599, 620-657, 918-1079
+  summarizer  reference models/baselines/model_summarizer.py:264-397, 834-847
+  synthesis   reference models/baselines/model_synthesis.py:212-489, 795-808
+structured like the reference (k unrolled encoder copies with shared weights,
+step-by-step LSTM loops) so it is also a fair stand-in for "the TF1 graph on
+CPU" when timed.  PARITY UNPINNED: the reference has no tests for this path
+and TF-1.3 is not runnable here (see oracle/tf_ops.py header).
+
+Never imported by the product path.
+"""
+import numpy as np
+import torch
+
+from demo2program_b200.manifest import build_manifests
+from . import tf_ops as T
+
+
+class OracleModel:
+    def __init__(self, cfg, flat_params, flat_state, dtype=torch.float64,
+                 is_train=True):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.is_train = is_train
+        self.pm, self.sm = build_manifests(cfg)
+        self.flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+        self.flat.requires_grad_(True)
+        self.state = torch.tensor(np.asarray(flat_state), dtype=dtype)
+        self.new_state = self.state.clone()
+
+    # -- parameter access ---------------------------------------------------
+    def p(self, name):
+        e = self.pm[name]
+        return self.flat[e.offset:e.offset + e.size].reshape(e.shape)
+
+    def s(self, name):
+        e = self.sm[name]
+        return self.state[e.offset:e.offset + e.size].reshape(e.shape)
+
+    def _set_state(self, name, val):
+        e = self.sm[name]
+        self.new_state[e.offset:e.offset + e.size] = val.detach().reshape(-1)
+
+    def _bn(self, x, scope):
+        """BN under `scope`; with k reuse-calls per step the moving stats are
+        updated k times in sequence (reference models/ops.py:20-23 with
+        updates_collections=None)."""
+        b = scope + '/BatchNorm/'
+        e_m, e_v = self.sm[b + 'moving_mean'], self.sm[b + 'moving_variance']
+        mm = self.new_state[e_m.offset:e_m.offset + e_m.size]
+        mv = self.new_state[e_v.offset:e_v.offset + e_v.size]
+        y, nmm, nmv = T.batch_norm(x, self.p(b + 'gamma'), self.p(b + 'beta'),
+                                   mm.clone(), mv.clone(), self.is_train)
+        if self.is_train:
+            self._set_state(b + 'moving_mean', nmm)
+            self._set_state(b + 'moving_variance', nmv)
+        return y
+
+    # -- reference sub-graphs -------------------------------------------------
+    def state_encoder(self, s):
+        """State_Encoder, reference models/model_full.py:216-231: conv ->
+        lrelu -> BN per layer.  s [N,h,w,d] -> [N,F]."""
+        x = s
+        for li in range(len(self.cfg.conv_channels())):
+            sc = 'Demo_Encoder/State_Encoder/conv%d' % (li + 1)
+            x = T.conv2d_3x3_s2_same(x, self.p(sc + '/Conv/weights'),
+                                     self.p(sc + '/Conv/biases'))
+            x = self._bn(T.lrelu(x), sc + '/bn_act')
+        return x.reshape(x.shape[0], -1)
+
+    def demo_encoder(self, s_h_i, len_i, per_i=None):
+        """Demo_Encoder, reference models/model_full.py:235-258."""
+        B, Tm = s_h_i.shape[:2]
+        f = self.state_encoder(s_h_i.reshape((B * Tm,) + s_h_i.shape[2:]))
+        f = f.reshape(B, Tm, -1)
+        if per_i is not None:
+            f = torch.cat([f, per_i], dim=-1)
+        sc = 'Demo_Encoder/rnn/basic_lstm_cell/'
+        return T.dynamic_rnn(f, len_i, self.p(sc + 'kernel'), self.p(sc + 'bias'))
+
+    def rn_pool(self, feat, scope):
+        """rn_pool, reference models/model_full.py:333-349. feat [B,k,H]."""
+        B, k, H = feat.shape
+        tile1 = feat.unsqueeze(1).expand(B, k, k, H)
+        tile2 = feat.unsqueeze(2).expand(B, k, k, H)
+        x = torch.cat([tile1, tile2], dim=3).reshape(B * k * k, 2 * H)
+        for fc in ('fc1', 'fc2'):
+            sc = '%s/rn_pool/%s' % (scope, fc)
+            x = x @ self.p(sc + '/fully_connected/weights') + \
+                self.p(sc + '/fully_connected/biases')
+            x = self._bn(T.lrelu(x), sc + '/bn_act')
+        return x.reshape(B, k, k, H).mean(1).mean(1)
+
+    def token_decoder(self, scope, h0, c0, gt_tokens, seq_len, max_len, vocab):
+        """LSTM_Decoder (teacher forcing), reference models/model_full.py:440-490."""
+        start = torch.full_like(gt_tokens[:, :1], vocab + 1)   # out of range (F6)
+        shifted = torch.cat([start, gt_tokens[:, :-1]], dim=1)
+        emb = T.embedding_lookup_gpu(
+            self.p(scope + '/Token_Embedding/embedding_map'), shifted)
+        d = scope + '/dynamic_decoder/'
+        return T.decode_training(
+            emb, seq_len, c0, h0, self.p(d + 'basic_lstm_cell/kernel'),
+            self.p(d + 'basic_lstm_cell/bias'),
+            self.p(d + 'output_projection/kernel'), max_len)
+
+    def token_decoder_greedy(self, scope, h0, c0, max_len, vocab, end_id):
+        table = self.p(scope + '/Token_Embedding/embedding_map')
+        d = scope + '/dynamic_decoder/'
+        return T.decode_greedy(
+            lambda ids: T.embedding_lookup_gpu(table, ids), vocab, end_id,
+            c0, h0, self.p(d + 'basic_lstm_cell/kernel'),
+            self.p(d + 'basic_lstm_cell/bias'),
+            self.p(d + 'output_projection/kernel'), max_len)
+
+    # -- whole graphs -----------------------------------------------------------
+    def forward(self, batch, greedy=False):
+        cfg, dt = self.cfg, self.dtype
+        s_h = torch.as_tensor(np.asarray(batch['s_h'])).to(dt)
+        demo_len = torch.as_tensor(np.asarray(batch['demo_len'])).long()
+        program_len = torch.as_tensor(np.asarray(batch['program_len'])).long()[:, 0]
+        program = torch.as_tensor(np.asarray(batch['program'])).to(dt)
+        ptoks = torch.as_tensor(np.asarray(batch['program_tokens'])).long()
+        k = cfg.k
+        out = {}
+        # Demo -> demo feature (k copies, shared weights; model_full.py:373-379)
+        hist1, h1, c1 = [], [], []
+        for i in range(k):
+            y, h, c = self.demo_encoder(s_h[:, i], demo_len[:, i])
+            hist1.append(y), h1.append(h), c1.append(c)
+        if cfg.model == 'synthesis_baseline':
+            hs, cs = torch.stack(h1, 1), torch.stack(c1, 1)
+            if cfg.demo_aggregation == 'avgpool':
+                h_sum, c_sum = hs.mean(1), cs.mean(1)
+            elif cfg.demo_aggregation == 'maxpool':
+                h_sum, c_sum = hs.max(1).values, cs.max(1).values
+            else:
+                raise ValueError('Unknown demo aggregation type')
+            demo_h, demo_c = h1, c1
+        else:
+            summary_h = torch.stack(h1, 1).mean(1)
+            summary_c = torch.stack(c1, 1).mean(1)
+            sc = 'SecondPathEncoder/rnn/basic_lstm_cell/'
+            demo_h, demo_c = [], []
+            for i in range(k):
+                _, h, c = T.dynamic_rnn(hist1[i], demo_len[:, i],
+                                        self.p(sc + 'kernel'), self.p(sc + 'bias'),
+                                        c0=summary_c, h0=summary_h)
+                demo_h.append(h), demo_c.append(c)
+            hs, cs = torch.stack(demo_h, 1), torch.stack(demo_c, 1)
+            h_sum = self.rn_pool(hs, 'demo_h_summary')
+            c_sum = self.rn_pool(cs, 'demo_c_summary')
+            if cfg.model == 'full':  # full: mean + rn (model_full.py:357-359)
+                h_sum = hs.mean(1) + h_sum
+                c_sum = cs.mean(1) + c_sum
+        out['demo_h_summary'], out['demo_c_summary'] = h_sum, c_sum
+
+        V, L = cfg.dim_program_token, cfg.max_program_len
+        logits = self.token_decoder('Program_Decoder', h_sum, c_sum, ptoks,
+                                    program_len, L, V)
+        out['pred_program'] = logits.transpose(1, 2)           # [B,V,L]
+        program_loss = T.softmax_ce_loss(logits, program.transpose(1, 2),
+                                         program_len)
+        out['program_loss'] = program_loss
+        loss = program_loss
+        if greedy:
+            gl, glen, gtok = self.token_decoder_greedy(
+                'Program_Decoder', h_sum, c_sum, L, V, cfg.program_end_token)
+            out['greedy_pred_program'] = gl.transpose(1, 2)
+            out['greedy_pred_program_len'] = glen.unsqueeze(1)
+            out['greedy_program_tokens'] = gtok
+
+        if cfg.model == 'full':
+            A, Tm, P = cfg.action_space, cfg.max_demo_len, cfg.per_dim
+            a_h = torch.as_tensor(np.asarray(batch['a_h'])).to(dt)
+            a_tok = torch.as_tensor(np.asarray(batch['a_h_tokens'])).long()
+            per = torch.as_tensor(np.asarray(batch['per'])).to(dt)
+            act_loss, per_loss = 0, 0
+            pa, pp, ga, galen = [], [], [], []
+            for i in range(k):
+                lg = self.token_decoder('Action_Decoder', demo_h[i], demo_c[i],
+                                        a_tok[:, i], demo_len[:, i], Tm, A)
+                pa.append(lg)
+                act_loss = act_loss + T.softmax_ce_loss(lg, a_h[:, i],
+                                                        demo_len[:, i])
+                if greedy:
+                    g, gln, _ = self.token_decoder_greedy(
+                        'Action_Decoder', demo_h[i], demo_c[i], Tm, A, A - 1)
+                    ga.append(g), galen.append(gln)
+            for i in range(k):
+                # Per_Encoder: fc(act=None) + BN over [B,T] (model_full.py:308-316)
+                sc = 'Per_Decoder/Per_Encoder/fc2'
+                x = per[:, i] @ self.p(sc + '/fully_connected/weights') + \
+                    self.p(sc + '/fully_connected/biases')
+                x = self._bn(x, sc + '/bn_act')
+                d = 'Per_Decoder/dynamic_decoder/'
+                lg = T.decode_training(
+                    x, demo_len[:, i], demo_c[i], demo_h[i],
+                    self.p(d + 'basic_lstm_cell/kernel'),
+                    self.p(d + 'basic_lstm_cell/bias'),
+                    self.p(d + 'output_projection/kernel'), Tm)
+                pp.append(lg)
+                per_loss = per_loss + T.sigmoid_ce_loss(lg, per[:, i],
+                                                        demo_len[:, i])
+            out['avg_action_loss'] = act_loss / k
+            out['avg_per_loss'] = per_loss / k
+            out['pred_action'] = torch.stack(pa, 1)   # [B,k,T,A]
+            out['pred_per'] = torch.stack(pp, 1)      # [B,k,T,P]
+            if greedy:
+                out['greedy_pred_action'] = torch.stack(ga, 1)
+                out['greedy_pred_action_len'] = torch.stack(galen, 1)
+            loss = loss + act_loss / k + per_loss / k
+        out['loss'] = loss
+        return out
+
+    def loss_and_grad(self, batch):
+        """Returns (loss float, flat grad tensor, outputs)."""
+        if self.flat.grad is not None:
+            self.flat.grad = None
+        out = self.forward(batch)
+        out['loss'].backward()
+        return float(out['loss'].detach()), self.flat.grad.detach().clone(), out
+
+    def commit_state(self):
+        self.state = self.new_state.clone()
+
+
+class OracleTrainer:
+    """optimize_loss(Adam, clip_gradients=20.0) over the flat buffer
+    (reference trainer.py:82-109; A.10)."""
+
+    def __init__(self, cfg, flat_params, flat_state, dtype=torch.float64,
+                 lr=1e-3, clip=20.0):
+        self.model = OracleModel(cfg, flat_params, flat_state, dtype)
+        self.m = torch.zeros_like(self.model.flat.detach())
+        self.v = torch.zeros_like(self.m)
+        self.step = 0
+        self.lr, self.clip = lr, clip
+        self.cfg = cfg
+
+    def learning_rate(self):
+        if self.cfg.lr_weight_decay:  # exponential_decay staircase (trainer.py:82-91)
+            return self.lr * 0.5 ** (self.step // 10000)
+        return self.lr
+
+    def train_step(self, batch):
+        loss, grad, out = self.model.loss_and_grad(batch)
+        (grad,), norm = T.clip_by_global_norm([grad], self.clip)
+        lr = self.learning_rate()
+        self.step += 1
+        with torch.no_grad():
+            T.adam_step(self.model.flat, grad, self.m, self.v, self.step, lr=lr)
+        self.model.commit_state()
+        return loss, float(norm), out
