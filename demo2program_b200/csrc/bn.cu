@@ -1,0 +1,378 @@
+// Per-slice BatchNorm machinery over [rows, C] matrices.
+//
+// Restates tf.contrib.layers.batch_norm(decay=0.9, eps=1e-3, center, scale,
+// updates_collections=None) as called at reference models/ops.py:20-23.
+// The reference instantiates the encoder k times with shared weights, so batch
+// statistics are per demonstration index ("slice"); slice(row) =
+// (row / seg) % nsl lets one launch cover all k copies for every layout used on
+// the path (frame-major conv activations: seg = T*OH*OW; time-major [T,R,C]
+// rows: seg = 1; RN-pool rows: nsl = 1).
+//
+// All reductions are two-stage (per-block partials in a caller-provided
+// workspace, then a fixed-order finalize) so results are run-to-run
+// deterministic.
+#include "common.cuh"
+
+namespace d2p {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ long long slice_row(long long q, int seg, int nsl, int sl) {
+    // q: slice-local row index -> global row
+    return ((q / seg) * nsl + sl) * (long long)seg + (q % seg);
+}
+
+// partial[(sl * nchunk + chunk) * C + c] = {sum a, sum b} where
+//   MODE 0: a = x,  b = x*x           (forward statistics)
+//   MODE 1: a = dy, b = dy * xhat     (backward; xhat from mean/rstd)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+colstats_partial(const float* __restrict__ X, const float* __restrict__ DY,
+                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                 long long rows_per_slice, int C, int seg, int nsl, int rows_per_chunk,
+                 float2* __restrict__ partial) {
+    extern __shared__ float2 red[];  // [RL][CT]
+    const int chunk = blockIdx.x, sl = blockIdx.y, nchunk = gridDim.x;
+    const int CT = C < kThreads ? C : kThreads;
+    const int RL = kThreads / CT;
+    const int rl = threadIdx.x / CT, ct = threadIdx.x % CT;
+    const bool active = rl < RL;
+    long long q0 = (long long)chunk * rows_per_chunk;
+    long long q1 = q0 + rows_per_chunk;
+    if (q1 > rows_per_slice) q1 = rows_per_slice;
+    for (int c0 = 0; c0 < C; c0 += CT) {   // trip count is block-uniform
+        const int c = c0 + ct;
+        const bool valid = active && c < C;
+        float sa = 0.f, sb = 0.f;
+        if (valid) {
+            float mu = 0.f, rs = 0.f;
+            if (MODE == 1) { mu = mean[sl * C + c]; rs = rstd[sl * C + c]; }
+            for (long long q = q0 + rl; q < q1; q += RL) {
+                long long row = slice_row(q, seg, nsl, sl);
+                float x = X[row * C + c];
+                if (MODE == 0) { sa += x; sb += x * x; }
+                else { float dy = DY[row * C + c]; sa += dy; sb += dy * (x - mu) * rs; }
+            }
+        }
+        if (active) red[rl * CT + ct] = make_float2(sa, sb);
+        __syncthreads();
+        if (threadIdx.x < CT && c < C) {
+            float2 acc = red[ct];
+            for (int r = 1; r < RL; ++r) { acc.x += red[r * CT + ct].x; acc.y += red[r * CT + ct].y; }
+            partial[((size_t)sl * nchunk + chunk) * C + c] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Forward finalize: one thread per channel, slices in order (the reference
+// updates the moving stats once per reuse call, i = 0..k-1).
+__global__ void bn_fwd_finalize(const float2* __restrict__ partial, int nchunk, int C, int nsl,
+                                double count, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                float* __restrict__ moving_var, float eps, float decay,
+                                int training, float* __restrict__ mean_out,
+                                float* __restrict__ rstd_out, float* __restrict__ scale,
+                                float* __restrict__ shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float g = gamma[c], b = beta[c];
+    if (!training) {
+        float mu = moving_mean[c], rs = rsqrtf(moving_var[c] + eps);
+        for (int sl = 0; sl < nsl; ++sl) {
+            mean_out[sl * C + c] = mu; rstd_out[sl * C + c] = rs;
+            scale[sl * C + c] = g * rs; shift[sl * C + c] = b - mu * g * rs;
+        }
+        return;
+    }
+    float mm = moving_mean[c], mv = moving_var[c];
+    for (int sl = 0; sl < nsl; ++sl) {
+        double s = 0.0, s2 = 0.0;
+        for (int j = 0; j < nchunk; ++j) {
+            float2 p = partial[((size_t)sl * nchunk + j) * C + c];
+            s += p.x; s2 += p.y;
+        }
+        double mu = s / count;
+        double var = s2 / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        float muf = (float)mu, varf = (float)var;
+        float rs = (float)(1.0 / sqrt(var + (double)eps));
+        mean_out[sl * C + c] = muf; rstd_out[sl * C + c] = rs;
+        scale[sl * C + c] = g * rs; shift[sl * C + c] = b - muf * g * rs;
+        mm -= (mm - muf) * (1.f - decay);
+        mv -= (mv - varf) * (1.f - decay);
+    }
+    moving_mean[c] = mm; moving_var[c] = mv;
+}
+
+// Backward finalize: coefficients for dx and the shared-parameter grads.
+//   dgamma[c] += sum_sl sum dy*xhat ; dbeta[c] += sum_sl sum dy
+//   k1[sl,c] = sum(dy)/M ; k2[sl,c] = sum(dy*xhat)/M
+__global__ void bn_bwd_finalize(const float2* __restrict__ partial, int nchunk, int C, int nsl,
+                                double count, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, float* __restrict__ k1,
+                                float* __restrict__ k2, int training) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double tg = 0.0, tb = 0.0;
+    for (int sl = 0; sl < nsl; ++sl) {
+        double s = 0.0, s2 = 0.0;
+        for (int j = 0; j < nchunk; ++j) {
+            float2 p = partial[((size_t)sl * nchunk + j) * C + c];
+            s += p.x; s2 += p.y;
+        }
+        tb += s; tg += s2;
+        k1[sl * C + c] = training ? (float)(s / count) : 0.f;
+        k2[sl * C + c] = training ? (float)(s2 / count) : 0.f;
+    }
+    dgamma[c] += (float)tg;
+    dbeta[c] += (float)tb;
+}
+
+// y = x*scale + shift, optionally permuting rows (r*T + t) -> (t*R + r)
+__global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, long long rows,
+                                int C, int seg, int nsl, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int permT, int permR) {
+    long long total = rows * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long row = idx / C;
+        int c = (int)(idx % C);
+        int sl = (int)((row / seg) % nsl);
+        float y = X[idx] * scale[sl * C + c] + shift[sl * C + c];
+        long long orow = row;
+        if (permT > 0) { long long r = row / permT; int t = (int)(row % permT); orow = (long long)t * permR + r; }
+        Y[orow * C + c] = y;
+    }
+}
+
+// da = gamma*rstd*(dy - k1 - xhat*k2); if ACT: dz = da * lrelu'(a) (a = post-activation
+// value that was normalised).  DY may be row-permuted like bn_apply's output.
+template <bool ACT>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ A, const float* __restrict__ DY,
+                                    float* __restrict__ DZ, long long rows, int C, int seg, int nsl,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ k1,
+                                    const float* __restrict__ k2, int permT, int permR) {
+    long long total = rows * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long row = idx / C;
+        int c = (int)(idx % C);
+        int sl = (int)((row / seg) % nsl);
+        long long drow = row;
+        if (permT > 0) { long long r = row / permT; int t = (int)(row % permT); drow = (long long)t * permR + r; }
+        float a = A[idx];
+        float rs = rstd[sl * C + c];
+        float xh = (a - mean[sl * C + c]) * rs;
+        float da = gamma[c] * rs * (DY[drow * C + c] - k1[sl * C + c] - xh * k2[sl * C + c]);
+        DZ[idx] = ACT ? da * lrelu_grad_from_out(a) : da;
+    }
+}
+
+__global__ void colsum_finalize(const float2* __restrict__ partial, int nchunk, int C,
+                                float* __restrict__ out, float beta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int j = 0; j < nchunk; ++j) s += partial[(size_t)j * C + c].x;
+    out[c] = (beta != 0.f ? beta * out[c] : 0.f) + (float)s;
+}
+
+// Gather rows of a slice-permuted matrix: used when DY is permuted but stats
+// must be read in A's row order.
+__global__ void permute_rows_kernel(const float* __restrict__ X, float* __restrict__ Y,
+                                    long long rows, int C, int permT, int permR) {
+    long long total = rows * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long row = idx / C;
+        int c = (int)(idx % C);
+        long long r = row / permT; int t = (int)(row % permT);
+        Y[idx] = X[((long long)t * permR + r) * C + c];
+    }
+}
+
+inline int pick_chunks(long long rows_per_slice, int nsl, int* rows_per_chunk) {
+    // aim for ~4 waves of blocks overall, at least 64 rows per block
+    long long target_blocks = 4LL * kNumSMs / (nsl > 0 ? nsl : 1);
+    if (target_blocks < 1) target_blocks = 1;
+    long long rpc = (rows_per_slice + target_blocks - 1) / target_blocks;
+    if (rpc < 64) rpc = 64;
+    *rows_per_chunk = (int)rpc;
+    return (int)((rows_per_slice + rpc - 1) / rpc);
+}
+
+inline int ew_blocks(long long total) {
+    long long b = (total + 255) / 256;
+    long long cap = 8LL * kNumSMs;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+size_t bn_ws_bytes(long long rows, int C, int nsl) {
+    int rpc;
+    int nchunk = pick_chunks(rows / nsl, nsl, &rpc);
+    return (size_t)nsl * nchunk * C * sizeof(float2);
+}
+
+// Forward statistics + scale/shift. stats layout: mean|rstd|scale|shift, each [nsl, C].
+int bn_forward_stats(cudaStream_t st, const float* X, long long rows, int C, int seg, int nsl,
+                     const float* gamma, const float* beta, float* moving_mean,
+                     float* moving_var, int training, float* stats, void* ws, size_t ws_bytes) {
+    D2P_REQUIRE(rows % ((long long)seg * nsl) == 0, "bn: rows %lld not divisible by seg*nsl", rows);
+    float* mean = stats; float* rstd = stats + (size_t)nsl * C;
+    float* scale = rstd + (size_t)nsl * C; float* shift = scale + (size_t)nsl * C;
+    int rpc = 0, nchunk = 0;
+    if (training) {
+        nchunk = pick_chunks(rows / nsl, nsl, &rpc);
+        D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
+        int CT = C < kThreads ? C : kThreads;
+        size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
+        colstats_partial<0><<<dim3(nchunk, nsl), kThreads, sm, st>>>(
+            X, nullptr, nullptr, nullptr, rows / nsl, C, seg, nsl, rpc, (float2*)ws);
+        D2P_CHECK_LAUNCH();
+    }
+    bn_fwd_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, nsl,
+                                                 (double)(rows / nsl), gamma, beta, moving_mean,
+                                                 moving_var, 1e-3f, 0.9f, training, mean, rstd,
+                                                 scale, shift);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+int bn_apply(cudaStream_t st, const float* X, float* Y, long long rows, int C, int seg, int nsl,
+             const float* stats, int permT, int permR) {
+    const float* scale = stats + 2 * (size_t)nsl * C;
+    const float* shift = stats + 3 * (size_t)nsl * C;
+    bn_apply_kernel<<<ew_blocks(rows * C), 256, 0, st>>>(X, Y, rows, C, seg, nsl, scale, shift,
+                                                        permT, permR);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+// Backward through BN (and optionally the activation before it).
+//   A: saved post-activation (pre-BN) values, DY: grad wrt BN output (row-permuted
+//   if permT > 0), DZ: out grad wrt the pre-activation (or pre-BN value when !act).
+//   coef: scratch [2, nsl, C]. dgamma/dbeta accumulate.
+int bn_backward(cudaStream_t st, const float* A, const float* DY, float* DZ, long long rows, int C,
+                int seg, int nsl, const float* gamma, const float* stats, float* dgamma,
+                float* dbeta, int training, int act, float* coef, void* ws, size_t ws_bytes,
+                int permT, int permR, float* dy_tmp) {
+    const float* mean = stats; const float* rstd = stats + (size_t)nsl * C;
+    const float* dy_lin = DY;
+    if (permT > 0) {
+        // statistics kernels read DY in A's row order
+        D2P_REQUIRE(dy_tmp != nullptr, "bn_backward: permuted DY needs dy_tmp");
+        permute_rows_kernel<<<ew_blocks(rows * C), 256, 0, st>>>(DY, dy_tmp, rows, C, permT, permR);
+        D2P_CHECK_LAUNCH();
+        dy_lin = dy_tmp;
+    }
+    int rpc;
+    int nchunk = pick_chunks(rows / nsl, nsl, &rpc);
+    D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
+    int CT = C < kThreads ? C : kThreads;
+    size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
+    colstats_partial<1><<<dim3(nchunk, nsl), kThreads, sm, st>>>(A, dy_lin, mean, rstd, rows / nsl,
+                                                                C, seg, nsl, rpc, (float2*)ws);
+    D2P_CHECK_LAUNCH();
+    float* k1 = coef; float* k2 = coef + (size_t)nsl * C;
+    bn_bwd_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, nsl,
+                                                 (double)(rows / nsl), dgamma, dbeta, k1, k2,
+                                                 training);
+    D2P_CHECK_LAUNCH();
+    if (act)
+        bn_bwd_apply_kernel<true><<<ew_blocks(rows * C), 256, 0, st>>>(
+            A, dy_lin, DZ, rows, C, seg, nsl, gamma, mean, rstd, k1, k2, 0, 0);
+    else
+        bn_bwd_apply_kernel<false><<<ew_blocks(rows * C), 256, 0, st>>>(
+            A, dy_lin, DZ, rows, C, seg, nsl, gamma, mean, rstd, k1, k2, 0, 0);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+// out[c] = beta*out[c] + sum_rows X[row, c]
+int colsum(cudaStream_t st, const float* X, long long rows, int C, float* out, float beta, void* ws,
+           size_t ws_bytes) {
+    int rpc;
+    int nchunk = pick_chunks(rows, 1, &rpc);
+    D2P_REQUIRE(ws_bytes >= (size_t)nchunk * C * sizeof(float2), "colsum: workspace too small");
+    int CT = C < kThreads ? C : kThreads;
+    size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
+    colstats_partial<0><<<dim3(nchunk, 1), kThreads, sm, st>>>(X, nullptr, nullptr, nullptr, rows, C,
+                                                              1, 1, rpc, (float2*)ws);
+    D2P_CHECK_LAUNCH();
+    colsum_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, out, beta);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace d2p
+
+// ---- fully-connected -> (lrelu) -> BN, the reference's ops.fc (models/ops.py:149-155) ----
+using namespace d2p;
+
+static size_t fc_bn_part_bytes(long long rows, int Cout, int nsl) {
+    size_t a = bn_ws_bytes(rows, Cout, nsl), b = bn_ws_bytes(rows, Cout, 1);
+    return ((a > b ? a : b) + 255) & ~(size_t)255;
+}
+
+extern "C" size_t d2p_fc_bn_saved_floats(long long rows, int Cout, int nsl) {
+    return (size_t)rows * Cout + 4 * (size_t)nsl * Cout;
+}
+
+extern "C" size_t d2p_fc_bn_ws_bytes(long long rows, int Cout, int nsl) {
+    size_t dz = (((size_t)rows * Cout * sizeof(float)) + 255) & ~(size_t)255;
+    size_t coef = ((2 * (size_t)nsl * Cout * sizeof(float)) + 255) & ~(size_t)255;
+    return dz + coef + fc_bn_part_bytes(rows, Cout, nsl);
+}
+
+namespace d2p { namespace {
+__global__ void lrelu_inplace_k(float* __restrict__ x, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        x[i] = lrelu_f(x[i]);
+}
+} }
+
+extern "C" int d2p_fc_bn_fwd(const float* X, long long rows, int Cin, int Cout, int seg, int nsl,
+                             int act, const d2p_fc_bn* p, float* Y, float* saved, int training,
+                             void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(X && p && Y && saved && ws, "fc_bn fwd: null buffer");
+    D2P_REQUIRE(ws_bytes >= d2p_fc_bn_ws_bytes(rows, Cout, nsl), "fc_bn fwd: workspace too small");
+    float* A = saved; float* stats = saved + (size_t)rows * Cout;
+    D2P_TRY(gemm(st, false, false, (int)rows, Cout, Cin, 1.f, X, Cin, p->w, Cout, 0.f, A, Cout, p->b));
+    if (act) {
+        lrelu_inplace_k<<<ew_blocks(rows * Cout), 256, 0, st>>>(A, (size_t)rows * Cout);
+        D2P_CHECK_LAUNCH();
+    }
+    D2P_TRY(bn_forward_stats(st, A, rows, Cout, seg, nsl, p->gamma, p->beta, p->moving_mean,
+                             p->moving_var, training, stats, ws, ws_bytes));
+    D2P_TRY(bn_apply(st, A, Y, rows, Cout, seg, nsl, stats, 0, 0));
+    return 0;
+}
+
+extern "C" int d2p_fc_bn_bwd(const float* X, long long rows, int Cin, int Cout, int seg, int nsl,
+                             int act, const d2p_fc_bn* p, const float* dY, const float* saved,
+                             float* dX, int training, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(X && p && dY && saved && ws, "fc_bn bwd: null buffer");
+    D2P_REQUIRE(p->dw && p->db && p->dgamma && p->dbeta, "fc_bn bwd: null grad buffer");
+    D2P_REQUIRE(ws_bytes >= d2p_fc_bn_ws_bytes(rows, Cout, nsl), "fc_bn bwd: workspace too small");
+    const float* A = saved; const float* stats = saved + (size_t)rows * Cout;
+    char* w = (char*)ws;
+    size_t dzb = (((size_t)rows * Cout * sizeof(float)) + 255) & ~(size_t)255;
+    size_t coefb = ((2 * (size_t)nsl * Cout * sizeof(float)) + 255) & ~(size_t)255;
+    float* dZ = (float*)w; float* coef = (float*)(w + dzb);
+    void* part = w + dzb + coefb; size_t part_bytes = ws_bytes - dzb - coefb;
+    D2P_TRY(bn_backward(st, A, dY, dZ, rows, Cout, seg, nsl, p->gamma, stats, p->dgamma, p->dbeta,
+                        training, act, coef, part, part_bytes, 0, 0, nullptr));
+    D2P_TRY(colsum(st, dZ, rows, Cout, p->db, 1.f, part, part_bytes));
+    D2P_TRY(gemm(st, true, false, Cin, Cout, (int)rows, 1.f, X, Cin, dZ, Cout, 1.f, p->dw, Cout));
+    if (dX) D2P_TRY(gemm(st, false, true, (int)rows, Cin, Cout, 1.f, dZ, Cout, p->w, Cout, 0.f, dX, Cin));
+    return 0;
+}

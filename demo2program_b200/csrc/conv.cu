@@ -1,0 +1,461 @@
+// Demonstration-frame CNN encoder (State_Encoder, reference
+// models/model_full.py:216-231 through ops.conv2d, models/ops.py:27-33):
+// per layer slim.conv2d(3x3, stride 2, SAME, bias) -> lrelu(0.2) -> BatchNorm
+// with train-mode batch statistics per demonstration index (the reference
+// instantiates the encoder k times, model_full.py:373-376).
+//
+// Layout: frames arrive as stored, [B, k, T, h, w, d] (u8 for Karel's bool /
+// ViZDoom's 0..255, or f32 as the reference feeds); frame n = (b*k+i)*T + t,
+// slice(n) = (n / T) % k.  Activations are NHWC fp32.  The BatchNorm of layer
+// l is applied on the fly when layer l+1 loads its input (scale/shift per
+// slice), so each layer is one pass: conv + bias + lrelu -> a_l, then a
+// two-stage statistics reduction.  The final feature is written time-major
+// [T, R, F] (R = B*k) for the LSTM.
+//
+// TF SAME geometry: pad_before = pad_total / 2, so every
+// Karel layer and ViZDoom L1-L4 pad (0 top/left, 1 bottom/right).
+#include "common.cuh"
+
+namespace d2p {
+
+int bn_forward_stats(cudaStream_t, const float*, long long, int, int, int, const float*,
+                     const float*, float*, float*, int, float*, void*, size_t);
+int bn_apply(cudaStream_t, const float*, float*, long long, int, int, int, const float*, int, int);
+int bn_backward(cudaStream_t, const float*, const float*, float*, long long, int, int, int,
+                const float*, const float*, float*, float*, int, int, float*, void*, size_t, int,
+                int, float*);
+int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, size_t);
+size_t bn_ws_bytes(long long rows, int C, int nsl);
+int permute_frames(cudaStream_t, const float*, float*, int, int, int, int);
+int unpermute_frames(cudaStream_t, const float*, float*, int, int, int, int);
+
+namespace {
+
+constexpr int PX = 32;          // output pixels per tile
+constexpr int MAXC = 48;        // max channels of any layer on the path
+
+struct Geo {
+    int N, IH, IW, CIN, OH, OW, COUT, PT, PL, T, k;
+};
+
+template <typename IN_T>
+__device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (float)in[idx]; }
+
+// a[n,oy,ox,:] = lrelu(bias + sum_taps W[ky,kx,:,:]^T x(n, 2oy+ky-PT, 2ox+kx-PL, :))
+// where x = in*scale[slice]+shift[slice] (identity if scale == nullptr), zero outside.
+template <typename IN_T>
+__global__ void __launch_bounds__(128)
+conv_fwd_kernel(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_scale,
+                const float* __restrict__ in_shift, const float* __restrict__ W,
+                const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float P[MAXC][PX + 1];
+    __shared__ float Wt[MAXC][MAXC];
+    const int tid = threadIdx.x, px = tid % PX, grp = tid / PX;
+    const int cpg = g.COUT / 4;  // channels per thread (COUT % 4 == 0)
+    const long long npix = (long long)g.N * g.OH * g.OW;
+    const long long p0 = (long long)blockIdx.x * PX;
+    float acc[MAXC / 4];
+#pragma unroll
+    for (int j = 0; j < MAXC / 4; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        for (int idx = tid; idx < PX * g.CIN; idx += 128) {
+            int pp = idx / g.CIN, ci = idx % g.CIN;
+            long long p = p0 + pp;
+            float v = 0.f;
+            if (p < npix) {
+                int ox = (int)(p % g.OW);
+                int oy = (int)((p / g.OW) % g.OH);
+                long long n = p / ((long long)g.OW * g.OH);
+                int iy = 2 * oy + ky - g.PT, ix = 2 * ox + kx - g.PL;
+                if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
+                    v = load_in(in, (((size_t)n * g.IH + iy) * g.IW + ix) * g.CIN + ci);
+                    if (in_scale) {
+                        int sl = (int)((n / g.T) % g.k);
+                        v = v * in_scale[sl * g.CIN + ci] + in_shift[sl * g.CIN + ci];
+                    }
+                }
+            }
+            P[ci][pp] = v;
+        }
+        for (int idx = tid; idx < g.CIN * g.COUT; idx += 128)
+            Wt[idx / g.COUT][idx % g.COUT] = W[(size_t)tap * g.CIN * g.COUT + idx];
+        __syncthreads();
+        for (int ci = 0; ci < g.CIN; ++ci) {
+            float v = P[ci][px];
+#pragma unroll
+            for (int j = 0; j < MAXC / 4; ++j)
+                if (j < cpg) acc[j] = fmaf(v, Wt[ci][grp * cpg + j], acc[j]);
+        }
+        __syncthreads();
+    }
+    long long p = p0 + px;
+    if (p < npix) {
+#pragma unroll
+        for (int j = 0; j < MAXC / 4; ++j)
+            if (j < cpg) {
+                int c = grp * cpg + j;
+                out[p * g.COUT + c] = lrelu_f(acc[j] + bias[c]);
+            }
+    }
+}
+
+// dX[n,iy,ix,ci] = sum_{taps, co} dZ[n,oy,ox,co] * W[ky,kx,ci,co], oy = (iy+PT-ky)/2 (exact)
+__global__ void __launch_bounds__(128)
+conv_bwd_dx_kernel(Geo g, const float* __restrict__ dZ, const float* __restrict__ W,
+                   float* __restrict__ dX) {
+    __shared__ float P[MAXC][PX + 1];
+    __shared__ float Wt[MAXC][MAXC + 1];  // [ci][co]
+    const int tid = threadIdx.x, px = tid % PX, grp = tid / PX;
+    const int cpg = g.CIN / 4;
+    const long long npix = (long long)g.N * g.IH * g.IW;
+    const long long p0 = (long long)blockIdx.x * PX;
+    float acc[MAXC / 4];
+#pragma unroll
+    for (int j = 0; j < MAXC / 4; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        for (int idx = tid; idx < PX * g.COUT; idx += 128) {
+            int pp = idx / g.COUT, co = idx % g.COUT;
+            long long p = p0 + pp;
+            float v = 0.f;
+            if (p < npix) {
+                int ix = (int)(p % g.IW);
+                int iy = (int)((p / g.IW) % g.IH);
+                long long n = p / ((long long)g.IW * g.IH);
+                int ty = iy + g.PT - ky, tx = ix + g.PL - kx;
+                if (ty >= 0 && tx >= 0 && (ty & 1) == 0 && (tx & 1) == 0) {
+                    int oy = ty >> 1, ox = tx >> 1;
+                    if (oy < g.OH && ox < g.OW)
+                        v = dZ[(((size_t)n * g.OH + oy) * g.OW + ox) * g.COUT + co];
+                }
+            }
+            P[co][pp] = v;
+        }
+        for (int idx = tid; idx < g.CIN * g.COUT; idx += 128)
+            Wt[idx / g.COUT][idx % g.COUT] = W[(size_t)tap * g.CIN * g.COUT + idx];
+        __syncthreads();
+        for (int co = 0; co < g.COUT; ++co) {
+            float v = P[co][px];
+#pragma unroll
+            for (int j = 0; j < MAXC / 4; ++j)
+                if (j < cpg) acc[j] = fmaf(v, Wt[grp * cpg + j][co], acc[j]);
+        }
+        __syncthreads();
+    }
+    long long p = p0 + px;
+    if (p < npix) {
+#pragma unroll
+        for (int j = 0; j < MAXC / 4; ++j)
+            if (j < cpg) dX[p * g.CIN + grp * cpg + j] = acc[j];
+    }
+}
+
+// partial[(blk*9 + tap) * CIN*COUT + ci*COUT + co] = sum over the block's pixel
+// chunk of x(p@tap, ci) * dZ(p, co).  grid = (nblk, 9).
+template <typename IN_T>
+__global__ void __launch_bounds__(256)
+conv_bwd_dw_kernel(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_scale,
+                   const float* __restrict__ in_shift, const float* __restrict__ dZ,
+                   int pix_per_block, float* __restrict__ partial) {
+    __shared__ float Xs[PX][MAXC + 1];
+    __shared__ float Zs[PX][MAXC + 1];
+    const int tid = threadIdx.x, tap = blockIdx.y, ky = tap / 3, kx = tap % 3;
+    const long long npix = (long long)g.N * g.OH * g.OW;
+    long long p0 = (long long)blockIdx.x * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > npix) p1 = npix;
+    const int nout = g.CIN * g.COUT;
+    float acc[9];  // ceil(48*48 / 256)
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+    for (long long pb = p0; pb < p1; pb += PX) {
+        for (int idx = tid; idx < PX * g.CIN; idx += 256) {
+            int pp = idx / g.CIN, ci = idx % g.CIN;
+            long long p = pb + pp;
+            float v = 0.f;
+            if (p < p1) {
+                int ox = (int)(p % g.OW);
+                int oy = (int)((p / g.OW) % g.OH);
+                long long n = p / ((long long)g.OW * g.OH);
+                int iy = 2 * oy + ky - g.PT, ix = 2 * ox + kx - g.PL;
+                if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
+                    v = load_in(in, (((size_t)n * g.IH + iy) * g.IW + ix) * g.CIN + ci);
+                    if (in_scale) {
+                        int sl = (int)((n / g.T) % g.k);
+                        v = v * in_scale[sl * g.CIN + ci] + in_shift[sl * g.CIN + ci];
+                    }
+                }
+            }
+            Xs[pp][ci] = v;
+        }
+        for (int idx = tid; idx < PX * g.COUT; idx += 256) {
+            int pp = idx / g.COUT, co = idx % g.COUT;
+            long long p = pb + pp;
+            Zs[pp][co] = p < p1 ? dZ[p * g.COUT + co] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            int o = tid + j * 256;
+            if (o < nout) {
+                int ci = o / g.COUT, co = o % g.COUT;
+                float a = acc[j];
+#pragma unroll 8
+                for (int pp = 0; pp < PX; ++pp) a = fmaf(Xs[pp][ci], Zs[pp][co], a);
+                acc[j] = a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        int o = tid + j * 256;
+        if (o < nout) partial[((size_t)blockIdx.x * 9 + tap) * nout + o] = acc[j];
+    }
+}
+
+// dW[tap, o] += sum_blk partial[blk, tap, o]
+__global__ void conv_dw_reduce(const float* __restrict__ partial, int nblk, int n,
+                               float* __restrict__ dW) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + i];
+    dW[i] += (float)s;
+}
+
+inline int dw_blocks(long long npix, int* ppb) {
+    long long target = 2LL * kNumSMs;
+    long long per = (npix + target - 1) / target;
+    per = (per + PX - 1) / PX * PX;
+    if (per < 8 * PX) per = 8 * PX;
+    *ppb = (int)per;
+    return (int)((npix + per - 1) / per);
+}
+
+int fill_geo(const d2p_conv_desc* d, int layer, Geo* g) {
+    int ih = d->h, iw = d->w, cin = d->d;
+    for (int l = 0; l <= layer; ++l) {
+        int oh = (ih + 1) / 2, ow = (iw + 1) / 2;
+        int pth = (oh - 1) * 2 + 3 - ih; if (pth < 0) pth = 0;
+        int ptw = (ow - 1) * 2 + 3 - iw; if (ptw < 0) ptw = 0;
+        if (l == layer) {
+            g->N = d->B * d->k * d->T; g->IH = ih; g->IW = iw; g->CIN = cin;
+            g->OH = oh; g->OW = ow; g->COUT = d->layers[l].cout;
+            g->PT = pth / 2; g->PL = ptw / 2; g->T = d->T; g->k = d->k;
+        }
+        ih = oh; iw = ow; cin = d->layers[l].cout;
+    }
+    return 0;
+}
+
+int check_desc(const d2p_conv_desc* d) {
+    D2P_REQUIRE(d != nullptr, "conv: null descriptor");
+    D2P_REQUIRE(d->n_layers >= 1 && d->n_layers <= D2P_MAX_CONV_LAYERS, "conv: n_layers=%d", d->n_layers);
+    D2P_REQUIRE(d->B > 0 && d->k > 0 && d->T > 0 && d->h > 0 && d->w > 0 && d->d > 0, "conv: bad dims");
+    D2P_REQUIRE(d->d <= MAXC, "conv: input depth %d > %d", d->d, MAXC);
+    D2P_REQUIRE(d->frames_dtype == D2P_U8 || d->frames_dtype == D2P_F32, "conv: frames dtype");
+    for (int l = 0; l < d->n_layers; ++l) {
+        int c = d->layers[l].cout;
+        D2P_REQUIRE(c > 0 && c <= MAXC && c % 4 == 0, "conv: layer %d cout=%d unsupported", l, c);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ---- saved-tensor layout ---------------------------------------------------
+// saved = for each layer l: act a_l [N,OH,OW,C] | stats [4, k, C]
+static size_t act_floats(const Geo& g) { return (size_t)g.N * g.OH * g.OW * g.COUT; }
+static size_t stat_floats(const Geo& g) { return (size_t)4 * g.k * g.COUT; }
+
+// scratch carve-up shared by fwd/bwd: dZ | dY | dy_tmp | coef | partials
+struct Plan {
+    Geo geo[D2P_MAX_CONV_LAYERS];
+    size_t off_dz, off_dy, off_tmp, off_coef, off_part, part_bytes, total;
+};
+
+static void make_plan(const d2p_conv_desc* d, Plan* p) {
+    size_t max_act = 0, max_in = 0, max_kc = 0, max_part = 0;
+    for (int l = 0; l < d->n_layers; ++l) {
+        Geo& g = p->geo[l];
+        fill_geo(d, l, &g);
+        size_t a = act_floats(g);
+        size_t i = (size_t)g.N * g.IH * g.IW * g.CIN;
+        if (a > max_act) max_act = a;
+        if (l > 0 && i > max_in) max_in = i;
+        if ((size_t)g.k * g.COUT > max_kc) max_kc = (size_t)g.k * g.COUT;
+        long long rows = (long long)g.N * g.OH * g.OW;
+        size_t bn = bn_ws_bytes(rows, g.COUT, g.k);
+        size_t cs = bn_ws_bytes(rows, g.COUT, 1);
+        int ppb; int nblk = dw_blocks(rows, &ppb);
+        size_t dw = (size_t)nblk * 9 * g.CIN * g.COUT * sizeof(float);
+        size_t m = bn > dw ? bn : dw; if (cs > m) m = cs;
+        if (m > max_part) max_part = m;
+    }
+    size_t dyf = max_act > max_in ? max_act : max_in;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    p->off_dz = 0;
+    p->off_dy = al(max_act * sizeof(float));
+    p->off_tmp = p->off_dy + al(dyf * sizeof(float));
+    p->off_coef = p->off_tmp + al(max_act * sizeof(float));
+    p->off_part = p->off_coef + al(2 * max_kc * sizeof(float));
+    p->part_bytes = al(max_part);
+    p->total = p->off_part + p->part_bytes;
+}
+
+namespace {
+__global__ void permute_frames_kernel(const float* __restrict__ X, float* __restrict__ Y, long long N,
+                                      int F, int T, int R, int inverse) {
+    long long total = N * F;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long n = idx / F; int f = (int)(idx % F);
+        long long r = n / T; int t = (int)(n % T);
+        long long m = (long long)t * R + r;
+        if (!inverse) Y[m * F + f] = X[idx]; else Y[idx] = X[m * F + f];
+    }
+}
+}  // namespace
+// frame-major [R*T, F] -> time-major [T*R, F]
+int permute_frames(cudaStream_t st, const float* X, float* Y, int N, int F, int T, int R) {
+    long long total = (long long)N * F;
+    int blocks = (int)((total + 255) / 256); if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    permute_frames_kernel<<<blocks, 256, 0, st>>>(X, Y, N, F, T, R, 0);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+int unpermute_frames(cudaStream_t st, const float* X, float* Y, int N, int F, int T, int R) {
+    long long total = (long long)N * F;
+    int blocks = (int)((total + 255) / 256); if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    permute_frames_kernel<<<blocks, 256, 0, st>>>(X, Y, N, F, T, R, 1);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace d2p
+
+using namespace d2p;
+
+extern "C" size_t d2p_conv_encoder_saved_floats(const d2p_conv_desc* d) {
+    if (check_desc(d)) return 0;
+    size_t n = 0;
+    for (int l = 0; l < d->n_layers; ++l) { Geo g; fill_geo(d, l, &g); n += act_floats(g) + stat_floats(g); }
+    return n;
+}
+
+extern "C" size_t d2p_conv_encoder_ws_bytes(const d2p_conv_desc* d) {
+    if (check_desc(d)) return 0;
+    Plan p; make_plan(d, &p);
+    return p.total;
+}
+
+extern "C" int d2p_conv_encoder_feature_dim(const d2p_conv_desc* d) {
+    if (check_desc(d)) return -1;
+    Geo g; fill_geo(d, d->n_layers - 1, &g);
+    return g.OH * g.OW * g.COUT;
+}
+
+extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, float* feat,
+                                    float* saved, int training, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_TRY(check_desc(d));
+    D2P_REQUIRE(frames && feat && saved && ws, "conv fwd: null buffer");
+    Plan p; make_plan(d, &p);
+    D2P_REQUIRE(ws_bytes >= p.total, "conv fwd: workspace too small (%zu < %zu)", ws_bytes, p.total);
+    char* wsb = (char*)ws;
+    const float* prev = nullptr; const float* prev_stats = nullptr;
+    float* sp = saved;
+    for (int l = 0; l < d->n_layers; ++l) {
+        const Geo& g = p.geo[l];
+        float* act = sp; float* stats = sp + act_floats(g);
+        sp = stats + stat_floats(g);
+        const d2p_conv_layer& L = d->layers[l];
+        D2P_REQUIRE(L.w && L.b && L.gamma && L.beta && L.moving_mean && L.moving_var, "conv fwd: layer %d params", l);
+        long long npix = (long long)g.N * g.OH * g.OW;
+        int blocks = cdiv(npix, PX);
+        const float* sc = prev_stats ? prev_stats + 2 * (size_t)g.k * g.CIN : nullptr;
+        const float* sh = prev_stats ? prev_stats + 3 * (size_t)g.k * g.CIN : nullptr;
+        if (l == 0 && d->frames_dtype == D2P_U8)
+            conv_fwd_kernel<uint8_t><<<blocks, 128, 0, st>>>(g, (const uint8_t*)frames, nullptr, nullptr, L.w, L.b, act);
+        else
+            conv_fwd_kernel<float><<<blocks, 128, 0, st>>>(g, l == 0 ? (const float*)frames : prev, sc, sh, L.w, L.b, act);
+        D2P_CHECK_LAUNCH();
+        D2P_TRY(bn_forward_stats(st, act, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma, L.beta,
+                                 L.moving_mean, L.moving_var, training, stats, wsb + p.off_part,
+                                 p.part_bytes));
+        prev = act; prev_stats = stats;
+        if (l == d->n_layers - 1) {
+            // feature = BN(a_L) flattened HWC, written time-major [T, R, F]
+            int F = g.OH * g.OW * g.COUT;
+            if (g.OH * g.OW == 1) {
+                D2P_TRY(bn_apply(st, act, feat, g.N, g.COUT, g.T, g.k, stats, g.T, d->B * d->k));
+            } else {
+                float* tmp = (float*)(wsb + p.off_tmp);
+                D2P_TRY(bn_apply(st, act, tmp, npix, g.COUT, g.T * g.OH * g.OW, g.k, stats, 0, 0));
+                D2P_TRY(permute_frames(st, tmp, feat, g.N, F, g.T, d->B * d->k));
+            }
+        }
+    }
+    return 0;
+}
+
+// Backward: dfeat [T,R,F] -> parameter grads (accumulated into layers[l].dw etc.).
+extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float* dfeat,
+                                    const float* saved, int training, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_TRY(check_desc(d));
+    D2P_REQUIRE(frames && dfeat && saved && ws, "conv bwd: null buffer");
+    Plan p; make_plan(d, &p);
+    D2P_REQUIRE(ws_bytes >= p.total, "conv bwd: workspace too small (%zu < %zu)", ws_bytes, p.total);
+    char* wsb = (char*)ws;
+    const float* acts[D2P_MAX_CONV_LAYERS]; const float* stats[D2P_MAX_CONV_LAYERS];
+    const float* sp = saved;
+    for (int l = 0; l < d->n_layers; ++l) {
+        acts[l] = sp; stats[l] = sp + act_floats(p.geo[l]);
+        sp = stats[l] + stat_floats(p.geo[l]);
+    }
+    float* dZ = (float*)(wsb + p.off_dz);
+    float* dY = (float*)(wsb + p.off_dy);      // grad wrt the BN output feeding layer l+1
+    float* dy_tmp = (float*)(wsb + p.off_tmp);
+    float* coef = (float*)(wsb + p.off_coef);
+    void* part = wsb + p.off_part;
+
+    for (int l = d->n_layers - 1; l >= 0; --l) {
+        const Geo& g = p.geo[l];
+        const d2p_conv_layer& L = d->layers[l];
+        D2P_REQUIRE(L.dw && L.db && L.dgamma && L.dbeta, "conv bwd: layer %d grads", l);
+        long long npix = (long long)g.N * g.OH * g.OW;
+        const float* dy_lin = dY;
+        if (l == d->n_layers - 1) {
+            // dfeat is time-major [T,R,F]; bring it back to frame order
+            D2P_TRY(unpermute_frames(st, dfeat, dy_tmp, g.N, g.OH * g.OW * g.COUT, g.T, d->B * d->k));
+            dy_lin = dy_tmp;
+        }
+        D2P_TRY(bn_backward(st, acts[l], dy_lin, dZ, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma,
+                            stats[l], L.dgamma, L.dbeta, training, 1, coef, part, p.part_bytes, 0, 0,
+                            nullptr));
+        D2P_TRY(colsum(st, dZ, npix, g.COUT, L.db, 1.0f, part, p.part_bytes));
+        int ppb; int nblk = dw_blocks(npix, &ppb);
+        const float* sc = l > 0 ? stats[l - 1] + 2 * (size_t)g.k * g.CIN : nullptr;
+        const float* sh = l > 0 ? stats[l - 1] + 3 * (size_t)g.k * g.CIN : nullptr;
+        if (l == 0 && d->frames_dtype == D2P_U8)
+            conv_bwd_dw_kernel<uint8_t><<<dim3(nblk, 9), 256, 0, st>>>(g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, (float*)part);
+        else
+            conv_bwd_dw_kernel<float><<<dim3(nblk, 9), 256, 0, st>>>(g, l == 0 ? (const float*)frames : acts[l - 1], sc, sh, dZ, ppb, (float*)part);
+        D2P_CHECK_LAUNCH();
+        int nw = 9 * g.CIN * g.COUT;
+        conv_dw_reduce<<<cdiv(nw, 256), 256, 0, st>>>((const float*)part, nblk, nw, L.dw);
+        D2P_CHECK_LAUNCH();
+        if (l > 0) {
+            D2P_REQUIRE(g.CIN % 4 == 0, "conv bwd: CIN %% 4");
+            long long nin = (long long)g.N * g.IH * g.IW;
+            conv_bwd_dx_kernel<<<cdiv(nin, PX), 128, 0, st>>>(g, dZ, L.w, dY);
+            D2P_CHECK_LAUNCH();
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,320 @@
+// Sequence-side ops of the decoders: token embedding gather with the
+// reference's <s> shift, masked softmax / sigmoid cross-entropy with the
+// reference's batch normaliser, the embedding-table gradient, and the small
+// [B,k,H] group reductions of the summarizer.
+//
+//  * Teacher forcing (reference models/model_full.py:446-450): decoder input at
+//    step t is Emb[token_dim+1] for t = 0 - out of range for the
+//    [token_dim+1, E] table, which TF's GPU gather turns into a zero row
+//     - and Emb[y_{t-1}] afterwards.
+//  * Sequence_Loss (model_full.py:620-657): ce summed over positions
+//    t < gt_len and divided by sum(gt_len) over the batch of that decoder
+//    instance; action / per losses are then averaged over the k instances.
+#include "common.cuh"
+
+namespace d2p {
+namespace {
+
+// X[t, r, :] = table[id(t,r)] or 0 if id out of range; id = t==0 ? start_id : tokens[r, t-1]
+__global__ void gather_shifted_kernel(const float* __restrict__ table, int vocab_rows, int E,
+                                      const int* __restrict__ tokens, int R, int L, int start_id,
+                                      float* __restrict__ X) {
+    size_t total = (size_t)L * R * E;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int e = (int)(idx % E);
+        size_t tr = idx / E;
+        int r = (int)(tr % R), t = (int)(tr / R);
+        int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
+        X[idx] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E + e] : 0.f;
+    }
+}
+
+// dTable[v, e] += sum_{(t,r): id(t,r) == v} dX[t,r,e]   (fixed order: deterministic)
+__global__ void embedding_bwd_kernel(const float* __restrict__ dX, int vocab_rows, int E,
+                                     const int* __restrict__ tokens, int R, int L, int start_id,
+                                     float* __restrict__ dTable) {
+    int v = blockIdx.y;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float acc = 0.f;
+    for (int t = 0; t < L; ++t)
+        for (int r = 0; r < R; ++r) {
+            int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
+            if (id == v) acc += dX[((size_t)t * R + r) * E + e];
+        }
+    dTable[(size_t)v * E + e] += acc;
+}
+
+// Per decoder-instance normalisers.  Rows r of the same instance share
+// r % nsl.  w[r] = coef / sum_{r' in instance} len[r'];  runlen[r] = max len.
+__global__ void seq_weights_kernel(const int* __restrict__ len, int R, int nsl, float coef,
+                                   int max_len, float* __restrict__ w, int* __restrict__ runlen) {
+    __shared__ int tot[64], mx[64];
+    for (int s = threadIdx.x; s < nsl; s += blockDim.x) {
+        int a = 0, m = 0;
+        for (int r = s; r < R; r += nsl) {
+            int l = len[r]; l = l < 0 ? 0 : (l > max_len ? max_len : l);
+            a += l; m = l > m ? l : m;
+        }
+        tot[s] = a; mx[s] = m;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        int s = r % nsl;
+        w[r] = tot[s] > 0 ? coef / (float)tot[s] : 0.f;
+        if (runlen) runlen[r] = mx[s];
+    }
+}
+
+// One warp per (t, r) row of logits [T,R,V].  Writes rowloss[t*R+r] and dlogits.
+// Rows with t >= runlen[r] are forced to zero logits (dynamic_decode's zero pad).
+__global__ void softmax_ce_kernel(float* __restrict__ logits, int T, int R, int V,
+                                  const int* __restrict__ labels /*[R, T]*/,
+                                  const int* __restrict__ len, const int* __restrict__ runlen,
+                                  const float* __restrict__ w, float* __restrict__ rowloss,
+                                  float* __restrict__ dlogits) {
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= T * R) return;
+    int t = row / R, r = row % R;
+    float* x = logits + (size_t)row * V;
+    float* dx = dlogits ? dlogits + (size_t)row * V : nullptr;
+    if (runlen && t >= runlen[r]) {
+        for (int v = lane; v < V; v += 32) { x[v] = 0.f; if (dx) dx[v] = 0.f; }
+        if (lane == 0) rowloss[row] = 0.f;
+        return;
+    }
+    if (t >= len[r]) {
+        if (dx) for (int v = lane; v < V; v += 32) dx[v] = 0.f;
+        if (lane == 0) rowloss[row] = 0.f;
+        return;
+    }
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, x[v]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(x[v] - m);
+    s = warp_sum(s);
+    float lse = m + logf(s);
+    int y = labels[(size_t)r * T + t];
+    float wr = w[r];
+    if (lane == 0) rowloss[row] = (y >= 0 && y < V) ? wr * (lse - x[y]) : 0.f;
+    if (dx)
+        for (int v = lane; v < V; v += 32) {
+            float p = expf(x[v] - lse);
+            dx[v] = wr * (p - (v == y ? 1.f : 0.f));
+        }
+}
+
+// sigmoid CE averaged over P (reference model_full.py:651-653); labels [R,T,P] float.
+__global__ void sigmoid_ce_kernel(float* __restrict__ logits, int T, int R, int P,
+                                  const float* __restrict__ labels, const int* __restrict__ len,
+                                  const int* __restrict__ runlen, const float* __restrict__ w,
+                                  float* __restrict__ rowloss, float* __restrict__ dlogits) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= T * R) return;
+    int t = row / R, r = row % R;
+    float* x = logits + (size_t)row * P;
+    float* dx = dlogits ? dlogits + (size_t)row * P : nullptr;
+    bool padded = runlen && t >= runlen[r];
+    bool live = !padded && t < len[r];
+    float acc = 0.f, wr = live ? w[r] / (float)P : 0.f;
+    for (int p = 0; p < P; ++p) {
+        if (padded) x[p] = 0.f;
+        float xv = x[p];
+        if (live) {
+            float z = labels[((size_t)r * T + t) * P + p];
+            acc += fmaxf(xv, 0.f) - xv * z + log1pf(expf(-fabsf(xv)));
+            if (dx) dx[p] = wr * (sigmoid_f(xv) - z);
+        } else if (dx) dx[p] = 0.f;
+    }
+    rowloss[row] = live ? w[r] * acc / (float)P : 0.f;
+}
+
+// out[0] (+)= sum x[0..n) in a fixed order (single block)
+__global__ void sum_reduce_kernel(const float* __restrict__ x, int n, float* __restrict__ out,
+                                  int accumulate) {
+    __shared__ double sh[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) a += x[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + (float)sh[0];
+}
+
+// out[b,:] = alpha * sum_i F[b,i,:] (+ out if accumulate)
+__global__ void group_sum_kernel(const float* __restrict__ F, int B, int k, int H, float alpha,
+                                 float* __restrict__ out, int accumulate) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    int b = idx / H, u = idx % H;
+    float a = 0.f;
+    for (int i = 0; i < k; ++i) a += F[((size_t)b * k + i) * H + u];
+    out[idx] = (accumulate ? out[idx] : 0.f) + alpha * a;
+}
+
+// out[b,i,:] = alpha * S[b,:] (+ out if accumulate)
+__global__ void group_bcast_kernel(const float* __restrict__ S, int B, int k, int H, float alpha,
+                                   float* __restrict__ out, int accumulate) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * k * H) return;
+    int u = (int)(idx % H);
+    int b = (int)(idx / ((size_t)k * H));
+    out[idx] = (accumulate ? out[idx] : 0.f) + alpha * S[(size_t)b * H + u];
+}
+
+// y = alpha*x + beta*y
+__global__ void axpby_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y,
+                             float beta, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        y[i] = alpha * x[i] + (beta != 0.f ? beta * y[i] : 0.f);
+}
+
+// [T,R,V] time-major logits -> [R,V,T] (the reference's [bs, n, len] layout,
+// model_full.py:486-489)
+__global__ void logits_to_bvl_kernel(const float* __restrict__ X, int T, int R, int V,
+                                     float* __restrict__ Y) {
+    size_t total = (size_t)T * R * V;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int t = (int)(idx % T);
+        size_t rv = idx / T;
+        int v = (int)(rv % V), r = (int)(rv / V);
+        Y[idx] = X[((size_t)t * R + r) * V + v];
+    }
+}
+
+// per [R,T,P] (batch-major, as fed) -> [T,R,P] time-major
+__global__ void rtp_to_trp_kernel(const float* __restrict__ X, int R, int T, int P,
+                                  float* __restrict__ Y) {
+    size_t total = (size_t)T * R * P;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int p = (int)(idx % P);
+        size_t tr = idx / P;
+        int r = (int)(tr % R), t = (int)(tr / R);
+        Y[idx] = X[((size_t)r * T + t) * P + p];
+    }
+}
+
+// lengths arrive as fp32 (reference models/model_full.py:155-171) -> int32
+__global__ void len_to_int_kernel(const float* __restrict__ x, int* __restrict__ y, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (int)x[i];
+}
+
+inline int ew_blocks(size_t total) {
+    size_t b = (total + 255) / 256, cap = 8 * (size_t)kNumSMs;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+}  // namespace d2p
+
+using namespace d2p;
+
+extern "C" int d2p_embed_shifted(const float* table, int vocab_rows, int E, const int* tokens,
+                                 int R, int L, int start_id, float* X, void* stream) {
+    D2P_REQUIRE(table && tokens && X && R > 0 && L > 0 && E > 0, "embed: bad arguments");
+    gather_shifted_kernel<<<ew_blocks((size_t)L * R * E), 256, 0, (cudaStream_t)stream>>>(
+        table, vocab_rows, E, tokens, R, L, start_id, X);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, const int* tokens,
+                                     int R, int L, int start_id, float* dTable, void* stream) {
+    D2P_REQUIRE(dX && tokens && dTable, "embed bwd: bad arguments");
+    embedding_bwd_kernel<<<dim3(cdiv(E, 128), vocab_rows), 128, 0, (cudaStream_t)stream>>>(
+        dX, vocab_rows, E, tokens, R, L, start_id, dTable);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_seq_weights(const int* len, int R, int nsl, float coef, int max_len, float* w,
+                               int* runlen, void* stream) {
+    D2P_REQUIRE(len && w && R > 0 && nsl > 0 && nsl <= 64 && R % nsl == 0, "seq_weights: bad arguments");
+    seq_weights_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(len, R, nsl, coef, max_len, w, runlen);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+// loss[0] (+)= sum_rows w[r]*ce ; dlogits optional. rowloss: scratch [T*R].
+extern "C" int d2p_softmax_ce(float* logits, int T, int R, int V, const int* labels, const int* len,
+                              const int* runlen, const float* w, float* rowloss, float* dlogits,
+                              float* loss, int accumulate, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(logits && labels && len && w && rowloss && loss, "softmax_ce: null buffer");
+    softmax_ce_kernel<<<cdiv((long long)T * R, 8), 256, 0, st>>>(logits, T, R, V, labels, len, runlen,
+                                                                w, rowloss, dlogits);
+    D2P_CHECK_LAUNCH();
+    sum_reduce_kernel<<<1, 256, 0, st>>>(rowloss, T * R, loss, accumulate);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_sigmoid_ce(float* logits, int T, int R, int P, const float* labels,
+                              const int* len, const int* runlen, const float* w, float* rowloss,
+                              float* dlogits, float* loss, int accumulate, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(logits && labels && len && w && rowloss && loss, "sigmoid_ce: null buffer");
+    sigmoid_ce_kernel<<<cdiv((long long)T * R, 256), 256, 0, st>>>(logits, T, R, P, labels, len,
+                                                                  runlen, w, rowloss, dlogits);
+    D2P_CHECK_LAUNCH();
+    sum_reduce_kernel<<<1, 256, 0, st>>>(rowloss, T * R, loss, accumulate);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_group_sum(const float* F, int B, int k, int H, float alpha, float* out,
+                             int accumulate, void* stream) {
+    D2P_REQUIRE(F && out, "group_sum: null buffer");
+    group_sum_kernel<<<cdiv((long long)B * H, 256), 256, 0, (cudaStream_t)stream>>>(F, B, k, H, alpha,
+                                                                                out, accumulate);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_group_bcast(const float* S, int B, int k, int H, float alpha, float* out,
+                               int accumulate, void* stream) {
+    D2P_REQUIRE(S && out, "group_bcast: null buffer");
+    group_bcast_kernel<<<cdiv((long long)B * k * H, 256), 256, 0, (cudaStream_t)stream>>>(
+        S, B, k, H, alpha, out, accumulate);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_axpby(const float* x, float alpha, float* y, float beta, size_t n, void* stream) {
+    D2P_REQUIRE(x && y, "axpby: null buffer");
+    if (n == 0) return 0;
+    axpby_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, alpha, y, beta, n);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_logits_to_bvl(const float* X, int T, int R, int V, float* Y, void* stream) {
+    D2P_REQUIRE(X && Y, "logits_to_bvl: null buffer");
+    logits_to_bvl_kernel<<<ew_blocks((size_t)T * R * V), 256, 0, (cudaStream_t)stream>>>(X, T, R, V, Y);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_rtp_to_trp(const float* X, int R, int T, int P, float* Y, void* stream) {
+    D2P_REQUIRE(X && Y, "rtp_to_trp: null buffer");
+    rtp_to_trp_kernel<<<ew_blocks((size_t)T * R * P), 256, 0, (cudaStream_t)stream>>>(X, R, T, P, Y);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_len_to_int(const float* x, int* y, int n, void* stream) {
+    D2P_REQUIRE(x && y, "len_to_int: null buffer");
+    len_to_int_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}

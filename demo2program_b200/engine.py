@@ -1,0 +1,470 @@
+"""Host orchestration of the demo2program train / eval step on one B200.
+
+Python only sequences C-ABI calls into libd2p.so (hand-written sm_100a CUDA);
+PyTorch is the device allocator, the stream provider and the NCCL plumbing.
+There is no autograd on the hot path: the backward pass is an explicit reverse
+sequence of `*_bwd` ops over preallocated buffers, so the whole step (forward,
+backward, clip + Adam) is a fixed launch sequence that is captured once into a
+CUDA graph and replayed.
+
+Graph restated (reference models/model_full.py:370-599, 918-1079; baselines
+model_summarizer.py:363-397, model_synthesis.py:325-358):
+  frames -> State_Encoder CNN -> Demo_Encoder LSTM (per demo, shared weights)
+         -> [summarizer/full] avg (h,c) over k -> SecondPathEncoder LSTM
+         -> rn_pool (+ mean in `full`) -> Program decoder (teacher forcing)
+         -> [full] Action decoder + Per decoder from each demo's (h,c)
+  loss = program + mean_k action + mean_k per.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, FcBn, check, ptr
+from .manifest import build_manifests
+
+
+def _al(n, a=64):
+    return (int(n) + a - 1) // a * a
+
+
+class Engine:
+    """Preallocated buffers + launch sequence for one model/config."""
+
+    def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
+                 frames_dtype=np.uint8, flat_params=None, flat_state=None,
+                 world_size=1, use_graph=True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
+                                'fallback)')
+        if cfg.model == 'induction_baseline':
+            raise NotImplementedError('induction_baseline uses InductionEngine')
+        cfg.validate()
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.is_train = bool(is_train)
+        self.world = int(world_size)
+        self.use_graph = use_graph
+        self.frames_u8 = np.dtype(frames_dtype) == np.uint8
+        self.pm, self.sm = build_manifests(cfg)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        p0 = self.pm.init_flat(seed) if flat_params is None else np.asarray(flat_params, np.float32)
+        s0 = self.sm.init_flat(seed) if flat_state is None else np.asarray(flat_state, np.float32)
+        self.params = torch.from_numpy(p0.copy()).to(self.dev)
+        self.state = torch.from_numpy(s0.copy()).to(self.dev)
+        self.grads = torch.zeros(self.pm.total, **f32)
+        self.adam_m = torch.zeros(self.pm.total, **f32)
+        self.adam_v = torch.zeros(self.pm.total, **f32)
+        self.adam_state = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        self.lr, self.clip = cfg.learning_rate, 20.0
+        self._alloc()
+        self._graph = None
+        self._graph_key = None
+
+    # ------------------------------------------------------------------ params
+    def P(self, name):
+        e = self.pm[name]
+        return self.params[e.offset:e.offset + e.size]
+
+    def G(self, name):
+        e = self.pm[name]
+        return self.grads[e.offset:e.offset + e.size]
+
+    def S(self, name):
+        e = self.sm[name]
+        return self.state[e.offset:e.offset + e.size]
+
+    def _fcbn(self, scope):
+        f, b = scope + '/fully_connected/', scope + '/bn_act/BatchNorm/'
+        s = FcBn()
+        s.w, s.b = ptr(self.P(f + 'weights')), ptr(self.P(f + 'biases'))
+        s.gamma, s.beta = ptr(self.P(b + 'gamma')), ptr(self.P(b + 'beta'))
+        s.moving_mean = ptr(self.S(b + 'moving_mean'))
+        s.moving_var = ptr(self.S(b + 'moving_variance'))
+        s.dw, s.db = ptr(self.G(f + 'weights')), ptr(self.G(f + 'biases'))
+        s.dgamma, s.dbeta = ptr(self.G(b + 'gamma')), ptr(self.G(b + 'beta'))
+        return s
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        cfg, lib = self.cfg, self.lib
+        B, k, T, H = cfg.batch_size, cfg.k, cfg.max_demo_len, cfg.num_lstm_cell_units
+        L, V, A, Pd = cfg.max_program_len, cfg.dim_program_token, cfg.action_space, cfg.per_dim
+        R = B * k
+        self.B, self.k, self.T, self.H, self.R = B, k, T, H, R
+        dev = self.dev
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        # ---- inputs (device) + pinned staging (host) ----
+        fdt = torch.uint8 if self.frames_u8 else torch.float32
+        self.d_frames = torch.zeros(B, k, T, cfg.h, cfg.w, cfg.depth, dtype=fdt, device=dev)
+        self.d_demo_len_f = z(R)
+        self.d_prog_len_f = z(B)
+        self.d_demo_len = zi(R)
+        self.d_prog_len = zi(B)
+        self.d_prog_tok = zi(B, L)
+        self.d_act_tok = zi(R, T)
+        self.d_per = z(R, T, Pd)
+        self.h_in = {
+            's_h': torch.zeros(B, k, T, cfg.h, cfg.w, cfg.depth, dtype=fdt).pin_memory(),
+            'demo_len': torch.zeros(R).pin_memory(),
+            'program_len': torch.zeros(B).pin_memory(),
+            'program_tokens': torch.zeros(B, L, dtype=torch.int32).pin_memory(),
+            'a_h_tokens': torch.zeros(R, T, dtype=torch.int32).pin_memory(),
+            'per': torch.zeros(R, T, Pd).pin_memory(),
+        }
+        self.h_loss = torch.zeros(4).pin_memory()
+        # ---- conv encoder ----
+        d = ConvDesc()
+        d.B, d.k, d.T, d.h, d.w, d.d = B, k, T, cfg.h, cfg.w, cfg.depth
+        d.frames_dtype = _lib.D2P_U8 if self.frames_u8 else _lib.D2P_F32
+        chans = cfg.conv_channels()
+        d.n_layers = len(chans)
+        for li, (_, cout) in enumerate(chans):
+            sc = 'Demo_Encoder/State_Encoder/conv%d' % (li + 1)
+            l = d.layers[li]
+            l.w, l.b = ptr(self.P(sc + '/Conv/weights')), ptr(self.P(sc + '/Conv/biases'))
+            bn = sc + '/bn_act/BatchNorm/'
+            l.gamma, l.beta = ptr(self.P(bn + 'gamma')), ptr(self.P(bn + 'beta'))
+            l.moving_mean = ptr(self.S(bn + 'moving_mean'))
+            l.moving_var = ptr(self.S(bn + 'moving_variance'))
+            l.dw, l.db = ptr(self.G(sc + '/Conv/weights')), ptr(self.G(sc + '/Conv/biases'))
+            l.dgamma, l.dbeta = ptr(self.G(bn + 'gamma')), ptr(self.G(bn + 'beta'))
+            l.cout = cout
+        self.conv_desc = d
+        self.F = lib.d2p_conv_encoder_feature_dim(C.byref(d))
+        assert self.F == cfg.feature_dim(), (self.F, cfg.feature_dim())
+        F = self.F
+        self.conv_saved = z(lib.d2p_conv_encoder_saved_floats(C.byref(d)))
+        ws = lib.d2p_conv_encoder_ws_bytes(C.byref(d))
+        self.feat = z(T, R, F)
+        self.dfeat = z(T, R, F)
+        # ---- LSTMs ----
+        def lstm_bufs(Tn, Rn, with_dx_in=None):
+            b = {'y': z(Tn, Rn, H), 'hT': z(Rn, H), 'cT': z(Rn, H),
+                 'gates': z(Tn, Rn, 4 * H), 'cells': z(Tn, Rn, H),
+                 'dh0': z(Rn, H), 'dc0': z(Rn, H)}
+            return b
+        ws = max(ws, lib.d2p_lstm_seq_bwd_ws_bytes(max(T, L), R, H))
+        self.enc = lstm_bufs(T, R)
+        self.model = cfg.model
+        two_pass = cfg.model in ('full', 'summarizer')
+        if two_pass:
+            self.sum1_h, self.sum1_c = z(B, H), z(B, H)
+            self.init2_h, self.init2_c = z(R, H), z(R, H)
+            self.sec = lstm_bufs(T, R)
+            self.dy1 = z(T, R, H)
+            self.rn_saved_h = z(lib.d2p_rn_pool_saved_floats(B, k, H))
+            self.rn_saved_c = z(lib.d2p_rn_pool_saved_floats(B, k, H))
+            ws = max(ws, lib.d2p_rn_pool_ws_bytes(B, k, H))
+            self.fc = {(s, f): self._fcbn('demo_%s_summary/rn_pool/%s' % (s, f))
+                       for s in 'hc' for f in ('fc1', 'fc2')}
+        self.dsum_h, self.dsum_c = z(B, H), z(B, H)       # decoder init state
+        self.dh2, self.dc2 = z(R, H), z(R, H)             # grads wrt per-demo (h,c)
+        # ---- program decoder ----
+        self.prog = lstm_bufs(L, B)
+        self.prog.update(X=z(L, B, H), logits=z(L, B, V), dlogits=z(L, B, V),
+                         dy=z(L, B, H), dX=z(L, B, H), rowloss=z(L * B), w=z(B),
+                         runlen=zi(B))
+        if cfg.model == 'full':
+            self.act = lstm_bufs(T, R)
+            self.act.update(X=z(T, R, H), logits=z(T, R, A), dlogits=z(T, R, A),
+                            dy=z(T, R, H), dX=z(T, R, H), rowloss=z(T * R), w=z(R),
+                            runlen=zi(R))
+            self.per = lstm_bufs(T, R)
+            self.per.update(X=z(T, R, H), logits=z(T, R, Pd), dlogits=z(T, R, Pd),
+                            dy=z(T, R, H), dX=z(T, R, H), rowloss=z(T * R),
+                            per_tm=z(T, R, Pd),
+                            fc_saved=z(lib.d2p_fc_bn_saved_floats(T * R, H, k)))
+            self.per_fc = self._fcbn('Per_Decoder/Per_Encoder/fc2')
+            ws = max(ws, lib.d2p_fc_bn_ws_bytes(T * R, H, k))
+        ws = max(ws, lib.d2p_adam_ws_bytes())
+        self.ws_bytes = _al(ws, 256)
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.loss = z(4)   # [total, program, action, per]
+        self.out_bvl = None
+
+    # ------------------------------------------------------------------ helpers
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _call(self, name, *args):
+        check(getattr(self.lib, name)(*args), name)
+
+    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b):
+        self._call('d2p_lstm_seq_fwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
+                   ptr(self.P(scope + 'kernel')), ptr(self.P(scope + 'bias')), 1.0,
+                   ptr(b['y']), ptr(b['hT']), ptr(b['cT']), ptr(b['gates']), ptr(b['cells']),
+                   self._st())
+
+    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX):
+        self._call('d2p_lstm_seq_bwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
+                   ptr(self.P(scope + 'kernel')), ptr(b['y']), ptr(b['gates']), ptr(b['cells']),
+                   ptr(dY), ptr(dhT), ptr(dcT), ptr(dX), ptr(self.G(scope + 'kernel')),
+                   ptr(self.G(scope + 'bias')), ptr(b['dh0']), ptr(b['dc0']), ptr(self.ws),
+                   self.ws_bytes, self._st())
+
+    def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc):
+        self._call('d2p_gemm', int(ta), int(tb), M, N, K, alpha, ptr(A), lda, ptr(Bm), ldb, beta,
+                   ptr(Cm), ldc, None, self._st())
+
+    # ------------------------------------------------------------------ inputs
+    def stage_batch(self, batch):
+        """numpy batch (reference feed_dict keys, models/model_full.py:185-206)
+        -> pinned host staging -> async H2D.  Returns bytes copied."""
+        h = self.h_in
+        fr = np.asarray(batch['s_h'])
+        h['s_h'].numpy()[...] = fr.astype(np.uint8 if self.frames_u8 else np.float32, copy=False)
+        h['demo_len'].numpy()[...] = np.asarray(batch['demo_len'], np.float32).reshape(-1)
+        h['program_len'].numpy()[...] = np.asarray(batch['program_len'], np.float32).reshape(-1)
+        h['program_tokens'].numpy()[...] = np.asarray(batch['program_tokens'], np.int32)
+        if self.model == 'full':
+            h['a_h_tokens'].numpy()[...] = np.asarray(batch['a_h_tokens'], np.int32).reshape(self.R, self.T)
+            h['per'].numpy()[...] = np.asarray(batch['per'], np.float32).reshape(self.R, self.T, -1)
+        return self.upload()
+
+    def upload(self):
+        """Async H2D of the staged batch (part of the timed e2e region)."""
+        h = self.h_in
+        n = 0
+        pairs = [(self.d_frames, h['s_h']), (self.d_demo_len_f, h['demo_len']),
+                 (self.d_prog_len_f, h['program_len']), (self.d_prog_tok, h['program_tokens'])]
+        if self.model == 'full':
+            pairs += [(self.d_act_tok, h['a_h_tokens']), (self.d_per, h['per'])]
+        for d, s in pairs:
+            d.copy_(s, non_blocking=True)
+            n += s.numel() * s.element_size()
+        return n
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, train_stats=None):
+        cfg, st = self.cfg, self._st()
+        B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
+        L, V = cfg.max_program_len, cfg.dim_program_token
+        tr = int(self.is_train if train_stats is None else train_stats)
+        call = self._call
+        call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, st)
+        call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, st)
+        call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, st)
+        self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
+                       'Demo_Encoder/rnn/basic_lstm_cell/', self.enc)
+        if self.model in ('full', 'summarizer'):
+            call('d2p_group_sum', ptr(self.enc['hT']), B, k, H, 1.0 / k, ptr(self.sum1_h), 0, st)
+            call('d2p_group_sum', ptr(self.enc['cT']), B, k, H, 1.0 / k, ptr(self.sum1_c), 0, st)
+            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0, ptr(self.init2_h), 0, st)
+            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0, ptr(self.init2_c), 0, st)
+            self._lstm_fwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
+                           'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec)
+            fin = self.sec
+            for s, out, saved in (('h', self.dsum_h, self.rn_saved_h),
+                                  ('c', self.dsum_c, self.rn_saved_c)):
+                call('d2p_rn_pool_fwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                     C.byref(self.fc[(s, 'fc2')]), ptr(out), ptr(saved), tr, ptr(self.ws),
+                     self.ws_bytes, st)
+                if self.model == 'full':   # mean + rn_pool (model_full.py:357-359)
+                    call('d2p_group_sum', ptr(fin[s + 'T']), B, k, H, 1.0 / k, ptr(out), 1, st)
+        else:
+            if cfg.demo_aggregation != 'avgpool':
+                raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
+            fin = self.enc
+            call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, st)
+            call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, st)
+        self.fin = fin
+        # ---- program decoder (teacher forcing) ----
+        p = self.prog
+        call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), st)
+        call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
+             V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), st)
+        self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                       'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p)
+        Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
+        self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
+        call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
+             ptr(p['runlen']), ptr(p['w']), ptr(p['rowloss']), ptr(p['dlogits']),
+             ptr(self.loss[1:]), 0, st)
+        if self.model == 'full':
+            A, Pd = cfg.action_space, cfg.per_dim
+            a = self.act
+            call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(a['w']), ptr(a['runlen']), st)
+            call('d2p_embed_shifted', ptr(self.P('Action_Decoder/Token_Embedding/embedding_map')),
+                 A + 1, H, ptr(self.d_act_tok), R, T, A + 1, ptr(a['X']), st)
+            self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a)
+            Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
+            call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
+                 ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
+                 ptr(self.loss[2:]), 0, st)
+            q = self.per
+            call('d2p_rtp_to_trp', ptr(self.d_per), R, T, Pd, ptr(q['per_tm']), st)
+            call('d2p_fc_bn_fwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
+                 ptr(q['X']), ptr(q['fc_saved']), tr, ptr(self.ws), self.ws_bytes, st)
+            self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q)
+            Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(0, 0, T * R, Pd, H, 1.0, q['y'], H, Wq, Pd, 0.0, q['logits'], Pd)
+            call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
+                 ptr(a['runlen']), ptr(a['w']), ptr(q['rowloss']), ptr(q['dlogits']),
+                 ptr(self.loss[3:]), 0, st)
+            # total = program + action + per
+            call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, st)
+            call('d2p_axpby', ptr(self.loss[2:]), 1.0, ptr(self.loss), 1.0, 1, st)
+            call('d2p_axpby', ptr(self.loss[3:]), 1.0, ptr(self.loss), 1.0, 1, st)
+        else:
+            call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, st)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self):
+        cfg, st = self.cfg, self._st()
+        B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
+        L, V = cfg.max_program_len, cfg.dim_program_token
+        tr = int(self.is_train)
+        call = self._call
+        fin = self.fin
+        self.grads.zero_()
+        # ---- program decoder ----
+        p = self.prog
+        Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
+        self._gemm(1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
+                   self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V)
+        self._gemm(0, 1, L * B, H, V, 1.0, p['dlogits'], V, Wp, V, 0.0, p['dy'], H)
+        self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                       'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
+                       p['dX'])
+        call('d2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
+             ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), st)
+        # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
+        have_dh2 = False
+        if self.model == 'full':
+            A, Pd = cfg.action_space, cfg.per_dim
+            a, q = self.act, self.per
+            Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
+                       self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A)
+            self._gemm(0, 1, T * R, H, A, 1.0, a['dlogits'], A, Wa, A, 0.0, a['dy'], H)
+            self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
+                           a['dX'])
+            call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
+                 ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), st)
+            Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
+                       self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd)
+            self._gemm(0, 1, T * R, H, Pd, 1.0, q['dlogits'], Pd, Wq, Pd, 0.0, q['dy'], H)
+            self._lstm_bwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, q['dy'], None, None,
+                           q['dX'])
+            call('d2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
+                 ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, st)
+            # dh2 = d(action init) + d(per init)
+            call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, st)
+            call('d2p_axpby', ptr(q['dh0']), 1.0, ptr(self.dh2), 1.0, R * H, st)
+            call('d2p_axpby', ptr(a['dc0']), 1.0, ptr(self.dc2), 0.0, R * H, st)
+            call('d2p_axpby', ptr(q['dc0']), 1.0, ptr(self.dc2), 1.0, R * H, st)
+            have_dh2 = True
+        if self.model in ('full', 'summarizer'):
+            for s, dsum, saved, dF in (('h', p['dh0'], self.rn_saved_h, self.dh2),
+                                       ('c', p['dc0'], self.rn_saved_c, self.dc2)):
+                if self.model == 'full':   # mean term
+                    call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), int(have_dh2), st)
+                else:
+                    dF.zero_()
+                call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                     C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
+                     self.ws_bytes, st)
+            sec = self.sec
+            self._lstm_bwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
+                           'SecondPathEncoder/rnn/basic_lstm_cell/', sec, None, self.dh2, self.dc2,
+                           self.dy1)
+            # init state = mean_i of first-pass finals, broadcast over i
+            call('d2p_group_sum', ptr(sec['dh0']), B, k, H, 1.0, ptr(self.sum1_h), 0, st)
+            call('d2p_group_sum', ptr(sec['dc0']), B, k, H, 1.0, ptr(self.sum1_c), 0, st)
+            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0 / k, ptr(self.dh2), 0, st)
+            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0 / k, ptr(self.dc2), 0, st)
+            dY1 = self.dy1
+        else:
+            call('d2p_group_bcast', ptr(p['dh0']), B, k, H, 1.0 / k, ptr(self.dh2), 0, st)
+            call('d2p_group_bcast', ptr(p['dc0']), B, k, H, 1.0 / k, ptr(self.dc2), 0, st)
+            dY1 = None
+        self._lstm_bwd(self.feat, T, R, F, self.d_demo_len, None, None,
+                       'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, dY1, self.dh2, self.dc2,
+                       self.dfeat)
+        call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.dfeat),
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, st)
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_step(self):
+        """clip_by_global_norm(20) + Adam (reference trainer.py:102-109); the
+        gradient is first averaged over ranks with ONE all-reduce of the flat
+        buffer when world_size > 1."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads)
+        decay = 10000 if self.cfg.lr_weight_decay else 0
+        self._call('d2p_clip_adam_step', ptr(self.params), ptr(self.grads), ptr(self.adam_m),
+                   ptr(self.adam_v), self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip,
+                   1.0 / self.world, decay, ptr(self.adam_state), ptr(self.ws), self.ws_bytes,
+                   self._st())
+
+    # ------------------------------------------------------------------ steps
+    def _step_body(self, with_opt):
+        self.forward()
+        self.backward()
+        if with_opt:
+            self.optimizer_step()
+
+    def train_step_device(self, with_opt=True):
+        """One train step over the batch already resident in HBM.  The launch
+        sequence is captured into a CUDA graph on first use and replayed."""
+        if not self.use_graph or self.world > 1:
+            self._step_body(with_opt)
+            return
+        key = bool(with_opt)
+        if self._graph is None or self._graph_key != key:
+            # warm-up outside capture (lazy module loading), then capture
+            snap = [t.clone() for t in (self.params, self.state, self.adam_m, self.adam_v,
+                                        self.adam_state)]
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                self._step_body(with_opt)
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            n0 = self.lib.d2p_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body(with_opt)
+            self.launches_per_step = self.lib.d2p_launch_count() - n0
+            for t, sv in zip((self.params, self.state, self.adam_m, self.adam_v, self.adam_state),
+                             snap):
+                t.copy_(sv)
+            torch.cuda.synchronize(self.dev)
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+
+    def train_step(self, batch):
+        """Public API: host batch in, loss out (H2D + step + D2H of the loss)."""
+        self.stage_batch(batch)
+        self.train_step_device(True)
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return float(self.h_loss[0])
+
+    # ------------------------------------------------------------------ outputs
+    def pred_program(self):
+        """[B, V, L] logits, the reference's `pred_program` layout
+        (models/model_full.py:486-489)."""
+        cfg = self.cfg
+        L, V, B = cfg.max_program_len, cfg.dim_program_token, self.B
+        out = torch.empty(B, V, L, dtype=torch.float32, device=self.dev)
+        self._call('d2p_logits_to_bvl', ptr(self.prog['logits']), L, B, V, ptr(out), self._st())
+        return out
+
+    def global_norm(self):
+        return float(self.adam_state[3].item())
+
+    def step_count(self):
+        return int(self.adam_state[0].item())

@@ -1,0 +1,188 @@
+/* libd2p - C ABI of the B200-native demo2program hot path.
+ *
+ * The reference (shaohua0116/demo2program) has no native/FFI layer: its seam
+ * is the Python `Model` class driven by trainer.py / evaler.py, and all
+ * arithmetic is delegated to TensorFlow-1.3 ops.  Each entry point below
+ * replaces the TF op sequence at the cited reference call site; the Python
+ * host (demo2program_b200/) binds them with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (the PyTorch
+ *    allocator); the library never allocates or frees user-visible memory;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    performs no host synchronisation and is CUDA-graph capturable;
+ *  - return value 0 = success, negative = d2p_status; d2p_last_error() returns
+ *    a thread-local message; nothing throws or aborts;
+ *  - sequences are time-major inside the library: [T, R, C] with R = B*k rows,
+ *    r = b*k + i (i = demonstration index);
+ *  - "saved" buffers carry forward activations to the matching *_bwd call,
+ *    "ws" buffers are scratch; query sizes with the *_floats / *_bytes calls;
+ *  - gradient outputs of parameters ACCUMULATE (+=) into the flat gradient
+ *    buffer, which the caller zeroes once per step.
+ */
+#ifndef D2P_H_
+#define D2P_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    D2P_OK = 0,
+    D2P_ERR_ARG = -1,   /* bad argument / shape / workspace size */
+    D2P_ERR_CUDA = -2   /* CUDA runtime error (message has the details) */
+} d2p_status;
+
+enum { D2P_U8 = 0, D2P_F32 = 1 };
+enum { D2P_MAX_CONV_LAYERS = 5 };
+
+const char* d2p_last_error(void);
+int d2p_version(void);
+/* kernels launched (or captured into a CUDA graph) by this library so far */
+long long d2p_launch_count(void);
+
+/* ---- K1: State_Encoder CNN --------------------------------------------------
+ * reference models/model_full.py:216-231 (State_Encoder) via ops.conv2d,
+ * models/ops.py:27-33: slim.conv2d(3x3, stride 2, SAME, bias) -> lrelu(0.2)
+ * -> contrib.layers.batch_norm, x3 (Karel) / x5 (ViZDoom); train-mode batch
+ * statistics are per demonstration index (model_full.py:373-376). */
+typedef struct {
+    const float* w;        /* [3,3,cin,cout] HWIO  (<scope>/Conv/weights) */
+    const float* b;        /* [cout]               (<scope>/Conv/biases) */
+    const float* gamma;    /* [cout] */
+    const float* beta;     /* [cout] */
+    float* moving_mean;    /* [cout] in/out */
+    float* moving_var;     /* [cout] in/out */
+    float* dw;             /* grads, accumulate; may be NULL for fwd-only */
+    float* db;
+    float* dgamma;
+    float* dbeta;
+    int cout;
+    int _pad;
+} d2p_conv_layer;
+
+typedef struct {
+    int B, k, T, h, w, d;  /* frames [B,k,T,h,w,d] */
+    int frames_dtype;      /* D2P_U8 (as stored) or D2P_F32 (as the reference feeds) */
+    int n_layers;
+    d2p_conv_layer layers[D2P_MAX_CONV_LAYERS];
+} d2p_conv_desc;
+
+size_t d2p_conv_encoder_saved_floats(const d2p_conv_desc* d);
+size_t d2p_conv_encoder_ws_bytes(const d2p_conv_desc* d);
+int d2p_conv_encoder_feature_dim(const d2p_conv_desc* d);
+/* feat: [T, R, F] time-major. training != 0: batch statistics + moving update. */
+int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, float* feat, float* saved,
+                         int training, void* ws, size_t ws_bytes, void* stream);
+int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float* dfeat,
+                         const float* saved, int training, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K2/K3: LSTM over a sequence -------------------------------------------
+ * reference models/model_full.py:244-258 (Demo_Encoder), :265-277
+ * (SecondPathEncoder), :465-471 (decoder cell loop): BasicLSTMCell, gate order
+ * i,j,f,o, forget_bias, dynamic_rnn length masking.
+ * X [T,R,In]; W [(In+H),4H] (TF kernel layout); Y [T,R,H] zero past len;
+ * gates [T,R,4H] and cells [T,R,H] are saved for the backward. */
+int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, const int* len, const float* h0,
+                     const float* c0, const float* W, const float* b, float forget_bias, float* Y,
+                     float* hT, float* cT, float* gates, float* cells, void* stream);
+size_t d2p_lstm_seq_bwd_ws_bytes(int T, int R, int H);
+/* gates is consumed (holds dZ on return). dY/dhT/dcT/dX may be NULL.
+ * dh0/dc0 [R,H] are required (they double as the running state grads). */
+int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, const int* len, const float* h0,
+                     const float* c0, const float* W, const float* Y, float* gates,
+                     const float* cells, const float* dY, const float* dhT, const float* dcT,
+                     float* dX, float* dW, float* db, float* dh0, float* dc0, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* ---- decoder inputs / losses -------------------------------------------------
+ * reference models/model_full.py:282-296 (Token_Embedding), :446-450 (<s>
+ * shift; the out-of-range start id yields a zero row, TF GPU gather),
+ * :620-657 (Sequence_Loss). tokens [R,L] int32; X [L,R,E]. */
+int d2p_embed_shifted(const float* table, int vocab_rows, int E, const int* tokens, int R, int L,
+                      int start_id, float* X, void* stream);
+int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, const int* tokens, int R, int L,
+                          int start_id, float* dTable, void* stream);
+/* w[r] = coef / sum(len over rows of the same decoder instance r % nsl);
+ * runlen[r] = max len over that instance (TrainingHelper runs max_b len steps). */
+int d2p_seq_weights(const int* len, int R, int nsl, float coef, int max_len, float* w, int* runlen,
+                    void* stream);
+/* logits [T,R,V] (rows t >= runlen forced to 0); labels [R,T] int32;
+ * loss[0] (+)= sum w[r]*ce over t < len[r]; dlogits optional. rowloss: scratch [T*R]. */
+int d2p_softmax_ce(float* logits, int T, int R, int V, const int* labels, const int* len,
+                   const int* runlen, const float* w, float* rowloss, float* dlogits, float* loss,
+                   int accumulate, void* stream);
+/* labels [R,T,P] float; ce = mean_P sigmoid_cross_entropy (model_full.py:651-653). */
+int d2p_sigmoid_ce(float* logits, int T, int R, int P, const float* labels, const int* len,
+                   const int* runlen, const float* w, float* rowloss, float* dlogits, float* loss,
+                   int accumulate, void* stream);
+
+/* ---- fc -> (lrelu) -> BN : ops.fc, reference models/ops.py:149-155 ------------
+ * used by Per_Encoder (model_full.py:308-316; act = 0, per-demo slices) */
+typedef struct {
+    const float* w;      /* [cin, cout] */
+    const float* b;
+    const float* gamma;
+    const float* beta;
+    float* moving_mean;
+    float* moving_var;
+    float* dw;
+    float* db;
+    float* dgamma;
+    float* dbeta;
+} d2p_fc_bn;
+
+size_t d2p_fc_bn_saved_floats(long long rows, int cout, int nsl);
+size_t d2p_fc_bn_ws_bytes(long long rows, int cout, int nsl);
+/* slice(row) = (row / seg) % nsl selects the BN statistics group. */
+int d2p_fc_bn_fwd(const float* X, long long rows, int cin, int cout, int seg, int nsl, int act,
+                  const d2p_fc_bn* p, float* Y, float* saved, int training, void* ws,
+                  size_t ws_bytes, void* stream);
+int d2p_fc_bn_bwd(const float* X, long long rows, int cin, int cout, int seg, int nsl, int act,
+                  const d2p_fc_bn* p, const float* dY, const float* saved, float* dX, int training,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K5: rn_pool, reference models/model_full.py:333-349 ---------------------
+ * F [B,k,H] -> pooled [B,H]; fc1->w is [2H,H], fc2->w is [H,H]. */
+size_t d2p_rn_pool_saved_floats(int B, int k, int H);
+size_t d2p_rn_pool_ws_bytes(int B, int k, int H);
+int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc_bn* fc1,
+                    const d2p_fc_bn* fc2, float* pooled, float* saved, int training, void* ws,
+                    size_t ws_bytes, void* stream);
+int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc_bn* fc1,
+                    const d2p_fc_bn* fc2, const float* dpooled, const float* saved, float* dF,
+                    int training, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- small [B,k,H] reductions (SummarizeFeature avgpool, model_full.py:351-362) */
+int d2p_group_sum(const float* F, int B, int k, int H, float alpha, float* out, int accumulate,
+                  void* stream);
+int d2p_group_bcast(const float* S, int B, int k, int H, float alpha, float* out, int accumulate,
+                    void* stream);
+int d2p_axpby(const float* x, float alpha, float* y, float beta, size_t n, void* stream);
+/* layout helpers at the facade boundary */
+int d2p_logits_to_bvl(const float* X, int T, int R, int V, float* Y, void* stream);
+int d2p_rtp_to_trp(const float* X, int R, int T, int P, float* Y, void* stream);
+int d2p_len_to_int(const float* x, int* y, int n, void* stream);
+
+/* ---- K7: clip_by_global_norm(20) + Adam, reference trainer.py:102-109 --------
+ * state: 8 device doubles, zeroed before the first step ([0] = step count,
+ * [3] = last global norm). grad_scale = 1/world_size after the NCCL sum. */
+size_t d2p_adam_ws_bytes(void);
+int d2p_clip_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr,
+                       float b1, float b2, float eps, float clip_norm, float grad_scale,
+                       int staircase_decay_steps, double* state, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ---- GEMM engine (exposed for tests): row-major
+ * C[M,N] = alpha*op(A)*op(B) + beta*C (+ bias[N]) */
+int d2p_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2P_H_ */

@@ -118,6 +118,7 @@ class OracleModel:
     # -- whole graphs -----------------------------------------------------------
     def forward(self, batch, greedy=False):
         cfg, dt = self.cfg, self.dtype
+        self.new_state = self.state.clone()   # moving stats advance once per forward
         s_h = torch.as_tensor(np.asarray(batch['s_h'])).to(dt)
         demo_len = torch.as_tensor(np.asarray(batch['demo_len'])).long()
         program_len = torch.as_tensor(np.asarray(batch['program_len'])).long()[:, 0]
