@@ -23,6 +23,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, FcBn, check, ptr
 from .manifest import build_manifests
+from .dp import allreduce_flat_gradients
 
 
 def _al(n, a=64):
@@ -401,12 +402,11 @@ class Engine:
         """clip_by_global_norm(20) + Adam (reference trainer.py:102-109); the
         gradient is first averaged over ranks with ONE all-reduce of the flat
         buffer when world_size > 1."""
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grads)
+        scale = allreduce_flat_gradients(self.grads, self.world)
         decay = 10000 if self.cfg.lr_weight_decay else 0
         self._call('d2p_clip_adam_step', ptr(self.params), ptr(self.grads), ptr(self.adam_m),
                    ptr(self.adam_v), self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip,
-                   1.0 / self.world, decay, ptr(self.adam_state), ptr(self.ws), self.ws_bytes,
+                   scale, decay, ptr(self.adam_state), ptr(self.ws), self.ws_bytes,
                    self._st())
 
     # ------------------------------------------------------------------ steps
