@@ -85,6 +85,9 @@ SIGNATURES = {
     'd2p_adam_ws_bytes': (_sz, []),
     'd2p_clip_adam_step': (_i, [_fp, _fp, _fp, _fp, _sz, _f, _f, _f, _f, _f, _f,
                                 _i, _fp, _fp, _sz, _fp]),
+    'd2p_gemm_tc_ws_bytes': (_sz, [_i, _i, _i]),
+    'd2p_gemm_tc': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
+                         _fp, _sz, _fp]),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),
 }

@@ -182,6 +182,13 @@ int d2p_gemm(int transA, int transB, int M, int N, int K, float alpha, const flo
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
              void* stream);
 
+/* Tensor-core engine (tcgen05 + TMEM, bf16x3 split = fp32-equivalent products).
+ * Same contract as d2p_gemm; ws holds the bf16 hi/lo operand splits. */
+size_t d2p_gemm_tc_ws_bytes(int M, int N, int K);
+int d2p_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
+                size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
