@@ -58,7 +58,8 @@ SIGNATURES = {
                               _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                               _sz, _fp]),
     'd2p_embed_shifted': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp]),
-    'd2p_embed_shifted_bwd': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp]),
+    'd2p_embed_shifted_bwd_ws_bytes': (_sz, [_i, _i, _i, _i]),
+    'd2p_embed_shifted_bwd': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp, _sz, _fp]),
     'd2p_seq_weights': (_i, [_fp, _i, _i, _f, _i, _fp, _fp, _fp]),
     'd2p_softmax_ce': (_i, [_fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                             _i, _fp]),
@@ -88,6 +89,8 @@ SIGNATURES = {
     'd2p_gemm_tc_ws_bytes': (_sz, [_i, _i, _i]),
     'd2p_gemm_tc': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                          _fp, _sz, _fp]),
+    'd2p_tc_configure': (_i, [_fp, _sz, _fp, _sz, _i]),
+    'd2p_tc_new_step': (_i, []),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),
 }

@@ -42,7 +42,8 @@ colstats_partial(const float* __restrict__ X, const float* __restrict__ DY,
     long long q0 = (long long)chunk * rows_per_chunk;
     long long q1 = q0 + rows_per_chunk;
     if (q1 > rows_per_slice) q1 = rows_per_slice;
-    for (int c0 = 0; c0 < C; c0 += CT) {   // trip count is block-uniform
+    {   // one column tile per blockIdx.z
+        const int c0 = blockIdx.z * CT;
         const int c = c0 + ct;
         const bool valid = active && c < C;
         float sa = 0.f, sb = 0.f;
@@ -67,8 +68,17 @@ colstats_partial(const float* __restrict__ X, const float* __restrict__ DY,
     }
 }
 
-// Forward finalize: one thread per channel, slices in order (the reference
-// updates the moving stats once per reuse call, i = 0..k-1).
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Finalize kernels: one WARP per channel (8 channels per 256-thread block); lanes
+// stride over the per-block partials and combine with a fixed shuffle tree, so the
+// result is deterministic.
+// Forward: slices in order (the reference updates the moving stats once per reuse
+// call, i = 0..k-1).
 __global__ void bn_fwd_finalize(const float2* __restrict__ partial, int nchunk, int C, int nsl,
                                 double count, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ moving_mean,
@@ -76,12 +86,13 @@ __global__ void bn_fwd_finalize(const float2* __restrict__ partial, int nchunk, 
                                 int training, float* __restrict__ mean_out,
                                 float* __restrict__ rstd_out, float* __restrict__ scale,
                                 float* __restrict__ shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
     if (c >= C) return;
     float g = gamma[c], b = beta[c];
     if (!training) {
         float mu = moving_mean[c], rs = rsqrtf(moving_var[c] + eps);
-        for (int sl = 0; sl < nsl; ++sl) {
+        for (int sl = lane; sl < nsl; sl += 32) {
             mean_out[sl * C + c] = mu; rstd_out[sl * C + c] = rs;
             scale[sl * C + c] = g * rs; shift[sl * C + c] = b - mu * g * rs;
         }
@@ -90,21 +101,24 @@ __global__ void bn_fwd_finalize(const float2* __restrict__ partial, int nchunk, 
     float mm = moving_mean[c], mv = moving_var[c];
     for (int sl = 0; sl < nsl; ++sl) {
         double s = 0.0, s2 = 0.0;
-        for (int j = 0; j < nchunk; ++j) {
+        for (int j = lane; j < nchunk; j += 32) {
             float2 p = partial[((size_t)sl * nchunk + j) * C + c];
             s += p.x; s2 += p.y;
         }
+        s = warp_sum_d(s); s2 = warp_sum_d(s2);
         double mu = s / count;
         double var = s2 / count - mu * mu;
         if (var < 0.0) var = 0.0;
         float muf = (float)mu, varf = (float)var;
         float rs = (float)(1.0 / sqrt(var + (double)eps));
-        mean_out[sl * C + c] = muf; rstd_out[sl * C + c] = rs;
-        scale[sl * C + c] = g * rs; shift[sl * C + c] = b - muf * g * rs;
+        if (lane == 0) {
+            mean_out[sl * C + c] = muf; rstd_out[sl * C + c] = rs;
+            scale[sl * C + c] = g * rs; shift[sl * C + c] = b - muf * g * rs;
+        }
         mm -= (mm - muf) * (1.f - decay);
         mv -= (mv - varf) * (1.f - decay);
     }
-    moving_mean[c] = mm; moving_var[c] = mv;
+    if (lane == 0) { moving_mean[c] = mm; moving_var[c] = mv; }
 }
 
 // Backward finalize: coefficients for dx and the shared-parameter grads.
@@ -114,21 +128,24 @@ __global__ void bn_bwd_finalize(const float2* __restrict__ partial, int nchunk, 
                                 double count, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ k1,
                                 float* __restrict__ k2, int training) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
     if (c >= C) return;
     double tg = 0.0, tb = 0.0;
     for (int sl = 0; sl < nsl; ++sl) {
         double s = 0.0, s2 = 0.0;
-        for (int j = 0; j < nchunk; ++j) {
+        for (int j = lane; j < nchunk; j += 32) {
             float2 p = partial[((size_t)sl * nchunk + j) * C + c];
             s += p.x; s2 += p.y;
         }
+        s = warp_sum_d(s); s2 = warp_sum_d(s2);
         tb += s; tg += s2;
-        k1[sl * C + c] = training ? (float)(s / count) : 0.f;
-        k2[sl * C + c] = training ? (float)(s2 / count) : 0.f;
+        if (lane == 0) {
+            k1[sl * C + c] = training ? (float)(s / count) : 0.f;
+            k2[sl * C + c] = training ? (float)(s2 / count) : 0.f;
+        }
     }
-    dgamma[c] += (float)tg;
-    dbeta[c] += (float)tb;
+    if (lane == 0) { dgamma[c] += (float)tg; dbeta[c] += (float)tb; }
 }
 
 // y = x*scale + shift, optionally permuting rows (r*T + t) -> (t*R + r)
@@ -174,11 +191,13 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ A, const float* __
 
 __global__ void colsum_finalize(const float2* __restrict__ partial, int nchunk, int C,
                                 float* __restrict__ out, float beta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
     if (c >= C) return;
     double s = 0.0;
-    for (int j = 0; j < nchunk; ++j) s += partial[(size_t)j * C + c].x;
-    out[c] = (beta != 0.f ? beta * out[c] : 0.f) + (float)s;
+    for (int j = lane; j < nchunk; j += 32) s += partial[(size_t)j * C + c].x;
+    s = warp_sum_d(s);
+    if (lane == 0) out[c] = (beta != 0.f ? beta * out[c] : 0.f) + (float)s;
 }
 
 // Gather rows of a slice-permuted matrix: used when DY is permuted but stats
@@ -232,11 +251,11 @@ int bn_forward_stats(cudaStream_t st, const float* X, long long rows, int C, int
         D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
         int CT = C < kThreads ? C : kThreads;
         size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-        colstats_partial<0><<<dim3(nchunk, nsl), kThreads, sm, st>>>(
+        colstats_partial<0><<<dim3(nchunk, nsl, cdiv(C, CT)), kThreads, sm, st>>>(
             X, nullptr, nullptr, nullptr, rows / nsl, C, seg, nsl, rpc, (float2*)ws);
         D2P_CHECK_LAUNCH();
     }
-    bn_fwd_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, nsl,
+    bn_fwd_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, nsl,
                                                  (double)(rows / nsl), gamma, beta, moving_mean,
                                                  moving_var, 1e-3f, 0.9f, training, mean, rstd,
                                                  scale, shift);
@@ -276,11 +295,11 @@ int bn_backward(cudaStream_t st, const float* A, const float* DY, float* DZ, lon
     D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
     int CT = C < kThreads ? C : kThreads;
     size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-    colstats_partial<1><<<dim3(nchunk, nsl), kThreads, sm, st>>>(A, dy_lin, mean, rstd, rows / nsl,
+    colstats_partial<1><<<dim3(nchunk, nsl, cdiv(C, CT)), kThreads, sm, st>>>(A, dy_lin, mean, rstd, rows / nsl,
                                                                 C, seg, nsl, rpc, (float2*)ws);
     D2P_CHECK_LAUNCH();
     float* k1 = coef; float* k2 = coef + (size_t)nsl * C;
-    bn_bwd_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, nsl,
+    bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, nsl,
                                                  (double)(rows / nsl), dgamma, dbeta, k1, k2,
                                                  training);
     D2P_CHECK_LAUNCH();
@@ -302,10 +321,10 @@ int colsum(cudaStream_t st, const float* X, long long rows, int C, float* out, f
     D2P_REQUIRE(ws_bytes >= (size_t)nchunk * C * sizeof(float2), "colsum: workspace too small");
     int CT = C < kThreads ? C : kThreads;
     size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-    colstats_partial<0><<<dim3(nchunk, 1), kThreads, sm, st>>>(X, nullptr, nullptr, nullptr, rows, C,
+    colstats_partial<0><<<dim3(nchunk, 1, cdiv(C, CT)), kThreads, sm, st>>>(X, nullptr, nullptr, nullptr, rows, C,
                                                               1, 1, rpc, (float2*)ws);
     D2P_CHECK_LAUNCH();
-    colsum_finalize<<<cdiv(C, 128), 128, 0, st>>>((const float2*)ws, nchunk, C, out, beta);
+    colsum_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, out, beta);
     D2P_CHECK_LAUNCH();
     return 0;
 }

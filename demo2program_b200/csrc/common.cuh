@@ -65,9 +65,14 @@ __device__ __forceinline__ float lrelu_grad_from_out(float a) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// internal engine entry points (gemm.cu)
+// internal engine entry points (gemm.cu / gemm_tc.cu)
+enum { GEMM_CONST_A = 1, GEMM_CONST_B = 2 };   // operand is a weight: pack once per step
 int gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha,
          const float* A, int lda, const float* B, int ldb, float beta, float* C,
-         int ldc, const float* bias = nullptr);
+         int ldc, const float* bias = nullptr, int flags = 0);
+bool tc_eligible(int M, int N, int K);
+int gemm_tc_auto(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha, const float* A,
+                 int lda, const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+                 int flags);
 
 }  // namespace d2p

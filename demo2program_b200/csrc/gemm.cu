@@ -100,9 +100,11 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
 
 int gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha,
          const float* A, int lda, const float* B, int ldb, float beta, float* C,
-         int ldc, const float* bias) {
+         int ldc, const float* bias, int flags) {
     if (M <= 0 || N <= 0) return 0;
     D2P_REQUIRE(K >= 0 && A && B && C, "gemm: bad arguments");
+    if (tc_eligible(M, N, K))   // tensor-core engine (tcgen05, bf16x3)
+        return gemm_tc_auto(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, flags);
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
     if (!ta && !tb)
         sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
@@ -122,5 +124,5 @@ extern "C" int d2p_gemm(int transA, int transB, int M, int N, int K, float alpha
                         const float* A, int lda, const float* B, int ldb, float beta,
                         float* C, int ldc, const float* bias, void* stream) {
     return d2p::gemm((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A,
-                     lda, B, ldb, beta, C, ldc, bias);
+                     lda, B, ldb, beta, C, ldc, bias, 0);
 }

@@ -101,11 +101,11 @@ extern "C" int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, con
     copy_or_zero<<<eb, 256, 0, st>>>(cT, c0, RH);
     D2P_CHECK_LAUNCH();
     // hoisted input contraction for all steps: gates = X*Wx + b
-    D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b));
+    D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
     for (int t = 0; t < T; ++t) {
         float* Gt = gates + (size_t)t * R * G4;
         if (t > 0 || h0 != nullptr)
-            D2P_TRY(gemm(st, false, false, R, G4, H, 1.f, hT, H, Wh, G4, 1.f, Gt, G4));
+            D2P_TRY(gemm(st, false, false, R, G4, H, 1.f, hT, H, Wh, G4, 1.f, Gt, G4, nullptr, GEMM_CONST_B));
         lstm_gates_fwd<<<eb, 256, 0, st>>>(Gt, cells + t * RH, Y + t * RH, hT, cT, len, t, R, H,
                                            forget_bias);
         D2P_CHECK_LAUNCH();
@@ -142,10 +142,10 @@ extern "C" int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, con
                                            c0, dY ? dY + t * RH : nullptr, dh0, dc0, len, t, R, H);
         D2P_CHECK_LAUNCH();
         if (t > 0 || h0 != nullptr)   // dh_{t-1} += dZ_t * Wh^T
-            D2P_TRY(gemm(st, false, true, R, H, G4, 1.f, Gt, G4, Wh, G4, 1.f, dh0, H));
+            D2P_TRY(gemm(st, false, true, R, H, G4, 1.f, Gt, G4, Wh, G4, 1.f, dh0, H, nullptr, GEMM_CONST_B));
     }
     // parameter and input gradients from the full dZ
-    if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In));
+    if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
     D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
     if (T > 1)
         D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));

@@ -126,14 +126,14 @@ extern "C" int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc
     float* st1 = A2 + rows * H; float* st2 = st1 + 4 * H;
     float* P = (float*)(w + p.d); float* Q = (float*)(w + p.e);
     float* X2 = (float*)(w + p.a);
-    D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w, H, 0.f, P, H));
-    D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w + (size_t)H * H, H, 0.f, Q, H));
+    D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w, H, 0.f, P, H, nullptr, GEMM_CONST_B));
+    D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w + (size_t)H * H, H, 0.f, Q, H, nullptr, GEMM_CONST_B));
     pair_add_lrelu<<<ewb(rows * H), 256, 0, st>>>(P, Q, fc1->b, B, k, H, A1);
     D2P_CHECK_LAUNCH();
     D2P_TRY(bn_forward_stats(st, A1, rows, H, 1, 1, fc1->gamma, fc1->beta, fc1->moving_mean,
                              fc1->moving_var, training, st1, w + p.part, p.part_bytes));
     D2P_TRY(bn_apply(st, A1, X2, rows, H, 1, 1, st1, 0, 0));
-    D2P_TRY(gemm(st, false, false, (int)rows, H, H, 1.f, X2, H, fc2->w, H, 0.f, A2, H, fc2->b));
+    D2P_TRY(gemm(st, false, false, (int)rows, H, H, 1.f, X2, H, fc2->w, H, 0.f, A2, H, fc2->b, GEMM_CONST_B));
     lrelu_inplace<<<ewb(rows * H), 256, 0, st>>>(A2, rows * H);
     D2P_CHECK_LAUNCH();
     D2P_TRY(bn_forward_stats(st, A2, rows, H, 1, 1, fc2->gamma, fc2->beta, fc2->moving_mean,
@@ -170,7 +170,7 @@ extern "C" int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc
     D2P_TRY(colsum(st, dZ, rows, H, fc2->db, 1.f, part, p.part_bytes));
     D2P_TRY(bn_apply(st, A1, X2, rows, H, 1, 1, st1, 0, 0));
     D2P_TRY(gemm(st, true, false, H, H, (int)rows, 1.f, X2, H, dZ, H, 1.f, fc2->dw, H));
-    D2P_TRY(gemm(st, false, true, (int)rows, H, H, 1.f, dZ, H, fc2->w, H, 0.f, dY, H));  // dX2
+    D2P_TRY(gemm(st, false, true, (int)rows, H, H, 1.f, dZ, H, fc2->w, H, 0.f, dY, H, nullptr, GEMM_CONST_B));  // dX2
     // first block
     D2P_TRY(bn_backward(st, A1, dY, dZ, rows, H, 1, 1, fc1->gamma, st1, fc1->dgamma, fc1->dbeta,
                         training, 1, coef, part, p.part_bytes, 0, 0, nullptr));
@@ -179,7 +179,7 @@ extern "C" int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc
     D2P_CHECK_LAUNCH();
     D2P_TRY(gemm(st, true, false, H, H, Bk, 1.f, F, H, dP, H, 1.f, fc1->dw, H));
     D2P_TRY(gemm(st, true, false, H, H, Bk, 1.f, F, H, dQ, H, 1.f, fc1->dw + (size_t)H * H, H));
-    D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, dP, H, fc1->w, H, 1.f, dF, H));
-    D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, dQ, H, fc1->w + (size_t)H * H, H, 1.f, dF, H));
+    D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, dP, H, fc1->w, H, 1.f, dF, H, nullptr, GEMM_CONST_B));
+    D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, dQ, H, fc1->w + (size_t)H * H, H, 1.f, dF, H, nullptr, GEMM_CONST_B));
     return 0;
 }

@@ -30,20 +30,34 @@ __global__ void gather_shifted_kernel(const float* __restrict__ table, int vocab
     }
 }
 
-// dTable[v, e] += sum_{(t,r): id(t,r) == v} dX[t,r,e]   (fixed order: deterministic)
-__global__ void embedding_bwd_kernel(const float* __restrict__ dX, int vocab_rows, int E,
-                                     const int* __restrict__ tokens, int R, int L, int start_id,
-                                     float* __restrict__ dTable) {
-    int v = blockIdx.y;
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    float acc = 0.f;
-    for (int t = 0; t < L; ++t)
-        for (int r = 0; r < R; ++r) {
+// dTable[v, e] += sum_{(t,r): id(t,r) == v} dX[t,r,e], two-stage and in a fixed
+// order (deterministic): stage 1 reduces a chunk of positions per block into
+// partial[chunk, v, e]; stage 2 sums the chunks.
+__global__ void embedding_bwd_partial(const float* __restrict__ dX, int vocab_rows, int E,
+                                      const int* __restrict__ tokens, int R, int L, int start_id,
+                                      int pos_per_chunk, float* __restrict__ partial) {
+    const int chunk = blockIdx.x, v = blockIdx.y;
+    const int p0 = chunk * pos_per_chunk;
+    int p1 = p0 + pos_per_chunk;
+    if (p1 > L * R) p1 = L * R;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float acc = 0.f;
+        for (int p = p0; p < p1; ++p) {
+            int t = p / R, r = p % R;
             int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
-            if (id == v) acc += dX[((size_t)t * R + r) * E + e];
+            if (id == v) acc += dX[(size_t)p * E + e];
         }
-    dTable[(size_t)v * E + e] += acc;
+        partial[((size_t)chunk * vocab_rows + v) * E + e] = acc;
+    }
+}
+
+__global__ void embedding_bwd_reduce(const float* __restrict__ partial, int nchunk, int n,
+                                     float* __restrict__ dTable) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int c = 0; c < nchunk; ++c) acc += partial[(size_t)c * n + i];
+    dTable[i] += acc;
 }
 
 // Per decoder-instance normalisers.  Rows r of the same instance share
@@ -228,11 +242,31 @@ extern "C" int d2p_embed_shifted(const float* table, int vocab_rows, int E, cons
     return 0;
 }
 
+static int embed_chunks(int R, int L, int* ppc) {
+    int pos = R * L;
+    int n = pos < 64 ? 1 : (pos / 64 < 64 ? pos / 64 : 64);
+    *ppc = (pos + n - 1) / n;
+    return (pos + *ppc - 1) / *ppc;
+}
+
+extern "C" size_t d2p_embed_shifted_bwd_ws_bytes(int vocab_rows, int E, int R, int L) {
+    int ppc;
+    return (size_t)embed_chunks(R, L, &ppc) * vocab_rows * E * sizeof(float);
+}
+
 extern "C" int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, const int* tokens,
-                                     int R, int L, int start_id, float* dTable, void* stream) {
-    D2P_REQUIRE(dX && tokens && dTable, "embed bwd: bad arguments");
-    embedding_bwd_kernel<<<dim3(cdiv(E, 128), vocab_rows), 128, 0, (cudaStream_t)stream>>>(
-        dX, vocab_rows, E, tokens, R, L, start_id, dTable);
+                                     int R, int L, int start_id, float* dTable, void* ws,
+                                     size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(dX && tokens && dTable && ws, "embed bwd: bad arguments");
+    int ppc;
+    int nchunk = embed_chunks(R, L, &ppc);
+    D2P_REQUIRE(ws_bytes >= (size_t)nchunk * vocab_rows * E * sizeof(float), "embed bwd: workspace too small");
+    embedding_bwd_partial<<<dim3(nchunk, vocab_rows), 256, 0, st>>>(dX, vocab_rows, E, tokens, R, L,
+                                                                    start_id, ppc, (float*)ws);
+    D2P_CHECK_LAUNCH();
+    int n = vocab_rows * E;
+    embedding_bwd_reduce<<<cdiv(n, 256), 256, 0, st>>>((const float*)ws, nchunk, n, dTable);
     D2P_CHECK_LAUNCH();
     return 0;
 }

@@ -35,7 +35,7 @@ class Engine:
 
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
                  frames_dtype=np.uint8, flat_params=None, flat_state=None,
-                 world_size=1, use_graph=True):
+                 world_size=1, use_graph=True, use_tc=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
@@ -62,8 +62,27 @@ class Engine:
         self.adam_state = torch.zeros(8, dtype=torch.float64, device=self.dev)
         self.lr, self.clip = cfg.learning_rate, 20.0
         self._alloc()
+        # tensor-core engine arena: packed bf16 hi/lo operands (activations in
+        # `scratch`, weights cached per step in `cache`)
+        self.use_tc = bool(use_tc)
+        if self.use_tc:
+            R, T, H = self.R, max(self.T, cfg.max_program_len), self.H
+            big = self.lib.d2p_gemm_tc_ws_bytes(T * R, 4 * H, 4 * H) + (8 << 20)
+            self.tc_scratch = torch.zeros(big, dtype=torch.uint8, device=self.dev)
+            self.tc_cache = torch.zeros(12 * self.pm.total + (16 << 20), dtype=torch.uint8,
+                                        device=self.dev)
+        self._tc_bind()
         self._graph = None
         self._graph_key = None
+
+    def _tc_bind(self):
+        """The arena registration is library-global: bind this engine's buffers
+        before issuing work (also invalidates the packed-weight cache)."""
+        if self.use_tc:
+            self.lib.d2p_tc_configure(ptr(self.tc_scratch), self.tc_scratch.numel(),
+                                      ptr(self.tc_cache), self.tc_cache.numel(), 1)
+        else:
+            self.lib.d2p_tc_configure(None, 0, None, 0, 0)
 
     # ------------------------------------------------------------------ params
     def P(self, name):
@@ -182,7 +201,9 @@ class Engine:
                             fc_saved=z(lib.d2p_fc_bn_saved_floats(T * R, H, k)))
             self.per_fc = self._fcbn('Per_Decoder/Per_Encoder/fc2')
             ws = max(ws, lib.d2p_fc_bn_ws_bytes(T * R, H, k))
-        ws = max(ws, lib.d2p_adam_ws_bytes())
+        ws = max(ws, lib.d2p_adam_ws_bytes(),
+                 lib.d2p_embed_shifted_bwd_ws_bytes(V + 1, H, B, L),
+                 lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, H, R, T))
         self.ws_bytes = _al(ws, 256)
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.loss = z(4)   # [total, program, action, per]
@@ -247,6 +268,7 @@ class Engine:
         L, V = cfg.max_program_len, cfg.dim_program_token
         tr = int(self.is_train if train_stats is None else train_stats)
         call = self._call
+        self._tc_bind()              # (re)bind this engine's arena; re-pack weights
         call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, st)
         call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, st)
         call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
@@ -337,7 +359,8 @@ class Engine:
                        'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
                        p['dX'])
         call('d2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
-             ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), st)
+             ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+             self.ws_bytes, st)
         # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
         have_dh2 = False
         if self.model == 'full':
@@ -351,7 +374,8 @@ class Engine:
                            'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
                            a['dX'])
             call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
-                 ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), st)
+                 ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                 self.ws_bytes, st)
             Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
                        self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd)

@@ -104,8 +104,9 @@ int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, const int* len
  * :620-657 (Sequence_Loss). tokens [R,L] int32; X [L,R,E]. */
 int d2p_embed_shifted(const float* table, int vocab_rows, int E, const int* tokens, int R, int L,
                       int start_id, float* X, void* stream);
+size_t d2p_embed_shifted_bwd_ws_bytes(int vocab_rows, int E, int R, int L);
 int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, const int* tokens, int R, int L,
-                          int start_id, float* dTable, void* stream);
+                          int start_id, float* dTable, void* ws, size_t ws_bytes, void* stream);
 /* w[r] = coef / sum(len over rows of the same decoder instance r % nsl);
  * runlen[r] = max len over that instance (TrainingHelper runs max_b len steps). */
 int d2p_seq_weights(const int* len, int R, int nsl, float coef, int max_len, float* w, int* runlen,
@@ -188,6 +189,14 @@ size_t d2p_gemm_tc_ws_bytes(int M, int N, int K);
 int d2p_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
                 size_t ws_bytes, void* stream);
+
+/* Arena for the tensor-core engine: `scratch` holds packed activations (reused by
+ * every GEMM on the stream), `cache` holds packed weights until d2p_tc_new_step()
+ * (call it whenever parameters changed).  With no arena configured (or
+ * enabled = 0) every contraction runs on the exact-fp32 SIMT engine. */
+int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache, size_t cache_bytes,
+                     int enabled);
+int d2p_tc_new_step(void);
 
 #ifdef __cplusplus
 }
