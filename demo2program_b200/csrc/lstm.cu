@@ -16,6 +16,14 @@ namespace d2p {
 
 int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, size_t);
 size_t bn_ws_bytes(long long rows, int C, int nsl);
+// tensor-core recurrence (lstm_tc.cu)
+bool lstm_tc_supported(int R, int H);
+int lstm_seq_fwd_tc(cudaStream_t, const float*, int, int, int, int, const int*, const float*,
+                    const float*, const float*, const float*, float, float*, float*, float*, float*,
+                    float*);
+int lstm_seq_bwd_tc(cudaStream_t, const float*, int, int, int, int, const int*, const float*,
+                    const float*, const float*, const float*, float*, const float*, const float*,
+                    const float*, const float*, float*, float*, float*, float*, float*, void*, size_t);
 
 namespace {
 
@@ -91,6 +99,8 @@ extern "C" int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, con
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(X && len && W && b && Y && hT && cT && gates && cells, "lstm fwd: null buffer");
     D2P_REQUIRE(T > 0 && R > 0 && In > 0 && H > 0, "lstm fwd: bad dims");
+    if (lstm_tc_supported(R, H))
+        return lstm_seq_fwd_tc(st, X, T, R, In, H, len, h0, c0, W, b, forget_bias, Y, hT, cT, gates, cells);
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;
@@ -125,6 +135,9 @@ extern "C" int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, con
                                 float* dh0, float* dc0, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(X && len && W && Y && gates && cells && dW && db && dh0 && dc0, "lstm bwd: null buffer");
+    if (lstm_tc_supported(R, H))
+        return lstm_seq_bwd_tc(st, X, T, R, In, H, len, h0, c0, W, Y, gates, cells, dY, dhT, dcT, dX, dW,
+                               db, dh0, dc0, ws, ws_bytes);
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;

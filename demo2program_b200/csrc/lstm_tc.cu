@@ -1,0 +1,292 @@
+// Tensor-core LSTM recurrence (tcgen05) with the cell non-linearity fused into
+// the GEMM epilogue.
+//
+// Forward step t (one launch): z = h_{t-1} * Wh (+ the hoisted X*Wx + b already
+// in gates[t]); the recurrent weight is packed ONCE per sequence with its
+// columns permuted so that every 64-wide output tile holds the i, j, f, o
+// columns of 16 hidden units.  The epilogue thread that owns accumulator row r
+// therefore sees all four gates of its units, applies BasicLSTMCell
+// (reference models/model_full.py:244) with dynamic_rnn masking
+// (A.5), and writes h_t both as fp32 (Y, state) and directly in the packed bf16
+// hi/lo operand format the next step's MMA consumes - no separate gate kernel,
+// no separate split/pack pass.
+//
+// Backward step t (two launches): a fused element-wise kernel combines the
+// split-K partial sums of dh (fixed order), back-propagates through the cell
+// and writes dZ_t as fp32 (for the dW / dX products) and as the packed A
+// operand; then one split-K tcgen05 GEMM produces the partial sums of
+// dh_{t-1} = dZ_t * Wh^T over all SMs.
+#include "tc_common.cuh"
+
+namespace d2p {
+
+using namespace tc;
+
+bool tc_available();
+int gemm_tc_nsplit(int K, int ksplit);
+int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, size_t);
+
+namespace {
+
+constexpr int LBN = 64, LSTAGES = 8, UPT = LBN / 4;   // 16 hidden units per tile
+
+__global__ void __launch_bounds__(128)
+lstm_step_fwd_kernel(Packed A, Packed B, int R, int H, float* __restrict__ gates_t,
+                     float* __restrict__ cells_t, float* __restrict__ Y_t,
+                     float* __restrict__ hstate, float* __restrict__ cstate,
+                     const int* __restrict__ len, int t, float forget_bias,
+                     uint8_t* __restrict__ hpk_next, int hpk_mgp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * LBN;
+    const uint32_t tmem_d = tc_mainloop<LBN, LSTAGES>(A, B, m0, n0, 0, (H + BK - 1) / BK, smem);
+
+    const int r = m0 + warp * 32 + lane;
+    const int u0 = blockIdx.x * UPT;
+    uint32_t acc[4][UPT];
+    const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_ld16(trow + g * UPT, acc[g]);
+    tmem_ld_wait();
+    if (r < R) {
+        const bool live = t < len[r];
+        float* grow = gates_t + (size_t)r * 4 * H + u0;
+        const size_t su = (size_t)r * H + u0;
+        float hn[UPT];
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < UPT; q += 4) {
+                float4 zi = *reinterpret_cast<const float4*>(grow + q);
+                float4 zj = *reinterpret_cast<const float4*>(grow + H + q);
+                float4 zf = *reinterpret_cast<const float4*>(grow + 2 * H + q);
+                float4 zo = *reinterpret_cast<const float4*>(grow + 3 * H + q);
+                float4 cp = *reinterpret_cast<const float4*>(cstate + su + q);
+                float pi[4] = {zi.x, zi.y, zi.z, zi.w}, pj[4] = {zj.x, zj.y, zj.z, zj.w};
+                float pf[4] = {zf.x, zf.y, zf.z, zf.w}, po[4] = {zo.x, zo.y, zo.z, zo.w};
+                float pc[4] = {cp.x, cp.y, cp.z, cp.w};
+                float gi[4], gj[4], gf[4], go[4], cn[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    gi[e] = sigmoid_f(pi[e] + __uint_as_float(acc[0][q + e]));
+                    gj[e] = tanhf(pj[e] + __uint_as_float(acc[1][q + e]));
+                    gf[e] = sigmoid_f(pf[e] + __uint_as_float(acc[2][q + e]) + forget_bias);
+                    go[e] = sigmoid_f(po[e] + __uint_as_float(acc[3][q + e]));
+                    cn[e] = pc[e] * gf[e] + gi[e] * gj[e];
+                    hn[q + e] = tanhf(cn[e]) * go[e];
+                }
+                *reinterpret_cast<float4*>(grow + q) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                *reinterpret_cast<float4*>(grow + H + q) = make_float4(gj[0], gj[1], gj[2], gj[3]);
+                *reinterpret_cast<float4*>(grow + 2 * H + q) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                *reinterpret_cast<float4*>(grow + 3 * H + q) = make_float4(go[0], go[1], go[2], go[3]);
+                float4 c4 = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                float4 h4 = make_float4(hn[q], hn[q + 1], hn[q + 2], hn[q + 3]);
+                *reinterpret_cast<float4*>(cells_t + su + q) = c4;
+                *reinterpret_cast<float4*>(cstate + su + q) = c4;
+                *reinterpret_cast<float4*>(Y_t + su + q) = h4;
+                *reinterpret_cast<float4*>(hstate + su + q) = h4;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < UPT; q += 4) {
+                float4 cp = *reinterpret_cast<const float4*>(cstate + su + q);
+                float4 hp = *reinterpret_cast<const float4*>(hstate + su + q);
+                *reinterpret_cast<float4*>(cells_t + su + q) = cp;
+                *reinterpret_cast<float4*>(Y_t + su + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                hn[q] = hp.x; hn[q + 1] = hp.y; hn[q + 2] = hp.z; hn[q + 3] = hp.w;
+            }
+        }
+        // h_t in packed operand format for step t+1 (k = hidden unit)
+        store_packed8(hpk_next, hpk_mgp, r, u0, hn);
+        store_packed8(hpk_next, hpk_mgp, r, u0 + 8, hn + 8);
+    }
+    tc_teardown<LBN>(tmem_d);
+}
+
+// Element-wise backward through the cell at step t for 8 hidden units of one row.
+//   dh_in = dhc + sum_s partial_s  (partial sums of dZ_{t+1} * Wh^T) + dY_t
+__global__ void lstm_bwd_point_kernel(float* __restrict__ G /*[R,4H] in: gates, out: dZ*/,
+                                      const float* __restrict__ cells_t,
+                                      const float* __restrict__ cells_prev,
+                                      const float* __restrict__ c0, const float* __restrict__ dY_t,
+                                      const float* __restrict__ partials, int nsplit,
+                                      float* __restrict__ dhc, float* __restrict__ dcs,
+                                      const int* __restrict__ len, int t, int R, int H,
+                                      uint8_t* __restrict__ dzpk, int dz_mgp) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ug = H / 8;
+    if (idx >= R * ug) return;
+    const int r = idx / ug, u0 = (idx % ug) * 8;
+    const size_t su = (size_t)r * H + u0;
+    float dh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dh[e] = dhc[su + e];
+    for (int s = 0; s < nsplit; ++s) {
+        const float* p = partials + (size_t)s * R * H + su;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dh[e] += p[e];
+    }
+    float* g = G + (size_t)r * 4 * H + u0;
+    float di[8], dj[8], df[8], dq[8];
+    if (t < len[r]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float i = g[e], j = g[H + e], f = g[2 * H + e], o = g[3 * H + e];
+            float c = cells_t[su + e];
+            float cprev = cells_prev ? cells_prev[su + e] : (c0 ? c0[su + e] : 0.f);
+            float dht = dh[e] + (dY_t ? dY_t[su + e] : 0.f);
+            float tcn = tanhf(c);
+            dq[e] = dht * tcn * o * (1.f - o);
+            float dc = dcs[su + e] + dht * o * (1.f - tcn * tcn);
+            di[e] = dc * j * i * (1.f - i);
+            dj[e] = dc * i * (1.f - j * j);
+            df[e] = dc * cprev * f * (1.f - f);
+            dcs[su + e] = dc * f;
+            dhc[su + e] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            di[e] = dj[e] = df[e] = dq[e] = 0.f;
+            dhc[su + e] = dh[e];   // state copied through: gradient passes unchanged
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { g[e] = di[e]; g[H + e] = dj[e]; g[2 * H + e] = df[e]; g[3 * H + e] = dq[e]; }
+    store_packed8(dzpk, dz_mgp, r, u0, di);
+    store_packed8(dzpk, dz_mgp, r, H + u0, dj);
+    store_packed8(dzpk, dz_mgp, r, 2 * H + u0, df);
+    store_packed8(dzpk, dz_mgp, r, 3 * H + u0, dq);
+}
+
+// dst += sum_s partial_s
+__global__ void add_partials_kernel(float* __restrict__ dst, const float* __restrict__ partials,
+                                    int nsplit, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = dst[i];
+    for (int s = 0; s < nsplit; ++s) a += partials[(size_t)s * n + i];
+    dst[i] = a;
+}
+
+__global__ void copy_or_zero_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src ? src[i] : 0.f;
+}
+
+}  // namespace
+
+bool lstm_tc_supported(int R, int H) {
+    return tc_available() && H % 32 == 0 && H >= 32 && R >= 1;
+}
+
+int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H, const int* len,
+                    const float* h0, const float* c0, const float* W, const float* b,
+                    float forget_bias, float* Y, float* hT, float* cT, float* gates, float* cells) {
+    const int G4 = 4 * H;
+    const float* Wx = W;
+    const float* Wh = W + (size_t)In * G4;
+    const size_t RH = (size_t)R * H;
+    const int eb = cdiv(RH, 256);
+    // phase 1: hoisted input contraction for all steps: gates = X*Wx + b
+    D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
+    // phase 2: recurrence (the arena is reused from offset 0; stream order makes that safe)
+    size_t off = 0;
+    const size_t hbytes = packed_bytes(R, H);
+    uint8_t* hpk[2];
+    hpk[0] = (uint8_t*)tc_scratch_alloc(&off, hbytes);
+    hpk[1] = (uint8_t*)tc_scratch_alloc(&off, hbytes);
+    D2P_REQUIRE(hpk[0] && hpk[1], "lstm fwd: tensor-core scratch arena too small");
+    const void* whpk;
+    D2P_TRY(get_packed(st, Wh, G4, H, G4, false, true, &off, &whpk, LBN, H));
+    if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, hpk[0]));
+    else D2P_CHECK_CUDA(cudaMemsetAsync(hpk[0], 0, hbytes, st));
+    D2P_CHECK_CUDA(cudaMemsetAsync(hpk[1], 0, hbytes, st));
+    copy_or_zero_k<<<eb, 256, 0, st>>>(hT, h0, RH);
+    D2P_CHECK_LAUNCH();
+    copy_or_zero_k<<<eb, 256, 0, st>>>(cT, c0, RH);
+    D2P_CHECK_LAUNCH();
+    constexpr size_t smem = tc_smem_bytes<LBN, LSTAGES>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_step_fwd_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int mgp_h = mgp_of(R);
+    dim3 grid(G4 / LBN, cdiv(R, BM));
+    for (int t = 0; t < T; ++t) {
+        Packed A{hpk[t & 1], mgp_h};
+        Packed B{(const uint8_t*)whpk, mgp_of(G4)};
+        lstm_step_fwd_kernel<<<grid, 128, smem, st>>>(A, B, R, H, gates + (size_t)t * R * G4,
+                                                      cells + t * RH, Y + t * RH, hT, cT, len, t,
+                                                      forget_bias, hpk[(t + 1) & 1], mgp_h);
+        D2P_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H, const int* len,
+                    const float* h0, const float* c0, const float* W, const float* Y, float* gates,
+                    const float* cells, const float* dY, const float* dhT, const float* dcT,
+                    float* dX, float* dW, float* db, float* dh0, float* dc0, void* ws,
+                    size_t ws_bytes) {
+    const int G4 = 4 * H;
+    const float* Wx = W;
+    const float* Wh = W + (size_t)In * G4;
+    float* dWx = dW;
+    float* dWh = dW + (size_t)In * G4;
+    const size_t RH = (size_t)R * H;
+    const int eb = cdiv(RH, 256);
+    // split-K factor of the per-step dh GEMM [R, H] = dZ_t [R, 4H] * Wh^T
+    long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
+    int ks = (int)(144 / (tiles64 < 1 ? 1 : tiles64));
+    const int nkb = cdiv(G4, BK);
+    if (ks > nkb / 8) ks = nkb / 8;
+    if (ks > 8) ks = 8;
+    if (ks < 1) ks = 1;
+    const int nsplit = gemm_tc_nsplit(G4, ks);
+
+    size_t off = 0;
+    const size_t zbytes = packed_bytes(R, G4);
+    uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(&off, zbytes);
+    float* partials = (float*)tc_scratch_alloc(&off, (size_t)nsplit * RH * sizeof(float));
+    D2P_REQUIRE(dzpk && partials, "lstm bwd: tensor-core scratch arena too small");
+    const void* whpk;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
+    D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));
+    D2P_CHECK_CUDA(cudaMemsetAsync(dzpk, 0, zbytes, st));
+    copy_or_zero_k<<<eb, 256, 0, st>>>(dh0, dhT, RH);   // dh0/dc0 double as the running carries
+    D2P_CHECK_LAUNCH();
+    copy_or_zero_k<<<eb, 256, 0, st>>>(dc0, dcT, RH);
+    D2P_CHECK_LAUNCH();
+    const int mgp_z = mgp_of(R);
+    const int pb = cdiv((long long)R * (H / 8), 128);
+    bool have_partials = false;
+    for (int t = T - 1; t >= 0; --t) {
+        float* Gt = gates + (size_t)t * R * G4;
+        lstm_bwd_point_kernel<<<pb, 128, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
+                                                  c0, dY ? dY + t * RH : nullptr, partials,
+                                                  have_partials ? nsplit : 0, dh0, dc0, len, t, R, H,
+                                                  dzpk, mgp_z);
+        D2P_CHECK_LAUNCH();
+        if (t > 0 || h0 != nullptr) {   // partial sums of dh_{t-1} = dZ_t * Wh^T
+            D2P_TRY(gemm_tc_packed(st, dzpk, whpk, R, H, G4, 1.f, 0.f, nullptr, H, nullptr, ks, partials));
+            have_partials = true;
+        } else {
+            have_partials = false;
+        }
+    }
+    if (have_partials) {   // dh0 = carry + last partial sums
+        add_partials_kernel<<<eb, 256, 0, st>>>(dh0, partials, nsplit, RH);
+        D2P_CHECK_LAUNCH();
+    }
+    // parameter and input gradients from the full dZ (arena reused from offset 0)
+    if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+    D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
+    if (T > 1)
+        D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
+    if (h0) D2P_TRY(gemm(st, true, false, H, G4, R, 1.f, h0, H, gates, G4, 1.f, dWh, G4));
+    D2P_TRY(colsum(st, gates, (long long)T * R, G4, db, 1.f, ws, ws_bytes));
+    return 0;
+}
+
+}  // namespace d2p
