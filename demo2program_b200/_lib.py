@@ -91,6 +91,7 @@ SIGNATURES = {
                          _fp, _sz, _fp]),
     'd2p_tc_configure': (_i, [_fp, _sz, _fp, _sz, _i]),
     'd2p_tc_new_step': (_i, []),
+    'd2p_debug_set_probe': (_i, [_fp]),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),
 }

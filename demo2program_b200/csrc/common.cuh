@@ -64,6 +64,10 @@ __device__ __forceinline__ float lrelu_grad_from_out(float a) {
     return a > 0.f ? 1.0f : (a < 0.f ? 0.2f : 0.6f);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Short-latency forms for the recurrent kernels, whose few resident warps cannot hide
+// long dependent instruction chains: ex2.approx + rcp (abs. error ~1e-7, i.e. fp32 rounding level)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * x)); }
 
 // internal engine entry points (gemm.cu / gemm_tc.cu)
 enum { GEMM_CONST_A = 1, GEMM_CONST_B = 2 };   // operand is a weight: pack once per step

@@ -13,16 +13,17 @@
 //
 // Kernel: one CTA per 128 x BN tile (BN = 64/128), 4 warps, warp-specialised
 // (producer lane / MMA-issuer lane / 4 epilogue warps), see tc_mainloop().
-//   * large grids: BN = 128, 3 stages (96 KB) -> two CTAs per SM, one CTA's
-//     epilogue overlaps the other's main loop;
-//   * small grids (recurrent steps, skinny products): BN = 64, 8 stages (192 KB)
-//     because a lone CTA must cover the L2/HBM latency by itself, plus split-K
-//     over blockIdx.z so that all SMs pull operand bytes; partial sums are
-//     combined in a fixed order (deterministic).
+//   * large grids: BN = 128, 3 stages x 64 KB (BK = 64);
+//   * small grids (recurrent steps, skinny products): BN = 64, 4 stages x 48 KB,
+//     plus split-K over blockIdx.z so that all SMs pull operand bytes; partial
+//     sums are combined in a fixed order (deterministic).
+// The epilogue parks each warp's 32 accumulator rows in the idle pipeline smem and
+// writes them back row by row (coalesced) instead of one row per thread.
 #include "tc_common.cuh"
 
 namespace d2p {
 
+int lstm_tc_set_probe(long long* buf);
 using namespace tc;
 
 namespace {
@@ -41,58 +42,65 @@ gemm_tc_kernel(Packed A, Packed B, int M, int N, int K, float alpha, float beta,
     if (nk > nk_per_split) nk = nk_per_split;
     const uint32_t tmem_d = tc_mainloop<BN, STAGES>(A, B, m0, n0, kb0, nk, smem);
 
-    const int m = m0 + warp * 32 + lane;
+    // ---- epilogue ----
+    // A thread owns one accumulator row, so storing straight from registers would touch
+    // 32 different cache lines per warp instruction.  Instead each warp parks its 32 rows
+    // in the (now idle) pipeline smem and writes them back row by row, fully coalesced.
     const bool split = partials != nullptr;
     float* out = split ? partials + (size_t)blockIdx.z * M * N : C;
     const int ldo = split ? N : ldc;
-    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    constexpr int SROW = BN + 4;                       // padded row (floats): conflict-free
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * SROW;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (m < M) {
-            float* crow = out + (size_t)m * ldo;
-            const int nb = n0 + c0;
-            if (split) {
-                if (vec_ok && nb + 32 <= N) {
+        float* srow = stage + (size_t)lane * SROW + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(crow + nb + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < N) crow[nb + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(srow + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    __syncwarp();
+    const float a_ = split ? 1.f : alpha, b_ = split ? 0.f : beta;
+    const float* bias_ = split ? nullptr : bias;
+    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                        (n0 + BN <= N);
+    const int mrow0 = m0 + warp * 32;
+    if (vec_ok) {
+        constexpr int LPR = BN / 4;                    // lanes per row (float4 each)
+        constexpr int RPI = 32 / LPR;                  // rows per warp instruction
+        const int cl = (lane % LPR) * 4, rl = lane / LPR;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_) bv = *reinterpret_cast<const float4*>(bias_ + n0 + cl);
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += RPI) {
+            const int row = rr + rl, m = mrow0 + row;
+            if (m < M) {
+                float4 x = *reinterpret_cast<const float4*>(stage + (size_t)row * SROW + cl);
+                float4 r = make_float4(a_ * x.x + bv.x, a_ * x.y + bv.y, a_ * x.z + bv.z, a_ * x.w + bv.w);
+                float4* dst = reinterpret_cast<float4*>(out + (size_t)m * ldo + n0 + cl);
+                if (b_ != 0.f) {
+                    float4 o = *dst;
+                    r.x += b_ * o.x; r.y += b_ * o.y; r.z += b_ * o.z; r.w += b_ * o.w;
                 }
-            } else if (vec_ok && nb + 32 <= N) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r;
-                    r.x = alpha * __uint_as_float(v[j]);     r.y = alpha * __uint_as_float(v[j + 1]);
-                    r.z = alpha * __uint_as_float(v[j + 2]); r.w = alpha * __uint_as_float(v[j + 3]);
-                    if (bias) {
-                        float4 b4 = *reinterpret_cast<const float4*>(bias + nb + j);
-                        r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
-                    }
-                    float4* dst = reinterpret_cast<float4*>(crow + nb + j);
-                    if (beta != 0.f) {
-                        float4 o = *dst;
-                        r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w;
-                    }
+                *dst = r;
+            }
+        }
+    } else {
+        for (int row = 0; row < 32; ++row) {
+            const int m = mrow0 + row;
+            if (m >= M) break;
+            for (int c = lane; c < BN; c += 32) {
+                const int n = n0 + c;
+                if (n < N) {
+                    float r = a_ * stage[(size_t)row * SROW + c];
+                    if (bias_) r += bias_[n];
+                    float* dst = out + (size_t)m * ldo + n;
+                    if (b_ != 0.f) r += b_ * *dst;
                     *dst = r;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    int n = nb + j;
-                    if (n < N) {
-                        float r = alpha * __uint_as_float(v[j]);
-                        if (bias) r += bias[n];
-                        if (beta != 0.f) r += beta * crow[n];
-                        crow[n] = r;
-                    }
                 }
             }
         }
@@ -130,10 +138,13 @@ __global__ void pack_bf16_kernel(const float* __restrict__ S, int MN, int K, int
     const size_t total = (size_t)kgp * mgp * 8;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
+        // idx = ((kb*mgp + mg)*8 + kgl)*8 + r : consecutive threads fill consecutive 16 B
         const int r = (int)(idx & 7);
         const size_t g = idx >> 3;
-        const int mg = (int)(g % mgp), kg = (int)(g / mgp);
-        const int mn = mg * 8 + r, k0 = kg * 8;
+        const int kgl = (int)(g & 7);
+        const size_t q = g >> 3;
+        const int mg = (int)(q % mgp), kb = (int)(q / mgp);
+        const int mn = mg * 8 + r, k0 = (kb * 8 + kgl) * 8;
         int col = mn;
         if (!K_CONTIG && gate_tile > 0 && mn < MN) {
             const int upt = gate_tile / 4;
@@ -191,9 +202,9 @@ TcState g_tc;
 int auto_ksplit(int M, int N, int K) {
     long long tiles64 = (long long)cdiv(N, 64) * cdiv(M, BM);
     int nk = cdiv(K, BK);
-    if (tiles64 > 48 || nk < 16) return 1;
+    if (tiles64 > 48 || nk < 8) return 1;
     long long s = 144 / tiles64;
-    if (s > nk / 8) s = nk / 8;
+    if (s > nk / 4) s = nk / 4;
     if (s > 8) s = 8;
     return s < 1 ? 1 : (int)s;
 }
@@ -229,7 +240,7 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
     bool narrow = (long long)cdiv(N, 128) * cdiv(M, BM) < kNumSMs;
     int zs;
     if (narrow)
-        zs = launch_tc<64, 8>(st, A, B, M, N, K, alpha, beta, C, ldc, bias, ksplit,
+        zs = launch_tc<64, 4>(st, A, B, M, N, K, alpha, beta, C, ldc, bias, ksplit,
                               use_part ? partials : nullptr);
     else
         zs = launch_tc<128, 3>(st, A, B, M, N, K, alpha, beta, C, ldc, bias, ksplit,
@@ -360,4 +371,10 @@ extern "C" int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache
 extern "C" int d2p_tc_new_step(void) {
     d2p::g_tc.cache_used = 0; d2p::g_tc.n_entries = 0;
     return 0;
+}
+
+// developer tool: SM-clock timeline probe of CTA (0,0,0) of the tensor-core kernels
+extern "C" int d2p_debug_set_probe(long long* buf) {
+    D2P_CHECK_CUDA(cudaMemcpyToSymbol(d2p::tc::g_tc_dbg, &buf, sizeof(buf)));
+    return d2p::lstm_tc_set_probe(buf);
 }

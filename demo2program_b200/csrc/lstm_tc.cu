@@ -28,134 +28,196 @@ int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, siz
 
 namespace {
 
-constexpr int LBN = 64, LSTAGES = 8, UPT = LBN / 4;   // 16 hidden units per tile
+constexpr int LBN = 64, LSTAGES = 3, UPT = LBN / 4;   // 16 hidden units per tile
+constexpr int LTHREADS = 512;                         // 2 role warps + 14 helper warps
+constexpr int ZROW = LBN + 4, SROW = UPT + 4;         // padded smem rows (floats)
+constexpr size_t L_PIPE_BYTES = tc_smem_bytes<LBN, LSTAGES>();
+constexpr size_t L_SMEM_BYTES = L_PIPE_BYTES + (size_t)BM * (ZROW + 2 * SROW) * sizeof(float);
 
-__global__ void __launch_bounds__(128)
+// Epilogue inputs of one 128-row x 16-unit tile, fetched into smem with coalesced
+// 16-byte loads by the helper warps WHILE the main loop runs.
+struct StepPrefetch {
+    const float* gates_t; const float* cstate; const float* hstate;
+    float* zs; float* cs; float* hs;
+    int m0, u0, R, H;
+    __device__ __forceinline__ void operator()(int w, int nw) const {
+        for (int idx = w; idx < BM * LBN / 4; idx += nw) {          // (row, gate) segments of 64 B
+            const int f4 = (idx & 3) * 4, seg = idx >> 2;
+            const int gate = seg & 3, row = seg >> 2;
+            if (m0 + row < R)
+                *reinterpret_cast<float4*>(zs + (size_t)row * ZROW + gate * UPT + f4) =
+                    *reinterpret_cast<const float4*>(gates_t + (size_t)(m0 + row) * 4 * H + gate * H + u0 + f4);
+        }
+        for (int idx = w; idx < BM * UPT / 4; idx += nw) {
+            const int f4 = (idx & 3) * 4, row = idx >> 2;
+            if (m0 + row < R) {
+                const size_t g = (size_t)(m0 + row) * H + u0 + f4;
+                *reinterpret_cast<float4*>(cs + (size_t)row * SROW + f4) = *reinterpret_cast<const float4*>(cstate + g);
+                *reinterpret_cast<float4*>(hs + (size_t)row * SROW + f4) = *reinterpret_cast<const float4*>(hstate + g);
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(LTHREADS)
 lstm_step_fwd_kernel(Packed A, Packed B, int R, int H, float* __restrict__ gates_t,
                      float* __restrict__ cells_t, float* __restrict__ Y_t,
                      float* __restrict__ hstate, float* __restrict__ cstate,
                      const int* __restrict__ len, int t, float forget_bias,
                      uint8_t* __restrict__ hpk_next, int hpk_mgp) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * LBN;
-    const uint32_t tmem_d = tc_mainloop<LBN, LSTAGES>(A, B, m0, n0, 0, (H + BK - 1) / BK, smem);
-
-    const int r = m0 + warp * 32 + lane;
     const int u0 = blockIdx.x * UPT;
-    uint32_t acc[4][UPT];
-    const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+    float* zs = reinterpret_cast<float*>(smem + L_PIPE_BYTES);      // [128][ZROW] pre-activations
+    float* cs = zs + (size_t)BM * ZROW;                             // [128][SROW] c_{t-1}
+    float* hs = cs + (size_t)BM * SROW;                             // [128][SROW] h_{t-1}
+    StepPrefetch pf{gates_t, cstate, hstate, zs, cs, hs, m0, u0, R, H};
+    const uint32_t tmem_d = tc_mainloop<LBN, LSTAGES>(A, B, m0, n0, 0, (H + BK - 1) / BK, smem, pf);
+
+    __syncthreads();   // prefetched tiles (helper warps) visible to every warp
+
+    // ---- epilogue, all 16 warps ----
+    // (1) z += accumulator: warp w adds gate (w / 4) for the 32 rows of TMEM lane quarter (w % 4)
+    {
+        const int q = warp & 3, g = warp >> 2;
+        uint32_t v[UPT];
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * UPT), v);
+        tmem_ld_wait();
+        float* zr = zs + (size_t)(q * 32 + lane) * ZROW + g * UPT;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) tmem_ld16(trow + g * UPT, acc[g]);
-    tmem_ld_wait();
-    if (r < R) {
-        const bool live = t < len[r];
-        float* grow = gates_t + (size_t)r * 4 * H + u0;
-        const size_t su = (size_t)r * H + u0;
-        float hn[UPT];
-        if (live) {
-#pragma unroll
-            for (int q = 0; q < UPT; q += 4) {
-                float4 zi = *reinterpret_cast<const float4*>(grow + q);
-                float4 zj = *reinterpret_cast<const float4*>(grow + H + q);
-                float4 zf = *reinterpret_cast<const float4*>(grow + 2 * H + q);
-                float4 zo = *reinterpret_cast<const float4*>(grow + 3 * H + q);
-                float4 cp = *reinterpret_cast<const float4*>(cstate + su + q);
-                float pi[4] = {zi.x, zi.y, zi.z, zi.w}, pj[4] = {zj.x, zj.y, zj.z, zj.w};
-                float pf[4] = {zf.x, zf.y, zf.z, zf.w}, po[4] = {zo.x, zo.y, zo.z, zo.w};
-                float pc[4] = {cp.x, cp.y, cp.z, cp.w};
+        for (int j = 0; j < UPT; j += 4) {
+            float4 z = *reinterpret_cast<float4*>(zr + j);
+            z.x += __uint_as_float(v[j]);     z.y += __uint_as_float(v[j + 1]);
+            z.z += __uint_as_float(v[j + 2]); z.w += __uint_as_float(v[j + 3]);
+            *reinterpret_cast<float4*>(zr + j) = z;
+        }
+    }
+    __syncthreads();
+    // (2) cell math: thread = (row, 4 hidden units); 64-byte segments per 4 lanes -> coalesced
+    {
+        const int row = tid >> 2, uq = (tid & 3) * 4;
+        const int r = m0 + row;
+        if (r < R) {
+            const bool live = t < len[r];
+            const float* zr = zs + (size_t)row * ZROW + uq;
+            const float4 hp = *reinterpret_cast<const float4*>(hs + (size_t)row * SROW + uq);
+            const size_t gu = (size_t)r * H + u0 + uq;
+            float hn[4] = {hp.x, hp.y, hp.z, hp.w};
+            if (live) {
+                const float4 zi = *reinterpret_cast<const float4*>(zr);
+                const float4 zj = *reinterpret_cast<const float4*>(zr + UPT);
+                const float4 zf = *reinterpret_cast<const float4*>(zr + 2 * UPT);
+                const float4 zo = *reinterpret_cast<const float4*>(zr + 3 * UPT);
+                const float4 cp = *reinterpret_cast<const float4*>(cs + (size_t)row * SROW + uq);
+                const float pi[4] = {zi.x, zi.y, zi.z, zi.w}, pj[4] = {zj.x, zj.y, zj.z, zj.w};
+                const float pf4[4] = {zf.x, zf.y, zf.z, zf.w}, po[4] = {zo.x, zo.y, zo.z, zo.w};
+                const float pc[4] = {cp.x, cp.y, cp.z, cp.w};
                 float gi[4], gj[4], gf[4], go[4], cn[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    gi[e] = sigmoid_f(pi[e] + __uint_as_float(acc[0][q + e]));
-                    gj[e] = tanhf(pj[e] + __uint_as_float(acc[1][q + e]));
-                    gf[e] = sigmoid_f(pf[e] + __uint_as_float(acc[2][q + e]) + forget_bias);
-                    go[e] = sigmoid_f(po[e] + __uint_as_float(acc[3][q + e]));
+                    gi[e] = sigmoid_fast(pi[e]);
+                    gj[e] = tanh_fast(pj[e]);
+                    gf[e] = sigmoid_fast(pf4[e] + forget_bias);
+                    go[e] = sigmoid_fast(po[e]);
                     cn[e] = pc[e] * gf[e] + gi[e] * gj[e];
-                    hn[q + e] = tanhf(cn[e]) * go[e];
+                    hn[e] = tanh_fast(cn[e]) * go[e];
                 }
-                *reinterpret_cast<float4*>(grow + q) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-                *reinterpret_cast<float4*>(grow + H + q) = make_float4(gj[0], gj[1], gj[2], gj[3]);
-                *reinterpret_cast<float4*>(grow + 2 * H + q) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-                *reinterpret_cast<float4*>(grow + 3 * H + q) = make_float4(go[0], go[1], go[2], go[3]);
-                float4 c4 = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                float4 h4 = make_float4(hn[q], hn[q + 1], hn[q + 2], hn[q + 3]);
-                *reinterpret_cast<float4*>(cells_t + su + q) = c4;
-                *reinterpret_cast<float4*>(cstate + su + q) = c4;
-                *reinterpret_cast<float4*>(Y_t + su + q) = h4;
-                *reinterpret_cast<float4*>(hstate + su + q) = h4;
+                float* grow = gates_t + (size_t)r * 4 * H + u0 + uq;
+                *reinterpret_cast<float4*>(grow) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                *reinterpret_cast<float4*>(grow + H) = make_float4(gj[0], gj[1], gj[2], gj[3]);
+                *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(go[0], go[1], go[2], go[3]);
+                const float4 c4 = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(cells_t + gu) = c4;
+                *reinterpret_cast<float4*>(cstate + gu) = c4;
+                *reinterpret_cast<float4*>(Y_t + gu) = h4;
+                *reinterpret_cast<float4*>(hstate + gu) = h4;
+            } else {
+                // t >= len: output row is zero, (c, h) are copied through (dynamic_rnn, A.5)
+                *reinterpret_cast<float4*>(cells_t + gu) =
+                    *reinterpret_cast<const float4*>(cs + (size_t)row * SROW + uq);
+                *reinterpret_cast<float4*>(Y_t + gu) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < UPT; q += 4) {
-                float4 cp = *reinterpret_cast<const float4*>(cstate + su + q);
-                float4 hp = *reinterpret_cast<const float4*>(hstate + su + q);
-                *reinterpret_cast<float4*>(cells_t + su + q) = cp;
-                *reinterpret_cast<float4*>(Y_t + su + q) = make_float4(0.f, 0.f, 0.f, 0.f);
-                hn[q] = hp.x; hn[q + 1] = hp.y; hn[q + 2] = hp.z; hn[q + 3] = hp.w;
-            }
+            // h_t (or the copied-through h_{t-1}) in packed operand format for step t+1
+            store_packed4(hpk_next, hpk_mgp, r, u0 + uq, hn);
         }
-        // h_t in packed operand format for step t+1 (k = hidden unit)
-        store_packed8(hpk_next, hpk_mgp, r, u0, hn);
-        store_packed8(hpk_next, hpk_mgp, r, u0 + 8, hn + 8);
     }
     tc_teardown<LBN>(tmem_d);
 }
 
-// Element-wise backward through the cell at step t for 8 hidden units of one row.
+__device__ __forceinline__ void ld4(const float* __restrict__ p, float* x) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+}
+__device__ __forceinline__ void st4(float* __restrict__ p, const float* x) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+
+// Element-wise backward through the cell at step t for 4 hidden units of one row.
 //   dh_in = dhc + sum_s partial_s  (partial sums of dZ_{t+1} * Wh^T) + dY_t
-__global__ void lstm_bwd_point_kernel(float* __restrict__ G /*[R,4H] in: gates, out: dZ*/,
-                                      const float* __restrict__ cells_t,
-                                      const float* __restrict__ cells_prev,
-                                      const float* __restrict__ c0, const float* __restrict__ dY_t,
-                                      const float* __restrict__ partials, int nsplit,
-                                      float* __restrict__ dhc, float* __restrict__ dcs,
-                                      const int* __restrict__ len, int t, int R, int H,
-                                      uint8_t* __restrict__ dzpk, int dz_mgp) {
+__global__ void __launch_bounds__(256)
+lstm_bwd_point_kernel(float* __restrict__ G /*[R,4H] in: gates, out: dZ*/,
+                      const float* __restrict__ cells_t, const float* __restrict__ cells_prev,
+                      const float* __restrict__ c0, const float* __restrict__ dY_t,
+                      const float* __restrict__ partials, int nsplit, float* __restrict__ dhc,
+                      float* __restrict__ dcs, const int* __restrict__ len, int t, int R, int H,
+                      uint8_t* __restrict__ dzpk, int dz_mgp) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ug = H / 8;
+    const int ug = H / 4;
     if (idx >= R * ug) return;
-    const int r = idx / ug, u0 = (idx % ug) * 8;
+    const int r = idx / ug, u0 = (idx % ug) * 4;
     const size_t su = (size_t)r * H + u0;
-    float dh[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dh[e] = dhc[su + e];
+    float dh[4], tmp[4];
+    ld4(dhc + su, dh);
     for (int s = 0; s < nsplit; ++s) {
-        const float* p = partials + (size_t)s * R * H + su;
+        ld4(partials + (size_t)s * R * H + su, tmp);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dh[e] += p[e];
+        for (int e = 0; e < 4; ++e) dh[e] += tmp[e];
     }
     float* g = G + (size_t)r * 4 * H + u0;
-    float di[8], dj[8], df[8], dq[8];
+    float di[4], dj[4], df[4], dq[4];
     if (t < len[r]) {
+        float gi[4], gj[4], gf[4], go[4], c[4], cp[4], dy[4], dc[4];
+        ld4(g, gi); ld4(g + H, gj); ld4(g + 2 * H, gf); ld4(g + 3 * H, go);
+        ld4(cells_t + su, c);
+        if (cells_prev) ld4(cells_prev + su, cp);
+        else if (c0) ld4(c0 + su, cp);
+        else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float i = g[e], j = g[H + e], f = g[2 * H + e], o = g[3 * H + e];
-            float c = cells_t[su + e];
-            float cprev = cells_prev ? cells_prev[su + e] : (c0 ? c0[su + e] : 0.f);
-            float dht = dh[e] + (dY_t ? dY_t[su + e] : 0.f);
-            float tcn = tanhf(c);
-            dq[e] = dht * tcn * o * (1.f - o);
-            float dc = dcs[su + e] + dht * o * (1.f - tcn * tcn);
-            di[e] = dc * j * i * (1.f - i);
-            dj[e] = dc * i * (1.f - j * j);
-            df[e] = dc * cprev * f * (1.f - f);
-            dcs[su + e] = dc * f;
-            dhc[su + e] = 0.f;
+            for (int e = 0; e < 4; ++e) cp[e] = 0.f;
         }
+        if (dY_t) ld4(dY_t + su, dy);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dy[e] = 0.f;
+        }
+        ld4(dcs + su, dc);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float dht = dh[e] + dy[e];
+            float tcn = tanh_fast(c[e]);
+            dq[e] = dht * tcn * go[e] * (1.f - go[e]);
+            float dct = dc[e] + dht * go[e] * (1.f - tcn * tcn);
+            di[e] = dct * gj[e] * gi[e] * (1.f - gi[e]);
+            dj[e] = dct * gi[e] * (1.f - gj[e] * gj[e]);
+            df[e] = dct * cp[e] * gf[e] * (1.f - gf[e]);
+            dc[e] = dct * gf[e];
+            tmp[e] = 0.f;
+        }
+        st4(dcs + su, dc);
+        st4(dhc + su, tmp);   // consumed: the recurrent GEMM's partial sums carry the new dh
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            di[e] = dj[e] = df[e] = dq[e] = 0.f;
-            dhc[su + e] = dh[e];   // state copied through: gradient passes unchanged
-        }
+        for (int e = 0; e < 4; ++e) di[e] = dj[e] = df[e] = dq[e] = 0.f;
+        st4(dhc + su, dh);    // state copied through: gradient passes unchanged
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { g[e] = di[e]; g[H + e] = dj[e]; g[2 * H + e] = df[e]; g[3 * H + e] = dq[e]; }
-    store_packed8(dzpk, dz_mgp, r, u0, di);
-    store_packed8(dzpk, dz_mgp, r, H + u0, dj);
-    store_packed8(dzpk, dz_mgp, r, 2 * H + u0, df);
-    store_packed8(dzpk, dz_mgp, r, 3 * H + u0, dq);
+    st4(g, di); st4(g + H, dj); st4(g + 2 * H, df); st4(g + 3 * H, dq);
+    store_packed4(dzpk, dz_mgp, r, u0, di);
+    store_packed4(dzpk, dz_mgp, r, H + u0, dj);
+    store_packed4(dzpk, dz_mgp, r, 2 * H + u0, df);
+    store_packed4(dzpk, dz_mgp, r, 3 * H + u0, dq);
 }
 
 // dst += sum_s partial_s
@@ -175,8 +237,13 @@ __global__ void copy_or_zero_k(float* __restrict__ dst, const float* __restrict_
 
 }  // namespace
 
+int lstm_tc_set_probe(long long* buf) {
+    D2P_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_tc_dbg, &buf, sizeof(buf)));
+    return 0;
+}
+
 bool lstm_tc_supported(int R, int H) {
-    return tc_available() && H % 32 == 0 && H >= 32 && R >= 1;
+    return tc_available() && H % 64 == 0 && H >= 64 && R >= 1;
 }
 
 int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H, const int* len,
@@ -205,7 +272,7 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     D2P_CHECK_LAUNCH();
     copy_or_zero_k<<<eb, 256, 0, st>>>(cT, c0, RH);
     D2P_CHECK_LAUNCH();
-    constexpr size_t smem = tc_smem_bytes<LBN, LSTAGES>();
+    constexpr size_t smem = L_SMEM_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_step_fwd_kernel,
@@ -217,7 +284,7 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     for (int t = 0; t < T; ++t) {
         Packed A{hpk[t & 1], mgp_h};
         Packed B{(const uint8_t*)whpk, mgp_of(G4)};
-        lstm_step_fwd_kernel<<<grid, 128, smem, st>>>(A, B, R, H, gates + (size_t)t * R * G4,
+        lstm_step_fwd_kernel<<<grid, LTHREADS, smem, st>>>(A, B, R, H, gates + (size_t)t * R * G4,
                                                       cells + t * RH, Y + t * RH, hT, cT, len, t,
                                                       forget_bias, hpk[(t + 1) & 1], mgp_h);
         D2P_CHECK_LAUNCH();
@@ -241,7 +308,7 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
     int ks = (int)(144 / (tiles64 < 1 ? 1 : tiles64));
     const int nkb = cdiv(G4, BK);
-    if (ks > nkb / 8) ks = nkb / 8;
+    if (ks > nkb / 4) ks = nkb / 4;
     if (ks > 8) ks = 8;
     if (ks < 1) ks = 1;
     const int nsplit = gemm_tc_nsplit(G4, ks);
@@ -259,11 +326,11 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     copy_or_zero_k<<<eb, 256, 0, st>>>(dc0, dcT, RH);
     D2P_CHECK_LAUNCH();
     const int mgp_z = mgp_of(R);
-    const int pb = cdiv((long long)R * (H / 8), 128);
+    const int pb = cdiv((long long)R * (H / 4), 256);
     bool have_partials = false;
     for (int t = T - 1; t >= 0; --t) {
         float* Gt = gates + (size_t)t * R * G4;
-        lstm_bwd_point_kernel<<<pb, 128, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
+        lstm_bwd_point_kernel<<<pb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
                                                   c0, dY ? dY + t * RH : nullptr, partials,
                                                   have_partials ? nsplit : 0, dh0, dc0, len, t, R, H,
                                                   dzpk, mgp_z);

@@ -1,13 +1,17 @@
 // Shared device code of the tcgen05 kernels: PTX wrappers, the packed operand
 // format and the warp-specialised bulk-copy -> tcgen05.mma main loop.
 //
-// Packed operand Op[mn, k] (bf16 hi/lo split, K-major UMMA core matrices):
-//     byte(mn, k, hl) = ((k/8 * MGp + mn/8) * 2 + hl) * 128 + (mn%8)*16 + (k%8)*2
-// MGp = mn-groups per k-group, padded to whole 128-row tiles; K padded to whole
-// 32-wide k-blocks (zero filled).  A ROWS x 8 slab is one contiguous ROWS*32 B
-// run that is already the no-swizzle canonical smem image (SBO = 256 B between
-// mn-groups, LBO = slab bytes between k-groups), so operands are fetched with
-// plain cp.async.bulk copies completing on an mbarrier.
+// Packed operand Op[mn, k] (bf16 hi/lo split, K-major UMMA core matrices of
+// 8 mn x 8 k = 128 B), ordered [k/64][mn/8][(k/8)%8][hi|lo]:
+//     byte(mn, k, hl) = ((((k/64)*MGp + mn/8)*8 + (k/8)%8)*2 + hl)*128 + (mn%8)*16 + (k%8)*2
+// MGp = mn-groups, padded to whole 128-row tiles; K padded to whole 64-wide
+// k-blocks (zero filled).  A ROWS x 64 operand tile is ONE contiguous ROWS*256 B
+// run in HBM that is already the no-swizzle canonical smem image (SBO = 2048 B
+// between mn-groups, LBO = 256 B between k-groups), so each pipeline stage is
+// fetched with two plain cp.async.bulk copies completing on an mbarrier.
+// (Measured on B200: a cp.async.bulk request costs ~250 SM cycles of issue
+// bandwidth whatever its size - 2 KB -> 8 B/clk, 24 KB -> 97 B/clk per SM - so
+// stages are made of few, large requests: 32 KB of A + 16/32 KB of B.)
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -15,7 +19,7 @@
 namespace d2p {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, KG_PER_BLOCK = BK / 8;
+constexpr int BM = 128, BK = 64, KG_PER_BLOCK = BK / 8;
 typedef __nv_bfloat16 bf16;
 
 struct Packed {
@@ -117,29 +121,55 @@ __device__ __forceinline__ void store_packed8(uint8_t* base, int mgp, int mn, in
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
-    uint8_t* p = base + (((size_t)(k0 >> 3) * mgp + (mn >> 3)) * 2) * 128 + (mn & 7) * 16;
+    uint8_t* p = base + (((((size_t)(k0 >> 6) * mgp + (mn >> 3)) * 8 + ((k0 >> 3) & 7)) * 2) * 128) +
+                 (mn & 7) * 16;
     *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// same for 4 consecutive k-elements (k0 multiple of 4): two 8-byte stores
+__device__ __forceinline__ void store_packed4(uint8_t* base, int mgp, int mn, int k0, const float* x) {
+    uint32_t h[2], l[2];
+    split2(x[0], x[1], h[0], l[0]);
+    split2(x[2], x[3], h[1], l[1]);
+    uint8_t* p = base + (((((size_t)(k0 >> 6) * mgp + (mn >> 3)) * 8 + ((k0 >> 3) & 7)) * 2) * 128) +
+                 (mn & 7) * 16 + (k0 & 7) * 2;
+    *reinterpret_cast<uint2*>(p) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(p + 128) = make_uint2(l[0], l[1]);
+}
+
+// optional timeline probe (developer tool): slots of SM-clock stamps for CTA (0,0,0)
+static __device__ long long* g_tc_dbg = nullptr;   // one copy per translation unit (no -rdc)
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    if (g_tc_dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        g_tc_dbg[slot] = clock64();
 }
 
 template <int BN, int STAGES>
 constexpr size_t tc_smem_bytes() {
-    return (size_t)STAGES * KG_PER_BLOCK * ((BM / 8) * 256 + (BN / 8) * 256);
+    return (size_t)STAGES * ((BM / 8) * 2048 + (BN / 8) * 2048);
 }
 
+struct NoPrefetch {
+    __device__ __forceinline__ void operator()(int, int) const {}
+};
+
 // Setup + producer + MMA issue for one 128 x BN accumulator tile over k-blocks
-// [kb0, kb0 + nk).  Returns the TMEM base address once the accumulator is
-// complete (all threads).  Call tc_teardown() after the epilogue.
-template <int BN, int STAGES>
+// [kb0, kb0 + nk).  Warp 0 / lane 0 produces, warp 1 / lane 0 issues the MMAs; the
+// other warps first run `prefetch(worker_index, n_workers)` (epilogue inputs ->
+// smem, overlapping the main loop).  Returns the TMEM base address once the
+// accumulator is complete (all threads).  Call tc_teardown() after the epilogue.
+template <int BN, int STAGES, class Prefetch = NoPrefetch>
 __device__ __forceinline__ uint32_t tc_mainloop(const Packed& A, const Packed& B, int m0, int n0,
-                                                int kb0, int nk, uint8_t* smem) {
-    constexpr uint32_t A_SLAB = (BM / 8) * 256, B_SLAB = (BN / 8) * 256;     // one k-group
-    constexpr uint32_t A_BYTES = KG_PER_BLOCK * A_SLAB, B_BYTES = KG_PER_BLOCK * B_SLAB;
+                                                int kb0, int nk, uint8_t* smem,
+                                                Prefetch prefetch = Prefetch()) {
+    constexpr uint32_t A_BYTES = (BM / 8) * 2048, B_BYTES = (BN / 8) * 2048;   // one k-block
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t LBO = 256, SBO = 2048;
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];   // full[S], empty[S], accum
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) dbg_stamp(0);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]),
                    accum = smem_u32(&bars[2 * STAGES]);
@@ -158,24 +188,27 @@ __device__ __forceinline__ uint32_t tc_mainloop(const Packed& A, const Packed& B
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) dbg_stamp(1);
 
     if (warp == 0 && lane == 0) {
         // ===== producer =====
-        const uint8_t* a_src = A.p + (size_t)(m0 / 8) * 256;
-        const uint8_t* b_src = B.p + (size_t)(n0 / 8) * 256;
-        const size_t a_kg = (size_t)A.mgp * 256, b_kg = (size_t)B.mgp * 256;
+        const uint8_t* a_src = A.p + (size_t)(m0 / 8) * 2048;
+        const uint8_t* b_src = B.p + (size_t)(n0 / 8) * 2048;
+        const size_t a_kb = (size_t)A.mgp * 2048, b_kb = (size_t)B.mgp * 2048;
+        const int rot = nk > 1 ? (int)((blockIdx.x * 3u + blockIdx.y * 7u) % (unsigned)nk) : 0;
         for (int i = 0; i < nk; ++i) {
             const int slot = i % STAGES;
             if (i >= STAGES) mbar_wait(empty0 + 8 * slot, ((i / STAGES) - 1) & 1);
             const uint32_t bar = full0 + 8 * slot;
             mbar_expect_tx(bar, STAGE_BYTES);
             const uint32_t sa = sbase + slot * STAGE_BYTES, sb = sa + A_BYTES;
-#pragma unroll
-            for (int g = 0; g < KG_PER_BLOCK; ++g) {
-                const size_t kg = (size_t)(kb0 + i) * KG_PER_BLOCK + g;
-                bulk_copy(sa + g * A_SLAB, a_src + kg * a_kg, A_SLAB, bar);
-                bulk_copy(sb + g * B_SLAB, b_src + kg * b_kg, B_SLAB, bar);
-            }
+            // CTAs that share an operand tile walk K in rotated order so that, at any
+            // instant, they hit different lines/L2 slices instead of hot-spotting one
+            int kr = i + rot;
+            if (kr >= nk) kr -= nk;
+            bulk_copy(sa, a_src + (size_t)(kb0 + kr) * a_kb, A_BYTES, bar);
+            bulk_copy(sb, b_src + (size_t)(kb0 + kr) * b_kb, B_BYTES, bar);
+            if (i < 20) dbg_stamp(8 + i);
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
@@ -185,14 +218,15 @@ __device__ __forceinline__ uint32_t tc_mainloop(const Packed& A, const Packed& B
         for (int i = 0; i < nk; ++i) {
             const int slot = i % STAGES;
             mbar_wait(full0 + 8 * slot, (i / STAGES) & 1);
+            if (i < 20) dbg_stamp(32 + i);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = sbase + slot * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
-                uint64_t ahi = make_desc(sa + kk * 2 * A_SLAB, A_SLAB, 256);
-                uint64_t alo = make_desc(sa + kk * 2 * A_SLAB + 128, A_SLAB, 256);
-                uint64_t bhi = make_desc(sb + kk * 2 * B_SLAB, B_SLAB, 256);
-                uint64_t blo = make_desc(sb + kk * 2 * B_SLAB + 128, B_SLAB, 256);
+                uint64_t ahi = make_desc(sa + kk * 2 * LBO, LBO, SBO);
+                uint64_t alo = make_desc(sa + kk * 2 * LBO + 128, LBO, SBO);
+                uint64_t bhi = make_desc(sb + kk * 2 * LBO, LBO, SBO);
+                uint64_t blo = make_desc(sb + kk * 2 * LBO + 128, LBO, SBO);
                 umma_bf16(tmem_d, ahi, bhi, idesc, (i > 0 || kk > 0) ? 1u : 0u);
                 umma_bf16(tmem_d, ahi, blo, idesc, 1u);
                 umma_bf16(tmem_d, alo, bhi, idesc, 1u);
@@ -200,17 +234,22 @@ __device__ __forceinline__ uint32_t tc_mainloop(const Packed& A, const Packed& B
             umma_commit(empty0 + 8 * slot);          // stage reusable once these MMAs retire
             if (i == nk - 1) umma_commit(accum);      // accumulator complete
         }
+    } else if (warp >= 2) {
+        prefetch((warp - 2) * 32 + lane, ((int)blockDim.x / 32 - 2) * 32);
     }
     __syncwarp();
     mbar_wait(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 64) dbg_stamp(2);
     return tmem_d;
 }
 
 template <int BN>
 __device__ __forceinline__ void tc_teardown(uint32_t tmem_d) {
+    if (threadIdx.x == 64) dbg_stamp(3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) dbg_stamp(4);
     if ((threadIdx.x >> 5) == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
                      "r"((uint32_t)BN));

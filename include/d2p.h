@@ -197,6 +197,9 @@ int d2p_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
 int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache, size_t cache_bytes,
                      int enabled);
 int d2p_tc_new_step(void);
+/* developer tool: record SM-clock stamps of CTA (0,0,0) of the tensor-core kernels
+ * into buf (>= 64 int64 on the device); NULL disables. */
+int d2p_debug_set_probe(long long* buf);
 
 #ifdef __cplusplus
 }
