@@ -65,6 +65,9 @@ SIGNATURES = {
                             _i, _fp]),
     'd2p_sigmoid_ce': (_i, [_fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                             _i, _fp]),
+    'd2p_greedy_ws_bytes': (_sz, [_i, _i, _i]),
+    'd2p_lstm_decoder_greedy': (_i, [_fp, _i, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp, _fp,
+                                     _fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_fc_bn_saved_floats': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_ws_bytes': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_fwd': (_i, [_fp, _ll, _i, _i, _i, _i, _i, _pf, _fp, _fp, _i, _fp,
@@ -89,6 +92,9 @@ SIGNATURES = {
     'd2p_gemm_tc_ws_bytes': (_sz, [_i, _i, _i]),
     'd2p_gemm_tc': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                          _fp, _sz, _fp]),
+    'd2p_packed_bytes': (_sz, [_i, _i]),
+    'd2p_pack_bf16': (_i, [_fp, _i, _i, _i, _i, _fp, _fp]),
+    'd2p_gemm_tc_packed': (_i, [_fp, _fp, _i, _i, _i, _f, _f, _fp, _i, _fp, _i, _fp, _fp]),
     'd2p_tc_configure': (_i, [_fp, _sz, _fp, _sz, _i]),
     'd2p_tc_new_step': (_i, []),
     'd2p_debug_set_probe': (_i, [_fp]),

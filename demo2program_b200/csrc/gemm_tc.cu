@@ -357,6 +357,22 @@ extern "C" int d2p_gemm_tc(int transA, int transB, int M, int N, int K, float al
                         beta, C, ldc, bias, ws, ws_bytes);
 }
 
+extern "C" size_t d2p_packed_bytes(int MN, int K) { return d2p::tc::packed_bytes(MN, K); }
+
+extern "C" int d2p_pack_bf16(const float* S, int MN, int K, int ld, int k_contig, void* out,
+                             void* stream) {
+    D2P_REQUIRE(S && out && MN > 0 && K > 0, "pack_bf16: bad arguments");
+    return d2p::pack_bf16((cudaStream_t)stream, S, MN, K, ld, k_contig != 0, out);
+}
+
+extern "C" int d2p_gemm_tc_packed(const void* Apk, const void* Bpk, int M, int N, int K, float alpha,
+                                  float beta, float* C, int ldc, const float* bias, int ksplit,
+                                  float* partials, void* stream) {
+    D2P_REQUIRE(Apk && Bpk && M > 0 && N > 0 && K > 0, "gemm_tc_packed: bad arguments");
+    return d2p::gemm_tc_packed((cudaStream_t)stream, Apk, Bpk, M, N, K, alpha, beta, C, ldc, bias,
+                               ksplit, partials);
+}
+
 // scratch: packed activations (reused by every GEMM on the stream);
 // cache: packed weights, valid until d2p_tc_new_step().
 extern "C" int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache, size_t cache_bytes,

@@ -1,0 +1,162 @@
+"""Dataset surface of the reference (karel_env/dataset_karel.py,
+vizdoom_env/dataset_vizdoom.py, */input_ops_*.py) for the CLI clones.
+
+`create_default_splits(path, num_k)` returns (train, test, val) objects with
+`.ids`, `.get_data(id)` (the 13-tuple of dataset_karel.py:38-115) and the
+`dsl_type/env_type/...` attributes the drivers read.  Two backends:
+  * `synthetic[:N]` as dataset_path -> seeded synthetic examples (no dataset is
+    available offline);
+  * a directory with data.hdf5 + id.txt -> h5py (imported lazily; not installed in
+    this image - the HDF5 reader is a "next" item).
+`batches(dataset, batch_size, shuffle)` replaces the TF queue pipeline
+(input_ops_karel.py:24-125) with a deterministic host iterator yielding the
+feed-dict dicts of models/model_full.py:185-206.
+"""
+import numpy as np
+
+from .config import karel_config
+from .synthetic import make_batch
+
+rs = np.random.RandomState(123)   # reference dataset_karel.py:11
+
+
+class SyntheticDataset(object):
+    def __init__(self, name, n, num_k, seed, dataset_type='karel'):
+        self.name, self.num_k = name, num_k
+        self._ids = ['%s_%06d' % (name, i) for i in range(n)]
+        self._seed = seed
+        self.dsl_type, self.env_type = 'prob', None
+        self._cfg = karel_config('full', batch_size=1, k=num_k)
+
+    @property
+    def ids(self):
+        return self._ids
+
+    def __len__(self):
+        return len(self._ids)
+
+    def _example(self, id):
+        idx = self._ids.index(id) if isinstance(id, str) else int(id)
+        return make_batch(self._cfg, seed=self._seed + idx, batch_size=1)
+
+    def get_data(self, id):
+        b = self._example(id)
+        sq = lambda k: b[k][0]
+        return (sq('program').astype(bool), sq('program_tokens'), sq('s_h'), sq('test_s_h'),
+                sq('a_h').astype(bool), sq('a_h_tokens'), sq('test_a_h').astype(bool),
+                sq('test_a_h_tokens'), sq('program_len'), sq('demo_len'), sq('test_demo_len'),
+                sq('per'), sq('test_per'))
+
+
+class H5Dataset(object):
+    """reference karel_env/dataset_karel.py:14-115 over h5py (lazy import)."""
+
+    def __init__(self, ids, dataset_path, name='default', num_k=10, is_train=True):
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError('reading %s/data.hdf5 needs h5py, which is not installed in this '
+                              'image; use --dataset_path synthetic' % dataset_path) from e
+        import os.path as osp
+        self._ids, self.name, self.num_k = list(ids), name, num_k
+        self.data = h5py.File(osp.join(dataset_path, 'data.hdf5'), 'r')
+        info = self.data['data_info']
+        g = lambda k: info[k][()]
+        self.dsl_type = g('dsl_type')
+        self.max_demo_len = int(g('max_demo_length'))
+        self.max_program_len = int(g('max_program_length'))
+        self.num_program_tokens = int(g('num_program_tokens'))
+        self.num_action_tokens = int(g('num_action_tokens'))
+        self.env_type = g('env_type') if 'env_type' in info else None
+
+    @property
+    def ids(self):
+        return self._ids
+
+    def __len__(self):
+        return len(self._ids)
+
+    def get_data(self, id):
+        d = self.data[id]
+        toks = d['program'][()]
+        L, T, A = self.max_program_len, self.max_demo_len, self.num_action_tokens
+        program = np.zeros([self.num_program_tokens, L], dtype=bool)
+        program[toks, np.arange(len(toks))] = 1
+        ptoks = np.zeros([L], dtype=toks.dtype)
+        ptoks[:len(toks)] = toks
+
+        def pad_demo(x):
+            out = np.zeros((x.shape[0], T) + x.shape[2:], dtype=x.dtype)
+            out[:, :x.shape[1]] = x
+            return out
+
+        def actions(a):   # quirk F10: one-hots from the per-program zero-padded matrix
+            hist = []
+            for t in a:
+                h = np.zeros([T, A + 1], dtype=bool)
+                h[np.arange(len(t)), t] = 1
+                h[len(t), A] = 1
+                hist.append(h)
+            hist = np.stack(hist, 0)
+            return hist, np.argmax(hist, axis=2)
+
+        demo, tdemo = pad_demo(d['s_h'][()]), pad_demo(d['test_s_h'][()])
+        ah, aht = actions(d['a_h'][()])
+        tah, taht = actions(d['test_a_h'][()])
+        pk, tpk = ('p_v_h', 'test_p_v_h') if 'p_v_h' in d else ('per', 'test_per')
+        per, tper = pad_demo(d[pk][()]), pad_demo(d[tpk][()])
+        k = self.num_k
+        return (program, ptoks, demo[:k], tdemo, ah[:k], aht[:k], tah, taht,
+                np.array([len(toks)], dtype=np.float32), d['s_h_len'][()][:k], d['test_s_h_len'][()],
+                per[:k], tper)
+
+
+def create_default_splits(dataset_path, num_k=10, is_train=True):
+    """reference karel_env/dataset_karel.py:131-160."""
+    if str(dataset_path).startswith('synthetic'):
+        n = int(dataset_path.split(':')[1]) if ':' in dataset_path else 512
+        return (SyntheticDataset('train', n, num_k, 1000), SyntheticDataset('test', max(n // 8, 32), num_k, 500000),
+                SyntheticDataset('val', max(n // 8, 32), num_k, 900000))
+    import os.path as osp
+    import h5py
+    with h5py.File(osp.join(dataset_path, 'data.hdf5'), 'r') as f:
+        nt, nte, nv = (int(f['data_info'][k][()]) for k in ('num_train', 'num_test', 'num_val'))
+    with open(osp.join(dataset_path, 'id.txt')) as fp:
+        ids = [s.strip() for s in fp.readlines() if s]
+    tr, te, va = ids[:nt], ids[nt:nt + nte], ids[nt + nte:nt + nte + nv]
+    rs.shuffle(tr); rs.shuffle(te); rs.shuffle(va)
+    mk = lambda i, n: H5Dataset(i, dataset_path, name=n, num_k=num_k, is_train=is_train)
+    return mk(tr, 'train'), mk(te, 'test'), mk(va, 'val')
+
+
+KEYS = ('program', 'program_tokens', 's_h', 'test_s_h', 'a_h', 'a_h_tokens', 'test_a_h',
+        'test_a_h_tokens', 'program_len', 'demo_len', 'test_demo_len', 'per', 'test_per')
+
+
+def collate(dataset, ids):
+    """load_fn + batch stacking (reference karel_env/input_ops_karel.py:52-116).  Frames stay
+    uint8 (the on-disk bool); everything else uses the reference's dtypes."""
+    cols = [dataset.get_data(i) for i in ids]
+    out = {'id': np.array([str(i).encode() for i in ids])}
+    for j, key in enumerate(KEYS):
+        arr = np.stack([c[j] for c in cols])
+        if key in ('s_h', 'test_s_h'):
+            arr = arr.astype(np.uint8)
+        elif key.endswith('_tokens'):
+            arr = arr.astype(np.int32)
+        else:
+            arr = arr.astype(np.float32)
+        out[key] = arr
+    return out
+
+
+def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None):
+    """Deterministic replacement of string_input_producer + shuffle_batch."""
+    r = np.random.RandomState(seed)
+    ids = list(dataset.ids)
+    e = 0
+    while epochs is None or e < epochs:
+        order = r.permutation(len(ids)) if shuffle else np.arange(len(ids))
+        for s in range(0, len(ids) - batch_size + 1, batch_size):
+            yield collate(dataset, [ids[i] for i in order[s:s + batch_size]])
+        e += 1

@@ -487,6 +487,54 @@ class Engine:
         self._call('d2p_logits_to_bvl', ptr(self.prog['logits']), L, B, V, ptr(out), self._st())
         return out
 
+    # ------------------------------------------------------------------ greedy decode
+    def _greedy(self, scope, vocab, end_id, max_len, rows, h0, c0, exact=True, nsl=1):
+        """GreedyEmbeddingHelper decode with the decoder under `scope` (reference
+        models/model_full.py:424-435).  exact=True runs every contraction on the
+        fp32 SIMT engine so that arg-max ties resolve as in fp32 arithmetic."""
+        H = self.H
+        logits = torch.zeros(max_len, rows, vocab, dtype=torch.float32, device=self.dev)
+        tokens = torch.zeros(max_len, rows, dtype=torch.int32, device=self.dev)
+        lengths = torch.zeros(rows, dtype=torch.int32, device=self.dev)
+        wsb = self.lib.d2p_greedy_ws_bytes(rows, H, H)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        if exact:
+            self.lib.d2p_tc_configure(None, 0, None, 0, 0)
+        else:
+            self._tc_bind()
+        d = scope + '/dynamic_decoder/'
+        try:
+            self._call('d2p_lstm_decoder_greedy',
+                       ptr(self.P(scope + '/Token_Embedding/embedding_map')), vocab + 1, H,
+                       ptr(self.P(d + 'basic_lstm_cell/kernel')), ptr(self.P(d + 'basic_lstm_cell/bias')),
+                       ptr(self.P(d + 'output_projection/kernel')), rows, H, vocab, vocab, end_id,
+                       max_len, nsl, ptr(h0), ptr(c0), ptr(logits), ptr(tokens), ptr(lengths), ptr(ws), wsb,
+                       self._st())
+        finally:
+            self._tc_bind()
+        return logits, tokens, lengths
+
+    def greedy_program(self, exact=True):
+        """After forward(): (greedy_pred_program [B,V,L], greedy_pred_program_len [B,1],
+        tokens [B,L]) - the reference's greedy program decoder outputs."""
+        cfg = self.cfg
+        L, V, B = cfg.max_program_len, cfg.dim_program_token, self.B
+        logits, tokens, lengths = self._greedy('Program_Decoder', V, cfg.program_end_token, L, B,
+                                               self.dsum_h, self.dsum_c, exact)
+        out = torch.empty(B, V, L, dtype=torch.float32, device=self.dev)
+        self._call('d2p_logits_to_bvl', ptr(logits), L, B, V, ptr(out), self._st())
+        return out, lengths.view(B, 1), tokens.t().contiguous()
+
+    def greedy_actions(self, exact=True):
+        """`full` only: greedy action decoders of all k demos, batched as R = B*k rows.
+        Returns (logits [B,k,T,A], lengths [B,k])."""
+        cfg = self.cfg
+        A, T = cfg.action_space, self.T
+        logits, tokens, lengths = self._greedy('Action_Decoder', A, A - 1, T, self.R,
+                                               self.fin['hT'], self.fin['cT'], exact, nsl=self.k)
+        return (logits.permute(1, 0, 2).reshape(self.B, self.k, T, A).contiguous(),
+                lengths.view(self.B, self.k))
+
     def global_norm(self):
         return float(self.adam_state[3].item())
 

@@ -121,6 +121,18 @@ int d2p_sigmoid_ce(float* logits, int T, int R, int P, const float* labels, cons
                    const int* runlen, const float* w, float* rowloss, float* dlogits, float* loss,
                    int accumulate, void* stream);
 
+/* ---- K4: greedy decode -------------------------------------------------------
+ * dynamic_decode(BasicDecoder(cell, GreedyEmbeddingHelper(embed, start, end), (c,h),
+ * Dense(V))) with maximum_iterations = max_len, reference models/model_full.py:424-435,
+ * 513-521.  logits [max_len, R, V] time-major, zero past the executed steps; tokens
+ * [max_len, R]; lengths [R] = first end-token step + 1, or max_len. */
+size_t d2p_greedy_ws_bytes(int R, int H, int E);
+int d2p_lstm_decoder_greedy(const float* table, int vocab_rows, int E, const float* W, const float* b,
+                            const float* proj, int R, int H, int V, int start_id, int end_id,
+                            int max_len, int nsl /* decoder instances: rows r share r % nsl */,
+                            const float* h0, const float* c0, float* logits, int* tokens,
+                            int* lengths, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- fc -> (lrelu) -> BN : ops.fc, reference models/ops.py:149-155 ------------
  * used by Per_Encoder (model_full.py:308-316; act = 0, per-demo slices) */
 typedef struct {
@@ -189,6 +201,17 @@ size_t d2p_gemm_tc_ws_bytes(int M, int N, int K);
 int d2p_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
                 size_t ws_bytes, void* stream);
+
+/* Packed-operand interface of the tensor-core engine: Op[mn,k] (MN x K) is split into
+ * bf16 hi/lo and stored as UMMA core matrices (d2p_packed_bytes bytes).  k_contig: the
+ * fp32 source is S[mn*ld + k] (1) or S[k*ld + mn] (0).  d2p_gemm_tc_packed computes
+ * C = alpha*A*B^T-form product of two packed operands (A: M x K, B: N x K); with
+ * ksplit > 1 (or C == NULL) raw partial sums go to partials[ksplit][M][N]. */
+size_t d2p_packed_bytes(int MN, int K);
+int d2p_pack_bf16(const float* S, int MN, int K, int ld, int k_contig, void* out, void* stream);
+int d2p_gemm_tc_packed(const void* Apk, const void* Bpk, int M, int N, int K, float alpha, float beta,
+                       float* C, int ldc, const float* bias, int ksplit, float* partials,
+                       void* stream);
 
 /* Arena for the tensor-core engine: `scratch` holds packed activations (reused by
  * every GEMM on the stream), `cache` holds packed weights until d2p_tc_new_step()

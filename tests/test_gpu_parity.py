@@ -121,3 +121,67 @@ def test_ops_reject_bad_arguments_on_gpu(lib):
     x = torch.zeros(8, device='cuda')
     assert lib.d2p_seq_weights(x.data_ptr(), 7, 3, 1.0, 5, x.data_ptr(), None, None) == -1
     assert b'seq_weights' in lib.d2p_last_error()
+
+
+def test_greedy_decode_tokens_match_oracle():
+    """K4: greedy program / action decode - token ids and lengths bit-exact against the
+    oracle (north_star: 'token-id sequences bit-exact under greedy decode'); logits to 1e-4."""
+    cfg = karel_config('full', batch_size=4, k=3)
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False, use_tc=False)
+    out = orc.model.forward(batch, greedy=True)
+    eng.stage_batch(batch)
+    eng.forward()
+    gp, glen, gtok = eng.greedy_program(exact=True)
+    torch.cuda.synchronize()
+    o_len = out['greedy_pred_program_len'].numpy()[:, 0]
+    assert np.array_equal(glen.cpu().numpy()[:, 0], o_len)
+    n = int(o_len.max())
+    assert np.array_equal(gtok.cpu().numpy()[:, :n], out['greedy_program_tokens'].numpy()[:, :n])
+    assert rel_err(gp.cpu().numpy(), out['greedy_pred_program'].detach().numpy()) < 1e-4
+    assert np.all(gp.cpu().numpy()[:, :, n:] == 0)          # zero pad past the executed steps
+    ga, galen = eng.greedy_actions(exact=True)
+    assert np.array_equal(galen.cpu().numpy(), out['greedy_pred_action_len'].numpy())
+    assert rel_err(ga.cpu().numpy(), out['greedy_pred_action'].detach().numpy()) < 1e-4
+
+
+def test_greedy_decode_with_tensor_cores_agrees():
+    cfg = karel_config('synthesis_baseline', batch_size=8, k=2)
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False, use_tc=True)
+    out = orc.model.forward(batch, greedy=True)
+    eng.stage_batch(batch)
+    eng.forward()
+    gp, glen, gtok = eng.greedy_program(exact=False)
+    torch.cuda.synchronize()
+    assert rel_err(gp.cpu().numpy(), out['greedy_pred_program'].detach().numpy()) < 1e-3
+    assert np.array_equal(glen.cpu().numpy()[:, 0], out['greedy_pred_program_len'].numpy()[:, 0])
+
+
+def test_eval_mode_uses_moving_statistics():
+    """Evaler builds the model with is_train=False (reference evaler.py:61): BN uses the
+    moving averages and does not update them."""
+    from oracle.models import OracleModel
+    cfg = karel_config('summarizer', batch_size=3, k=2)
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False, is_train=False)
+    s0 = eng.state.clone()
+    om = OracleModel(cfg, orc.model.flat.detach().numpy(), orc.model.state.numpy(), is_train=False)
+    out = om.forward(batch)
+    eng.stage_batch(batch)
+    eng.forward()
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss[0]) - float(out['loss'])) < LOSS_TOL
+    assert torch.equal(eng.state, s0)
+
+
+def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
+    """trainer.py / evaler.py with the reference's flags on synthetic data."""
+    import trainer, evaler, glob, os
+    monkeypatch.chdir(tmp_path)
+    trainer.main(['--model', 'synthesis_baseline', '--dataset_path', 'synthetic:64', '--num_k', '2',
+                  '--batch_size', '8', '--max_steps', '3', '--log_step', '1', '--test_sample_step', '2'])
+    ck = glob.glob(str(tmp_path / 'train_dir' / '*' / 'model-*.npz'))
+    assert ck, 'trainer wrote no checkpoint'
+    evaler.main(['--model', 'synthesis_baseline', '--dataset_path', 'synthetic:64', '--num_k', '2',
+                 '--batch_size', '8', '--max_steps', '2', '--checkpoint', ck[0], '--quiet',
+                 '--summary_file', str(tmp_path / 'report.txt')])
+    rep = open(tmp_path / 'report.txt').read()
+    assert 'program_loss' in rep and 'greedy_program_token_acc' in rep

@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Training driver with the reference's CLI (reference trainer.py:243-344).
+
+Same flags (--model/--dataset_type/--dataset_path/--checkpoint/--log_step/...),
+same dataset-derived config fields (trainer.py:312-335), same log line
+(trainer.py:227-240), same train_dir naming (trainer.py:37-53); the TF graph +
+session is replaced by `demo2program_b200.model.Model` (libd2p on one B200, or one
+process per GPU under torchrun with a single NCCL all-reduce of the gradients).
+Deviations (documented in DESIGN.md): `--dataset_path synthetic[:N]` selects seeded
+synthetic data; checkpoints are .npz files keyed by TF variable name; TensorBoard
+summaries and the host-interpreter metrics are not produced.
+"""
+import argparse
+import logging
+import os
+import time
+
+import numpy as np
+
+log = logging.getLogger('d2p')
+
+
+class Trainer(object):
+    @staticmethod
+    def get_model_class(model_name):
+        from demo2program_b200.model import get_model_class
+        return get_model_class(model_name)
+
+    def __init__(self, config, dataset, dataset_test):
+        self.config = config
+        hyper_parameter_str = 'bs_{}_lr_{}_{}_cell_{}'.format(
+            config.batch_size, config.learning_rate, config.encoder_rnn_type,
+            config.num_lstm_cell_units)
+        if config.scheduled_sampling:
+            hyper_parameter_str += '_sd_{}'.format(config.scheduled_sampling_decay_steps)
+        hyper_parameter_str += '_k_{}'.format(config.num_k)
+        self.train_dir = './train_dir/%s-%s-%s-%s-%s-%s' % (
+            config.dataset_type, '_'.join(config.dataset_path.split('/')), config.model,
+            config.prefix, hyper_parameter_str, time.strftime("%Y%m%d-%H%M%S"))
+        os.makedirs(self.train_dir, exist_ok=True)
+        log.info("Train Dir: %s", self.train_dir)
+        from demo2program_b200.dataset import batches
+        self.batch_size = config.batch_size
+        self.batch_train = batches(dataset, self.batch_size, shuffle=True, seed=config.rank)
+        self.batch_test = batches(dataset_test, self.batch_size, shuffle=False)
+        Model = self.get_model_class(config.model)
+        log.info("Using Model class: %s", Model)
+        self.model = Model(config, debug_information=config.debug, world_size=config.world_size,
+                           device='cuda:%d' % config.local_rank)
+        self.log_step = config.log_step
+        self.test_sample_step = config.test_sample_step
+        if config.checkpoint is not None:
+            log.info("Checkpoint path: %s", config.checkpoint)
+            self.model.load_state_dict(dict(np.load(config.checkpoint)), trainable_only=True)
+            log.info("Loaded the pretrain parameters from the provided checkpoint path")
+
+    def train(self, max_steps=1000000):
+        log.info("Training Starts!")
+        ckpt_save_step = 1000
+        for s in range(max_steps):
+            step, loss, step_time = self.run_single_step(self.batch_train, step=s, is_train=True)
+            if s % self.log_step == 0:
+                self.log_step_message(step, loss, step_time)
+            if s % self.test_sample_step == 0:
+                step, test_loss, test_time = self.run_test(self.batch_test)
+                self.log_step_message(step, test_loss, test_time, is_train=False)
+            if s % ckpt_save_step == 0 and self.config.rank == 0:
+                log.info("Saved checkpoint at %d", s)
+                np.savez(os.path.join(self.train_dir, 'model-%d.npz' % step), **self.model.state_dict())
+
+    def run_single_step(self, batch, step=None, is_train=True):
+        _start_time = time.time()
+        batch_chunk = next(batch)
+        feed = self.model.get_feed_dict(batch_chunk, step=step, is_training=is_train)
+        loss = self.model.run_train_step(feed)
+        return self.model.engine.step_count(), loss, time.time() - _start_time
+
+    def run_test(self, batch):
+        # like the reference (trainer.py:79-80) the trainer's model keeps batch statistics here
+        _start_time = time.time()
+        feed = self.model.get_feed_dict(next(batch), is_training=False)
+        loss = self.model.run_eval_step(feed, greedy=False)
+        return self.model.engine.step_count(), loss, time.time() - _start_time
+
+    def log_step_message(self, step, loss, step_time, is_train=True):
+        if step_time == 0:
+            step_time = 0.001
+        log.info((" [{split_mode:5s} step {step:4d}] " + "Loss: {loss:.5f} " +
+                  "({sec_per_batch:.3f} sec/batch, {instance_per_sec:.3f} " + "instances/sec) "
+                  ).format(split_mode=(is_train and 'train' or 'val'), step=step, loss=loss,
+                           sec_per_batch=step_time, instance_per_sec=self.batch_size / step_time))
+
+
+def add_model_flags(parser):
+    parser.add_argument('--encoder_rnn_type', default='lstm', choices=['lstm', 'rnn', 'gru'])
+    parser.add_argument('--num_lstm_cell_units', type=int, default=512)
+    parser.add_argument('--demo_aggregation', type=str, default='avgpool',
+                        choices=['concat', 'avgpool', 'maxpool'],
+                        help='how to aggregate the demo features')
+    # fields the reference's induction model reads but its CLI never defines
+    # (models/baselines/model_induction.py:194-212) - added with defaults
+    parser.add_argument('--pixel_input', action='store_true', default=False)
+    parser.add_argument('--attn_type', type=str, default='luong')
+    parser.add_argument('--state_encoder_fc', action='store_true', default=False)
+    parser.add_argument('--concat_state_feature_direct_prediction', action='store_true', default=False)
+    parser.add_argument('--stack_subsequent_state', action='store_true', default=False)
+
+
+def set_data_dims(config, dataset_train):
+    """reference trainer.py:305-335."""
+    data_tuple = dataset_train.get_data(dataset_train.ids[0])
+    program, _, s_h, test_s_h, a_h, _, _, _, program_len, demo_len, test_demo_len, per, test_per = \
+        data_tuple[:13]
+    config.dim_program_token = int(np.asarray(program.shape)[0])
+    config.max_program_len = int(np.asarray(program.shape)[1])
+    config.k = int(np.asarray(s_h.shape)[0])
+    config.test_k = int(np.asarray(test_s_h.shape)[0])
+    config.max_demo_len = int(np.asarray(s_h.shape)[1])
+    config.h, config.w, config.depth = (int(x) for x in s_h.shape[2:5])
+    config.action_space = int(np.asarray(a_h.shape)[2])
+    config.per_dim = int(np.asarray(per.shape)[2])
+    if config.dataset_type == 'karel':
+        config.dsl_type = dataset_train.dsl_type
+        config.env_type = dataset_train.env_type
+        config.vizdoom_pos_keys = []
+        config.vizdoom_max_init_pos_len = -1
+        config.perception_type = ''
+        config.level = None
+    elif config.dataset_type == 'vizdoom':
+        config.dsl_type = 'vizdoom_default'
+        config.env_type = 'vizdoom_default'
+        config.vizdoom_pos_keys = getattr(dataset_train, 'vizdoom_pos_keys', [])
+        config.vizdoom_max_init_pos_len = getattr(dataset_train, 'vizdoom_max_init_pos_len', -1)
+        config.perception_type = getattr(dataset_train, 'perception_type', '')
+        config.level = getattr(dataset_train, 'level', None)
+    else:
+        raise ValueError(config.dataset_type)
+
+
+def main(argv=None):
+    logging.basicConfig(level=logging.INFO, format='%(asctime)s %(message)s')
+    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('--debug', action='store_true', default=False)
+    parser.add_argument('--prefix', type=str, default='default', help='a nickanme for the training')
+    parser.add_argument('--model', type=str, default='full',
+                        choices=['synthesis_baseline', 'induction_baseline', 'summarizer', 'full'])
+    parser.add_argument('--dataset_type', type=str, default='karel', choices=['karel', 'vizdoom'])
+    parser.add_argument('--dataset_path', type=str, default='datasets/karel_dataset')
+    parser.add_argument('--checkpoint', type=str, default=None)
+    parser.add_argument('--log_step', type=int, default=10)
+    parser.add_argument('--write_summary_step', type=int, default=100)
+    parser.add_argument('--test_sample_step', type=int, default=100)
+    parser.add_argument('--num_k', type=int, default=10, help='the number of seen demonstrations')
+    parser.add_argument('--batch_size', type=int, default=32)
+    parser.add_argument('--learning_rate', type=float, default=0.001)
+    parser.add_argument('--lr_weight_decay', action='store_true', default=False)
+    parser.add_argument('--scheduled_sampling', action='store_true', default=False)
+    parser.add_argument('--scheduled_sampling_decay_steps', type=int, default=20000)
+    parser.add_argument('--max_steps', type=int, default=1000000,
+                        help='(addition) stop after this many steps')
+    add_model_flags(parser)
+    config = parser.parse_args(argv)
+    if config.scheduled_sampling:
+        raise ValueError('scheduled sampling is unseeded/non-deterministic in the reference and is '
+                         'out of scope of the B200 path')
+    # one process per GPU (torchrun); single process otherwise
+    config.rank = int(os.environ.get('RANK', '0'))
+    config.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    config.world_size = int(os.environ.get('WORLD_SIZE', '1'))
+    if config.world_size > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(config.local_rank)
+        dist.init_process_group('nccl')
+    from demo2program_b200 import dataset
+    if config.dataset_type not in ('karel', 'vizdoom'):
+        raise ValueError(config.dataset_type)
+    dataset_train, dataset_test, dataset_val = dataset.create_default_splits(
+        config.dataset_path, num_k=config.num_k)
+    set_data_dims(config, dataset_train)
+    trainer = Trainer(config, dataset_train, dataset_test)
+    log.warning("dataset: %s, learning_rate: %f", config.dataset_path, config.learning_rate)
+    trainer.train(config.max_steps)
+
+
+if __name__ == '__main__':
+    main()
