@@ -68,6 +68,11 @@ SIGNATURES = {
     'd2p_greedy_ws_bytes': (_sz, [_i, _i, _i]),
     'd2p_lstm_decoder_greedy': (_i, [_fp, _i, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp, _fp,
                                      _fp, _fp, _fp, _fp, _sz, _fp]),
+    'd2p_luong_pool_attention': (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp]),
+    'd2p_induction_decode_ws_bytes': (_sz, [_i, _i, _i]),
+    'd2p_induction_decode': (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp,
+                                  _fp, _fp, _i, _fp, _fp, _fp, _fp, _sz, _fp]),
+    'd2p_concat_cols': (_i, [_fp, _i, _fp, _i, _ll, _fp, _fp]),
     'd2p_fc_bn_saved_floats': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_ws_bytes': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_fwd': (_i, [_fp, _ll, _i, _i, _i, _i, _i, _pf, _fp, _fp, _i, _fp,

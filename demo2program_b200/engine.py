@@ -440,34 +440,60 @@ class Engine:
         if with_opt:
             self.optimizer_step()
 
+    def _capture(self, fn):
+        """Warm up `fn` on a side stream (lazy module loading), then capture it."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        n0 = self.lib.d2p_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g, self.lib.d2p_launch_count() - n0
+
+    def _adam_only(self, scale):
+        decay = 10000 if self.cfg.lr_weight_decay else 0
+        self._call('d2p_clip_adam_step', ptr(self.params), ptr(self.grads), ptr(self.adam_m),
+                   ptr(self.adam_v), self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip,
+                   scale, decay, ptr(self.adam_state), ptr(self.ws), self.ws_bytes, self._st())
+
     def train_step_device(self, with_opt=True):
         """One train step over the batch already resident in HBM.  The launch
-        sequence is captured into a CUDA graph on first use and replayed."""
-        if not self.use_graph or self.world > 1:
+        sequence is captured into CUDA graphs on first use and replayed: one graph
+        for the whole step on a single GPU; with data parallelism a forward+backward
+        graph, the single NCCL all-reduce of the flat gradients, and a clip+Adam graph."""
+        if not self.use_graph:
             self._step_body(with_opt)
             return
         key = bool(with_opt)
         if self._graph is None or self._graph_key != key:
-            # warm-up outside capture (lazy module loading), then capture
             snap = [t.clone() for t in (self.params, self.state, self.adam_m, self.adam_v,
                                         self.adam_state)]
-            s = torch.cuda.Stream(self.dev)
-            s.wait_stream(torch.cuda.current_stream(self.dev))
-            with torch.cuda.stream(s):
-                self._step_body(with_opt)
-            torch.cuda.current_stream(self.dev).wait_stream(s)
-            torch.cuda.synchronize(self.dev)
-            n0 = self.lib.d2p_launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_body(with_opt)
-            self.launches_per_step = self.lib.d2p_launch_count() - n0
+            if self.world > 1:
+                def fb():
+                    self.forward()
+                    self.backward()
+                g1, n1 = self._capture(fb)
+                g2, n2 = self._capture(lambda: self._adam_only(1.0 / self.world))
+                self._graph, self.launches_per_step = (g1, g2), n1 + n2
+            else:
+                g, n = self._capture(lambda: self._step_body(with_opt))
+                self._graph, self.launches_per_step = g, n
             for t, sv in zip((self.params, self.state, self.adam_m, self.adam_v, self.adam_state),
                              snap):
                 t.copy_(sv)
             torch.cuda.synchronize(self.dev)
-            self._graph, self._graph_key = g, key
-        self._graph.replay()
+            self._graph_key = key
+        if self.world > 1:
+            self._graph[0].replay()
+            if with_opt:
+                allreduce_flat_gradients(self.grads, self.world)
+                self._graph[1].replay()
+        else:
+            self._graph.replay()
 
     def train_step(self, batch):
         """Public API: host batch in, loss out (H2D + step + D2H of the loss)."""

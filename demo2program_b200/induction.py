@@ -1,0 +1,237 @@
+"""Induction baseline (reference models/baselines/model_induction.py): encoder
+(CNN features ++ perception vector -> LSTM), avg aggregate, k-way pooled Luong
+attention decoder predicting the action sequences of the `test_k` unseen demos.
+
+Inference path only (BASELINE.json configs[4]: greedy decode, batch 512): the
+teacher-forced forward pass with its loss, and the greedy decoder.  Training this
+baseline (attention backward) is not part of the benchmarked path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, ptr
+from .manifest import build_manifests
+
+
+class InductionEngine:
+    def __init__(self, cfg, device='cuda:0', seed=0, is_train=False, frames_dtype=np.uint8,
+                 flat_params=None, flat_state=None, use_tc=True, **_):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU fallback)')
+        if cfg.model != 'induction_baseline':
+            raise ValueError(cfg.model)
+        for flag in ('pixel_input', 'state_encoder_fc', 'concat_state_feature_direct_prediction',
+                     'stack_subsequent_state'):
+            if getattr(cfg, flag):
+                raise NotImplementedError('induction_baseline with %s=True' % flag)
+        if cfg.attn_type != 'luong':
+            raise ValueError('Unknown attention type')
+        cfg.validate()
+        self.cfg, self.dev = cfg, torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.is_train = bool(is_train)
+        self.frames_u8 = np.dtype(frames_dtype) == np.uint8
+        self.pm, self.sm = build_manifests(cfg)
+        p0 = self.pm.init_flat(seed) if flat_params is None else np.asarray(flat_params, np.float32)
+        s0 = self.sm.init_flat(seed) if flat_state is None else np.asarray(flat_state, np.float32)
+        self.params = torch.from_numpy(p0.copy()).to(self.dev)
+        self.state = torch.from_numpy(s0.copy()).to(self.dev)
+        self.use_tc = bool(use_tc)
+        self._alloc()
+
+    def P(self, name):
+        e = self.pm[name]
+        return self.params[e.offset:e.offset + e.size]
+
+    def S(self, name):
+        e = self.sm[name]
+        return self.state[e.offset:e.offset + e.size]
+
+    def _alloc(self):
+        cfg, lib, dev = self.cfg, self.lib, self.dev
+        B, k, tk, T, H = cfg.batch_size, cfg.k, cfg.test_k, cfg.max_demo_len, cfg.num_lstm_cell_units
+        A, Pd = cfg.action_space, cfg.per_dim
+        R, R2 = B * k, B * tk
+        self.B, self.k, self.tk, self.T, self.H, self.R, self.R2 = B, k, tk, T, H, R, R2
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        fdt = torch.uint8 if self.frames_u8 else torch.float32
+        self.d_frames = torch.zeros(B, k, T, cfg.h, cfg.w, cfg.depth, dtype=fdt, device=dev)
+        self.d_per = z(R, T, Pd)
+        self.d_demo_len_f, self.d_tlen_f = z(R), z(R2)
+        self.d_demo_len, self.d_tlen = zi(R), zi(R2)
+        self.d_ttok = zi(R2, T)
+        d = ConvDesc()
+        d.B, d.k, d.T, d.h, d.w, d.d = B, k, T, cfg.h, cfg.w, cfg.depth
+        d.frames_dtype = _lib.D2P_U8 if self.frames_u8 else _lib.D2P_F32
+        chans = cfg.conv_channels()
+        d.n_layers = len(chans)
+        for li, (_, cout) in enumerate(chans):
+            sc = 'Demo_Encoder/State_Encoder/conv%d' % (li + 1)
+            l, bn = d.layers[li], sc + '/bn_act/BatchNorm/'
+            l.w, l.b = ptr(self.P(sc + '/Conv/weights')), ptr(self.P(sc + '/Conv/biases'))
+            l.gamma, l.beta = ptr(self.P(bn + 'gamma')), ptr(self.P(bn + 'beta'))
+            l.moving_mean, l.moving_var = ptr(self.S(bn + 'moving_mean')), ptr(self.S(bn + 'moving_variance'))
+            l.cout = cout
+        self.conv_desc = d
+        F = lib.d2p_conv_encoder_feature_dim(C.byref(d))
+        self.F = F
+        self.conv_saved = z(lib.d2p_conv_encoder_saved_floats(C.byref(d)))
+        ws = max(lib.d2p_conv_encoder_ws_bytes(C.byref(d)), lib.d2p_induction_decode_ws_bytes(B, tk, H))
+        self.ws_bytes = (ws + 255) // 256 * 256
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.feat, self.per_tm, self.X = z(T, R, F), z(T, R, Pd), z(T, R, F + Pd)
+        self.Y, self.keys = z(T, R, H), z(T, R, H)
+        self.hT, self.cT = z(R, H), z(R, H)
+        self.gates, self.cells = z(T, R, 4 * H), z(T, R, H)
+        self.h_sum, self.c_sum = z(B, H), z(B, H)
+        self.logits = z(T, R2, A)
+        self.rowloss, self.w, self.runlen = z(T * R2), z(R2), zi(R2)
+        self.loss = z(1)
+        if self.use_tc:
+            big = lib.d2p_gemm_tc_ws_bytes(T * R, 4 * H, max(H, F + Pd)) + (8 << 20)
+            self.tc_scratch = torch.zeros(big, dtype=torch.uint8, device=dev)
+            self.tc_cache = torch.zeros(12 * self.pm.total + (16 << 20), dtype=torch.uint8, device=dev)
+
+    def _tc_bind(self, enabled=True):
+        if self.use_tc and enabled:
+            self.lib.d2p_tc_configure(ptr(self.tc_scratch), self.tc_scratch.numel(),
+                                      ptr(self.tc_cache), self.tc_cache.numel(), 1)
+        else:
+            self.lib.d2p_tc_configure(None, 0, None, 0, 0)
+
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _call(self, name, *args):
+        check(getattr(self.lib, name)(*args), name)
+
+    def stage_batch(self, batch):
+        """numpy feed (keys of model_induction.py:358-381) -> device."""
+        dev = self.dev
+        fr = np.asarray(batch['s_h']).astype(np.uint8 if self.frames_u8 else np.float32, copy=False)
+        self.d_frames.copy_(torch.from_numpy(np.ascontiguousarray(fr)))
+        self.d_per.copy_(torch.from_numpy(np.asarray(batch['per'], np.float32).reshape(self.R, self.T, -1)))
+        self.d_demo_len_f.copy_(torch.from_numpy(np.asarray(batch['demo_len'], np.float32).reshape(-1)))
+        self.d_tlen_f.copy_(torch.from_numpy(np.asarray(batch['test_demo_len'], np.float32).reshape(-1)))
+        self.d_ttok.copy_(torch.from_numpy(
+            np.asarray(batch['test_a_h_tokens'], np.int32).reshape(self.R2, self.T)))
+
+    def encode(self, exact=False):
+        """Demo_Encoder for all k demos + avg aggregate + attention keys."""
+        cfg, st, call = self.cfg, self._st(), self._call
+        B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
+        Pd = cfg.per_dim
+        self._tc_bind(not exact)
+        tr = int(self.is_train)
+        call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, st)
+        call('d2p_len_to_int', ptr(self.d_tlen_f), ptr(self.d_tlen), self.R2, st)
+        call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, st)
+        call('d2p_rtp_to_trp', ptr(self.d_per), R, T, Pd, ptr(self.per_tm), st)
+        call('d2p_concat_cols', ptr(self.feat), F, ptr(self.per_tm), Pd, T * R, ptr(self.X), st)
+        sc = 'Demo_Encoder/rnn/basic_lstm_cell/'
+        call('d2p_lstm_seq_fwd', ptr(self.X), T, R, F + Pd, H, ptr(self.d_demo_len), None, None,
+             ptr(self.P(sc + 'kernel')), ptr(self.P(sc + 'bias')), 1.0, ptr(self.Y), ptr(self.hT),
+             ptr(self.cT), ptr(self.gates), ptr(self.cells), st)
+        call('d2p_group_sum', ptr(self.hT), B, k, H, 1.0 / k, ptr(self.h_sum), 0, st)
+        call('d2p_group_sum', ptr(self.cT), B, k, H, 1.0 / k, ptr(self.c_sum), 0, st)
+        # keys = values * W_mem (LuongAttention memory_layer); values = Y (zero past len)
+        call('d2p_gemm', 0, 0, T * R, H, H, 1.0, ptr(self.Y), H,
+             ptr(self.P('AttnMechanism/memory_layer/kernel')), H, 0.0, ptr(self.keys), H, None, st)
+
+    def _decode(self, tokens, out_tokens, lengths, exact):
+        cfg, st = self.cfg, self._st()
+        w = 'Manipulation/dynamic_decoder/pooling_attention_wrapper/'
+        self._tc_bind(not exact)
+        self._call('d2p_induction_decode', ptr(self.keys), ptr(self.Y), ptr(self.d_demo_len), self.B,
+                   self.k, self.tk, self.T, self.H, ptr(self.h_sum), ptr(self.c_sum),
+                   ptr(self.P('Manipulation/Token_Embedding/embedding_map')), cfg.action_space,
+                   ptr(self.P(w + 'basic_lstm_cell/kernel')), ptr(self.P(w + 'basic_lstm_cell/bias')),
+                   ptr(self.P(w + 'attention_layer/kernel')),
+                   ptr(self.P('Manipulation/dynamic_decoder/output_projection/kernel')),
+                   ptr(tokens), self.T, ptr(self.logits), ptr(out_tokens), ptr(lengths), ptr(self.ws),
+                   self.ws_bytes, st)
+
+    def forward_teacher(self, exact=False):
+        """Teacher-forced decoders + loss = mean over test_k of the masked CE
+        (model_induction.py:788-819).  Returns pred_action [B, test_k, T, A]."""
+        A, T, R2, tk, st = self.cfg.action_space, self.T, self.R2, self.tk, self._st()
+        self._decode(self.d_ttok, None, None, exact)
+        self._call('d2p_seq_weights', ptr(self.d_tlen), R2, tk, 1.0 / tk, T, ptr(self.w), ptr(self.runlen), st)
+        self._call('d2p_softmax_ce', ptr(self.logits), T, R2, A, ptr(self.d_ttok), ptr(self.d_tlen),
+                   ptr(self.runlen), ptr(self.w), ptr(self.rowloss), None, ptr(self.loss), 0, st)
+        return self.logits.permute(1, 0, 2).reshape(self.B, tk, T, A).contiguous()
+
+    def greedy(self, exact=True):
+        """Greedy action decode of every unseen demo: (logits [B,test_k,T,A], lengths [B,test_k])."""
+        A, T, R2, tk = self.cfg.action_space, self.T, self.R2, self.tk
+        toks = torch.zeros(T, R2, dtype=torch.int32, device=self.dev)
+        lens = torch.zeros(R2, dtype=torch.int32, device=self.dev)
+        self._decode(None, toks, lens, exact)
+        return (self.logits.permute(1, 0, 2).reshape(self.B, tk, T, A).contiguous(),
+                lens.view(self.B, tk))
+
+
+class InductionModel(object):
+    """Reference-facing facade for `--model induction_baseline` (evaluation only)."""
+
+    def __init__(self, config, debug_information=False, is_train=True, global_step=None, **kw):
+        from .config import D2PConfig
+        from .model import config_from_namespace
+        self.config = config if isinstance(config, D2PConfig) else config_from_namespace(config)
+        self.engine = InductionEngine(self.config, is_train=is_train, **kw)
+        self.batch_size = self.config.batch_size
+        self.loss, self.output = None, []
+        self.report_loss, self.report_accuracy, self.report_hist = {}, {}, {}
+        # program-related evaler fetches are empty lists in the reference (model_induction.py:850-875)
+        self.pred_program = self.greedy_pred_program = []
+        self.program_len = self.greedy_pred_program_len = []
+        self.ground_truth_program = []
+
+    def get_feed_dict(self, batch_chunk, step=None, is_training=True):
+        for key in ('s_h', 'per', 'demo_len', 'test_a_h', 'test_a_h_tokens', 'test_demo_len'):
+            if key not in batch_chunk:
+                raise KeyError('batch_chunk is missing %s' % key)
+        return batch_chunk
+
+    def run_train_step(self, feed):
+        raise NotImplementedError('training the induction baseline is outside the B200 hot path '
+                                  '(inference / greedy decode only)')
+
+    def run_eval_step(self, feed, greedy=True):
+        eng = self.engine
+        eng.stage_batch(feed)
+        eng.encode()
+        pred = eng.forward_teacher()
+        torch.cuda.current_stream(eng.dev).synchronize()
+        self.loss = float(eng.loss[0])
+        self.report_loss = {'avg_action_loss': self.loss}
+        self.output = [np.asarray(feed['test_a_h']), pred.cpu().numpy()]
+        if greedy:
+            g, gl = eng.greedy()
+            self.greedy_pred_action, self.greedy_pred_action_len = g.cpu().numpy(), gl.cpu().numpy()
+        return self.loss
+
+    def state_dict(self):
+        eng = self.engine
+        p, s = eng.params.cpu().numpy(), eng.state.cpu().numpy()
+        out = {e.name: p[e.offset:e.offset + e.size].reshape(e.shape).copy() for e in eng.pm}
+        out.update({e.name: s[e.offset:e.offset + e.size].reshape(e.shape).copy() for e in eng.sm})
+        return out
+
+    def load_state_dict(self, d, trainable_only=False):
+        eng = self.engine
+        p, s = eng.params.cpu().numpy(), eng.state.cpu().numpy()
+        for e in eng.pm:
+            if e.name in d:
+                p[e.offset:e.offset + e.size] = np.asarray(d[e.name], np.float32).reshape(-1)
+        for e in eng.sm:
+            if e.name in d and not trainable_only:
+                s[e.offset:e.offset + e.size] = np.asarray(d[e.name], np.float32).reshape(-1)
+        eng.params.copy_(torch.from_numpy(p))
+        eng.state.copy_(torch.from_numpy(s))

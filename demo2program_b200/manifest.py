@@ -156,15 +156,16 @@ def build_manifests(cfg):
         m.add('Per_Decoder/dynamic_decoder/output_projection/kernel',
               (H, cfg.per_dim), 'glorot', (H, cfg.per_dim))
     if cfg.model == 'induction_baseline':
+        # scopes: AttnMechanism (memory_layer), Manipulation (decoder), reference
+        # models/baselines/model_induction.py:638-709
         A = cfg.action_space
-        sc = 'Action_Decoder'
+        m.add('AttnMechanism/memory_layer/kernel', (H, H), 'glorot', (H, H))
+        sc = 'Manipulation'
         m.add(sc + '/Token_Embedding/embedding_map', (A + 1, H), 'emb')
-        m.add(sc + '/memory_layer/kernel', (H, H), 'glorot', (H, H))
+        w = sc + '/dynamic_decoder/pooling_attention_wrapper/'
         # cell input = [emb ; attention] (2H) ++ h (H)
-        m.add(sc + '/attention_wrapper/basic_lstm_cell/kernel', (3 * H, 4 * H),
-              'glorot', (3 * H, 4 * H))
-        m.add(sc + '/attention_wrapper/basic_lstm_cell/bias', (4 * H,), 'zeros')
-        m.add(sc + '/attention_wrapper/attention_layer/kernel', (2 * H, H),
-              'glorot', (2 * H, H))
-        m.add(sc + '/output_projection/kernel', (H, A), 'glorot', (H, A))
+        m.add(w + 'basic_lstm_cell/kernel', (3 * H, 4 * H), 'glorot', (3 * H, 4 * H))
+        m.add(w + 'basic_lstm_cell/bias', (4 * H,), 'zeros')
+        m.add(w + 'attention_layer/kernel', (2 * H, H), 'glorot', (2 * H, H))
+        m.add(sc + '/dynamic_decoder/output_projection/kernel', (H, A), 'glorot', (H, A))
     return m, s

@@ -133,6 +133,27 @@ int d2p_lstm_decoder_greedy(const float* table, int vocab_rows, int E, const flo
                             const float* h0, const float* c0, float* logits, int* tokens,
                             int* lengths, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K6: pooled Luong attention + induction decoder --------------------------------
+ * reference models/baselines/model_induction.py:25-53, 107-182, 638-709.
+ * keys/values [T, R, H] time-major (R = B*k, keys = values * W_mem), mem_len [R];
+ * queries q [B*test_k, H]; ctx = mean over the k memories of the attention contexts. */
+int d2p_luong_pool_attention(const float* q, const float* keys, const float* values,
+                             const int* mem_len, int B, int k, int tk, int T, int H, float* ctx,
+                             void* stream);
+size_t d2p_induction_decode_ws_bytes(int B, int tk, int H);
+/* tokens [B*test_k, Tdec] int32 = teacher forcing, NULL = greedy (start A, end A-1).
+ * logits [Tdec, B*test_k, A]; greedy also fills out_tokens [Tdec, B*test_k], lengths. */
+int d2p_induction_decode(const float* keys, const float* values, const int* mem_len, int B, int k,
+                         int tk, int T, int H, const float* h_sum, const float* c_sum,
+                         const float* table, int A, const float* Wcell, const float* bcell,
+                         const float* Wa, const float* proj, const int* tokens, int Tdec,
+                         float* logits, int* out_tokens, int* lengths, void* ws, size_t ws_bytes,
+                         void* stream);
+/* out[row] = [A[row, :F1] ; B[row, :F2]]  (conv features ++ perception vector,
+ * model_induction.py:399-424) */
+int d2p_concat_cols(const float* A, int F1, const float* Bm, int F2, long long rows, float* out,
+                    void* stream);
+
 /* ---- fc -> (lrelu) -> BN : ops.fc, reference models/ops.py:149-155 ------------
  * used by Per_Encoder (model_full.py:308-316; act = 0, per-demo slices) */
 typedef struct {

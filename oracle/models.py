@@ -216,6 +216,82 @@ class OracleModel:
         out['loss'] = loss
         return out
 
+    # -- induction baseline (inference path; reference model_induction.py:383-819) ------
+    def forward_induction(self, batch, greedy=False):
+        cfg, dt = self.cfg, self.dtype
+        self.new_state = self.state.clone()
+        s_h = torch.as_tensor(np.asarray(batch['s_h'])).to(dt)
+        per = torch.as_tensor(np.asarray(batch['per'])).to(dt)
+        demo_len = torch.as_tensor(np.asarray(batch['demo_len'])).long()
+        t_len = torch.as_tensor(np.asarray(batch['test_demo_len'])).long()
+        t_tok = torch.as_tensor(np.asarray(batch['test_a_h_tokens'])).long()
+        t_oh = torch.as_tensor(np.asarray(batch['test_a_h'])).to(dt)
+        k, tk, A, Tm = cfg.k, cfg.test_k, cfg.action_space, cfg.max_demo_len
+        hist, hs, cs = [], [], []
+        for i in range(k):
+            y, h, c = self.demo_encoder(s_h[:, i], demo_len[:, i], per_i=per[:, i])
+            hist.append(y), hs.append(h), cs.append(c)
+        h_sum, c_sum = torch.stack(hs, 1).mean(1), torch.stack(cs, 1).mean(1)
+        values = torch.stack(hist, 1)                                   # [B,k,T,H], zero past len
+        keys = values @ self.p('AttnMechanism/memory_layer/kernel')
+        w = 'Manipulation/dynamic_decoder/pooling_attention_wrapper/'
+        kernel, bias = self.p(w + 'basic_lstm_cell/kernel'), self.p(w + 'basic_lstm_cell/bias')
+        w_a = self.p(w + 'attention_layer/kernel')
+        proj = self.p('Manipulation/dynamic_decoder/output_projection/kernel')
+        table = self.p('Manipulation/Token_Embedding/embedding_map')
+        B, H = h_sum.shape
+
+        def step(x_emb, c, h, att):
+            c, h = T.lstm_cell(torch.cat([x_emb, att], 1), c, h, kernel, bias)
+            att = T.luong_pooled_attention(h, keys, values, demo_len, w_a)
+            return c, h, att, att @ proj
+
+        out = {'demo_h_summary': h_sum, 'demo_c_summary': c_sum}
+        loss, logits_all, g_logits, g_lens = 0, [], [], []
+        for j in range(tk):
+            # swapped initial state: cell c := h-summary, cell h := c-summary
+            c, h, att = h_sum, c_sum, h_sum.new_zeros(B, H)
+            start = torch.full_like(t_tok[:, j, :1], A + 1)
+            emb = T.embedding_lookup_gpu(table, torch.cat([start, t_tok[:, j, :-1]], 1))
+            n_iter = max(int(min(int(t_len[:, j].max()), Tm)), 1)
+            lg = []
+            for t in range(n_iter):
+                c, h, att, l = step(emb[:, t], c, h, att)
+                lg.append(l)
+            lg = torch.stack(lg, 1)
+            if n_iter < Tm:
+                lg = torch.cat([lg, lg.new_zeros(B, Tm - n_iter, A)], 1)
+            logits_all.append(lg)
+            loss = loss + T.softmax_ce_loss(lg, t_oh[:, j], t_len[:, j])
+            if greedy:
+                with torch.no_grad():
+                    c, h, att = h_sum, c_sum, h_sum.new_zeros(B, H)
+                    ids = torch.full((B,), A, dtype=torch.long)
+                    fin = torch.zeros(B, dtype=torch.bool)
+                    ln = torch.zeros(B, dtype=torch.long)
+                    gl = []
+                    for t in range(Tm):
+                        c, h, att, l = step(T.embedding_lookup_gpu(table, ids), c, h, att)
+                        ids = l.argmax(1)
+                        nxt = fin | (ids == A - 1)
+                        if t + 1 >= Tm:
+                            nxt = torch.ones_like(nxt)
+                        ln = torch.where(~fin & nxt, torch.full_like(ln, t + 1), ln)
+                        fin = nxt
+                        gl.append(l)
+                        if bool(fin.all()):
+                            break
+                    gl = torch.stack(gl, 1)
+                    if gl.shape[1] < Tm:
+                        gl = torch.cat([gl, gl.new_zeros(B, Tm - gl.shape[1], A)], 1)
+                    g_logits.append(gl), g_lens.append(ln)
+        out['pred_action'] = torch.stack(logits_all, 1)                 # [B,test_k,T,A]
+        out['avg_action_loss'] = out['loss'] = loss / tk
+        if greedy:
+            out['greedy_pred_action'] = torch.stack(g_logits, 1)
+            out['greedy_pred_action_len'] = torch.stack(g_lens, 1)
+        return out
+
     def loss_and_grad(self, batch):
         """Returns (loss float, flat grad tensor, outputs)."""
         if self.flat.grad is not None:

@@ -219,3 +219,20 @@ def adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     m.mul_(b1).add_(g, alpha=1 - b1)
     v.mul_(b2).addcmul_(g, g, value=1 - b2)
     p.sub_(lr_t * m / (v.sqrt() + eps))
+
+
+def luong_pooled_attention(h, keys, values, mem_len, w_a):
+    """One PoolingAttentionWrapper step after the cell (reference
+    models/baselines/model_induction.py:25-53, 156-169):
+    for every memory i: score = h . keys_i^T (no scale), positions >= len -> -inf,
+    softmax, context_i = alpha . values_i, attention_i = [h ; context_i] @ W_a (shared);
+    output = mean_i attention_i.
+    h [B,H]; keys/values [B,k,T,H]; mem_len [B,k]; w_a [2H,H]."""
+    B, k, Tm, H = keys.shape
+    score = torch.einsum('bh,bkth->bkt', h, keys)
+    mask = torch.arange(Tm, device=h.device)[None, None, :] < mem_len[:, :, None]
+    score = torch.where(mask, score, torch.full_like(score, float('-inf')))
+    alpha = torch.softmax(score, dim=-1)
+    ctx = torch.einsum('bkt,bkth->bkh', alpha, values)
+    att = torch.cat([h.unsqueeze(1).expand(B, k, H), ctx], dim=-1) @ w_a     # [B,k,H]
+    return att.mean(1)

@@ -185,3 +185,62 @@ def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
                  '--summary_file', str(tmp_path / 'report.txt')])
     rep = open(tmp_path / 'report.txt').read()
     assert 'program_loss' in rep and 'greedy_program_token_acc' in rep
+
+
+@pytest.mark.parametrize('is_train', [False, True])
+def test_induction_forward_and_greedy_match_oracle(is_train):
+    """K6: pooled Luong attention decoder (teacher-forced loss + greedy) of the induction
+    baseline against the oracle; the swapped (c, h) initial state included."""
+    from oracle.models import OracleModel
+    from demo2program_b200.induction import InductionEngine
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('induction_baseline', batch_size=4, k=3)
+    pm, sm = build_manifests(cfg)
+    p0, s0 = pm.init_flat(5), sm.init_flat(5)
+    s0 = s0 + np.random.RandomState(1).uniform(0.0, 0.3, s0.shape).astype(np.float32)
+    batch = make_batch(cfg, seed=11)
+    om = OracleModel(cfg, p0, s0, is_train=is_train)
+    out = om.forward_induction(batch, greedy=True)
+    for use_tc, tol in ((False, 1e-4), (True, 1e-3)):
+        eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=is_train, use_tc=use_tc)
+        eng.stage_batch(batch)
+        eng.encode(exact=not use_tc)
+        pred = eng.forward_teacher(exact=not use_tc)
+        torch.cuda.synchronize()
+        assert abs(float(eng.loss[0]) - float(out['loss'].detach())) < LOSS_TOL
+        assert rel_err(eng.h_sum.cpu().numpy(), out['demo_h_summary'].detach().numpy()) < tol
+        assert rel_err(pred.cpu().numpy(), out['pred_action'].detach().numpy()) < tol
+        if not use_tc:
+            g, gl = eng.greedy(exact=True)
+            assert np.array_equal(gl.cpu().numpy(), out['greedy_pred_action_len'].numpy())
+            assert rel_err(g.cpu().numpy(), out['greedy_pred_action'].numpy()) < tol
+
+
+def test_luong_attention_kernel_against_torch():
+    """Fused score + masked softmax + context + mean-over-k kernel vs plain torch fp64."""
+    from demo2program_b200 import _lib
+    lib = _lib.load()
+    B, k, tk, T, H = 5, 3, 4, 20, 512
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(B * tk, H, generator=g)
+    keys = torch.randn(T, B * k, H, generator=g) * 0.2
+    vals = torch.randn(T, B * k, H, generator=g)
+    ln = torch.randint(1, T + 1, (B * k,), generator=g).int()
+    ctx = torch.zeros(B * tk, H, device='cuda')
+    qd, kd, vd, ld = q.cuda(), keys.cuda(), vals.cuda(), ln.cuda()
+    rc = lib.d2p_luong_pool_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), ld.data_ptr(), B, k, tk,
+                                      T, H, ctx.data_ptr(), None)
+    assert rc == 0, lib.d2p_last_error()
+    torch.cuda.synchronize()
+    K4 = keys.double().permute(1, 0, 2).reshape(B, k, T, H)
+    V4 = vals.double().permute(1, 0, 2).reshape(B, k, T, H)
+    L2 = ln.long().reshape(B, k)
+    ref = torch.zeros(B, tk, H, dtype=torch.float64)
+    for j in range(tk):
+        h = q.double().reshape(B, tk, H)[:, j]
+        sc = torch.einsum('bh,bkth->bkt', h, K4)
+        mask = torch.arange(T)[None, None] < L2[:, :, None]
+        al = torch.softmax(torch.where(mask, sc, torch.full_like(sc, float('-inf'))), -1)
+        ref[:, j] = torch.einsum('bkt,bkth->bkh', al, V4).mean(1)
+    assert rel_err(ctx.cpu().numpy().reshape(B, tk, H), ref.numpy()) < 1e-5
