@@ -102,6 +102,7 @@ SIGNATURES = {
     'd2p_gemm_tc_packed': (_i, [_fp, _fp, _i, _i, _i, _f, _f, _fp, _i, _fp, _i, _fp, _fp]),
     'd2p_tc_configure': (_i, [_fp, _sz, _fp, _sz, _i]),
     'd2p_tc_new_step': (_i, []),
+    'd2p_tc_bind_stream': (_i, [_fp, _fp, _sz]),
     'd2p_debug_set_probe': (_i, [_fp]),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),

@@ -190,8 +190,10 @@ int launch_tc(cudaStream_t st, Packed A, Packed B, int M, int N, int K, float al
 }
 
 struct CacheEntry { const float* src; int MN, K, ld, gate_tile; bool k_contig; size_t off; };
+struct StreamArena { cudaStream_t st; char* p; size_t bytes; };
 struct TcState {
     char* scratch = nullptr; size_t scratch_bytes = 0;
+    StreamArena per_stream[8]; int n_streams = 0;   // side streams of concurrent graph branches
     char* cache = nullptr; size_t cache_bytes = 0; size_t cache_used = 0;
     CacheEntry entries[256]; int n_entries = 0;
     int enabled = 1;
@@ -286,10 +288,13 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha,
 // ---- arena + per-step cache of packed constant operands (weights) ------------
 bool tc_available() { return g_tc.enabled && g_tc.scratch != nullptr; }
 
-void* tc_scratch_alloc(size_t* scratch_off, size_t bytes) {
+void* tc_scratch_alloc(cudaStream_t st, size_t* scratch_off, size_t bytes) {
+    char* base = g_tc.scratch; size_t cap = g_tc.scratch_bytes;
+    for (int i = 0; i < g_tc.n_streams; ++i)
+        if (g_tc.per_stream[i].st == st) { base = g_tc.per_stream[i].p; cap = g_tc.per_stream[i].bytes; }
     bytes = al256(bytes);
-    if (*scratch_off + bytes > g_tc.scratch_bytes) return nullptr;
-    void* p = g_tc.scratch + *scratch_off;
+    if (*scratch_off + bytes > cap) return nullptr;
+    void* p = base + *scratch_off;
     *scratch_off += bytes;
     return p;
 }
@@ -316,7 +321,7 @@ int get_packed(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_co
             return 0;
         }
     }
-    void* dst = tc_scratch_alloc(scratch_off, bytes);
+    void* dst = tc_scratch_alloc(st, scratch_off, bytes);
     D2P_REQUIRE(dst != nullptr, "tensor-core scratch arena too small");
     D2P_TRY(pack_bf16(st, S, MN, K, ld, k_contig, dst, gate_tile, gate_H));
     *out = dst;
@@ -339,7 +344,7 @@ int gemm_tc_auto(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float a
     int ks = auto_ksplit(M, N, K);
     float* part = nullptr;
     if (ks > 1) {
-        part = (float*)tc_scratch_alloc(&off, (size_t)ks * M * N * sizeof(float));
+        part = (float*)tc_scratch_alloc(st, &off, (size_t)ks * M * N * sizeof(float));
         if (!part) ks = 1;
     }
     return gemm_tc_packed(st, apk, bpk, M, N, K, alpha, beta, C, ldc, bias, ks, part);
@@ -381,6 +386,16 @@ extern "C" int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache
     d2p::g_tc.cache = (char*)cache; d2p::g_tc.cache_bytes = cache_bytes;
     d2p::g_tc.cache_used = 0; d2p::g_tc.n_entries = 0;
     d2p::g_tc.enabled = enabled;
+    d2p::g_tc.n_streams = 0;
+    return 0;
+}
+
+// Give `stream` its own scratch arena (same size class as the default one) so that
+// independent branches of the step can pack operands concurrently.
+extern "C" int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes) {
+    D2P_REQUIRE(d2p::g_tc.n_streams < 8 && scratch != nullptr, "tc_bind_stream: too many streams");
+    d2p::g_tc.per_stream[d2p::g_tc.n_streams++] =
+        d2p::StreamArena{(cudaStream_t)stream, (char*)scratch, scratch_bytes};
     return 0;
 }
 

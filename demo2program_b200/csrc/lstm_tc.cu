@@ -260,8 +260,8 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     size_t off = 0;
     const size_t hbytes = packed_bytes(R, H);
     uint8_t* hpk[2];
-    hpk[0] = (uint8_t*)tc_scratch_alloc(&off, hbytes);
-    hpk[1] = (uint8_t*)tc_scratch_alloc(&off, hbytes);
+    hpk[0] = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
+    hpk[1] = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
     D2P_REQUIRE(hpk[0] && hpk[1], "lstm fwd: tensor-core scratch arena too small");
     const void* whpk;
     D2P_TRY(get_packed(st, Wh, G4, H, G4, false, true, &off, &whpk, LBN, H));
@@ -315,8 +315,8 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
 
     size_t off = 0;
     const size_t zbytes = packed_bytes(R, G4);
-    uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(&off, zbytes);
-    float* partials = (float*)tc_scratch_alloc(&off, (size_t)nsplit * RH * sizeof(float));
+    uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
+    float* partials = (float*)tc_scratch_alloc(st, &off, (size_t)nsplit * RH * sizeof(float));
     D2P_REQUIRE(dzpk && partials, "lstm bwd: tensor-core scratch arena too small");
     const void* whpk;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));

@@ -266,6 +266,6 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
                    float* partials = nullptr);
 int get_packed(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_contig, bool is_const,
                size_t* scratch_off, const void** out, int gate_tile = 0, int gate_H = 0);
-void* tc_scratch_alloc(size_t* scratch_off, size_t bytes);
+void* tc_scratch_alloc(cudaStream_t st, size_t* scratch_off, size_t bytes);
 
 }  // namespace d2p

@@ -35,7 +35,7 @@ class Engine:
 
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
                  frames_dtype=np.uint8, flat_params=None, flat_state=None,
-                 world_size=1, use_graph=True, use_tc=True):
+                 world_size=1, use_graph=True, use_tc=True, concurrent=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
@@ -71,9 +71,20 @@ class Engine:
             self.tc_scratch = torch.zeros(big, dtype=torch.uint8, device=self.dev)
             self.tc_cache = torch.zeros(12 * self.pm.total + (16 << 20), dtype=torch.uint8,
                                         device=self.dev)
+        # side streams for the independent branches (three decoders, two RN pools)
+        self.concurrent = bool(concurrent)
+        self.side_streams = [torch.cuda.Stream(self.dev) for _ in range(2)] if self.concurrent else []
+        for s_ in self.side_streams:
+            self._ws_side[s_.cuda_stream] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.tc_side = [torch.zeros_like(self.tc_scratch) for _ in self.side_streams] if self.use_tc else []
         self._tc_bind()
         self._graph = None
         self._graph_key = None
+
+    @property
+    def ws(self):
+        """Scratch buffer of the current stream (side branches have their own)."""
+        return self._ws_side.get(torch.cuda.current_stream(self.dev).cuda_stream, self._ws_main)
 
     def _tc_bind(self):
         """The arena registration is library-global: bind this engine's buffers
@@ -81,6 +92,8 @@ class Engine:
         if self.use_tc:
             self.lib.d2p_tc_configure(ptr(self.tc_scratch), self.tc_scratch.numel(),
                                       ptr(self.tc_cache), self.tc_cache.numel(), 1)
+            for s_, arena in zip(self.side_streams, self.tc_side):
+                self.lib.d2p_tc_bind_stream(s_.cuda_stream, ptr(arena), arena.numel())
         else:
             self.lib.d2p_tc_configure(None, 0, None, 0, 0)
 
@@ -205,7 +218,8 @@ class Engine:
                  lib.d2p_embed_shifted_bwd_ws_bytes(V + 1, H, B, L),
                  lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, H, R, T))
         self.ws_bytes = _al(ws, 256)
-        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self._ws_main = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self._ws_side = {}
         self.loss = z(4)   # [total, program, action, per]
         self.out_bvl = None
 
@@ -261,165 +275,213 @@ class Engine:
             n += s.numel() * s.element_size()
         return n
 
+    # ------------------------------------------------------------------ branches
+    def _parallel(self, fns):
+        """Run independent branches of the step concurrently: fns[0] on the current
+        stream, the others on side streams that fork from / rejoin it (also valid
+        inside CUDA-graph capture).  Every branch has its own scratch buffers."""
+        if not self.concurrent or len(fns) == 1:
+            for fn in fns:
+                fn()
+            return
+        main = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        used = []
+        for fn, s in zip(fns[1:], self.side_streams):
+            s.wait_event(ev)
+            with torch.cuda.stream(s):
+                fn()
+            used.append(s)
+        fns[0]()
+        for s in used:
+            main.wait_stream(s)
+
     # ------------------------------------------------------------------ forward
     def forward(self, train_stats=None):
-        cfg, st = self.cfg, self._st()
+        cfg = self.cfg
         B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
         L, V = cfg.max_program_len, cfg.dim_program_token
         tr = int(self.is_train if train_stats is None else train_stats)
-        call = self._call
-        self._tc_bind()              # (re)bind this engine's arena; re-pack weights
-        call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, st)
-        call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, st)
+        call, S = self._call, self._st
+        self._tc_bind()              # (re)bind this engine's arenas; re-pack weights
+        call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, S())
+        call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, S())
         call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
-             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, st)
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
         self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc)
         if self.model in ('full', 'summarizer'):
-            call('d2p_group_sum', ptr(self.enc['hT']), B, k, H, 1.0 / k, ptr(self.sum1_h), 0, st)
-            call('d2p_group_sum', ptr(self.enc['cT']), B, k, H, 1.0 / k, ptr(self.sum1_c), 0, st)
-            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0, ptr(self.init2_h), 0, st)
-            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0, ptr(self.init2_c), 0, st)
+            call('d2p_group_sum', ptr(self.enc['hT']), B, k, H, 1.0 / k, ptr(self.sum1_h), 0, S())
+            call('d2p_group_sum', ptr(self.enc['cT']), B, k, H, 1.0 / k, ptr(self.sum1_c), 0, S())
+            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0, ptr(self.init2_h), 0, S())
+            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0, ptr(self.init2_c), 0, S())
             self._lstm_fwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
                            'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec)
             fin = self.sec
-            for s, out, saved in (('h', self.dsum_h, self.rn_saved_h),
-                                  ('c', self.dsum_c, self.rn_saved_c)):
-                call('d2p_rn_pool_fwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
-                     C.byref(self.fc[(s, 'fc2')]), ptr(out), ptr(saved), tr, ptr(self.ws),
-                     self.ws_bytes, st)
-                if self.model == 'full':   # mean + rn_pool (model_full.py:357-359)
-                    call('d2p_group_sum', ptr(fin[s + 'T']), B, k, H, 1.0 / k, ptr(out), 1, st)
+
+            def pool(s, out, saved):
+                def run():
+                    call('d2p_rn_pool_fwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                         C.byref(self.fc[(s, 'fc2')]), ptr(out), ptr(saved), tr, ptr(self.ws),
+                         self.ws_bytes, S())
+                    if self.model == 'full':   # mean + rn_pool (model_full.py:357-359)
+                        call('d2p_group_sum', ptr(fin[s + 'T']), B, k, H, 1.0 / k, ptr(out), 1, S())
+                return run
+            self._parallel([pool('h', self.dsum_h, self.rn_saved_h),
+                            pool('c', self.dsum_c, self.rn_saved_c)])
         else:
             if cfg.demo_aggregation != 'avgpool':
                 raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
             fin = self.enc
-            call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, st)
-            call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, st)
+            call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, S())
+            call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, S())
         self.fin = fin
-        # ---- program decoder (teacher forcing) ----
-        p = self.prog
-        call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), st)
-        call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
-             V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), st)
-        self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
-                       'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p)
-        Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
-        self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
-        call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
-             ptr(p['runlen']), ptr(p['w']), ptr(p['rowloss']), ptr(p['dlogits']),
-             ptr(self.loss[1:]), 0, st)
-        if self.model == 'full':
-            A, Pd = cfg.action_space, cfg.per_dim
-            a = self.act
-            call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(a['w']), ptr(a['runlen']), st)
+
+        def prog_fwd():   # program decoder (teacher forcing)
+            p = self.prog
+            call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), S())
+            call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
+                 V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), S())
+            self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p)
+            Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
+            call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
+                 ptr(p['runlen']), ptr(p['w']), ptr(p['rowloss']), ptr(p['dlogits']),
+                 ptr(self.loss[1:]), 0, S())
+
+        if self.model != 'full':
+            prog_fwd()
+            call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
+            return
+        A, Pd = cfg.action_space, cfg.per_dim
+        a, q = self.act, self.per
+        # instance normalisers / run lengths shared by the action and per decoders
+        call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(a['w']), ptr(a['runlen']), S())
+
+        def act_fwd():
             call('d2p_embed_shifted', ptr(self.P('Action_Decoder/Token_Embedding/embedding_map')),
-                 A + 1, H, ptr(self.d_act_tok), R, T, A + 1, ptr(a['X']), st)
+                 A + 1, H, ptr(self.d_act_tok), R, T, A + 1, ptr(a['X']), S())
             self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
                            'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a)
             Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
             call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
                  ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
-                 ptr(self.loss[2:]), 0, st)
-            q = self.per
-            call('d2p_rtp_to_trp', ptr(self.d_per), R, T, Pd, ptr(q['per_tm']), st)
+                 ptr(self.loss[2:]), 0, S())
+
+        def per_fwd():
+            call('d2p_rtp_to_trp', ptr(self.d_per), R, T, Pd, ptr(q['per_tm']), S())
             call('d2p_fc_bn_fwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
-                 ptr(q['X']), ptr(q['fc_saved']), tr, ptr(self.ws), self.ws_bytes, st)
+                 ptr(q['X']), ptr(q['fc_saved']), tr, ptr(self.ws), self.ws_bytes, S())
             self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
                            'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q)
             Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(0, 0, T * R, Pd, H, 1.0, q['y'], H, Wq, Pd, 0.0, q['logits'], Pd)
             call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
                  ptr(a['runlen']), ptr(a['w']), ptr(q['rowloss']), ptr(q['dlogits']),
-                 ptr(self.loss[3:]), 0, st)
-            # total = program + action + per
-            call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, st)
-            call('d2p_axpby', ptr(self.loss[2:]), 1.0, ptr(self.loss), 1.0, 1, st)
-            call('d2p_axpby', ptr(self.loss[3:]), 1.0, ptr(self.loss), 1.0, 1, st)
-        else:
-            call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, st)
+                 ptr(self.loss[3:]), 0, S())
+
+        self._parallel([prog_fwd, act_fwd, per_fwd])
+        # total = program + action + per
+        call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
+        call('d2p_axpby', ptr(self.loss[2:]), 1.0, ptr(self.loss), 1.0, 1, S())
+        call('d2p_axpby', ptr(self.loss[3:]), 1.0, ptr(self.loss), 1.0, 1, S())
 
     # ------------------------------------------------------------------ backward
     def backward(self):
-        cfg, st = self.cfg, self._st()
+        cfg = self.cfg
         B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
         L, V = cfg.max_program_len, cfg.dim_program_token
         tr = int(self.is_train)
-        call = self._call
+        call, S = self._call, self._st
         fin = self.fin
         self.grads.zero_()
-        # ---- program decoder ----
         p = self.prog
-        Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
-        self._gemm(1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
-                   self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V)
-        self._gemm(0, 1, L * B, H, V, 1.0, p['dlogits'], V, Wp, V, 0.0, p['dy'], H)
-        self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
-                       'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
-                       p['dX'])
-        call('d2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
-             ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-             self.ws_bytes, st)
-        # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
+
+        def prog_bwd():
+            Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
+            self._gemm(1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
+                       self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V)
+            self._gemm(0, 1, L * B, H, V, 1.0, p['dlogits'], V, Wp, V, 0.0, p['dy'], H)
+            self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
+                           p['dX'])
+            call('d2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
+                 ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                 self.ws_bytes, S())
+            # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
+
         have_dh2 = False
         if self.model == 'full':
             A, Pd = cfg.action_space, cfg.per_dim
             a, q = self.act, self.per
-            Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
-                       self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A)
-            self._gemm(0, 1, T * R, H, A, 1.0, a['dlogits'], A, Wa, A, 0.0, a['dy'], H)
-            self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
-                           a['dX'])
-            call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
-                 ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-                 self.ws_bytes, st)
-            Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
-                       self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd)
-            self._gemm(0, 1, T * R, H, Pd, 1.0, q['dlogits'], Pd, Wq, Pd, 0.0, q['dy'], H)
-            self._lstm_bwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, q['dy'], None, None,
-                           q['dX'])
-            call('d2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
-                 ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, st)
+
+            def act_bwd():
+                Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
+                self._gemm(1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
+                           self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A)
+                self._gemm(0, 1, T * R, H, A, 1.0, a['dlogits'], A, Wa, A, 0.0, a['dy'], H)
+                self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                               'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
+                               a['dX'])
+                call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
+                     ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                     self.ws_bytes, S())
+
+            def per_bwd():
+                Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
+                self._gemm(1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
+                           self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd)
+                self._gemm(0, 1, T * R, H, Pd, 1.0, q['dlogits'], Pd, Wq, Pd, 0.0, q['dy'], H)
+                self._lstm_bwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                               'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, q['dy'], None, None,
+                               q['dX'])
+                call('d2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
+                     ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, S())
+
+            self._parallel([prog_bwd, act_bwd, per_bwd])
             # dh2 = d(action init) + d(per init)
-            call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, st)
-            call('d2p_axpby', ptr(q['dh0']), 1.0, ptr(self.dh2), 1.0, R * H, st)
-            call('d2p_axpby', ptr(a['dc0']), 1.0, ptr(self.dc2), 0.0, R * H, st)
-            call('d2p_axpby', ptr(q['dc0']), 1.0, ptr(self.dc2), 1.0, R * H, st)
+            call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, S())
+            call('d2p_axpby', ptr(q['dh0']), 1.0, ptr(self.dh2), 1.0, R * H, S())
+            call('d2p_axpby', ptr(a['dc0']), 1.0, ptr(self.dc2), 0.0, R * H, S())
+            call('d2p_axpby', ptr(q['dc0']), 1.0, ptr(self.dc2), 1.0, R * H, S())
             have_dh2 = True
+        else:
+            prog_bwd()
         if self.model in ('full', 'summarizer'):
-            for s, dsum, saved, dF in (('h', p['dh0'], self.rn_saved_h, self.dh2),
-                                       ('c', p['dc0'], self.rn_saved_c, self.dc2)):
-                if self.model == 'full':   # mean term
-                    call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), int(have_dh2), st)
-                else:
-                    dF.zero_()
-                call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
-                     C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
-                     self.ws_bytes, st)
+            def pool_bwd(s, dsum, saved, dF):
+                def run():
+                    if self.model == 'full':   # mean term
+                        call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), int(have_dh2), S())
+                    else:
+                        dF.zero_()
+                    call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                         C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
+                         self.ws_bytes, S())
+                return run
+            self._parallel([pool_bwd('h', p['dh0'], self.rn_saved_h, self.dh2),
+                            pool_bwd('c', p['dc0'], self.rn_saved_c, self.dc2)])
             sec = self.sec
             self._lstm_bwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
                            'SecondPathEncoder/rnn/basic_lstm_cell/', sec, None, self.dh2, self.dc2,
                            self.dy1)
             # init state = mean_i of first-pass finals, broadcast over i
-            call('d2p_group_sum', ptr(sec['dh0']), B, k, H, 1.0, ptr(self.sum1_h), 0, st)
-            call('d2p_group_sum', ptr(sec['dc0']), B, k, H, 1.0, ptr(self.sum1_c), 0, st)
-            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0 / k, ptr(self.dh2), 0, st)
-            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0 / k, ptr(self.dc2), 0, st)
+            call('d2p_group_sum', ptr(sec['dh0']), B, k, H, 1.0, ptr(self.sum1_h), 0, S())
+            call('d2p_group_sum', ptr(sec['dc0']), B, k, H, 1.0, ptr(self.sum1_c), 0, S())
+            call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0 / k, ptr(self.dh2), 0, S())
+            call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0 / k, ptr(self.dc2), 0, S())
             dY1 = self.dy1
         else:
-            call('d2p_group_bcast', ptr(p['dh0']), B, k, H, 1.0 / k, ptr(self.dh2), 0, st)
-            call('d2p_group_bcast', ptr(p['dc0']), B, k, H, 1.0 / k, ptr(self.dc2), 0, st)
+            call('d2p_group_bcast', ptr(p['dh0']), B, k, H, 1.0 / k, ptr(self.dh2), 0, S())
+            call('d2p_group_bcast', ptr(p['dc0']), B, k, H, 1.0 / k, ptr(self.dc2), 0, S())
             dY1 = None
         self._lstm_bwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, dY1, self.dh2, self.dc2,
                        self.dfeat)
         call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.dfeat),
-             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, st)
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):

@@ -241,6 +241,8 @@ int d2p_gemm_tc_packed(const void* Apk, const void* Bpk, int M, int N, int K, fl
 int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache, size_t cache_bytes,
                      int enabled);
 int d2p_tc_new_step(void);
+/* per-stream scratch arena for concurrent branches (call after d2p_tc_configure) */
+int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes);
 /* developer tool: record SM-clock stamps of CTA (0,0,0) of the tensor-core kernels
  * into buf (>= 64 int64 on the device); NULL disables. */
 int d2p_debug_set_probe(long long* buf);
