@@ -52,11 +52,11 @@ SIGNATURES = {
     'd2p_conv_encoder_fwd': (_i, [_pd, _fp, _fp, _fp, _i, _fp, _sz, _fp]),
     'd2p_conv_encoder_bwd': (_i, [_pd, _fp, _fp, _fp, _i, _fp, _sz, _fp]),
     'd2p_lstm_seq_fwd': (_i, [_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _f,
-                              _fp, _fp, _fp, _fp, _fp, _fp]),
+                              _fp, _fp, _fp, _fp, _fp, _i, _fp]),
     'd2p_lstm_seq_bwd_ws_bytes': (_sz, [_i, _i, _i]),
     'd2p_lstm_seq_bwd': (_i, [_fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp,
                               _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
-                              _sz, _fp]),
+                              _sz, _i, _fp]),
     'd2p_embed_shifted': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp]),
     'd2p_embed_shifted_bwd_ws_bytes': (_sz, [_i, _i, _i, _i]),
     'd2p_embed_shifted_bwd': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp, _sz, _fp]),

@@ -20,10 +20,11 @@ size_t bn_ws_bytes(long long rows, int C, int nsl);
 bool lstm_tc_supported(int R, int H);
 int lstm_seq_fwd_tc(cudaStream_t, const float*, int, int, int, int, const int*, const float*,
                     const float*, const float*, const float*, float, float*, float*, float*, float*,
-                    float*);
+                    float*, int);
 int lstm_seq_bwd_tc(cudaStream_t, const float*, int, int, int, int, const int*, const float*,
                     const float*, const float*, const float*, float*, const float*, const float*,
-                    const float*, const float*, float*, float*, float*, float*, float*, void*, size_t);
+                    const float*, const float*, float*, float*, float*, float*, float*, void*, size_t,
+                    int);
 
 namespace {
 
@@ -95,23 +96,26 @@ using namespace d2p;
 extern "C" int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, const int* len,
                                 const float* h0, const float* c0, const float* W, const float* b,
                                 float forget_bias, float* Y, float* hT, float* cT, float* gates,
-                                float* cells, void* stream) {
+                                float* cells, int phases, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(X && len && W && b && Y && hT && cT && gates && cells, "lstm fwd: null buffer");
     D2P_REQUIRE(T > 0 && R > 0 && In > 0 && H > 0, "lstm fwd: bad dims");
     if (lstm_tc_supported(R, H))
-        return lstm_seq_fwd_tc(st, X, T, R, In, H, len, h0, c0, W, b, forget_bias, Y, hT, cT, gates, cells);
+        return lstm_seq_fwd_tc(st, X, T, R, In, H, len, h0, c0, W, b, forget_bias, Y, hT, cT, gates, cells,
+                               phases);
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;
     size_t RH = (size_t)R * H;
     int eb = cdiv(RH, 256);
+    // hoisted input contraction for all steps: gates = X*Wx + b
+    if (phases & D2P_LSTM_INPUT)
+        D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
+    if (!(phases & D2P_LSTM_RECUR)) return 0;
     copy_or_zero<<<eb, 256, 0, st>>>(hT, h0, RH);
     D2P_CHECK_LAUNCH();
     copy_or_zero<<<eb, 256, 0, st>>>(cT, c0, RH);
     D2P_CHECK_LAUNCH();
-    // hoisted input contraction for all steps: gates = X*Wx + b
-    D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
     for (int t = 0; t < T; ++t) {
         float* Gt = gates + (size_t)t * R * G4;
         if (t > 0 || h0 != nullptr)
@@ -132,12 +136,13 @@ extern "C" int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, con
                                 const float* h0, const float* c0, const float* W, const float* Y,
                                 float* gates, const float* cells, const float* dY,
                                 const float* dhT, const float* dcT, float* dX, float* dW, float* db,
-                                float* dh0, float* dc0, void* ws, size_t ws_bytes, void* stream) {
+                                float* dh0, float* dc0, void* ws, size_t ws_bytes, int phases,
+                                void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(X && len && W && Y && gates && cells && dW && db && dh0 && dc0, "lstm bwd: null buffer");
     if (lstm_tc_supported(R, H))
         return lstm_seq_bwd_tc(st, X, T, R, In, H, len, h0, c0, W, Y, gates, cells, dY, dhT, dcT, dX, dW,
-                               db, dh0, dc0, ws, ws_bytes);
+                               db, dh0, dc0, ws, ws_bytes, phases);
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;
@@ -145,20 +150,23 @@ extern "C" int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, con
     float* dWh = dW + (size_t)In * G4;
     size_t RH = (size_t)R * H;
     int eb = cdiv(RH, 256);
+    if (phases & D2P_LSTM_BWD_RECUR) {
     copy_or_zero<<<eb, 256, 0, st>>>(dh0, dhT, RH);   // dh0/dc0 double as the running dh/dc
-    D2P_CHECK_LAUNCH();
-    copy_or_zero<<<eb, 256, 0, st>>>(dc0, dcT, RH);
-    D2P_CHECK_LAUNCH();
-    for (int t = T - 1; t >= 0; --t) {
-        float* Gt = gates + (size_t)t * R * G4;
-        lstm_gates_bwd<<<eb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
-                                           c0, dY ? dY + t * RH : nullptr, dh0, dc0, len, t, R, H);
         D2P_CHECK_LAUNCH();
-        if (t > 0 || h0 != nullptr)   // dh_{t-1} += dZ_t * Wh^T
-            D2P_TRY(gemm(st, false, true, R, H, G4, 1.f, Gt, G4, Wh, G4, 1.f, dh0, H, nullptr, GEMM_CONST_B));
+        copy_or_zero<<<eb, 256, 0, st>>>(dc0, dcT, RH);
+        D2P_CHECK_LAUNCH();
+        for (int t = T - 1; t >= 0; --t) {
+            float* Gt = gates + (size_t)t * R * G4;
+            lstm_gates_bwd<<<eb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
+                                               c0, dY ? dY + t * RH : nullptr, dh0, dc0, len, t, R, H);
+            D2P_CHECK_LAUNCH();
+            if (t > 0 || h0 != nullptr)   // dh_{t-1} += dZ_t * Wh^T
+                D2P_TRY(gemm(st, false, true, R, H, G4, 1.f, Gt, G4, Wh, G4, 1.f, dh0, H, nullptr, GEMM_CONST_B));
+        }
+        if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
     }
-    // parameter and input gradients from the full dZ
-    if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+    if (!(phases & D2P_LSTM_BWD_PARAMS)) return 0;
+    // parameter gradients from the full dZ
     D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
     if (T > 1)
         D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));

@@ -248,14 +248,17 @@ bool lstm_tc_supported(int R, int H) {
 
 int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H, const int* len,
                     const float* h0, const float* c0, const float* W, const float* b,
-                    float forget_bias, float* Y, float* hT, float* cT, float* gates, float* cells) {
+                    float forget_bias, float* Y, float* hT, float* cT, float* gates, float* cells,
+                    int phases) {
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;
     const size_t RH = (size_t)R * H;
     const int eb = cdiv(RH, 256);
     // phase 1: hoisted input contraction for all steps: gates = X*Wx + b
-    D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
+    if (phases & D2P_LSTM_INPUT)
+        D2P_TRY(gemm(st, false, false, T * R, G4, In, 1.f, X, In, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
+    if (!(phases & D2P_LSTM_RECUR)) return 0;
     // phase 2: recurrence (the arena is reused from offset 0; stream order makes that safe)
     size_t off = 0;
     const size_t hbytes = packed_bytes(R, H);
@@ -296,7 +299,7 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
                     const float* h0, const float* c0, const float* W, const float* Y, float* gates,
                     const float* cells, const float* dY, const float* dhT, const float* dcT,
                     float* dX, float* dW, float* db, float* dh0, float* dc0, void* ws,
-                    size_t ws_bytes) {
+                    size_t ws_bytes, int phases) {
     const int G4 = 4 * H;
     const float* Wx = W;
     const float* Wh = W + (size_t)In * G4;
@@ -304,50 +307,54 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     float* dWh = dW + (size_t)In * G4;
     const size_t RH = (size_t)R * H;
     const int eb = cdiv(RH, 256);
+    if (phases & D2P_LSTM_BWD_RECUR) {
     // split-K factor of the per-step dh GEMM [R, H] = dZ_t [R, 4H] * Wh^T
-    long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
-    int ks = (int)(144 / (tiles64 < 1 ? 1 : tiles64));
-    const int nkb = cdiv(G4, BK);
-    if (ks > nkb / 4) ks = nkb / 4;
-    if (ks > 8) ks = 8;
-    if (ks < 1) ks = 1;
-    const int nsplit = gemm_tc_nsplit(G4, ks);
+        long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
+        int ks = (int)(144 / (tiles64 < 1 ? 1 : tiles64));
+        const int nkb = cdiv(G4, BK);
+        if (ks > nkb / 4) ks = nkb / 4;
+        if (ks > 8) ks = 8;
+        if (ks < 1) ks = 1;
+        const int nsplit = gemm_tc_nsplit(G4, ks);
 
-    size_t off = 0;
-    const size_t zbytes = packed_bytes(R, G4);
-    uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
-    float* partials = (float*)tc_scratch_alloc(st, &off, (size_t)nsplit * RH * sizeof(float));
-    D2P_REQUIRE(dzpk && partials, "lstm bwd: tensor-core scratch arena too small");
-    const void* whpk;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
-    D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));
-    D2P_CHECK_CUDA(cudaMemsetAsync(dzpk, 0, zbytes, st));
-    copy_or_zero_k<<<eb, 256, 0, st>>>(dh0, dhT, RH);   // dh0/dc0 double as the running carries
-    D2P_CHECK_LAUNCH();
-    copy_or_zero_k<<<eb, 256, 0, st>>>(dc0, dcT, RH);
-    D2P_CHECK_LAUNCH();
-    const int mgp_z = mgp_of(R);
-    const int pb = cdiv((long long)R * (H / 4), 256);
-    bool have_partials = false;
-    for (int t = T - 1; t >= 0; --t) {
-        float* Gt = gates + (size_t)t * R * G4;
-        lstm_bwd_point_kernel<<<pb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
-                                                  c0, dY ? dY + t * RH : nullptr, partials,
-                                                  have_partials ? nsplit : 0, dh0, dc0, len, t, R, H,
-                                                  dzpk, mgp_z);
+        size_t off = 0;
+        const size_t zbytes = packed_bytes(R, G4);
+        uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
+        float* partials = (float*)tc_scratch_alloc(st, &off, (size_t)nsplit * RH * sizeof(float));
+        D2P_REQUIRE(dzpk && partials, "lstm bwd: tensor-core scratch arena too small");
+        const void* whpk;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
+        D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));
+        D2P_CHECK_CUDA(cudaMemsetAsync(dzpk, 0, zbytes, st));
+        copy_or_zero_k<<<eb, 256, 0, st>>>(dh0, dhT, RH);   // dh0/dc0 double as the running carries
         D2P_CHECK_LAUNCH();
-        if (t > 0 || h0 != nullptr) {   // partial sums of dh_{t-1} = dZ_t * Wh^T
-            D2P_TRY(gemm_tc_packed(st, dzpk, whpk, R, H, G4, 1.f, 0.f, nullptr, H, nullptr, ks, partials));
-            have_partials = true;
-        } else {
-            have_partials = false;
+        copy_or_zero_k<<<eb, 256, 0, st>>>(dc0, dcT, RH);
+        D2P_CHECK_LAUNCH();
+        const int mgp_z = mgp_of(R);
+        const int pb = cdiv((long long)R * (H / 4), 256);
+        bool have_partials = false;
+        for (int t = T - 1; t >= 0; --t) {
+            float* Gt = gates + (size_t)t * R * G4;
+            lstm_bwd_point_kernel<<<pb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
+                                                      c0, dY ? dY + t * RH : nullptr, partials,
+                                                      have_partials ? nsplit : 0, dh0, dc0, len, t, R, H,
+                                                      dzpk, mgp_z);
+            D2P_CHECK_LAUNCH();
+            if (t > 0 || h0 != nullptr) {   // partial sums of dh_{t-1} = dZ_t * Wh^T
+                D2P_TRY(gemm_tc_packed(st, dzpk, whpk, R, H, G4, 1.f, 0.f, nullptr, H, nullptr, ks, partials));
+                have_partials = true;
+            } else {
+                have_partials = false;
+            }
         }
+        if (have_partials) {   // dh0 = carry + last partial sums
+            add_partials_kernel<<<eb, 256, 0, st>>>(dh0, partials, nsplit, RH);
+            D2P_CHECK_LAUNCH();
+        }
+        // input gradient from the full dZ (arena reused from offset 0)
+        if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
     }
-    if (have_partials) {   // dh0 = carry + last partial sums
-        add_partials_kernel<<<eb, 256, 0, st>>>(dh0, partials, nsplit, RH);
-        D2P_CHECK_LAUNCH();
-    }
-    // parameter and input gradients from the full dZ (arena reused from offset 0)
-    if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+    if (!(phases & D2P_LSTM_BWD_PARAMS)) return 0;
+    // parameter gradients from the full dZ
     D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
     if (T > 1)
         D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));

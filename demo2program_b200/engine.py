@@ -74,9 +74,11 @@ class Engine:
         # side streams for the independent branches (three decoders, two RN pools)
         self.concurrent = bool(concurrent)
         self.side_streams = [torch.cuda.Stream(self.dev) for _ in range(2)] if self.concurrent else []
-        for s_ in self.side_streams:
+        self.grad_stream = torch.cuda.Stream(self.dev) if self.concurrent else None
+        for s_ in self.side_streams + ([self.grad_stream] if self.concurrent else []):
             self._ws_side[s_.cuda_stream] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
-        self.tc_side = [torch.zeros_like(self.tc_scratch) for _ in self.side_streams] if self.use_tc else []
+        self._all_side = self.side_streams + ([self.grad_stream] if self.concurrent else [])
+        self.tc_side = [torch.zeros_like(self.tc_scratch) for _ in self._all_side] if self.use_tc else []
         self._tc_bind()
         self._graph = None
         self._graph_key = None
@@ -92,7 +94,7 @@ class Engine:
         if self.use_tc:
             self.lib.d2p_tc_configure(ptr(self.tc_scratch), self.tc_scratch.numel(),
                                       ptr(self.tc_cache), self.tc_cache.numel(), 1)
-            for s_, arena in zip(self.side_streams, self.tc_side):
+            for s_, arena in zip(self._all_side, self.tc_side):
                 self.lib.d2p_tc_bind_stream(s_.cuda_stream, ptr(arena), arena.numel())
         else:
             self.lib.d2p_tc_configure(None, 0, None, 0, 0)
@@ -230,18 +232,32 @@ class Engine:
     def _call(self, name, *args):
         check(getattr(self.lib, name)(*args), name)
 
-    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b):
+    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3):
         self._call('d2p_lstm_seq_fwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
                    ptr(self.P(scope + 'kernel')), ptr(self.P(scope + 'bias')), 1.0,
                    ptr(b['y']), ptr(b['hT']), ptr(b['cT']), ptr(b['gates']), ptr(b['cells']),
-                   self._st())
+                   phases, self._st())
 
-    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX):
+    def _lstm_bwd_call(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, phases):
         self._call('d2p_lstm_seq_bwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
                    ptr(self.P(scope + 'kernel')), ptr(b['y']), ptr(b['gates']), ptr(b['cells']),
                    ptr(dY), ptr(dhT), ptr(dcT), ptr(dX), ptr(self.G(scope + 'kernel')),
                    ptr(self.G(scope + 'bias')), ptr(b['dh0']), ptr(b['dc0']), ptr(self.ws),
-                   self.ws_bytes, self._st())
+                   self.ws_bytes, phases, self._st())
+
+    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX):
+        """BPTT recurrence (+ dX) on the current stream; the parameter-gradient products
+        (dWx, dWh, db: large, throughput-bound) are handed to the gradient stream so they
+        overlap with the latency-bound recurrences that follow."""
+        if not self.concurrent:
+            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 3)
+            return
+        self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 1)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.grad_stream.wait_event(ev)
+        with torch.cuda.stream(self.grad_stream):
+            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, None, 2)
 
     def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc):
         self._call('d2p_gemm', int(ta), int(tb), M, N, K, alpha, ptr(A), lda, ptr(Bm), ldb, beta,
@@ -307,6 +323,53 @@ class Engine:
         self._tc_bind()              # (re)bind this engine's arenas; re-pack weights
         call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, S())
         call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, S())
+        # The decoders' hoisted input products (teacher-forced embeddings x Wx) do not depend
+        # on the encoder: issue them on the side streams now, under the encoder recurrence.
+        p = self.prog
+
+        def prog_in():
+            call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
+                 V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), S())
+            self._lstm_fwd(p['X'], L, B, H, self.d_prog_len, None, None,
+                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, phases=1)
+
+        def act_in():
+            a = self.act
+            call('d2p_embed_shifted', ptr(self.P('Action_Decoder/Token_Embedding/embedding_map')),
+                 cfg.action_space + 1, H, ptr(self.d_act_tok), R, T, cfg.action_space + 1, ptr(a['X']), S())
+            self._lstm_fwd(a['X'], T, R, H, self.d_demo_len, None, None,
+                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=1)
+
+        def per_in():
+            q = self.per
+            call('d2p_rtp_to_trp', ptr(self.d_per), R, T, cfg.per_dim, ptr(q['per_tm']), S())
+            call('d2p_fc_bn_fwd', ptr(q['per_tm']), T * R, cfg.per_dim, H, 1, k, 0, C.byref(self.per_fc),
+                 ptr(q['X']), ptr(q['fc_saved']), tr, ptr(self.ws), self.ws_bytes, S())
+            self._lstm_fwd(q['X'], T, R, H, self.d_demo_len, None, None,
+                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, phases=1)
+
+        self._ev_prog_in = None
+        if self.concurrent:
+            main = torch.cuda.current_stream(self.dev)
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            s1, s2 = self.side_streams
+            s1.wait_event(ev0)
+            with torch.cuda.stream(s1):
+                if self.model == 'full':
+                    act_in()
+                prog_in()
+                self._ev_prog_in = torch.cuda.Event()
+                self._ev_prog_in.record(s1)
+            if self.model == 'full':
+                s2.wait_event(ev0)
+                with torch.cuda.stream(s2):
+                    per_in()
+        else:
+            prog_in()
+            if self.model == 'full':
+                act_in()
+                per_in()
         call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
         self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
@@ -339,12 +402,11 @@ class Engine:
         self.fin = fin
 
         def prog_fwd():   # program decoder (teacher forcing)
-            p = self.prog
             call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), S())
-            call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
-                 V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), S())
+            if self._ev_prog_in is not None:
+                torch.cuda.current_stream(self.dev).wait_event(self._ev_prog_in)
             self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
-                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p)
+                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, phases=2)
             Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
             call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
@@ -353,6 +415,8 @@ class Engine:
 
         if self.model != 'full':
             prog_fwd()
+            if self.concurrent:
+                torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[0])
             call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
             return
         A, Pd = cfg.action_space, cfg.per_dim
@@ -361,10 +425,8 @@ class Engine:
         call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(a['w']), ptr(a['runlen']), S())
 
         def act_fwd():
-            call('d2p_embed_shifted', ptr(self.P('Action_Decoder/Token_Embedding/embedding_map')),
-                 A + 1, H, ptr(self.d_act_tok), R, T, A + 1, ptr(a['X']), S())
             self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a)
+                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=2)
             Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
             call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
@@ -372,11 +434,8 @@ class Engine:
                  ptr(self.loss[2:]), 0, S())
 
         def per_fwd():
-            call('d2p_rtp_to_trp', ptr(self.d_per), R, T, Pd, ptr(q['per_tm']), S())
-            call('d2p_fc_bn_fwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
-                 ptr(q['X']), ptr(q['fc_saved']), tr, ptr(self.ws), self.ws_bytes, S())
             self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q)
+                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, phases=2)
             Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
             self._gemm(0, 0, T * R, Pd, H, 1.0, q['y'], H, Wq, Pd, 0.0, q['logits'], Pd)
             call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
@@ -482,6 +541,8 @@ class Engine:
                        self.dfeat)
         call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.dfeat),
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
+        if self.concurrent:   # parameter-gradient products must land before the optimizer
+            torch.cuda.current_stream(self.dev).wait_stream(self.grad_stream)
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):

@@ -137,7 +137,7 @@ class InductionEngine:
         sc = 'Demo_Encoder/rnn/basic_lstm_cell/'
         call('d2p_lstm_seq_fwd', ptr(self.X), T, R, F + Pd, H, ptr(self.d_demo_len), None, None,
              ptr(self.P(sc + 'kernel')), ptr(self.P(sc + 'bias')), 1.0, ptr(self.Y), ptr(self.hT),
-             ptr(self.cT), ptr(self.gates), ptr(self.cells), st)
+             ptr(self.cT), ptr(self.gates), ptr(self.cells), 3, st)
         call('d2p_group_sum', ptr(self.hT), B, k, H, 1.0 / k, ptr(self.h_sum), 0, st)
         call('d2p_group_sum', ptr(self.cT), B, k, H, 1.0 / k, ptr(self.c_sum), 0, st)
         # keys = values * W_mem (LuongAttention memory_layer); values = Y (zero past len)

@@ -86,9 +86,15 @@ int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float
  * i,j,f,o, forget_bias, dynamic_rnn length masking.
  * X [T,R,In]; W [(In+H),4H] (TF kernel layout); Y [T,R,H] zero past len;
  * gates [T,R,4H] and cells [T,R,H] are saved for the backward. */
+enum { D2P_LSTM_INPUT = 1,      /* gates = X*Wx + b for all steps (independent of h0/c0) */
+       D2P_LSTM_RECUR = 2,      /* the recurrence over T steps */
+       D2P_LSTM_BWD_RECUR = 1,  /* BPTT recurrence + dX, dh0, dc0 */
+       D2P_LSTM_BWD_PARAMS = 2  /* dW, db from the dZ left in `gates` by the recurrence phase */ };
+/* `phases` selects which parts run (3 = all); the parts may be issued on different
+ * streams as long as the stream order of the data dependencies is kept. */
 int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, const int* len, const float* h0,
                      const float* c0, const float* W, const float* b, float forget_bias, float* Y,
-                     float* hT, float* cT, float* gates, float* cells, void* stream);
+                     float* hT, float* cT, float* gates, float* cells, int phases, void* stream);
 size_t d2p_lstm_seq_bwd_ws_bytes(int T, int R, int H);
 /* gates is consumed (holds dZ on return). dY/dhT/dcT/dX may be NULL.
  * dh0/dc0 [R,H] are required (they double as the running state grads). */
@@ -96,7 +102,7 @@ int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, const int* len
                      const float* c0, const float* W, const float* Y, float* gates,
                      const float* cells, const float* dY, const float* dhT, const float* dcT,
                      float* dX, float* dW, float* db, float* dh0, float* dc0, void* ws,
-                     size_t ws_bytes, void* stream);
+                     size_t ws_bytes, int phases, void* stream);
 
 /* ---- decoder inputs / losses -------------------------------------------------
  * reference models/model_full.py:282-296 (Token_Embedding), :446-450 (<s>

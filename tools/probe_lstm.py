@@ -23,7 +23,7 @@ probe = torch.zeros(64, dtype=torch.int64, device=dev)
 
 def run():
     check(lib.d2p_lstm_seq_fwd(ptr(X), T, R, In, H, ptr(ln), None, None, ptr(W), ptr(b), 1.0, ptr(Y), ptr(hT),
-                               ptr(cT), ptr(gates), ptr(cells), st), 'fwd')
+                               ptr(cT), ptr(gates), ptr(cells), 3, st), 'fwd')
 
 
 for _ in range(3):
