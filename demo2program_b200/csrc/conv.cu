@@ -41,6 +41,8 @@ struct Geo {
 template <typename IN_T>
 __device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (float)in[idx]; }
 
+#include "conv_v2.cuh"
+
 // a[n,oy,ox,:] = lrelu(bias + sum_taps W[ky,kx,:,:]^T x(n, 2oy+ky-PT, 2ox+kx-PL, :))
 // where x = in*scale[slice]+shift[slice] (identity if scale == nullptr), zero outside.
 template <typename IN_T>
@@ -258,12 +260,79 @@ int check_desc(const d2p_conv_desc* d) {
     D2P_REQUIRE(d->frames_dtype == D2P_U8 || d->frames_dtype == D2P_F32, "conv: frames dtype");
     for (int l = 0; l < d->n_layers; ++l) {
         int c = d->layers[l].cout;
-        D2P_REQUIRE(c > 0 && c <= MAXC && c % 4 == 0, "conv: layer %d cout=%d unsupported", l, c);
+        D2P_REQUIRE(c == 16 || c == 32 || c == 48, "conv: layer %d cout=%d unsupported (16/32/48)", l, c);
     }
     return 0;
 }
 
 }  // namespace
+
+// ---- launch helpers for the register-blocked kernels (conv_v2.cuh) ------------------------
+template <typename K>
+static int cv_set_smem(K kernel, size_t bytes) {
+    D2P_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <typename IN_T>
+static int launch_conv_fwd(cudaStream_t st, const Geo& g, const IN_T* in, const float* sc, const float* sh,
+                           const float* W, const float* b, float* out) {
+    const long long npix = (long long)g.N * g.OH * g.OW;
+    const int K3 = 3 * g.CIN;
+    const size_t smem = ((size_t)K3 * CV_TP + (size_t)K3 * g.COUT) * sizeof(float);
+    int blocks = cdiv(npix, CV_TP);
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+#define D2P_CV_FWD(C)                                                                         \
+    do {                                                                                      \
+        D2P_TRY(cv_set_smem(conv_fwd_v2<C, IN_T>, smem));                                     \
+        conv_fwd_v2<C, IN_T><<<blocks, CV_THREADS, smem, st>>>(g, in, sc, sh, W, b, out);     \
+    } while (0)
+    if (g.COUT == 16) D2P_CV_FWD(16);
+    else if (g.COUT == 32) D2P_CV_FWD(32);
+    else if (g.COUT == 48) D2P_CV_FWD(48);
+    else return fail(D2P_ERR_ARG, "conv fwd: unsupported channel count %d (16/32/48)", g.COUT);
+#undef D2P_CV_FWD
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+static int launch_conv_dx(cudaStream_t st, const Geo& g, const float* dZ, const float* W, float* dX) {
+    const long long nmax = (long long)g.N * ((g.IH + 1) / 2) * ((g.IW + 1) / 2);
+    const size_t smem = ((size_t)g.COUT * CV_TP + (size_t)g.COUT * g.CIN) * sizeof(float);
+    int blocks = cdiv(nmax, CV_TP);
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+#define D2P_CV_DX(C)                                                                          \
+    do {                                                                                      \
+        D2P_TRY(cv_set_smem(conv_bwd_dx_v2<C>, smem));                                        \
+        conv_bwd_dx_v2<C><<<dim3(blocks, 4), CV_THREADS, smem, st>>>(g, dZ, W, dX);           \
+    } while (0)
+    if (g.CIN == 16) D2P_CV_DX(16);
+    else if (g.CIN == 32) D2P_CV_DX(32);
+    else if (g.CIN == 48) D2P_CV_DX(48);
+    else return fail(D2P_ERR_ARG, "conv bwd dx: unsupported channel count %d (16/32/48)", g.CIN);
+#undef D2P_CV_DX
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename IN_T>
+static int launch_conv_dw(cudaStream_t st, const Geo& g, const IN_T* in, const float* sc, const float* sh,
+                          const float* dZ, int ppb, int nblk, float* partial) {
+    const int K3 = 3 * g.CIN;
+    const size_t smem = ((size_t)CV_TP * (K3 + 1) + (size_t)CV_TP * g.COUT) * sizeof(float);
+#define D2P_CV_DW(C)                                                                          \
+    do {                                                                                      \
+        D2P_TRY(cv_set_smem(conv_bwd_dw_v2<C, IN_T>, smem));                                  \
+        conv_bwd_dw_v2<C, IN_T><<<dim3(nblk, 3), CV_THREADS, smem, st>>>(g, in, sc, sh, dZ, ppb, partial); \
+    } while (0)
+    if (g.COUT == 16) D2P_CV_DW(16);
+    else if (g.COUT == 32) D2P_CV_DW(32);
+    else if (g.COUT == 48) D2P_CV_DW(48);
+    else return fail(D2P_ERR_ARG, "conv bwd dw: unsupported channel count %d (16/32/48)", g.COUT);
+#undef D2P_CV_DW
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
 
 // ---- saved-tensor layout ---------------------------------------------------
 // saved = for each layer l: act a_l [N,OH,OW,C] | stats [4, k, C]
@@ -378,11 +447,11 @@ extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, 
         int blocks = cdiv(npix, PX);
         const float* sc = prev_stats ? prev_stats + 2 * (size_t)g.k * g.CIN : nullptr;
         const float* sh = prev_stats ? prev_stats + 3 * (size_t)g.k * g.CIN : nullptr;
+        (void)blocks;
         if (l == 0 && d->frames_dtype == D2P_U8)
-            conv_fwd_kernel<uint8_t><<<blocks, 128, 0, st>>>(g, (const uint8_t*)frames, nullptr, nullptr, L.w, L.b, act);
+            D2P_TRY(launch_conv_fwd<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, L.w, L.b, act));
         else
-            conv_fwd_kernel<float><<<blocks, 128, 0, st>>>(g, l == 0 ? (const float*)frames : prev, sc, sh, L.w, L.b, act);
-        D2P_CHECK_LAUNCH();
+            D2P_TRY(launch_conv_fwd<float>(st, g, l == 0 ? (const float*)frames : prev, sc, sh, L.w, L.b, act));
         D2P_TRY(bn_forward_stats(st, act, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma, L.beta,
                                  L.moving_mean, L.moving_var, training, stats, wsb + p.off_part,
                                  p.part_bytes));
@@ -443,18 +512,17 @@ extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, 
         const float* sc = l > 0 ? stats[l - 1] + 2 * (size_t)g.k * g.CIN : nullptr;
         const float* sh = l > 0 ? stats[l - 1] + 3 * (size_t)g.k * g.CIN : nullptr;
         if (l == 0 && d->frames_dtype == D2P_U8)
-            conv_bwd_dw_kernel<uint8_t><<<dim3(nblk, 9), 256, 0, st>>>(g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, (float*)part);
+            D2P_TRY(launch_conv_dw<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, nblk, (float*)part));
         else
-            conv_bwd_dw_kernel<float><<<dim3(nblk, 9), 256, 0, st>>>(g, l == 0 ? (const float*)frames : acts[l - 1], sc, sh, dZ, ppb, (float*)part);
-        D2P_CHECK_LAUNCH();
+            D2P_TRY(launch_conv_dw<float>(st, g, l == 0 ? (const float*)frames : acts[l - 1], sc, sh, dZ, ppb, nblk, (float*)part));
         int nw = 9 * g.CIN * g.COUT;
         conv_dw_reduce<<<cdiv(nw, 256), 256, 0, st>>>((const float*)part, nblk, nw, L.dw);
         D2P_CHECK_LAUNCH();
         if (l > 0) {
             D2P_REQUIRE(g.CIN % 4 == 0, "conv bwd: CIN %% 4");
             long long nin = (long long)g.N * g.IH * g.IW;
-            conv_bwd_dx_kernel<<<cdiv(nin, PX), 128, 0, st>>>(g, dZ, L.w, dY);
-            D2P_CHECK_LAUNCH();
+            (void)nin;
+            D2P_TRY(launch_conv_dx(st, g, dZ, L.w, dY));
         }
     }
     return 0;

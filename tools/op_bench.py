@@ -11,7 +11,7 @@ from demo2program_b200.engine import Engine
 from demo2program_b200.synthetic import make_batch
 
 cfg = karel_config('full', batch_size=32, k=10)
-eng = Engine(cfg, use_graph=False)
+eng = Engine(cfg, use_graph=False, concurrent=False)
 batch = make_batch(cfg, seed=123)
 eng.stage_batch(batch)
 for _ in range(3):
@@ -35,9 +35,9 @@ eng._call = timed_call
 orig_fwd, orig_bwd = eng._lstm_fwd, eng._lstm_bwd
 
 
-def lf(X, Tn, Rn, In, lens, h0, c0, scope, b):
-    tag[0] = scope.split('/')[0] + ':'
-    orig_fwd(X, Tn, Rn, In, lens, h0, c0, scope, b)
+def lf(X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3):
+    tag[0] = scope.split('/')[0] + ':p%d:' % phases
+    orig_fwd(X, Tn, Rn, In, lens, h0, c0, scope, b, phases)
     tag[0] = ''
 
 
@@ -48,6 +48,17 @@ def lb(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX):
 
 
 eng._lstm_fwd, eng._lstm_bwd = lf, lb
+orig_bwd = eng._lstm_bwd_call
+
+
+def lbc(*a):
+    tag[0] = a[7].split('/')[0] + ':bwd%d:' % a[-1]
+    orig_bwd(*a)
+    tag[0] = ''
+
+
+eng._lstm_bwd_call = lbc
+eng._lstm_bwd = Engine._lstm_bwd.__get__(eng)
 N = 5
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record()
