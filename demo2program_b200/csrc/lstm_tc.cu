@@ -25,6 +25,12 @@ using namespace tc;
 bool tc_available();
 int gemm_tc_nsplit(int K, int ksplit);
 int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, size_t);
+// fp32 CUDA-core step kernels for R <= 32 (lstm_skinny.cu)
+bool lstm_skinny_supported(int R, int H);
+int lstm_skinny_nsplit(int H);
+int lstm_skinny_fwd_step(cudaStream_t, const float*, int, int, float*, float*, float*, const float*, float*, float*,
+                         const int*, int, float);
+int lstm_skinny_bwd_step(cudaStream_t, const float*, const float*, int, int, float*);
 
 namespace {
 
@@ -214,6 +220,7 @@ lstm_bwd_point_kernel(float* __restrict__ G /*[R,4H] in: gates, out: dZ*/,
         st4(dhc + su, dh);    // state copied through: gradient passes unchanged
     }
     st4(g, di); st4(g + H, dj); st4(g + 2 * H, df); st4(g + 3 * H, dq);
+    if (!dzpk) return;   // fp32 (small-R) recurrence reads dZ from G
     store_packed4(dzpk, dz_mgp, r, u0, di);
     store_packed4(dzpk, dz_mgp, r, H + u0, dj);
     store_packed4(dzpk, dz_mgp, r, 2 * H + u0, df);
@@ -242,6 +249,8 @@ int lstm_tc_set_probe(long long* buf) {
     return 0;
 }
 
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 bool lstm_tc_supported(int R, int H) {
     return tc_available() && H % 64 == 0 && H >= 64 && R >= 1;
 }
@@ -261,6 +270,20 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     if (!(phases & D2P_LSTM_RECUR)) return 0;
     // phase 2: recurrence (the arena is reused from offset 0; stream order makes that safe)
     size_t off = 0;
+    if (lstm_skinny_supported(R, H) && aligned16(Wh) && aligned16(hT) && aligned16(gates)) {
+        // every CTA reads all of h_{t-1}: ping-pong between hT and a scratch copy
+        float* hb[2] = {hT, (float*)tc_scratch_alloc(st, &off, RH * sizeof(float))};
+        D2P_REQUIRE(hb[1], "lstm fwd: scratch arena too small");
+        copy_or_zero_k<<<eb, 256, 0, st>>>(hT, h0, RH);
+        D2P_CHECK_LAUNCH();
+        copy_or_zero_k<<<eb, 256, 0, st>>>(cT, c0, RH);
+        D2P_CHECK_LAUNCH();
+        for (int t = 0; t < T; ++t)
+            D2P_TRY(lstm_skinny_fwd_step(st, Wh, R, H, gates + (size_t)t * R * G4, cells + t * RH, Y + t * RH,
+                                         hb[t & 1], hb[(t + 1) & 1], cT, len, t, forget_bias));
+        if (T & 1) D2P_CHECK_CUDA(cudaMemcpyAsync(hT, hb[1], RH * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     const size_t hbytes = packed_bytes(R, H);
     uint8_t* hpk[2];
     hpk[0] = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
@@ -315,16 +338,19 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
         if (ks > nkb / 4) ks = nkb / 4;
         if (ks > 8) ks = 8;
         if (ks < 1) ks = 1;
-        const int nsplit = gemm_tc_nsplit(G4, ks);
+        const bool skinny = lstm_skinny_supported(R, H) && aligned16(Wh) && aligned16(gates);
+        const int nsplit = skinny ? lstm_skinny_nsplit(H) : gemm_tc_nsplit(G4, ks);
 
         size_t off = 0;
         const size_t zbytes = packed_bytes(R, G4);
         uint8_t* dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
         float* partials = (float*)tc_scratch_alloc(st, &off, (size_t)nsplit * RH * sizeof(float));
         D2P_REQUIRE(dzpk && partials, "lstm bwd: tensor-core scratch arena too small");
-        const void* whpk;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
-        D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));
-        D2P_CHECK_CUDA(cudaMemsetAsync(dzpk, 0, zbytes, st));
+        const void* whpk = nullptr;   // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
+        if (!skinny) {
+            D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &whpk));
+            D2P_CHECK_CUDA(cudaMemsetAsync(dzpk, 0, zbytes, st));
+        }
         copy_or_zero_k<<<eb, 256, 0, st>>>(dh0, dhT, RH);   // dh0/dc0 double as the running carries
         D2P_CHECK_LAUNCH();
         copy_or_zero_k<<<eb, 256, 0, st>>>(dc0, dcT, RH);
@@ -337,10 +363,11 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
             lstm_bwd_point_kernel<<<pb, 256, 0, st>>>(Gt, cells + t * RH, t > 0 ? cells + (t - 1) * RH : nullptr,
                                                       c0, dY ? dY + t * RH : nullptr, partials,
                                                       have_partials ? nsplit : 0, dh0, dc0, len, t, R, H,
-                                                      dzpk, mgp_z);
+                                                      skinny ? nullptr : dzpk, mgp_z);
             D2P_CHECK_LAUNCH();
             if (t > 0 || h0 != nullptr) {   // partial sums of dh_{t-1} = dZ_t * Wh^T
-                D2P_TRY(gemm_tc_packed(st, dzpk, whpk, R, H, G4, 1.f, 0.f, nullptr, H, nullptr, ks, partials));
+                if (skinny) D2P_TRY(lstm_skinny_bwd_step(st, Gt, Wh, R, H, partials));
+                else D2P_TRY(gemm_tc_packed(st, dzpk, whpk, R, H, G4, 1.f, 0.f, nullptr, H, nullptr, ks, partials));
                 have_partials = true;
             } else {
                 have_partials = false;
