@@ -212,7 +212,12 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
     float* Zs = cv_smem + (size_t)CV_TP * AST;
     const int tid = threadIdx.x, ky = blockIdx.y;
     const int c4 = (tid % C4) * 4, rl = tid / C4;
-    const bool active = rl < RL;
+    // few slab rows (3*CIN < RL, e.g. the RGB input layer): the spare row lanes split the
+    // tile's pixels into PG groups that are summed through shared memory at the end
+    const int PG = K3 < RL ? RL / K3 : 1;
+    const int row0 = PG > 1 ? rl % K3 : rl;
+    const int pgp = PG > 1 ? rl / K3 : 0;
+    const bool active = pgp < PG;
     const long long npix = (long long)g.N * g.OH * g.OW;
     const long long p0 = (long long)blockIdx.x * pix_per_block;
     long long p1 = p0 + pix_per_block;
@@ -253,11 +258,11 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
         }
         __syncthreads();
         if (active) {
-            for (int pp = 0; pp < CV_TP; ++pp) {
+            for (int pp = pgp; pp < CV_TP; pp += PG) {
                 const float4 z4 = *reinterpret_cast<const float4*>(Zs + pp * COUT + c4);
 #pragma unroll
                 for (int r = 0; r < MAXROWS; ++r) {
-                    const int row = rl + r * RL;
+                    const int row = row0 + r * RL;
                     if (row < K3) {
                         const float a = As[(size_t)pp * AST + row];
                         acc[r][0] = fmaf(a, z4.x, acc[r][0]); acc[r][1] = fmaf(a, z4.y, acc[r][1]);
@@ -268,11 +273,23 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
         }
         __syncthreads();
     }
-    if (active) {
+    if (PG > 1) {   // combine the pixel groups (the last tile's trailing barrier makes As reusable)
+        float* red = As;   // [PG][K3][COUT] <= RL*COUT floats <= CV_TP*AST
+        if (active)
+            *reinterpret_cast<float4*>(red + ((size_t)pgp * K3 + row0) * COUT + c4) =
+                make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        __syncthreads();
+        if (active && pgp == 0)
+            for (int p2 = 1; p2 < PG; ++p2) {
+                const float4 o = *reinterpret_cast<const float4*>(red + ((size_t)p2 * K3 + row0) * COUT + c4);
+                acc[0][0] += o.x; acc[0][1] += o.y; acc[0][2] += o.z; acc[0][3] += o.w;
+            }
+    }
+    if (active && pgp == 0) {
         float* dst = partial + ((size_t)blockIdx.x * 3 + ky) * K3 * COUT;
 #pragma unroll
         for (int r = 0; r < MAXROWS; ++r) {
-            const int row = rl + r * RL;
+            const int row = row0 + r * RL;
             if (row < K3)
                 *reinterpret_cast<float4*>(dst + (size_t)row * COUT + c4) =
                     make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);

@@ -16,20 +16,21 @@
 namespace d2p {
 namespace {
 
+// X rows have stride ldx (>= E)
 __global__ void gather_rows_kernel(const float* __restrict__ table, int vocab_rows, int E,
-                                   const int* __restrict__ ids, int R, float* __restrict__ X) {
+                                   const int* __restrict__ ids, int R, float* __restrict__ X, int ldx) {
     size_t total = (size_t)R * E;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(idx / E), e = (int)(idx % E);
         int id = ids[r];
-        X[idx] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E + e] : 0.f;
+        X[(size_t)r * ldx + e] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E + e] : 0.f;
     }
 }
 
-// in-place BasicLSTMCell on pre-activations G [R,4H]; (c, h) updated in place
+// in-place BasicLSTMCell on pre-activations G [R,4H]; (c, h) updated in place; h rows have stride ldh
 __global__ void lstm_cell_infer_kernel(const float* __restrict__ G, float* __restrict__ c,
-                                       float* __restrict__ h, int R, int H, float forget_bias) {
+                                       float* __restrict__ h, int ldh, int R, int H, float forget_bias) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R * H) return;
     int r = idx / H, u = idx % H;
@@ -38,7 +39,7 @@ __global__ void lstm_cell_infer_kernel(const float* __restrict__ G, float* __res
     float f = sigmoid_f(g[2 * H + u] + forget_bias), o = sigmoid_f(g[3 * H + u]);
     float cn = c[idx] * f + i * j;
     c[idx] = cn;
-    h[idx] = tanhf(cn) * o;
+    h[(size_t)r * ldh + u] = tanhf(cn) * o;
 }
 
 // one warp per row: argmax (lowest index on ties), finished / length bookkeeping
@@ -108,115 +109,178 @@ __global__ void copy_k(float* __restrict__ dst, const float* __restrict__ src, s
 // seen demo i: score = h . keys[b,i,t',:], positions >= len[b,i] masked to -inf, softmax,
 // context_i = alpha . values[b,i]; the k attention vectors [h; context_i] W_a are averaged.
 // W_a is shared and linear, so mean_i([h;ctx_i] W_a) = h W_a[:H] + (mean_i ctx_i) W_a[H:]:
-// this kernel emits mean_i ctx_i.  One CTA per batch element serves all test_k queries,
-// so every key/value row is read from HBM exactly once per decode step.
+// these kernels emit mean_i ctx_i.
+// One CTA per (demo i, batch element b) serves all test_k queries, so every key/value row
+// is read from HBM exactly once per decode step and B*k CTAs keep enough bytes in flight;
+// the per-demo contexts go to a [B,k,tk,H] scratch and a second kernel averages over i in
+// a fixed order (deterministic).
 constexpr int ATT_MAX_Q = 8, ATT_MAX_T = 64, ATT_THREADS = 256;
 
 __global__ void __launch_bounds__(ATT_THREADS)
-luong_pool_attn_kernel(const float* __restrict__ q /*[B*tk,H]*/, const float* __restrict__ keys,
-                       const float* __restrict__ values /*[T,R,H]*/, const int* __restrict__ mem_len,
-                       int B, int k, int tk, int T, int H, float* __restrict__ ctx /*[B*tk,H]*/) {
+luong_attn_partial_kernel(const float* __restrict__ q /*rows b*tk+j, stride ldq*/, int ldq,
+                          const float* __restrict__ keys, const float* __restrict__ values /*[T,R,H]*/,
+                          const int* __restrict__ mem_len, int B, int k, int tk, int T, int H,
+                          float* __restrict__ part /*[B,k,tk,H]*/) {
     extern __shared__ float sm[];
     float* qs = sm;                         // [tk][H]
     float* sc = sm + (size_t)tk * H;        // [tk][ATT_MAX_T]
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int R = B * k, nwarp = ATT_THREADS / 32;
-    for (int idx = tid; idx < tk * H; idx += ATT_THREADS) qs[idx] = q[(size_t)b * tk * H + idx];
+    const int i = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = B * k, nwarp = ATT_THREADS / 32, r = b * k + i;
+    for (int idx = tid; idx < tk * H; idx += ATT_THREADS) {
+        const int j = idx / H, u = idx - j * H;
+        qs[idx] = q[((size_t)b * tk + j) * ldq + u];
+    }
+    int len = mem_len[r];
+    len = len < 0 ? 0 : (len > T ? T : len);
+    __syncthreads();
+    // scores: one warp per memory position, the row's loads issued before any use
+    for (int t = warp; t < len; t += nwarp) {
+        const float* krow = keys + ((size_t)t * R + r) * H;
+        float part_s[ATT_MAX_Q];
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_Q; ++j) part_s[j] = 0.f;
+        for (int u0 = 0; u0 < H; u0 += 512) {
+            float4 kv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = u0 + e * 128 + lane * 4;
+                kv[e] = u < H ? __ldcs(reinterpret_cast<const float4*>(krow + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = u0 + e * 128 + lane * 4;
+                if (u < H) {
+#pragma unroll
+                    for (int j = 0; j < ATT_MAX_Q; ++j)
+                        if (j < tk) {
+                            const float4 qv = *reinterpret_cast<const float4*>(qs + (size_t)j * H + u);
+                            part_s[j] += kv[e].x * qv.x + kv[e].y * qv.y + kv[e].z * qv.z + kv[e].w * qv.w;
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_Q; ++j)
+            if (j < tk) {
+                float sv = warp_sum(part_s[j]);
+                if (lane == 0) sc[j * ATT_MAX_T + t] = sv;
+            }
+    }
+    __syncthreads();
+    // masked softmax over t' < len: warp j normalises query j
+    for (int j = warp; j < tk; j += nwarp) {
+        float m = -INFINITY;
+        for (int t = lane; t < len; t += 32) m = fmaxf(m, sc[j * ATT_MAX_T + t]);
+        m = warp_max(m);
+        float z = 0.f;
+        for (int t = lane; t < len; t += 32) z += expf(sc[j * ATT_MAX_T + t] - m);
+        z = warp_sum(z);
+        for (int t = lane; t < len; t += 32)
+            sc[j * ATT_MAX_T + t] = expf(sc[j * ATT_MAX_T + t] - m) / z;
+    }
+    __syncthreads();
+    // context: a thread owns 4 consecutive hidden units; when H/4 < ATT_THREADS the thread
+    // groups interleave the memory positions and are combined through shared memory.
+    // Value rows are independent loads, 4 positions in flight per thread.
+    const int q4 = H / 4, ng = ATT_THREADS / q4 > 0 ? ATT_THREADS / q4 : 1;
+    const int grp = tid / q4, u = (tid - grp * q4) * 4;
+    float* red = sc + (size_t)tk * ATT_MAX_T;     // [ng][tk][H]
     float acc[ATT_MAX_Q][4];
 #pragma unroll
     for (int j = 0; j < ATT_MAX_Q; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    __syncthreads();
-    for (int i = 0; i < k; ++i) {
-        const int r = b * k + i;
-        int len = mem_len[r];
-        len = len < 0 ? 0 : (len > T ? T : len);
-        // scores: one warp per memory position
-        for (int t = warp; t < len; t += nwarp) {
-            const float* krow = keys + ((size_t)t * R + r) * H;
-            float part[ATT_MAX_Q];
+    if (grp < ng) {
+        const float* vbase = values + (size_t)r * H + u;
+        const size_t tstride = (size_t)R * H;
+        int t = grp;
+        for (; t + 3 * ng < len; t += 4 * ng) {
+            float4 v[4];
 #pragma unroll
-            for (int j = 0; j < ATT_MAX_Q; ++j) part[j] = 0.f;
-            for (int u = lane * 4; u < H; u += 128) {
-                float4 kv = *reinterpret_cast<const float4*>(krow + u);
+            for (int e = 0; e < 4; ++e)
+                v[e] = __ldcs(reinterpret_cast<const float4*>(vbase + (size_t)(t + e * ng) * tstride));
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
 #pragma unroll
                 for (int j = 0; j < ATT_MAX_Q; ++j)
                     if (j < tk) {
-                        const float* qj = qs + (size_t)j * H + u;
-                        part[j] += kv.x * qj[0] + kv.y * qj[1] + kv.z * qj[2] + kv.w * qj[3];
+                        const float a = sc[j * ATT_MAX_T + t + e * ng];
+                        acc[j][0] = fmaf(a, v[e].x, acc[j][0]); acc[j][1] = fmaf(a, v[e].y, acc[j][1]);
+                        acc[j][2] = fmaf(a, v[e].z, acc[j][2]); acc[j][3] = fmaf(a, v[e].w, acc[j][3]);
                     }
-            }
+        }
+        for (; t < len; t += ng) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(vbase + (size_t)t * tstride));
 #pragma unroll
             for (int j = 0; j < ATT_MAX_Q; ++j)
                 if (j < tk) {
-                    float s = warp_sum(part[j]);
-                    if (lane == 0) sc[j * ATT_MAX_T + t] = s;
+                    const float a = sc[j * ATT_MAX_T + t];
+                    acc[j][0] = fmaf(a, v.x, acc[j][0]); acc[j][1] = fmaf(a, v.y, acc[j][1]);
+                    acc[j][2] = fmaf(a, v.z, acc[j][2]); acc[j][3] = fmaf(a, v.w, acc[j][3]);
                 }
         }
-        __syncthreads();
-        // masked softmax over t' < len: warp j normalises query j
-        for (int j = warp; j < tk; j += nwarp) {
-            float m = -INFINITY;
-            for (int t = lane; t < len; t += 32) m = fmaxf(m, sc[j * ATT_MAX_T + t]);
-            m = warp_max(m);
-            float z = 0.f;
-            for (int t = lane; t < len; t += 32) z += expf(sc[j * ATT_MAX_T + t] - m);
-            z = warp_sum(z);
-            for (int t = lane; t < len; t += 32)
-                sc[j * ATT_MAX_T + t] = expf(sc[j * ATT_MAX_T + t] - m) / z;
+        if (grp > 0) {
+#pragma unroll
+            for (int j = 0; j < ATT_MAX_Q; ++j)
+                if (j < tk)
+                    *reinterpret_cast<float4*>(red + ((size_t)grp * tk + j) * H + u) =
+                        make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
         }
-        __syncthreads();
-        // context: each thread owns hidden units tid, tid+256, ...; value rows read once
-        for (int t = 0; t < len; ++t) {
-            const float* vrow = values + ((size_t)t * R + r) * H;
+    }
+    __syncthreads();
+    if (grp == 0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int u = tid + e * ATT_THREADS;
-                if (u < H) {
-                    const float v = vrow[u];
-#pragma unroll
-                    for (int j = 0; j < ATT_MAX_Q; ++j)
-                        if (j < tk) acc[j][e] = fmaf(sc[j * ATT_MAX_T + t], v, acc[j][e]);
+        for (int j = 0; j < ATT_MAX_Q; ++j)
+            if (j < tk) {
+                float4 a = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                for (int g2 = 1; g2 < ng; ++g2) {
+                    const float4 p = *reinterpret_cast<const float4*>(red + ((size_t)g2 * tk + j) * H + u);
+                    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
                 }
+                *reinterpret_cast<float4*>(part + (((size_t)b * k + i) * tk + j) * H + u) = a;
             }
-        }
-        __syncthreads();
+    }
+}
+
+// ctx[(b*tk+j)*ldc + u] = (1/k) sum_i part[b,i,j,u], i in increasing order
+__global__ void luong_attn_mean_kernel(const float* __restrict__ part, int B, int k, int tk, int H,
+                                       float* __restrict__ ctx, int ldc) {
+    const size_t n4 = (size_t)B * tk * (H / 4);
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= n4) return;
+    const int u = (int)(idx % (H / 4)) * 4;
+    const size_t bj = idx / (H / 4);
+    const int j = (int)(bj % tk);
+    const size_t b = bj / tk;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < k; ++i) {
+        const float4 p = *reinterpret_cast<const float4*>(part + ((b * k + i) * tk + j) * H + u);
+        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
     }
     const float inv = 1.f / (float)k;
-#pragma unroll
-    for (int j = 0; j < ATT_MAX_Q; ++j)
-        if (j < tk)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int u = tid + e * ATT_THREADS;
-                if (u < H) ctx[((size_t)b * tk + j) * H + u] = acc[j][e] * inv;
-            }
+    *reinterpret_cast<float4*>(ctx + bj * ldc + u) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
 }
 
 // x[r2,:] = table[id] with id = (t == 0 ? start_id : tokens[r2, t-1]); out of range -> 0
 __global__ void gather_step_kernel(const float* __restrict__ table, int vocab_rows, int E,
                                    const int* __restrict__ tokens, int R2, int L, int t, int start_id,
-                                   float* __restrict__ X) {
+                                   float* __restrict__ X, int ldx) {
     size_t total = (size_t)R2 * E;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(idx / E), e = (int)(idx % E);
         int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
-        X[idx] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E + e] : 0.f;
+        X[(size_t)r * ldx + e] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E + e] : 0.f;
     }
 }
 
+// out[(b*tk+j)*ldo + u] = S ? S[b,u] : 0
 __global__ void bcast_rows_kernel(const float* __restrict__ S, int B, int tk, int H,
-                                  float* __restrict__ out) {
+                                  float* __restrict__ out, int ldo) {
     size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * tk * H) return;
-    out[idx] = S[(idx / ((size_t)tk * H)) * H + idx % H];
-}
-
-__global__ void fill_zero_k(float* __restrict__ x, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) x[i] = 0.f;
+    const size_t row = idx / H;
+    out[row * ldo + idx % H] = S ? S[(row / tk) * H + idx % H] : 0.f;
 }
 
 // out[row, :] = [A[row, :F1] ; Bm[row, :F2]]
@@ -246,23 +310,47 @@ extern "C" int d2p_concat_cols(const float* A, int F1, const float* Bm, int F2, 
     return 0;
 }
 
-extern "C" int d2p_luong_pool_attention(const float* q, const float* keys, const float* values,
+extern "C" size_t d2p_luong_pool_attention_ws_bytes(int B, int k, int tk, int H) {
+    return (size_t)B * k * tk * H * sizeof(float);   // per-demo contexts [B,k,tk,H]
+}
+
+// q rows (b*tk + j) have stride ldq, ctx rows stride ldc (both >= H, multiples of 4 floats)
+extern "C" int d2p_luong_pool_attention(const float* q, int ldq, const float* keys, const float* values,
                                         const int* mem_len, int B, int k, int tk, int T, int H,
-                                        float* ctx, void* stream) {
-    D2P_REQUIRE(q && keys && values && mem_len && ctx, "luong attention: null buffer");
-    D2P_REQUIRE(tk >= 1 && tk <= ATT_MAX_Q && T <= ATT_MAX_T && H % 4 == 0 && H <= 4 * ATT_THREADS,
+                                        float* ctx, int ldc, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(q && keys && values && mem_len && ctx && ws, "luong attention: null buffer");
+    D2P_REQUIRE(B > 0 && k > 0 && tk >= 1 && tk <= ATT_MAX_Q && T >= 1 && T <= ATT_MAX_T && H >= 4 &&
+                H % 4 == 0 && H <= 4 * ATT_THREADS,
                 "luong attention: unsupported dims (test_k=%d T=%d H=%d)", tk, T, H);
-    size_t smem = ((size_t)tk * H + (size_t)tk * ATT_MAX_T) * sizeof(float);
-    luong_pool_attn_kernel<<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>(q, keys, values, mem_len, B, k,
-                                                                          tk, T, H, ctx);
+    D2P_REQUIRE(ldq >= H && ldc >= H && ldq % 4 == 0 && ldc % 4 == 0, "luong attention: bad row strides");
+    D2P_REQUIRE(ws_bytes >= d2p_luong_pool_attention_ws_bytes(B, k, tk, H), "luong attention: workspace too small");
+    D2P_REQUIRE((((uintptr_t)q | (uintptr_t)keys | (uintptr_t)values | (uintptr_t)ctx | (uintptr_t)ws) & 15) == 0,
+                "luong attention: buffers must be 16-byte aligned");
+    const int q4 = H / 4, ng = ATT_THREADS / q4 > 0 ? ATT_THREADS / q4 : 1;
+    const size_t smem = ((size_t)tk * H + (size_t)tk * ATT_MAX_T + (ng > 1 ? (size_t)ng * tk * H : 0)) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(luong_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            100 * 1024));
+        attr = true;
+    }
+    D2P_REQUIRE(smem <= 100 * 1024, "luong attention: shared memory budget exceeded");
+    float* part = (float*)ws;
+    luong_attn_partial_kernel<<<dim3(k, B), ATT_THREADS, smem, st>>>(q, ldq, keys, values, mem_len, B, k, tk, T,
+                                                                     H, part);
+    D2P_CHECK_LAUNCH();
+    const size_t n4 = (size_t)B * tk * (H / 4);
+    luong_attn_mean_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(part, B, k, tk, H, ctx, ldc);
     D2P_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" size_t d2p_induction_decode_ws_bytes(int B, int tk, int H) {
+extern "C" size_t d2p_induction_decode_ws_bytes(int B, int k, int tk, int H) {
     size_t R2 = (size_t)B * tk;
-    // x | att | ctx | h | c [R2,H] | gates [R2,4H] | ids, finished [R2] | all_done[64]
-    return (R2 * 9 * H) * sizeof(float) + (2 * R2 + 64) * sizeof(int) + 256;
+    // [x|att|h|ctx] [R2,4H] | c [R2,H] | gates [R2,4H] | per-demo contexts | ids, finished [R2] | all_done[64]
+    return (R2 * 9 * H) * sizeof(float) + d2p_luong_pool_attention_ws_bytes(B, k, tk, H) +
+           (2 * R2 + 64) * sizeof(int) + 256;
 }
 
 // Attention-LSTM action decoder of the induction baseline over R2 = B*test_k rows
@@ -270,6 +358,9 @@ extern "C" size_t d2p_induction_decode_ws_bytes(int B, int tk, int H) {
 // range -> zero row); tokens == NULL: greedy (start id = A, end id = A-1).
 // Initial cell state reproduces the reference's swap (model_induction.py:674-676):
 // c := demo_h_summary, h := demo_c_summary.  logits [Tdec, R2, A] time-major.
+// The step state lives in one [R2, 4H] buffer  x | attention | h | context  so that the
+// cell's input contraction [x; attention_{t-1}; h_{t-1}] * W (K = 3H) and the attention
+// layer [h; context] * W_a (K = 2H) are each ONE product over adjacent columns.
 extern "C" int d2p_induction_decode(const float* keys, const float* values, const int* mem_len, int B,
                                     int k, int tk, int T, int H, const float* h_sum,
                                     const float* c_sum, const float* table, int A, const float* Wcell,
@@ -279,42 +370,45 @@ extern "C" int d2p_induction_decode(const float* keys, const float* values, cons
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(keys && values && mem_len && h_sum && c_sum && table && Wcell && bcell && Wa && proj &&
                 logits && ws, "induction decode: null buffer");
-    D2P_REQUIRE(ws_bytes >= d2p_induction_decode_ws_bytes(B, tk, H), "induction decode: workspace too small");
+    D2P_REQUIRE(ws_bytes >= d2p_induction_decode_ws_bytes(B, k, tk, H), "induction decode: workspace too small");
+    D2P_REQUIRE(H % 4 == 0, "induction decode: H must be a multiple of 4");
     const bool greedy = tokens == nullptr;
     if (greedy) D2P_REQUIRE(out_tokens && lengths, "induction decode: greedy needs token/length outputs");
-    const int R2 = B * tk, G4 = 4 * H;
+    const int R2 = B * tk, G4 = 4 * H, LD = 4 * H;
     const size_t RH = (size_t)R2 * H;
-    float* x = (float*)ws;
-    float* att = x + RH; float* ctx = att + RH; float* h = ctx + RH; float* c = h + RH;
+    float* xs = (float*)ws;                       // [R2, 4H]
+    float* x = xs; float* att = xs + H; float* h = xs + 2 * H; float* ctx = xs + 3 * H;
+    float* c = xs + (size_t)R2 * LD;
     float* gates = c + RH;
-    int* ids = (int*)(gates + (size_t)R2 * G4);
+    float* part = gates + (size_t)R2 * G4;
+    const size_t part_bytes = d2p_luong_pool_attention_ws_bytes(B, k, tk, H);
+    int* ids = (int*)((char*)part + part_bytes);
     int* finished = ids + R2; int* all_done = finished + R2;
     const int eb = cdiv((long long)RH, 256);
-    bcast_rows_kernel<<<eb, 256, 0, st>>>(h_sum, B, tk, H, c);   // swapped on purpose (F8)
+    bcast_rows_kernel<<<eb, 256, 0, st>>>(h_sum, B, tk, H, c, H);   // swapped on purpose (F8)
     D2P_CHECK_LAUNCH();
-    bcast_rows_kernel<<<eb, 256, 0, st>>>(c_sum, B, tk, H, h);
+    bcast_rows_kernel<<<eb, 256, 0, st>>>(c_sum, B, tk, H, h, LD);
     D2P_CHECK_LAUNCH();
-    fill_zero_k<<<eb, 256, 0, st>>>(att, RH);
+    bcast_rows_kernel<<<eb, 256, 0, st>>>(nullptr, B, tk, H, att, LD);   // attention_0 = 0
     D2P_CHECK_LAUNCH();
     if (greedy) {
         greedy_init_kernel<<<cdiv(R2, 256), 256, 0, st>>>(ids, finished, lengths, all_done, R2, tk, A);
         D2P_CHECK_LAUNCH();
     }
     for (int t = 0; t < Tdec; ++t) {
-        if (greedy) gather_rows_kernel<<<eb, 256, 0, st>>>(table, A + 1, H, ids, R2, x);
-        else gather_step_kernel<<<eb, 256, 0, st>>>(table, A + 1, H, tokens, R2, Tdec, t, A + 1, x);
+        if (greedy) gather_rows_kernel<<<eb, 256, 0, st>>>(table, A + 1, H, ids, R2, x, LD);
+        else gather_step_kernel<<<eb, 256, 0, st>>>(table, A + 1, H, tokens, R2, Tdec, t, A + 1, x, LD);
         D2P_CHECK_LAUNCH();
-        // cell input = [emb ; attention_{t-1}], recurrent input h: kernel rows [0,H) [H,2H) [2H,3H)
-        D2P_TRY(gemm(st, false, false, R2, G4, H, 1.f, x, H, Wcell, G4, 0.f, gates, G4, bcell, GEMM_CONST_B));
-        D2P_TRY(gemm(st, false, false, R2, G4, H, 1.f, att, H, Wcell + (size_t)H * G4, G4, 1.f, gates, G4, nullptr, GEMM_CONST_B));
-        D2P_TRY(gemm(st, false, false, R2, G4, H, 1.f, h, H, Wcell + (size_t)2 * H * G4, G4, 1.f, gates, G4, nullptr, GEMM_CONST_B));
-        lstm_cell_infer_kernel<<<eb, 256, 0, st>>>(gates, c, h, R2, H, 1.0f);
+        // kernel rows [0,H) take the embedding, [H,2H) attention_{t-1}, [2H,3H) h_{t-1}
+        D2P_TRY(gemm(st, false, false, R2, G4, 3 * H, 1.f, xs, LD, Wcell, G4, 0.f, gates, G4, bcell, GEMM_CONST_B));
+        lstm_cell_infer_kernel<<<eb, 256, 0, st>>>(gates, c, h, LD, R2, H, 1.0f);
         D2P_CHECK_LAUNCH();
-        D2P_TRY(d2p_luong_pool_attention(h, keys, values, mem_len, B, k, tk, T, H, ctx, stream));
-        D2P_TRY(gemm(st, false, false, R2, H, H, 1.f, h, H, Wa, H, 0.f, att, H, nullptr, GEMM_CONST_B));
-        D2P_TRY(gemm(st, false, false, R2, H, H, 1.f, ctx, H, Wa + (size_t)H * H, H, 1.f, att, H, nullptr, GEMM_CONST_B));
+        D2P_TRY(d2p_luong_pool_attention(h, LD, keys, values, mem_len, B, k, tk, T, H, ctx, LD, part, part_bytes,
+                                         stream));
+        // attention_t = [h_t; mean context] * W_a  (reads columns [2H,4H), writes [H,2H))
+        D2P_TRY(gemm(st, false, false, R2, H, 2 * H, 1.f, h, LD, Wa, H, 0.f, att, LD, nullptr, GEMM_CONST_B));
         float* lt = logits + (size_t)t * R2 * A;
-        D2P_TRY(gemm(st, false, false, R2, A, H, 1.f, att, H, proj, A, 0.f, lt, A, nullptr, GEMM_CONST_B));
+        D2P_TRY(gemm(st, false, false, R2, A, H, 1.f, att, LD, proj, A, 0.f, lt, A, nullptr, GEMM_CONST_B));
         if (greedy) {
             greedy_update_kernel<<<cdiv(R2, 8), 256, 0, st>>>(lt, R2, A, t, Tdec, A - 1, ids, finished, lengths,
                                                               out_tokens + (size_t)t * R2, all_done, tk);
@@ -359,11 +453,11 @@ extern "C" int d2p_lstm_decoder_greedy(const float* table, int vocab_rows, int E
     D2P_CHECK_LAUNCH();
     for (int t = 0; t < max_len; ++t) {
         size_t tot = (size_t)R * E;
-        gather_rows_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(table, vocab_rows, E, ids, R, x);
+        gather_rows_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(table, vocab_rows, E, ids, R, x, E);
         D2P_CHECK_LAUNCH();
         D2P_TRY(gemm(st, false, false, R, G4, E, 1.f, x, E, Wx, G4, 0.f, gates, G4, b, GEMM_CONST_B));
         D2P_TRY(gemm(st, false, false, R, G4, H, 1.f, h, H, Wh, G4, 1.f, gates, G4, nullptr, GEMM_CONST_B));
-        lstm_cell_infer_kernel<<<cdiv((long long)R * H, 256), 256, 0, st>>>(gates, c, h, R, H, 1.0f);
+        lstm_cell_infer_kernel<<<cdiv((long long)R * H, 256), 256, 0, st>>>(gates, c, h, H, R, H, 1.0f);
         D2P_CHECK_LAUNCH();
         float* lt = logits + (size_t)t * R * V;
         D2P_TRY(gemm(st, false, false, R, V, H, 1.f, h, H, proj, V, 0.f, lt, V, nullptr, GEMM_CONST_B));

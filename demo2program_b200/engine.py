@@ -626,6 +626,81 @@ class Engine:
         torch.cuda.current_stream(self.dev).synchronize()
         return float(self.h_loss[0])
 
+    def _input_pairs(self):
+        h = self.h_in
+        pairs = [(self.d_frames, h['s_h']), (self.d_demo_len_f, h['demo_len']),
+                 (self.d_prog_len_f, h['program_len']), (self.d_prog_tok, h['program_tokens'])]
+        if self.model == 'full':
+            pairs += [(self.d_act_tok, h['a_h_tokens']), (self.d_per, h['per'])]
+        return pairs
+
+    def train_steps(self, batches):
+        """Public API for a training loop (reference trainer.py:126-160): iterates host
+        batches and yields each step's loss.  The input path is double-buffered: while
+        step i runs, batch i+1 is copied into the second pinned staging set and sent to
+        the device on a copy stream, and step i's loss is read back after step i+1 has
+        been enqueued.  Every step still pays its own H2D and its loss D2H, but they
+        overlap the neighbouring steps' kernels and the device queue never drains."""
+        dev = self.dev
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, '_pf'):
+            pairs = self._input_pairs()
+            self._pf = {
+                'stream': torch.cuda.Stream(dev),
+                'host': [[torch.empty_like(s).pin_memory() for _, s in pairs] for _ in range(2)],
+                'dev': [[torch.empty_like(d) for d, _ in pairs] for _ in range(2)],
+                'ready': [torch.cuda.Event() for _ in range(2)],
+                'free': [torch.cuda.Event() for _ in range(2)],
+                'done': [torch.cuda.Event() for _ in range(2)],
+                'loss': [torch.zeros(4).pin_memory() for _ in range(2)],
+            }
+        pf = self._pf
+        keys = ['s_h', 'demo_len', 'program_len', 'program_tokens'] + \
+            (['a_h_tokens', 'per'] if self.model == 'full' else [])
+
+        def prefetch(batch, slot, wait_free):
+            hs, ds = pf['host'][slot], pf['dev'][slot]
+            if wait_free:
+                pf['free'][slot].synchronize()     # step that last read this slot has consumed it
+            for key, hbuf in zip(keys, hs):
+                hbuf.numpy()[...] = np.asarray(batch[key]).reshape(hbuf.shape)
+            with torch.cuda.stream(pf['stream']):
+                for hbuf, dbuf in zip(hs, ds):
+                    dbuf.copy_(hbuf, non_blocking=True)
+                pf['ready'][slot].record(pf['stream'])
+
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        prefetch(nxt, 0, False)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            # enqueue step i behind step i-1 (the device queue never drains)
+            main.wait_event(pf['ready'][slot])
+            for (d, _), sdev in zip(self._input_pairs(), pf['dev'][slot]):
+                d.copy_(sdev, non_blocking=True)
+            pf['free'][slot].record(main)
+            self.train_step_device(True)
+            pf['loss'][slot].copy_(self.loss, non_blocking=True)
+            pf['done'][slot].record(main)
+            # read back step i-1's loss while step i runs
+            if i >= 1:
+                pf['done'][slot ^ 1].synchronize()
+                yield float(pf['loss'][slot ^ 1][0])
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                prefetch(nxt, slot ^ 1, i >= 1)
+            i += 1
+        last = (i - 1) & 1
+        pf['done'][last].synchronize()
+        yield float(pf['loss'][last][0])
+
     # ------------------------------------------------------------------ outputs
     def pred_program(self):
         """[B, V, L] logits, the reference's `pred_program` layout

@@ -81,7 +81,7 @@ class InductionEngine:
         F = lib.d2p_conv_encoder_feature_dim(C.byref(d))
         self.F = F
         self.conv_saved = z(lib.d2p_conv_encoder_saved_floats(C.byref(d)))
-        ws = max(lib.d2p_conv_encoder_ws_bytes(C.byref(d)), lib.d2p_induction_decode_ws_bytes(B, tk, H))
+        ws = max(lib.d2p_conv_encoder_ws_bytes(C.byref(d)), lib.d2p_induction_decode_ws_bytes(B, k, tk, H))
         self.ws_bytes = (ws + 255) // 256 * 256
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.feat, self.per_tm, self.X = z(T, R, F), z(T, R, Pd), z(T, R, F + Pd)

@@ -143,10 +143,13 @@ int d2p_lstm_decoder_greedy(const float* table, int vocab_rows, int E, const flo
  * reference models/baselines/model_induction.py:25-53, 107-182, 638-709.
  * keys/values [T, R, H] time-major (R = B*k, keys = values * W_mem), mem_len [R];
  * queries q [B*test_k, H]; ctx = mean over the k memories of the attention contexts. */
-int d2p_luong_pool_attention(const float* q, const float* keys, const float* values,
+size_t d2p_luong_pool_attention_ws_bytes(int B, int k, int tk, int H);
+/* q rows have stride ldq floats, ctx rows stride ldc (>= H, multiples of 4; 16-byte aligned
+ * buffers); ws holds the per-memory contexts [B, k, test_k, H] that are averaged in order. */
+int d2p_luong_pool_attention(const float* q, int ldq, const float* keys, const float* values,
                              const int* mem_len, int B, int k, int tk, int T, int H, float* ctx,
-                             void* stream);
-size_t d2p_induction_decode_ws_bytes(int B, int tk, int H);
+                             int ldc, void* ws, size_t ws_bytes, void* stream);
+size_t d2p_induction_decode_ws_bytes(int B, int k, int tk, int H);
 /* tokens [B*test_k, Tdec] int32 = teacher forcing, NULL = greedy (start A, end A-1).
  * logits [Tdec, B*test_k, A]; greedy also fills out_tokens [Tdec, B*test_k], lengths. */
 int d2p_induction_decode(const float* keys, const float* values, const int* mem_len, int B, int k,

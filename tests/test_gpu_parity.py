@@ -71,6 +71,21 @@ def test_graph_replay_equals_eager():
     assert e2.launches_per_step > 0
 
 
+def test_pipelined_train_steps_equal_synchronous_steps():
+    """Engine.train_steps (double-buffered H2D) must give exactly the losses and
+    parameters of train_step called batch by batch."""
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('full', batch_size=4, k=3)
+    _, e1, _, _, _ = oracle_and_engine(cfg, use_graph=True)
+    _, e2, _, _, _ = oracle_and_engine(cfg, use_graph=True)
+    batches = [make_batch(cfg, seed=40 + i) for i in range(5)]
+    l1 = [e1.train_step(b) for b in batches]
+    l2 = list(e2.train_steps(iter(batches)))
+    assert l1 == l2
+    assert torch.equal(e1.params, e2.params)
+    assert list(e2.train_steps(iter([]))) == []
+
+
 def test_f32_frames_equal_u8_frames():
     cfg = karel_config('synthesis_baseline', batch_size=4, k=2)
     _, e1, batch, _, _ = oracle_and_engine(cfg, use_graph=False)
@@ -229,10 +244,23 @@ def test_luong_attention_kernel_against_torch():
     ln = torch.randint(1, T + 1, (B * k,), generator=g).int()
     ctx = torch.zeros(B * tk, H, device='cuda')
     qd, kd, vd, ld = q.cuda(), keys.cuda(), vals.cuda(), ln.cuda()
-    rc = lib.d2p_luong_pool_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), ld.data_ptr(), B, k, tk,
-                                      T, H, ctx.data_ptr(), None)
+    ws = torch.zeros(lib.d2p_luong_pool_attention_ws_bytes(B, k, tk, H), dtype=torch.uint8, device='cuda')
+    rc = lib.d2p_luong_pool_attention(qd.data_ptr(), H, kd.data_ptr(), vd.data_ptr(), ld.data_ptr(), B, k, tk,
+                                      T, H, ctx.data_ptr(), H, ws.data_ptr(), ws.numel(), None)
     assert rc == 0, lib.d2p_last_error()
     torch.cuda.synchronize()
+    # strided query / context rows (the decoder keeps them inside its [x|att|h|ctx] buffer)
+    wide_q = torch.zeros(B * tk, 3 * H, device='cuda')
+    wide_q[:, H:2 * H] = qd
+    wide_c = torch.zeros(B * tk, 2 * H, device='cuda')
+    rc = lib.d2p_luong_pool_attention(wide_q.data_ptr() + 4 * H, 3 * H, kd.data_ptr(), vd.data_ptr(),
+                                      ld.data_ptr(), B, k, tk, T, H, wide_c.data_ptr() + 4 * H, 2 * H,
+                                      ws.data_ptr(), ws.numel(), None)
+    assert rc == 0, lib.d2p_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(wide_c[:, H:], ctx) and float(wide_c[:, :H].abs().max()) == 0.0
+    assert lib.d2p_luong_pool_attention(qd.data_ptr(), H, kd.data_ptr(), vd.data_ptr(), ld.data_ptr(), B, k,
+                                        tk, T, H, ctx.data_ptr(), H, ws.data_ptr(), 16, None) != 0
     K4 = keys.double().permute(1, 0, 2).reshape(B, k, T, H)
     V4 = vals.double().permute(1, 0, 2).reshape(B, k, T, H)
     L2 = ln.long().reshape(B, k)
