@@ -68,6 +68,82 @@ colstats_partial(const float* __restrict__ X, const float* __restrict__ DY,
     }
 }
 
+// Same reduction for C % 4 == 0 and 16-byte aligned rows: a thread owns a channel quad,
+// 16-byte loads, four rows in flight (the large ViZDoom activations are HBM-bound here).
+// smem: float red[RL][CT4][8]
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+colstats_partial_v4(const float* __restrict__ X, const float* __restrict__ DY,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    long long rows_per_slice, int C, int seg, int nsl, int rows_per_chunk,
+                    float2* __restrict__ partial) {
+    extern __shared__ float red4[];
+    const int chunk = blockIdx.x, sl = blockIdx.y, nchunk = gridDim.x;
+    const int C4 = C / 4;
+    const int CT = C4 < kThreads ? C4 : kThreads;
+    const int RL = kThreads / CT;
+    const int rl = threadIdx.x / CT, ct = threadIdx.x % CT;
+    const int cq = blockIdx.z * CT + ct;
+    const bool valid = rl < RL && cq < C4;
+    long long q0 = (long long)chunk * rows_per_chunk;
+    long long q1 = q0 + rows_per_chunk;
+    if (q1 > rows_per_slice) q1 = rows_per_slice;
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+        float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu;
+        if (MODE == 1) {
+            mu = *reinterpret_cast<const float4*>(mean + (size_t)sl * C + cq * 4);
+            rs = *reinterpret_cast<const float4*>(rstd + (size_t)sl * C + cq * 4);
+        }
+        for (long long q = q0 + rl; q < q1; q += 4LL * RL) {
+            float4 x[4], dy[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long qe = q + (long long)e * RL;
+                if (qe < q1) {
+                    const size_t off = (size_t)slice_row(qe, seg, nsl, sl) * C + cq * 4;
+                    x[e] = *reinterpret_cast<const float4*>(X + off);
+                    if (MODE == 1) dy[e] = *reinterpret_cast<const float4*>(DY + off);
+                } else {
+                    x[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == 1) { dy[e] = x[e]; x[e] = mu; }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (MODE == 0) {
+                    sa[0] += x[e].x; sa[1] += x[e].y; sa[2] += x[e].z; sa[3] += x[e].w;
+                    sb[0] += x[e].x * x[e].x; sb[1] += x[e].y * x[e].y;
+                    sb[2] += x[e].z * x[e].z; sb[3] += x[e].w * x[e].w;
+                } else {
+                    sa[0] += dy[e].x; sa[1] += dy[e].y; sa[2] += dy[e].z; sa[3] += dy[e].w;
+                    sb[0] += dy[e].x * (x[e].x - mu.x) * rs.x; sb[1] += dy[e].y * (x[e].y - mu.y) * rs.y;
+                    sb[2] += dy[e].z * (x[e].z - mu.z) * rs.z; sb[3] += dy[e].w * (x[e].w - mu.w) * rs.w;
+                }
+            }
+        }
+    }
+    if (rl < RL) {
+        float* d = red4 + ((size_t)rl * CT + ct) * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d[j] = sa[j]; d[4 + j] = sb[j]; }
+    }
+    __syncthreads();
+    // thread (ct, j): channel cq*4 + j, summed over the row lanes in order
+    for (int w = threadIdx.x; w < CT * 4; w += kThreads) {
+        const int ct2 = w / 4, j = w % 4;
+        const int cq2 = blockIdx.z * CT + ct2;
+        if (cq2 < C4) {
+            float a = 0.f, b = 0.f;
+            for (int r = 0; r < RL; ++r) {
+                const float* d = red4 + ((size_t)r * CT + ct2) * 8;
+                a += d[j]; b += d[4 + j];
+            }
+            partial[((size_t)sl * nchunk + chunk) * C + cq2 * 4 + j] = make_float2(a, b);
+        }
+    }
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -189,6 +265,40 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ A, const float* __
     }
 }
 
+// 16-byte variant for the contiguous (unpermuted) case, C % 4 == 0, rows*C/4 < 2^32
+template <bool ACT>
+__global__ void bn_bwd_apply_v4(const float4* __restrict__ A, const float4* __restrict__ DY,
+                                float4* __restrict__ DZ, unsigned total4, unsigned C4, unsigned seg,
+                                unsigned nsl, const float4* __restrict__ gamma, const float4* __restrict__ mean,
+                                const float4* __restrict__ rstd, const float4* __restrict__ k1,
+                                const float4* __restrict__ k2) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+        float4 a[2], dy[2];
+        unsigned idx[2] = {i0, i0 + stride};
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            if (idx[e] < total4) { a[e] = A[idx[e]]; dy[e] = DY[idx[e]]; }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (idx[e] >= total4) continue;
+            const unsigned row = idx[e] / C4, cq = idx[e] - row * C4;
+            const unsigned p = ((row / seg) % nsl) * C4 + cq;
+            const float4 g = gamma[cq], rs = rstd[p], mu = mean[p], q1 = k1[p], q2 = k2[p];
+            float4 o;
+            o.x = g.x * rs.x * (dy[e].x - q1.x - (a[e].x - mu.x) * rs.x * q2.x);
+            o.y = g.y * rs.y * (dy[e].y - q1.y - (a[e].y - mu.y) * rs.y * q2.y);
+            o.z = g.z * rs.z * (dy[e].z - q1.z - (a[e].z - mu.z) * rs.z * q2.z);
+            o.w = g.w * rs.w * (dy[e].w - q1.w - (a[e].w - mu.w) * rs.w * q2.w);
+            if (ACT) {
+                o.x *= lrelu_grad_from_out(a[e].x); o.y *= lrelu_grad_from_out(a[e].y);
+                o.z *= lrelu_grad_from_out(a[e].z); o.w *= lrelu_grad_from_out(a[e].w);
+            }
+            DZ[idx[e]] = o;
+        }
+    }
+}
+
 __global__ void colsum_finalize(const float2* __restrict__ partial, int nchunk, int C,
                                 float* __restrict__ out, float beta) {
     const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -232,6 +342,27 @@ inline int ew_blocks(long long total) {
 
 }  // namespace
 
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// launches the column-statistics reduction (vectorised when the layout allows)
+template <int MODE>
+int launch_colstats(cudaStream_t st, const float* X, const float* DY, const float* mean, const float* rstd,
+                    long long rows_per_slice, int C, int seg, int nsl, int nchunk, int rpc, float2* ws) {
+    if (C % 4 == 0 && al16(X) && (MODE == 0 || (al16(DY) && al16(mean) && al16(rstd)))) {
+        const int C4 = C / 4, CT = C4 < kThreads ? C4 : kThreads;
+        const size_t sm = (size_t)(kThreads / CT) * CT * 8 * sizeof(float);
+        colstats_partial_v4<MODE><<<dim3(nchunk, nsl, cdiv(C4, CT)), kThreads, sm, st>>>(
+            X, DY, mean, rstd, rows_per_slice, C, seg, nsl, rpc, ws);
+    } else {
+        const int CT = C < kThreads ? C : kThreads;
+        const size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
+        colstats_partial<MODE><<<dim3(nchunk, nsl, cdiv(C, CT)), kThreads, sm, st>>>(
+            X, DY, mean, rstd, rows_per_slice, C, seg, nsl, rpc, ws);
+    }
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
 size_t bn_ws_bytes(long long rows, int C, int nsl) {
     int rpc;
     int nchunk = pick_chunks(rows / nsl, nsl, &rpc);
@@ -249,11 +380,8 @@ int bn_forward_stats(cudaStream_t st, const float* X, long long rows, int C, int
     if (training) {
         nchunk = pick_chunks(rows / nsl, nsl, &rpc);
         D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
-        int CT = C < kThreads ? C : kThreads;
-        size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-        colstats_partial<0><<<dim3(nchunk, nsl, cdiv(C, CT)), kThreads, sm, st>>>(
-            X, nullptr, nullptr, nullptr, rows / nsl, C, seg, nsl, rpc, (float2*)ws);
-        D2P_CHECK_LAUNCH();
+        D2P_TRY(launch_colstats<0>(st, X, nullptr, nullptr, nullptr, rows / nsl, C, seg, nsl, nchunk, rpc,
+                                   (float2*)ws));
     }
     bn_fwd_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, nsl,
                                                  (double)(rows / nsl), gamma, beta, moving_mean,
@@ -293,17 +421,25 @@ int bn_backward(cudaStream_t st, const float* A, const float* DY, float* DZ, lon
     int rpc;
     int nchunk = pick_chunks(rows / nsl, nsl, &rpc);
     D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
-    int CT = C < kThreads ? C : kThreads;
-    size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-    colstats_partial<1><<<dim3(nchunk, nsl, cdiv(C, CT)), kThreads, sm, st>>>(A, dy_lin, mean, rstd, rows / nsl,
-                                                                C, seg, nsl, rpc, (float2*)ws);
-    D2P_CHECK_LAUNCH();
+    D2P_TRY(launch_colstats<1>(st, A, dy_lin, mean, rstd, rows / nsl, C, seg, nsl, nchunk, rpc, (float2*)ws));
     float* k1 = coef; float* k2 = coef + (size_t)nsl * C;
     bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, nsl,
                                                  (double)(rows / nsl), dgamma, dbeta, k1, k2,
                                                  training);
     D2P_CHECK_LAUNCH();
-    if (act)
+    const bool v4 = C % 4 == 0 && rows * C / 4 < (1LL << 32) && al16(A) && al16(dy_lin) && al16(DZ) &&
+                    al16(gamma) && al16(mean) && al16(rstd) && al16(k1) && al16(k2);
+    if (v4) {
+        const unsigned total4 = (unsigned)(rows * C / 4);
+        const int blocks = ew_blocks((long long)total4);
+#define D2P_BWD_APPLY_V4(ACT_)                                                                          \
+        bn_bwd_apply_v4<ACT_><<<blocks, 256, 0, st>>>(                                                  \
+            (const float4*)A, (const float4*)dy_lin, (float4*)DZ, total4, (unsigned)(C / 4), (unsigned)seg, \
+            (unsigned)nsl, (const float4*)gamma, (const float4*)mean, (const float4*)rstd,              \
+            (const float4*)k1, (const float4*)k2)
+        if (act) D2P_BWD_APPLY_V4(true); else D2P_BWD_APPLY_V4(false);
+#undef D2P_BWD_APPLY_V4
+    } else if (act)
         bn_bwd_apply_kernel<true><<<ew_blocks(rows * C), 256, 0, st>>>(
             A, dy_lin, DZ, rows, C, seg, nsl, gamma, mean, rstd, k1, k2, 0, 0);
     else
@@ -319,11 +455,7 @@ int colsum(cudaStream_t st, const float* X, long long rows, int C, float* out, f
     int rpc;
     int nchunk = pick_chunks(rows, 1, &rpc);
     D2P_REQUIRE(ws_bytes >= (size_t)nchunk * C * sizeof(float2), "colsum: workspace too small");
-    int CT = C < kThreads ? C : kThreads;
-    size_t sm = (size_t)(kThreads / CT) * CT * sizeof(float2);
-    colstats_partial<0><<<dim3(nchunk, 1, cdiv(C, CT)), kThreads, sm, st>>>(X, nullptr, nullptr, nullptr, rows, C,
-                                                              1, 1, rpc, (float2*)ws);
-    D2P_CHECK_LAUNCH();
+    D2P_TRY(launch_colstats<0>(st, X, nullptr, nullptr, nullptr, rows, C, 1, 1, nchunk, rpc, (float2*)ws));
     colsum_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, out, beta);
     D2P_CHECK_LAUNCH();
     return 0;
