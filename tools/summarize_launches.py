@@ -6,7 +6,7 @@ import re
 import sys
 
 path = sys.argv[1]
-skip = sys.argv[2] if len(sys.argv) > 2 else '0'      # launches to skip (warm-up step); 'half' = first half
+skip = sys.argv[2] if len(sys.argv) > 2 else '0'      # launches to skip (warm-up step); 'half' | 'after:<kernel name>'
 rows = []
 with open(path) as f:
     lines = [l for l in f if not l.startswith('==')]
@@ -19,7 +19,14 @@ for r in rd:
     v = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3}.get(unit, 1e-3) * v
     name = re.sub(r'\(.*', '', r['Kernel Name'])
     rows.append((name, v))
-rows = rows[(len(rows) // 2 if skip == 'half' else int(skip)):]
+if skip == 'half':
+    rows = rows[len(rows) // 2:]
+elif skip.startswith('after:'):          # everything after the first launch whose name contains the text
+    key = skip[6:]
+    first = next(i for i, (n, _) in enumerate(rows) if key in n)
+    rows = rows[first + 1:]
+else:
+    rows = rows[int(skip):]
 tot = sum(v for _, v in rows)
 agg = collections.OrderedDict()
 for n, v in rows:
