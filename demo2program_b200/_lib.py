@@ -74,6 +74,10 @@ SIGNATURES = {
     'd2p_induction_decode': (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp,
                                   _fp, _fp, _i, _fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_concat_cols': (_i, [_fp, _i, _fp, _i, _ll, _fp, _fp]),
+    'd2p_karel_check_syntax': (_i, [_fp, _i]),
+    'd2p_karel_execute': (_i, [_fp, _i, _fp, _i, _i, _i, _i, _fp, _fp]),
+    'd2p_karel_programs_equal': (_i, [_fp, _i, _fp, _i]),
+    'd2p_karel_eval_batch': (_i, [_fp, _fp, _fp, _i, _i, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i]),
     'd2p_fc_bn_saved_floats': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_ws_bytes': (_sz, [_ll, _i, _i]),
     'd2p_fc_bn_fwd': (_i, [_fp, _ll, _i, _i, _i, _i, _i, _pf, _fp, _fp, _i, _fp,

@@ -42,181 +42,6 @@ template <typename IN_T>
 __device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (float)in[idx]; }
 
 #include "conv_v2.cuh"
-
-// a[n,oy,ox,:] = lrelu(bias + sum_taps W[ky,kx,:,:]^T x(n, 2oy+ky-PT, 2ox+kx-PL, :))
-// where x = in*scale[slice]+shift[slice] (identity if scale == nullptr), zero outside.
-template <typename IN_T>
-__global__ void __launch_bounds__(128)
-conv_fwd_kernel(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_scale,
-                const float* __restrict__ in_shift, const float* __restrict__ W,
-                const float* __restrict__ bias, float* __restrict__ out) {
-    __shared__ float P[MAXC][PX + 1];
-    __shared__ float Wt[MAXC][MAXC];
-    const int tid = threadIdx.x, px = tid % PX, grp = tid / PX;
-    const int cpg = g.COUT / 4;  // channels per thread (COUT % 4 == 0)
-    const long long npix = (long long)g.N * g.OH * g.OW;
-    const long long p0 = (long long)blockIdx.x * PX;
-    float acc[MAXC / 4];
-#pragma unroll
-    for (int j = 0; j < MAXC / 4; ++j) acc[j] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        for (int idx = tid; idx < PX * g.CIN; idx += 128) {
-            int pp = idx / g.CIN, ci = idx % g.CIN;
-            long long p = p0 + pp;
-            float v = 0.f;
-            if (p < npix) {
-                int ox = (int)(p % g.OW);
-                int oy = (int)((p / g.OW) % g.OH);
-                long long n = p / ((long long)g.OW * g.OH);
-                int iy = 2 * oy + ky - g.PT, ix = 2 * ox + kx - g.PL;
-                if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
-                    v = load_in(in, (((size_t)n * g.IH + iy) * g.IW + ix) * g.CIN + ci);
-                    if (in_scale) {
-                        int sl = (int)((n / g.T) % g.k);
-                        v = v * in_scale[sl * g.CIN + ci] + in_shift[sl * g.CIN + ci];
-                    }
-                }
-            }
-            P[ci][pp] = v;
-        }
-        for (int idx = tid; idx < g.CIN * g.COUT; idx += 128)
-            Wt[idx / g.COUT][idx % g.COUT] = W[(size_t)tap * g.CIN * g.COUT + idx];
-        __syncthreads();
-        for (int ci = 0; ci < g.CIN; ++ci) {
-            float v = P[ci][px];
-#pragma unroll
-            for (int j = 0; j < MAXC / 4; ++j)
-                if (j < cpg) acc[j] = fmaf(v, Wt[ci][grp * cpg + j], acc[j]);
-        }
-        __syncthreads();
-    }
-    long long p = p0 + px;
-    if (p < npix) {
-#pragma unroll
-        for (int j = 0; j < MAXC / 4; ++j)
-            if (j < cpg) {
-                int c = grp * cpg + j;
-                out[p * g.COUT + c] = lrelu_f(acc[j] + bias[c]);
-            }
-    }
-}
-
-// dX[n,iy,ix,ci] = sum_{taps, co} dZ[n,oy,ox,co] * W[ky,kx,ci,co], oy = (iy+PT-ky)/2 (exact)
-__global__ void __launch_bounds__(128)
-conv_bwd_dx_kernel(Geo g, const float* __restrict__ dZ, const float* __restrict__ W,
-                   float* __restrict__ dX) {
-    __shared__ float P[MAXC][PX + 1];
-    __shared__ float Wt[MAXC][MAXC + 1];  // [ci][co]
-    const int tid = threadIdx.x, px = tid % PX, grp = tid / PX;
-    const int cpg = g.CIN / 4;
-    const long long npix = (long long)g.N * g.IH * g.IW;
-    const long long p0 = (long long)blockIdx.x * PX;
-    float acc[MAXC / 4];
-#pragma unroll
-    for (int j = 0; j < MAXC / 4; ++j) acc[j] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        for (int idx = tid; idx < PX * g.COUT; idx += 128) {
-            int pp = idx / g.COUT, co = idx % g.COUT;
-            long long p = p0 + pp;
-            float v = 0.f;
-            if (p < npix) {
-                int ix = (int)(p % g.IW);
-                int iy = (int)((p / g.IW) % g.IH);
-                long long n = p / ((long long)g.IW * g.IH);
-                int ty = iy + g.PT - ky, tx = ix + g.PL - kx;
-                if (ty >= 0 && tx >= 0 && (ty & 1) == 0 && (tx & 1) == 0) {
-                    int oy = ty >> 1, ox = tx >> 1;
-                    if (oy < g.OH && ox < g.OW)
-                        v = dZ[(((size_t)n * g.OH + oy) * g.OW + ox) * g.COUT + co];
-                }
-            }
-            P[co][pp] = v;
-        }
-        for (int idx = tid; idx < g.CIN * g.COUT; idx += 128)
-            Wt[idx / g.COUT][idx % g.COUT] = W[(size_t)tap * g.CIN * g.COUT + idx];
-        __syncthreads();
-        for (int co = 0; co < g.COUT; ++co) {
-            float v = P[co][px];
-#pragma unroll
-            for (int j = 0; j < MAXC / 4; ++j)
-                if (j < cpg) acc[j] = fmaf(v, Wt[grp * cpg + j][co], acc[j]);
-        }
-        __syncthreads();
-    }
-    long long p = p0 + px;
-    if (p < npix) {
-#pragma unroll
-        for (int j = 0; j < MAXC / 4; ++j)
-            if (j < cpg) dX[p * g.CIN + grp * cpg + j] = acc[j];
-    }
-}
-
-// partial[(blk*9 + tap) * CIN*COUT + ci*COUT + co] = sum over the block's pixel
-// chunk of x(p@tap, ci) * dZ(p, co).  grid = (nblk, 9).
-template <typename IN_T>
-__global__ void __launch_bounds__(256)
-conv_bwd_dw_kernel(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_scale,
-                   const float* __restrict__ in_shift, const float* __restrict__ dZ,
-                   int pix_per_block, float* __restrict__ partial) {
-    __shared__ float Xs[PX][MAXC + 1];
-    __shared__ float Zs[PX][MAXC + 1];
-    const int tid = threadIdx.x, tap = blockIdx.y, ky = tap / 3, kx = tap % 3;
-    const long long npix = (long long)g.N * g.OH * g.OW;
-    long long p0 = (long long)blockIdx.x * pix_per_block;
-    long long p1 = p0 + pix_per_block;
-    if (p1 > npix) p1 = npix;
-    const int nout = g.CIN * g.COUT;
-    float acc[9];  // ceil(48*48 / 256)
-#pragma unroll
-    for (int j = 0; j < 9; ++j) acc[j] = 0.f;
-    for (long long pb = p0; pb < p1; pb += PX) {
-        for (int idx = tid; idx < PX * g.CIN; idx += 256) {
-            int pp = idx / g.CIN, ci = idx % g.CIN;
-            long long p = pb + pp;
-            float v = 0.f;
-            if (p < p1) {
-                int ox = (int)(p % g.OW);
-                int oy = (int)((p / g.OW) % g.OH);
-                long long n = p / ((long long)g.OW * g.OH);
-                int iy = 2 * oy + ky - g.PT, ix = 2 * ox + kx - g.PL;
-                if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
-                    v = load_in(in, (((size_t)n * g.IH + iy) * g.IW + ix) * g.CIN + ci);
-                    if (in_scale) {
-                        int sl = (int)((n / g.T) % g.k);
-                        v = v * in_scale[sl * g.CIN + ci] + in_shift[sl * g.CIN + ci];
-                    }
-                }
-            }
-            Xs[pp][ci] = v;
-        }
-        for (int idx = tid; idx < PX * g.COUT; idx += 256) {
-            int pp = idx / g.COUT, co = idx % g.COUT;
-            long long p = pb + pp;
-            Zs[pp][co] = p < p1 ? dZ[p * g.COUT + co] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            int o = tid + j * 256;
-            if (o < nout) {
-                int ci = o / g.COUT, co = o % g.COUT;
-                float a = acc[j];
-#pragma unroll 8
-                for (int pp = 0; pp < PX; ++pp) a = fmaf(Xs[pp][ci], Zs[pp][co], a);
-                acc[j] = a;
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-        int o = tid + j * 256;
-        if (o < nout) partial[((size_t)blockIdx.x * 9 + tap) * nout + o] = acc[j];
-    }
-}
-
 // dW[tap, o] += sum_blk partial[blk, tap, o]
 __global__ void conv_dw_reduce(const float* __restrict__ partial, int nblk, int n,
                                float* __restrict__ dW) {

@@ -9,9 +9,10 @@ attributes `.loss .output .report_loss .report_accuracy .report_hist
 .ground_truth_program`.  There is no TF session: `run_train_step(feed)` /
 `run_eval_step(feed)` take the feed dict and refresh those attributes.
 
-Metrics that need the DSL parser / Karel interpreter on the host (syntax,
-exact-program and execution accuracies, reference models/model_full.py:602-616,
-713-916) are out of scope and reported as NaN / empty.
+Metrics that need the DSL parser / interpreter on the host (syntax, exact-program and
+execution accuracies, reference models/model_full.py:602-616, 713-916) are computed for
+Karel by the native library (`karel_dsl.py` -> csrc/karel_dsl.cu); the ViZDoom
+ones need the game engine and are reported as NaN / empty.
 """
 import numpy as np
 import torch
@@ -54,7 +55,12 @@ def _seq_stats(logits_bvl, gt_tokens, pred_len, gt_len):
     eq = (pred == gt_tokens).float()
     token_acc = float((eq * min_mask).sum() / max_mask.sum().clamp(min=1))
     seq_eq = ((pred.float() * gt_mask) == (gt_tokens.float() * gt_mask)).all(1) & (pred_len == gt_len)
-    return token_acc, float(seq_eq.float().mean()), pred
+    return token_acc, float(seq_eq.float().mean()), pred, seq_eq
+
+
+def _acc_hist(num_correct, k):
+    """CompareDemoAndExecution's histogram (reference models/model_full.py:889-895)."""
+    return np.array([float(np.mean(num_correct == i)) for i in range(k + 1)], np.float32)
 
 
 class Model(object):
@@ -70,7 +76,7 @@ class Model(object):
         self.report_loss, self.report_accuracy, self.report_hist = {}, {}, {}
         self.pred_program = self.program_len = self.ground_truth_program = None
         self.greedy_pred_program = self.greedy_pred_program_len = None
-        # host-interpreter metrics are out of scope: empty fetches, like the induction model's
+        # host-interpreter metrics: filled by run_eval_step for Karel, empty otherwise
         self.program_is_correct_syntax = self.greedy_program_is_correct_syntax = []
         self.program_num_execution_correct = self.program_is_correct_execution = []
         self.greedy_num_execution_correct = self.greedy_is_correct_execution = []
@@ -95,7 +101,7 @@ class Model(object):
         gt_tok = torch.as_tensor(np.asarray(feed['program_tokens'])).long().to(dev)
         gt_len = torch.as_tensor(self.program_len[:, 0]).long().to(dev)
         pp = eng.pred_program()
-        tacc, sacc, _ = _seq_stats(pp, gt_tok, gt_len, gt_len)
+        tacc, sacc, ptok, psame = _seq_stats(pp, gt_tok, gt_len, gt_len)
         losses = eng.loss.cpu().numpy()
         self.pred_program = pp.cpu().numpy()
         self.loss = float(losses[0])
@@ -107,7 +113,7 @@ class Model(object):
             self.report_loss['avg_action_loss'] = float(losses[2])
         if greedy:
             gp, glen, _ = eng.greedy_program()
-            gt, gs, _ = _seq_stats(gp, gt_tok, glen[:, 0].long(), gt_len)
+            gt, gs, gtok, gsame = _seq_stats(gp, gt_tok, glen[:, 0].long(), gt_len)
             self.greedy_pred_program = gp.cpu().numpy()
             self.greedy_pred_program_len = glen.cpu().numpy()
             self.report_accuracy.update({'greedy_program_token_acc': gt, 'greedy_program_seq_acc': gs,
@@ -115,6 +121,43 @@ class Model(object):
                                          'greedy_exact_program_accuracy': float('nan')})
         self.report_hist = {}
         self.output = [self.ground_truth_program, self.pred_program]
+        if cfg.dataset_type == 'karel':
+            self._karel_metrics(feed, 'program', 'pred', ptok, self.program_len[:, 0], psame)
+            if greedy:
+                self._karel_metrics(feed, 'greedy', 'greedy', gtok, self.greedy_pred_program_len[:, 0], gsame)
+
+    def _karel_metrics(self, feed, name, exact_name, pred_tokens, pred_len, is_same_seq):
+        """Syntax / exact-program / execution accuracies of one decoded program batch
+        (reference models/model_full.py:931-1013: the teacher-forced pass uses the
+        ground-truth lengths, the greedy pass its own)."""
+        from . import karel_dsl
+        cfg = self.config
+        tok = pred_tokens.cpu().numpy().astype(np.int32)
+        same = is_same_seq.cpu().numpy().astype(np.uint8)
+        plen = np.asarray(pred_len, np.int32)
+        gt_tok = np.asarray(feed['program_tokens'], np.int32)
+        gt_len = self.program_len[:, 0]
+        make_error = cfg.env_type != 'no_error'
+        prefix = 'program' if name == 'program' else 'greedy'
+        for split, key, lkey in (('', 's_h', 'demo_len'), ('test_', 'test_s_h', 'test_demo_len')):
+            syn, exe, num = karel_dsl.eval_batch(tok, plen, same, np.asarray(feed[key]) != 0,
+                                                 np.asarray(feed[lkey]).astype(np.int32), make_error)
+            k = exe.shape[1]
+            if name == 'program':
+                setattr(self, split + 'program_num_execution_correct', num)
+                setattr(self, split + 'program_is_correct_execution', exe.astype(bool))
+            else:
+                setattr(self, split + 'greedy_num_execution_correct', num)
+                setattr(self, split + 'greedy_is_correct_execution', exe.astype(bool))
+            self.report_hist[split + ('program' if name == 'program' else 'greedy_program') +
+                             '_execution_acc_hist'] = _acc_hist(num, k)
+        setattr(self, prefix + '_program_is_correct_syntax' if name == 'greedy' else 'program_is_correct_syntax', syn)
+        exact = np.array([float(syn[b] == 1 and karel_dsl.programs_equal(tok[b, :plen[b]], gt_tok[b, :gt_len[b]]) == 1)
+                          for b in range(tok.shape[0])], np.float32)
+        setattr(self, exact_name + '_exact_program_correct', exact)
+        self.report_accuracy[prefix + '_syntax_acc' if name == 'program' else 'greedy_program_syntax_acc'] = \
+            float(syn.mean())
+        self.report_accuracy[exact_name + '_exact_program_accuracy'] = float(exact.mean())
 
     def run_eval_step(self, feed, greedy=True):
         """Forward only (evaler.py:253-280): BN uses moving statistics when the model

@@ -163,6 +163,28 @@ int d2p_induction_decode(const float* keys, const float* values, const int* mem_
 int d2p_concat_cols(const float* A, int F1, const float* Bm, int F2, long long rows, float* out,
                     void* stream);
 
+/* ---- Karel DSL on the host: parser, interpreter, evaluation metrics --------
+ * HOST pointers, CPU code.  Token ids follow the reference vocabulary (dsl_prob.py:13-28, INT
+ * expanded).  Replaces the per-step Python py_funcs of models/model_full.py:602-616
+ * (check_correct_syntax -> karel_env/dsl/dsl_parse.py:252-265), 747-787
+ * (generate_program_output_karel -> dsl_parse.py rule closures + karel_env/karel.py:33-185),
+ * 712-727 (exact_program_compare_karel -> karel_env/dsl/dsl_enum_program.py), 870-897
+ * (CompareDemoAndExecution). */
+int d2p_karel_check_syntax(const int* tokens, int len);          /* 1 parses, 0 does not */
+/* state0 [h, w, 16] u8; s_h receives min(n_states, max_states) states (may be NULL).
+ * returns 1 = ran to completion, 0 = run-time failure / time-out, -1 = does not parse */
+int d2p_karel_execute(const int* tokens, int len, const unsigned char* state0, int h, int w,
+                      int make_error, int max_states, unsigned char* s_h, int* n_states);
+/* canonical-form comparison: 1 equal, 0 different, -1 either side is not a complete program */
+int d2p_karel_programs_equal(const int* a, int la, const int* b, int lb);
+/* tokens [B, L], lens [B], is_same_seq [B] u8, demos [B, k, T, h, w, 16] u8, demo_len [B, k];
+ * out: is_correct_syntax [B], is_correct_execution [B, k], num_correct_execution [B].
+ * nthreads <= 0: all host threads. */
+int d2p_karel_eval_batch(const int* tokens, const int* lens, const unsigned char* is_same_seq, int B,
+                         int L, const unsigned char* demos, const int* demo_len, int k, int T, int h,
+                         int w, int make_error, float* is_correct_syntax,
+                         float* is_correct_execution, float* num_correct_execution, int nthreads);
+
 /* ---- fc -> (lrelu) -> BN : ops.fc, reference models/ops.py:149-155 ------------
  * used by Per_Encoder (model_full.py:308-316; act = 0, per-demo slices) */
 typedef struct {

@@ -187,6 +187,41 @@ def test_eval_mode_uses_moving_statistics():
     assert torch.equal(eng.state, s0)
 
 
+def test_model_facade_reports_karel_program_metrics():
+    """evaler-facing facade: syntax / exact-program / execution accuracies come from the native
+    Karel DSL library and agree with the oracle restatement on the facade's own predictions."""
+    from demo2program_b200.model import Model
+    from demo2program_b200.synthetic import make_batch
+    from oracle import karel_dsl as okd
+    cfg = karel_config('full', batch_size=6, k=3)
+    m = Model(cfg, is_train=False, use_graph=False)
+    batch = make_batch(cfg, seed=5)
+    # make some ground truths real programs so that not everything is a syntax error
+    from demo2program_b200.vocab import karel_vocab
+    v = karel_vocab()
+    prog = v.str2intseq('DEF run m( REPEAT R=2 r( turnLeft r) m)')
+    batch['program_tokens'][0, :] = 0
+    batch['program_tokens'][0, :len(prog)] = prog
+    batch['program_len'][0] = len(prog)
+    m.run_eval_step(m.get_feed_dict(batch), greedy=True)
+    ra = m.report_accuracy
+    for key in ('program_syntax_acc', 'greedy_program_syntax_acc', 'pred_exact_program_accuracy',
+                'greedy_exact_program_accuracy'):
+        assert 0.0 <= ra[key] <= 1.0, key
+    assert set(m.report_hist) == {'program_execution_acc_hist', 'greedy_program_execution_acc_hist',
+                                  'test_program_execution_acc_hist', 'test_greedy_program_execution_acc_hist'}
+    assert abs(m.report_hist['program_execution_acc_hist'].sum() - 1.0) < 1e-6
+    tok = m.greedy_pred_program.argmax(1).astype(np.int32)
+    glen = m.greedy_pred_program_len[:, 0]
+    gt, gl = np.asarray(batch['program_tokens']), np.asarray(batch['program_len'])[:, 0].astype(int)
+    same = np.array([glen[b] == gl[b] and np.array_equal(tok[b, :gl[b]], gt[b, :gl[b]]) for b in range(6)])
+    syn, exe, num = okd.eval_batch(tok, glen, same, np.asarray(batch['s_h']) != 0,
+                                   np.asarray(batch['demo_len']).astype(int))
+    assert np.array_equal(syn, m.greedy_program_is_correct_syntax)
+    assert np.array_equal(exe.astype(bool), m.greedy_is_correct_execution)
+    assert np.array_equal(num, m.greedy_num_execution_correct)
+
+
 def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
     """trainer.py / evaler.py with the reference's flags on synthetic data."""
     import trainer, evaler, glob, os
@@ -199,7 +234,8 @@ def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
                  '--batch_size', '8', '--max_steps', '2', '--checkpoint', ck[0], '--quiet',
                  '--summary_file', str(tmp_path / 'report.txt')])
     rep = open(tmp_path / 'report.txt').read()
-    assert 'program_loss' in rep and 'greedy_program_token_acc' in rep
+    assert 'program_loss' in rep and 'greedy_program_token_acc' in rep and 'program_syntax_acc' in rep
+    assert 'nan' not in rep.lower()
 
 
 @pytest.mark.parametrize('is_train', [False, True])
