@@ -24,6 +24,7 @@
 namespace d2p {
 
 int lstm_tc_set_probe(long long* buf);
+int lstm_persist_set_probe(long long* buf);
 using namespace tc;
 
 namespace {
@@ -132,10 +133,18 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partials, int ksp
 // gate_tile > 0 (LSTM kernels only, !K_CONTIG): rows are permuted so that every
 // gate_tile-wide tile holds the i,j,f,o columns of gate_tile/4 hidden units:
 //   mn = tile*gate_tile + g*(gate_tile/4) + u  ->  col = g*H + tile*(gate_tile/4) + u
+// gate_tile >= 1000 selects the SLAB format of the persistent recurrence kernels (the
+// remainder is the gate tile, 0 = no permutation): per (k-block, 64-row slab) one 16 KB
+// chunk [hi|lo][row group 0..7][k-group 0..7][8 rows x 16 B], so that the 8 hi groups and
+// the 8 lo groups of a slab are 16 row groups at a uniform 1 KB stride - ONE N = 128 MMA
+// operand [Bhi | Blo]:
+//   byte = ((kb*(mgp/8) + mg/8)*2 + hl)*8192 + (mg%8)*1024 + kgl*128 + r*16
 template <bool K_CONTIG>
 __global__ void pack_bf16_kernel(const float* __restrict__ S, int MN, int K, int ld, int mgp, int kgp,
                                  uint8_t* __restrict__ out, int gate_tile, int gate_H) {
     const size_t total = (size_t)kgp * mgp * 8;
+    const bool slab = gate_tile >= 1000;
+    if (slab) gate_tile -= 1000;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         // idx = ((kb*mgp + mg)*8 + kgl)*8 + r : consecutive threads fill consecutive 16 B
@@ -162,9 +171,16 @@ __global__ void pack_bf16_kernel(const float* __restrict__ S, int MN, int K, int
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
-        uint8_t* base = out + (g * 2) * 128 + r * 16;
-        *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(base + 128) = make_uint4(l[0], l[1], l[2], l[3]);
+        if (slab) {
+            uint8_t* base = out + (((size_t)kb * (mgp >> 3) + (mg >> 3)) * 2) * 8192 + (mg & 7) * 1024 +
+                            kgl * 128 + r * 16;
+            *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(base + 8192) = make_uint4(l[0], l[1], l[2], l[3]);
+        } else {
+            uint8_t* base = out + (g * 2) * 128 + r * 16;
+            *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(base + 128) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
     }
 }
 
@@ -221,7 +237,8 @@ int pack_bf16(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_con
     size_t b = (total + 255) / 256, cap = 16 * (size_t)kNumSMs;
     int blocks = (int)(b < cap ? (b < 1 ? 1 : b) : cap);
     if (k_contig)
-        pack_bf16_kernel<true><<<blocks, 256, 0, st>>>(S, MN, K, ld, mgp, kgp, (uint8_t*)out, 0, 0);
+        pack_bf16_kernel<true><<<blocks, 256, 0, st>>>(S, MN, K, ld, mgp, kgp, (uint8_t*)out,
+                                                      gate_tile >= 1000 ? 1000 : 0, 0);
     else
         pack_bf16_kernel<false><<<blocks, 256, 0, st>>>(S, MN, K, ld, mgp, kgp, (uint8_t*)out,
                                                        gate_tile, gate_H);
@@ -407,5 +424,6 @@ extern "C" int d2p_tc_new_step(void) {
 // developer tool: SM-clock timeline probe of CTA (0,0,0) of the tensor-core kernels
 extern "C" int d2p_debug_set_probe(long long* buf) {
     D2P_CHECK_CUDA(cudaMemcpyToSymbol(d2p::tc::g_tc_dbg, &buf, sizeof(buf)));
+    D2P_TRY(d2p::lstm_persist_set_probe(buf));
     return d2p::lstm_tc_set_probe(buf);
 }

@@ -1,0 +1,580 @@
+// Persistent weight-stationary LSTM recurrence (tcgen05 / TMEM), forward and backward.
+//
+// One cooperative launch runs ALL T steps of tf.nn.dynamic_rnn(BasicLSTMCell) /
+// the teacher-forced decoder cell loop (reference models/model_full.py:244-258,
+// 265-277, 465-471) instead of one launch per step:
+//
+//  * grid = (32 column CTAs) x (row tiles of 128 sequence rows), one CTA per SM.
+//    Every CTA keeps its slab of the recurrent weight resident in shared memory for
+//    the whole sequence: forward 64 gate columns (i, j, f, o of 16 hidden units) x
+//    K = 512 as bf16 hi/lo = 128 KB; backward a 64-unit x 512-gate-column slab of
+//    Wh^T, also 128 KB.  Only the 128-row operand (h_{t-1}, resp. dZ_t) streams
+//    through a 2 x 32 KB bulk-copy ring each step.
+//  * the cell state c, the carried h (forward) and the dc / dh carries (backward)
+//    of the thread's (row, 4 hidden units) live in REGISTERS across all steps.
+//  * steps are separated by a release/acquire counter barrier among the 32 CTAs
+//    of one row tile (row tiles never exchange data), not by kernel boundaries:
+//    h_t is written in packed operand form with generic stores, published with
+//    fence.proxy.async + a gpu-scope release, and fetched by the next step's
+//    cp.async.bulk after an acquire + proxy fence.
+//  * forward epilogue = BasicLSTMCell + dynamic_rnn masking, exactly as the
+//    per-step kernel (lstm_tc.cu).  Backward: phase P (element-wise, all CTAs,
+//    sums the 4 split-K partial slabs in fixed order, writes dZ_t as fp32 and as
+//    packed operand), barrier, phase G (partial sums of dZ_t * Wh^T for one
+//    K-chunk = one gate), barrier.
+//
+// Spin waits are bounded (about 2 s of SM clock): a barrier that never completes sets an
+// error word instead of hanging the device; the host checks it where it can (eager
+// calls) and the engine's parity tests would fail loudly on the garbage it leaves.
+#include "tc_common.cuh"
+
+namespace d2p {
+
+using namespace tc;
+bool tc_available();
+
+namespace {
+
+constexpr int PH = 512;                         // hidden size served by the persistent kernels
+constexpr int PNKB = PH / BK;                   // 8 k-blocks of the resident slab
+constexpr int PBN = 64, PUPT = PBN / 4;         // 64 accumulator columns = 16 hidden units x 4 gates
+constexpr int PTHREADS = 512;
+constexpr int PCOLS = 32;                       // column CTAs per row tile
+constexpr int PTMEM = 2 * PBN;                  // accumulator columns: [A*Bhi (+Alo*Bhi) | Ahi*Blo]
+constexpr int PMAXSLOTS = 8;                    // ring slots (one per k-block when the row tile is small)
+constexpr uint32_t PB_BYTES = (PBN / 8) * 2048; // 16 KB: 64 n x 64 k, hi/lo
+constexpr size_t P_W_BYTES = (size_t)PNKB * PB_BYTES;     // 128 KB resident slab
+constexpr size_t P_RING_BYTES = 96 * 1024;                // streamed operand ring
+constexpr size_t P_SMEM = P_W_BYTES + P_RING_BYTES;
+constexpr long long P_SPIN_CYCLES = 4000000000LL;
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_relaxed(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Wait until *ctr >= target.  err[0] becomes non-zero if any wait in the grid ran out of
+// time; from then on every wait returns immediately so that the kernel still terminates.
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, unsigned* err) {
+    if (ld_acquire(ctr) >= target) return;
+    const long long t0 = clock64();
+    int it = 0;
+    while (ld_acquire(ctr) < target) {
+        if ((++it & 63) == 0) {
+            if (ld_acquire(err) != 0u) return;
+            if (clock64() - t0 > P_SPIN_CYCLES) { atomicExch(err, 1u); return; }
+        }
+    }
+}
+
+// timeline probe (developer tool): stamps of CTA (0,0) during step index P_PROBE_STEP
+constexpr int P_PROBE_STEP = 5;
+__device__ __forceinline__ void pstamp(int step, int slot) {
+    if (g_tc_dbg != nullptr && step == P_PROBE_STEP && blockIdx.x == 0 && blockIdx.y == 0)
+        g_tc_dbg[64 + slot] = clock64();   // slots 0..63 belong to the per-step kernels' probe
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void ld4r(const float* p, float* x) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ void st4r(float* p, const float* x) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+// 4 consecutive accumulator columns of this thread's TMEM lane (row)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* x) {
+    uint32_t v0, v1, v2, v3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(taddr));
+    x[0] = __uint_as_float(v0); x[1] = __uint_as_float(v1); x[2] = __uint_as_float(v2); x[3] = __uint_as_float(v3);
+}
+
+// barriers: full[PMAXSLOTS], empty[PMAXSLOTS], accum, wfull
+struct PersistBars {
+    uint32_t full0, empty0, accum, wfull;
+    int nslots;            // ring slots in use: min(8, ring bytes / bytes of one streamed k-block)
+    uint32_t a_bytes;      // bytes of one streamed k-block (whole 8-row groups of the row tile)
+};
+// ring position of a role lane (producer or MMA issuer), carried across steps
+struct RingPos { int slot; uint32_t wraps; };
+__device__ __forceinline__ void ring_next(RingPos& r, int nslots) {
+    if (++r.slot == nslots) { r.slot = 0; ++r.wraps; }
+}
+
+// Common setup: barriers, TMEM (64 columns), zeroed ring, resident weight slab.
+__device__ __forceinline__ uint32_t persist_setup(uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot,
+                                                  PersistBars& pb, int rows, const uint8_t* wsrc,
+                                                  size_t w_kb_stride) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pb.full0 = smem_u32(&bars[0]);
+    pb.empty0 = smem_u32(&bars[PMAXSLOTS]);
+    pb.accum = smem_u32(&bars[2 * PMAXSLOTS]);
+    pb.wfull = smem_u32(&bars[2 * PMAXSLOTS + 1]);
+    pb.a_bytes = (uint32_t)((rows + 7) / 8) * 2048u;
+    // the MMA reads a full 128-row image (32 KB) from every slot: the last slot must still end inside the ring
+    pb.nslots = (int)((P_RING_BYTES - (BM / 8) * 2048) / pb.a_bytes) + 1;
+    if (pb.nslots > PMAXSLOTS) pb.nslots = PMAXSLOTS;
+    if (tid == 0) {
+        for (int s = 0; s < 2 * PMAXSLOTS + 2; ++s) mbar_init(pb.full0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "r"((uint32_t)PTMEM));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // the MMA always reads 128 rows per slot: rows a partial row tile never loads must be finite
+    uint4* ring = reinterpret_cast<uint4*>(smem + P_W_BYTES);
+    for (int i = tid; i < (int)(P_RING_BYTES / 16); i += PTHREADS) ring[i] = make_uint4(0, 0, 0, 0);
+    proxy_fence();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+        mbar_expect_tx(pb.wfull, (uint32_t)P_W_BYTES);
+        for (int kb = 0; kb < PNKB; ++kb)
+            bulk_copy(smem_u32(smem) + kb * PB_BYTES, wsrc + (size_t)kb * w_kb_stride, PB_BYTES, pb.wfull);
+    }
+    return *tmem_slot;
+}
+
+// One pass of the streamed operand over the resident slab.  Column CTAs walk the 8 k-blocks
+// in rotated order (rot) so that the 32 CTAs of a row tile do not queue on one L2 line range.
+__device__ __forceinline__ void persist_produce(const PersistBars& pb, RingPos& rp, uint32_t sbase,
+                                                const uint8_t* a_src, size_t a_kb_stride, int rot) {
+    for (int kb = 0; kb < PNKB; ++kb) {
+        if (rp.wraps > 0) mbar_wait(pb.empty0 + 8 * rp.slot, (rp.wraps - 1) & 1);
+        const uint32_t bar = pb.full0 + 8 * rp.slot;
+        mbar_expect_tx(bar, pb.a_bytes);
+        bulk_copy(sbase + (uint32_t)P_W_BYTES + rp.slot * pb.a_bytes,
+                  a_src + (size_t)((kb + rot) & (PNKB - 1)) * a_kb_stride, pb.a_bytes, bar);
+        ring_next(rp, pb.nslots);
+    }
+}
+__device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, uint32_t sbase, uint32_t tmem_d,
+                                            int rot, bool first_round) {
+    // streamed operand: standard packed core matrices (hi/lo interleaved, LBO 256, SBO 2048);
+    // resident slab: [hi|lo][group][k-group] (LBO 128, SBO 1024) - 16 uniform row groups, so
+    // Ahi * [Bhi | Blo] is ONE N = 128 MMA into columns [0,64) | [64,128), then Alo * Bhi (N = 64)
+    // accumulates into [0,64).  (Measured: an M = 128 MMA costs ~68 cycles whatever N <= 128.)
+    constexpr uint32_t LBO = 256, SBO = 2048, WLBO = 128, WSBO = 1024;
+    constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PBN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * PBN) >> 3) << 17) |
+                                  ((uint32_t)(BM >> 4) << 24);
+    if (first_round) mbar_wait(pb.wfull, 0);
+    for (int kb = 0; kb < PNKB; ++kb) {
+        mbar_wait(pb.full0 + 8 * rp.slot, rp.wraps & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = sbase + (uint32_t)P_W_BYTES + rp.slot * pb.a_bytes;
+        const uint32_t sb = sbase + ((kb + rot) & (PNKB - 1)) * PB_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ahi = make_desc(sa + kk * 2 * LBO, LBO, SBO);
+            const uint64_t alo = make_desc(sa + kk * 2 * LBO + 128, LBO, SBO);
+            const uint64_t bw = make_desc(sb + kk * 2 * WLBO, WLBO, WSBO);
+            umma_bf16(tmem_d, ahi, bw, idesc128, (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, alo, bw, idesc64, 1u);
+        }
+        umma_commit(pb.empty0 + 8 * rp.slot);
+        if (kb == PNKB - 1) umma_commit(pb.accum);
+        ring_next(rp, pb.nslots);
+    }
+}
+
+struct FwdArgs {
+    const uint8_t* whpk; int mgp_w;     // Op_B[n = permuted gate column, k = hidden unit], gate tile 64
+    uint8_t* hpk0; uint8_t* hpk1; int mgp_h;   // packed h ping-pong (hpk0 holds h0 on entry)
+    float* gates; float* cells; float* Y;
+    const float* h0; const float* c0; float* hT; float* cT;
+    const int* len; int R, T; float forget_bias;
+    unsigned* sync;                     // [row tiles] arrival counters, sync[63] = error word
+};
+
+__global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const FwdArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.y, m0 = mt * BM, n0 = blockIdx.x * PBN, u0 = blockIdx.x * PUPT;
+    const int H = PH, G4 = 4 * PH, R = a.R, rot = blockIdx.x & (PNKB - 1);
+    unsigned* ctr = a.sync + mt;
+    unsigned* err = a.sync + 63;
+    int rows = R - m0;
+    if (rows > BM) rows = BM;
+    PersistBars pb;
+    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a.whpk + (size_t)(n0 / PBN) * PB_BYTES,
+                                          (size_t)a.mgp_w * 2048);
+    const uint32_t sbase = smem_u32(smem);
+    const size_t a_kb_stride = (size_t)a.mgp_h * 2048;
+    RingPos rp{0, 0};   // used by the producer lane and (separately) by the MMA lane
+
+    // This thread's item: accumulator row (= its TMEM lane) 32 (warp % 4) + lane, hidden units
+    // u0 + 4 (warp / 4) .. + 4.  The cell state c and the carried h stay in registers.
+    const int row = (warp & 3) * 32 + lane, jq = (warp >> 2) * 4, r = m0 + row;
+    const bool valid = r < R;
+    const size_t su = (size_t)(valid ? r : 0) * H + u0 + jq;
+    const uint32_t tacc = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)jq;
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
+    int mylen = 0;
+    if (valid) {
+        mylen = a.len[r];
+        if (a.c0) ld4r(a.c0 + su, c);
+        if (a.h0) ld4r(a.h0 + su, h);
+    }
+
+    for (int t = 0; t < a.T; ++t) {
+        float* grow = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u0 + jq;
+        const bool live = valid && t < mylen;
+        // hoisted x*Wx + b part of this thread's pre-activations: in flight during the main loop
+        float zi[4], zj[4], zf[4], zo[4];
+        if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
+        if (tid == 0) pstamp(t, 0);
+        if (warp == 0 && lane == 0) {
+            if (t > 0) grid_wait(ctr, (unsigned)(PCOLS * t), err);
+            pstamp(t, 1);
+            proxy_fence();
+            persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot);
+            pstamp(t, 2);
+        } else if (warp == 1 && lane == 0) {
+            persist_mma(pb, rp, sbase, tmem_d, rot, t == 0);
+            pstamp(t, 3);
+            // only this lane polls the accumulator barrier; everybody else parks on the hardware
+            // CTA barrier below (hundreds of threads spinning on try_wait steal shared-memory
+            // bandwidth from the tensor core's operand reads)
+            mbar_wait(pb.accum, t & 1);
+        }
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) pstamp(t, 5);
+        float ai[4], aj[4], af[4], ao[4];
+        float bi[4], bj[4], bf[4], bo[4];
+        tmem_ld4(tacc, ai); tmem_ld4(tacc + PUPT, aj); tmem_ld4(tacc + 2 * PUPT, af); tmem_ld4(tacc + 3 * PUPT, ao);
+        tmem_ld4(tacc + PBN, bi); tmem_ld4(tacc + PBN + PUPT, bj); tmem_ld4(tacc + PBN + 2 * PUPT, bf);
+        tmem_ld4(tacc + PBN + 3 * PUPT, bo);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ai[e] += bi[e]; aj[e] += bj[e]; af[e] += bf[e]; ao[e] += bo[e]; }
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                zi[e] = sigmoid_fast(zi[e] + ai[e]);
+                zj[e] = tanh_fast(zj[e] + aj[e]);
+                zf[e] = sigmoid_fast(zf[e] + af[e] + a.forget_bias);
+                zo[e] = sigmoid_fast(zo[e] + ao[e]);
+                c[e] = c[e] * zf[e] + zi[e] * zj[e];
+                h[e] = tanh_fast(c[e]) * zo[e];
+            }
+        }
+        if (tid == 64) pstamp(t, 6);
+        // publish h_t (or the carried h) as next step's packed operand FIRST; everything the
+        // backward pass needs is stored after the arrive, off the step-to-step critical path
+        if (t + 1 < a.T) {
+            if (valid) store_packed4((t & 1) ? a.hpk0 : a.hpk1, a.mgp_h, r, u0 + jq, h);
+            if (tid == 64) pstamp(t, 7);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // one gpu-scope fence by the arriving thread publishes the whole CTA's stores (they
+        // happen-before it through the CTA barrier; fences are cumulative).  The second CTA
+        // barrier keeps the bulky stores below out of the store queue that fence has to drain.
+        if (t + 1 < a.T) {
+            if (tid == 0) { __threadfence(); proxy_fence(); red_relaxed(ctr, 1u); pstamp(t, 8); }
+            __syncthreads();
+        }
+        if (valid) {
+            const size_t gu = (size_t)t * R * H + su;
+            if (live) {
+                st4r(grow, zi); st4r(grow + H, zj); st4r(grow + 2 * H, zf); st4r(grow + 3 * H, zo);
+                st4r(a.Y + gu, h);
+            } else {
+                // t >= len: output row is zero, (c, h) are carried through (dynamic_rnn, A.5)
+                *reinterpret_cast<float4*>(a.Y + gu) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            st4r(a.cells + gu, c);
+        }
+        if (tid == 64) pstamp(t, 9);
+    }
+    if (valid) {
+        st4r(a.hT + su, h);
+        st4r(a.cT + su, c);
+    }
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
+}
+
+struct BwdArgs {
+    const uint8_t* wtpk; int mgp_w;     // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
+    uint8_t* dzpk; int mgp_z;           // packed dZ_t [R, 4H]
+    float* partials;                    // [4][R][H] split-K partial sums of dh_{t-1}
+    float* gates;                       // [T,R,4H] in: activated gates, out: dZ
+    const float* cells; const float* c0; const float* dY;
+    const float* dhT; const float* dcT; float* dh0; float* dc0;
+    const int* len; int R, T, has_h0;
+    unsigned* sync;                     // [0,8): phase-P counters, [8,16): phase-G counters, [63] error
+};
+
+__global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const BwdArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.y, m0 = mt * BM;
+    const int q = blockIdx.x, nt = q >> 2, ks = q & 3;     // 64-unit output tile, K-chunk (= gate)
+    const int n0 = nt * PBN, kb0 = ks * PNKB, rot = nt & (PNKB - 1);
+    const int H = PH, G4 = 4 * PH, R = a.R;
+    const size_t RH = (size_t)R * H;
+    unsigned* ctrP = a.sync + mt;
+    unsigned* ctrG = a.sync + 8 + mt;
+    unsigned* err = a.sync + 63;
+    int rows = R - m0;
+    if (rows > BM) rows = BM;
+    PersistBars pb;
+    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows,
+                                          a.wtpk + (size_t)kb0 * a.mgp_w * 2048 + (size_t)nt * PB_BYTES,
+                                          (size_t)a.mgp_w * 2048);
+    const uint32_t sbase = smem_u32(smem);
+    const size_t a_kb_stride = (size_t)a.mgp_z * 2048;
+    RingPos rp{0, 0};
+
+    // phase-P item of this thread: (row, 4 hidden units) of units [16 q, 16 q + 16)
+    const int row = tid >> 2, u = q * PUPT + (tid & 3) * 4, r = m0 + row;
+    const bool valid = r < R;
+    const size_t su = (size_t)(valid ? r : 0) * H + u;
+    float dhc[4] = {0.f, 0.f, 0.f, 0.f}, dcc[4] = {0.f, 0.f, 0.f, 0.f};
+    int mylen = 0;
+    if (valid) {
+        mylen = a.len[r];
+        if (a.dhT) ld4r(a.dhT + su, dhc);
+        if (a.dcT) ld4r(a.dcT + su, dcc);
+    }
+    int ground = 0;          // GEMM rounds completed so far
+    bool have_partials = false;
+    for (int t = a.T - 1; t >= 0; --t) {
+        const int step = a.T - 1 - t;
+        if (tid == 0) pstamp(step, 16);
+        // ---- phase P: dZ_t for this CTA's 16 hidden units ----
+        float* g = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u;
+        float gi[4], gj[4], gf[4], go[4], cc[4], cp[4], dy[4];
+        const bool live = valid && t < mylen;
+        if (live) {   // operands that do not depend on the previous step: fetch before waiting
+            ld4r(g, gi); ld4r(g + H, gj); ld4r(g + 2 * H, gf); ld4r(g + 3 * H, go);
+            ld4r(a.cells + (size_t)t * RH + su, cc);
+            if (t > 0) ld4r(a.cells + (size_t)(t - 1) * RH + su, cp);
+            else if (a.c0) ld4r(a.c0 + su, cp);
+            else { cp[0] = cp[1] = cp[2] = cp[3] = 0.f; }
+            if (a.dY) ld4r(a.dY + (size_t)t * RH + su, dy);
+            else { dy[0] = dy[1] = dy[2] = dy[3] = 0.f; }
+        }
+        if (have_partials) {
+            if (tid == 0) { grid_wait(ctrG, (unsigned)(PCOLS * ground), err); pstamp(step, 17); }
+            __syncthreads();
+            if (valid) {
+                const float4 p0 = ldcg4(a.partials + su), p1 = ldcg4(a.partials + RH + su);
+                const float4 p2 = ldcg4(a.partials + 2 * RH + su), p3 = ldcg4(a.partials + 3 * RH + su);
+                dhc[0] += p0.x; dhc[1] += p0.y; dhc[2] += p0.z; dhc[3] += p0.w;
+                dhc[0] += p1.x; dhc[1] += p1.y; dhc[2] += p1.z; dhc[3] += p1.w;
+                dhc[0] += p2.x; dhc[1] += p2.y; dhc[2] += p2.z; dhc[3] += p2.w;
+                dhc[0] += p3.x; dhc[1] += p3.y; dhc[2] += p3.z; dhc[3] += p3.w;
+            }
+        }
+        if (tid == 64) pstamp(step, 18);
+        float di[4], dj[4], df[4], dq[4];
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float dht = dhc[e] + dy[e];
+                const float tcn = tanh_fast(cc[e]);
+                dq[e] = dht * tcn * go[e] * (1.f - go[e]);
+                const float dct = dcc[e] + dht * go[e] * (1.f - tcn * tcn);
+                di[e] = dct * gj[e] * gi[e] * (1.f - gi[e]);
+                dj[e] = dct * gi[e] * (1.f - gj[e] * gj[e]);
+                df[e] = dct * cp[e] * gf[e] * (1.f - gf[e]);
+                dcc[e] = dct * gf[e];
+                dhc[e] = 0.f;   // consumed: the recurrent product carries the new dh
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) di[e] = dj[e] = df[e] = dq[e] = 0.f;   // state copied through
+        }
+        const bool do_gemm = t > 0 || a.has_h0;
+        if (do_gemm) {
+            // packed operand first, then publish; the fp32 dZ (for the dW / dX products after the
+            // kernel) is stored behind the arrive
+            if (valid) {
+                store_packed4(a.dzpk, a.mgp_z, r, u, di);
+                store_packed4(a.dzpk, a.mgp_z, r, H + u, dj);
+                store_packed4(a.dzpk, a.mgp_z, r, 2 * H + u, df);
+                store_packed4(a.dzpk, a.mgp_z, r, 3 * H + u, dq);
+            }
+            if (tid == 64) pstamp(step, 19);
+            __syncthreads();
+            if (tid == 0) { __threadfence(); proxy_fence(); red_relaxed(ctrP, 1u); pstamp(step, 20); }
+            __syncthreads();
+        }
+        if (valid) { st4r(g, di); st4r(g + H, dj); st4r(g + 2 * H, df); st4r(g + 3 * H, dq); }
+        if (!do_gemm) { have_partials = false; break; }
+        // ---- phase G: partial[ks] = dZ_t[:, gate ks] * Wh[n-tile, gate ks]^T ----
+        if (warp == 0 && lane == 0) {
+            grid_wait(ctrP, (unsigned)(PCOLS * (ground + 1)), err);
+            pstamp(step, 21);
+            proxy_fence();
+            persist_produce(pb, rp, sbase, a.dzpk + ((size_t)kb0 * a.mgp_z + m0 / 8) * 2048, a_kb_stride, rot);
+        } else if (warp == 1 && lane == 0) {
+            persist_mma(pb, rp, sbase, tmem_d, rot, ground == 0);
+            mbar_wait(pb.accum, ground & 1);
+        }
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) pstamp(step, 22);
+        {
+            const int lq = warp & 3, cg = warp >> 2;
+            uint32_t v[PUPT], w[PUPT];
+            tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cg * PUPT), v);
+            tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(PBN + cg * PUPT), w);
+            tmem_ld_wait();
+            const int orow = m0 + lq * 32 + lane;
+            if (orow < R) {
+                float* dst = a.partials + (size_t)ks * RH + (size_t)orow * H + n0 + cg * PUPT;
+#pragma unroll
+                for (int j = 0; j < PUPT; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) =
+                        make_float4(__uint_as_float(v[j]) + __uint_as_float(w[j]),
+                                    __uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1]),
+                                    __uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2]),
+                                    __uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3]));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (tid == 64) pstamp(step, 23);
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) { __threadfence(); red_relaxed(ctrG, 1u); pstamp(step, 24); }
+        ++ground;
+        have_partials = true;
+    }
+    if (have_partials) {   // dh0 = carry + last partial sums
+        if (tid == 0) grid_wait(ctrG, (unsigned)(PCOLS * ground), err);
+        __syncthreads();
+        if (valid) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const float4 p = ldcg4(a.partials + (size_t)s * RH + su);
+                dhc[0] += p.x; dhc[1] += p.y; dhc[2] += p.z; dhc[3] += p.w;
+            }
+        }
+    }
+    if (valid) {
+        st4r(a.dh0 + su, dhc);
+        st4r(a.dc0 + su, dcc);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
+}
+
+int g_persist_mode = 1;   // 0 = per-step launches, 1 = persistent kernels where supported
+
+template <class Args>
+int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(PTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    count_launch();
+    return 0;
+}
+
+}  // namespace
+
+int lstm_persist_set_probe(long long* buf) {
+    D2P_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_tc_dbg, &buf, sizeof(buf)));
+    return 0;
+}
+
+bool lstm_persist_supported(int R, int H) {
+    return g_persist_mode != 0 && tc_available() && H == PH && R >= 1 && cdiv(R, BM) * PCOLS <= kNumSMs;
+}
+
+// Recurrence phase of lstm_seq_fwd: gates already hold X*Wx + b.
+int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
+                     const float* Wh, float forget_bias, float* Y, float* hT, float* cT, float* gates,
+                     float* cells) {
+    const int G4 = 4 * H;
+    size_t off = 0;
+    const size_t hbytes = packed_bytes(R, H);
+    FwdArgs a;
+    a.hpk0 = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
+    a.hpk1 = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
+    a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
+    D2P_REQUIRE(a.hpk0 && a.hpk1 && a.sync, "lstm persist fwd: tensor-core scratch arena too small");
+    const void* whpk;
+    D2P_TRY(get_packed(st, Wh, G4, H, G4, false, true, &off, &whpk, 1000 + PBN, H));
+    if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, a.hpk0));
+    else D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk0, 0, hbytes, st));
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk1, 0, hbytes, st));
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
+    a.whpk = (const uint8_t*)whpk; a.mgp_w = mgp_of(G4); a.mgp_h = mgp_of(R);
+    a.gates = gates; a.cells = cells; a.Y = Y; a.h0 = h0; a.c0 = c0; a.hT = hT; a.cT = cT;
+    a.len = len; a.R = R; a.T = T; a.forget_bias = forget_bias;
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)P_SMEM));
+        attr_set = true;
+    }
+    return launch_coop<FwdArgs>(lstm_persist_fwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a);
+}
+
+// Recurrence phase of lstm_seq_bwd (without dX): gates -> dZ, dh0, dc0.
+int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
+                     const float* Wh, float* gates, const float* cells, const float* dY, const float* dhT,
+                     const float* dcT, float* dh0, float* dc0) {
+    const int G4 = 4 * H;
+    size_t off = 0;
+    const size_t zbytes = packed_bytes(R, G4);
+    BwdArgs a;
+    a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
+    a.partials = (float*)tc_scratch_alloc(st, &off, (size_t)4 * R * H * sizeof(float));
+    a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
+    D2P_REQUIRE(a.dzpk && a.partials && a.sync, "lstm persist bwd: tensor-core scratch arena too small");
+    const void* wtpk;
+    D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
+    a.wtpk = (const uint8_t*)wtpk; a.mgp_w = mgp_of(H); a.mgp_z = mgp_of(R);
+    a.gates = gates; a.cells = cells; a.c0 = c0; a.dY = dY; a.dhT = dhT; a.dcT = dcT;
+    a.dh0 = dh0; a.dc0 = dc0; a.len = len; a.R = R; a.T = T; a.has_h0 = h0 != nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)P_SMEM));
+        attr_set = true;
+    }
+    return launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a);
+}
+
+}  // namespace d2p
+
+// 0: one launch per recurrent step; 1 (default): persistent kernels where supported.
+extern "C" int d2p_lstm_set_persistent(int mode) {
+    d2p::g_persist_mode = mode;
+    return 0;
+}

@@ -31,6 +31,12 @@ int lstm_skinny_nsplit(int H);
 int lstm_skinny_fwd_step(cudaStream_t, const float*, int, int, float*, float*, float*, const float*, float*, float*,
                          const int*, int, float);
 int lstm_skinny_bwd_step(cudaStream_t, const float*, const float*, int, int, float*);
+// persistent weight-stationary recurrences (lstm_persist.cu)
+bool lstm_persist_supported(int R, int H);
+int lstm_persist_fwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float,
+                     float*, float*, float*, float*, float*);
+int lstm_persist_bwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float*,
+                     const float*, const float*, const float*, const float*, float*, float*);
 
 namespace {
 
@@ -270,6 +276,9 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     if (!(phases & D2P_LSTM_RECUR)) return 0;
     // phase 2: recurrence (the arena is reused from offset 0; stream order makes that safe)
     size_t off = 0;
+    if (lstm_persist_supported(R, H) && aligned16(Wh) && aligned16(gates) && aligned16(hT) && aligned16(cT) &&
+        (!h0 || aligned16(h0)) && (!c0 || aligned16(c0)))
+        return lstm_persist_fwd(st, T, R, H, len, h0, c0, Wh, forget_bias, Y, hT, cT, gates, cells);
     if (lstm_skinny_supported(R, H) && aligned16(Wh) && aligned16(hT) && aligned16(gates)) {
         // every CTA reads all of h_{t-1}: ping-pong between hT and a scratch copy
         float* hb[2] = {hT, (float*)tc_scratch_alloc(st, &off, RH * sizeof(float))};
@@ -330,7 +339,13 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     float* dWh = dW + (size_t)In * G4;
     const size_t RH = (size_t)R * H;
     const int eb = cdiv(RH, 256);
-    if (phases & D2P_LSTM_BWD_RECUR) {
+    const bool persist = lstm_persist_supported(R, H) && aligned16(Wh) && aligned16(gates) && aligned16(dh0) &&
+                         aligned16(dc0) && (!dhT || aligned16(dhT)) && (!dcT || aligned16(dcT)) &&
+                         (!dY || aligned16(dY)) && (!c0 || aligned16(c0));
+    if ((phases & D2P_LSTM_BWD_RECUR) && persist) {
+        D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0));
+        if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+    } else if (phases & D2P_LSTM_BWD_RECUR) {
     // split-K factor of the per-step dh GEMM [R, H] = dZ_t [R, 4H] * Wh^T
         long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
         int ks = (int)(144 / (tiles64 < 1 ? 1 : tiles64));

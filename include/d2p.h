@@ -274,8 +274,16 @@ int d2p_tc_configure(void* scratch, size_t scratch_bytes, void* cache, size_t ca
 int d2p_tc_new_step(void);
 /* per-stream scratch arena for concurrent branches (call after d2p_tc_configure) */
 int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes);
+/* Recurrence scheduling of d2p_lstm_seq_fwd / d2p_lstm_seq_bwd (the while_loop of
+ * tf.nn.dynamic_rnn / dynamic_decode, reference models/model_full.py:254,274,469):
+ * 1 (default) = ONE persistent cooperative kernel per sequence where supported
+ * (H = 512, <= 512 rows, tensor-core arena configured): recurrent weight resident in
+ * shared memory, cell state in registers, steps separated by a release/acquire barrier
+ * among the CTAs of a row tile; 0 = one launch per time step. */
+int d2p_lstm_set_persistent(int mode);
 /* developer tool: record SM-clock stamps of CTA (0,0,0) of the tensor-core kernels
- * into buf (>= 64 int64 on the device); NULL disables. */
+ * into buf (>= 128 int64 on the device; the persistent recurrence kernels use
+ * slots 64..127); NULL disables. */
 int d2p_debug_set_probe(long long* buf);
 
 #ifdef __cplusplus
