@@ -231,8 +231,8 @@ int auto_ksplit(int M, int N, int K) {
 
 // Pack Op[mn,k] (MN x K) from an fp32 array; k_contig selects the source memory order.
 int pack_bf16(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_contig, void* out,
-              int gate_tile, int gate_H) {
-    const int mgp = mgp_of(MN), kgp = kgp_of(K);
+              int gate_tile, int gate_H, int mgp_override) {
+    const int mgp = mgp_override > 0 ? mgp_override : mgp_of(MN), kgp = kgp_of(K);
     size_t total = (size_t)kgp * mgp * 8;
     size_t b = (total + 255) / 256, cap = 16 * (size_t)kNumSMs;
     int blocks = (int)(b < cap ? (b < 1 ? 1 : b) : cap);

@@ -87,6 +87,19 @@ __device__ __forceinline__ void ld4r(const float* p, float* x) {
 __device__ __forceinline__ void st4r(float* p, const float* x) {
     *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
 }
+// MUFU-only forms (ex2.approx + rcp.approx: ~2 ulp, the fp32 rounding level of the cell)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_p(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_p(float x) { return 1.0f - 2.0f * rcp_approx(1.0f + __expf(2.0f * x)); }
+// staging of the per-step outputs in the (idle) operand ring: [array][row][16 units + 4 pad]
+constexpr int PSROW = PUPT + 4;
+__device__ __forceinline__ float* stage_ptr(float* stg, int arr, int row, int unit) {
+    return stg + ((size_t)arr * BM + row) * PSROW + unit;
+}
 // 4 consecutive accumulator columns of this thread's TMEM lane (row)
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* x) {
     uint32_t v0, v1, v2, v3;
@@ -98,6 +111,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* x) {
 // barriers: full[PMAXSLOTS], empty[PMAXSLOTS], accum, wfull
 struct PersistBars {
     uint32_t full0, empty0, accum, wfull;
+    bool single;           // the whole streamed tile (8 k-blocks) is one contiguous run: one bulk copy
     int nslots;            // ring slots in use: min(8, ring bytes / bytes of one streamed k-block)
     uint32_t a_bytes;      // bytes of one streamed k-block (whole 8-row groups of the row tile)
 };
@@ -109,8 +123,8 @@ __device__ __forceinline__ void ring_next(RingPos& r, int nslots) {
 
 // Common setup: barriers, TMEM (64 columns), zeroed ring, resident weight slab.
 __device__ __forceinline__ uint32_t persist_setup(uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot,
-                                                  PersistBars& pb, int rows, const uint8_t* wsrc,
-                                                  size_t w_kb_stride) {
+                                                  PersistBars& pb, int rows, size_t a_kb_stride,
+                                                  const uint8_t* wsrc, size_t w_kb_stride) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     pb.full0 = smem_u32(&bars[0]);
     pb.empty0 = smem_u32(&bars[PMAXSLOTS]);
@@ -120,6 +134,7 @@ __device__ __forceinline__ uint32_t persist_setup(uint8_t* smem, uint64_t* bars,
     // the MMA reads a full 128-row image (32 KB) from every slot: the last slot must still end inside the ring
     pb.nslots = (int)((P_RING_BYTES - (BM / 8) * 2048) / pb.a_bytes) + 1;
     if (pb.nslots > PMAXSLOTS) pb.nslots = PMAXSLOTS;
+    pb.single = pb.nslots == PNKB && a_kb_stride == (size_t)pb.a_bytes;
     if (tid == 0) {
         for (int s = 0; s < 2 * PMAXSLOTS + 2; ++s) mbar_init(pb.full0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -149,8 +164,16 @@ __device__ __forceinline__ uint32_t persist_setup(uint8_t* smem, uint64_t* bars,
 // in rotated order (rot) so that the 32 CTAs of a row tile do not queue on one L2 line range.
 __device__ __forceinline__ void persist_produce(const PersistBars& pb, RingPos& rp, uint32_t sbase,
                                                 const uint8_t* a_src, size_t a_kb_stride, int rot) {
+    if (pb.single) {
+        // small row tile stored without row padding: the 8 k-blocks are one contiguous run that
+        // fills the 8 slots in order - one request instead of eight (~300 issue cycles each)
+        mbar_expect_tx(pb.full0, PNKB * pb.a_bytes);
+        bulk_copy(sbase + (uint32_t)P_W_BYTES, a_src, PNKB * pb.a_bytes, pb.full0);
+        ++rp.wraps;
+        return;
+    }
     for (int kb = 0; kb < PNKB; ++kb) {
-        if (rp.wraps > 0) mbar_wait(pb.empty0 + 8 * rp.slot, (rp.wraps - 1) & 1);
+        if (pb.nslots < PNKB && rp.wraps > 0) mbar_wait(pb.empty0 + 8 * rp.slot, (rp.wraps - 1) & 1);
         const uint32_t bar = pb.full0 + 8 * rp.slot;
         mbar_expect_tx(bar, pb.a_bytes);
         bulk_copy(sbase + (uint32_t)P_W_BYTES + rp.slot * pb.a_bytes,
@@ -158,6 +181,22 @@ __device__ __forceinline__ void persist_produce(const PersistBars& pb, RingPos& 
         ring_next(rp, pb.nslots);
     }
 }
+// tcgen05.mma with a compile-time accumulate flag (no predicate set-up on the issue path)
+template <bool ACC>
+__device__ __forceinline__ void umma_imm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+
+// The issuing lane cannot run ahead of the tensor pipe (measured: ALU work between two
+// tcgen05.mma adds to the MMA time), so the descriptors are formed by adding constants to the
+// low word of two base descriptors instead of being rebuilt per MMA.
 __device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, uint32_t sbase, uint32_t tmem_d,
                                             int rot, bool first_round) {
     // streamed operand: standard packed core matrices (hi/lo interleaved, LBO 256, SBO 2048);
@@ -169,21 +208,27 @@ __device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, 
                                  ((uint32_t)(BM >> 4) << 24);
     constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * PBN) >> 3) << 17) |
                                   ((uint32_t)(BM >> 4) << 24);
+    const uint64_t a_base = make_desc(sbase + (uint32_t)P_W_BYTES, LBO, SBO);
+    const uint64_t w_base = make_desc(sbase, WLBO, WSBO);
+    const uint32_t a_slot = pb.a_bytes >> 4;
     if (first_round) mbar_wait(pb.wfull, 0);
+#pragma unroll 1
+    if (pb.single) rot = 0;
     for (int kb = 0; kb < PNKB; ++kb) {
-        mbar_wait(pb.full0 + 8 * rp.slot, rp.wraps & 1);
+        if (!pb.single || kb == 0) mbar_wait(pb.full0 + 8 * (pb.single ? 0 : rp.slot), rp.wraps & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = sbase + (uint32_t)P_W_BYTES + rp.slot * pb.a_bytes;
-        const uint32_t sb = sbase + ((kb + rot) & (PNKB - 1)) * PB_BYTES;
+        const uint64_t ad = a_base + (uint64_t)(rp.slot * a_slot);
+        const uint64_t wd = w_base + (uint64_t)(((kb + rot) & (PNKB - 1)) * (PB_BYTES >> 4));
+        if (kb == 0) umma_imm<false>(tmem_d, ad, wd, idesc128);
+        else umma_imm<true>(tmem_d, ad, wd, idesc128);
+        umma_imm<true>(tmem_d, ad + 8, wd, idesc64);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t ahi = make_desc(sa + kk * 2 * LBO, LBO, SBO);
-            const uint64_t alo = make_desc(sa + kk * 2 * LBO + 128, LBO, SBO);
-            const uint64_t bw = make_desc(sb + kk * 2 * WLBO, WLBO, WSBO);
-            umma_bf16(tmem_d, ahi, bw, idesc128, (kb > 0 || kk > 0) ? 1u : 0u);
-            umma_bf16(tmem_d, alo, bw, idesc64, 1u);
+        for (int kk = 1; kk < BK / 16; ++kk) {
+            umma_imm<true>(tmem_d, ad + kk * 32, wd + kk * 16, idesc128);
+            umma_imm<true>(tmem_d, ad + kk * 32 + 8, wd + kk * 16, idesc64);
         }
-        umma_commit(pb.empty0 + 8 * rp.slot);
+        // slots are recycled within a step only when the ring is shorter than the 8 k-blocks
+        if (pb.nslots < PNKB) umma_commit(pb.empty0 + 8 * rp.slot);
         if (kb == PNKB - 1) umma_commit(pb.accum);
         ring_next(rp, pb.nslots);
     }
@@ -210,10 +255,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
     int rows = R - m0;
     if (rows > BM) rows = BM;
     PersistBars pb;
-    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a.whpk + (size_t)(n0 / PBN) * PB_BYTES,
-                                          (size_t)a.mgp_w * 2048);
-    const uint32_t sbase = smem_u32(smem);
     const size_t a_kb_stride = (size_t)a.mgp_h * 2048;
+    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a_kb_stride,
+                                          a.whpk + (size_t)(n0 / PBN) * PB_BYTES, (size_t)a.mgp_w * 2048);
+    const uint32_t sbase = smem_u32(smem);
     RingPos rp{0, 0};   // used by the producer lane and (separately) by the MMA lane
 
     // This thread's item: accumulator row (= its TMEM lane) 32 (warp % 4) + lane, hidden units
@@ -230,8 +275,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         if (a.h0) ld4r(a.h0 + su, h);
     }
 
+    // copy-out item of this thread (coalesced: 4 lanes per row, 64 B per row and array)
+    const int crow = tid >> 2, cpart = (tid & 3) * 4, cr = m0 + crow;
+    const bool cvalid = cr < R;
+    const int clen = cvalid ? a.len[cr] : 0;
+    float* stg = reinterpret_cast<float*>(smem + P_W_BYTES);
+
     for (int t = 0; t < a.T; ++t) {
-        float* grow = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u0 + jq;
+        const float* grow = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u0 + jq;
         const bool live = valid && t < mylen;
         // hoisted x*Wx + b part of this thread's pre-activations: in flight during the main loop
         float zi[4], zj[4], zf[4], zo[4];
@@ -240,7 +291,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         if (warp == 0 && lane == 0) {
             if (t > 0) grid_wait(ctr, (unsigned)(PCOLS * t), err);
             pstamp(t, 1);
-            proxy_fence();
+            proxy_fence();   // also orders the previous step's generic staging accesses before the bulk writes
             persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot);
             pstamp(t, 2);
         } else if (warp == 1 && lane == 0) {
@@ -260,48 +311,57 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         tmem_ld4(tacc + PBN, bi); tmem_ld4(tacc + PBN + PUPT, bj); tmem_ld4(tacc + PBN + 2 * PUPT, bf);
         tmem_ld4(tacc + PBN + 3 * PUPT, bo);
         tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { ai[e] += bi[e]; aj[e] += bj[e]; af[e] += bf[e]; ao[e] += bo[e]; }
         if (live) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                zi[e] = sigmoid_fast(zi[e] + ai[e]);
-                zj[e] = tanh_fast(zj[e] + aj[e]);
-                zf[e] = sigmoid_fast(zf[e] + af[e] + a.forget_bias);
-                zo[e] = sigmoid_fast(zo[e] + ao[e]);
+                zi[e] = sigmoid_p(zi[e] + (ai[e] + bi[e]));
+                zj[e] = tanh_p(zj[e] + (aj[e] + bj[e]));
+                zf[e] = sigmoid_p(zf[e] + (af[e] + bf[e]) + a.forget_bias);
+                zo[e] = sigmoid_p(zo[e] + (ao[e] + bo[e]));
                 c[e] = c[e] * zf[e] + zi[e] * zj[e];
-                h[e] = tanh_fast(c[e]) * zo[e];
+                h[e] = tanh_p(c[e]) * zo[e];
             }
         }
         if (tid == 64) pstamp(t, 6);
         // publish h_t (or the carried h) as next step's packed operand FIRST; everything the
-        // backward pass needs is stored after the arrive, off the step-to-step critical path
-        if (t + 1 < a.T) {
-            if (valid) store_packed4((t & 1) ? a.hpk0 : a.hpk1, a.mgp_h, r, u0 + jq, h);
-            if (tid == 64) pstamp(t, 7);
-        }
+        // backward pass needs is written out after the arrive, off the step-to-step critical path
+        if (t + 1 < a.T && valid) store_packed4((t & 1) ? a.hpk0 : a.hpk1, a.mgp_h, r, u0 + jq, h);
+        if (tid == 64) pstamp(t, 7);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncthreads();   // all MMAs of this step retired (ring idle), accumulator read, h_t stores issued
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // one gpu-scope fence by the arriving thread publishes the whole CTA's stores (they
-        // happen-before it through the CTA barrier; fences are cumulative).  The second CTA
-        // barrier keeps the bulky stores below out of the store queue that fence has to drain.
-        if (t + 1 < a.T) {
-            if (tid == 0) { __threadfence(); proxy_fence(); red_relaxed(ctr, 1u); pstamp(t, 8); }
-            __syncthreads();
-        }
+        // happen-before it through the CTA barrier; fences are cumulative)
+        if (tid == 0 && t + 1 < a.T) { __threadfence(); proxy_fence(); red_relaxed(ctr, 1u); pstamp(t, 8); }
+        // The thread that owns an accumulator row holds 16 B of each output row; writing those
+        // straight to HBM costs 32 cache lines per warp store.  Park the outputs in the idle
+        // ring and write them back with 4 lanes per row (64 B segments).
         if (valid) {
-            const size_t gu = (size_t)t * R * H + su;
             if (live) {
-                st4r(grow, zi); st4r(grow + H, zj); st4r(grow + 2 * H, zf); st4r(grow + 3 * H, zo);
-                st4r(a.Y + gu, h);
+                st4r(stage_ptr(stg, 0, row, jq), zi); st4r(stage_ptr(stg, 1, row, jq), zj);
+                st4r(stage_ptr(stg, 2, row, jq), zf); st4r(stage_ptr(stg, 3, row, jq), zo);
+            }
+            st4r(stage_ptr(stg, 4, row, jq), c);
+            st4r(stage_ptr(stg, 5, row, jq), h);
+        }
+        __syncthreads();
+        if (cvalid) {
+            const size_t gu = ((size_t)t * R + cr) * H + u0 + cpart;
+            *reinterpret_cast<float4*>(a.cells + gu) = *reinterpret_cast<const float4*>(stage_ptr(stg, 4, crow, cpart));
+            if (t < clen) {
+                float* gout = a.gates + ((size_t)t * R + cr) * G4 + u0 + cpart;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<float4*>(gout + g * H) =
+                        *reinterpret_cast<const float4*>(stage_ptr(stg, g, crow, cpart));
+                *reinterpret_cast<float4*>(a.Y + gu) = *reinterpret_cast<const float4*>(stage_ptr(stg, 5, crow, cpart));
             } else {
                 // t >= len: output row is zero, (c, h) are carried through (dynamic_rnn, A.5)
                 *reinterpret_cast<float4*>(a.Y + gu) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            st4r(a.cells + gu, c);
         }
         if (tid == 64) pstamp(t, 9);
+        __syncthreads();   // staging drained before the next step's bulk copies land in the ring
     }
     if (valid) {
         st4r(a.hT + su, h);
@@ -339,11 +399,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     int rows = R - m0;
     if (rows > BM) rows = BM;
     PersistBars pb;
-    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows,
+    const size_t a_kb_stride = (size_t)a.mgp_z * 2048;
+    const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a_kb_stride,
                                           a.wtpk + (size_t)kb0 * a.mgp_w * 2048 + (size_t)nt * PB_BYTES,
                                           (size_t)a.mgp_w * 2048);
     const uint32_t sbase = smem_u32(smem);
-    const size_t a_kb_stride = (size_t)a.mgp_z * 2048;
     RingPos rp{0, 0};
 
     // phase-P item of this thread: (row, 4 hidden units) of units [16 q, 16 q + 16)
@@ -519,7 +579,9 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
                      float* cells) {
     const int G4 = 4 * H;
     size_t off = 0;
-    const size_t hbytes = packed_bytes(R, H);
+    // R <= 32: no padding to 128-row tiles, so a row tile's 8 k-blocks are contiguous (one bulk copy)
+    const int mgp_h = R <= 32 ? cdiv(R, 8) : mgp_of(R);
+    const size_t hbytes = (size_t)kgp_of(H) * mgp_h * 256;
     FwdArgs a;
     a.hpk0 = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
     a.hpk1 = (uint8_t*)tc_scratch_alloc(st, &off, hbytes);
@@ -527,11 +589,11 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
     D2P_REQUIRE(a.hpk0 && a.hpk1 && a.sync, "lstm persist fwd: tensor-core scratch arena too small");
     const void* whpk;
     D2P_TRY(get_packed(st, Wh, G4, H, G4, false, true, &off, &whpk, 1000 + PBN, H));
-    if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, a.hpk0));
+    if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, a.hpk0, 0, 0, mgp_h));
     else D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk0, 0, hbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk1, 0, hbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
-    a.whpk = (const uint8_t*)whpk; a.mgp_w = mgp_of(G4); a.mgp_h = mgp_of(R);
+    a.whpk = (const uint8_t*)whpk; a.mgp_w = mgp_of(G4); a.mgp_h = mgp_h;
     a.gates = gates; a.cells = cells; a.Y = Y; a.h0 = h0; a.c0 = c0; a.hT = hT; a.cT = cT;
     a.len = len; a.R = R; a.T = T; a.forget_bias = forget_bias;
     static bool attr_set = false;
@@ -549,7 +611,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
                      const float* dcT, float* dh0, float* dc0) {
     const int G4 = 4 * H;
     size_t off = 0;
-    const size_t zbytes = packed_bytes(R, G4);
+    const int mgp_z = R <= 32 ? cdiv(R, 8) : mgp_of(R);
+    const size_t zbytes = (size_t)kgp_of(G4) * mgp_z * 256;
     BwdArgs a;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
     a.partials = (float*)tc_scratch_alloc(st, &off, (size_t)4 * R * H * sizeof(float));
@@ -559,7 +622,7 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
-    a.wtpk = (const uint8_t*)wtpk; a.mgp_w = mgp_of(H); a.mgp_z = mgp_of(R);
+    a.wtpk = (const uint8_t*)wtpk; a.mgp_w = mgp_of(H); a.mgp_z = mgp_z;
     a.gates = gates; a.cells = cells; a.c0 = c0; a.dY = dY; a.dhT = dhT; a.dcT = dcT;
     a.dh0 = dh0; a.dc0 = dc0; a.len = len; a.R = R; a.T = T; a.has_h0 = h0 != nullptr;
     static bool attr_set = false;

@@ -260,7 +260,7 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_d) {
 
 // host-side API of gemm_tc.cu
 int pack_bf16(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_contig, void* out,
-              int gate_tile = 0, int gate_H = 0);
+              int gate_tile = 0, int gate_H = 0, int mgp_override = 0);
 int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int N, int K, float alpha,
                    float beta, float* C, int ldc, const float* bias, int ksplit = 1,
                    float* partials = nullptr);

@@ -71,6 +71,70 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int dist
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256u));
 }
+// mode 4: the persistent LSTM kernel's inner loop: per k16 one N=128 MMA (A: mode-0 packed image,
+// B: slab [hi|lo] image, LBO 128 / SBO 1024) and one N=64 MMA, commit every 8 MMAs.
+__global__ void __launch_bounds__(512) loop_kernel(int n_kb, int commit_every, int nthreads_wait, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t tmem_base;
+    for (int i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_base;
+    if (threadIdx.x == 32) {
+        const uint32_t i64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t i128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t sw = smem_u32(smem), sa = sw + 128 * 1024;
+        const long long t0 = clock64();
+        int n = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const uint32_t a = sa + (kb & 7) * 4096, b = sw + (kb & 7) * 16384;
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ahi = make_desc(a + kk * 512, 256, 2048, 0), alo = make_desc(a + kk * 512 + 128, 256, 2048, 0);
+                const uint64_t bw = make_desc(b + kk * 256, 128, 1024, 0);
+                umma(tm, ahi, bw, i128, (kb | kk) != 0);
+                umma(tm, alo, bw, i64, 1);
+                n += 2;
+                if (commit_every && n % commit_every == 0)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[1])) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+        mbar_wait(smem_u32(&bar[0]), 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    } else if ((int)threadIdx.x < nthreads_wait && threadIdx.x != 32) {
+        mbar_wait(smem_u32(&bar[0]), 0);     // other threads spinning on the accumulator barrier
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128u));
+}
+void run_loop(int n_kb, int commit_every, int nwait, long long* d) {
+    const int smem = 192 * 1024;
+    cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    long long h[148];
+    for (int rep = 0; rep < 2; ++rep) {
+        loop_kernel<<<96, 512, smem>>>(n_kb, commit_every, nwait, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return; }
+    }
+    cudaMemcpy(h, d, sizeof(long long) * 96, cudaMemcpyDeviceToHost);
+    long long tot = 0;
+    for (int i = 0; i < 96; ++i) tot += h[i];
+    printf("persist loop: %d k-blocks (%d MMAs), commit every %d, %d threads polling: %.0f cycles = %.1f cyc/mma\n", n_kb,
+           n_kb * 8, commit_every, nwait, (double)tot / 96, (double)tot / 96 / (n_kb * 8));
+}
 template <int N>
 void run(int mode, int n_mma, int grid, long long* d) {
     const int smem = 192 * 1024;
@@ -90,7 +154,11 @@ void run(int mode, int n_mma, int grid, long long* d) {
 int main() {
     long long* d;
     cudaMalloc(&d, sizeof(long long) * 2 * 148);
-    for (int mode = 0; mode < 4; ++mode) {
+    run_loop(8, 0, 0, d);
+    run_loop(80, 0, 0, d);
+    for (int ce = 2; ce <= 64; ce *= 2) run_loop(80, ce, 0, d);
+    run_loop(8, 8, 512, d);
+    for (int mode = 0; mode < 4; mode += 3) {
         run<64>(mode, 96, 1, d);
         run<64>(mode, 960, 148, d);
         run<128>(mode, 960, 148, d);

@@ -15,7 +15,7 @@ cache = torch.zeros(128 << 20, dtype=torch.uint8, device=dev)
 lib.d2p_tc_configure(ptr(scratch), scratch.numel(), ptr(cache), cache.numel(), 1)
 lib.d2p_lstm_set_persistent(1)
 FW = ['top', 'grid barrier passed', 'last bulk copy issued', 'last MMA issued', None, 'accum ready',
-      'cell math done', 'packed h stored + fenced', 'arrive issued', 'gates/Y/cells stores issued']
+      'cell math done', 'packed h stores issued', 'arrive issued', 'copy-out stores issued']
 BW = ['top', 'G-barrier passed', 'partials summed', 'dZ stores issued', 'P arrive issued', 'P-barrier passed',
       'accum ready', 'partials stored', 'G arrive issued']
 
