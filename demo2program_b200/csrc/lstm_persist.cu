@@ -556,7 +556,7 @@ int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t s
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_persist_mode == 2 ? 0 : 1;   // mode 2 (experiment): plain launch
     D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     count_launch();
     return 0;

@@ -352,3 +352,19 @@ extern "C" int d2p_len_to_int(const float* x, int* y, int n, void* stream) {
     D2P_CHECK_LAUNCH();
     return 0;
 }
+
+// developer tool: write the GPU global timer (ns) into buf[slot] in stream order - an
+// in-graph timeline of the step when called between ops during capture
+namespace d2p { namespace {
+__global__ void stamp_kernel(unsigned long long* buf, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    buf[slot] = t;
+}
+} }
+extern "C" int d2p_debug_stamp(unsigned long long* buf, int slot, void* stream) {
+    D2P_REQUIRE(buf != nullptr && slot >= 0, "debug_stamp: bad arguments");
+    d2p::stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(buf, slot);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}

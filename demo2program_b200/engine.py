@@ -73,7 +73,7 @@ class Engine:
                                         device=self.dev)
         # side streams for the independent branches (three decoders, two RN pools)
         self.concurrent = bool(concurrent)
-        self.side_streams = [torch.cuda.Stream(self.dev) for _ in range(2)] if self.concurrent else []
+        self.side_streams = [torch.cuda.Stream(self.dev) for _ in range(3)] if self.concurrent else []
         self.grad_stream = torch.cuda.Stream(self.dev) if self.concurrent else None
         for s_ in self.side_streams + ([self.grad_stream] if self.concurrent else []):
             self._ws_side[s_.cuda_stream] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
@@ -199,6 +199,7 @@ class Engine:
                        for s in 'hc' for f in ('fc1', 'fc2')}
         self.dsum_h, self.dsum_c = z(B, H), z(B, H)       # decoder init state
         self.dh2, self.dc2 = z(R, H), z(R, H)             # grads wrt per-demo (h,c)
+        self.pool_dh, self.pool_dc = z(R, H), z(R, H)     # rn_pool / mean contributions to them
         # ---- program decoder ----
         self.prog = lstm_bufs(L, B)
         self.prog.update(X=z(L, B, H), logits=z(L, B, V), dlogits=z(L, B, V),
@@ -228,6 +229,17 @@ class Engine:
     # ------------------------------------------------------------------ helpers
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _stamp(self, name):
+        """Developer timeline (tools/timeline.py): with self.timeline set to an int64 device
+        tensor, record the GPU global timer at this point of the current stream."""
+        tl = getattr(self, 'timeline', None)
+        if tl is None:
+            return
+        names = self.timeline_names
+        if name not in names:
+            names.append(name)
+        check(self.lib.d2p_debug_stamp(ptr(tl), names.index(name), self._st()), 'stamp')
 
     def _call(self, name, *args):
         check(getattr(self.lib, name)(*args), name)
@@ -292,7 +304,7 @@ class Engine:
         return n
 
     # ------------------------------------------------------------------ branches
-    def _parallel(self, fns):
+    def _parallel(self, fns, streams=None):
         """Run independent branches of the step concurrently: fns[0] on the current
         stream, the others on side streams that fork from / rejoin it (also valid
         inside CUDA-graph capture).  Every branch has its own scratch buffers."""
@@ -304,7 +316,7 @@ class Engine:
         ev = torch.cuda.Event()
         ev.record(main)
         used = []
-        for fn, s in zip(fns[1:], self.side_streams):
+        for fn, s in zip(fns[1:], streams or self.side_streams):
             s.wait_event(ev)
             with torch.cuda.stream(s):
                 fn()
@@ -321,6 +333,7 @@ class Engine:
         tr = int(self.is_train if train_stats is None else train_stats)
         call, S = self._call, self._st
         self._tc_bind()              # (re)bind this engine's arenas; re-pack weights
+        self._stamp('fwd start')
         call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, S())
         call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, S())
         # The decoders' hoisted input products (teacher-forced embeddings x Wx) do not depend
@@ -353,7 +366,7 @@ class Engine:
             main = torch.cuda.current_stream(self.dev)
             ev0 = torch.cuda.Event()
             ev0.record(main)
-            s1, s2 = self.side_streams
+            s1, s2 = self.side_streams[:2]
             s1.wait_event(ev0)
             with torch.cuda.stream(s1):
                 if self.model == 'full':
@@ -372,8 +385,10 @@ class Engine:
                 per_in()
         call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
+        self._stamp('conv fwd done')
         self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc)
+        self._stamp('encoder lstm fwd done')
         if self.model in ('full', 'summarizer'):
             call('d2p_group_sum', ptr(self.enc['hT']), B, k, H, 1.0 / k, ptr(self.sum1_h), 0, S())
             call('d2p_group_sum', ptr(self.enc['cT']), B, k, H, 1.0 / k, ptr(self.sum1_c), 0, S())
@@ -381,6 +396,7 @@ class Engine:
             call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0, ptr(self.init2_c), 0, S())
             self._lstm_fwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
                            'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec)
+            self._stamp('second-path lstm fwd done')
             fin = self.sec
 
             def pool(s, out, saved):
@@ -393,6 +409,7 @@ class Engine:
                 return run
             self._parallel([pool('h', self.dsum_h, self.rn_saved_h),
                             pool('c', self.dsum_c, self.rn_saved_c)])
+            self._stamp('pools fwd done')
         else:
             if cfg.demo_aggregation != 'avgpool':
                 raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
@@ -412,6 +429,7 @@ class Engine:
             call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
                  ptr(p['runlen']), ptr(p['w']), ptr(p['rowloss']), ptr(p['dlogits']),
                  ptr(self.loss[1:]), 0, S())
+            self._stamp('program decoder fwd done')
 
         if self.model != 'full':
             prog_fwd()
@@ -432,6 +450,7 @@ class Engine:
             call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
                  ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
                  ptr(self.loss[2:]), 0, S())
+            self._stamp('action decoder fwd done')
 
         def per_fwd():
             self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
@@ -441,8 +460,18 @@ class Engine:
             call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
                  ptr(a['runlen']), ptr(a['w']), ptr(q['rowloss']), ptr(q['dlogits']),
                  ptr(self.loss[3:]), 0, S())
+            self._stamp('per decoder fwd done')
 
-        self._parallel([prog_fwd, act_fwd, per_fwd])
+        # The two k*B-row decoders are persistent kernels of 96 CTAs each: they cannot be
+        # resident together, and a half-placed second one would only hold the SMs the
+        # 32-CTA program decoder needs.  Chain them on one stream next to the program decoder.
+        def act_then_per():
+            act_fwd()
+            if self.concurrent:   # the per decoder's hoisted input product ran on side stream 2
+                torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[1])
+            per_fwd()
+        self._parallel([prog_fwd, act_then_per])
+        self._stamp('fwd done')
         # total = program + action + per
         call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
         call('d2p_axpby', ptr(self.loss[2:]), 1.0, ptr(self.loss), 1.0, 1, S())
@@ -458,6 +487,7 @@ class Engine:
         fin = self.fin
         self.grads.zero_()
         p = self.prog
+        self._stamp('bwd start')
 
         def prog_bwd():
             Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
@@ -471,8 +501,19 @@ class Engine:
                  ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
                  self.ws_bytes, S())
             # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
+            self._stamp('program decoder bwd done')
 
-        have_dh2 = False
+        def pool_bwd(s, dsum, saved, dF):
+            def run():
+                if self.model == 'full':   # mean term
+                    call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), 0, S())
+                else:
+                    dF.zero_()
+                call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                     C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
+                     self.ws_bytes, S())
+            return run
+
         if self.model == 'full':
             A, Pd = cfg.action_space, cfg.per_dim
             a, q = self.act, self.per
@@ -488,6 +529,7 @@ class Engine:
                 call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
                      ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
                      self.ws_bytes, S())
+                self._stamp('action decoder bwd done')
 
             def per_bwd():
                 Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
@@ -499,33 +541,41 @@ class Engine:
                                q['dX'])
                 call('d2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
                      ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, S())
+                self._stamp('per decoder bwd done')
 
-            self._parallel([prog_bwd, act_bwd, per_bwd])
-            # dh2 = d(action init) + d(per init)
+            # The summary pools only need the program decoder's (dh0, dc0): back-propagate them
+            # right behind it (h on this stream, c on the third side stream) while the two
+            # k*B-row decoders - which cannot share the SMs as persistent kernels - still run.
+            def prog_then_pools():
+                prog_bwd()
+                self._parallel([pool_bwd('h', p['dh0'], self.rn_saved_h, self.pool_dh),
+                                pool_bwd('c', p['dc0'], self.rn_saved_c, self.pool_dc)],
+                               streams=self.side_streams[2:])
+                self._stamp('pools bwd done')
+
+            def act_then_per_bwd():
+                act_bwd()
+                per_bwd()
+            self._parallel([prog_then_pools, act_then_per_bwd])
+            self._stamp('decoders + pools bwd joined')
+            # dh2 = d(action init) + d(per init) + d(pools)
             call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, S())
             call('d2p_axpby', ptr(q['dh0']), 1.0, ptr(self.dh2), 1.0, R * H, S())
+            call('d2p_axpby', ptr(self.pool_dh), 1.0, ptr(self.dh2), 1.0, R * H, S())
             call('d2p_axpby', ptr(a['dc0']), 1.0, ptr(self.dc2), 0.0, R * H, S())
             call('d2p_axpby', ptr(q['dc0']), 1.0, ptr(self.dc2), 1.0, R * H, S())
-            have_dh2 = True
+            call('d2p_axpby', ptr(self.pool_dc), 1.0, ptr(self.dc2), 1.0, R * H, S())
         else:
             prog_bwd()
+            if self.model == 'summarizer':
+                self._parallel([pool_bwd('h', p['dh0'], self.rn_saved_h, self.dh2),
+                                pool_bwd('c', p['dc0'], self.rn_saved_c, self.dc2)])
         if self.model in ('full', 'summarizer'):
-            def pool_bwd(s, dsum, saved, dF):
-                def run():
-                    if self.model == 'full':   # mean term
-                        call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), int(have_dh2), S())
-                    else:
-                        dF.zero_()
-                    call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
-                         C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
-                         self.ws_bytes, S())
-                return run
-            self._parallel([pool_bwd('h', p['dh0'], self.rn_saved_h, self.dh2),
-                            pool_bwd('c', p['dc0'], self.rn_saved_c, self.dc2)])
             sec = self.sec
             self._lstm_bwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
                            'SecondPathEncoder/rnn/basic_lstm_cell/', sec, None, self.dh2, self.dc2,
                            self.dy1)
+            self._stamp('second-path lstm bwd done')
             # init state = mean_i of first-pass finals, broadcast over i
             call('d2p_group_sum', ptr(sec['dh0']), B, k, H, 1.0, ptr(self.sum1_h), 0, S())
             call('d2p_group_sum', ptr(sec['dc0']), B, k, H, 1.0, ptr(self.sum1_c), 0, S())
@@ -539,10 +589,13 @@ class Engine:
         self._lstm_bwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, dY1, self.dh2, self.dc2,
                        self.dfeat)
+        self._stamp('encoder lstm bwd done')
         call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.dfeat),
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
+        self._stamp('conv bwd done')
         if self.concurrent:   # parameter-gradient products must land before the optimizer
             torch.cuda.current_stream(self.dev).wait_stream(self.grad_stream)
+        self._stamp('bwd done (weight-gradient stream joined)')
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
@@ -555,6 +608,7 @@ class Engine:
                    ptr(self.adam_v), self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip,
                    scale, decay, ptr(self.adam_state), ptr(self.ws), self.ws_bytes,
                    self._st())
+        self._stamp('clip + adam done')
 
     # ------------------------------------------------------------------ steps
     def _step_body(self, with_opt):

@@ -285,6 +285,9 @@ int d2p_lstm_set_persistent(int mode);
  * into buf (>= 128 int64 on the device; the persistent recurrence kernels use
  * slots 64..127); NULL disables. */
 int d2p_debug_set_probe(long long* buf);
+/* developer tool: one-thread kernel that writes %globaltimer (ns) into buf[slot] in stream
+ * order; called between ops during graph capture it yields the timeline of a replay. */
+int d2p_debug_stamp(unsigned long long* buf, int slot, void* stream);
 
 #ifdef __cplusplus
 }
