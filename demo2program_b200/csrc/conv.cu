@@ -28,6 +28,10 @@ int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, siz
 size_t bn_ws_bytes(long long rows, int C, int nsl);
 int permute_frames(cudaStream_t, const float*, float*, int, int, int, int);
 int unpermute_frames(cudaStream_t, const float*, float*, int, int, int, int);
+// fused single-kernel Karel forward (conv_fused.cu)
+bool conv_fused_supported(const d2p_conv_desc* d, int training, size_t ws_bytes);
+int conv_fused_fwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, float* feat, float* saved,
+                   int training, void* ws);
 
 namespace {
 
@@ -260,6 +264,8 @@ extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, 
     Plan p; make_plan(d, &p);
     D2P_REQUIRE(ws_bytes >= p.total, "conv fwd: workspace too small (%zu < %zu)", ws_bytes, p.total);
     char* wsb = (char*)ws;
+    if (conv_fused_supported(d, training, p.part_bytes))
+        return conv_fused_fwd(st, d, frames, feat, saved, training, wsb + p.off_part);
     const float* prev = nullptr; const float* prev_stats = nullptr;
     float* sp = saved;
     for (int l = 0; l < d->n_layers; ++l) {

@@ -1,0 +1,416 @@
+// Fused Karel State_Encoder forward: conv1 -> lrelu -> BN -> conv2 -> lrelu -> BN -> conv3 ->
+// lrelu -> BN -> flatten in ONE cooperative kernel (reference models/model_full.py:216-231
+// through ops.conv2d / ops.bn_act / ops.lrelu, models/ops.py:7-33; 8x8x16 frames ->
+// 4x4x16 -> 2x2x32 -> 1x1x48, TF SAME padding = (0 top/left, 1 bottom/right)).
+//
+// The per-layer pipeline (conv kernel + statistics passes + finalize, 15 launches) is launch-
+// latency bound at Karel sizes: 6400 frames are 6.5 MB of u8 input.  Here
+//   * the grid is k slices x G CTAs (k = demonstration index = BatchNorm slice, reference
+//     model_full.py:373-376; G = min(B, 148 / k)), one CTA per SM; a CTA owns a few whole
+//     demonstrations of ONE slice, so BatchNorm statistics are exchanged only among the G
+//     CTAs of a slice (fixed-order partial sums -> deterministic);
+//   * frames are read once as stored (u8, 16-byte channel vectors through the read-only path);
+//     all three activations of the CTA's frames stay in shared memory, weights too;
+//   * the three statistics exchanges are release/acquire counter barriers per slice;
+//   * the pre-BatchNorm activations and the per-slice statistics are still written out in the
+//     layout the backward pass reads (d2p_conv_encoder_saved_floats).
+// Eval mode (moving statistics) needs no exchange at all and streams any number of frames
+// per CTA in chunks of 64.
+#include "common.cuh"
+
+namespace d2p {
+namespace {
+
+constexpr int KF_THREADS = 512;
+constexpr int KF_MAXF = 64;                       // frames per chunk held in shared memory
+constexpr int KF_W1 = 9 * 16 * 16, KF_W2 = 9 * 16 * 32, KF_W3 = 4 * 32 * 48;
+constexpr int KF_RED = 32 * 48 * 2;
+constexpr size_t KF_SMEM = (size_t)(KF_W1 + KF_W2 + KF_W3 + KF_MAXF * (256 + 128 + 48) + KF_RED + 512) * sizeof(float);
+constexpr long long KF_SPIN_CYCLES = 4000000000LL;
+constexpr float KF_EPS = 1e-3f, KF_DECAY = 0.9f;
+
+struct KfLayer {
+    const float* w; const float* b; const float* gamma; const float* beta;
+    float* moving_mean; float* moving_var;
+    float* act;      // saved pre-BN activation [N, P, C]
+    float* stats;    // saved [mean | rstd | scale | shift] x [k, C]
+};
+struct KfArgs {
+    const void* frames; int frames_u8;
+    int B, k, T, gs, training;
+    KfLayer L[3];
+    float* feat;         // [T, R, 48]
+    float2* partials;    // [3][k][gs][48]
+    float* var;          // [3][k][48] batch variances (for the moving update)
+    unsigned* sync;      // [3*k] slice counters, [60] ticket, [63] error word
+};
+
+__device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, unsigned* err) {
+    if (kf_ld_acquire(ctr) >= target) return;
+    const long long t0 = clock64();
+    int it = 0;
+    while (kf_ld_acquire(ctr) < target) {
+        if ((++it & 63) == 0) {
+            if (kf_ld_acquire(err) != 0u) return;
+            if (clock64() - t0 > KF_SPIN_CYCLES) { atomicExch(err, 1u); return; }
+        }
+    }
+}
+
+__device__ __forceinline__ void kf_load16(const void* frames, int u8, size_t pix, float* x) {
+    if (u8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(frames) + pix * 16));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[q * 4 + b] = (float)((w[q] >> (8 * b)) & 0xffu);
+    } else {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + pix * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(p + q);
+            x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+        }
+    }
+}
+
+// acc[0..16) += x * w[0..16)
+__device__ __forceinline__ void kf_fma16(float x, const float* __restrict__ w, float* acc) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
+        acc[q * 4] = fmaf(x, ww.x, acc[q * 4]);         acc[q * 4 + 1] = fmaf(x, ww.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(x, ww.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x, ww.w, acc[q * 4 + 3]);
+    }
+}
+
+// Per-channel (sum, sum of squares) of A[rows][C] over this CTA's rows -> red[0..C) (float2),
+// fixed summation order.
+template <int C>
+__device__ __forceinline__ void kf_col_stats(const float* __restrict__ A, int rows, float* red, float2* out) {
+    constexpr int G = KF_THREADS / C;     // row groups
+    const int tid = threadIdx.x, c = tid % C, g = tid / C;
+    if (g < G) {
+        float s = 0.f, s2 = 0.f;
+        for (int r = g; r < rows; r += G) {
+            const float v = A[(size_t)r * C + c];
+            s += v; s2 = fmaf(v, v, s2);
+        }
+        red[(g * C + c) * 2] = s; red[(g * C + c) * 2 + 1] = s2;
+    }
+    __syncthreads();
+    if (tid < C) {
+        double s = 0.0, s2 = 0.0;
+        for (int gg = 0; gg < G; ++gg) { s += red[(gg * C + tid) * 2]; s2 += red[(gg * C + tid) * 2 + 1]; }
+        out[tid] = make_float2((float)s, (float)s2);
+    }
+}
+
+// Statistics exchange + finalize of layer `l` (C channels): scale/shift of this CTA's slice
+// into sc/sh (shared memory).
+template <int C>
+__device__ __forceinline__ void kf_bn_finalize(const KfArgs& a, int l, int slice, int j, const float* A, int rows,
+                                               int pixels, float* red, float* sc, float* sh) {
+    const int tid = threadIdx.x;
+    const KfLayer& L = a.L[l];
+    float* st = L.stats;
+    const int kC = a.k * C;
+    if (a.training) {
+        float2* mine = a.partials + ((size_t)(l * a.k + slice) * a.gs + j) * 48;
+        kf_col_stats<C>(A, rows, red, mine);
+        __syncthreads();
+        unsigned* ctr = a.sync + l * a.k + slice;
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            kf_wait(ctr, (unsigned)a.gs, a.sync + 63);
+        }
+        __syncthreads();
+        if (tid < C) {
+            double s = 0.0, s2 = 0.0;
+            const float2* p = a.partials + (size_t)(l * a.k + slice) * a.gs * 48 + tid;
+            for (int jj = 0; jj < a.gs; ++jj) {
+                const float2 v = __ldcg(p + (size_t)jj * 48);
+                s += v.x; s2 += v.y;
+            }
+            const double count = (double)a.B * a.T * pixels;
+            const double mu = s / count;
+            double var = s2 / count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float muf = (float)mu;
+            const float rs = (float)(1.0 / sqrt(var + (double)KF_EPS));
+            const float g = L.gamma[tid], b = L.beta[tid];
+            sc[tid] = g * rs; sh[tid] = b - muf * g * rs;
+            if (j == 0) {
+                st[slice * C + tid] = muf; st[kC + slice * C + tid] = rs;
+                st[2 * kC + slice * C + tid] = g * rs; st[3 * kC + slice * C + tid] = b - muf * g * rs;
+                a.var[(l * a.k + slice) * 48 + tid] = (float)var;
+            }
+        }
+    } else if (tid < C) {
+        const float mu = L.moving_mean[tid], rs = rsqrtf(L.moving_var[tid] + KF_EPS);
+        const float g = L.gamma[tid], b = L.beta[tid];
+        sc[tid] = g * rs; sh[tid] = b - mu * g * rs;
+        if (j == 0) {
+            st[slice * C + tid] = mu; st[kC + slice * C + tid] = rs;
+            st[2 * kC + slice * C + tid] = g * rs; st[3 * kC + slice * C + tid] = b - mu * g * rs;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* W1s = sm;
+    float* W2s = W1s + KF_W1;
+    float* W3s = W2s + KF_W2;
+    float* A1 = W3s + KF_W3;
+    float* A2 = A1 + KF_MAXF * 256;
+    float* A3 = A2 + KF_MAXF * 128;
+    float* red = A3 + KF_MAXF * 48;
+    float* misc = red + KF_RED;          // b1[16] b2[32] b3[48] | sc[48] sh[48]
+    float* b1s = misc; float* b2s = misc + 16; float* b3s = misc + 48;
+    float* sc = misc + 96; float* sh = misc + 144;
+    const int tid = threadIdx.x;
+    const int slice = blockIdx.x / a.gs, j = blockIdx.x % a.gs;
+    const int b0 = (int)((long long)j * a.B / a.gs), b1 = (int)((long long)(j + 1) * a.B / a.gs);
+    const int nfr = (b1 - b0) * a.T;
+    const int R = a.B * a.k;
+
+    for (int i = tid; i < KF_W1; i += KF_THREADS) W1s[i] = a.L[0].w[i];
+    for (int i = tid; i < KF_W2; i += KF_THREADS) W2s[i] = a.L[1].w[i];
+    for (int i = tid; i < KF_W3; i += KF_THREADS) {
+        // taps (kh, kw) in {0,1}^2 of the 3x3 kernel: the only ones inside the 2x2 input
+        const int tap = i / (32 * 48), rem = i % (32 * 48);
+        W3s[i] = a.L[2].w[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem];
+    }
+    if (tid < 16) b1s[tid] = a.L[0].b[tid];
+    if (tid < 32) b2s[tid] = a.L[1].b[tid];
+    if (tid < 48) b3s[tid] = a.L[2].b[tid];
+    __syncthreads();
+
+    for (int f0 = 0; f0 < nfr; f0 += KF_MAXF) {
+        const int fc = nfr - f0 < KF_MAXF ? nfr - f0 : KF_MAXF;
+        // ---- conv1 (8x8x16 -> 4x4x16) + bias + lrelu ----
+        for (int it = tid; it < fc * 16; it += KF_THREADS) {
+            const int f = it >> 4, px = it & 15, oh = px >> 2, ow = px & 3;
+            const int fl = f0 + f;
+            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = b1s[c];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int ih = 2 * oh + kh;
+                if (ih >= 8) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int iw = 2 * ow + kw;
+                    if (iw >= 8) continue;
+                    float x[16];
+                    kf_load16(a.frames, a.frames_u8, n * 64 + ih * 8 + iw, x);
+                    const float* w = W1s + (kh * 3 + kw) * 256;
+#pragma unroll
+                    for (int ci = 0; ci < 16; ++ci) kf_fma16(x[ci], w + ci * 16, acc);
+                }
+            }
+            float* o = A1 + (size_t)f * 256 + px * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
+                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+        }
+        __syncthreads();
+        for (int idx = tid; idx < fc * 64; idx += KF_THREADS) {   // saved a1, 1 KB per frame
+            const int f = idx >> 6, fl = f0 + f;
+            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            *reinterpret_cast<float4*>(a.L[0].act + n * 256 + (idx & 63) * 4) =
+                *reinterpret_cast<const float4*>(A1 + (size_t)idx * 4);
+        }
+        kf_bn_finalize<16>(a, 0, slice, j, A1, fc * 16, 16, red, sc, sh);
+        for (int idx = tid; idx < fc * 256; idx += KF_THREADS) A1[idx] = fmaf(A1[idx], sc[idx & 15], sh[idx & 15]);
+        __syncthreads();
+        // ---- conv2 (4x4x16 -> 2x2x32): item = (16 output channels, frame, pixel) ----
+        for (int it = tid; it < fc * 8; it += KF_THREADS) {
+            const int half = it / (fc * 4), rem = it - half * fc * 4;
+            const int f = rem >> 2, px = rem & 3, oh = px >> 1, ow = px & 1;
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = b2s[half * 16 + c];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int ih = 2 * oh + kh;
+                if (ih >= 4) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int iw = 2 * ow + kw;
+                    if (iw >= 4) continue;
+                    const float* xin = A1 + (size_t)f * 256 + (ih * 4 + iw) * 16;
+                    const float* w = W2s + (kh * 3 + kw) * 512 + half * 16;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xin + c4 * 4);
+                        kf_fma16(xv.x, w + (c4 * 4) * 32, acc);     kf_fma16(xv.y, w + (c4 * 4 + 1) * 32, acc);
+                        kf_fma16(xv.z, w + (c4 * 4 + 2) * 32, acc); kf_fma16(xv.w, w + (c4 * 4 + 3) * 32, acc);
+                    }
+                }
+            }
+            float* o = A2 + (size_t)f * 128 + px * 32 + half * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
+                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+        }
+        __syncthreads();
+        for (int idx = tid; idx < fc * 32; idx += KF_THREADS) {   // saved a2, 512 B per frame
+            const int f = idx >> 5, fl = f0 + f;
+            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            *reinterpret_cast<float4*>(a.L[1].act + n * 128 + (idx & 31) * 4) =
+                *reinterpret_cast<const float4*>(A2 + (size_t)idx * 4);
+        }
+        kf_bn_finalize<32>(a, 1, slice, j, A2, fc * 4, 4, red, sc, sh);
+        for (int idx = tid; idx < fc * 128; idx += KF_THREADS) A2[idx] = fmaf(A2[idx], sc[idx & 31], sh[idx & 31]);
+        __syncthreads();
+        // ---- conv3 (2x2x32 -> 1x1x48): item = (16 output channels, frame) ----
+        for (int it = tid; it < fc * 3; it += KF_THREADS) {
+            const int g3 = it / fc, f = it - g3 * fc;
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = b3s[g3 * 16 + c];
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                const float* xin = A2 + (size_t)f * 128 + tap * 32;
+                const float* w = W3s + tap * 32 * 48 + g3 * 16;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xin + c4 * 4);
+                    kf_fma16(xv.x, w + (c4 * 4) * 48, acc);     kf_fma16(xv.y, w + (c4 * 4 + 1) * 48, acc);
+                    kf_fma16(xv.z, w + (c4 * 4 + 2) * 48, acc); kf_fma16(xv.w, w + (c4 * 4 + 3) * 48, acc);
+                }
+            }
+            float* o = A3 + (size_t)f * 48 + g3 * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
+                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+        }
+        __syncthreads();
+        for (int idx = tid; idx < fc * 12; idx += KF_THREADS) {   // saved a3, 192 B per frame
+            const int f = idx / 12, fl = f0 + f;
+            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            *reinterpret_cast<float4*>(a.L[2].act + n * 48 + (idx % 12) * 4) =
+                *reinterpret_cast<const float4*>(A3 + (size_t)idx * 4);
+        }
+        kf_bn_finalize<48>(a, 2, slice, j, A3, fc, 1, red, sc, sh);
+        // ---- feature = BN(a3), time-major [T, R, 48] ----
+        for (int idx = tid; idx < fc * 48; idx += KF_THREADS) {
+            const int f = idx / 48, c = idx - f * 48, fl = f0 + f;
+            const int r = (b0 + fl / a.T) * a.k + slice, t = fl % a.T;
+            a.feat[((size_t)t * R + r) * 48 + c] = fmaf(A3[idx], sc[c], sh[c]);
+        }
+        __syncthreads();
+    }
+    if (!a.training) return;
+    // ---- moving statistics: the last CTA to finish applies the k per-slice updates in slice
+    // order (the reference updates them once per encoder instance, ops.py:20-23) ----
+    __shared__ unsigned last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(a.sync + 60, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int idx = tid; idx < 96; idx += KF_THREADS) {
+        const int l = idx < 16 ? 0 : (idx < 48 ? 1 : 2);
+        const int C = l == 0 ? 16 : (l == 1 ? 32 : 48);
+        const int c = idx - (l == 0 ? 0 : (l == 1 ? 16 : 48));
+        const KfLayer& L = a.L[l];
+        float mm = L.moving_mean[c], mv = L.moving_var[c];
+        for (int sl = 0; sl < a.k; ++sl) {
+            const float mu = __ldcg(L.stats + sl * C + c);
+            const float var = __ldcg(a.var + (l * a.k + sl) * 48 + c);
+            mm -= (mm - mu) * (1.f - KF_DECAY);
+            mv -= (mv - var) * (1.f - KF_DECAY);
+        }
+        L.moving_mean[c] = mm; L.moving_var[c] = mv;
+    }
+}
+
+int g_conv_fused = 1;
+
+}  // namespace
+
+size_t conv_fused_ws_bytes(const d2p_conv_desc* d) {
+    const int gs = d->B < kNumSMs / d->k ? d->B : kNumSMs / d->k;
+    return (size_t)3 * d->k * gs * 48 * sizeof(float2) + (size_t)3 * d->k * 48 * sizeof(float) + 256 + 512;
+}
+
+bool conv_fused_supported(const d2p_conv_desc* d, int training, size_t ws_bytes) {
+    if (!g_conv_fused) return false;
+    if (d->n_layers != 3 || d->h != 8 || d->w != 8 || d->d != 16) return false;
+    if (d->layers[0].cout != 16 || d->layers[1].cout != 32 || d->layers[2].cout != 48) return false;
+    if (d->k < 1 || d->k > kNumSMs) return false;
+    const int gs = d->B < kNumSMs / d->k ? d->B : kNumSMs / d->k;
+    const int max_demos = (d->B + gs - 1) / gs;
+    if (training && max_demos * d->T > KF_MAXF) return false;   // statistics need the CTA's frames resident
+    return ws_bytes >= conv_fused_ws_bytes(d);
+}
+
+// saved layout as d2p_conv_encoder_saved_floats: per layer [act | stats]
+int conv_fused_fwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, float* feat, float* saved,
+                   int training, void* ws) {
+    KfArgs a;
+    a.frames = frames; a.frames_u8 = d->frames_dtype == D2P_U8;
+    a.B = d->B; a.k = d->k; a.T = d->T; a.training = training;
+    a.gs = d->B < kNumSMs / d->k ? d->B : kNumSMs / d->k;
+    const size_t N = (size_t)d->B * d->k * d->T;
+    const int P[3] = {16, 4, 1}, Cc[3] = {16, 32, 48};
+    float* sp = saved;
+    for (int l = 0; l < 3; ++l) {
+        const d2p_conv_layer& L = d->layers[l];
+        D2P_REQUIRE(L.w && L.b && L.gamma && L.beta && L.moving_mean && L.moving_var, "conv fwd: layer %d params", l);
+        a.L[l].w = L.w; a.L[l].b = L.b; a.L[l].gamma = L.gamma; a.L[l].beta = L.beta;
+        a.L[l].moving_mean = L.moving_mean; a.L[l].moving_var = L.moving_var;
+        a.L[l].act = sp; sp += N * P[l] * Cc[l];
+        a.L[l].stats = sp; sp += (size_t)4 * d->k * Cc[l];
+    }
+    a.feat = feat;
+    char* w = (char*)ws;
+    a.sync = (unsigned*)w; w += 256;
+    a.partials = (float2*)w; w += (size_t)3 * d->k * a.gs * 48 * sizeof(float2);
+    a.var = (float*)w;
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(karel_conv_fwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)KF_SMEM));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(d->k * a.gs);
+    cfg.blockDim = dim3(KF_THREADS);
+    cfg.dynamicSmemBytes = KF_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = training ? 1 : 0;   // eval mode has no inter-CTA exchange
+    D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, karel_conv_fwd_fused, a));
+    count_launch();
+    return 0;
+}
+
+}  // namespace d2p
+
+// 1 (default): fused single-kernel Karel encoder forward where supported; 0: per-layer kernels.
+extern "C" int d2p_conv_set_fused(int mode) {
+    d2p::g_conv_fused = mode;
+    return 0;
+}

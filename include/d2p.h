@@ -79,6 +79,10 @@ int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, float* feat
                          int training, void* ws, size_t ws_bytes, void* stream);
 int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float* dfeat,
                          const float* saved, int training, void* ws, size_t ws_bytes, void* stream);
+/* 1 (default): the Karel geometry (8x8x16 -> 16/32/48 channels) runs as ONE cooperative kernel
+ * (conv -> lrelu -> BatchNorm x3, activations in shared memory, per-slice statistics exchanged
+ * among the CTAs of a slice); 0: one kernel sequence per layer (always used for ViZDoom). */
+int d2p_conv_set_fused(int mode);
 
 /* ---- K2/K3: LSTM over a sequence -------------------------------------------
  * reference models/model_full.py:244-258 (Demo_Encoder), :265-277

@@ -321,3 +321,59 @@ def test_vizdoom_deep_conv_path_matches_oracle():
     orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False, use_tc=False)
     assert eng.F == 432
     _check_step(orc, eng, batch, pm)
+
+
+# ---- schedule variants of the same path must agree ---------------------------------------------
+def _run_variant(cfg, batch, fused, persistent, frames_dtype=np.uint8, is_train=True):
+    from demo2program_b200 import _lib
+    from demo2program_b200.engine import Engine
+    lib = _lib.load()
+    lib.d2p_conv_set_fused(fused)
+    lib.d2p_lstm_set_persistent(persistent)
+    try:
+        eng = Engine(cfg, use_graph=False, frames_dtype=frames_dtype, is_train=is_train)
+        eng.stage_batch(batch)
+        eng.forward()
+        eng.backward()
+        torch.cuda.synchronize()
+        return {'loss': eng.loss.cpu().numpy().copy(), 'feat': eng.feat.cpu().numpy().copy(),
+                'saved': eng.conv_saved.cpu().numpy().copy(), 'state': eng.state.cpu().numpy().copy(),
+                'grads': eng.grads.cpu().numpy().copy()}
+    finally:
+        lib.d2p_conv_set_fused(1)
+        lib.d2p_lstm_set_persistent(1)
+
+
+@pytest.mark.parametrize('B,k,dtype,train', [(32, 10, np.uint8, True),     # C2: 140 CTAs, 2-3 demos each
+                                             (4, 3, np.float32, True),     # fp32 frames as the reference feeds
+                                             (5, 2, np.uint8, False),      # eval: moving statistics, no exchange
+                                             (40, 3, np.uint8, False)])    # eval, several 64-frame chunks per CTA
+def test_fused_conv_encoder_matches_layered(B, k, dtype, train):
+    """The single-kernel Karel encoder forward (conv_fused.cu) against the per-layer kernels:
+    features, saved activations / statistics, BatchNorm moving statistics, and the gradients the
+    (shared) backward derives from what it saved."""
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('full', batch_size=B, k=k)
+    batch = make_batch(cfg, seed=5)
+    if dtype == np.float32:
+        batch = dict(batch)
+        batch['s_h'] = np.asarray(batch['s_h'], np.float32)
+    a = _run_variant(cfg, batch, 0, 1, dtype, train)
+    b = _run_variant(cfg, batch, 1, 1, dtype, train)
+    assert rel_err(b['feat'], a['feat']) < 2e-5
+    assert rel_err(b['saved'], a['saved']) < 2e-5
+    assert rel_err(b['state'], a['state']) < 2e-6
+    assert abs(float(b['loss'][0] - a['loss'][0])) < 1e-5
+    assert rel_err(b['grads'], a['grads']) < 1e-4
+
+
+@pytest.mark.parametrize('model,B,k', [('full', 32, 10), ('full', 4, 3), ('synthesis_baseline', 8, 2)])
+def test_persistent_recurrence_matches_per_step(model, B, k):
+    """lstm_persist.cu (one cooperative kernel per sequence) against one launch per step."""
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config(model, batch_size=B, k=k)
+    batch = make_batch(cfg, seed=9)
+    a = _run_variant(cfg, batch, 1, 0)
+    b = _run_variant(cfg, batch, 1, 1)
+    assert abs(float(b['loss'][0] - a['loss'][0])) < 2e-5
+    assert rel_err(b['grads'], a['grads']) < 1e-4
