@@ -375,14 +375,42 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
 struct BwdArgs {
     const uint8_t* wtpk; int mgp_w;     // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
     uint8_t* dzpk; int mgp_z;           // packed dZ_t [R, 4H]
-    float* partials;                    // [4][R][H] split-K partial sums of dh_{t-1}
     float* gates;                       // [T,R,4H] in: activated gates, out: dZ
     const float* cells; const float* c0; const float* dY;
     const float* dhT; const float* dcT; float* dh0; float* dc0;
     const int* len; int R, T, has_h0;
-    unsigned* sync;                     // [0,8): phase-P counters, [8,16): phase-G counters, [63] error
+    unsigned* sync;                     // [row tiles] dZ_t published counters, [63] error word
 };
 
+// cluster helpers (the 4 K-chunk CTAs of one 64-unit output tile form a cluster)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(cta_rank));
+    float4 v;
+    // no "memory" clobber: the four loads of a reduction stay in flight together; they are
+    // ordered against the cluster barrier (which has one)
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr));
+    return v;
+}
+constexpr int PGROW = PBN + 4;          // staged partial-sum tile row (floats): conflict-free float4 columns
+
+// Backward recurrence.  CTA q of a row tile: output tile nt = q / 4 (64 hidden units), K-chunk
+// ks = q % 4 (= gate ks, 512 gate columns); the 4 K-chunk CTAs of a tile are one CLUSTER.
+// Step t:  phase P - this CTA's 16 hidden units (64 nt + 16 ks ..): dh = carry + the four
+//          partial tiles of the cluster (own + 3 over distributed shared memory, fixed order),
+//          cell backward, dZ_t published as packed operand;
+//          row-tile barrier;
+//          phase G - partial[ks] = dZ_t[:, gate ks] * Wh[tile nt, gate ks]^T into the
+//          accumulator, parked in the (idle) ring for the cluster;
+//          cluster barrier.
+// The partial sums never leave the SMs.  A peer's reads of this CTA's parked tile are over before
+// that peer publishes its dZ, i.e. before this CTA's next bulk copies (which wait for all 32
+// publishers of the row tile) can overwrite the ring.
 __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const BwdArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2];
@@ -390,11 +418,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mt = blockIdx.y, m0 = mt * BM;
     const int q = blockIdx.x, nt = q >> 2, ks = q & 3;     // 64-unit output tile, K-chunk (= gate)
-    const int n0 = nt * PBN, kb0 = ks * PNKB, rot = nt & (PNKB - 1);
+    const int kb0 = ks * PNKB, rot = nt & (PNKB - 1);
     const int H = PH, G4 = 4 * PH, R = a.R;
     const size_t RH = (size_t)R * H;
     unsigned* ctrP = a.sync + mt;
-    unsigned* ctrG = a.sync + 8 + mt;
     unsigned* err = a.sync + 63;
     int rows = R - m0;
     if (rows > BM) rows = BM;
@@ -404,12 +431,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
                                           a.wtpk + (size_t)kb0 * a.mgp_w * 2048 + (size_t)nt * PB_BYTES,
                                           (size_t)a.mgp_w * 2048);
     const uint32_t sbase = smem_u32(smem);
+    float* stage = reinterpret_cast<float*>(smem + P_W_BYTES);          // [128][PGROW] partial tile
+    const uint32_t stage_u32 = sbase + (uint32_t)P_W_BYTES;
     RingPos rp{0, 0};
 
     // phase-P item of this thread: (row, 4 hidden units) of units [16 q, 16 q + 16)
-    const int row = tid >> 2, u = q * PUPT + (tid & 3) * 4, r = m0 + row;
+    const int row = tid >> 2, up = (tid & 3) * 4, u = q * PUPT + up, r = m0 + row;
     const bool valid = r < R;
     const size_t su = (size_t)(valid ? r : 0) * H + u;
+    // my 16 B of each partial tile: row `row`, tile columns 16 ks + up .. + 4
+    const uint32_t my_part = stage_u32 + (uint32_t)((row * PGROW + ks * PUPT + up) * sizeof(float));
     float dhc[4] = {0.f, 0.f, 0.f, 0.f}, dcc[4] = {0.f, 0.f, 0.f, 0.f};
     int mylen = 0;
     if (valid) {
@@ -417,6 +448,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         if (a.dhT) ld4r(a.dhT + su, dhc);
         if (a.dcT) ld4r(a.dcT + su, dcc);
     }
+    cluster_sync_all();      // every CTA of the cluster is resident and set up before any remote access
     int ground = 0;          // GEMM rounds completed so far
     bool have_partials = false;
     for (int t = a.T - 1; t >= 0; --t) {
@@ -426,7 +458,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         float* g = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u;
         float gi[4], gj[4], gf[4], go[4], cc[4], cp[4], dy[4];
         const bool live = valid && t < mylen;
-        if (live) {   // operands that do not depend on the previous step: fetch before waiting
+        if (live) {
             ld4r(g, gi); ld4r(g + H, gj); ld4r(g + 2 * H, gf); ld4r(g + 3 * H, go);
             ld4r(a.cells + (size_t)t * RH + su, cc);
             if (t > 0) ld4r(a.cells + (size_t)(t - 1) * RH + su, cp);
@@ -435,17 +467,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             if (a.dY) ld4r(a.dY + (size_t)t * RH + su, dy);
             else { dy[0] = dy[1] = dy[2] = dy[3] = 0.f; }
         }
-        if (have_partials) {
-            if (tid == 0) { grid_wait(ctrG, (unsigned)(PCOLS * ground), err); pstamp(step, 17); }
-            __syncthreads();
-            if (valid) {
-                const float4 p0 = ldcg4(a.partials + su), p1 = ldcg4(a.partials + RH + su);
-                const float4 p2 = ldcg4(a.partials + 2 * RH + su), p3 = ldcg4(a.partials + 3 * RH + su);
-                dhc[0] += p0.x; dhc[1] += p0.y; dhc[2] += p0.z; dhc[3] += p0.w;
-                dhc[0] += p1.x; dhc[1] += p1.y; dhc[2] += p1.z; dhc[3] += p1.w;
-                dhc[0] += p2.x; dhc[1] += p2.y; dhc[2] += p2.z; dhc[3] += p2.w;
-                dhc[0] += p3.x; dhc[1] += p3.y; dhc[2] += p3.z; dhc[3] += p3.w;
-            }
+        if (have_partials && valid) {
+            const float4 p0 = ld_dsmem4(my_part, 0u), p1 = ld_dsmem4(my_part, 1u);
+            const float4 p2 = ld_dsmem4(my_part, 2u), p3 = ld_dsmem4(my_part, 3u);
+            // fixed order: K-chunks 0..3
+            dhc[0] += p0.x; dhc[1] += p0.y; dhc[2] += p0.z; dhc[3] += p0.w;
+            dhc[0] += p1.x; dhc[1] += p1.y; dhc[2] += p1.z; dhc[3] += p1.w;
+            dhc[0] += p2.x; dhc[1] += p2.y; dhc[2] += p2.z; dhc[3] += p2.w;
+            dhc[0] += p3.x; dhc[1] += p3.y; dhc[2] += p3.z; dhc[3] += p3.w;
         }
         if (tid == 64) pstamp(step, 18);
         float di[4], dj[4], df[4], dq[4];
@@ -453,7 +482,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float dht = dhc[e] + dy[e];
-                const float tcn = tanh_fast(cc[e]);
+                const float tcn = tanh_p(cc[e]);
                 dq[e] = dht * tcn * go[e] * (1.f - go[e]);
                 const float dct = dcc[e] + dht * go[e] * (1.f - tcn * tcn);
                 di[e] = dct * gj[e] * gi[e] * (1.f - gi[e]);
@@ -496,41 +525,34 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) pstamp(step, 22);
-        {
+        {   // accumulator ([A*Bhi + Alo*Bhi | Ahi*Blo]) -> the idle ring, one row per thread
             const int lq = warp & 3, cg = warp >> 2;
             uint32_t v[PUPT], w[PUPT];
             tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cg * PUPT), v);
             tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(PBN + cg * PUPT), w);
             tmem_ld_wait();
-            const int orow = m0 + lq * 32 + lane;
-            if (orow < R) {
-                float* dst = a.partials + (size_t)ks * RH + (size_t)orow * H + n0 + cg * PUPT;
+            float* dst = stage + (size_t)(lq * 32 + lane) * PGROW + cg * PUPT;
 #pragma unroll
-                for (int j = 0; j < PUPT; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) =
-                        make_float4(__uint_as_float(v[j]) + __uint_as_float(w[j]),
-                                    __uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1]),
-                                    __uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2]),
-                                    __uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3]));
-            }
+            for (int j = 0; j < PUPT; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(__uint_as_float(v[j]) + __uint_as_float(w[j]),
+                                __uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1]),
+                                __uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2]),
+                                __uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (tid == 64) pstamp(step, 23);
-        __syncthreads();
+        cluster_sync_all();      // the four partial tiles of the cluster are parked and visible
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0) { __threadfence(); red_relaxed(ctrG, 1u); pstamp(step, 24); }
+        if (tid == 0) pstamp(step, 24);
         ++ground;
         have_partials = true;
     }
-    if (have_partials) {   // dh0 = carry + last partial sums
-        if (tid == 0) grid_wait(ctrG, (unsigned)(PCOLS * ground), err);
-        __syncthreads();
-        if (valid) {
+    if (have_partials && valid) {   // dh0 = carry + last partial sums
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const float4 p = ldcg4(a.partials + (size_t)s * RH + su);
-                dhc[0] += p.x; dhc[1] += p.y; dhc[2] += p.z; dhc[3] += p.w;
-            }
+        for (int sc = 0; sc < 4; ++sc) {
+            const float4 p = ld_dsmem4(my_part, (uint32_t)sc);
+            dhc[0] += p.x; dhc[1] += p.y; dhc[2] += p.z; dhc[3] += p.w;
         }
     }
     if (valid) {
@@ -538,7 +560,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         st4r(a.dc0 + su, dcc);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();      // no CTA leaves while a peer may still read its shared memory
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
 }
@@ -546,17 +568,27 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
 int g_persist_mode = 1;   // 0 = per-step launches, 1 = persistent kernels where supported
 
 template <class Args>
-int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args) {
+int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args,
+                int cluster_x = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(PTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (g_persist_mode != 2) {   // mode 2 (experiment): plain launch
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_persist_mode == 2 ? 0 : 1;   // mode 2 (experiment): plain launch
+    cfg.numAttrs = n;
     D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     count_launch();
     return 0;
@@ -615,9 +647,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     const size_t zbytes = (size_t)kgp_of(G4) * mgp_z * 256;
     BwdArgs a;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
-    a.partials = (float*)tc_scratch_alloc(st, &off, (size_t)4 * R * H * sizeof(float));
     a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
-    D2P_REQUIRE(a.dzpk && a.partials && a.sync, "lstm persist bwd: tensor-core scratch arena too small");
+    D2P_REQUIRE(a.dzpk && a.sync, "lstm persist bwd: tensor-core scratch arena too small");
     const void* wtpk;
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
@@ -631,7 +662,7 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
                                             (int)P_SMEM));
         attr_set = true;
     }
-    return launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a);
+    return launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a, 4);
 }
 
 }  // namespace d2p

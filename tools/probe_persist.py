@@ -16,8 +16,8 @@ lib.d2p_tc_configure(ptr(scratch), scratch.numel(), ptr(cache), cache.numel(), 1
 lib.d2p_lstm_set_persistent(1)
 FW = ['top', 'grid barrier passed', 'last bulk copy issued', 'last MMA issued', None, 'accum ready',
       'cell math done', 'packed h stores issued', 'arrive issued', 'copy-out stores issued']
-BW = ['top', 'G-barrier passed', 'partials summed', 'dZ stores issued', 'P arrive issued', 'P-barrier passed',
-      'accum ready', 'partials stored', 'G arrive issued']
+BW = ['top', None, 'cluster partials summed (DSMEM)', 'packed dZ stores issued', 'publish (arrive) issued',
+      'row-tile barrier passed', 'accum ready', 'partial tile parked in ring', 'cluster barrier passed']
 
 for (T, R) in [(20, 320), (50, 32)]:
     In = 512
@@ -55,4 +55,5 @@ for (T, R) in [(20, 320), (50, 32)]:
             print('   %-28s +%d' % (n, p[i] - p[0]))
     print('== backward step 5')
     for i, n in enumerate(BW):
-        print('   %-28s +%d' % (n, p[16 + i] - p[16]))
+        if n:
+            print('   %-34s +%d' % (n, p[16 + i] - p[16]))
