@@ -345,6 +345,25 @@ int get_packed(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_co
     return 0;
 }
 
+size_t tc_scratch_capacity(cudaStream_t st) {
+    size_t cap = g_tc.scratch_bytes;
+    for (int i = 0; i < g_tc.n_streams; ++i)
+        if (g_tc.per_stream[i].st == st) cap = g_tc.per_stream[i].bytes;
+    return cap;
+}
+
+// Packed operands in, heuristic split-K with partial sums from the stream's arena.
+int gemm_tc_packed_auto(cudaStream_t st, const void* Apk, const void* Bpk, int M, int N, int K, float alpha,
+                        float beta, float* C, int ldc, size_t* scratch_off) {
+    int ks = auto_ksplit(M, N, K);
+    float* part = nullptr;
+    if (ks > 1) {
+        part = (float*)tc_scratch_alloc(st, scratch_off, (size_t)ks * M * N * sizeof(float));
+        if (!part) ks = 1;
+    }
+    return gemm_tc_packed(st, Apk, Bpk, M, N, K, alpha, beta, C, ldc, nullptr, ks, part);
+}
+
 bool tc_eligible(int M, int N, int K) {
     if (!tc_available()) return false;
     if ((double)M * N * K < (double)(1 << 18)) return false;   // tiny: SIMT engine

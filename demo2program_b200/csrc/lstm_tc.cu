@@ -397,9 +397,26 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     }
     if (!(phases & D2P_LSTM_BWD_PARAMS)) return 0;
     // parameter gradients from the full dZ
-    D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
-    if (T > 1)
-        D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
+    const size_t shared_need = al256(packed_bytes(G4, T * R)) + al256(packed_bytes(In, T * R)) +
+                               al256(packed_bytes(H, T * R)) + 2 * al256((size_t)8 * (In > H ? In : H) * G4 * 4);
+    if (tc_available() && R % BK == 0 && T > 1 && tc_eligible(In, G4, T * R) && tc_eligible(H, G4, (T - 1) * R) &&
+        shared_need <= tc_scratch_capacity(st)) {
+        // dWx = X^T dZ and dWh = Y[0..T-2]^T dZ[1..T-1] contract over the (time, row) axis of the
+        // same dZ: pack it ONCE (k-blocks are whole time-row groups when R % 64 == 0; the
+        // recurrent product starts R / 64 k-blocks in)
+        size_t off = 0;
+        const void *zpk, *xpk, *ypk;
+        D2P_TRY(get_packed(st, gates, G4, T * R, G4, false, false, &off, &zpk));
+        D2P_TRY(get_packed(st, X, In, T * R, In, false, false, &off, &xpk));
+        D2P_TRY(gemm_tc_packed_auto(st, xpk, zpk, In, G4, T * R, 1.f, 1.f, dWx, G4, &off));
+        D2P_TRY(get_packed(st, Y, H, (T - 1) * R, H, false, false, &off, &ypk));
+        const uint8_t* zsub = (const uint8_t*)zpk + (size_t)(R / BK) * mgp_of(G4) * 2048;
+        D2P_TRY(gemm_tc_packed_auto(st, ypk, zsub, H, G4, (T - 1) * R, 1.f, 1.f, dWh, G4, &off));
+    } else {
+        D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
+        if (T > 1)
+            D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
+    }
     if (h0) D2P_TRY(gemm(st, true, false, H, G4, R, 1.f, h0, H, gates, G4, 1.f, dWh, G4));
     D2P_TRY(colsum(st, gates, (long long)T * R, G4, db, 1.f, ws, ws_bytes));
     return 0;

@@ -33,21 +33,29 @@ __global__ void gather_shifted_kernel(const float* __restrict__ table, int vocab
 // dTable[v, e] += sum_{(t,r): id(t,r) == v} dX[t,r,e], two-stage and in a fixed
 // order (deterministic): stage 1 reduces a chunk of positions per block into
 // partial[chunk, v, e]; stage 2 sums the chunks.
-__global__ void embedding_bwd_partial(const float* __restrict__ dX, int vocab_rows, int E,
-                                      const int* __restrict__ tokens, int R, int L, int start_id,
-                                      int pos_per_chunk, float* __restrict__ partial) {
-    const int chunk = blockIdx.x, v = blockIdx.y;
+// Block (chunk, 128-wide slice of E): one pass over the chunk's positions, every dX element is
+// read once; thread e owns column e of a [vocab_rows][128] shared-memory accumulator, so the
+// position order (hence the result) is fixed.
+constexpr int EB_COLS = 128;
+__global__ void __launch_bounds__(EB_COLS)
+embedding_bwd_partial(const float* __restrict__ dX, int vocab_rows, int E,
+                      const int* __restrict__ tokens, int R, int L, int start_id,
+                      int pos_per_chunk, float* __restrict__ partial) {
+    extern __shared__ float eb_acc[];   // [vocab_rows][EB_COLS]
+    const int chunk = blockIdx.x, e = blockIdx.y * EB_COLS + threadIdx.x;
+    for (int v = 0; v < vocab_rows; ++v) eb_acc[v * EB_COLS + threadIdx.x] = 0.f;
     const int p0 = chunk * pos_per_chunk;
     int p1 = p0 + pos_per_chunk;
     if (p1 > L * R) p1 = L * R;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        float acc = 0.f;
+    if (e < E) {
+        int t = p0 / R, r = p0 - t * R;
         for (int p = p0; p < p1; ++p) {
-            int t = p / R, r = p % R;
-            int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
-            if (id == v) acc += dX[(size_t)p * E + e];
+            const int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
+            if (id >= 0 && id < vocab_rows) eb_acc[id * EB_COLS + threadIdx.x] += dX[(size_t)p * E + e];
+            if (++r == R) { r = 0; ++t; }
         }
-        partial[((size_t)chunk * vocab_rows + v) * E + e] = acc;
+        for (int v = 0; v < vocab_rows; ++v)
+            partial[((size_t)chunk * vocab_rows + v) * E + e] = eb_acc[v * EB_COLS + threadIdx.x];
     }
 }
 
@@ -262,8 +270,10 @@ extern "C" int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, con
     int ppc;
     int nchunk = embed_chunks(R, L, &ppc);
     D2P_REQUIRE(ws_bytes >= (size_t)nchunk * vocab_rows * E * sizeof(float), "embed bwd: workspace too small");
-    embedding_bwd_partial<<<dim3(nchunk, vocab_rows), 256, 0, st>>>(dX, vocab_rows, E, tokens, R, L,
-                                                                    start_id, ppc, (float*)ws);
+    const size_t eb_smem = (size_t)vocab_rows * EB_COLS * sizeof(float);
+    D2P_REQUIRE(eb_smem <= 48 * 1024, "embed bwd: vocabulary of %d rows too large", vocab_rows);
+    embedding_bwd_partial<<<dim3(nchunk, cdiv(E, EB_COLS)), EB_COLS, eb_smem, st>>>(
+        dX, vocab_rows, E, tokens, R, L, start_id, ppc, (float*)ws);
     D2P_CHECK_LAUNCH();
     int n = vocab_rows * E;
     embedding_bwd_reduce<<<cdiv(n, 256), 256, 0, st>>>((const float*)ws, nchunk, n, dTable);

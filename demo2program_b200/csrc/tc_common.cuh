@@ -267,5 +267,8 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
 int get_packed(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_contig, bool is_const,
                size_t* scratch_off, const void** out, int gate_tile = 0, int gate_H = 0);
 void* tc_scratch_alloc(cudaStream_t st, size_t* scratch_off, size_t bytes);
+size_t tc_scratch_capacity(cudaStream_t st);
+int gemm_tc_packed_auto(cudaStream_t st, const void* Apk, const void* Bpk, int M, int N, int K, float alpha,
+                        float beta, float* C, int ldc, size_t* scratch_off);
 
 }  // namespace d2p

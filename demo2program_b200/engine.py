@@ -73,7 +73,10 @@ class Engine:
                                         device=self.dev)
         # side streams for the independent branches (three decoders, two RN pools)
         self.concurrent = bool(concurrent)
-        self.side_streams = [torch.cuda.Stream(self.dev) for _ in range(3)] if self.concurrent else []
+        self.side_streams = [torch.cuda.Stream(self.dev, priority=-1) for _ in range(3)] if self.concurrent else []
+        # the latency-bound chain runs at high priority; the throughput-bound weight-gradient
+        # products (grad_stream, default = lowest priority) fill whatever SMs are left
+        self.main_stream = torch.cuda.Stream(self.dev, priority=-1) if self.concurrent else None
         self.grad_stream = torch.cuda.Stream(self.dev) if self.concurrent else None
         for s_ in self.side_streams + ([self.grad_stream] if self.concurrent else []):
             self._ws_side[s_.cuda_stream] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
@@ -271,6 +274,18 @@ class Engine:
         with torch.cuda.stream(self.grad_stream):
             self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, None, 2)
 
+    def _deferred(self, fn):
+        """Run parameter-gradient-only work behind the current stream's work, on the
+        (low-priority) gradient stream: it is joined once, before the optimizer."""
+        if not self.concurrent:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.grad_stream.wait_event(ev)
+        with torch.cuda.stream(self.grad_stream):
+            fn()
+
     def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc):
         self._call('d2p_gemm', int(ta), int(tb), M, N, K, alpha, ptr(A), lda, ptr(Bm), ldb, beta,
                    ptr(Cm), ldc, None, self._st())
@@ -361,6 +376,11 @@ class Engine:
             self._lstm_fwd(q['X'], T, R, H, self.d_demo_len, None, None,
                            'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, phases=1)
 
+        # the frame encoder is one cooperative kernel over (nearly) all SMs: the side branches
+        # fork behind it and overlap the encoder recurrence (96 of 148 SMs) instead
+        call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
+             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
+        self._stamp('conv fwd done')
         self._ev_prog_in = None
         if self.concurrent:
             main = torch.cuda.current_stream(self.dev)
@@ -383,9 +403,6 @@ class Engine:
             if self.model == 'full':
                 act_in()
                 per_in()
-        call('d2p_conv_encoder_fwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.feat),
-             ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
-        self._stamp('conv fwd done')
         self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc)
         self._stamp('encoder lstm fwd done')
@@ -491,15 +508,17 @@ class Engine:
 
         def prog_bwd():
             Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
-                       self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V)
+            self._deferred(lambda: self._gemm(
+                1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
+                self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V))
             self._gemm(0, 1, L * B, H, V, 1.0, p['dlogits'], V, Wp, V, 0.0, p['dy'], H)
             self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
                            'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
                            p['dX'])
-            call('d2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
-                 ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-                 self.ws_bytes, S())
+            self._deferred(lambda: call(
+                'd2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
+                ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                self.ws_bytes, S()))
             # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
             self._stamp('program decoder bwd done')
 
@@ -520,27 +539,32 @@ class Engine:
 
             def act_bwd():
                 Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
-                self._gemm(1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
-                           self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A)
+                self._deferred(lambda: self._gemm(
+                    1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
+                    self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A))
                 self._gemm(0, 1, T * R, H, A, 1.0, a['dlogits'], A, Wa, A, 0.0, a['dy'], H)
                 self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
                                'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
                                a['dX'])
-                call('d2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
-                     ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-                     self.ws_bytes, S())
+                self._deferred(lambda: call(
+                    'd2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
+                    ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                    self.ws_bytes, S()))
                 self._stamp('action decoder bwd done')
 
             def per_bwd():
                 Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
-                self._gemm(1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
-                           self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd)
+                self._deferred(lambda: self._gemm(
+                    1, 0, H, Pd, T * R, 1.0, q['y'], H, q['dlogits'], Pd, 1.0,
+                    self.G('Per_Decoder/dynamic_decoder/output_projection/kernel'), Pd))
                 self._gemm(0, 1, T * R, H, Pd, 1.0, q['dlogits'], Pd, Wq, Pd, 0.0, q['dy'], H)
                 self._lstm_bwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
                                'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, q['dy'], None, None,
                                q['dX'])
-                call('d2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
-                     ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, S())
+                # Per_Encoder fc + BatchNorm: parameter gradients only (its input is data)
+                self._deferred(lambda: call(
+                    'd2p_fc_bn_bwd', ptr(q['per_tm']), T * R, Pd, H, 1, k, 0, C.byref(self.per_fc),
+                    ptr(q['dX']), ptr(q['fc_saved']), None, tr, ptr(self.ws), self.ws_bytes, S()))
                 self._stamp('per decoder bwd done')
 
             # The summary pools only need the program decoder's (dh0, dc0): back-propagate them
@@ -612,10 +636,20 @@ class Engine:
 
     # ------------------------------------------------------------------ steps
     def _step_body(self, with_opt):
-        self.forward()
-        self.backward()
-        if with_opt:
-            self.optimizer_step()
+        if self.main_stream is None:
+            self.forward()
+            self.backward()
+            if with_opt:
+                self.optimizer_step()
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self.main_stream.wait_stream(cur)
+        with torch.cuda.stream(self.main_stream):
+            self.forward()
+            self.backward()
+            if with_opt:
+                self.optimizer_step()
+        cur.wait_stream(self.main_stream)
 
     def _capture(self, fn):
         """Warm up `fn` on a side stream (lazy module loading), then capture it."""

@@ -7,6 +7,11 @@ from demo2program_b200.config import karel_config
 from demo2program_b200.engine import Engine
 from demo2program_b200.synthetic import make_batch
 
+import os
+from demo2program_b200 import _lib
+# ncu cannot launch a kernel that is both cooperative and clustered (LaunchFailed): profile the
+# persistent kernels with a plain launch (mode 2; launches are serialised under ncu anyway)
+_lib.load().d2p_lstm_set_persistent(int(os.environ.get('D2P_PERSIST', '2')))
 cfg = karel_config('full', batch_size=32, k=10)
 eng = Engine(cfg, use_graph=False)
 batch = make_batch(cfg, seed=123)
