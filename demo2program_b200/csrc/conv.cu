@@ -32,6 +32,11 @@ int unpermute_frames(cudaStream_t, const float*, float*, int, int, int, int);
 bool conv_fused_supported(const d2p_conv_desc* d, int training, size_t ws_bytes);
 int conv_fused_fwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, float* feat, float* saved,
                    int training, void* ws);
+bool conv_fused_bwd_supported(const d2p_conv_desc* d, int training, size_t ws_bytes);
+size_t conv_fused_ws_bytes(const d2p_conv_desc* d);
+size_t conv_fused_bwd_ws_bytes(const d2p_conv_desc* d);
+int conv_fused_bwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, const float* dfeat,
+                   const float* saved, void* ws);
 
 namespace {
 
@@ -192,6 +197,11 @@ static void make_plan(const d2p_conv_desc* d, Plan* p) {
         size_t m = bn > dw ? bn : dw; if (cs > m) m = cs;
         if (m > max_part) max_part = m;
     }
+    if (d->n_layers == 3 && d->h == 8 && d->w == 8 && d->d == 16 && d->k >= 1 && d->k <= kNumSMs) {
+        // exchange buffers of the fused single-kernel Karel paths (conv_fused.cu)
+        if (conv_fused_ws_bytes(d) > max_part) max_part = conv_fused_ws_bytes(d);
+        if (conv_fused_bwd_ws_bytes(d) > max_part) max_part = conv_fused_bwd_ws_bytes(d);
+    }
     size_t dyf = max_act > max_in ? max_act : max_in;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     p->off_dz = 0;
@@ -312,6 +322,8 @@ extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, 
     Plan p; make_plan(d, &p);
     D2P_REQUIRE(ws_bytes >= p.total, "conv bwd: workspace too small (%zu < %zu)", ws_bytes, p.total);
     char* wsb = (char*)ws;
+    if (conv_fused_bwd_supported(d, training, p.part_bytes))
+        return conv_fused_bwd(st, d, frames, dfeat, saved, wsb + p.off_part);
     const float* acts[D2P_MAX_CONV_LAYERS]; const float* stats[D2P_MAX_CONV_LAYERS];
     const float* sp = saved;
     for (int l = 0; l < d->n_layers; ++l) {

@@ -342,6 +342,310 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
     }
 }
 
+// =====================================================================================
+// Fused backward of the same three layers (training mode): dfeat -> BatchNorm
+// backward -> lrelu' -> {bias, weight, input} gradients, layer 3 down to layer 1, with the
+// activations, their gradients and the weights in shared memory.  Same grid as the forward
+// (a CTA owns whole demonstrations of one BatchNorm slice): the per-slice sums of the
+// BatchNorm backward are exchanged among the CTAs of a slice (three counter barriers), every
+// CTA leaves its partial weight / bias gradients in the workspace, and after one grid-wide
+// barrier the partials are summed in a fixed order by all CTAs (deterministic).
+// =====================================================================================
+constexpr int KB_MAXF = 60;
+constexpr int KB_A1 = KB_MAXF * 256, KB_A2 = KB_MAXF * 128, KB_A3 = KB_MAXF * 48;
+// float offsets: A1 | D1 (A3, D3 alias its head) | A2 | D2 (u8 frames alias A2+D2) | W | red | misc
+constexpr int KB_OFF_A1 = 0, KB_OFF_D1 = KB_A1, KB_OFF_A2 = 2 * KB_A1, KB_OFF_D2 = KB_OFF_A2 + KB_A2;
+// weights are staged with padded rows (W3: 52 floats per (tap, ci) row, W2: 36) so that lanes that walk
+// consecutive rows with 16-byte loads fall into different banks
+constexpr int KB_W3S = 52, KB_W2S = 36, KB_WBUF = 128 * KB_W3S;
+constexpr int KB_OFF_W = KB_OFF_D2 + KB_A2, KB_OFF_RED = KB_OFF_W + KB_WBUF, KB_OFF_MISC = KB_OFF_RED + KF_RED;
+constexpr size_t KB_SMEM = (size_t)(KB_OFF_MISC + 1024) * sizeof(float);
+// per-CTA partial gradients: dW1 | dW2 | dW3 (4 live taps) | db1 | db2 | db3
+constexpr int KB_P_W1 = 0, KB_P_W2 = KF_W1, KB_P_W3 = KF_W1 + KF_W2, KB_P_B1 = KB_P_W3 + KF_W3;
+constexpr int KB_P_B2 = KB_P_B1 + 16, KB_P_B3 = KB_P_B2 + 32, KB_PART = KB_P_B3 + 48;
+
+struct KbLayer {
+    const float* w; const float* gamma; const float* act; const float* stats;
+    float* dw; float* db; float* dgamma; float* dbeta;
+};
+struct KbArgs {
+    const void* frames; int frames_u8; const float* dfeat;
+    int B, k, T, gs;
+    KbLayer L[3];
+    float2* partials;    // [3][k][gs][48] per-CTA (sum dy, sum dy*xhat)
+    float2* totals;      // [3][k][48] per-slice totals
+    float* part;         // [grid][KB_PART] per-CTA partial weight / bias gradients
+    unsigned* sync;      // [3*k] slice counters, [61] grid counter, [63] error word
+};
+
+// red[0..C) <- per-channel sums over this CTA's rows of f(row, channel) (two values), fixed order
+template <int C, class F>
+__device__ __forceinline__ void kb_col_sums(int rows, float* red, float2* out, F f) {
+    constexpr int G = KF_THREADS / C;
+    const int tid = threadIdx.x, c = tid % C, g = tid / C;
+    if (g < G) {
+        float s = 0.f, s2 = 0.f;
+        for (int r = g; r < rows; r += G) { const float2 v = f(r, c); s += v.x; s2 += v.y; }
+        red[(g * C + c) * 2] = s; red[(g * C + c) * 2 + 1] = s2;
+    }
+    __syncthreads();
+    if (tid < C) {
+        double s = 0.0, s2 = 0.0;
+        for (int gg = 0; gg < G; ++gg) { s += red[(gg * C + tid) * 2]; s2 += red[(gg * C + tid) * 2 + 1]; }
+        out[tid] = make_float2((float)s, (float)s2);
+    }
+    __syncthreads();
+}
+
+// BatchNorm backward + lrelu' of one layer, in place: D <- dz.  mean/rstd/coef vectors in `v`
+// (shared): v[0..C) mean, [C..2C) rstd, [2C..3C) gamma*rstd, [3C..4C) k1, [4C..5C) k2.
+template <int C>
+__device__ __forceinline__ void kb_bn_bwd(const KbArgs& a, int l, int slice, int j, const float* A, float* D,
+                                          int rows, int pixels, float* red, float* v, float* part_db) {
+    const int tid = threadIdx.x;
+    const KbLayer& L = a.L[l];
+    const int kC = a.k * C;
+    if (tid < C) {
+        v[tid] = L.stats[slice * C + tid];
+        v[C + tid] = L.stats[kC + slice * C + tid];
+        v[2 * C + tid] = L.gamma[tid] * v[C + tid];
+    }
+    __syncthreads();
+    float2* mine = a.partials + ((size_t)(l * a.k + slice) * a.gs + j) * 48;
+    kb_col_sums<C>(rows, red, mine, [&](int r, int c) {
+        const float dy = D[(size_t)r * C + c];
+        return make_float2(dy, dy * (A[(size_t)r * C + c] - v[c]) * v[C + c]);
+    });
+    unsigned* ctr = a.sync + l * a.k + slice;
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        kf_wait(ctr, (unsigned)a.gs, a.sync + 63);
+    }
+    __syncthreads();
+    if (tid < C) {
+        double s = 0.0, s2 = 0.0;
+        const float2* p = a.partials + (size_t)(l * a.k + slice) * a.gs * 48 + tid;
+        for (int jj = 0; jj < a.gs; ++jj) { const float2 q = __ldcg(p + (size_t)jj * 48); s += q.x; s2 += q.y; }
+        const double count = (double)a.B * a.T * pixels;
+        v[3 * C + tid] = (float)(s / count);
+        v[4 * C + tid] = (float)(s2 / count);
+        if (j == 0) a.totals[(l * a.k + slice) * 48 + tid] = make_float2((float)s, (float)s2);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rows * C; idx += KF_THREADS) {
+        const int c = idx % C;
+        const float act = A[idx];
+        const float xhat = (act - v[c]) * v[C + c];
+        const float da = v[2 * C + c] * (D[idx] - v[3 * C + c] - xhat * v[4 * C + c]);
+        D[idx] = da * lrelu_grad_from_out(act);
+    }
+    __syncthreads();
+    // bias gradient partial: column sums of dz
+    float2* tmp = reinterpret_cast<float2*>(red + KF_RED - 128);
+    kb_col_sums<C>(rows, red, tmp, [&](int r, int c) { return make_float2(D[(size_t)r * C + c], 0.f); });
+    if (tid < C) part_db[tid] = tmp[tid].x;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* A1 = sm + KB_OFF_A1; float* D1 = sm + KB_OFF_D1;
+    float* A3 = D1; float* D3 = D1 + KB_A3;                 // dead before dy1 is written
+    float* A2 = sm + KB_OFF_A2; float* D2 = sm + KB_OFF_D2;
+    uint8_t* FR = reinterpret_cast<uint8_t*>(A2);            // frames (layer 1), A2/D2 dead by then
+    float* Ws = sm + KB_OFF_W;
+    float* red = sm + KB_OFF_RED;
+    float* misc = sm + KB_OFF_MISC;                          // [0,256) BN vectors | [256,352) sc/sh of the input layer
+    float* scin = misc + 256; float* shin = misc + 320;
+    const int tid = threadIdx.x;
+    const int slice = blockIdx.x / a.gs, j = blockIdx.x % a.gs;
+    const int b0 = (int)((long long)j * a.B / a.gs), b1 = (int)((long long)(j + 1) * a.B / a.gs);
+    const int nfr = (b1 - b0) * a.T;
+    const int R = a.B * a.k;
+    float* mypart = a.part + (size_t)blockIdx.x * KB_PART;
+    auto frame_n = [&](int f) { return ((size_t)(b0 + f / a.T) * a.k + slice) * a.T + f % a.T; };
+
+    // ---- load saved activations, dfeat, W3 ----
+    for (int idx = tid; idx < nfr * 64; idx += KF_THREADS)
+        *reinterpret_cast<float4*>(A1 + (size_t)idx * 4) =
+            *reinterpret_cast<const float4*>(a.L[0].act + frame_n(idx >> 6) * 256 + (idx & 63) * 4);
+    for (int idx = tid; idx < nfr * 32; idx += KF_THREADS)
+        *reinterpret_cast<float4*>(A2 + (size_t)idx * 4) =
+            *reinterpret_cast<const float4*>(a.L[1].act + frame_n(idx >> 5) * 128 + (idx & 31) * 4);
+    for (int idx = tid; idx < nfr * 12; idx += KF_THREADS) {
+        const int f = idx / 12, q = idx % 12;
+        *reinterpret_cast<float4*>(A3 + (size_t)idx * 4) =
+            *reinterpret_cast<const float4*>(a.L[2].act + frame_n(f) * 48 + q * 4);
+        const int r = (b0 + f / a.T) * a.k + slice, t = f % a.T;
+        *reinterpret_cast<float4*>(D3 + (size_t)idx * 4) =
+            *reinterpret_cast<const float4*>(a.dfeat + ((size_t)t * R + r) * 48 + q * 4);
+    }
+    for (int i = tid; i < KF_W3; i += KF_THREADS) {
+        const int tap = i / (32 * 48), rem = i % (32 * 48);
+        Ws[(i / 48) * KB_W3S + i % 48] = a.L[2].w[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem];
+    }
+    if (tid < 32) {   // BatchNorm of layer 2 as applied to conv3's input
+        scin[tid] = a.L[1].stats[2 * a.k * 32 + slice * 32 + tid];
+        shin[tid] = a.L[1].stats[3 * a.k * 32 + slice * 32 + tid];
+    }
+    __syncthreads();
+
+    // ================= layer 3 =================
+    kb_bn_bwd<48>(a, 2, slice, j, A3, D3, nfr, 1, red, misc, mypart + KB_P_B3);
+    // dW3[tap][ci][co] = sum_f x2n[f][tap][ci] * dz3[f][co]
+    if (tid < 480) {
+        const int co = tid % 48, g = tid / 48;
+        for (int pr = g; pr < 128; pr += 10) {           // pr = tap*32 + ci
+            const int ci = pr & 31;
+            const float sc = scin[ci], sh = shin[ci];
+            float acc = 0.f;
+            for (int f = 0; f < nfr; ++f)
+                acc = fmaf(fmaf(A2[(size_t)f * 128 + pr], sc, sh), D3[(size_t)f * 48 + co], acc);
+            mypart[KB_P_W3 + pr * 48 + co] = acc;
+        }
+    }
+    // dy2[f][tap][ci] = sum_co dz3[f][co] * W3[tap][ci][co]
+    for (int idx = tid; idx < nfr * 128; idx += KF_THREADS) {
+        const int f = idx >> 7, pr = idx & 127;
+        const float* w = Ws + pr * KB_W3S;
+        const float* dz = D3 + (size_t)f * 48;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
+            const float4 dd = *reinterpret_cast<const float4*>(dz + q * 4);
+            acc = fmaf(ww.x, dd.x, acc); acc = fmaf(ww.y, dd.y, acc); acc = fmaf(ww.z, dd.z, acc); acc = fmaf(ww.w, dd.w, acc);
+        }
+        D2[idx] = acc;
+    }
+    __syncthreads();
+    // ================= layer 2 =================
+    for (int i = tid; i < KF_W2; i += KF_THREADS) Ws[(i >> 5) * KB_W2S + (i & 31)] = a.L[1].w[i];
+    if (tid < 16) {
+        scin[tid] = a.L[0].stats[2 * a.k * 16 + slice * 16 + tid];
+        shin[tid] = a.L[0].stats[3 * a.k * 16 + slice * 16 + tid];
+    }
+    kb_bn_bwd<32>(a, 1, slice, j, A2, D2, nfr * 4, 4, red, misc, mypart + KB_P_B2);
+    // dW2[tap][ci][co] = sum_{f, opx valid} x1n[f][ipx][ci] * dz2[f][opx][co]
+    {
+        const int co = tid & 31, g = tid >> 5;             // 16 groups
+        for (int pr = g; pr < 144; pr += 16) {             // pr = tap*16 + ci
+            const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
+            const float sc = scin[ci], sh = shin[ci];
+            float acc = 0.f;
+            for (int oh = 0; oh < 2; ++oh) {
+                const int ih = 2 * oh + kh;
+                if (ih >= 4) continue;
+                for (int ow = 0; ow < 2; ++ow) {
+                    const int iw = 2 * ow + kw;
+                    if (iw >= 4) continue;
+                    const float* xa = A1 + (ih * 4 + iw) * 16 + ci;
+                    const float* dz = D2 + (oh * 2 + ow) * 32 + co;
+                    for (int f = 0; f < nfr; ++f)
+                        acc = fmaf(fmaf(xa[(size_t)f * 256], sc, sh), dz[(size_t)f * 128], acc);
+                }
+            }
+            mypart[KB_P_W2 + pr * 32 + co] = acc;
+        }
+    }
+    __syncthreads();   // A3 / D3 (aliasing D1) are dead from here
+    // dy1[f][ipx][ci] = sum_{(opx, tap): ipx = 2 opx + tap} sum_co dz2[f][opx][co] * W2[tap][ci][co]
+    for (int idx = tid; idx < nfr * 256; idx += KF_THREADS) {
+        const int f = idx >> 8, ipx = (idx >> 4) & 15, ci = idx & 15, ih = ipx >> 2, iw = ipx & 3;
+        float acc = 0.f;
+        for (int oh = 0; oh < 2; ++oh) {
+            const int kh = ih - 2 * oh;
+            if (kh < 0 || kh > 2) continue;
+            for (int ow = 0; ow < 2; ++ow) {
+                const int kw = iw - 2 * ow;
+                if (kw < 0 || kw > 2) continue;
+                const float* w = Ws + ((kh * 3 + kw) * 16 + ci) * KB_W2S;
+                const float* dz = D2 + (size_t)f * 128 + (oh * 2 + ow) * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
+                    const float4 dd = *reinterpret_cast<const float4*>(dz + q * 4);
+                    acc = fmaf(ww.x, dd.x, acc); acc = fmaf(ww.y, dd.y, acc); acc = fmaf(ww.z, dd.z, acc); acc = fmaf(ww.w, dd.w, acc);
+                }
+            }
+        }
+        D1[idx] = acc;
+    }
+    __syncthreads();
+    // ================= layer 1 =================
+    kb_bn_bwd<16>(a, 0, slice, j, A1, D1, nfr * 16, 16, red, misc, mypart + KB_P_B1);
+    if (a.frames_u8)
+        for (int idx = tid; idx < nfr * 64; idx += KF_THREADS)   // frames as stored: 1 KB each
+            *reinterpret_cast<uint4*>(FR + (size_t)idx * 16) = __ldg(reinterpret_cast<const uint4*>(
+                static_cast<const uint8_t*>(a.frames) + frame_n(idx >> 6) * 1024 + (idx & 63) * 16));
+    __syncthreads();
+    // dW1[tap][ci][co] = sum_{f, opx valid} x0[f][ipx][ci] * dz1[f][opx][co]
+    {
+        const int co = tid & 15, g = tid >> 4;             // 32 groups
+        const float* ff = static_cast<const float*>(a.frames);   // fp32 frames (as the reference feeds): from L2
+        for (int pr = g; pr < 144; pr += 32) {
+            const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
+            float acc = 0.f;
+            for (int oh = 0; oh < 4; ++oh) {
+                const int ih = 2 * oh + kh;
+                if (ih >= 8) continue;
+                for (int ow = 0; ow < 4; ++ow) {
+                    const int iw = 2 * ow + kw;
+                    if (iw >= 8) continue;
+                    const int xo = (ih * 8 + iw) * 16 + ci;
+                    const float* dz = D1 + (oh * 4 + ow) * 16 + co;
+                    if (a.frames_u8) {
+                        for (int f = 0; f < nfr; ++f) {
+                            const uint8_t x = FR[(size_t)f * 1024 + xo];
+                            if (x) acc = fmaf((float)x, dz[(size_t)f * 256], acc);
+                        }
+                    } else {
+                        for (int f = 0; f < nfr; ++f) {
+                            const float x = __ldg(ff + frame_n(f) * 1024 + xo);
+                            if (x != 0.f) acc = fmaf(x, dz[(size_t)f * 256], acc);
+                        }
+                    }
+                }
+            }
+            mypart[KB_P_W1 + pr * 16 + co] = acc;
+        }
+    }
+    // ================= grid-wide fixed-order reduction of the partial gradients =================
+    __syncthreads();
+    unsigned* gctr = a.sync + 61;
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(gctr, 1u);
+        kf_wait(gctr, gridDim.x, a.sync + 63);
+    }
+    __syncthreads();
+    for (int idx = blockIdx.x * KF_THREADS + tid; idx < KB_PART + 96; idx += gridDim.x * KF_THREADS)
+    if (idx < KB_PART) {
+        double s = 0.0;
+        for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(a.part + (size_t)c * KB_PART + idx);
+        const float v = (float)s;
+        if (idx < KB_P_W2) a.L[0].dw[idx] += v;
+        else if (idx < KB_P_W3) a.L[1].dw[idx - KB_P_W2] += v;
+        else if (idx < KB_P_B1) {
+            const int i = idx - KB_P_W3, tap = i / (32 * 48), rem = i % (32 * 48);
+            a.L[2].dw[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem] += v;
+        } else if (idx < KB_P_B2) a.L[0].db[idx - KB_P_B1] += v;
+        else if (idx < KB_P_B3) a.L[1].db[idx - KB_P_B2] += v;
+        else a.L[2].db[idx - KB_P_B3] += v;
+    } else {   // dgamma / dbeta: slice totals in slice order
+        const int c96 = idx - KB_PART;
+        const int l = c96 < 16 ? 0 : (c96 < 48 ? 1 : 2), c = c96 - (l == 0 ? 0 : (l == 1 ? 16 : 48));
+        double tg = 0.0, tb = 0.0;
+        for (int sl = 0; sl < a.k; ++sl) {
+            const float2 t2 = __ldcg(a.totals + (l * a.k + sl) * 48 + c);
+            tb += t2.x; tg += t2.y;
+        }
+        a.L[l].dgamma[c] += (float)tg;
+        a.L[l].dbeta[c] += (float)tb;
+    }
+}
+
 int g_conv_fused = 1;
 
 }  // namespace
@@ -403,6 +707,68 @@ int conv_fused_fwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, 
     cfg.attrs = attr;
     cfg.numAttrs = training ? 1 : 0;   // eval mode has no inter-CTA exchange
     D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, karel_conv_fwd_fused, a));
+    count_launch();
+    return 0;
+}
+
+
+static int kb_gs(const d2p_conv_desc* d) { return d->B < kNumSMs / d->k ? d->B : kNumSMs / d->k; }
+
+size_t conv_fused_bwd_ws_bytes(const d2p_conv_desc* d) {
+    const int gs = kb_gs(d);
+    return 256 + (size_t)3 * d->k * gs * 48 * sizeof(float2) + (size_t)3 * d->k * 48 * sizeof(float2) +
+           (size_t)d->k * gs * KB_PART * sizeof(float) + 512;
+}
+
+bool conv_fused_bwd_supported(const d2p_conv_desc* d, int training, size_t ws_bytes) {
+    if (!g_conv_fused || !training) return false;
+    if (d->n_layers != 3 || d->h != 8 || d->w != 8 || d->d != 16) return false;
+    if (d->layers[0].cout != 16 || d->layers[1].cout != 32 || d->layers[2].cout != 48) return false;
+    if (d->k < 1 || d->k > kNumSMs) return false;
+    const int gs = kb_gs(d);
+    if (((d->B + gs - 1) / gs) * d->T > KB_MAXF) return false;
+    return ws_bytes >= conv_fused_bwd_ws_bytes(d);
+}
+
+int conv_fused_bwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, const float* dfeat,
+                   const float* saved, void* ws) {
+    KbArgs a;
+    a.frames = frames; a.frames_u8 = d->frames_dtype == D2P_U8; a.dfeat = dfeat;
+    a.B = d->B; a.k = d->k; a.T = d->T; a.gs = kb_gs(d);
+    const size_t N = (size_t)d->B * d->k * d->T;
+    const int P[3] = {16, 4, 1}, Cc[3] = {16, 32, 48};
+    const float* sp = saved;
+    for (int l = 0; l < 3; ++l) {
+        const d2p_conv_layer& L = d->layers[l];
+        D2P_REQUIRE(L.w && L.gamma && L.dw && L.db && L.dgamma && L.dbeta, "conv bwd: layer %d params/grads", l);
+        a.L[l].w = L.w; a.L[l].gamma = L.gamma; a.L[l].dw = L.dw; a.L[l].db = L.db;
+        a.L[l].dgamma = L.dgamma; a.L[l].dbeta = L.dbeta;
+        a.L[l].act = sp; sp += N * P[l] * Cc[l];
+        a.L[l].stats = sp; sp += (size_t)4 * d->k * Cc[l];
+    }
+    char* w = (char*)ws;
+    a.sync = (unsigned*)w; w += 256;
+    a.partials = (float2*)w; w += (size_t)3 * d->k * a.gs * 48 * sizeof(float2);
+    a.totals = (float2*)w; w += (size_t)3 * d->k * 48 * sizeof(float2);
+    a.part = (float*)w;
+    D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(karel_conv_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)KB_SMEM));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(d->k * a.gs);
+    cfg.blockDim = dim3(KF_THREADS);
+    cfg.dynamicSmemBytes = KB_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    D2P_CHECK_CUDA(cudaLaunchKernelEx(&cfg, karel_conv_bwd_fused, a));
     count_launch();
     return 0;
 }
