@@ -145,54 +145,64 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(eng, iters=30):
-    """CUDA-event time of the dominant kernel in isolation.
+def time_dominant_kernel(eng, iters=20):
+    """CUDA-event time of the dominant kernels in isolation, on the stream they are launched on.
 
-    By share of the step (profiles/: ncu launch list) the top kernel is
-    `gemm_tc_kernel<64,4>`: the per-time-step recurrent products of the five LSTMs
-    (backward: dh_{t-1} = dZ_t * Wh^T, [R, 4H] x [4H, H], split-K over 6 slabs; 130 launches
-    per step) plus the dW products.  It is timed here exactly as the recurrence launches
-    it: packed (bf16 hi/lo) operands prepared beforehand, split-K partial sums as output.
-    Algorithmic FLOPs = 2*M*N*K (fp32-equivalent; the tensor pipe executes 3x that)."""
+    By share of the step (profiles/r01b_launches_2steps_c2.txt, ncu launch list) the top kernels
+    are the two persistent recurrence kernels, `lstm_persist_bwd_kernel` (19.5 %) and
+    `lstm_persist_fwd_kernel` (19.2 %): ONE cooperative launch per LSTM sequence, recurrent weight
+    resident in shared memory, tcgen05 gate GEMM per step (csrc/lstm_persist.cu).  They are timed
+    here exactly as the step launches them, through d2p_lstm_seq_fwd / d2p_lstm_seq_bwd with
+    phases = "recurrence only", for the k*B-row LSTMs (R = 320 rows, T = 20 steps: four of the
+    five LSTMs of the model).  The hoisted input product is re-run untimed before every timed
+    launch (the recurrence consumes `gates` in place), the L2 is flushed before that.
+    Algorithmic FLOPs per launch = 2*R*H*4H per step x T steps (fp32-equivalent; the bf16x3 split
+    executes 3x that on the tensor pipe; the backward has the same count)."""
     import torch
-    from demo2program_b200._lib import ptr
+    from demo2program_b200._lib import ptr, check
     lib = eng.lib
-    R, H = eng.R, eng.H
-    M, N, K = R, H, 4 * H
-    A = torch.randn(M, K, device=eng.dev)
-    Bm = torch.randn(N, K, device=eng.dev)
-    apk = torch.empty(lib.d2p_packed_bytes(M, K), dtype=torch.uint8, device=eng.dev)
-    bpk = torch.empty(lib.d2p_packed_bytes(N, K), dtype=torch.uint8, device=eng.dev)
-    ks = 6
-    part = torch.empty(ks * M * N, device=eng.dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
-    st = torch.cuda.current_stream(eng.dev)
-    lib.d2p_pack_bf16(ptr(A), M, K, K, 1, ptr(apk), st.cuda_stream)
-    lib.d2p_pack_bf16(ptr(Bm), N, K, K, 1, ptr(bpk), st.cuda_stream)
+    R, H, T = eng.R, eng.H, eng.T
+    dev = eng.dev
+    z = lambda *s: torch.zeros(*s, device=dev)
+    g = torch.Generator(device='cpu').manual_seed(0)
+    X = (torch.randn(T, R, H, generator=g) * 0.5).to(dev)
+    W = (torch.randn(2 * H, 4 * H, generator=g) * 0.05).to(dev)
+    b = z(4 * H)
+    lens = torch.randint(8, T + 1, (R,), generator=g, dtype=torch.int32).to(dev)
+    Y, hT, cT, gates, cells = z(T, R, H), z(R, H), z(R, H), z(T, R, 4 * H), z(T, R, H)
+    dY, dW, db, dh0, dc0 = (torch.randn(T, R, H, generator=g) * 0.1).to(dev), z(2 * H, 4 * H), z(4 * H), z(R, H), z(R, H)
+    wsb = lib.d2p_lstm_seq_bwd_ws_bytes(T, R, H)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev)
+    eng._tc_bind()
 
-    def launch():
-        rc = lib.d2p_gemm_tc_packed(ptr(apk), ptr(bpk), M, N, K, 1.0, 0.0, None, N, None, ks,
-                                    ptr(part), st.cuda_stream)
-        assert rc == 0, lib.d2p_last_error()
+    def fwd(ph):
+        check(lib.d2p_lstm_seq_fwd(ptr(X), T, R, H, H, ptr(lens), None, None, ptr(W), ptr(b), 1.0, ptr(Y),
+                                   ptr(hT), ptr(cT), ptr(gates), ptr(cells), ph, st.cuda_stream), 'lstm fwd')
 
-    for _ in range(3):
-        launch()
-    tot = 0.0
-    for _ in range(iters):
+    def bwd():
+        check(lib.d2p_lstm_seq_bwd(ptr(X), T, R, H, H, ptr(lens), None, None, ptr(W), ptr(Y), ptr(gates),
+                                   ptr(cells), ptr(dY), None, None, None, ptr(dW), ptr(db), ptr(dh0), ptr(dc0),
+                                   ptr(ws), wsb, 1, st.cuda_stream), 'lstm bwd')
+
+    tf = tb = 0.0
+    for i in range(iters + 2):
         flush.zero_()
-        # the step itself finds both operands in L2 (weights packed once per step, dZ_t written
-        # by the preceding kernel): touch them again after the flush
-        apk.add_(0); bpk.add_(0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        launch()
-        e1.record(st)
-        e1.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms = tot / iters
-    flops = 2.0 * M * N * K
-    return {'kernel': 'gemm_tc_kernel<64,4> (tcgen05 bf16x3, split-K 6: recurrent dh = dZ_t * Wh^T)',
-            'shape': [M, N, K], 'ms': ms, 'tflops': flops / (ms * 1e-3) / 1e12}
+        fwd(1)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(st); fwd(2); e[1].record(st)
+        e[2].record(st); bwd(); e[3].record(st)
+        e[3].synchronize()
+        if i >= 2:
+            tf += e[0].elapsed_time(e[1]); tb += e[2].elapsed_time(e[3])
+    tf /= iters; tb /= iters
+    flops = 2.0 * R * H * 4 * H * T
+    return {'kernel': 'lstm_persist_fwd_kernel (persistent weight-stationary LSTM recurrence, tcgen05 bf16x3 '
+                      'gate GEMM per step, R=320 rows x T=20 steps in one cooperative launch)',
+            'shape': [R, 4 * H, H, T], 'ms': tf, 'tflops': flops / (tf * 1e-3) / 1e12,
+            'bwd': {'kernel': 'lstm_persist_bwd_kernel (clusters of 4 split-K CTAs, DSMEM reduction)',
+                    'ms': tb, 'tflops': flops / (tb * 1e-3) / 1e12}}
 
 
 def run_ours(args):
@@ -272,10 +282,13 @@ def run_ours(args):
     roofline = {
         'bound': 'tensor', 'achieved': dom['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
         'frac': dom['tflops'] / pk['bf16_tflops'], 'traffic': None,
-        'kernel': dom['kernel'], 'shape_MNK': dom['shape'], 'kernel_ms': dom['ms'],
+        'kernel': dom['kernel'], 'shape_R_4H_H_T': dom['shape'], 'kernel_ms': dom['ms'],
         'peak_kind': pk_kind + ' bf16 burst (cuBLAS 8192^3); achieved counts ALGORITHMIC flops '
-                     '2*M*N*K - the bf16x3 split executes 3x that on the tensor pipe',
+                     '2*R*H*4H*T - the bf16x3 split executes 3x that on the tensor pipe; the kernel is '
+                     'a chain of T dependent steps on 96 of 148 SMs (latency-bound, see DESIGN.md)',
         'tensor_pipe_tflops_executed': 3 * dom['tflops'],
+        'second_kernel': {'kernel': dom['bwd']['kernel'], 'kernel_ms': dom['bwd']['ms'],
+                          'achieved': dom['bwd']['tflops'], 'frac': dom['bwd']['tflops'] / pk['bf16_tflops']},
     }
     cpu = None
     if not args.no_cpu_baseline:

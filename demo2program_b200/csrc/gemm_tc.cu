@@ -256,7 +256,10 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
     if (ksplit <= 0) ksplit = 1;
     const bool use_part = ksplit > 1 || C == nullptr;
     if (use_part) D2P_REQUIRE(partials != nullptr, "gemm_tc: split-K needs a partials buffer");
-    bool narrow = (long long)cdiv(N, 128) * cdiv(M, BM) < kNumSMs;
+    // few wide tiles with a long K: 128-wide tiles split over K fill the SMs with half the MMA
+    // instructions of 64-wide tiles (an M = 128 MMA costs ~68 cycles for N = 64 and N = 128 alike)
+    const long long tiles128 = (long long)cdiv(N, 128) * cdiv(M, BM);
+    bool narrow = tiles128 < kNumSMs && !(ksplit > 1 && tiles128 * ksplit >= kNumSMs / 2 && N % 128 == 0);
     int zs;
     if (narrow)
         zs = launch_tc<64, 4>(st, A, B, M, N, K, alpha, beta, C, ldc, bias, ksplit,
@@ -356,6 +359,13 @@ size_t tc_scratch_capacity(cudaStream_t st) {
 int gemm_tc_packed_auto(cudaStream_t st, const void* Apk, const void* Bpk, int M, int N, int K, float alpha,
                         float beta, float* C, int ldc, size_t* scratch_off) {
     int ks = auto_ksplit(M, N, K);
+    const long long tiles128 = (long long)cdiv(N, 128) * cdiv(M, BM);
+    const int nk = cdiv(K, BK);
+    if (ks == 1 && N % 128 == 0 && tiles128 <= kNumSMs / 2 && nk >= 32) {   // e.g. dW = X^T dZ: 512 x 2048 x 6400
+        ks = (int)(kNumSMs / tiles128);
+        if (ks > nk / 16) ks = nk / 16;
+        if (ks > 8) ks = 8;
+    }
     float* part = nullptr;
     if (ks > 1) {
         part = (float*)tc_scratch_alloc(st, scratch_off, (size_t)ks * M * N * sizeof(float));
