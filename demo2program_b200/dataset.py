@@ -207,13 +207,74 @@ def collate(dataset, ids):
     return out
 
 
-def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None):
-    """Deterministic replacement of string_input_producer + shuffle_batch."""
+_WORKER_DATASET = None      # inherited by forked loader processes
+_WORKER_SLOTS = None        # anonymous shared mappings the workers write the large arrays into
+_BIG_KEYS = ('s_h', 'test_s_h', 'program', 'a_h', 'test_a_h', 'per', 'test_per')
+
+
+def _collate_job(job):
+    slot, id_list = job
+    b = collate(_WORKER_DATASET, id_list)
+    meta = {}
+    off = 0
+    buf = _WORKER_SLOTS[slot]
+    for key in _BIG_KEYS:          # large arrays travel through shared memory, not the result pipe
+        a = np.ascontiguousarray(b.pop(key))
+        n = a.nbytes
+        buf[off:off + n] = a.reshape(-1).view(np.uint8)
+        meta[key] = (off, a.shape, a.dtype.str)
+        off += (n + 63) // 64 * 64
+    return slot, meta, b
+
+
+def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None, workers=0, lookahead=4):
+    """Deterministic replacement of string_input_producer + shuffle_batch (reference
+    karel_env/input_ops_karel.py:24-125 uses 16 loader threads and an unordered queue).  The
+    per-example work is Python-bound (~0.6 ms), so `workers` > 0 assembles batches in forked
+    loader PROCESSES (the memory-mapped HDF5 file is shared read-only; the large arrays come back
+    through anonymous shared mappings) and still delivers them in the seeded order."""
     r = np.random.RandomState(seed)
     ids = list(dataset.ids)
-    e = 0
-    while epochs is None or e < epochs:
-        order = r.permutation(len(ids)) if shuffle else np.arange(len(ids))
-        for s in range(0, len(ids) - batch_size + 1, batch_size):
-            yield collate(dataset, [ids[i] for i in order[s:s + batch_size]])
-        e += 1
+
+    def id_lists():
+        e = 0
+        while epochs is None or e < epochs:
+            order = r.permutation(len(ids)) if shuffle else np.arange(len(ids))
+            for s in range(0, len(ids) - batch_size + 1, batch_size):
+                yield [ids[i] for i in order[s:s + batch_size]]
+            e += 1
+
+    if workers <= 0:
+        for lst in id_lists():
+            yield collate(dataset, lst)
+        return
+    import collections
+    import mmap
+    import multiprocessing as mp
+    global _WORKER_DATASET, _WORKER_SLOTS
+    probe = collate(dataset, ids[:1])
+    per_example = sum((probe[k].nbytes + 63) // 64 * 64 for k in _BIG_KEYS)
+    nslots = workers + max(lookahead, 2)
+    maps = [mmap.mmap(-1, per_example * batch_size + 4096) for _ in range(nslots)]
+    _WORKER_DATASET = dataset
+    _WORKER_SLOTS = [np.frombuffer(m, np.uint8) for m in maps]
+    free = collections.deque(range(nslots))
+    pending = collections.deque()
+
+    def finish(res):
+        slot, meta, b = res.get()
+        buf = _WORKER_SLOTS[slot]
+        for key, (off, shape, dt) in meta.items():
+            n = int(np.prod(shape)) * np.dtype(dt).itemsize
+            b[key] = buf[off:off + n].view(dt).reshape(shape).copy()
+        free.append(slot)
+        return b
+
+    with mp.get_context('fork').Pool(workers) as pool:
+        for lst in id_lists():
+            if not free:
+                yield finish(pending.popleft())
+            pending.append(pool.apply_async(_collate_job, ((free.popleft(), lst),)))
+        while pending:
+            yield finish(pending.popleft())
+    _WORKER_SLOTS = None

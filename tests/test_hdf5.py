@@ -132,3 +132,17 @@ def test_batches_iterator_over_hdf5_dataset(tmp_path):
         assert b['s_h'].shape == (4, 3, 20, 8, 8, 16) and b['program'].shape == (4, 50, 50)
         seen += [x.decode() for x in b['id']]
     assert sorted(seen) == sorted(tr.ids)
+
+
+def test_loader_processes_deliver_the_same_batches_in_the_same_order(tmp_path):
+    from demo2program_b200 import dataset as ds
+    d = str(tmp_path / 'karel_ds3')
+    ds.write_karel_dataset(d, 12, 2, 2, 3, test_k=2, seed=3)
+    tr, _, _ = ds.create_default_splits(d, num_k=2)
+    a = list(ds.batches(tr, 4, shuffle=True, seed=5, epochs=2))
+    b = list(ds.batches(tr, 4, shuffle=True, seed=5, epochs=2, workers=2))
+    assert len(a) == len(b) == 6
+    for x, y in zip(a, b):
+        assert set(x) == set(y)
+        for key in x:
+            assert x[key].dtype == y[key].dtype and np.array_equal(x[key], y[key]), key

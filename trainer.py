@@ -41,7 +41,8 @@ class Trainer(object):
         log.info("Train Dir: %s", self.train_dir)
         from demo2program_b200.dataset import batches
         self.batch_size = config.batch_size
-        self.batch_train = batches(dataset, self.batch_size, shuffle=True, seed=config.rank)
+        self.batch_train = batches(dataset, self.batch_size, shuffle=True, seed=config.rank,
+                                   workers=getattr(config, 'loader_workers', 0))
         self.batch_test = batches(dataset_test, self.batch_size, shuffle=False)
         Model = self.get_model_class(config.model)
         log.info("Using Model class: %s", Model)
@@ -146,6 +147,9 @@ def main(argv=None):
                         choices=['synthesis_baseline', 'induction_baseline', 'summarizer', 'full'])
     parser.add_argument('--dataset_type', type=str, default='karel', choices=['karel', 'vizdoom'])
     parser.add_argument('--dataset_path', type=str, default='datasets/karel_dataset')
+    # not in the reference (it hard-codes 16 loader threads, input_ops_karel.py:118-123):
+    parser.add_argument('--loader_workers', type=int, default=0,
+                        help='forked loader processes assembling batches ahead of the step (0 = inline)')
     parser.add_argument('--checkpoint', type=str, default=None)
     parser.add_argument('--log_step', type=int, default=10)
     parser.add_argument('--write_summary_step', type=int, default=100)
