@@ -111,6 +111,7 @@ SIGNATURES = {
     'd2p_debug_set_probe': (_i, [_fp]),
     'd2p_lstm_set_persistent': (_i, [_i]),
     'd2p_conv_set_fused': (_i, [_i]),
+    'd2p_device_error': (_i, [_fp]),
     'd2p_debug_stamp': (_i, [_fp, _i, _fp]),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),

@@ -45,6 +45,8 @@ struct KfArgs {
     unsigned* sync;      // [3*k] slice counters, [60] ticket, [63] error word
 };
 
+__device__ unsigned g_conv_sticky_error = 0;   // a slice / grid barrier timed out (see d2p_device_error)
+
 __device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -57,7 +59,7 @@ __device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, un
     while (kf_ld_acquire(ctr) < target) {
         if ((++it & 63) == 0) {
             if (kf_ld_acquire(err) != 0u) return;
-            if (clock64() - t0 > KF_SPIN_CYCLES) { atomicExch(err, 1u); return; }
+            if (clock64() - t0 > KF_SPIN_CYCLES) { atomicExch(err, 1u); atomicExch(&g_conv_sticky_error, 2u); return; }
         }
     }
 }
@@ -774,6 +776,26 @@ int conv_fused_bwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, 
 }
 
 }  // namespace d2p
+
+namespace d2p {
+int lstm_persist_error(unsigned* out, bool clear);
+}
+// Synchronises the device and reports (and clears) whether a step barrier of a persistent /
+// cooperative kernel timed out since the last call: 0 = none, bit 0 = LSTM recurrence, bit 1 =
+// fused conv encoder.  Results produced by such a launch are invalid.
+extern "C" int d2p_device_error(int* flags) {
+    D2P_REQUIRE(flags != nullptr, "device_error: null argument");
+    D2P_CHECK_CUDA(cudaDeviceSynchronize());
+    unsigned a = 0, b = 0;
+    D2P_TRY(d2p::lstm_persist_error(&a, true));
+    D2P_CHECK_CUDA(cudaMemcpyFromSymbol(&b, d2p::g_conv_sticky_error, sizeof(unsigned)));
+    if (b) {
+        const unsigned zero = 0;
+        D2P_CHECK_CUDA(cudaMemcpyToSymbol(d2p::g_conv_sticky_error, &zero, sizeof(unsigned)));
+    }
+    *flags = (int)(a | b);
+    return 0;
+}
 
 // 1 (default): fused single-kernel Karel encoder forward where supported; 0: per-layer kernels.
 extern "C" int d2p_conv_set_fused(int mode) {

@@ -58,6 +58,10 @@ __device__ __forceinline__ void red_relaxed(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// Sticky device-side error word: a step barrier that timed out anywhere since the last query
+// (d2p_device_error); the per-launch word in the arena is recycled by later kernels.
+__device__ unsigned g_persist_sticky_error = 0;
+
 // Wait until *ctr >= target.  err[0] becomes non-zero if any wait in the grid ran out of
 // time; from then on every wait returns immediately so that the kernel still terminates.
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, unsigned* err) {
@@ -67,7 +71,7 @@ __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, 
     while (ld_acquire(ctr) < target) {
         if ((++it & 63) == 0) {
             if (ld_acquire(err) != 0u) return;
-            if (clock64() - t0 > P_SPIN_CYCLES) { atomicExch(err, 1u); return; }
+            if (clock64() - t0 > P_SPIN_CYCLES) { atomicExch(err, 1u); atomicExch(&g_persist_sticky_error, 1u); return; }
         }
     }
 }
@@ -595,6 +599,15 @@ int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t s
 }
 
 }  // namespace
+
+int lstm_persist_error(unsigned* out, bool clear) {
+    D2P_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_persist_sticky_error, sizeof(unsigned)));
+    if (clear && *out) {
+        const unsigned zero = 0;
+        D2P_CHECK_CUDA(cudaMemcpyToSymbol(g_persist_sticky_error, &zero, sizeof(unsigned)));
+    }
+    return 0;
+}
 
 int lstm_persist_set_probe(long long* buf) {
     D2P_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_tc_dbg, &buf, sizeof(buf)));

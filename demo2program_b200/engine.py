@@ -706,12 +706,24 @@ class Engine:
         else:
             self._graph.replay()
 
+    def check_device(self):
+        """Fail loudly if a step barrier of a persistent kernel timed out (d2p_device_error):
+        the step's results would be garbage.  Synchronises the device."""
+        flags = C.c_int(0)
+        check(self.lib.d2p_device_error(C.byref(flags)), 'd2p_device_error')
+        if flags.value:
+            raise _lib.D2PError('a persistent-kernel step barrier timed out (flags=%d: bit 0 LSTM '
+                                'recurrence, bit 1 fused conv encoder); results are invalid - were two '
+                                'persistent launches that cannot be co-resident issued on different '
+                                'streams?' % flags.value)
+
     def train_step(self, batch):
         """Public API: host batch in, loss out (H2D + step + D2H of the loss)."""
         self.stage_batch(batch)
         self.train_step_device(True)
         self.h_loss.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
+        self.check_device()
         return float(self.h_loss[0])
 
     def _input_pairs(self):
@@ -787,6 +799,7 @@ class Engine:
             i += 1
         last = (i - 1) & 1
         pf['done'][last].synchronize()
+        self.check_device()
         yield float(pf['loss'][last][0])
 
     # ------------------------------------------------------------------ outputs

@@ -285,6 +285,11 @@ int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes);
  * shared memory, cell state in registers, steps separated by a release/acquire barrier
  * among the CTAs of a row tile; 0 = one launch per time step. */
 int d2p_lstm_set_persistent(int mode);
+/* Synchronises the device and reports (then clears) whether a step barrier of one of the persistent
+ * cooperative kernels ran into its ~2 s spin limit since the last call (0 = none, bit 0 = LSTM
+ * recurrence, bit 1 = fused conv encoder); the outputs of such a launch are invalid.  The engine
+ * checks it whenever it hands a loss to the caller. */
+int d2p_device_error(int* flags);
 /* developer tool: record SM-clock stamps of CTA (0,0,0) of the tensor-core kernels
  * into buf (>= 128 int64 on the device; the persistent recurrence kernels use
  * slots 64..127); NULL disables. */

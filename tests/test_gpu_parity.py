@@ -350,6 +350,7 @@ def _run_variant(cfg, batch, fused, persistent, frames_dtype=np.uint8, is_train=
         eng.forward()
         eng.backward()
         torch.cuda.synchronize()
+        eng.check_device()
         return {'loss': eng.loss.cpu().numpy().copy(), 'feat': eng.feat.cpu().numpy().copy(),
                 'saved': eng.conv_saved.cpu().numpy().copy(), 'state': eng.state.cpu().numpy().copy(),
                 'grads': eng.grads.cpu().numpy().copy()}
