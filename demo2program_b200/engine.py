@@ -32,6 +32,7 @@ def _al(n, a=64):
 
 class Engine:
     """Preallocated buffers + launch sequence for one model/config."""
+    N_GRAD_STREAMS = 2
 
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
                  frames_dtype=np.uint8, flat_params=None, flat_state=None,
@@ -77,10 +78,11 @@ class Engine:
         # the latency-bound chain runs at high priority; the throughput-bound weight-gradient
         # products (grad_stream, default = lowest priority) fill whatever SMs are left
         self.main_stream = torch.cuda.Stream(self.dev, priority=-1) if self.concurrent else None
-        self.grad_stream = torch.cuda.Stream(self.dev) if self.concurrent else None
-        for s_ in self.side_streams + ([self.grad_stream] if self.concurrent else []):
+        self.grad_streams = [torch.cuda.Stream(self.dev) for _ in range(self.N_GRAD_STREAMS)] if self.concurrent else []
+        self._grad_rr = 0
+        for s_ in self.side_streams + self.grad_streams:
             self._ws_side[s_.cuda_stream] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
-        self._all_side = self.side_streams + ([self.grad_stream] if self.concurrent else [])
+        self._all_side = self.side_streams + self.grad_streams
         self.tc_side = [torch.zeros_like(self.tc_scratch) for _ in self._all_side] if self.use_tc else []
         self._tc_bind()
         self._graph = None
@@ -270,9 +272,17 @@ class Engine:
         self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 1)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        self.grad_stream.wait_event(ev)
-        with torch.cuda.stream(self.grad_stream):
+        gs = self._next_grad_stream()
+        gs.wait_event(ev)
+        with torch.cuda.stream(gs):
             self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, None, 2)
+
+    def _next_grad_stream(self):
+        """Gradient streams are used round-robin: the weight-gradient work of one LSTM (operand
+        packing, two products, a column sum) is a serial chain, several of them overlap."""
+        s_ = self.grad_streams[self._grad_rr % len(self.grad_streams)]
+        self._grad_rr += 1
+        return s_
 
     def _deferred(self, fn):
         """Run parameter-gradient-only work behind the current stream's work, on the
@@ -282,8 +292,9 @@ class Engine:
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        self.grad_stream.wait_event(ev)
-        with torch.cuda.stream(self.grad_stream):
+        gs = self._next_grad_stream()
+        gs.wait_event(ev)
+        with torch.cuda.stream(gs):
             fn()
 
     def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc):
@@ -503,6 +514,7 @@ class Engine:
         call, S = self._call, self._st
         fin = self.fin
         self.grads.zero_()
+        self._grad_rr = 0
         p = self.prog
         self._stamp('bwd start')
 
@@ -618,7 +630,8 @@ class Engine:
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())
         self._stamp('conv bwd done')
         if self.concurrent:   # parameter-gradient products must land before the optimizer
-            torch.cuda.current_stream(self.dev).wait_stream(self.grad_stream)
+            for gs in self.grad_streams:
+                torch.cuda.current_stream(self.dev).wait_stream(gs)
         self._stamp('bwd done (weight-gradient stream joined)')
 
     # ------------------------------------------------------------------ optimizer
