@@ -45,6 +45,11 @@ struct KfArgs {
     unsigned* sync;      // [3*k] slice counters, [60] ticket, [63] error word
 };
 
+// timeline probe (developer tool, tools/probe_conv.py): SM-clock stamps of CTA 0, slots 96..127
+__device__ long long* g_conv_dbg = nullptr;
+__device__ __forceinline__ void cstamp(int slot) {
+    if (g_conv_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_conv_dbg[96 + slot] = clock64();
+}
 __device__ unsigned g_conv_sticky_error = 0;   // a slice / grid barrier timed out (see d2p_device_error)
 
 __device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
@@ -181,8 +186,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
     float* sc = misc + 96; float* sh = misc + 144;
     const int tid = threadIdx.x;
     const int slice = blockIdx.x / a.gs, j = blockIdx.x % a.gs;
-    const int b0 = (int)((long long)j * a.B / a.gs), b1 = (int)((long long)(j + 1) * a.B / a.gs);
-    const int nfr = (b1 - b0) * a.T;
+    // frames of this slice are (b, t) pairs, b*T + t in [0, B*T): an even share per CTA
+    const int g0 = (int)((long long)j * a.B * a.T / a.gs), g1 = (int)((long long)(j + 1) * a.B * a.T / a.gs);
+    const int nfr = g1 - g0;
     const int R = a.B * a.k;
 
     for (int i = tid; i < KF_W1; i += KF_THREADS) W1s[i] = a.L[0].w[i];
@@ -202,8 +208,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
         // ---- conv1 (8x8x16 -> 4x4x16) + bias + lrelu ----
         for (int it = tid; it < fc * 16; it += KF_THREADS) {
             const int f = it >> 4, px = it & 15, oh = px >> 2, ow = px & 3;
-            const int fl = f0 + f;
-            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            const int fl = g0 + f0 + f;
+            const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
             float acc[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = b1s[c];
@@ -230,8 +236,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
         }
         __syncthreads();
         for (int idx = tid; idx < fc * 64; idx += KF_THREADS) {   // saved a1, 1 KB per frame
-            const int f = idx >> 6, fl = f0 + f;
-            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            const int f = idx >> 6, fl = g0 + f0 + f;
+            const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
             *reinterpret_cast<float4*>(a.L[0].act + n * 256 + (idx & 63) * 4) =
                 *reinterpret_cast<const float4*>(A1 + (size_t)idx * 4);
         }
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
         }
         __syncthreads();
         for (int idx = tid; idx < fc * 32; idx += KF_THREADS) {   // saved a2, 512 B per frame
-            const int f = idx >> 5, fl = f0 + f;
-            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            const int f = idx >> 5, fl = g0 + f0 + f;
+            const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
             *reinterpret_cast<float4*>(a.L[1].act + n * 128 + (idx & 31) * 4) =
                 *reinterpret_cast<const float4*>(A2 + (size_t)idx * 4);
         }
@@ -304,16 +310,16 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
         }
         __syncthreads();
         for (int idx = tid; idx < fc * 12; idx += KF_THREADS) {   // saved a3, 192 B per frame
-            const int f = idx / 12, fl = f0 + f;
-            const size_t n = ((size_t)(b0 + fl / a.T) * a.k + slice) * a.T + fl % a.T;
+            const int f = idx / 12, fl = g0 + f0 + f;
+            const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
             *reinterpret_cast<float4*>(a.L[2].act + n * 48 + (idx % 12) * 4) =
                 *reinterpret_cast<const float4*>(A3 + (size_t)idx * 4);
         }
         kf_bn_finalize<48>(a, 2, slice, j, A3, fc, 1, red, sc, sh);
         // ---- feature = BN(a3), time-major [T, R, 48] ----
         for (int idx = tid; idx < fc * 48; idx += KF_THREADS) {
-            const int f = idx / 48, c = idx - f * 48, fl = f0 + f;
-            const int r = (b0 + fl / a.T) * a.k + slice, t = fl % a.T;
+            const int f = idx / 48, c = idx - f * 48, fl = g0 + f0 + f;
+            const int r = (fl / a.T) * a.k + slice, t = fl % a.T;
             a.feat[((size_t)t * R + r) * 48 + c] = fmaf(A3[idx], sc[c], sh[c]);
         }
         __syncthreads();
@@ -462,12 +468,13 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     float* scin = misc + 256; float* shin = misc + 320;
     const int tid = threadIdx.x;
     const int slice = blockIdx.x / a.gs, j = blockIdx.x % a.gs;
-    const int b0 = (int)((long long)j * a.B / a.gs), b1 = (int)((long long)(j + 1) * a.B / a.gs);
-    const int nfr = (b1 - b0) * a.T;
+    const int g0 = (int)((long long)j * a.B * a.T / a.gs), g1 = (int)((long long)(j + 1) * a.B * a.T / a.gs);
+    const int nfr = g1 - g0;
     const int R = a.B * a.k;
     float* mypart = a.part + (size_t)blockIdx.x * KB_PART;
-    auto frame_n = [&](int f) { return ((size_t)(b0 + f / a.T) * a.k + slice) * a.T + f % a.T; };
+    auto frame_n = [&](int f) { return ((size_t)((g0 + f) / a.T) * a.k + slice) * a.T + (g0 + f) % a.T; };
 
+    cstamp(0);
     // ---- load saved activations, dfeat, W3 ----
     for (int idx = tid; idx < nfr * 64; idx += KF_THREADS)
         *reinterpret_cast<float4*>(A1 + (size_t)idx * 4) =
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         const int f = idx / 12, q = idx % 12;
         *reinterpret_cast<float4*>(A3 + (size_t)idx * 4) =
             *reinterpret_cast<const float4*>(a.L[2].act + frame_n(f) * 48 + q * 4);
-        const int r = (b0 + f / a.T) * a.k + slice, t = f % a.T;
+        const int r = ((g0 + f) / a.T) * a.k + slice, t = (g0 + f) % a.T;
         *reinterpret_cast<float4*>(D3 + (size_t)idx * 4) =
             *reinterpret_cast<const float4*>(a.dfeat + ((size_t)t * R + r) * 48 + q * 4);
     }
@@ -493,20 +500,24 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     }
     __syncthreads();
 
+    cstamp(1);
     // ================= layer 3 =================
     kb_bn_bwd<48>(a, 2, slice, j, A3, D3, nfr, 1, red, misc, mypart + KB_P_B3);
-    // dW3[tap][ci][co] = sum_f x2n[f][tap][ci] * dz3[f][co]
-    if (tid < 480) {
-        const int co = tid % 48, g = tid / 48;
-        for (int pr = g; pr < 128; pr += 10) {           // pr = tap*32 + ci
-            const int ci = pr & 31;
-            const float sc = scin[ci], sh = shin[ci];
-            float acc = 0.f;
-            for (int f = 0; f < nfr; ++f)
-                acc = fmaf(fmaf(A2[(size_t)f * 128 + pr], sc, sh), D3[(size_t)f * 48 + co], acc);
-            mypart[KB_P_W3 + pr * 48 + co] = acc;
+    cstamp(2);
+    // dW3[tap][ci][co] = sum_f x2n[f][tap][ci] * dz3[f][co]; item = ((tap, ci), 4 output channels):
+    // one scalar + one 16-byte shared-memory load per 4 FMAs
+    for (int it = tid; it < 128 * 12; it += KF_THREADS) {
+        const int pr = it / 12, c4 = (it - pr * 12) * 4, ci = pr & 31;     // pr = tap*32 + ci
+        const float sc = scin[ci], sh = shin[ci];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = 0; f < nfr; ++f) {
+            const float x = fmaf(A2[(size_t)f * 128 + pr], sc, sh);
+            const float4 d = *reinterpret_cast<const float4*>(D3 + (size_t)f * 48 + c4);
+            acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y); acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
         }
+        *reinterpret_cast<float4*>(mypart + KB_P_W3 + pr * 48 + c4) = acc;
     }
+    cstamp(3);
     // dy2[f][tap][ci] = sum_co dz3[f][co] * W3[tap][ci][co]
     for (int idx = tid; idx < nfr * 128; idx += KF_THREADS) {
         const int f = idx >> 7, pr = idx & 127;
@@ -522,6 +533,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         D2[idx] = acc;
     }
     __syncthreads();
+    cstamp(4);
     // ================= layer 2 =================
     for (int i = tid; i < KF_W2; i += KF_THREADS) Ws[(i >> 5) * KB_W2S + (i & 31)] = a.L[1].w[i];
     if (tid < 16) {
@@ -529,66 +541,87 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         shin[tid] = a.L[0].stats[3 * a.k * 16 + slice * 16 + tid];
     }
     kb_bn_bwd<32>(a, 1, slice, j, A2, D2, nfr * 4, 4, red, misc, mypart + KB_P_B2);
-    // dW2[tap][ci][co] = sum_{f, opx valid} x1n[f][ipx][ci] * dz2[f][opx][co]
-    {
-        const int co = tid & 31, g = tid >> 5;             // 16 groups
-        for (int pr = g; pr < 144; pr += 16) {             // pr = tap*16 + ci
-            const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
-            const float sc = scin[ci], sh = shin[ci];
-            float acc = 0.f;
-            for (int oh = 0; oh < 2; ++oh) {
-                const int ih = 2 * oh + kh;
-                if (ih >= 4) continue;
-                for (int ow = 0; ow < 2; ++ow) {
-                    const int iw = 2 * ow + kw;
-                    if (iw >= 4) continue;
-                    const float* xa = A1 + (ih * 4 + iw) * 16 + ci;
-                    const float* dz = D2 + (oh * 2 + ow) * 32 + co;
-                    for (int f = 0; f < nfr; ++f)
-                        acc = fmaf(fmaf(xa[(size_t)f * 256], sc, sh), dz[(size_t)f * 128], acc);
+    cstamp(5);
+    // dW2[tap][ci][co] = sum_{f, opx valid} x1n[f][ipx][ci] * dz2[f][opx][co]; item = ((tap, ci), 4 co)
+    for (int it = tid; it < 144 * 8; it += KF_THREADS) {
+        const int pr = it >> 3, c4 = (it & 7) * 4;             // pr = tap*16 + ci
+        const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
+        const float sc = scin[ci], sh = shin[ci];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int oh = 0; oh < 2; ++oh) {
+            const int ih = 2 * oh + kh;
+            if (ih >= 4) continue;
+            for (int ow = 0; ow < 2; ++ow) {
+                const int iw = 2 * ow + kw;
+                if (iw >= 4) continue;
+                const float* xa = A1 + (ih * 4 + iw) * 16 + ci;
+                const float* dz = D2 + (oh * 2 + ow) * 32 + c4;
+                for (int f = 0; f < nfr; ++f) {
+                    const float x = fmaf(xa[(size_t)f * 256], sc, sh);
+                    const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)f * 128);
+                    acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y); acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
                 }
             }
-            mypart[KB_P_W2 + pr * 32 + co] = acc;
         }
+        *reinterpret_cast<float4*>(mypart + KB_P_W2 + pr * 32 + c4) = acc;
     }
+    cstamp(6);
     __syncthreads();   // A3 / D3 (aliasing D1) are dead from here
     // dy1[f][ipx][ci] = sum_{(opx, tap): ipx = 2 opx + tap} sum_co dz2[f][opx][co] * W2[tap][ci][co]
-    for (int idx = tid; idx < nfr * 256; idx += KF_THREADS) {
-        const int f = idx >> 8, ipx = (idx >> 4) & 15, ci = idx & 15, ih = ipx >> 2, iw = ipx & 3;
-        float acc = 0.f;
-        for (int oh = 0; oh < 2; ++oh) {
-            const int kh = ih - 2 * oh;
-            if (kh < 0 || kh > 2) continue;
-            for (int ow = 0; ow < 2; ++ow) {
-                const int kw = iw - 2 * ow;
-                if (kw < 0 || kw > 2) continue;
-                const float* w = Ws + ((kh * 3 + kw) * 16 + ci) * KB_W2S;
-                const float* dz = D2 + (size_t)f * 128 + (oh * 2 + ow) * 32;
+    // item = (frame, input channel): the 16 input pixels accumulate in registers; per (output pixel,
+    // tap) pair one broadcast 16-byte load of dz2 and one conflict-free 16-byte load of the weight row
+    for (int it = tid; it < nfr * 16; it += KF_THREADS) {
+        const int f = it >> 4, ci = it & 15;
+        float acc[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
-                    const float4 dd = *reinterpret_cast<const float4*>(dz + q * 4);
-                    acc = fmaf(ww.x, dd.x, acc); acc = fmaf(ww.y, dd.y, acc); acc = fmaf(ww.z, dd.z, acc); acc = fmaf(ww.w, dd.w, acc);
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int opx = 0; opx < 4; ++opx) {
+            const float* dz = D2 + (size_t)f * 128 + opx * 32;
+            float4 dd[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dd[q] = *reinterpret_cast<const float4*>(dz + q * 4);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int ih = 2 * (opx >> 1) + kh;
+                if (ih >= 4) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int iw = 2 * (opx & 1) + kw;
+                    if (iw >= 4) continue;
+                    const float* w = Ws + ((kh * 3 + kw) * 16 + ci) * KB_W2S;
+                    float s4 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
+                        s4 = fmaf(ww.x, dd[q].x, s4); s4 = fmaf(ww.y, dd[q].y, s4);
+                        s4 = fmaf(ww.z, dd[q].z, s4); s4 = fmaf(ww.w, dd[q].w, s4);
+                    }
+                    acc[ih * 4 + iw] += s4;
                 }
             }
         }
-        D1[idx] = acc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D1[(size_t)f * 256 + i * 16 + ci] = acc[i];
     }
     __syncthreads();
+    cstamp(7);
     // ================= layer 1 =================
     kb_bn_bwd<16>(a, 0, slice, j, A1, D1, nfr * 16, 16, red, misc, mypart + KB_P_B1);
+    cstamp(8);
     if (a.frames_u8)
         for (int idx = tid; idx < nfr * 64; idx += KF_THREADS)   // frames as stored: 1 KB each
             *reinterpret_cast<uint4*>(FR + (size_t)idx * 16) = __ldg(reinterpret_cast<const uint4*>(
                 static_cast<const uint8_t*>(a.frames) + frame_n(idx >> 6) * 1024 + (idx & 63) * 16));
     __syncthreads();
-    // dW1[tap][ci][co] = sum_{f, opx valid} x0[f][ipx][ci] * dz1[f][opx][co]
+    // dW1[tap][ci][co] = sum_{f, opx valid} x0[f][ipx][ci] * dz1[f][opx][co]; item = ((tap, ci), 4 co);
+    // Karel frames are one-hot planes: most x are zero and skip the gradient load
     {
-        const int co = tid & 15, g = tid >> 4;             // 32 groups
         const float* ff = static_cast<const float*>(a.frames);   // fp32 frames (as the reference feeds): from L2
-        for (int pr = g; pr < 144; pr += 32) {
+        for (int it = tid; it < 144 * 4; it += KF_THREADS) {
+            const int pr = it >> 2, c4 = (it & 3) * 4;
             const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
-            float acc = 0.f;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int oh = 0; oh < 4; ++oh) {
                 const int ih = 2 * oh + kh;
                 if (ih >= 8) continue;
@@ -596,23 +629,36 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                     const int iw = 2 * ow + kw;
                     if (iw >= 8) continue;
                     const int xo = (ih * 8 + iw) * 16 + ci;
-                    const float* dz = D1 + (oh * 4 + ow) * 16 + co;
+                    const float* dz = D1 + (oh * 4 + ow) * 16 + c4;
+                    int f = 0;
                     if (a.frames_u8) {
-                        for (int f = 0; f < nfr; ++f) {
-                            const uint8_t x = FR[(size_t)f * 1024 + xo];
-                            if (x) acc = fmaf((float)x, dz[(size_t)f * 256], acc);
+                        for (; f + 4 <= nfr; f += 4) {     // four independent loads in flight
+                            float x[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) x[u] = (float)FR[(size_t)(f + u) * 1024 + xo];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (x[u] != 0.f) {
+                                    const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)(f + u) * 256);
+                                    acc.x = fmaf(x[u], d.x, acc.x); acc.y = fmaf(x[u], d.y, acc.y);
+                                    acc.z = fmaf(x[u], d.z, acc.z); acc.w = fmaf(x[u], d.w, acc.w);
+                                }
                         }
-                    } else {
-                        for (int f = 0; f < nfr; ++f) {
-                            const float x = __ldg(ff + frame_n(f) * 1024 + xo);
-                            if (x != 0.f) acc = fmaf(x, dz[(size_t)f * 256], acc);
+                    }
+                    for (; f < nfr; ++f) {
+                        const float x = a.frames_u8 ? (float)FR[(size_t)f * 1024 + xo] : __ldg(ff + frame_n(f) * 1024 + xo);
+                        if (x != 0.f) {
+                            const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)f * 256);
+                            acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y);
+                            acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
                         }
                     }
                 }
             }
-            mypart[KB_P_W1 + pr * 16 + co] = acc;
+            *reinterpret_cast<float4*>(mypart + KB_P_W1 + pr * 16 + c4) = acc;
         }
     }
+    cstamp(9);
     // ================= grid-wide fixed-order reduction of the partial gradients =================
     __syncthreads();
     unsigned* gctr = a.sync + 61;
@@ -622,6 +668,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         kf_wait(gctr, gridDim.x, a.sync + 63);
     }
     __syncthreads();
+    cstamp(10);
     for (int idx = blockIdx.x * KF_THREADS + tid; idx < KB_PART + 96; idx += gridDim.x * KF_THREADS)
     if (idx < KB_PART) {
         double s = 0.0;
@@ -646,6 +693,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         a.L[l].dgamma[c] += (float)tg;
         a.L[l].dbeta[c] += (float)tb;
     }
+    cstamp(11);
 }
 
 int g_conv_fused = 1;
@@ -663,8 +711,7 @@ bool conv_fused_supported(const d2p_conv_desc* d, int training, size_t ws_bytes)
     if (d->layers[0].cout != 16 || d->layers[1].cout != 32 || d->layers[2].cout != 48) return false;
     if (d->k < 1 || d->k > kNumSMs) return false;
     const int gs = d->B < kNumSMs / d->k ? d->B : kNumSMs / d->k;
-    const int max_demos = (d->B + gs - 1) / gs;
-    if (training && max_demos * d->T > KF_MAXF) return false;   // statistics need the CTA's frames resident
+    if (training && (d->B * d->T + gs - 1) / gs > KF_MAXF) return false;   // statistics need the CTA's frames resident
     return ws_bytes >= conv_fused_ws_bytes(d);
 }
 
@@ -728,7 +775,7 @@ bool conv_fused_bwd_supported(const d2p_conv_desc* d, int training, size_t ws_by
     if (d->layers[0].cout != 16 || d->layers[1].cout != 32 || d->layers[2].cout != 48) return false;
     if (d->k < 1 || d->k > kNumSMs) return false;
     const int gs = kb_gs(d);
-    if (((d->B + gs - 1) / gs) * d->T > KB_MAXF) return false;
+    if ((d->B * d->T + gs - 1) / gs > KB_MAXF) return false;
     return ws_bytes >= conv_fused_bwd_ws_bytes(d);
 }
 
@@ -779,6 +826,10 @@ int conv_fused_bwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, 
 
 namespace d2p {
 int lstm_persist_error(unsigned* out, bool clear);
+int conv_fused_set_probe(long long* buf) {
+    D2P_CHECK_CUDA(cudaMemcpyToSymbol(g_conv_dbg, &buf, sizeof(buf)));
+    return 0;
+}
 }
 // Synchronises the device and reports (and clears) whether a step barrier of a persistent /
 // cooperative kernel timed out since the last call: 0 = none, bit 0 = LSTM recurrence, bit 1 =

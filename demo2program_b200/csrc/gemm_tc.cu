@@ -25,6 +25,7 @@ namespace d2p {
 
 int lstm_tc_set_probe(long long* buf);
 int lstm_persist_set_probe(long long* buf);
+int conv_fused_set_probe(long long* buf);
 using namespace tc;
 
 namespace {
@@ -454,5 +455,6 @@ extern "C" int d2p_tc_new_step(void) {
 extern "C" int d2p_debug_set_probe(long long* buf) {
     D2P_CHECK_CUDA(cudaMemcpyToSymbol(d2p::tc::g_tc_dbg, &buf, sizeof(buf)));
     D2P_TRY(d2p::lstm_persist_set_probe(buf));
+    D2P_TRY(d2p::conv_fused_set_probe(buf));
     return d2p::lstm_tc_set_probe(buf);
 }
