@@ -383,6 +383,7 @@ struct BwdArgs {
     const float* cells; const float* c0; const float* dY;
     const float* dhT; const float* dcT; float* dh0; float* dc0;
     const int* len; int R, T, has_h0;
+    float* dbpart;                      // [row tiles][4H] column sums of dZ over this tile's rows and all steps
     unsigned* sync;                     // [row tiles] dZ_t published counters, [63] error word
 };
 
@@ -446,6 +447,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     // my 16 B of each partial tile: row `row`, tile columns 16 ks + up .. + 4
     const uint32_t my_part = stage_u32 + (uint32_t)((row * PGROW + ks * PUPT + up) * sizeof(float));
     float dhc[4] = {0.f, 0.f, 0.f, 0.f}, dcc[4] = {0.f, 0.f, 0.f, 0.f};
+    float sdb[16];           // bias gradient: this thread's dZ summed over the steps (i | j | f | o)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sdb[e] = 0.f;
     int mylen = 0;
     if (valid) {
         mylen = a.len[r];
@@ -494,6 +498,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
                 df[e] = dct * cp[e] * gf[e] * (1.f - gf[e]);
                 dcc[e] = dct * gf[e];
                 dhc[e] = 0.f;   // consumed: the recurrent product carries the new dh
+                sdb[e] += di[e]; sdb[4 + e] += dj[e]; sdb[8 + e] += df[e]; sdb[12 + e] += dq[e];
             }
         } else {
 #pragma unroll
@@ -564,7 +569,22 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         st4r(a.dc0 + su, dcc);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();      // no CTA leaves while a peer may still read its shared memory
+    cluster_sync_all();      // no CTA leaves (or recycles its ring) while a peer may still read its shared memory
+    // bias gradient: column sums of dZ over this tile's rows, fixed order (rows 0..127)
+    {
+        float* srow = stage + (size_t)row * PGROW + up;
+#pragma unroll
+        for (int gte = 0; gte < 4; ++gte)
+            *reinterpret_cast<float4*>(srow + gte * PUPT) =
+                valid ? make_float4(sdb[gte * 4], sdb[gte * 4 + 1], sdb[gte * 4 + 2], sdb[gte * 4 + 3])
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        if (tid < PBN) {
+            float s = 0.f;
+            for (int rr = 0; rr < BM; ++rr) s += stage[(size_t)rr * PGROW + tid];
+            a.dbpart[(size_t)mt * G4 + (tid >> 4) * H + q * PUPT + (tid & 15)] = s;
+        }
+    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
 }
@@ -651,9 +671,20 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
 }
 
 // Recurrence phase of lstm_seq_bwd (without dX): gates -> dZ, dh0, dc0.
+namespace {
+__global__ void add_db_partials(const float* __restrict__ part, int nt, int n, float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int t = 0; t < nt; ++t) s += part[(size_t)t * n + i];
+    db[i] += s;
+}
+}  // namespace
+
+// The kernel also accumulates the bias gradient (column sums of dZ): db += sum over row tiles.
 int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
                      const float* Wh, float* gates, const float* cells, const float* dY, const float* dhT,
-                     const float* dcT, float* dh0, float* dc0) {
+                     const float* dcT, float* dh0, float* dc0, float* db) {
     const int G4 = 4 * H;
     size_t off = 0;
     const int mgp_z = R <= 32 ? cdiv(R, 8) : mgp_of(R);
@@ -661,7 +692,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     BwdArgs a;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
     a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
-    D2P_REQUIRE(a.dzpk && a.sync, "lstm persist bwd: tensor-core scratch arena too small");
+    a.dbpart = (float*)tc_scratch_alloc(st, &off, (size_t)cdiv(R, BM) * G4 * sizeof(float));
+    D2P_REQUIRE(a.dzpk && a.sync && a.dbpart, "lstm persist bwd: tensor-core scratch arena too small");
     const void* wtpk;
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
@@ -675,7 +707,10 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
                                             (int)P_SMEM));
         attr_set = true;
     }
-    return launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a, 4);
+    D2P_TRY(launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a, 4));
+    add_db_partials<<<cdiv(G4, 256), 256, 0, st>>>(a.dbpart, cdiv(R, BM), G4, db);
+    D2P_CHECK_LAUNCH();
+    return 0;
 }
 
 }  // namespace d2p

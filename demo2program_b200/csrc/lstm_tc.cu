@@ -36,7 +36,7 @@ bool lstm_persist_supported(int R, int H);
 int lstm_persist_fwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float,
                      float*, float*, float*, float*, float*);
 int lstm_persist_bwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float*,
-                     const float*, const float*, const float*, const float*, float*, float*);
+                     const float*, const float*, const float*, const float*, float*, float*, float*);
 
 namespace {
 
@@ -343,7 +343,7 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
                          aligned16(dc0) && (!dhT || aligned16(dhT)) && (!dcT || aligned16(dcT)) &&
                          (!dY || aligned16(dY)) && (!c0 || aligned16(c0));
     if ((phases & D2P_LSTM_BWD_RECUR) && persist) {
-        D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0));
+        D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0, db));
         if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
     } else if (phases & D2P_LSTM_BWD_RECUR) {
     // split-K factor of the per-step dh GEMM [R, H] = dZ_t [R, 4H] * Wh^T
@@ -418,7 +418,8 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
             D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
     }
     if (h0) D2P_TRY(gemm(st, true, false, H, G4, R, 1.f, h0, H, gates, G4, 1.f, dWh, G4));
-    D2P_TRY(colsum(st, gates, (long long)T * R, G4, db, 1.f, ws, ws_bytes));
+    // (the persistent recurrence kernel has already accumulated db while it produced dZ)
+    if (!persist) D2P_TRY(colsum(st, gates, (long long)T * R, G4, db, 1.f, ws, ws_bytes));
     return 0;
 }
 
