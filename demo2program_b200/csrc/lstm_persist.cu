@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
 
 struct BwdArgs {
     const uint8_t* wtpk; int mgp_w;     // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
-    uint8_t* dzpk; int mgp_z;           // packed dZ_t [R, 4H]
+    uint8_t* dzpk; int mgp_z;           // packed dZ: one step [R, 4H], or (full != 0) all steps [T*R, 4H]
+    int full;                           // dZ_t lives at rows t*R.. of the full operand (reused by the dX product)
     float* gates;                       // [T,R,4H] in: activated gates, out: dZ
     const float* cells; const float* c0; const float* dY;
     const float* dhT; const float* dcT; float* dh0; float* dc0;
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     bool have_partials = false;
     for (int t = a.T - 1; t >= 0; --t) {
         const int step = a.T - 1 - t;
+        const int zrow0 = a.full ? t * R : 0;      // first packed row of this step's dZ
         if (tid == 0) pstamp(step, 16);
         // ---- phase P: dZ_t for this CTA's 16 hidden units ----
         float* g = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u;
@@ -505,15 +507,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             for (int e = 0; e < 4; ++e) di[e] = dj[e] = df[e] = dq[e] = 0.f;   // state copied through
         }
         const bool do_gemm = t > 0 || a.has_h0;
+        if (valid && (do_gemm || a.full)) {
+            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, u, di);
+            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, H + u, dj);
+            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 2 * H + u, df);
+            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 3 * H + u, dq);
+        }
         if (do_gemm) {
-            // packed operand first, then publish; the fp32 dZ (for the dW / dX products after the
+            // packed operand first, then publish; the fp32 dZ (for the dW products after the
             // kernel) is stored behind the arrive
-            if (valid) {
-                store_packed4(a.dzpk, a.mgp_z, r, u, di);
-                store_packed4(a.dzpk, a.mgp_z, r, H + u, dj);
-                store_packed4(a.dzpk, a.mgp_z, r, 2 * H + u, df);
-                store_packed4(a.dzpk, a.mgp_z, r, 3 * H + u, dq);
-            }
             if (tid == 64) pstamp(step, 19);
             __syncthreads();
             if (tid == 0) { __threadfence(); proxy_fence(); red_relaxed(ctrP, 1u); pstamp(step, 20); }
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             grid_wait(ctrP, (unsigned)(PCOLS * (ground + 1)), err);
             pstamp(step, 21);
             proxy_fence();
-            persist_produce(pb, rp, sbase, a.dzpk + ((size_t)kb0 * a.mgp_z + m0 / 8) * 2048, a_kb_stride, rot);
+            persist_produce(pb, rp, sbase, a.dzpk + ((size_t)kb0 * a.mgp_z + (zrow0 + m0) / 8) * 2048, a_kb_stride, rot);
         } else if (warp == 1 && lane == 0) {
             persist_mma(pb, rp, sbase, tmem_d, rot, ground == 0);
             mbar_wait(pb.accum, ground & 1);
@@ -684,19 +686,24 @@ __global__ void add_db_partials(const float* __restrict__ part, int nt, int n, f
 // The kernel also accumulates the bias gradient (column sums of dZ): db += sum over row tiles.
 int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
                      const float* Wh, float* gates, const float* cells, const float* dY, const float* dhT,
-                     const float* dcT, float* dh0, float* dc0, float* db) {
+                     const float* dcT, float* dh0, float* dc0, float* db, const void** dz_full, size_t* off_out) {
     const int G4 = 4 * H;
     size_t off = 0;
-    const int mgp_z = R <= 32 ? cdiv(R, 8) : mgp_of(R);
+    // R > 32 and whole 8-row groups per step: the kernel writes dZ_t straight into the packed
+    // [T*R, 4H] operand the dX product consumes (no pack pass over dZ afterwards)
+    const bool full = dz_full != nullptr && R > 32 && R % 8 == 0 &&
+                      al256((size_t)kgp_of(G4) * mgp_of(T * R) * 256) + (16u << 20) <= tc_scratch_capacity(st);
+    const int mgp_z = full ? mgp_of(T * R) : (R <= 32 ? cdiv(R, 8) : mgp_of(R));
     const size_t zbytes = (size_t)kgp_of(G4) * mgp_z * 256;
     BwdArgs a;
+    a.full = full ? 1 : 0;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
     a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
     a.dbpart = (float*)tc_scratch_alloc(st, &off, (size_t)cdiv(R, BM) * G4 * sizeof(float));
     D2P_REQUIRE(a.dzpk && a.sync && a.dbpart, "lstm persist bwd: tensor-core scratch arena too small");
     const void* wtpk;
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
-    D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
+    if (!full || mgp_of(T * R) * 8 != T * R) D2P_CHECK_CUDA(cudaMemsetAsync(a.dzpk, 0, zbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
     a.wtpk = (const uint8_t*)wtpk; a.mgp_w = mgp_of(H); a.mgp_z = mgp_z;
     a.gates = gates; a.cells = cells; a.c0 = c0; a.dY = dY; a.dhT = dhT; a.dcT = dcT;
@@ -710,6 +717,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     D2P_TRY(launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a, 4));
     add_db_partials<<<cdiv(G4, 256), 256, 0, st>>>(a.dbpart, cdiv(R, BM), G4, db);
     D2P_CHECK_LAUNCH();
+    if (dz_full) *dz_full = full ? a.dzpk : nullptr;
+    if (off_out) *off_out = off;
     return 0;
 }
 

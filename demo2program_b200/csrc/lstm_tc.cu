@@ -36,7 +36,8 @@ bool lstm_persist_supported(int R, int H);
 int lstm_persist_fwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float,
                      float*, float*, float*, float*, float*);
 int lstm_persist_bwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float*,
-                     const float*, const float*, const float*, const float*, float*, float*, float*);
+                     const float*, const float*, const float*, const float*, float*, float*, float*, const void**,
+                     size_t*);
 
 namespace {
 
@@ -343,8 +344,17 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
                          aligned16(dc0) && (!dhT || aligned16(dhT)) && (!dcT || aligned16(dcT)) &&
                          (!dY || aligned16(dY)) && (!c0 || aligned16(c0));
     if ((phases & D2P_LSTM_BWD_RECUR) && persist) {
-        D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0, db));
-        if (dX) D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+        const void* dzfull = nullptr;
+        size_t off = 0;
+        D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0, db,
+                                 dX ? &dzfull : nullptr, &off));
+        if (dX && dzfull && tc_eligible(T * R, In, G4)) {   // dX = dZ * Wx^T from the operand the kernel packed
+            const void* wxpk;
+            D2P_TRY(get_packed(st, Wx, In, G4, G4, true, true, &off, &wxpk));
+            D2P_TRY(gemm_tc_packed_auto(st, dzfull, wxpk, T * R, In, G4, 1.f, 0.f, dX, In, &off));
+        } else if (dX) {
+            D2P_TRY(gemm(st, false, true, T * R, In, G4, 1.f, gates, G4, Wx, G4, 0.f, dX, In, nullptr, GEMM_CONST_B));
+        }
     } else if (phases & D2P_LSTM_BWD_RECUR) {
     // split-K factor of the per-step dh GEMM [R, H] = dZ_t [R, 4H] * Wh^T
         long long tiles64 = (long long)cdiv(H, 64) * cdiv(R, BM);
