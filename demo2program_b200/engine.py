@@ -330,7 +330,7 @@ class Engine:
         return n
 
     # ------------------------------------------------------------------ branches
-    def _parallel(self, fns, streams=None):
+    def _parallel(self, fns, streams=None, join=True):
         """Run independent branches of the step concurrently: fns[0] on the current
         stream, the others on side streams that fork from / rejoin it (also valid
         inside CUDA-graph capture).  Every branch has its own scratch buffers."""
@@ -348,11 +348,16 @@ class Engine:
                 fn()
             used.append(s)
         fns[0]()
+        if not join:          # the caller joins later (forward tail overlapping the backward head)
+            return used
         for s in used:
             main.wait_stream(s)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, train_stats=None):
+    def forward(self, train_stats=None, open_tail=False):
+        """open_tail (train step only): do not wait for the action / per decoders at the end - the
+        backward pass starts with the program decoder and the summary pools, which do not depend on
+        them, and joins their stream itself."""
         cfg = self.cfg
         B, k, T, H, R, F = self.B, self.k, self.T, self.H, self.R, self.F
         L, V = cfg.max_program_len, cfg.dim_program_token
@@ -498,9 +503,15 @@ class Engine:
             if self.concurrent:   # the per decoder's hoisted input product ran on side stream 2
                 torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[1])
             per_fwd()
-        self._parallel([prog_fwd, act_then_per])
+        self._fwd_open = bool(open_tail and self.concurrent)
+        self._parallel([prog_fwd, act_then_per], join=not self._fwd_open)
         self._stamp('fwd done')
-        # total = program + action + per
+        if not self._fwd_open:
+            self._total_loss()
+
+    def _total_loss(self):
+        """total = program + action + per"""
+        call, S = self._call, self._st
         call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
         call('d2p_axpby', ptr(self.loss[2:]), 1.0, ptr(self.loss), 1.0, 1, S())
         call('d2p_axpby', ptr(self.loss[3:]), 1.0, ptr(self.loss), 1.0, 1, S())
@@ -593,6 +604,9 @@ class Engine:
                 act_bwd()
                 per_bwd()
             self._parallel([prog_then_pools, act_then_per_bwd])
+            if getattr(self, '_fwd_open', False):   # the forward's action / per decoders are joined now
+                self._total_loss()
+                self._fwd_open = False
             self._stamp('decoders + pools bwd joined')
             # dh2 = d(action init) + d(per init) + d(pools)
             call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, S())
@@ -658,7 +672,7 @@ class Engine:
         cur = torch.cuda.current_stream(self.dev)
         self.main_stream.wait_stream(cur)
         with torch.cuda.stream(self.main_stream):
-            self.forward()
+            self.forward(open_tail=self.model == 'full')
             self.backward()
             if with_opt:
                 self.optimizer_step()
@@ -697,10 +711,7 @@ class Engine:
             snap = [t.clone() for t in (self.params, self.state, self.adam_m, self.adam_v,
                                         self.adam_state)]
             if self.world > 1:
-                def fb():
-                    self.forward()
-                    self.backward()
-                g1, n1 = self._capture(fb)
+                g1, n1 = self._capture(lambda: self._step_body(False))
                 g2, n2 = self._capture(lambda: self._adam_only(1.0 / self.world))
                 self._graph, self.launches_per_step = (g1, g2), n1 + n2
             else:
