@@ -143,14 +143,24 @@ extern "C" int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc
     return 0;
 }
 
+extern "C" size_t d2p_rn_pool_bwd_hold_floats(int B, int k, int H) {
+    return 2 * (size_t)B * k * k * H + 2 * (size_t)B * k * H;
+}
+
 // dF += d(pooled)/dF.  Parameter grads accumulate into fc1/fc2 grad pointers.
+// phases / hold: with a caller-owned `hold` buffer (d2p_rn_pool_bwd_hold_floats) the call can be
+// split: phases & 1 = the data path (dF, plus the BatchNorm scale/shift gradients that fall out of
+// it) leaving both dZ and the pair sums in `hold`; phases & 2 = the weight / bias gradients from
+// `hold` - they may run later, on another stream.  hold == NULL: one call does everything.
 extern "C" int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc_bn* fc1,
                                const d2p_fc_bn* fc2, const float* dpooled, const float* saved,
-                               float* dF, int training, void* ws, size_t ws_bytes, void* stream) {
+                               float* dF, int training, void* ws, size_t ws_bytes, int phases,
+                               float* hold, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     D2P_REQUIRE(F && fc1 && fc2 && dpooled && saved && dF && ws, "rn_pool bwd: null buffer");
     D2P_REQUIRE(fc1->dw && fc1->db && fc1->dgamma && fc1->dbeta && fc2->dw && fc2->db &&
                 fc2->dgamma && fc2->dbeta, "rn_pool bwd: null grad buffer");
+    D2P_REQUIRE(hold != nullptr || phases == 3, "rn_pool bwd: a split call needs a hold buffer");
     Plan p = plan(B, k, H);
     D2P_REQUIRE(ws_bytes >= p.total, "rn_pool bwd: workspace too small");
     char* w = (char*)ws;
@@ -162,6 +172,32 @@ extern "C" int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc
     float* dP = (float*)(w + p.d); float* dQ = (float*)(w + p.e);
     float* coef = (float*)(w + p.coef);
     void* part = w + p.part;
+    if (hold != nullptr) {
+        float* dZ2 = hold; float* dZ1 = hold + rows * H;
+        float* hP = dZ1 + rows * H; float* hQ = hP + (size_t)Bk * H;
+        if (phases & 1) {
+            bcast_pairs<<<ewb(rows * H), 256, 0, st>>>(dpooled, B, kk, H, dY);
+            D2P_CHECK_LAUNCH();
+            D2P_TRY(bn_backward(st, A2, dY, dZ2, rows, H, 1, 1, fc2->gamma, st2, fc2->dgamma, fc2->dbeta,
+                                training, 1, coef, part, p.part_bytes, 0, 0, nullptr));
+            D2P_TRY(gemm(st, false, true, (int)rows, H, H, 1.f, dZ2, H, fc2->w, H, 0.f, dY, H, nullptr, GEMM_CONST_B));
+            D2P_TRY(bn_backward(st, A1, dY, dZ1, rows, H, 1, 1, fc1->gamma, st1, fc1->dgamma, fc1->dbeta,
+                                training, 1, coef, part, p.part_bytes, 0, 0, nullptr));
+            pair_reduce<<<ewb((size_t)Bk * H), 256, 0, st>>>(dZ1, B, k, H, hP, hQ);
+            D2P_CHECK_LAUNCH();
+            D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, hP, H, fc1->w, H, 1.f, dF, H, nullptr, GEMM_CONST_B));
+            D2P_TRY(gemm(st, false, true, Bk, H, H, 1.f, hQ, H, fc1->w + (size_t)H * H, H, 1.f, dF, H, nullptr, GEMM_CONST_B));
+        }
+        if (phases & 2) {
+            D2P_TRY(colsum(st, dZ2, rows, H, fc2->db, 1.f, part, p.part_bytes));
+            D2P_TRY(bn_apply(st, A1, X2, rows, H, 1, 1, st1, 0, 0));
+            D2P_TRY(gemm(st, true, false, H, H, (int)rows, 1.f, X2, H, dZ2, H, 1.f, fc2->dw, H));
+            D2P_TRY(colsum(st, dZ1, rows, H, fc1->db, 1.f, part, p.part_bytes));
+            D2P_TRY(gemm(st, true, false, H, H, Bk, 1.f, F, H, hP, H, 1.f, fc1->dw, H));
+            D2P_TRY(gemm(st, true, false, H, H, Bk, 1.f, F, H, hQ, H, 1.f, fc1->dw + (size_t)H * H, H));
+        }
+        return 0;
+    }
     // second block
     bcast_pairs<<<ewb(rows * H), 256, 0, st>>>(dpooled, B, kk, H, dY);
     D2P_CHECK_LAUNCH();

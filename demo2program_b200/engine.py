@@ -199,6 +199,7 @@ class Engine:
             self.dy1 = z(T, R, H)
             self.rn_saved_h = z(lib.d2p_rn_pool_saved_floats(B, k, H))
             self.rn_saved_c = z(lib.d2p_rn_pool_saved_floats(B, k, H))
+            self.rn_hold = {s_: z(lib.d2p_rn_pool_bwd_hold_floats(B, k, H)) for s_ in 'hc'}
             ws = max(ws, lib.d2p_rn_pool_ws_bytes(B, k, H))
             self.fc = {(s, f): self._fcbn('demo_%s_summary/rn_pool/%s' % (s, f))
                        for s in 'hc' for f in ('fc1', 'fc2')}
@@ -551,9 +552,13 @@ class Engine:
                     call('d2p_group_bcast', ptr(dsum), B, k, H, 1.0 / k, ptr(dF), 0, S())
                 else:
                     dF.zero_()
-                call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
-                     C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
-                     self.ws_bytes, S())
+                # data path now; the fc weight / bias gradients only read `hold`: gradient stream
+                def part(ph):
+                    call('d2p_rn_pool_bwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
+                         C.byref(self.fc[(s, 'fc2')]), ptr(dsum), ptr(saved), ptr(dF), tr, ptr(self.ws),
+                         self.ws_bytes, ph, ptr(self.rn_hold[s]), S())
+                part(1)
+                self._deferred(lambda: part(2))
             return run
 
         if self.model == 'full':

@@ -221,9 +221,14 @@ size_t d2p_rn_pool_ws_bytes(int B, int k, int H);
 int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc_bn* fc1,
                     const d2p_fc_bn* fc2, float* pooled, float* saved, int training, void* ws,
                     size_t ws_bytes, void* stream);
+/* phases / hold: hold == NULL and phases == 3: everything in one call.  With a caller-owned hold
+ * buffer (d2p_rn_pool_bwd_hold_floats floats) the call may be split: phases & 1 = data path (dF and
+ * the BatchNorm scale/shift gradients), phases & 2 = the fc weight / bias gradients, which only read
+ * `hold` and may run later on another stream (with that stream's own workspace). */
+size_t d2p_rn_pool_bwd_hold_floats(int B, int k, int H);
 int d2p_rn_pool_bwd(const float* F, int B, int k, int H, const d2p_fc_bn* fc1,
                     const d2p_fc_bn* fc2, const float* dpooled, const float* saved, float* dF,
-                    int training, void* ws, size_t ws_bytes, void* stream);
+                    int training, void* ws, size_t ws_bytes, int phases, float* hold, void* stream);
 
 /* ---- small [B,k,H] reductions (SummarizeFeature avgpool, model_full.py:351-362) */
 int d2p_group_sum(const float* F, int B, int k, int H, float alpha, float* out, int accumulate,
