@@ -125,20 +125,92 @@ class H5Dataset(object):
                 per[:k], tper)
 
 
-def create_default_splits(dataset_path, num_k=10, is_train=True):
-    """reference karel_env/dataset_karel.py:131-160."""
+class H5DatasetVizdoom(object):
+    """reference vizdoom_env/dataset_vizdoom.py:14-140 over h5py or hdf5_lite: the Karel tuple plus
+    (init_pos, init_pos_len, test_init_pos, test_init_pos_len); `--num_k` slices the stored seen
+    demos BEFORE padding (:61, :74, :105-106, :120-125)."""
+
+    def __init__(self, ids, dataset_path, name='default', num_k=10, is_train=True):
+        self._ids, self.name, self.num_k = list(ids), name, num_k
+        self.data = open_hdf5(osp.join(dataset_path, 'data.hdf5'))
+        info = self.data['data_info']
+        g = lambda k: info[k][()]
+        self.num_demo = int(g('num_demo_per_program'))
+        self.max_demo_len = int(g('max_demo_length'))
+        self.max_program_len = int(g('max_program_length'))
+        self.num_program_tokens = int(g('num_program_tokens'))
+        self.num_action_tokens = int(g('num_action_tokens'))
+        self.vizdoom_pos_keys = [_text(v) for v in np.asarray(g('vizdoom_pos_keys')).reshape(-1)]
+        self.vizdoom_max_init_pos_len = int(g('vizdoom_max_init_pos_len'))
+        self.perception_type = _text(g('perception_type'))
+        self.level = _text(g('level')) if 'level' in info else 'not_simple'
+        self.k = int(g('num_demo_per_program'))
+        self.test_k = int(g('num_test_demo_per_program'))
+        self.s_h_h, self.s_h_w, self.s_h_c = int(g('s_h_h')), int(g('s_h_w')), int(g('s_h_c'))
+        self.dsl_type, self.env_type = 'vizdoom', None
+
+    @property
+    def ids(self):
+        return self._ids
+
+    def __len__(self):
+        return len(self._ids)
+
+    def get_data(self, id):
+        d, k = self.data[id], self.num_k
+        T, A, L = self.max_demo_len, self.num_action_tokens, self.max_program_len
+        toks = d['program'][()]
+        program = np.zeros([self.num_program_tokens, L], dtype=bool)
+        program[toks, np.arange(len(toks))] = 1
+        ptoks = np.zeros([L], dtype=toks.dtype)
+        ptoks[:len(toks)] = toks
+
+        def pad_time(x):
+            out = np.zeros((x.shape[0], T) + x.shape[2:], dtype=x.dtype)
+            out[:, :x.shape[1]] = x
+            return out
+
+        def actions(a):
+            hist = []
+            for t in a:
+                h = np.zeros([T, A + 1], dtype=bool)
+                h[np.arange(len(t)), t] = 1
+                h[len(t), A] = 1
+                hist.append(h)
+            hist = np.stack(hist, 0)
+            return hist, np.argmax(hist, axis=2)
+
+        def pad_pos(x):
+            out = np.zeros([x.shape[0], x.shape[1], self.vizdoom_max_init_pos_len, 2], dtype=x.dtype)
+            out[:, :, :x.shape[2], :] = x
+            return out
+
+        demo, tdemo = pad_time(d['s_h'][()][:k]), pad_time(d['test_s_h'][()])
+        ah, aht = actions(d['a_h'][()][:k])
+        tah, taht = actions(d['test_a_h'][()])
+        per, tper = pad_time(d['p_v_h'][()][:k]), pad_time(d['test_p_v_h'][()])
+        return (program, ptoks, demo, tdemo, ah, aht, tah, taht,
+                np.array([len(toks)], dtype=np.float32), d['s_h_len'][()][:k], d['test_s_h_len'][()],
+                per, tper, pad_pos(d['vizdoom_init_pos'][()][:k]), d['vizdoom_init_pos_len'][()][:k],
+                pad_pos(d['test_vizdoom_init_pos'][()]), d['test_vizdoom_init_pos_len'][()])
+
+
+def create_default_splits(dataset_path, num_k=10, is_train=True, dataset_type='karel'):
+    """reference karel_env/dataset_karel.py:131-160 / vizdoom_env/dataset_vizdoom.py:157-185."""
     if str(dataset_path).startswith('synthetic'):
         n = int(dataset_path.split(':')[1]) if ':' in dataset_path else 512
         return (SyntheticDataset('train', n, num_k, 1000), SyntheticDataset('test', max(n // 8, 32), num_k, 500000),
                 SyntheticDataset('val', max(n // 8, 32), num_k, 900000))
     f = open_hdf5(osp.join(dataset_path, 'data.hdf5'))
     nt, nte, nv = (int(f['data_info'][k][()]) for k in ('num_train', 'num_test', 'num_val'))
+    vizdoom = dataset_type == 'vizdoom' or 'vizdoom_pos_keys' in f['data_info']
     f.close()
     with open(osp.join(dataset_path, 'id.txt')) as fp:
         ids = [s.strip() for s in fp.readlines() if s]
     tr, te, va = ids[:nt], ids[nt:nt + nte], ids[nt + nte:nt + nte + nv]
     rs.shuffle(tr); rs.shuffle(te); rs.shuffle(va)
-    mk = lambda i, n: H5Dataset(i, dataset_path, name=n, num_k=num_k, is_train=is_train)
+    cls = H5DatasetVizdoom if vizdoom else H5Dataset
+    mk = lambda i, n: cls(i, dataset_path, name=n, num_k=num_k, is_train=is_train)
     return mk(tr, 'train'), mk(te, 'test'), mk(va, 'val')
 
 
@@ -190,12 +262,16 @@ KEYS = ('program', 'program_tokens', 's_h', 'test_s_h', 'a_h', 'a_h_tokens', 'te
         'test_a_h_tokens', 'program_len', 'demo_len', 'test_demo_len', 'per', 'test_per')
 
 
+VIZDOOM_EXTRA_KEYS = ('init_pos', 'init_pos_len', 'test_init_pos', 'test_init_pos_len')
+
+
 def collate(dataset, ids):
     """load_fn + batch stacking (reference karel_env/input_ops_karel.py:52-116).  Frames stay
     uint8 (the on-disk bool); everything else uses the reference's dtypes."""
     cols = [dataset.get_data(i) for i in ids]
     out = {'id': np.array([str(i).encode() for i in ids])}
-    for j, key in enumerate(KEYS):
+    keys = KEYS + (VIZDOOM_EXTRA_KEYS if cols and len(cols[0]) == len(KEYS) + 4 else ())
+    for j, key in enumerate(keys):
         arr = np.stack([c[j] for c in cols])
         if key in ('s_h', 'test_s_h'):
             arr = arr.astype(np.uint8)

@@ -140,7 +140,8 @@ def main(argv=None):
     config.write_summary = not config.no_write_summary
     from demo2program_b200 import dataset
     dataset_train, dataset_test, dataset_val = dataset.create_default_splits(
-        config.dataset_path, num_k=config.num_k, is_train=False)
+        config.dataset_path, num_k=config.num_k, is_train=False,
+        dataset_type=getattr(config, "dataset_type", "karel"))
     ds = {'train': dataset_train, 'test': dataset_test, 'val': dataset_val}[config.dataset_split]
     if config.max_steps == 0:
         config.max_steps = int(len(ds) / config.batch_size)   # reference evaler.py:448-449

@@ -146,3 +146,61 @@ def test_loader_processes_deliver_the_same_batches_in_the_same_order(tmp_path):
         assert set(x) == set(y)
         for key in x:
             assert x[key].dtype == y[key].dtype and np.array_equal(x[key], y[key]), key
+
+
+def test_vizdoom_dataset_directory(tmp_path):
+    """vizdoom_env/dataset_vizdoom.py:14-140: --num_k slices the stored seen demos before padding,
+    actions carry quirk F10, init positions are padded to vizdoom_max_init_pos_len."""
+    from demo2program_b200 import dataset as ds
+    rs = np.random.RandomState(4)
+    K, TK, T, L, V, A, P, PL = 5, 3, 7, 12, 20, 11, 6, 4
+    tree, ids, src = {}, [], {}
+    for i in range(6):
+        n = rs.randint(4, L + 1)
+        lens, tlens = rs.randint(2, T + 1, K), rs.randint(2, T + 1, TK)
+        m, tm = int(lens.max()), int(tlens.max())
+        ex = {'program': rs.randint(0, V, n).astype(np.int8),
+              's_h': rs.randint(0, 256, (K, m, 6, 5, 3)).astype(np.int16),
+              'test_s_h': rs.randint(0, 256, (TK, tm, 6, 5, 3)).astype(np.int16),
+              'a_h': rs.randint(0, A, (K, m - 1)).astype(np.int8), 'test_a_h': rs.randint(0, A, (TK, tm - 1)).astype(np.int8),
+              's_h_len': lens.astype(np.int16), 'test_s_h_len': tlens.astype(np.int16),
+              'p_v_h': rs.rand(K, m, P) > 0.5, 'test_p_v_h': rs.rand(TK, tm, P) > 0.5,
+              'vizdoom_init_pos': rs.randn(K, 2, 3, 2), 'vizdoom_init_pos_len': rs.randint(0, 4, (K, 2)).astype(np.int16),
+              'test_vizdoom_init_pos': rs.randn(TK, 2, 2, 2), 'test_vizdoom_init_pos_len': rs.randint(0, 3, (TK, 2)).astype(np.int16)}
+        name = 'viz_%d' % i
+        tree[name], src[name] = ex, ex
+        ids.append(name)
+    tree['data_info'] = {'num_demo_per_program': np.int64(K), 'num_test_demo_per_program': np.int64(TK),
+                         'max_demo_length': np.int64(T), 'max_program_length': np.int64(L),
+                         'num_program_tokens': np.int64(V), 'num_action_tokens': np.int64(A),
+                         'vizdoom_pos_keys': np.array([b'player_pos', b'demon_pos']), 'vizdoom_max_init_pos_len': np.int64(PL),
+                         'perception_type': 'simple', 'level': 'simple', 's_h_h': np.int64(6), 's_h_w': np.int64(5),
+                         's_h_c': np.int64(3), 'num_train': np.int64(4), 'num_test': np.int64(1), 'num_val': np.int64(1)}
+    d = tmp_path / 'viz'
+    d.mkdir()
+    hdf5_lite.write_hdf5(str(d / 'data.hdf5'), tree)
+    (d / 'id.txt').write_text('\n'.join(ids) + '\n')
+    num_k = 3
+    tr, te, va = ds.create_default_splits(str(d), num_k=num_k, dataset_type='vizdoom')
+    assert isinstance(tr, ds.H5DatasetVizdoom) and (len(tr), len(te), len(va)) == (4, 1, 1)
+    assert tr.vizdoom_pos_keys == ['player_pos', 'demon_pos'] and tr.level == 'simple' and tr.test_k == TK
+    for ex_id in tr.ids:
+        e = src[ex_id]
+        t = tr.get_data(ex_id)
+        assert len(t) == 17
+        program, ptok, s_h, ts_h, a_h, a_tok, ta_h, ta_tok, plen, dlen, tdlen, per, tper, ip, ipl, tip, tipl = t
+        n = len(e['program'])
+        assert program.shape == (V, L) and program.sum() == n and ptok[:n].tolist() == e['program'].tolist()
+        assert s_h.shape == (num_k, T, 6, 5, 3) and ts_h.shape == (TK, T, 6, 5, 3)
+        m = e['s_h'].shape[1]
+        assert np.array_equal(s_h[:, :m], e['s_h'][:num_k]) and not s_h[:, m:].any()
+        assert a_h.shape == (num_k, T, A + 1) and a_h[:, m - 1, A].all()        # <e> at the program-max position (F10)
+        assert np.array_equal(a_tok[:, :m - 1], e['a_h'][:num_k])
+        assert dlen.tolist() == e['s_h_len'][:num_k].tolist() and tdlen.tolist() == e['test_s_h_len'].tolist()
+        assert per.shape == (num_k, T, P) and np.array_equal(per[:, :m], e['p_v_h'][:num_k])
+        assert ip.shape == (num_k, 2, PL, 2) and np.array_equal(ip[:, :, :3], e['vizdoom_init_pos'][:num_k])
+        assert not ip[:, :, 3:].any() and tip.shape == (TK, 2, PL, 2)
+        assert ipl.tolist() == e['vizdoom_init_pos_len'][:num_k].tolist()
+    b = ds.collate(tr, tr.ids[:2])
+    assert b['s_h'].dtype == np.uint8 and b['init_pos'].shape == (2, num_k, 2, PL, 2)
+    assert set(ds.VIZDOOM_EXTRA_KEYS) <= set(b)

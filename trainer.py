@@ -180,7 +180,7 @@ def main(argv=None):
     if config.dataset_type not in ('karel', 'vizdoom'):
         raise ValueError(config.dataset_type)
     dataset_train, dataset_test, dataset_val = dataset.create_default_splits(
-        config.dataset_path, num_k=config.num_k)
+        config.dataset_path, num_k=config.num_k, dataset_type=config.dataset_type)
     set_data_dims(config, dataset_train)
     trainer = Trainer(config, dataset_train, dataset_test)
     log.warning("dataset: %s, learning_rate: %f", config.dataset_path, config.learning_rate)
