@@ -71,7 +71,7 @@ SIGNATURES = {
     'd2p_luong_pool_attention_ws_bytes': (_sz, [_i, _i, _i, _i]),
     'd2p_luong_pool_attention': (_i, [_fp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _i, _fp, _sz, _fp]),
     'd2p_induction_decode_ws_bytes': (_sz, [_i, _i, _i, _i]),
-    'd2p_induction_decode': (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp,
+    'd2p_induction_decode': (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp,
                                   _fp, _fp, _i, _fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_concat_cols': (_i, [_fp, _i, _fp, _i, _ll, _fp, _fp]),
     'd2p_karel_check_syntax': (_i, [_fp, _i]),

@@ -349,7 +349,8 @@ extern "C" int d2p_luong_pool_attention(const float* q, int ldq, const float* ke
 extern "C" size_t d2p_induction_decode_ws_bytes(int B, int k, int tk, int H) {
     size_t R2 = (size_t)B * tk;
     // [x|att|h|ctx] [R2,4H] | c [R2,H] | gates [R2,4H] | per-demo contexts | ids, finished [R2] | all_done[64]
-    return (R2 * 9 * H) * sizeof(float) + d2p_luong_pool_attention_ws_bytes(B, k, tk, H) +
+    // (+ [R2,H] for the folded memory-layer query h * W_mem^T)
+    return (R2 * 10 * H) * sizeof(float) + d2p_luong_pool_attention_ws_bytes(B, k, tk, H) +
            (2 * R2 + 64) * sizeof(int) + 256;
 }
 
@@ -361,15 +362,21 @@ extern "C" size_t d2p_induction_decode_ws_bytes(int B, int k, int tk, int H) {
 // The step state lives in one [R2, 4H] buffer  x | attention | h | context  so that the
 // cell's input contraction [x; attention_{t-1}; h_{t-1}] * W (K = 3H) and the attention
 // layer [h; context] * W_a (K = 2H) are each ONE product over adjacent columns.
-extern "C" int d2p_induction_decode(const float* keys, const float* values, const int* mem_len, int B,
+// keys == NULL with memory_layer [H,H] given: the LuongAttention memory layer is folded into the
+// query - score_t = h . (values_t W_mem) = (W_mem h) . values_t - so the keys tensor is never
+// materialised (identical up to fp32 summation order).  Measured at C5: the encoder saves the
+// 54 GFLOP key product (-0.3 ms) but every decode step pays a [B*test_k, H, H] product and the
+// attention kernel is latency-, not byte-bound (+0.4 ms over 20 steps): off by default.
+extern "C" int d2p_induction_decode(const float* keys, const float* memory_layer, const float* values,
+                                    const int* mem_len, int B,
                                     int k, int tk, int T, int H, const float* h_sum,
                                     const float* c_sum, const float* table, int A, const float* Wcell,
                                     const float* bcell, const float* Wa, const float* proj,
                                     const int* tokens, int Tdec, float* logits, int* out_tokens,
                                     int* lengths, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    D2P_REQUIRE(keys && values && mem_len && h_sum && c_sum && table && Wcell && bcell && Wa && proj &&
-                logits && ws, "induction decode: null buffer");
+    D2P_REQUIRE((keys || memory_layer) && values && mem_len && h_sum && c_sum && table && Wcell && bcell && Wa &&
+                proj && logits && ws, "induction decode: null buffer");
     D2P_REQUIRE(ws_bytes >= d2p_induction_decode_ws_bytes(B, k, tk, H), "induction decode: workspace too small");
     D2P_REQUIRE(H % 4 == 0, "induction decode: H must be a multiple of 4");
     const bool greedy = tokens == nullptr;
@@ -382,7 +389,8 @@ extern "C" int d2p_induction_decode(const float* keys, const float* values, cons
     float* gates = c + RH;
     float* part = gates + (size_t)R2 * G4;
     const size_t part_bytes = d2p_luong_pool_attention_ws_bytes(B, k, tk, H);
-    int* ids = (int*)((char*)part + part_bytes);
+    float* qp = (float*)((char*)part + part_bytes);      // [R2, H] folded query
+    int* ids = (int*)(qp + RH);
     int* finished = ids + R2; int* all_done = finished + R2;
     const int eb = cdiv((long long)RH, 256);
     bcast_rows_kernel<<<eb, 256, 0, st>>>(h_sum, B, tk, H, c, H);   // swapped on purpose (F8)
@@ -403,8 +411,14 @@ extern "C" int d2p_induction_decode(const float* keys, const float* values, cons
         D2P_TRY(gemm(st, false, false, R2, G4, 3 * H, 1.f, xs, LD, Wcell, G4, 0.f, gates, G4, bcell, GEMM_CONST_B));
         lstm_cell_infer_kernel<<<eb, 256, 0, st>>>(gates, c, h, LD, R2, H, 1.0f);
         D2P_CHECK_LAUNCH();
-        D2P_TRY(d2p_luong_pool_attention(h, LD, keys, values, mem_len, B, k, tk, T, H, ctx, LD, part, part_bytes,
-                                         stream));
+        if (keys) {
+            D2P_TRY(d2p_luong_pool_attention(h, LD, keys, values, mem_len, B, k, tk, T, H, ctx, LD, part,
+                                             part_bytes, stream));
+        } else {   // q' = W_mem h, scored against the values themselves
+            D2P_TRY(gemm(st, false, true, R2, H, H, 1.f, h, LD, memory_layer, H, 0.f, qp, H, nullptr, GEMM_CONST_B));
+            D2P_TRY(d2p_luong_pool_attention(qp, H, values, values, mem_len, B, k, tk, T, H, ctx, LD, part,
+                                             part_bytes, stream));
+        }
         // attention_t = [h_t; mean context] * W_a  (reads columns [2H,4H), writes [H,2H))
         D2P_TRY(gemm(st, false, false, R2, H, 2 * H, 1.f, h, LD, Wa, H, 0.f, att, LD, nullptr, GEMM_CONST_B));
         float* lt = logits + (size_t)t * R2 * A;

@@ -18,8 +18,12 @@ from .manifest import build_manifests
 
 class InductionEngine:
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=False, frames_dtype=np.uint8,
-                 flat_params=None, flat_state=None, use_tc=True, **_):
+                 flat_params=None, flat_state=None, use_tc=True, fold_memory_layer=False, **_):
         self.lib = _lib.load()
+        # score = h . (values W_mem) = (W_mem h) . values: with the memory layer folded into the
+        # query the keys tensor is never built (encode -0.3 ms at C5) but every decode step pays a
+        # small product and the attention kernel is latency-bound (+0.4 ms): off by default
+        self.fold_memory_layer = bool(fold_memory_layer)
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU fallback)')
         if cfg.model != 'induction_baseline':
@@ -140,15 +144,19 @@ class InductionEngine:
              ptr(self.cT), ptr(self.gates), ptr(self.cells), 3, st)
         call('d2p_group_sum', ptr(self.hT), B, k, H, 1.0 / k, ptr(self.h_sum), 0, st)
         call('d2p_group_sum', ptr(self.cT), B, k, H, 1.0 / k, ptr(self.c_sum), 0, st)
-        # keys = values * W_mem (LuongAttention memory_layer); values = Y (zero past len)
-        call('d2p_gemm', 0, 0, T * R, H, H, 1.0, ptr(self.Y), H,
-             ptr(self.P('AttnMechanism/memory_layer/kernel')), H, 0.0, ptr(self.keys), H, None, st)
+        # values = Y (zero past len).  keys = values * W_mem (LuongAttention memory_layer) are only
+        # materialised when the memory layer is NOT folded into the decoder's query
+        if not self.fold_memory_layer:
+            call('d2p_gemm', 0, 0, T * R, H, H, 1.0, ptr(self.Y), H,
+                 ptr(self.P('AttnMechanism/memory_layer/kernel')), H, 0.0, ptr(self.keys), H, None, st)
 
     def _decode(self, tokens, out_tokens, lengths, exact):
         cfg, st = self.cfg, self._st()
         w = 'Manipulation/dynamic_decoder/pooling_attention_wrapper/'
         self._tc_bind(not exact)
-        self._call('d2p_induction_decode', ptr(self.keys), ptr(self.Y), ptr(self.d_demo_len), self.B,
+        fold = self.fold_memory_layer
+        self._call('d2p_induction_decode', None if fold else ptr(self.keys),
+                   ptr(self.P('AttnMechanism/memory_layer/kernel')), ptr(self.Y), ptr(self.d_demo_len), self.B,
                    self.k, self.tk, self.T, self.H, ptr(self.h_sum), ptr(self.c_sum),
                    ptr(self.P('Manipulation/Token_Embedding/embedding_map')), cfg.action_space,
                    ptr(self.P(w + 'basic_lstm_cell/kernel')), ptr(self.P(w + 'basic_lstm_cell/bias')),

@@ -155,8 +155,12 @@ int d2p_luong_pool_attention(const float* q, int ldq, const float* keys, const f
                              int ldc, void* ws, size_t ws_bytes, void* stream);
 size_t d2p_induction_decode_ws_bytes(int B, int k, int tk, int H);
 /* tokens [B*test_k, Tdec] int32 = teacher forcing, NULL = greedy (start A, end A-1).
- * logits [Tdec, B*test_k, A]; greedy also fills out_tokens [Tdec, B*test_k], lengths. */
-int d2p_induction_decode(const float* keys, const float* values, const int* mem_len, int B, int k,
+ * logits [Tdec, B*test_k, A]; greedy also fills out_tokens [Tdec, B*test_k], lengths.
+ * keys = values * memory_layer precomputed by the caller, or keys == NULL and memory_layer [H,H]
+ * (LuongAttention's Dense(num_units, no bias), model_induction.py:647-649) given: the layer is
+ * folded into the query, each step then reads `values` only. */
+int d2p_induction_decode(const float* keys, const float* memory_layer, const float* values,
+                         const int* mem_len, int B, int k,
                          int tk, int T, int H, const float* h_sum, const float* c_sum,
                          const float* table, int A, const float* Wcell, const float* bcell,
                          const float* Wa, const float* proj, const int* tokens, int Tdec,

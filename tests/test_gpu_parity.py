@@ -267,8 +267,10 @@ def test_induction_forward_and_greedy_match_oracle(is_train):
     batch = make_batch(cfg, seed=11)
     om = OracleModel(cfg, p0, s0, is_train=is_train)
     out = om.forward_induction(batch, greedy=True)
-    for use_tc, tol in ((False, 1e-4), (True, 1e-3)):
-        eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=is_train, use_tc=use_tc)
+    # fold = LuongAttention's memory layer applied to the query instead of the memory (optional)
+    for use_tc, tol, fold in ((False, 1e-4, False), (False, 1e-4, True), (True, 1e-3, False)):
+        eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=is_train, use_tc=use_tc,
+                              fold_memory_layer=fold)
         eng.stage_batch(batch)
         eng.encode(exact=not use_tc)
         pred = eng.forward_teacher(exact=not use_tc)
