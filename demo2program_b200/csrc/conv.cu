@@ -152,8 +152,13 @@ static int launch_conv_dx(cudaStream_t st, const Geo& g, const float* dZ, const 
 template <typename IN_T>
 static int launch_conv_dw(cudaStream_t st, const Geo& g, const IN_T* in, const float* sc, const float* sh,
                           const float* dZ, int ppb, int nblk, float* partial) {
+    if (g.CIN == 3 && sc == nullptr && g.COUT == 16) {   // RGB input layer: register-resident accumulators
+        conv_bwd_dw_cin3<IN_T, 4><<<nblk, CV_THREADS, 0, st>>>(g, in, dZ, ppb, partial);
+        D2P_CHECK_LAUNCH();
+        return 0;
+    }
     const int K3 = 3 * g.CIN;
-    const size_t smem = ((size_t)CV_TP * (K3 + 1) + (size_t)CV_TP * g.COUT) * sizeof(float);
+    const size_t smem = ((size_t)K3 * (CV_TP + 4) + CV_TP + (size_t)CV_TP * g.COUT) * sizeof(float);
 #define D2P_CV_DW(C)                                                                          \
     do {                                                                                      \
         D2P_TRY(cv_set_smem(conv_bwd_dw_v2<C, IN_T>, smem));                                  \

@@ -208,8 +208,9 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
     constexpr int RL = CV_THREADS / C4;          // row lanes
     constexpr int MAXROWS = (3 * MAXC + RL - 1) / RL;
     const int K3 = 3 * g.CIN, AST = K3 + 1;
+    constexpr int APT = CV_TP + 4;               // pitch of the transposed slab [row][pixel]
     float* As = cv_smem;
-    float* Zs = cv_smem + (size_t)CV_TP * AST;
+    float* Zs = cv_smem + (size_t)K3 * APT + CV_TP;
     const int tid = threadIdx.x, ky = blockIdx.y;
     const int c4 = (tid % C4) * 4, rl = tid / C4;
     // few slab rows (3*CIN < RL, e.g. the RGB input layer): the spare row lanes split the
@@ -249,7 +250,10 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
                     for (int c = 0; c < g.CIN; ++c)
                         v[c] = v[c] * in_scale[sl * g.CIN + c] + in_shift[sl * g.CIN + c];
             }
-            for (int c = 0; c < g.CIN; ++c) As[(size_t)tid * AST + kx * g.CIN + c] = ok ? v[c] : 0.f;
+            if (PG == 1)   // transposed slab: a 16-byte load covers 4 pixels of one row
+                for (int c = 0; c < g.CIN; ++c) As[(size_t)(kx * g.CIN + c) * APT + tid] = ok ? v[c] : 0.f;
+            else
+                for (int c = 0; c < g.CIN; ++c) As[(size_t)tid * AST + kx * g.CIN + c] = ok ? v[c] : 0.f;
         }
         {
             float z[MAXC];
@@ -257,7 +261,29 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
             for (int c = 0; c < COUT; ++c) Zs[tid * COUT + c] = pv ? z[c] : 0.f;
         }
         __syncthreads();
-        if (active) {
+        if (PG == 1) {
+            // 4 pixels per step: 4 dZ quads + one slab vector per row feed 16 FMAs per row
+            for (int pp = 0; pp < CV_TP; pp += 4) {
+                float4 z[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) z[e] = *reinterpret_cast<const float4*>(Zs + (pp + e) * COUT + c4);
+#pragma unroll
+                for (int r = 0; r < MAXROWS; ++r) {
+                    const int row = row0 + r * RL;
+                    if (row < K3) {
+                        const float4 a = *reinterpret_cast<const float4*>(As + (size_t)row * APT + pp);
+                        acc[r][0] = fmaf(a.x, z[0].x, acc[r][0]); acc[r][1] = fmaf(a.x, z[0].y, acc[r][1]);
+                        acc[r][2] = fmaf(a.x, z[0].z, acc[r][2]); acc[r][3] = fmaf(a.x, z[0].w, acc[r][3]);
+                        acc[r][0] = fmaf(a.y, z[1].x, acc[r][0]); acc[r][1] = fmaf(a.y, z[1].y, acc[r][1]);
+                        acc[r][2] = fmaf(a.y, z[1].z, acc[r][2]); acc[r][3] = fmaf(a.y, z[1].w, acc[r][3]);
+                        acc[r][0] = fmaf(a.z, z[2].x, acc[r][0]); acc[r][1] = fmaf(a.z, z[2].y, acc[r][1]);
+                        acc[r][2] = fmaf(a.z, z[2].z, acc[r][2]); acc[r][3] = fmaf(a.z, z[2].w, acc[r][3]);
+                        acc[r][0] = fmaf(a.w, z[3].x, acc[r][0]); acc[r][1] = fmaf(a.w, z[3].y, acc[r][1]);
+                        acc[r][2] = fmaf(a.w, z[3].z, acc[r][2]); acc[r][3] = fmaf(a.w, z[3].w, acc[r][3]);
+                    }
+                }
+            }
+        } else if (active) {
             for (int pp = pgp; pp < CV_TP; pp += PG) {
                 const float4 z4 = *reinterpret_cast<const float4*>(Zs + pp * COUT + c4);
 #pragma unroll
@@ -294,5 +320,78 @@ conv_bwd_dw_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_
                 *reinterpret_cast<float4*>(dst + (size_t)row * COUT + c4) =
                     make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
+    }
+}
+
+
+// ---- backward, weight gradient of a 3-channel input layer (ViZDoom RGB frames) ---------------------
+// 9*3 = 27 slab rows: far too few for the row-lane scheme above (one FMA per two shared-memory
+// loads).  Here a thread keeps ALL 27 x 4 accumulators of one output-channel quad in registers and
+// streams its own pixels: 27 input bytes (all loads of a pixel issued before the first FMA; the 3x3
+// windows overlap, so they are L1 hits) + one 16-byte dZ load feed 108 FMAs.  The COUT/4 quads of a
+// pixel sit in adjacent lanes: they share the input loads (one transaction) and read one contiguous
+// dZ row.  grid = nblk; the block's threads are combined with a fixed shuffle / shared-memory tree
+// (deterministic) into the same partial layout as conv_bwd_dw_v2.
+template <typename IN_T, int NQ /* COUT / 4 */>
+__global__ void __launch_bounds__(CV_THREADS)
+conv_bwd_dw_cin3(Geo g, const IN_T* __restrict__ in, const float* __restrict__ dZ, int pix_per_block,
+                 float* __restrict__ partial) {
+    constexpr int PPI = CV_THREADS / NQ;        // pixels per block iteration
+    __shared__ float red[CV_THREADS / 32][NQ][108];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = tid % NQ, c4 = quad * 4;
+    const long long npix = (long long)g.N * g.OH * g.OW;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > npix) p1 = npix;
+    float acc[27][4];
+#pragma unroll
+    for (int r = 0; r < 27; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+    for (long long p = p0 + tid / NQ; p < p1; p += PPI) {
+        const int ox = (int)(p % g.OW), oy = (int)((p / g.OW) % g.OH);
+        const long long n = p / ((long long)g.OW * g.OH);
+        const float4 z = *reinterpret_cast<const float4*>(dZ + (size_t)p * g.COUT + c4);
+        const IN_T* base = in + (size_t)n * g.IH * g.IW * 3;
+        float x[27];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy + ky - g.PT;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox + kx - g.PL;
+                const bool ok = iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+                const IN_T* px = base + ((size_t)(ok ? iy : 0) * g.IW + (ok ? ix : 0)) * 3;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = (float)__ldg(px + ci);
+                    x[(ky * 3 + kx) * 3 + ci] = ok ? v : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 27; ++r) {
+            acc[r][0] = fmaf(x[r], z.x, acc[r][0]); acc[r][1] = fmaf(x[r], z.y, acc[r][1]);
+            acc[r][2] = fmaf(x[r], z.z, acc[r][2]); acc[r][3] = fmaf(x[r], z.w, acc[r][3]);
+        }
+    }
+    // lanes with the same quad: strides NQ, 2 NQ, ... within the warp
+#pragma unroll
+    for (int r = 0; r < 27; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = acc[r][j];
+#pragma unroll
+            for (int o = 16; o >= NQ; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < NQ) red[warp][lane][r * 4 + j] = v;
+        }
+    __syncthreads();
+    for (int idx = tid; idx < NQ * 108; idx += CV_THREADS) {
+        const int qd = idx / 108, e = idx - qd * 108;
+        float s_ = 0.f;
+#pragma unroll
+        for (int w = 0; w < CV_THREADS / 32; ++w) s_ += red[w][qd][e];
+        // partial[blk][ky][kx*CIN+ci][co]: 27 rows of COUT
+        partial[((size_t)blockIdx.x * 27 + e / 4) * g.COUT + qd * 4 + (e & 3)] = s_;
     }
 }

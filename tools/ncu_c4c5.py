@@ -8,6 +8,10 @@ from demo2program_b200.engine import Engine
 from demo2program_b200.synthetic import make_batch, make_vizdoom_batch
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'c4'
+import os
+from demo2program_b200 import _lib
+# ncu cannot launch cooperative + clustered kernels: plain launch for the persistent recurrences
+_lib.load().d2p_lstm_set_persistent(int(os.environ.get('D2P_PERSIST', '2')))
 if which == 'c4':
     cfg = vizdoom_config('full', batch_size=32, k=10)
     eng = Engine(cfg, use_graph=False, concurrent=False)
