@@ -42,6 +42,45 @@ def test_loss_and_gradients_match_oracle(model, B, k):
     assert rel_err(eng.dsum_h.cpu().numpy(), out['demo_h_summary'].detach().numpy()) < 1e-4
 
 
+def test_engine_matches_committed_golden():
+    """The CUDA path against tests/golden/oracle_golden.json (committed oracle outputs on seeded
+    inputs; generator: tests/golden/make_oracle_golden.py) - no oracle code runs here."""
+    import json
+    import os
+    from demo2program_b200.engine import Engine
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                                         'oracle_golden.json')))
+    for g in golden:
+        cfg = karel_config(g['model'], batch_size=g['B'], k=g['k'])
+        pm, sm = build_manifests(cfg)
+        p0, s0 = pm.init_flat(0), sm.init_flat(0)
+        rs = np.random.RandomState(17)
+        for e in pm:
+            if e.name.endswith('/beta') or e.name.endswith('biases') or e.name.endswith('/bias'):
+                p0[e.offset:e.offset + e.size] = rs.uniform(-0.1, 0.1, e.size)
+            if e.name.endswith('/gamma'):
+                p0[e.offset:e.offset + e.size] = rs.uniform(0.8, 1.2, e.size)
+        eng = Engine(cfg, flat_params=p0, flat_state=s0, use_graph=False)
+        eng.stage_batch(make_batch(cfg, seed=1))
+        eng.forward()
+        eng.backward()
+        torch.cuda.synchronize()
+        assert abs(float(eng.loss[0]) - g['loss']) < LOSS_TOL, g['model']
+        gr = eng.grads.cpu().numpy().astype(np.float64)
+        assert abs(np.sqrt((gr ** 2).sum()) - g['grad_norm']) < 2e-4 * g['grad_norm']
+        w = np.cos(np.arange(gr.size) * 0.37)
+        assert abs((gr * w).sum() - g['grad_projection']) < 2e-4 * g['grad_norm']
+        for e_name, v in g['grad_group_sqnorm'].items():
+            mine = sum(float((gr[e.offset:e.offset + e.size] ** 2).sum()) for e in pm
+                       if e.name.split('/')[0] == e_name)
+            assert abs(np.sqrt(mine) - np.sqrt(v)) < 3e-4 * max(np.sqrt(v), 1e-3 * g['grad_norm']), e_name
+        pp = eng.pred_program().cpu().numpy()[0, :6, :4]
+        assert np.abs(pp - np.asarray(g['pred_program_slice'])).max() < 1e-4
+        assert np.abs(eng.dsum_h.cpu().numpy()[0, :6] - np.asarray(g['demo_h_summary_slice'])).max() < 1e-4
+
+
 def test_training_trajectory_matches_oracle():
     """5 optimizer steps (clip + TF-Adam + BN moving stats) stay within 1e-4 in loss."""
     cfg = karel_config('full', batch_size=4, k=3)

@@ -209,3 +209,26 @@ def test_full_model_gradient_finite_difference():
             ln = float(OracleModel(cfg, pn, sm.init_flat(3)).forward(batch)['loss'])
             fd = (lp - ln) / (2 * d)
             assert abs(fd - float(grad[i])) < 1e-6 + 1e-4 * abs(fd), (name, fd, float(grad[i]))
+
+
+def test_oracle_reproduces_golden():
+    """tests/golden/oracle_golden.json (generated by tests/golden/make_oracle_golden.py) pins the
+    oracle's arithmetic: loss, gradient norms per variable group, a projection of the flat gradient,
+    logits / summary slices for the three teacher-forced model families."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    import make_oracle_golden as G
+    golden = json.load(open(os.path.join(here, 'golden', 'oracle_golden.json')))
+    assert [(g['model'], g['B'], g['k']) for g in golden] == G.CASES
+    for g in golden[:2]:          # the two small families keep the CPU suite short
+        r = G.oracle_case(g['model'], g['B'], g['k'])
+        assert abs(r['loss'] - g['loss']) < 1e-10
+        assert abs(r['grad_norm'] - g['grad_norm']) < 1e-9 * max(1.0, g['grad_norm'])
+        assert abs(r['grad_projection'] - g['grad_projection']) < 1e-9
+        for k_, v in g['grad_group_sqnorm'].items():
+            assert abs(r['grad_group_sqnorm'][k_] - v) < 1e-9 * max(1.0, v), k_
+        np.testing.assert_allclose(r['pred_program_slice'], g['pred_program_slice'], atol=1e-9)
+        np.testing.assert_allclose(r['demo_h_summary_slice'], g['demo_h_summary_slice'], atol=1e-9)
