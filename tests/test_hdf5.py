@@ -204,3 +204,34 @@ def test_vizdoom_dataset_directory(tmp_path):
     b = ds.collate(tr, tr.ids[:2])
     assert b['s_h'].dtype == np.uint8 and b['init_pos'].shape == (2, num_k, 2, PL, 2)
     assert set(ds.VIZDOOM_EXTRA_KEYS) <= set(b)
+
+
+def test_karel_loader_matches_reference_loader_golden(tmp_path):
+    """tests/golden/dataset_karel_golden.json: digests of the 13-tuples the REFERENCE's
+    karel_env/dataset_karel.py Dataset.get_data returns (run in the build container by
+    tests/golden/make_dataset_golden.py over hdf5_lite-as-h5py) on a seeded dataset directory, and
+    the reference's shuffled split ids.  Our loader must return the same arrays (shape, dtype,
+    bytes) in the same split order."""
+    from demo2program_b200 import dataset as ds
+    g = json.load(open(os.path.join(HERE, 'golden', 'dataset_karel_golden.json')))
+    sp = g['spec']
+    d = str(tmp_path / 'golden_ds')
+    ds.write_karel_dataset(d, sp['n_train'], sp['n_test'], sp['n_val'], sp['k'], test_k=sp['test_k'], seed=sp['seed'])
+    ds.rs = np.random.RandomState(123)          # the module-level shuffler of a fresh process
+    tr, te, va = ds.create_default_splits(d, num_k=g['num_k'])
+    assert list(tr.ids) == g['splits']['train'] and list(te.ids) == g['splits']['test'] and list(va.ids) == g['splits']['val']
+    for k_, v in g['attrs'].items():
+        assert getattr(tr, k_) == v
+    n = 0
+    for split in (tr, te, va):
+        for ex_id in split.ids:
+            got = split.get_data(ex_id)
+            want = g['examples'][ex_id]
+            assert len(got) == len(want) == 13
+            for j, (a, w) in enumerate(zip(got, want)):
+                a = np.ascontiguousarray(np.asarray(a))
+                assert list(a.shape) == w['shape'], (ex_id, j, a.shape, w['shape'])
+                assert str(a.dtype) == w['dtype'], (ex_id, j, a.dtype, w['dtype'])
+                assert _digest(a) == w['sha256'], (ex_id, j)
+            n += 1
+    assert n == 17

@@ -193,3 +193,51 @@ def test_batch_metrics_match_oracle():
         for a, b_ in zip(got, want):
             assert np.array_equal(a, b_)
     assert 0 < want[1].sum() < B * k and want[0].sum() < B
+
+
+# ---- pinned against the reference's own code ----------------------------------------------------
+def _golden():
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'karel_dsl_golden.json')))
+    states = [np.unpackbits(np.asarray(s, np.uint8))[:8 * 8 * 16].reshape(8, 8, 16).astype(bool) for s in g['states']]
+    return g, states
+
+
+def test_golden_vocabulary_is_the_reference_vocabulary():
+    g, _ = _golden()
+    assert g['vocab'] == V.int2token
+
+
+def test_parser_interpreter_and_canonical_compare_match_reference_golden():
+    """tests/golden/karel_dsl_golden.json holds outputs of the REFERENCE's karel_env/dsl/dsl_parse.py,
+    karel_env/karel.py and karel_env/dsl/dsl_enum_program.py, run in the build container on programs
+    from the reference's own sampler (tests/golden/make_karel_dsl_golden.py).  Both the oracle
+    restatement and the native library must reproduce: the parse verdict of 330 token sequences, the
+    run status / history length / sha256 of the state history of 708 executions (two initial states,
+    make_error on and off), and 150 canonical-form equalities."""
+    import hashlib
+    g, states = _golden()
+    n_runs = n_ok = 0
+    for c in g['cases']:
+        words = [V.int2token[t] for t in c['tokens']]
+        assert okd.parse(words)[1] == c['syntax'], ' '.join(words)
+        assert kd.check_syntax(c['tokens']) == c['syntax'], ' '.join(words)
+        for r in c['runs']:
+            s0 = states[r['state']]
+            st_o, hist_o = okd.execute(words, s0, r['make_error'])
+            st_n, hist_n = kd.execute(c['tokens'], s0, r['make_error'])
+            assert (st_o == 1) == r['ok'] and (st_n == 1) == r['ok'], (' '.join(words), r)
+            n_runs += 1
+            if r['ok']:
+                n_ok += 1
+                ho = np.stack(hist_o, 0).astype(np.uint8)
+                assert ho.shape[0] == r['len'] == hist_n.shape[0]
+                assert hashlib.sha256(ho.tobytes()).hexdigest() == r['sha256']
+                assert hashlib.sha256(np.ascontiguousarray(hist_n.astype(np.uint8)).tobytes()).hexdigest() == r['sha256']
+    assert n_runs == 708 and n_ok > 400
+    for p in g['pairs']:
+        a, b = g['cases'][p['a']]['tokens'], g['cases'][p['b']]['tokens']
+        wa, wb = [V.int2token[t] for t in a], [V.int2token[t] for t in b]
+        assert okd.programs_equal(wa, wb) == int(p['equal'])
+        assert kd.programs_equal(a, b) == int(p['equal'])

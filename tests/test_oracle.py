@@ -232,3 +232,21 @@ def test_oracle_reproduces_golden():
             assert abs(r['grad_group_sqnorm'][k_] - v) < 1e-9 * max(1.0, v), k_
         np.testing.assert_allclose(r['pred_program_slice'], g['pred_program_slice'], atol=1e-9)
         np.testing.assert_allclose(r['demo_h_summary_slice'], g['demo_h_summary_slice'], atol=1e-9)
+
+
+def test_synthetic_state_sampler_matches_reference_golden():
+    """tests/golden/karel_states_golden.json: states drawn by the REFERENCE's
+    karel_env/generator.py KarelStateGenerator (run in the build container,
+    tests/golden/make_state_golden.py); synthetic.KarelSim must draw bit-identical ones from the
+    same RandomState stream."""
+    import json
+    import os
+    from demo2program_b200.synthetic import KarelSim
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'karel_states_golden.json')))
+    for seed, states in g.items():
+        rng = np.random.RandomState(int(seed))
+        for st in states:
+            sim = KarelSim(rng, 8, 8, 0.1)
+            want = np.unpackbits(np.asarray(st['bits'], np.uint8))[:8 * 8 * 16].reshape(8, 8, 16).astype(bool)
+            assert np.array_equal(np.asarray(sim.s, bool), want), seed
+            assert (sim.y, sim.x) == (st['y'], st['x']) and int(sim.s[:, :, 4].sum()) == st['walls']
