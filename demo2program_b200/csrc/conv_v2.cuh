@@ -11,6 +11,25 @@
 constexpr int CV_TP = 128;       // pixels per tile
 constexpr int CV_THREADS = 128;
 
+// CG (2, 4 or 6) consecutive weights of a slab row; CG and the row pitch are even, so 8-byte (16-byte
+// for CG = 4) shared-memory loads are aligned - one or a few vector loads instead of CG scalar ones
+template <int CG>
+__device__ __forceinline__ void cv_load_w(const float* __restrict__ p, float* b) {
+    if (CG == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    } else if (CG % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < CG; j += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(p + j);
+            b[j] = v.x; b[j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CG; ++j) b[j] = p[j];
+    }
+}
+
 template <typename IN_T>
 __device__ __forceinline__ void cv_load_channels(const IN_T* __restrict__ p, int cin, float* v);
 template <>
@@ -97,8 +116,7 @@ conv_fwd_v2(Geo g, const IN_T* __restrict__ in, const float* __restrict__ in_sca
                 const float4 a1 = *reinterpret_cast<const float4*>(As + (size_t)kk * CV_TP + pg * 8 + 4);
                 const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 float b[CG];
-#pragma unroll
-                for (int j = 0; j < CG; ++j) b[j] = Ws[kk * COUT + cg * CG + j];
+                cv_load_w<CG>(Ws + kk * COUT + cg * CG, b);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -170,8 +188,7 @@ conv_bwd_dx_v2(Geo g, const float* __restrict__ dZ, const float* __restrict__ W,
                     const float4 a1 = *reinterpret_cast<const float4*>(As + (size_t)kk * CV_TP + pg * 8 + 4);
                     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     float b[CG];
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) b[j] = Ws[kk * CIN + cg * CG + j];
+                    cv_load_w<CG>(Ws + kk * CIN + cg * CG, b);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll

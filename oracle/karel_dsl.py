@@ -1,8 +1,14 @@
 """TEST INFRASTRUCTURE ONLY - CPU restatement of the reference's Karel DSL parser, interpreter
 and program-level metrics; the product path (demo2program_b200/csrc/karel_dsl.cu) never imports
-this file.  Parity unpinned: the reference ships no tests or golden vectors for this code and is
-Python-2-only (`zip(*t)[0]`, karel_env/dsl/dsl_parse.py:8), so it cannot be imported here; the
-restatement follows its sources line by line:
+this file.  PINNED against the reference itself: karel_env/dsl/dsl_parse.py, karel_env/karel.py and
+karel_env/dsl/dsl_enum_program.py are plain Python and do run in the build container once
+`zip(*t)[0]` (dsl_parse.py:8, a Python-2 idiom) is patched at run time;
+tests/golden/make_karel_dsl_golden.py runs them on 330 token sequences and stores parse verdicts,
+708 execution results (sha256 of the state histories) and 150 canonical-form equalities in
+tests/golden/karel_dsl_golden.json, which this restatement and the native library both reproduce
+bit-exactly (tests/test_karel_dsl.py).  The batch metric composition (`eval_batch`) follows
+models/model_full.py, whose closures live inside the TF graph builder and cannot be imported.
+The restatement follows the sources line by line:
 
   * parser / rule closures   karel_env/dsl/dsl_parse.py:4-13, 21-262
   * Karel world              karel_env/karel.py:33-185
