@@ -284,7 +284,10 @@ def run_ours(args):
     dom = time_dominant_kernel(eng)
     roofline = {
         'bound': 'tensor', 'achieved': dom['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
-        'frac': dom['tflops'] / pk['bf16_tflops'], 'traffic': None,
+        'frac': dom['tflops'] / pk['bf16_tflops'],
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one launch, from the
+        # committed `ncu --set full` capture (profiles/r01b_ncu_full_metrics.txt: 41.9 MB read + 13.6 MB written)
+        'traffic': 55.5e6, 'traffic_unit': 'bytes/launch (ncu --set full, cold cache)',
         'kernel': dom['kernel'], 'shape_R_4H_H_T': dom['shape'], 'kernel_ms': dom['ms'],
         'peak_kind': pk_kind + ' bf16 burst (cuBLAS 8192^3); achieved counts ALGORITHMIC flops '
                      '2*R*H*4H*T - the bf16x3 split executes 3x that on the tensor pipe; the kernel is '
@@ -294,7 +297,7 @@ def run_ours(args):
                           'achieved': dom['bwd']['tflops'], 'frac': dom['bwd']['tflops'] / pk['bf16_tflops']},
     }
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         sec, ctoks, threads = cpu_reference_step_time(cfg, 2, 1)
         cpu = {'value': ctoks / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': '2 full train steps of %s (1 warm-up), oracle restatement of the TF1 graph, '
