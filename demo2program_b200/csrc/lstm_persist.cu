@@ -101,6 +101,7 @@ __device__ __forceinline__ float sigmoid_p(float x) { return rcp_approx(1.0f + _
 __device__ __forceinline__ float tanh_p(float x) { return 1.0f - 2.0f * rcp_approx(1.0f + __expf(2.0f * x)); }
 // staging of the per-step outputs in the (idle) operand ring: [array][row][16 units + 4 pad]
 constexpr int PSROW = PUPT + 4;
+constexpr size_t P_STAGE_BYTES = (size_t)6 * 128 * PSROW * sizeof(float);   // 6 arrays x 128 rows
 __device__ __forceinline__ float* stage_ptr(float* stg, int arr, int row, int unit) {
     return stg + ((size_t)arr * BM + row) * PSROW + unit;
 }
@@ -120,9 +121,11 @@ struct PersistBars {
     uint32_t a_bytes;      // bytes of one streamed k-block (whole 8-row groups of the row tile)
 };
 // ring position of a role lane (producer or MMA issuer), carried across steps
-struct RingPos { int slot; uint32_t wraps; };
+// (bit s of `par` = parity of this lane's next wait on slot s, bit s of `used` = slot s has been
+// filled before: per-slot phases, so that a step may start at any slot)
+struct RingPos { int slot; uint32_t par; uint32_t used; };
 __device__ __forceinline__ void ring_next(RingPos& r, int nslots) {
-    if (++r.slot == nslots) { r.slot = 0; ++r.wraps; }
+    if (++r.slot == nslots) r.slot = 0;
 }
 
 // Common setup: barriers, TMEM (64 columns), zeroed ring, resident weight slab.
@@ -167,21 +170,24 @@ __device__ __forceinline__ uint32_t persist_setup(uint8_t* smem, uint64_t* bars,
 // One pass of the streamed operand over the resident slab.  Column CTAs walk the 8 k-blocks
 // in rotated order (rot) so that the 32 CTAs of a row tile do not queue on one L2 line range.
 __device__ __forceinline__ void persist_produce(const PersistBars& pb, RingPos& rp, uint32_t sbase,
-                                                const uint8_t* a_src, size_t a_kb_stride, int rot) {
+                                                const uint8_t* a_src, size_t a_kb_stride, int rot,
+                                                int kb_first = 0, int kb_end = PNKB) {
     if (pb.single) {
         // small row tile stored without row padding: the 8 k-blocks are one contiguous run that
         // fills the 8 slots in order - one request instead of eight (~300 issue cycles each)
         mbar_expect_tx(pb.full0, PNKB * pb.a_bytes);
         bulk_copy(sbase + (uint32_t)P_W_BYTES, a_src, PNKB * pb.a_bytes, pb.full0);
-        ++rp.wraps;
         return;
     }
-    for (int kb = 0; kb < PNKB; ++kb) {
-        if (pb.nslots < PNKB && rp.wraps > 0) mbar_wait(pb.empty0 + 8 * rp.slot, (rp.wraps - 1) & 1);
+    for (int kb = kb_first; kb < kb_end; ++kb) {
+        const uint32_t bit = 1u << rp.slot;
+        if (pb.nslots < PNKB && (rp.used & bit)) mbar_wait(pb.empty0 + 8 * rp.slot, ((rp.par >> rp.slot) & 1u) ^ 1u);
         const uint32_t bar = pb.full0 + 8 * rp.slot;
         mbar_expect_tx(bar, pb.a_bytes);
         bulk_copy(sbase + (uint32_t)P_W_BYTES + rp.slot * pb.a_bytes,
                   a_src + (size_t)((kb + rot) & (PNKB - 1)) * a_kb_stride, pb.a_bytes, bar);
+        rp.par ^= bit;
+        rp.used |= bit;
         ring_next(rp, pb.nslots);
     }
 }
@@ -219,7 +225,11 @@ __device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, 
 #pragma unroll 1
     if (pb.single) rot = 0;
     for (int kb = 0; kb < PNKB; ++kb) {
-        if (!pb.single || kb == 0) mbar_wait(pb.full0 + 8 * (pb.single ? 0 : rp.slot), rp.wraps & 1);
+        if (!pb.single || kb == 0) {
+            const int ws = pb.single ? 0 : rp.slot;
+            mbar_wait(pb.full0 + 8 * ws, (rp.par >> ws) & 1u);
+            rp.par ^= 1u << ws;
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t ad = a_base + (uint64_t)(rp.slot * a_slot);
         const uint64_t wd = w_base + (uint64_t)(((kb + rot) & (PNKB - 1)) * (PB_BYTES >> 4));
@@ -263,7 +273,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
     const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a_kb_stride,
                                           a.whpk + (size_t)(n0 / PBN) * PB_BYTES, (size_t)a.mgp_w * 2048);
     const uint32_t sbase = smem_u32(smem);
-    RingPos rp{0, 0};   // used by the producer lane and (separately) by the MMA lane
+    RingPos rp{0, 0, 0};   // used by the producer lane and (separately) by the MMA lane
+    // Early first block: the per-step outputs are staged in the low P_STAGE_BYTES of the ring; when
+    // the LAST ring slot lies above them, every step starts its slot sequence there, and the
+    // producer fetches the first k-block of step t+1 while step t's copy-out is still draining
+    // (the step barrier and one bulk-copy latency disappear behind the copy-out).
+    const bool early = !pb.single && pb.nslots < PNKB &&
+                       (uint32_t)(pb.nslots - 1) * pb.a_bytes >= (uint32_t)P_STAGE_BYTES;
+    bool early_issued = false;   // (producer lane) k-block 0 of the coming step is already in flight
 
     // This thread's item: accumulator row (= its TMEM lane) 32 (warp % 4) + lane, hidden units
     // u0 + 4 (warp / 4) .. + 4.  The cell state c and the carried h stay in registers.
@@ -293,12 +310,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
         if (tid == 0) pstamp(t, 0);
         if (warp == 0 && lane == 0) {
-            if (t > 0) grid_wait(ctr, (unsigned)(PCOLS * t), err);
+            if (t > 0 && !early_issued) grid_wait(ctr, (unsigned)(PCOLS * t), err);
             pstamp(t, 1);
             proxy_fence();   // also orders the previous step's generic staging accesses before the bulk writes
-            persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot);
+            if (early && !early_issued) rp.slot = pb.nslots - 1;
+            persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot,
+                            early_issued ? 1 : 0);
             pstamp(t, 2);
         } else if (warp == 1 && lane == 0) {
+            if (early) rp.slot = pb.nslots - 1;
             persist_mma(pb, rp, sbase, tmem_d, rot, t == 0);
             pstamp(t, 3);
             // only this lane polls the accumulator barrier; everybody else parks on the hardware
@@ -365,7 +385,21 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
             }
         }
         if (tid == 64) pstamp(t, 9);
-        __syncthreads();   // staging drained before the next step's bulk copies land in the ring
+        if (tid == 0) {
+            early_issued = false;
+            if (early && t + 1 < a.T) {
+                // k-block 0 of step t+1 into the slot above the staging area (all MMAs of step t
+                // have retired: its empty barrier is already complete)
+                grid_wait(ctr, (unsigned)(PCOLS * (t + 1)), err);
+                proxy_fence();
+                rp.slot = pb.nslots - 1;
+                persist_produce(pb, rp, sbase, (((t + 1) & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048,
+                                a_kb_stride, rot, 0, 1);
+                early_issued = true;
+                pstamp(t, 10);
+            }
+        }
+        __syncthreads();   // staging drained before the next step's bulk copies land in the lower slots
     }
     if (valid) {
         st4r(a.hT + su, h);
@@ -439,7 +473,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     const uint32_t sbase = smem_u32(smem);
     float* stage = reinterpret_cast<float*>(smem + P_W_BYTES);          // [128][PGROW] partial tile
     const uint32_t stage_u32 = sbase + (uint32_t)P_W_BYTES;
-    RingPos rp{0, 0};
+    RingPos rp{0, 0, 0};
 
     // phase-P item of this thread: (row, 4 hidden units) of units [16 q, 16 q + 16)
     const int row = tid >> 2, up = (tid & 3) * 4, u = q * PUPT + up, r = m0 + row;

@@ -84,7 +84,7 @@ def run(T, R, In, with_init, mode, seed=0, reps=0):
 
 def main():
     ok = True
-    for (T, R, In, init) in [(20, 320, 48, False), (20, 320, 512, True), (50, 32, 512, True), (7, 130, 512, True),
+    for (T, R, In, init) in [(20, 320, 48, False), (20, 320, 512, True), (50, 32, 512, True), (7, 130, 512, True), (6, 40, 512, True), (4, 120, 512, True), (5, 56, 512, False),
                              (3, 5, 512, False)]:
         a, ta = run(T, R, In, init, 0, reps=5)
         b, tb = run(T, R, In, init, 1, reps=5)
