@@ -35,12 +35,19 @@ class Evaler(object):
         log.info("Using Model class: %s", Model)
         self.model = Model(config, is_train=False)
         self.checkpoint = config.checkpoint
+        from demo2program_b200 import tf_checkpoint
+        if self.checkpoint == '' and self.train_dir:
+            # tf.train.latest_checkpoint(train_dir) (reference evaler.py:86), else the newest .npz
+            self.checkpoint = tf_checkpoint.latest_checkpoint(self.train_dir) or ''
         if self.checkpoint == '' and self.train_dir:
             cands = sorted(glob.glob(os.path.join(self.train_dir, 'model-*.npz')),
                            key=lambda p: int(p.rsplit('-', 1)[1][:-4]))
             self.checkpoint = cands[-1] if cands else ''
         if self.checkpoint:
-            self.model.load_state_dict(dict(np.load(self.checkpoint)))
+            if tf_checkpoint.is_tf_checkpoint(self.checkpoint):
+                tf_checkpoint.load_model(self.checkpoint, self.model, restore_optimizer=False)
+            else:
+                self.model.load_state_dict(dict(np.load(self.checkpoint)))
             log.info("Loaded from checkpoint: %s", self.checkpoint)
         else:
             log.warning("No checkpoint given: evaluating the initial parameters")

@@ -307,6 +307,11 @@ int d2p_debug_set_probe(long long* buf);
  * order; called between ops during graph capture it yields the timeline of a replay. */
 int d2p_debug_stamp(unsigned long long* buf, int slot, void* stream);
 
+/* Host-side CRC-32C (Castagnoli), running form: pass 0 (or the value returned for the bytes so
+ * far).  Used by demo2program_b200/tf_checkpoint.py for the block and tensor checksums of
+ * TensorFlow checkpoint files (tf.train.Saver at reference trainer.py:114,145,182, evaler.py:82-99). */
+unsigned int d2p_crc32c(const void* data, size_t n, unsigned int crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
 same seeded inputs.  Floating-point path: tolerances are written per test;
 BASELINE.json's north_star asks for training loss within 1e-4 (fp32)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -275,6 +277,51 @@ def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
     rep = open(tmp_path / 'report.txt').read()
     assert 'program_loss' in rep and 'greedy_program_token_acc' in rep and 'program_syntax_acc' in rep
     assert 'nan' not in rep.lower()
+    # the trainer also writes the reference's own checkpoint format (TF tensor bundle + state file);
+    # the evaler finds it through the train_dir like tf.train.latest_checkpoint and reports the same
+    train_dir = os.path.dirname(ck[0])
+    assert os.path.exists(os.path.join(train_dir, 'checkpoint'))
+    assert glob.glob(os.path.join(train_dir, 'model-*.index')) and glob.glob(os.path.join(train_dir, 'model-*.data-00000-of-00001'))
+    evaler.main(['--model', 'synthesis_baseline', '--dataset_path', 'synthetic:64', '--num_k', '2',
+                 '--batch_size', '8', '--max_steps', '2', '--train_dir', train_dir, '--quiet',
+                 '--summary_file', str(tmp_path / 'report_tf.txt')])
+    strip = lambda t: [l for l in t.splitlines() if 'heckpoint' not in l and 'time' not in l.lower()]
+    assert strip(open(tmp_path / 'report_tf.txt').read()) == strip(rep)
+
+
+def test_tf_checkpoint_resume_is_bitwise(tmp_path):
+    """save_model / load_model (TF tensor-bundle files by variable name, incl. Adam slots and
+    global_step): a restored model continues exactly like the one that kept running; the
+    trainable-only restore (pretrain_saver, reference trainer.py:115,145) leaves BatchNorm moving
+    statistics and the optimizer untouched."""
+    from demo2program_b200 import tf_checkpoint as tfc
+    from demo2program_b200.model import Model
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('full', batch_size=4, k=3)
+    batches = [make_batch(cfg, seed=20 + i) for i in range(4)]
+    a = Model(cfg, use_graph=False)
+    for b in batches[:2]:
+        a.engine.train_step(b)
+    prefix = str(tmp_path / 'model-2')
+    names = tfc.save_model(prefix, a)
+    assert 'global_step' in names and 'optimizer_pixel_loss/Demo_Encoder/rnn/basic_lstm_cell/kernel/Adam_1' in names
+    assert int(tfc.load_checkpoint(prefix, names=['global_step'])['global_step']) == 2
+    b2 = Model(cfg, use_graph=False)
+    assert tfc.load_model(prefix, b2) == 2
+    for t in ('params', 'state', 'adam_m', 'adam_v'):
+        assert torch.equal(getattr(a.engine, t), getattr(b2.engine, t)), t
+    for b in batches[2:]:
+        la, lb = a.engine.train_step(b), b2.engine.train_step(b)
+        assert float(la) == float(lb)
+    assert torch.equal(a.engine.params, b2.engine.params)
+    c = Model(cfg, use_graph=False)
+    s0 = c.engine.state.clone()
+    tfc.load_model(prefix, c, trainable_only=True)
+    assert torch.equal(c.engine.state, s0) and c.engine.step_count() == 0
+    assert float(c.engine.adam_m.abs().max()) == 0.0
+    os.remove(prefix + '.index')
+    with pytest.raises(IOError):
+        tfc.load_model(prefix, c)
 
 
 def test_cli_trainer_on_hdf5_dataset_directory(tmp_path, monkeypatch):

@@ -52,7 +52,13 @@ class Trainer(object):
         self.test_sample_step = config.test_sample_step
         if config.checkpoint is not None:
             log.info("Checkpoint path: %s", config.checkpoint)
-            self.model.load_state_dict(dict(np.load(config.checkpoint)), trainable_only=True)
+            # a TF checkpoint prefix (what the reference's Saver writes, e.g. .../model-5000) or a
+            # .npz keyed by variable name; trainable variables only (pretrain_saver, trainer.py:115,145)
+            from demo2program_b200 import tf_checkpoint
+            if tf_checkpoint.is_tf_checkpoint(config.checkpoint):
+                tf_checkpoint.load_model(config.checkpoint, self.model, trainable_only=True)
+            else:
+                self.model.load_state_dict(dict(np.load(config.checkpoint)), trainable_only=True)
             log.info("Loaded the pretrain parameters from the provided checkpoint path")
 
     def train(self, max_steps=1000000):
@@ -68,6 +74,10 @@ class Trainer(object):
             if s % ckpt_save_step == 0 and self.config.rank == 0:
                 log.info("Saved checkpoint at %d", s)
                 np.savez(os.path.join(self.train_dir, 'model-%d.npz' % step), **self.model.state_dict())
+                # and in the reference's own format (saver.save(..., 'model', global_step), trainer.py:182):
+                # model-<step>.index / .data-00000-of-00001 + the `checkpoint` state file
+                from demo2program_b200 import tf_checkpoint
+                tf_checkpoint.save_model(os.path.join(self.train_dir, 'model-%d' % step), self.model)
 
     def run_single_step(self, batch, step=None, is_train=True):
         _start_time = time.time()
