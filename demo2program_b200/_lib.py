@@ -114,6 +114,7 @@ SIGNATURES = {
     'd2p_conv_set_fused': (_i, [_i]),
     'd2p_device_error': (_i, [_fp]),
     'd2p_debug_stamp': (_i, [_fp, _i, _fp]),
+    'd2p_gemm_set_persistent': (_i, [_i]),
     'd2p_crc32c': (C.c_uint32, [_fp, _sz, C.c_uint32]),
     'd2p_gemm': (_i, [_i, _i, _i, _i, _i, _f, _fp, _i, _fp, _i, _f, _fp, _i, _fp,
                       _fp]),

@@ -110,6 +110,196 @@ gemm_tc_kernel(Packed A, Packed B, int M, int N, int K, float alpha, float beta,
     tc_teardown<BN>(tmem_d);
 }
 
+
+// ---- persistent variant for large products (more output tiles than SMs, no split-K) ----
+// One CTA per SM keeps pulling 128 x 128 output tiles from an atomic tile counter (dynamic: the
+// grid may share the GPU with a persistent recurrence kernel, so CTAs start at different times).
+// Six warps: producer lane, MMA-issuer lane, four epilogue warps.  The accumulator is double
+// buffered in TMEM (2 x 128 columns): while the epilogue warps drain tile i (tcgen05.ld ->
+// per-warp staging rows -> coalesced stores, alpha/beta/bias applied), the producer and the MMA
+// lane are already running the k-loop of tile i+1, so the tensor pipe does not idle during the
+// epilogue and barrier / TMEM set-up is paid once per CTA instead of once per tile.
+//   tile queue:   tq_full[4] / tq_empty[4]  (producer -> MMA lane + 4 epilogue warps)
+//   operand ring: full[3] / empty[3]        (bulk copies -> MMA, tcgen05.commit -> producer)
+//   accumulators: acc_full[2] / acc_empty[2] (tcgen05.commit -> epilogue, epilogue -> MMA)
+constexpr int PG_STAGES = 3, PG_BN = 128, PG_NQ = 4, PG_THREADS = 192, PG_HALF = 64;
+constexpr int PG_SROW = PG_HALF + 4;
+constexpr uint32_t PG_A_BYTES = (BM / 8) * 2048, PG_B_BYTES = (PG_BN / 8) * 2048;
+constexpr uint32_t PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
+constexpr size_t PG_SMEM = (size_t)PG_STAGES * PG_STAGE_BYTES + (size_t)4 * 32 * PG_SROW * sizeof(float);
+
+__global__ void __launch_bounds__(PG_THREADS, 1)
+gemm_tc_persist_kernel(Packed A, Packed B, int M, int N, int K, float alpha, float beta,
+                       float* __restrict__ C, int ldc, const float* __restrict__ bias,
+                       unsigned* __restrict__ tile_ctr) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * PG_STAGES + 4 + 2 * PG_NQ];
+    __shared__ int tile_ids[PG_NQ];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntn = N / PG_BN, ntm = (M + BM - 1) / BM, ntiles = ntn * ntm, nk = (K + BK - 1) / BK;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[PG_STAGES]);
+    const uint32_t accf0 = smem_u32(&bars[2 * PG_STAGES]), acce0 = accf0 + 16;
+    const uint32_t tqf0 = acce0 + 16, tqe0 = tqf0 + 8 * PG_NQ;
+    if (tid == 0) {
+        for (int s = 0; s < 2 * PG_STAGES; ++s) mbar_init(full0 + 8 * s, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(accf0 + 8 * s, 1); mbar_init(acce0 + 8 * s, 4); }
+        for (int s = 0; s < PG_NQ; ++s) { mbar_init(tqf0 + 8 * s, 1); mbar_init(tqe0 + 8 * s, 5); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * PG_BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    volatile int* tq = tile_ids;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer: tile queue + operand ring =====
+            const size_t a_kb = (size_t)A.mgp * 2048, b_kb = (size_t)B.mgp * 2048;
+            uint32_t it = 0;
+            for (int i = 0;; ++i) {
+                const int q = i & (PG_NQ - 1);
+                if (i >= PG_NQ) mbar_wait(tqe0 + 8 * q, ((i / PG_NQ) - 1) & 1);
+                const unsigned t = atomicAdd(tile_ctr, 1u);
+                const int tile = t < (unsigned)ntiles ? (int)t : -1;
+                tq[q] = tile;
+                mbar_arrive(tqf0 + 8 * q);
+                if (tile < 0) break;
+                const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * PG_BN;
+                const uint8_t* a_src = A.p + (size_t)(m0 / 8) * 2048;
+                const uint8_t* b_src = B.p + (size_t)(n0 / 8) * 2048;
+                int kr = nk > 1 ? (int)(((unsigned)tile * 5u) % (unsigned)nk) : 0;   // rotated K order per tile
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t slot = it % PG_STAGES;
+                    if (it >= (uint32_t)PG_STAGES) mbar_wait(empty0 + 8 * slot, ((it / PG_STAGES) - 1) & 1);
+                    const uint32_t bar = full0 + 8 * slot;
+                    mbar_expect_tx(bar, PG_STAGE_BYTES);
+                    const uint32_t sa = sbase + slot * PG_STAGE_BYTES, sb = sa + PG_A_BYTES;
+                    bulk_copy(sa, a_src + (size_t)kr * a_kb, PG_A_BYTES, bar);
+                    bulk_copy(sb, b_src + (size_t)kr * b_kb, PG_B_BYTES, bar);
+                    if (++kr == nk) kr = 0;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t LBO = 256, SBO = 2048;
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PG_BN >> 3) << 17) |
+                                       ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0;
+            for (int i = 0;; ++i) {
+                const int q = i & (PG_NQ - 1);
+                mbar_wait(tqf0 + 8 * q, (i / PG_NQ) & 1);
+                const int tile = tq[q];
+                mbar_arrive(tqe0 + 8 * q);
+                if (tile < 0) break;
+                const int buf = i & 1;
+                if (i >= 2) mbar_wait(acce0 + 8 * buf, ((i >> 1) - 1) & 1);   // epilogue has drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_d + (uint32_t)(buf * PG_BN);
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t slot = it % PG_STAGES;
+                    mbar_wait(full0 + 8 * slot, (it / PG_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = sbase + slot * PG_STAGE_BYTES, sb = sa + PG_A_BYTES;
+                    const uint64_t a0 = make_desc(sa, LBO, SBO), b0 = make_desc(sb, LBO, SBO);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t ahi = a0 + (uint64_t)(kk * 32), alo = ahi + 8;
+                        const uint64_t bhi = b0 + (uint64_t)(kk * 32), blo = bhi + 8;
+                        umma_bf16(d, ahi, bhi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                        umma_bf16(d, ahi, blo, idesc, 1u);
+                        umma_bf16(d, alo, bhi, idesc, 1u);
+                    }
+                    umma_commit(empty0 + 8 * slot);
+                }
+                umma_commit(accf0 + 8 * buf);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 =====
+        const int lq = warp & 3;
+        float* stage = reinterpret_cast<float*>(smem + (size_t)PG_STAGES * PG_STAGE_BYTES) +
+                       (size_t)(warp - 2) * 32 * PG_SROW;
+        const int cl = (lane & 15) * 4, rl = lane >> 4;
+        for (int i = 0;; ++i) {
+            const int q = i & (PG_NQ - 1);
+            if (lane == 0) mbar_wait(tqf0 + 8 * q, (i / PG_NQ) & 1);   // one polling lane per warp
+            __syncwarp();
+            const int tile = tq[q];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tqe0 + 8 * q);
+            if (tile < 0) break;
+            const int buf = i & 1;
+            if (lane == 0) mbar_wait(accf0 + 8 * buf, (i >> 1) & 1);
+            __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m0 = (tile / ntn) * BM + lq * 32, n0 = (tile % ntn) * PG_BN;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32], w[32];
+                const uint32_t ta = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * PG_BN + half * PG_HALF);
+                tmem_ld32(ta, v);
+                tmem_ld32(ta + 32, w);
+                tmem_ld_wait();
+                if (half == 1) {   // accumulator fully read: hand the buffer back to the MMA lane
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+                }
+                float* srow = stage + (size_t)lane * PG_SROW;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    *reinterpret_cast<float4*>(srow + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    *reinterpret_cast<float4*>(srow + 32 + j) =
+                        make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]),
+                                    __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
+                }
+                __syncwarp();
+                const int nc = n0 + half * PG_HALF + cl;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) bv = *reinterpret_cast<const float4*>(bias + nc);
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int row = rr + rl, m = m0 + row;
+                    if (m < M) {
+                        const float4 x = *reinterpret_cast<const float4*>(stage + (size_t)row * PG_SROW + cl);
+                        float4 r = make_float4(alpha * x.x + bv.x, alpha * x.y + bv.y, alpha * x.z + bv.z,
+                                               alpha * x.w + bv.w);
+                        float4* dst = reinterpret_cast<float4*>(C + (size_t)m * ldc + nc);
+                        if (beta != 0.f) {
+                            const float4 o = *dst;
+                            r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w;
+                        }
+                        *dst = r;
+                    }
+                }
+                __syncwarp();   // staging rows are rewritten by the next half / tile
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                     "r"((uint32_t)(2 * PG_BN)));
+}
+
+int g_persist_gemm = 0;   // d2p_gemm_set_persistent: 0 = always one CTA per tile (default until validated on the GPU)
+
 // C = alpha * sum_z partials[z] + beta*C + bias
 __global__ void splitk_reduce_kernel(const float* __restrict__ partials, int ksplit, int M, int N,
                                      float alpha, float beta, float* __restrict__ C, int ldc,
@@ -230,6 +420,8 @@ int auto_ksplit(int M, int N, int K) {
 
 }  // namespace
 
+unsigned* tc_tile_counter(cudaStream_t st);
+
 // Pack Op[mn,k] (MN x K) from an fp32 array; k_contig selects the source memory order.
 int pack_bf16(cudaStream_t st, const float* S, int MN, int K, int ld, bool k_contig, void* out,
               int gate_tile, int gate_H, int mgp_override) {
@@ -260,6 +452,22 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
     // few wide tiles with a long K: 128-wide tiles split over K fill the SMs with half the MMA
     // instructions of 64-wide tiles (an M = 128 MMA costs ~68 cycles for N = 64 and N = 128 alike)
     const long long tiles128 = (long long)cdiv(N, 128) * cdiv(M, BM);
+    if (!use_part && g_persist_gemm && tiles128 > kNumSMs && N % PG_BN == 0 && ldc % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+        unsigned* ctr = tc_tile_counter(st);
+        if (ctr != nullptr) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                D2P_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG_SMEM));
+                attr_set = true;
+            }
+            D2P_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
+            gemm_tc_persist_kernel<<<kNumSMs, PG_THREADS, PG_SMEM, st>>>(A, B, M, N, K, alpha, beta, C, ldc, bias, ctr);
+            D2P_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     bool narrow = tiles128 < kNumSMs && !(ksplit > 1 && tiles128 * ksplit >= kNumSMs / 2 && N % 128 == 0);
     int zs;
     if (narrow)
@@ -309,10 +517,23 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha,
 // ---- arena + per-step cache of packed constant operands (weights) ------------
 bool tc_available() { return g_tc.enabled && g_tc.scratch != nullptr; }
 
+// The last TC_ARENA_TAIL bytes of every stream's arena hold the tile counter of the persistent
+// GEMM kernel (stream-ordered reuse, like the rest of the arena).
+constexpr size_t TC_ARENA_TAIL = 256;
+
+unsigned* tc_tile_counter(cudaStream_t st) {
+    char* base = g_tc.scratch; size_t cap = g_tc.scratch_bytes;
+    for (int i = 0; i < g_tc.n_streams; ++i)
+        if (g_tc.per_stream[i].st == st) { base = g_tc.per_stream[i].p; cap = g_tc.per_stream[i].bytes; }
+    if (!g_tc.enabled || base == nullptr || cap < 2 * TC_ARENA_TAIL) return nullptr;
+    return reinterpret_cast<unsigned*>(base + ((cap - TC_ARENA_TAIL) & ~(size_t)255));
+}
+
 void* tc_scratch_alloc(cudaStream_t st, size_t* scratch_off, size_t bytes) {
     char* base = g_tc.scratch; size_t cap = g_tc.scratch_bytes;
     for (int i = 0; i < g_tc.n_streams; ++i)
         if (g_tc.per_stream[i].st == st) { base = g_tc.per_stream[i].p; cap = g_tc.per_stream[i].bytes; }
+    cap = cap >= 2 * TC_ARENA_TAIL ? ((cap - TC_ARENA_TAIL) & ~(size_t)255) : 0;
     bytes = al256(bytes);
     if (*scratch_off + bytes > cap) return nullptr;
     void* p = base + *scratch_off;
@@ -353,7 +574,7 @@ size_t tc_scratch_capacity(cudaStream_t st) {
     size_t cap = g_tc.scratch_bytes;
     for (int i = 0; i < g_tc.n_streams; ++i)
         if (g_tc.per_stream[i].st == st) cap = g_tc.per_stream[i].bytes;
-    return cap;
+    return cap >= 2 * TC_ARENA_TAIL ? ((cap - TC_ARENA_TAIL) & ~(size_t)255) : 0;
 }
 
 // Packed operands in, heuristic split-K with partial sums from the stream's arena.
@@ -443,6 +664,13 @@ extern "C" int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_by
     D2P_REQUIRE(d2p::g_tc.n_streams < 8 && scratch != nullptr, "tc_bind_stream: too many streams");
     d2p::g_tc.per_stream[d2p::g_tc.n_streams++] =
         d2p::StreamArena{(cudaStream_t)stream, (char*)scratch, scratch_bytes};
+    return 0;
+}
+
+// 1 (default): products with more 128 x 128 output tiles than SMs run on the persistent kernel
+// (dynamic tile queue, epilogue overlapped with the next tile's k-loop); 0: one CTA per tile.
+extern "C" int d2p_gemm_set_persistent(int mode) {
+    d2p::g_persist_gemm = mode;
     return 0;
 }
 

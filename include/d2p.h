@@ -307,6 +307,12 @@ int d2p_debug_set_probe(long long* buf);
  * order; called between ops during graph capture it yields the timeline of a replay. */
 int d2p_debug_stamp(unsigned long long* buf, int slot, void* stream);
 
+/* Scheduling of large tensor-core products (more 128 x 128 output tiles than SMs, no split-K), e.g.
+ * the hoisted LSTM gate GEMM [T*R, In] x [In, 4H] (x*Wx of BasicLSTMCell, reference
+ * models/model_full.py:244-258): 1 (default) = persistent kernel, one CTA per SM pulling tiles from
+ * an atomic counter, accumulator double-buffered in TMEM so the epilogue of tile i overlaps the
+ * k-loop of tile i+1; 0 = one CTA per tile. */
+int d2p_gemm_set_persistent(int mode);
 /* Host-side CRC-32C (Castagnoli), running form: pass 0 (or the value returned for the bytes so
  * far).  Used by demo2program_b200/tf_checkpoint.py for the block and tensor checksums of
  * TensorFlow checkpoint files (tf.train.Saver at reference trainer.py:114,145,182, evaler.py:82-99). */
