@@ -298,7 +298,7 @@ gemm_tc_persist_kernel(Packed A, Packed B, int M, int N, int K, float alpha, flo
                      "r"((uint32_t)(2 * PG_BN)));
 }
 
-int g_persist_gemm = 0;   // d2p_gemm_set_persistent: 0 = always one CTA per tile (default until validated on the GPU)
+int g_persist_gemm = 1;   // d2p_gemm_set_persistent: 0 = always one CTA per tile
 
 // C = alpha * sum_z partials[z] + beta*C + bias
 __global__ void splitk_reduce_kernel(const float* __restrict__ partials, int ksplit, int M, int N,
