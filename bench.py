@@ -198,7 +198,33 @@ def time_dominant_kernel(eng, iters=20):
             tf += e[0].elapsed_time(e[1]); tb += e[2].elapsed_time(e[3])
     tf /= iters; tb /= iters
     flops = 2.0 * R * H * 4 * H * T
-    return {'kernel': 'lstm_persist_fwd_kernel (persistent weight-stationary LSTM recurrence, tcgen05 bf16x3 '
+    # the hoisted gate GEMM of the same LSTM, x*Wx for all T steps at once: [T*R, H] x [H, 4H] on the
+    # persistent tile-queue tensor-core kernel (gemm_tc_persist_kernel), packed operands resident
+    M, N, K = T * R, 4 * H, H
+    A2 = (torch.randn(M, K, generator=g)).to(dev)
+    B2 = (torch.randn(N, K, generator=g)).to(dev)
+    C2 = z(M, N)
+    apk = torch.empty(lib.d2p_packed_bytes(M, K), dtype=torch.uint8, device=dev)
+    bpk = torch.empty(lib.d2p_packed_bytes(N, K), dtype=torch.uint8, device=dev)
+    check(lib.d2p_pack_bf16(ptr(A2), M, K, K, 1, ptr(apk), st.cuda_stream), 'pack')
+    check(lib.d2p_pack_bf16(ptr(B2), N, K, K, 1, ptr(bpk), st.cuda_stream), 'pack')
+    tg = 0.0
+    for i in range(iters + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        check(lib.d2p_gemm_tc_packed(ptr(apk), ptr(bpk), M, N, K, 1.0, 0.0, ptr(C2), N, None, 1, None,
+                                     st.cuda_stream), 'gate gemm')
+        e1.record(st)
+        e1.synchronize()
+        if i >= 2:
+            tg += e0.elapsed_time(e1)
+    tg /= iters
+    gflops = 2.0 * M * N * K
+    gate = {'kernel': 'gemm_tc_persist_kernel (hoisted LSTM gate GEMM x*Wx, persistent tile queue, TMEM '
+                      'double-buffered accumulator, bf16x3)', 'shape_M_N_K': [M, N, K], 'ms': tg,
+            'tflops': gflops / (tg * 1e-3) / 1e12}
+    return {'gate_gemm': gate, 'kernel': 'lstm_persist_fwd_kernel (persistent weight-stationary LSTM recurrence, tcgen05 bf16x3 '
                       'gate GEMM per step, R=320 rows x T=20 steps in one cooperative launch)',
             'shape': [R, 4 * H, H, T], 'ms': tf, 'tflops': flops / (tf * 1e-3) / 1e12,
             'bwd': {'kernel': 'lstm_persist_bwd_kernel (clusters of 4 split-K CTAs, DSMEM reduction)',
@@ -286,13 +312,20 @@ def run_ours(args):
         'bound': 'tensor', 'achieved': dom['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
         'frac': dom['tflops'] / pk['bf16_tflops'],
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one launch, from the
-        # committed `ncu --set full` capture (profiles/r01b_ncu_full_metrics.txt: 41.9 MB read + 13.6 MB written)
-        'traffic': 55.5e6, 'traffic_unit': 'bytes/launch (ncu --set full, cold cache)',
+        # committed `ncu --set full` capture (profiles/r01d_ncu_full_metrics.txt: 41.9 MB read + 16.3 MB written)
+        'traffic': 58.3e6, 'traffic_unit': 'bytes/launch (ncu --set full, cold cache)',
         'kernel': dom['kernel'], 'shape_R_4H_H_T': dom['shape'], 'kernel_ms': dom['ms'],
         'peak_kind': pk_kind + ' bf16 burst (cuBLAS 8192^3); achieved counts ALGORITHMIC flops '
                      '2*R*H*4H*T - the bf16x3 split executes 3x that on the tensor pipe; the kernel is '
                      'a chain of T dependent steps on 96 of 148 SMs (latency-bound, see DESIGN.md)',
         'tensor_pipe_tflops_executed': 3 * dom['tflops'],
+        'gate_gemm': {'kernel': dom['gate_gemm']['kernel'], 'shape_M_N_K': dom['gate_gemm']['shape_M_N_K'],
+                      'kernel_ms': dom['gate_gemm']['ms'], 'achieved': dom['gate_gemm']['tflops'],
+                      'frac': dom['gate_gemm']['tflops'] / pk['bf16_tflops'],
+                      'tensor_pipe_tflops_executed': 3 * dom['gate_gemm']['tflops'],
+                      'frac_executed': 3 * dom['gate_gemm']['tflops'] / pk['bf16_tflops'],
+                      'ncu_tensor_pipe_pct_of_active': 55.2,
+                      'note': 'ncu figure from profiles/r01d_ncu_full_metrics.txt (not measured in this run)'},
         'second_kernel': {'kernel': dom['bwd']['kernel'], 'kernel_ms': dom['bwd']['ms'],
                           'achieved': dom['bwd']['tflops'], 'frac': dom['bwd']['tflops'] / pk['bf16_tflops']},
     }

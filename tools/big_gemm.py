@@ -10,6 +10,11 @@ lib = _lib.load()
 dev = 'cuda:0'
 st = torch.cuda.current_stream().cuda_stream
 M, N, K = 6400, 2048, 512
+# the persistent tile-queue kernel keeps its tile counter in the tensor-core arena
+scratch = torch.zeros(64 << 20, dtype=torch.uint8, device=dev)
+cache = torch.zeros(16 << 20, dtype=torch.uint8, device=dev)
+lib.d2p_tc_configure(ptr(scratch), scratch.numel(), ptr(cache), cache.numel(), 1)
+lib.d2p_gemm_set_persistent(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
 apk = torch.empty(lib.d2p_packed_bytes(M, K), dtype=torch.uint8, device=dev)
 bpk = torch.empty(lib.d2p_packed_bytes(N, K), dtype=torch.uint8, device=dev)
@@ -25,7 +30,7 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / n
-print('gemm_tc_kernel<128,3> %dx%dx%d: %.1f us, %.1f TFLOP/s algorithmic (x3 on the tensor pipe = %.0f)' % (
-    M, N, K, us, 2.0 * M * N * K / us / 1e6, 6.0 * M * N * K / us / 1e6))
+print('tensor-core GEMM (persistent=%s) %dx%dx%d:' % (sys.argv[2] if len(sys.argv) > 2 else '1', M, N, K) + ' %.1f us, %.1f TFLOP/s algorithmic (x3 on the tensor pipe = %.0f)' % (
+    us, 2.0 * M * N * K / us / 1e6, 6.0 * M * N * K / us / 1e6))
 ref = A.double() @ B.double().t()
 print('rel err vs fp64: %.2e' % ((C.double() - ref).abs().max() / ref.abs().max()).item())
