@@ -243,7 +243,20 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        # NCCL prints its version banner on the C-level stdout when the communicator is created:
+        # send fd 1 to stderr meanwhile so that rank 0's stdout carries the JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(dev))
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = karel_config('full', batch_size=32, k=10)
     eng = Engine(cfg, device=dev, world_size=world, use_graph=True)
     batch = make_batch(cfg, seed=123 + rank)     # each rank: its own shard
