@@ -122,16 +122,24 @@ gemm_tc_kernel(Packed A, Packed B, int M, int N, int K, float alpha, float beta,
 //   tile queue:   tq_full[4] / tq_empty[4]  (producer -> MMA lane + 4 epilogue warps)
 //   operand ring: full[3] / empty[3]        (bulk copies -> MMA, tcgen05.commit -> producer)
 //   accumulators: acc_full[2] / acc_empty[2] (tcgen05.commit -> epilogue, epilogue -> MMA)
-constexpr int PG_STAGES = 3, PG_BN = 128, PG_NQ = 4, PG_THREADS = 192, PG_HALF = 64;
+// Two shapes: 128 x 128 tiles with a 3 x 64 KB operand ring, and - when N is a multiple of 256 and
+// there are still more tiles than SMs - 128 x 256 tiles with a 2 x 96 KB ring: the three N = 256
+// MMAs of a k16 read 36 KB of shared memory in 384 cycles instead of 24 KB in 204 (shared-memory
+// operand bandwidth is what bounds the 128-wide tile), accumulators fill all 512 TMEM columns.
+constexpr int PG_NQ = 4, PG_THREADS = 192, PG_HALF = 64;
 constexpr int PG_SROW = PG_HALF + 4;
-constexpr uint32_t PG_A_BYTES = (BM / 8) * 2048, PG_B_BYTES = (PG_BN / 8) * 2048;
-constexpr uint32_t PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
-constexpr size_t PG_SMEM = (size_t)PG_STAGES * PG_STAGE_BYTES + (size_t)4 * 32 * PG_SROW * sizeof(float);
+constexpr uint32_t PG_A_BYTES = (BM / 8) * 2048;
+constexpr size_t PG_SMEM = (size_t)3 * 65536 + (size_t)4 * 32 * PG_SROW * sizeof(float);   // same for both shapes
 
+template <int PG_BN, int PG_STAGES>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 gemm_tc_persist_kernel(Packed A, Packed B, int M, int N, int K, float alpha, float beta,
                        float* __restrict__ C, int ldc, const float* __restrict__ bias,
                        unsigned* __restrict__ tile_ctr) {
+    constexpr uint32_t PG_B_BYTES = (PG_BN / 8) * 2048;
+    constexpr uint32_t PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
+    static_assert((size_t)PG_STAGES * PG_STAGE_BYTES == (size_t)3 * 65536, "operand ring is 192 KB");
+    static_assert(2 * PG_BN <= 512, "two accumulators must fit the 512 TMEM columns");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * PG_STAGES + 4 + 2 * PG_NQ];
     __shared__ int tile_ids[PG_NQ];
@@ -247,13 +255,13 @@ gemm_tc_persist_kernel(Packed A, Packed B, int M, int N, int K, float alpha, flo
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int m0 = (tile / ntn) * BM + lq * 32, n0 = (tile % ntn) * PG_BN;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < PG_BN / PG_HALF; ++half) {
                 uint32_t v[32], w[32];
                 const uint32_t ta = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * PG_BN + half * PG_HALF);
                 tmem_ld32(ta, v);
                 tmem_ld32(ta + 32, w);
                 tmem_ld_wait();
-                if (half == 1) {   // accumulator fully read: hand the buffer back to the MMA lane
+                if (half == PG_BN / PG_HALF - 1) {   // accumulator fully read: hand the buffer back to the MMA lane
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce0 + 8 * buf);
@@ -298,7 +306,7 @@ gemm_tc_persist_kernel(Packed A, Packed B, int M, int N, int K, float alpha, flo
                      "r"((uint32_t)(2 * PG_BN)));
 }
 
-int g_persist_gemm = 1;   // d2p_gemm_set_persistent: 0 = always one CTA per tile
+int g_persist_gemm = 1;   // d2p_gemm_set_persistent: 0 = always one CTA per tile, bit 1 = 128 x 256 tiles where they fit
 
 // C = alpha * sum_z partials[z] + beta*C + bias
 __global__ void splitk_reduce_kernel(const float* __restrict__ partials, int ksplit, int M, int N,
@@ -452,18 +460,26 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
     // few wide tiles with a long K: 128-wide tiles split over K fill the SMs with half the MMA
     // instructions of 64-wide tiles (an M = 128 MMA costs ~68 cycles for N = 64 and N = 128 alike)
     const long long tiles128 = (long long)cdiv(N, 128) * cdiv(M, BM);
-    if (!use_part && g_persist_gemm && tiles128 > kNumSMs && N % PG_BN == 0 && ldc % 4 == 0 &&
+    if (!use_part && g_persist_gemm && tiles128 > kNumSMs && N % 128 == 0 && ldc % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
         unsigned* ctr = tc_tile_counter(st);
         if (ctr != nullptr) {
             static bool attr_set = false;
             if (!attr_set) {
-                D2P_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel,
+                D2P_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<128, 3>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG_SMEM));
+                D2P_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<256, 2>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PG_SMEM));
                 attr_set = true;
             }
             D2P_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
-            gemm_tc_persist_kernel<<<kNumSMs, PG_THREADS, PG_SMEM, st>>>(A, B, M, N, K, alpha, beta, C, ldc, bias, ctr);
+            const bool wide = (g_persist_gemm & 2) && N % 256 == 0 && (long long)(N / 256) * cdiv(M, BM) > kNumSMs;
+            if (wide)
+                gemm_tc_persist_kernel<256, 2><<<kNumSMs, PG_THREADS, PG_SMEM, st>>>(A, B, M, N, K, alpha, beta, C,
+                                                                                    ldc, bias, ctr);
+            else
+                gemm_tc_persist_kernel<128, 3><<<kNumSMs, PG_THREADS, PG_SMEM, st>>>(A, B, M, N, K, alpha, beta, C,
+                                                                                    ldc, bias, ctr);
             D2P_CHECK_LAUNCH();
             return 0;
         }

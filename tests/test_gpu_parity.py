@@ -480,3 +480,46 @@ def test_persistent_recurrence_matches_per_step(model, B, k):
     b = _run_variant(cfg, batch, 1, 1)
     assert abs(float(b['loss'][0] - a['loss'][0])) < 2e-5
     assert rel_err(b['grads'], a['grads']) < 1e-4
+
+
+@pytest.mark.parametrize('M,N,K,alpha,beta,bias', [(6400, 2048, 512, 1.0, 0.0, False),    # hoisted LSTM gate GEMM (C2)
+                                                    (2500, 1024, 200, 0.5, 1.0, True),     # ragged M and K, epilogue terms
+                                                    (19000, 128, 48, 1.0, 0.0, True)])     # one tile column, one k-block
+def test_persistent_gemm_matches_fp64_and_per_tile_kernel(lib, M, N, K, alpha, beta, bias):
+    """gemm_tc_persist_kernel (atomic tile queue, double-buffered TMEM accumulator) against a torch
+    fp64 product and against the one-CTA-per-tile kernel (d2p_gemm_set_persistent(0)); fp32-equivalent
+    (bf16x3) floating point: 2e-5 of the largest |C|."""
+    from demo2program_b200._lib import check, ptr
+    dev = 'cuda:0'
+    st = torch.cuda.current_stream().cuda_stream
+    scratch = torch.zeros(64 << 20, dtype=torch.uint8, device=dev)
+    cache = torch.zeros(16 << 20, dtype=torch.uint8, device=dev)
+    lib.d2p_tc_configure(ptr(scratch), scratch.numel(), ptr(cache), cache.numel(), 1)
+    g = torch.Generator(device='cpu').manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    Bt = torch.randn(N, K, generator=g).to(dev)
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    bv = torch.randn(N, generator=g).to(dev) if bias else None
+    apk = torch.zeros(lib.d2p_packed_bytes(M, K), dtype=torch.uint8, device=dev)
+    bpk = torch.zeros(lib.d2p_packed_bytes(N, K), dtype=torch.uint8, device=dev)
+    check(lib.d2p_pack_bf16(ptr(A), M, K, K, 1, ptr(apk), st), 'pack A')
+    check(lib.d2p_pack_bf16(ptr(Bt), N, K, K, 1, ptr(bpk), st), 'pack B')
+    ref = alpha * (A.double() @ Bt.double().t()) + beta * C0.double()
+    if bias:
+        ref = ref + bv.double()
+    out = {}
+    try:
+        for mode in (0, 1):
+            lib.d2p_gemm_set_persistent(mode)
+            C = C0.clone()
+            n0 = lib.d2p_launch_count()
+            check(lib.d2p_gemm_tc_packed(ptr(apk), ptr(bpk), M, N, K, alpha, beta, ptr(C), N, ptr(bv), 1, None, st),
+                  'gemm')
+            torch.cuda.synchronize()
+            out[mode] = C
+            assert float((C.double() - ref).abs().max() / ref.abs().max()) < 2e-5, mode
+    finally:
+        lib.d2p_gemm_set_persistent(1)
+    assert float((out[0] - out[1]).abs().max() / ref.abs().max()) < 2e-5
+    if K <= 64:      # a single k-block: both kernels add the same products in the same order
+        assert torch.equal(out[0], out[1])

@@ -56,11 +56,14 @@ for (M, N, K) in [(6400, 2048, 512), (6400, 512, 2048), (6400, 2048, 48), (3200,
     e0, t0, c0 = run(M, N, K, 0, reps=20)
     e1, t1, c1 = run(M, N, K, 1, reps=20)
     e2, _, _ = run(M, N, K, 1, alpha=0.5, beta=1.0, bias=True)
+    e3, t3, c3 = run(M, N, K, 3, reps=20)                       # 128 x 256 tiles where they fit
+    e4, _, _ = run(M, N, K, 3, alpha=0.5, beta=1.0, bias=True)
     d = (c0 - c1).abs().max().item()
-    flag = '' if max(e1, e2) < 2e-5 else '   <<<< BAD'
+    flag = '' if max(e1, e2, e3, e4) < 2e-5 else '   <<<< BAD'
     bad += bool(flag)
     fl = 2.0 * M * N * K
     print('M%6d N%5d K%5d  per-tile %.2e %6.1f us (%5.1f TF/s) | persistent %.2e %6.1f us (%5.1f TF/s) | beta/bias %.2e | '
-          'max |diff| %.1e%s' % (M, N, K, e0, t0, fl / t0 / 1e6, e1, t1, fl / t1 / 1e6, e2, d, flag))
+          'max |diff| %.1e | wide tiles %.2e / %.2e %6.1f us (%5.1f TF/s)%s' % (
+              M, N, K, e0, t0, fl / t0 / 1e6, e1, t1, fl / t1 / 1e6, e2, d, e3, e4, t3, fl / t3 / 1e6, flag))
 print('GEMM_PERSIST_CHECK', 'OK' if not bad else 'FAILED')
 sys.exit(1 if bad else 0)
