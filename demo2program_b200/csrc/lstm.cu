@@ -167,7 +167,8 @@ extern "C" int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, con
     }
     if (!(phases & D2P_LSTM_BWD_PARAMS)) return 0;
     // parameter gradients from the full dZ
-    D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
+    if (!(phases & D2P_LSTM_BWD_NO_DWX))
+        D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
     if (T > 1)
         D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
     if (h0) D2P_TRY(gemm(st, true, false, H, G4, R, 1.f, h0, H, gates, G4, 1.f, dWh, G4));

@@ -417,13 +417,16 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
         size_t off = 0;
         const void *zpk, *xpk, *ypk;
         D2P_TRY(get_packed(st, gates, G4, T * R, G4, false, false, &off, &zpk));
-        D2P_TRY(get_packed(st, X, In, T * R, In, false, false, &off, &xpk));
-        D2P_TRY(gemm_tc_packed_auto(st, xpk, zpk, In, G4, T * R, 1.f, 1.f, dWx, G4, &off));
+        if (!(phases & D2P_LSTM_BWD_NO_DWX)) {
+            D2P_TRY(get_packed(st, X, In, T * R, In, false, false, &off, &xpk));
+            D2P_TRY(gemm_tc_packed_auto(st, xpk, zpk, In, G4, T * R, 1.f, 1.f, dWx, G4, &off));
+        }
         D2P_TRY(get_packed(st, Y, H, (T - 1) * R, H, false, false, &off, &ypk));
         const uint8_t* zsub = (const uint8_t*)zpk + (size_t)(R / BK) * mgp_of(G4) * 2048;
         D2P_TRY(gemm_tc_packed_auto(st, ypk, zsub, H, G4, (T - 1) * R, 1.f, 1.f, dWh, G4, &off));
     } else {
-        D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
+        if (!(phases & D2P_LSTM_BWD_NO_DWX))
+            D2P_TRY(gemm(st, true, false, In, G4, T * R, 1.f, X, In, gates, G4, 1.f, dWx, G4));
         if (T > 1)
             D2P_TRY(gemm(st, true, false, H, G4, (T - 1) * R, 1.f, Y, H, gates + (size_t)R * G4, G4, 1.f, dWh, G4));
     }

@@ -36,8 +36,13 @@ class Engine:
 
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
                  frames_dtype=np.uint8, flat_params=None, flat_state=None,
-                 world_size=1, use_graph=True, use_tc=True, concurrent=True):
+                 world_size=1, use_graph=True, use_tc=True, concurrent=True, token_tables=True):
         self.lib = _lib.load()
+        # token_tables: the teacher-forced token decoders feed embedding rows, so their input
+        # products have at most V+1 distinct rows: gates = (E*Wx + b)[token] in the forward,
+        # dWx = E^T*S and dE = S*Wx^T from the per-token sums S of dZ in the backward, instead of
+        # [T*R]-row products (same arithmetic, different association; False = row-by-row products)
+        self.token_tables = bool(token_tables)
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
                                 'fallback)')
@@ -223,9 +228,13 @@ class Engine:
                             fc_saved=z(lib.d2p_fc_bn_saved_floats(T * R, H, k)))
             self.per_fc = self._fcbn('Per_Decoder/Per_Encoder/fc2')
             ws = max(ws, lib.d2p_fc_bn_ws_bytes(T * R, H, k))
+        # per-token tables of the token decoders: [rows + 1 (the <s> row = bias), 4H] and dZ sums [rows, 4H]
+        self.prog.update(tab=z(V + 2, 4 * H), tsum=z(V + 1, 4 * H))
+        if cfg.model == 'full':
+            self.act.update(tab=z(A + 2, 4 * H), tsum=z(A + 1, 4 * H))
         ws = max(ws, lib.d2p_adam_ws_bytes(),
-                 lib.d2p_embed_shifted_bwd_ws_bytes(V + 1, H, B, L),
-                 lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, H, R, T))
+                 lib.d2p_embed_shifted_bwd_ws_bytes(V + 1, 4 * H, B, L),
+                 lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, 4 * H, R, T))
         self.ws_bytes = _al(ws, 256)
         self._ws_main = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
         self._ws_side = {}
@@ -263,12 +272,19 @@ class Engine:
                    ptr(self.G(scope + 'bias')), ptr(b['dh0']), ptr(b['dc0']), ptr(self.ws),
                    self.ws_bytes, phases, self._st())
 
-    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX):
+    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, token_fn=None):
         """BPTT recurrence (+ dX) on the current stream; the parameter-gradient products
         (dWx, dWh, db: large, throughput-bound) are handed to the gradient stream so they
-        overlap with the latency-bound recurrences that follow."""
+        overlap with the latency-bound recurrences that follow.  token_fn (token decoders with
+        token_tables): no dX, no [T*R]-row dWx product - token_fn() forms dWx and dE from the
+        per-token sums of dZ, behind the dWh product on the same gradient stream."""
+        nodwx = 4 if token_fn is not None else 0      # D2P_LSTM_BWD_NO_DWX
+        if token_fn is not None:
+            dX = None
         if not self.concurrent:
-            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 3)
+            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 3 | nodwx)
+            if token_fn is not None:
+                token_fn()
             return
         self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, 1)
         ev = torch.cuda.Event()
@@ -276,7 +292,9 @@ class Engine:
         gs = self._next_grad_stream()
         gs.wait_event(ev)
         with torch.cuda.stream(gs):
-            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, None, 2)
+            self._lstm_bwd_call(X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, None, 2 | nodwx)
+            if token_fn is not None:
+                token_fn()
 
     def _next_grad_stream(self):
         """Gradient streams are used round-robin: the weight-gradient work of one LSTM (operand
@@ -298,9 +316,31 @@ class Engine:
         with torch.cuda.stream(gs):
             fn()
 
-    def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc):
+    def _gemm(self, ta, tb, M, N, K, alpha, A, lda, Bm, ldb, beta, Cm, ldc, bias=None):
         self._call('d2p_gemm', int(ta), int(tb), M, N, K, alpha, ptr(A), lda, ptr(Bm), ldb, beta,
-                   ptr(Cm), ldc, None, self._st())
+                   ptr(Cm), ldc, ptr(bias), self._st())
+
+    def _token_gates(self, emb_name, scope, rows, tokens, Rn, Tn, b):
+        """Hoisted input product of a teacher-forced token decoder without the [T*R]-row GEMM:
+        tab[v] = E[v]*Wx + bias for the `rows` embedding rows, tab[rows] = bias (the out-of-range
+        <s> id embeds to zeros), gates[t, r] = tab[id(t, r)]."""
+        H = self.H
+        E, W, bias = self.P(emb_name), self.P(scope + 'kernel'), self.P(scope + 'bias')
+        self._gemm(0, 0, rows, 4 * H, H, 1.0, E, H, W, 4 * H, 0.0, b['tab'], 4 * H, bias=bias)
+        self._call('d2p_axpby', ptr(bias), 1.0, ptr(b['tab'][rows]), 0.0, 4 * H, self._st())
+        self._call('d2p_embed_shifted', ptr(b['tab']), rows + 1, 4 * H, ptr(tokens), Rn, Tn, rows,
+                   ptr(b['gates']), self._st())
+
+    def _token_grads(self, emb_name, scope, rows, tokens, Rn, Tn, b):
+        """Backward of _token_gates from the dZ left in b['gates']: S[v] = sum of the dZ rows that
+        were fed token v (fixed order), dE += S*Wx^T, dWx += E^T*S."""
+        H = self.H
+        E, W = self.P(emb_name), self.P(scope + 'kernel')
+        b['tsum'].zero_()
+        self._call('d2p_embed_shifted_bwd', ptr(b['gates']), rows, 4 * H, ptr(tokens), Rn, Tn, rows,
+                   ptr(b['tsum']), ptr(self.ws), self.ws_bytes, self._st())
+        self._gemm(0, 1, rows, H, 4 * H, 1.0, b['tsum'], 4 * H, W, 4 * H, 1.0, self.G(emb_name), H)
+        self._gemm(1, 0, H, 4 * H, rows, 1.0, E, H, b['tsum'], 4 * H, 1.0, self.G(scope + 'kernel'), 4 * H)
 
     # ------------------------------------------------------------------ inputs
     def stage_batch(self, batch):
@@ -373,6 +413,11 @@ class Engine:
         p = self.prog
 
         def prog_in():
+            if self.token_tables:
+                self._token_gates('Program_Decoder/Token_Embedding/embedding_map',
+                                  'Program_Decoder/dynamic_decoder/basic_lstm_cell/', V + 1,
+                                  self.d_prog_tok, B, L, p)
+                return
             call('d2p_embed_shifted', ptr(self.P('Program_Decoder/Token_Embedding/embedding_map')),
                  V + 1, H, ptr(self.d_prog_tok), B, L, V + 1, ptr(p['X']), S())
             self._lstm_fwd(p['X'], L, B, H, self.d_prog_len, None, None,
@@ -380,6 +425,11 @@ class Engine:
 
         def act_in():
             a = self.act
+            if self.token_tables:
+                self._token_gates('Action_Decoder/Token_Embedding/embedding_map',
+                                  'Action_Decoder/dynamic_decoder/basic_lstm_cell/', cfg.action_space + 1,
+                                  self.d_act_tok, R, T, a)
+                return
             call('d2p_embed_shifted', ptr(self.P('Action_Decoder/Token_Embedding/embedding_map')),
                  cfg.action_space + 1, H, ptr(self.d_act_tok), R, T, cfg.action_space + 1, ptr(a['X']), S())
             self._lstm_fwd(a['X'], T, R, H, self.d_demo_len, None, None,
@@ -536,13 +586,21 @@ class Engine:
                 1, 0, H, V, L * B, 1.0, p['y'], H, p['dlogits'], V, 1.0,
                 self.G('Program_Decoder/dynamic_decoder/output_projection/kernel'), V))
             self._gemm(0, 1, L * B, H, V, 1.0, p['dlogits'], V, Wp, V, 0.0, p['dy'], H)
-            self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
-                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
-                           p['dX'])
-            self._deferred(lambda: call(
-                'd2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
-                ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-                self.ws_bytes, S()))
+            if self.token_tables:
+                self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                               'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
+                               None, token_fn=lambda: self._token_grads(
+                                   'Program_Decoder/Token_Embedding/embedding_map',
+                                   'Program_Decoder/dynamic_decoder/basic_lstm_cell/', V + 1,
+                                   self.d_prog_tok, B, L, p))
+            else:
+                self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                               'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
+                               p['dX'])
+                self._deferred(lambda: call(
+                    'd2p_embed_shifted_bwd', ptr(p['dX']), V + 1, H, ptr(self.d_prog_tok), B, L, V + 1,
+                    ptr(self.G('Program_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                    self.ws_bytes, S()))
             # p['dh0'], p['dc0'] = grad wrt (demo_h_summary, demo_c_summary)
             self._stamp('program decoder bwd done')
 
@@ -571,13 +629,21 @@ class Engine:
                     1, 0, H, A, T * R, 1.0, a['y'], H, a['dlogits'], A, 1.0,
                     self.G('Action_Decoder/dynamic_decoder/output_projection/kernel'), A))
                 self._gemm(0, 1, T * R, H, A, 1.0, a['dlogits'], A, Wa, A, 0.0, a['dy'], H)
-                self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                               'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
-                               a['dX'])
-                self._deferred(lambda: call(
-                    'd2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
-                    ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
-                    self.ws_bytes, S()))
+                if self.token_tables:
+                    self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                                   'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
+                                   None, token_fn=lambda: self._token_grads(
+                                       'Action_Decoder/Token_Embedding/embedding_map',
+                                       'Action_Decoder/dynamic_decoder/basic_lstm_cell/', A + 1,
+                                       self.d_act_tok, R, T, a))
+                else:
+                    self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                                   'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,
+                                   a['dX'])
+                    self._deferred(lambda: call(
+                        'd2p_embed_shifted_bwd', ptr(a['dX']), A + 1, H, ptr(self.d_act_tok), R, T, A + 1,
+                        ptr(self.G('Action_Decoder/Token_Embedding/embedding_map')), ptr(self.ws),
+                        self.ws_bytes, S()))
                 self._stamp('action decoder bwd done')
 
             def per_bwd():

@@ -93,7 +93,12 @@ int d2p_conv_set_fused(int mode);
 enum { D2P_LSTM_INPUT = 1,      /* gates = X*Wx + b for all steps (independent of h0/c0) */
        D2P_LSTM_RECUR = 2,      /* the recurrence over T steps */
        D2P_LSTM_BWD_RECUR = 1,  /* BPTT recurrence + dX, dh0, dc0 */
-       D2P_LSTM_BWD_PARAMS = 2  /* dW, db from the dZ left in `gates` by the recurrence phase */ };
+       D2P_LSTM_BWD_PARAMS = 2, /* dW, db from the dZ left in `gates` by the recurrence phase */
+       D2P_LSTM_BWD_NO_DWX = 4  /* with BWD_PARAMS: leave the input-weight rows dW[0:In] alone (X is not read).
+                                 * For a teacher-forced token decoder (X = embedding rows, reference
+                                 * models/model_full.py:440-471) the caller forms dWx = E^T * S and
+                                 * dE = S * Wx^T from the per-token sums S[v] = sum of dZ rows fed token v
+                                 * (d2p_embed_shifted_bwd on dZ): a [V+1]-row product instead of a [T*R]-row one */ };
 /* `phases` selects which parts run (3 = all); the parts may be issued on different
  * streams as long as the stream order of the data dependencies is kept. */
 int d2p_lstm_seq_fwd(const float* X, int T, int R, int In, int H, const int* len, const float* h0,

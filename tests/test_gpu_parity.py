@@ -523,3 +523,36 @@ def test_persistent_gemm_matches_fp64_and_per_tile_kernel(lib, M, N, K, alpha, b
     assert float((out[0] - out[1]).abs().max() / ref.abs().max()) < 2e-5
     if K <= 64:      # a single k-block: both kernels add the same products in the same order
         assert torch.equal(out[0], out[1])
+
+
+@pytest.mark.parametrize('model,B,k,use_graph', [('full', 32, 10, True), ('full', 4, 3, False),
+                                                 ('synthesis_baseline', 8, 2, False)])
+def test_token_table_decoders_match_row_products(model, B, k, use_graph):
+    """Teacher-forced token decoders (reference models/model_full.py:440-471: embedding_lookup ->
+    BasicLSTMCell): gates = (E*Wx + b)[token] and dWx / dE from the per-token sums of dZ
+    (Engine(token_tables=True), the default) against the row-by-row products X*Wx, X^T*dZ, dZ*Wx^T
+    followed by the embedding scatter: same loss, same gradients up to summation order."""
+    from demo2program_b200.engine import Engine
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config(model, batch_size=B, k=k)
+    batch = make_batch(cfg, seed=17)
+    res = {}
+    for tt in (False, True):
+        eng = Engine(cfg, use_graph=use_graph, token_tables=tt)
+        if use_graph:
+            eng.stage_batch(batch)
+            eng.train_step_device(False)       # captured forward + backward, no optimizer
+            eng.train_step_device(False)       # replay
+        else:
+            eng.stage_batch(batch)
+            eng.forward()
+            eng.backward()
+        torch.cuda.synchronize()
+        eng.check_device()
+        res[tt] = (eng.loss.cpu().numpy().copy(), eng.grads.cpu().numpy().copy(), eng.pm)
+    (l0, g0, pm), (l1, g1, _) = res[False], res[True]
+    assert np.abs(l0 - l1).max() < 2e-6
+    gmax = np.abs(g0).max()
+    for e in pm:
+        a, b = g0[e.offset:e.offset + e.size], g1[e.offset:e.offset + e.size]
+        assert np.abs(a - b).max() < 2e-5 * np.abs(a).max() + 1e-7 * gmax, e.name
