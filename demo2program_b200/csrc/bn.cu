@@ -241,6 +241,19 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__
     }
 }
 
+// one slice, no row permutation, C % 4 == 0, 16-byte aligned: float4, 32-bit index math
+__global__ void bn_apply_v4_kernel(const float4* __restrict__ X, float4* __restrict__ Y, unsigned total4,
+                                   unsigned C4, const float* __restrict__ scale,
+                                   const float* __restrict__ shift) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += gridDim.x * blockDim.x) {
+        const unsigned c = (idx % C4) * 4;
+        const float4 x = X[idx];
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+        const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+        Y[idx] = make_float4(x.x * sc.x + sh.x, x.y * sc.y + sh.y, x.z * sc.z + sh.z, x.w * sc.w + sh.w);
+    }
+}
+
 // da = gamma*rstd*(dy - k1 - xhat*k2); if ACT: dz = da * lrelu'(a) (a = post-activation
 // value that was normalised).  DY may be row-permuted like bn_apply's output.
 template <bool ACT>
@@ -395,8 +408,15 @@ int bn_apply(cudaStream_t st, const float* X, float* Y, long long rows, int C, i
              const float* stats, int permT, int permR) {
     const float* scale = stats + 2 * (size_t)nsl * C;
     const float* shift = stats + 3 * (size_t)nsl * C;
-    bn_apply_kernel<<<ew_blocks(rows * C), 256, 0, st>>>(X, Y, rows, C, seg, nsl, scale, shift,
-                                                        permT, permR);
+    if (nsl == 1 && permT <= 0 && C % 4 == 0 && rows * C < (1LL << 31) &&
+        ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(scale) |
+          reinterpret_cast<uintptr_t>(shift)) & 15) == 0)
+        bn_apply_v4_kernel<<<ew_blocks(rows * C / 4), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y), (unsigned)(rows * C / 4),
+            (unsigned)(C / 4), scale, shift);
+    else
+        bn_apply_kernel<<<ew_blocks(rows * C), 256, 0, st>>>(X, Y, rows, C, seg, nsl, scale, shift,
+                                                            permT, permR);
     D2P_CHECK_LAUNCH();
     return 0;
 }

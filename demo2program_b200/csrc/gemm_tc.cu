@@ -383,6 +383,32 @@ __global__ void pack_bf16_kernel(const float* __restrict__ S, int MN, int K, int
     }
 }
 
+// float4 form (N, ldc multiples of 4, 16-byte aligned pointers, M*N < 2^31): 32-bit index math only
+__global__ void splitk_reduce_v4_kernel(const float4* __restrict__ partials, int ksplit, int M, int N4,
+                                        float alpha, float beta, float* __restrict__ C, int ldc,
+                                        const float* __restrict__ bias) {
+    const unsigned total = (unsigned)M * (unsigned)N4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned m = idx / (unsigned)N4, n4 = idx - m * (unsigned)N4;
+        float4 s = partials[idx];
+        for (int z = 1; z < ksplit; ++z) {          // fixed order z = 0, 1, ...
+            const float4 p = partials[(size_t)z * total + idx];
+            s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+        }
+        float4 r = make_float4(alpha * s.x, alpha * s.y, alpha * s.z, alpha * s.w);
+        if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + 4 * n4);
+            r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+        }
+        float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + 4 * n4);
+        if (beta != 0.f) {
+            const float4 o = *c;
+            r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w;
+        }
+        *c = r;
+    }
+}
+
 // returns the number of k-splits launched (>= 1) or a negative status
 template <int BN, int STAGES>
 int launch_tc(cudaStream_t st, Packed A, Packed B, int M, int N, int K, float alpha, float beta,
@@ -495,9 +521,18 @@ int gemm_tc_packed(cudaStream_t st, const void* Apk, const void* Bpk, int M, int
     if (zs < 0) return zs;
     if (use_part && C != nullptr) {
         size_t total = (size_t)M * N;
-        size_t b = (total + 255) / 256, cap = 8 * (size_t)kNumSMs;
-        splitk_reduce_kernel<<<(int)(b < cap ? b : cap), 256, 0, st>>>(partials, zs, M, N, alpha, beta,
-                                                                      C, ldc, bias);
+        const bool v4 = N % 4 == 0 && ldc % 4 == 0 && total < ((size_t)1 << 31) &&
+                        ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(partials) |
+                          reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+        if (v4) {
+            size_t b = (total / 4 + 255) / 256, cap = 8 * (size_t)kNumSMs;
+            splitk_reduce_v4_kernel<<<(int)(b < cap ? b : cap), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(partials), zs, M, N / 4, alpha, beta, C, ldc, bias);
+        } else {
+            size_t b = (total + 255) / 256, cap = 8 * (size_t)kNumSMs;
+            splitk_reduce_kernel<<<(int)(b < cap ? b : cap), 256, 0, st>>>(partials, zs, M, N, alpha, beta,
+                                                                          C, ldc, bias);
+        }
         D2P_CHECK_LAUNCH();
     }
     return 0;

@@ -35,6 +35,21 @@ __global__ void pair_add_lrelu(const float* __restrict__ P, const float* __restr
     }
 }
 
+// float4 form of pair_add_lrelu (H % 4 == 0, fewer than 2^31 elements): 32-bit index math
+__global__ void pair_add_lrelu_v4(const float4* __restrict__ P, const float4* __restrict__ Q,
+                                  const float4* __restrict__ bias, unsigned B, unsigned k, unsigned H4,
+                                  float4* __restrict__ A) {
+    const unsigned total = B * k * k * H4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned row = idx / H4, u = idx - row * H4;
+        const unsigned bi = row / k, j = row - bi * k;      // bi = b*k + i
+        const unsigned b = bi / k;
+        const float4 p = P[(b * k + j) * H4 + u], q = Q[bi * H4 + u], c = bias[u];
+        A[idx] = make_float4(lrelu_f(p.x + q.x + c.x), lrelu_f(p.y + q.y + c.y), lrelu_f(p.z + q.z + c.z),
+                             lrelu_f(p.w + q.w + c.w));
+    }
+}
+
 __global__ void lrelu_inplace(float* __restrict__ x, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x)
@@ -128,7 +143,15 @@ extern "C" int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc
     float* X2 = (float*)(w + p.a);
     D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w, H, 0.f, P, H, nullptr, GEMM_CONST_B));
     D2P_TRY(gemm(st, false, false, Bk, H, H, 1.f, F, H, fc1->w + (size_t)H * H, H, 0.f, Q, H, nullptr, GEMM_CONST_B));
-    pair_add_lrelu<<<ewb(rows * H), 256, 0, st>>>(P, Q, fc1->b, B, k, H, A1);
+    if (H % 4 == 0 && rows * H < (1LL << 31) &&
+        ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(fc1->b) |
+          reinterpret_cast<uintptr_t>(A1)) & 15) == 0)
+        pair_add_lrelu_v4<<<ewb(rows * H / 4), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(P), reinterpret_cast<const float4*>(Q),
+            reinterpret_cast<const float4*>(fc1->b), (unsigned)B, (unsigned)k, (unsigned)(H / 4),
+            reinterpret_cast<float4*>(A1));
+    else
+        pair_add_lrelu<<<ewb(rows * H), 256, 0, st>>>(P, Q, fc1->b, B, k, H, A1);
     D2P_CHECK_LAUNCH();
     D2P_TRY(bn_forward_stats(st, A1, rows, H, 1, 1, fc1->gamma, fc1->beta, fc1->moving_mean,
                              fc1->moving_var, training, st1, w + p.part, p.part_bytes));
