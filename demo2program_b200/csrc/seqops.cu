@@ -30,6 +30,19 @@ __global__ void gather_shifted_kernel(const float* __restrict__ table, int vocab
     }
 }
 
+// float4 form (E % 4 == 0, 16-byte aligned, fewer than 2^31 elements): 32-bit index math
+__global__ void gather_shifted_v4_kernel(const float4* __restrict__ table, int vocab_rows, unsigned E4,
+                                         const int* __restrict__ tokens, unsigned R, unsigned L, int start_id,
+                                         float4* __restrict__ X) {
+    const unsigned total = L * R * E4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned tr = idx / E4, e = idx - tr * E4;
+        const unsigned t = tr / R, r = tr - t * R;
+        const int id = t == 0 ? start_id : tokens[(size_t)r * L + t - 1];
+        X[idx] = (id >= 0 && id < vocab_rows) ? table[(size_t)id * E4 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // dTable[v, e] += sum_{(t,r): id(t,r) == v} dX[t,r,e], two-stage and in a fixed
 // order (deterministic): stage 1 reduces a chunk of positions per block into
 // partial[chunk, v, e]; stage 2 sums the chunks.
@@ -244,15 +257,22 @@ using namespace d2p;
 extern "C" int d2p_embed_shifted(const float* table, int vocab_rows, int E, const int* tokens,
                                  int R, int L, int start_id, float* X, void* stream) {
     D2P_REQUIRE(table && tokens && X && R > 0 && L > 0 && E > 0, "embed: bad arguments");
-    gather_shifted_kernel<<<ew_blocks((size_t)L * R * E), 256, 0, (cudaStream_t)stream>>>(
-        table, vocab_rows, E, tokens, R, L, start_id, X);
+    if (E % 4 == 0 && (size_t)L * R * E < ((size_t)1 << 31) &&
+        ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(X)) & 15) == 0)
+        gather_shifted_v4_kernel<<<ew_blocks((size_t)L * R * E / 4), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(table), vocab_rows, (unsigned)(E / 4), tokens, (unsigned)R,
+            (unsigned)L, start_id, reinterpret_cast<float4*>(X));
+    else
+        gather_shifted_kernel<<<ew_blocks((size_t)L * R * E), 256, 0, (cudaStream_t)stream>>>(
+            table, vocab_rows, E, tokens, R, L, start_id, X);
     D2P_CHECK_LAUNCH();
     return 0;
 }
 
 static int embed_chunks(int R, int L, int* ppc) {
     int pos = R * L;
-    int n = pos < 64 ? 1 : (pos / 64 < 64 ? pos / 64 : 64);
+    // ~32 positions per chunk (each thread walks its chunk serially), at most 256 chunks
+    int n = pos < 64 ? 1 : (pos / 32 < 256 ? pos / 32 : 256);
     *ppc = (pos + n - 1) / n;
     return (pos + *ppc - 1) / *ppc;
 }
