@@ -338,11 +338,12 @@ __global__ void permute_rows_kernel(const float* __restrict__ X, float* __restri
 }
 
 inline int pick_chunks(long long rows_per_slice, int nsl, int* rows_per_chunk) {
-    // aim for ~4 waves of blocks overall, at least 64 rows per block
+    // aim for ~4 waves of blocks overall, at least 16 rows per block (a 3200-row activation of the
+    // summary pools was 50 blocks on 148 SMs with 64: latency-bound on a third of the GPU)
     long long target_blocks = 4LL * kNumSMs / (nsl > 0 ? nsl : 1);
     if (target_blocks < 1) target_blocks = 1;
     long long rpc = (rows_per_slice + target_blocks - 1) / target_blocks;
-    if (rpc < 64) rpc = 64;
+    if (rpc < 16) rpc = 16;
     *rows_per_chunk = (int)rpc;
     return (int)((rows_per_slice + rpc - 1) / rpc);
 }
