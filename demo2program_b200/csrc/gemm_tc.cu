@@ -447,7 +447,7 @@ int auto_ksplit(int M, int N, int K) {
     int nk = cdiv(K, BK);
     if (tiles64 > 48 || nk < 8) return 1;
     long long s = 144 / tiles64;
-    if (s > nk / 4) s = nk / 4;
+    if (s > nk / 8) s = nk / 8;   // at least 8 k-blocks per split: below that the reduction pass costs more than it saves
     if (s > 8) s = 8;
     return s < 1 ? 1 : (int)s;
 }
