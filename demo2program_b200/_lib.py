@@ -94,6 +94,7 @@ SIGNATURES = {
     'd2p_group_sum': (_i, [_fp, _i, _i, _i, _f, _fp, _i, _fp]),
     'd2p_group_bcast': (_i, [_fp, _i, _i, _i, _f, _fp, _i, _fp]),
     'd2p_axpby': (_i, [_fp, _f, _fp, _f, _sz, _fp]),
+    'd2p_add3': (_i, [_fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_logits_to_bvl': (_i, [_fp, _i, _i, _i, _fp, _fp]),
     'd2p_rtp_to_trp': (_i, [_fp, _i, _i, _i, _fp, _fp]),
     'd2p_len_to_int': (_i, [_fp, _fp, _i, _fp]),

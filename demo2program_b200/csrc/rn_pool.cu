@@ -68,6 +68,22 @@ __global__ void pooled_mean(const float* __restrict__ A, int B, int kk, int H,
     pooled[idx] = scale[u] * (a / (float)kk) + shift[u];
 }
 
+// the same with the kk rows of a batch element split over 4 thread rows (fixed-order combine):
+// grid (B, H / 128), block (128, 4)
+__global__ void pooled_mean_v2(const float* __restrict__ A, int kk, int H, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float* __restrict__ pooled) {
+    __shared__ float part[4][128];
+    const int b = blockIdx.x, u = blockIdx.y * 128 + threadIdx.x, y = threadIdx.y;
+    float a = 0.f;
+    for (int q = y; q < kk; q += 4) a += A[((size_t)b * kk + q) * H + u];
+    part[y][threadIdx.x] = a;
+    __syncthreads();
+    if (y == 0) {
+        const float s = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
+        pooled[(size_t)b * H + u] = scale[u] * (s / (float)kk) + shift[u];
+    }
+}
+
 __global__ void bcast_pairs(const float* __restrict__ dpooled, int B, int kk, int H,
                             float* __restrict__ dY) {
     size_t total = (size_t)B * kk * H;
@@ -161,7 +177,10 @@ extern "C" int d2p_rn_pool_fwd(const float* F, int B, int k, int H, const d2p_fc
     D2P_CHECK_LAUNCH();
     D2P_TRY(bn_forward_stats(st, A2, rows, H, 1, 1, fc2->gamma, fc2->beta, fc2->moving_mean,
                              fc2->moving_var, training, st2, w + p.part, p.part_bytes));
-    pooled_mean<<<cdiv((long long)B * H, 256), 256, 0, st>>>(A2, B, kk, H, st2 + 2 * H, st2 + 3 * H, pooled);
+    if (H % 128 == 0)
+        pooled_mean_v2<<<dim3(B, H / 128), dim3(128, 4), 0, st>>>(A2, kk, H, st2 + 2 * H, st2 + 3 * H, pooled);
+    else
+        pooled_mean<<<cdiv((long long)B * H, 256), 256, 0, st>>>(A2, B, kk, H, st2 + 2 * H, st2 + 3 * H, pooled);
     D2P_CHECK_LAUNCH();
     return 0;
 }

@@ -362,6 +362,23 @@ extern "C" int d2p_axpby(const float* x, float alpha, float* y, float beta, size
     return 0;
 }
 
+namespace d2p { namespace {
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                            const float* __restrict__ c, float* __restrict__ y, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = (a[i] + b[i]) + c[i];
+}
+} }
+
+// y = (a + b) + c  (one pass instead of three axpby launches; same association as the chain it replaces)
+extern "C" int d2p_add3(const float* a, const float* b, const float* c, float* y, size_t n, void* stream) {
+    D2P_REQUIRE(a && b && c && y, "add3: null buffer");
+    if (n == 0) return 0;
+    d2p::add3_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, c, y, n);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int d2p_logits_to_bvl(const float* X, int T, int R, int V, float* Y, void* stream) {
     D2P_REQUIRE(X && Y, "logits_to_bvl: null buffer");
     logits_to_bvl_kernel<<<ew_blocks((size_t)T * R * V), 256, 0, (cudaStream_t)stream>>>(X, T, R, V, Y);

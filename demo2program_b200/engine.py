@@ -413,6 +413,10 @@ class Engine:
         p = self.prog
 
         def prog_in():
+            # the gradient buffer is cleared here, on a side stream under the encoder recurrence, instead
+            # of at the head of the backward pass (this branch is joined before the program decoder runs)
+            self.grads.zero_()
+            self._grads_zeroed = True
             if self.token_tables:
                 self._token_gates('Program_Decoder/Token_Embedding/embedding_map',
                                   'Program_Decoder/dynamic_decoder/basic_lstm_cell/', V + 1,
@@ -575,7 +579,9 @@ class Engine:
         tr = int(self.is_train)
         call, S = self._call, self._st
         fin = self.fin
-        self.grads.zero_()
+        if not getattr(self, '_grads_zeroed', False):
+            self.grads.zero_()
+        self._grads_zeroed = False
         self._grad_rr = 0
         p = self.prog
         self._stamp('bwd start')
@@ -680,12 +686,8 @@ class Engine:
                 self._fwd_open = False
             self._stamp('decoders + pools bwd joined')
             # dh2 = d(action init) + d(per init) + d(pools)
-            call('d2p_axpby', ptr(a['dh0']), 1.0, ptr(self.dh2), 0.0, R * H, S())
-            call('d2p_axpby', ptr(q['dh0']), 1.0, ptr(self.dh2), 1.0, R * H, S())
-            call('d2p_axpby', ptr(self.pool_dh), 1.0, ptr(self.dh2), 1.0, R * H, S())
-            call('d2p_axpby', ptr(a['dc0']), 1.0, ptr(self.dc2), 0.0, R * H, S())
-            call('d2p_axpby', ptr(q['dc0']), 1.0, ptr(self.dc2), 1.0, R * H, S())
-            call('d2p_axpby', ptr(self.pool_dc), 1.0, ptr(self.dc2), 1.0, R * H, S())
+            call('d2p_add3', ptr(a['dh0']), ptr(q['dh0']), ptr(self.pool_dh), ptr(self.dh2), R * H, S())
+            call('d2p_add3', ptr(a['dc0']), ptr(q['dc0']), ptr(self.pool_dc), ptr(self.dc2), R * H, S())
         else:
             prog_bwd()
             if self.model == 'summarizer':

@@ -245,6 +245,10 @@ int d2p_group_sum(const float* F, int B, int k, int H, float alpha, float* out, 
 int d2p_group_bcast(const float* S, int B, int k, int H, float alpha, float* out, int accumulate,
                     void* stream);
 int d2p_axpby(const float* x, float alpha, float* y, float beta, size_t n, void* stream);
+/* y = (a + b) + c: the sum of the three gradient contributions to the per-demonstration summary state
+ * (action decoder, perception decoder, summary pools; reference models/model_full.py:918-1079 adds the three
+ * losses, so the state's gradient is the sum of the three branches) in one pass. */
+int d2p_add3(const float* a, const float* b, const float* c, float* y, size_t n, void* stream);
 /* layout helpers at the facade boundary */
 int d2p_logits_to_bvl(const float* X, int T, int R, int V, float* Y, void* stream);
 int d2p_rtp_to_trp(const float* X, int R, int T, int P, float* Y, void* stream);
