@@ -68,6 +68,29 @@ class SyntheticDataset(object):
                 sq('per'), sq('test_per'))
 
 
+def _action_one_hots(a, T, A):
+    """The reference's per-demonstration loop (karel_env/dataset_karel.py:66-77,
+    vizdoom_env/dataset_vizdoom.py:86-99) for all demonstrations at once: row i of the stored
+    (per-program zero-padded) action matrix `a` gives h[i, t, a[i, t]] = 1 for every stored column t,
+    then the end token h[i, len(row), A] = 1; tokens = argmax.  Like the loop, it raises IndexError
+    when the stored rows are already T long."""
+    a = np.asarray(a)
+    if a.ndim != 2:                      # ragged / empty input: keep the row-by-row form
+        hist = []
+        for t in a:
+            h = np.zeros([T, A + 1], dtype=bool)
+            h[np.arange(len(t)), t] = 1
+            h[len(t), A] = 1
+            hist.append(h)
+        hist = np.stack(hist, 0)
+        return hist, np.argmax(hist, axis=2)
+    n, m = a.shape
+    hist = np.zeros([n, T, A + 1], dtype=bool)
+    hist[np.arange(n)[:, None], np.arange(m)[None, :], a] = 1
+    hist[:, m, A] = 1
+    return hist, np.argmax(hist, axis=2)
+
+
 class H5Dataset(object):
     """reference karel_env/dataset_karel.py:14-115 over h5py (lazy import)."""
 
@@ -105,14 +128,7 @@ class H5Dataset(object):
             return out
 
         def actions(a):   # quirk F10: one-hots from the per-program zero-padded matrix
-            hist = []
-            for t in a:
-                h = np.zeros([T, A + 1], dtype=bool)
-                h[np.arange(len(t)), t] = 1
-                h[len(t), A] = 1
-                hist.append(h)
-            hist = np.stack(hist, 0)
-            return hist, np.argmax(hist, axis=2)
+            return _action_one_hots(a, T, A)
 
         demo, tdemo = pad_demo(d['s_h'][()]), pad_demo(d['test_s_h'][()])
         ah, aht = actions(d['a_h'][()])
@@ -171,14 +187,7 @@ class H5DatasetVizdoom(object):
             return out
 
         def actions(a):
-            hist = []
-            for t in a:
-                h = np.zeros([T, A + 1], dtype=bool)
-                h[np.arange(len(t)), t] = 1
-                h[len(t), A] = 1
-                hist.append(h)
-            hist = np.stack(hist, 0)
-            return hist, np.argmax(hist, axis=2)
+            return _action_one_hots(a, T, A)
 
         def pad_pos(x):
             out = np.zeros([x.shape[0], x.shape[1], self.vizdoom_max_init_pos_len, 2], dtype=x.dtype)
@@ -274,7 +283,8 @@ def collate(dataset, ids):
     for j, key in enumerate(keys):
         arr = np.stack([c[j] for c in cols])
         if key in ('s_h', 'test_s_h'):
-            arr = arr.astype(np.uint8)
+            # the stored bool frames ARE the u8 frames (0/1 bytes): reinterpret, do not copy
+            arr = arr.view(np.uint8) if arr.dtype == np.bool_ else arr.astype(np.uint8)
         elif key.endswith('_tokens'):
             arr = arr.astype(np.int32)
         else:

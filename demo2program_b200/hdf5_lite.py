@@ -100,7 +100,10 @@ class Dataset(object):
 
     @property
     def size(self):
-        return int(np.prod(self.shape, dtype=np.int64))
+        n = 1
+        for d in self.shape:
+            n *= int(d)
+        return n
 
     def _raw(self):
         buf, lo, dt = self._f._buf, self._layout, self._dt.dtype
