@@ -235,3 +235,28 @@ def test_karel_loader_matches_reference_loader_golden(tmp_path):
                 assert _digest(a) == w['sha256'], (ex_id, j)
             n += 1
     assert n == 17
+
+
+def test_action_one_hots_equal_the_reference_loop():
+    """dataset._action_one_hots (vectorised) against the per-demonstration loop of
+    karel_env/dataset_karel.py:66-77, incl. quirk F10 (the end token sits behind the zero PADDED
+    row, padding zeros count as action 0) and the IndexError when the stored rows are T long."""
+    import pytest
+    from demo2program_b200.dataset import _action_one_hots
+    rs = np.random.RandomState(3)
+    T, A = 20, 5
+    for n, m in [(10, 7), (1, 1), (5, 19), (3, 0)]:
+        a = rs.randint(0, A, size=(n, m)).astype(np.int64)
+        a[:, m // 2:] *= rs.randint(0, 2, size=(n, m - m // 2))       # zero padding inside the rows
+        hist = []
+        for t in a:
+            h = np.zeros([T, A + 1], dtype=bool)
+            h[np.arange(len(t)), t] = 1
+            h[len(t), A] = 1
+            hist.append(h)
+        ref = np.stack(hist, 0)
+        got, tok = _action_one_hots(a, T, A)
+        assert got.dtype == np.bool_ and np.array_equal(got, ref)
+        assert np.array_equal(tok, np.argmax(ref, axis=2))
+    with pytest.raises(IndexError):
+        _action_one_hots(np.zeros((2, T), np.int64), T, A)
