@@ -348,6 +348,10 @@ def run_ours(args):
         cpu = {'value': ctoks / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': '2 full train steps of %s (1 warm-up), oracle restatement of the TF1 graph, '
                          'torch CPU fp32' % WORKLOAD, 'ms_per_step': sec * 1e3}
+        # also a single-thread figure (one step, no warm-up: ~15 s)
+        sec1, _, _ = cpu_reference_step_time(cfg, 1, 0, threads=1)
+        cpu['one_thread'] = {'value': ctoks / sec1, 'unit': UNIT, 'cores': 1, 'ms_per_step': sec1 * 1e3,
+                             'sample': '1 full train step, no warm-up'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
