@@ -69,3 +69,10 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_lib.D2PError):
         _lib.load()
+
+
+def test_integration_md_lists_every_entry_point():
+    """INTEGRATION.md section 6 is the map from each C-ABI entry point to the reference site it replaces."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = [f for f in _header_functions() if f not in doc]
+    assert not missing, missing
