@@ -231,6 +231,109 @@ def time_dominant_kernel(eng, iters=20):
                     'ms': tb, 'tflops': flops / (tb * 1e-3) / 1e12}}
 
 
+def _event_ms(fn, iters, warmup=2, flush=None):
+    """Mean CUDA-event time of fn() on the current stream, L2 flushed before each timed call."""
+    import torch
+    st = torch.cuda.current_stream()
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        fn()
+        e1.record(st)
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def secondary_configs(flush, pk):
+    """The other BASELINE.json configs on their shipped default paths, a few device-timed steps each
+    (rank 0, N=1): C1 Karel synthesis_baseline k=2 B=8 train step, C4 ViZDoom full k=10 B=32 train
+    step, C5 Karel induction_baseline B=512 encode + greedy decode (default exact=None path: tensor
+    cores + arg-max margin guard).  Algorithmic work per SURVEY 8(d) / Appendix C."""
+    import torch
+    from demo2program_b200.config import karel_config, vizdoom_config
+    from demo2program_b200.engine import Engine
+    from demo2program_b200.synthetic import make_batch, make_vizdoom_batch, program_tokens_in_batch
+    out = {}
+
+    def train_cfg(name, cfg, batch, iters, extra):
+        try:
+            eng = Engine(cfg, use_graph=True)
+            eng.stage_batch(batch)
+            ms = _event_ms(lambda: eng.train_step_device(True), iters, warmup=3, flush=flush)
+            eng.check_device()
+            toks = program_tokens_in_batch(batch)
+            d = {'ms_per_step': ms, 'program_tokens_per_s': toks / (ms * 1e-3),
+                 'instances_per_s': cfg.batch_size / (ms * 1e-3), 'steps': iters,
+                 'gpu_launches_per_step': int(eng.launches_per_step)}
+            d.update(extra(eng, ms))
+            out[name] = d
+            del eng
+        except Exception as e:          # a secondary config must not take the headline line down
+            out[name] = {'error': repr(e)}
+        torch.cuda.empty_cache()
+
+    cfg1 = karel_config('synthesis_baseline', batch_size=8, k=2)
+    train_cfg('c1_karel_synthesis_k2_b8_train_step', cfg1, make_batch(cfg1, seed=123), 20,
+              lambda eng, ms: {'params': int(eng.pm.total)})
+    cfg4 = vizdoom_config('full', batch_size=32, k=10)
+    frames4 = cfg4.batch_size * cfg4.k * cfg4.max_demo_len
+
+    def c4_extra(eng, ms):
+        conv_flop = 27.7e6 * frames4            # conv fwd+bwd, SURVEY Appendix C
+        lstm_flop = 3 * (2.0 * eng.R * eng.T * 4 * eng.H * ((eng.F + eng.H) + 3 * 2 * eng.H) +
+                         2.0 * eng.B * cfg4.max_program_len * 4 * eng.H * 2 * eng.H)
+        tf = (conv_flop + lstm_flop) / (ms * 1e-3) / 1e12
+        return {'algorithmic_tflop_per_step': (conv_flop + lstm_flop) / 1e12, 'tflops': tf,
+                'frac_of_bf16_sustained_peak': tf / pk['bf16_tflops_sustained'],
+                'conv_algorithmic_gflop_fwd_bwd': conv_flop / 1e9}
+    train_cfg('c4_vizdoom_full_k10_b32_T20_train_step', cfg4, make_vizdoom_batch(cfg4, seed=123), 8, c4_extra)
+    try:
+        from demo2program_b200.induction import InductionEngine
+        cfg5 = karel_config('induction_baseline', batch_size=512, k=10)
+        eng = InductionEngine(cfg5, is_train=False)
+        eng.stage_batch(make_batch(cfg5, seed=123))
+        enc = _event_ms(lambda: eng.encode(), 5, flush=flush)
+        dec = _event_ms(lambda: eng.greedy(), 5, flush=flush)
+        kv = 2.0 * eng.B * eng.k * eng.T * eng.H * 4
+        frames5 = eng.B * eng.k * eng.T
+        out['c5_karel_induction_greedy_b512_k10'] = {
+            'encode_ms': enc, 'greedy_decode_ms': dec, 'latency_ms': enc + dec,
+            'greedy_path': eng.greedy_path, 'near_tie_argmaxes': int(getattr(eng, 'greedy_near_ties', -1)),
+            'unseen_demos_decoded_per_s': eng.R2 / ((enc + dec) * 1e-3),
+            'decode_steps': eng.T, 'kv_bytes_per_decode_step': kv,
+            'decode_GBps_kv_read_once_per_step': kv * eng.T / dec / 1e6,
+            'decode_frac_hbm': kv * eng.T / dec / 1e6 / pk['hbm_gbs'],
+            'encode_conv_algorithmic_bytes': 1216.0 * frames5}
+        del eng
+    except Exception as e:
+        out['c5_karel_induction_greedy_b512_k10'] = {'error': repr(e)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` summary (profiles/ncu_traffic.json, written by tools/ncu_traffic.py
+    from the capture); None when no capture of this kernel is committed."""
+    path = os.path.join(HERE, 'profiles', 'ncu_traffic.json')
+    try:
+        with open(path) as f:
+            tab = json.load(f)
+    except (OSError, ValueError):
+        return None, None
+    for name, rec in tab.items():
+        if kernel_substr in name:
+            return rec.get('dram_bytes_per_launch'), rec.get('source')
+    return None, None
+
+
 def run_ours(args):
     import torch
     from demo2program_b200.config import karel_config
@@ -304,6 +407,15 @@ def run_ours(args):
     launches_graph = getattr(eng, 'launches_per_step', None)
     if launches_graph is None:   # eager (multi-GPU) path counts live launches
         launches_graph = (eng.lib.d2p_launch_count() - n0) // (2 * args.steps)
+    # every rank must hold bit-identical parameters after the same number of averaged-gradient steps
+    w32 = eng.params.view(torch.int32).to(torch.int64)
+    csum = torch.stack([w32.sum(), (w32 * (torch.arange(w32.numel(), device=dev) % 65521 + 1)).sum()])
+    params_match = None
+    if world > 1:
+        gathered = [torch.zeros_like(csum) for _ in range(world)]
+        torch.distributed.all_gather(gathered, csum)
+        params_match = all(torch.equal(gathered[0], x) for x in gathered)
+    eng.check_device()
     t = torch.tensor([dev_ms, e2e_s, float(toks)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -326,7 +438,7 @@ def run_ours(args):
         'frac': dom['tflops'] / pk['bf16_tflops'],
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one launch, from the
         # committed `ncu --set full` capture (profiles/r01d_ncu_full_metrics.txt: 41.9 MB read + 16.3 MB written)
-        'traffic': 58.3e6, 'traffic_unit': 'bytes/launch (ncu --set full, cold cache)',
+        'traffic': None, 'traffic_unit': 'bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)',
         'kernel': dom['kernel'], 'shape_R_4H_H_T': dom['shape'], 'kernel_ms': dom['ms'],
         'peak_kind': pk_kind + ' bf16 burst (cuBLAS 8192^3); achieved counts ALGORITHMIC flops '
                      '2*R*H*4H*T - the bf16x3 split executes 3x that on the tensor pipe; the kernel is '
@@ -342,6 +454,12 @@ def run_ours(args):
         'second_kernel': {'kernel': dom['bwd']['kernel'], 'kernel_ms': dom['bwd']['ms'],
                           'achieved': dom['bwd']['tflops'], 'frac': dom['bwd']['tflops'] / pk['bf16_tflops']},
     }
+    roofline['traffic'], roofline['traffic_source'] = ncu_traffic('lstm_persist_fwd')
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        del eng
+        torch.cuda.empty_cache()
+        secondary = secondary_configs(flush, pk)
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         sec, ctoks, threads = cpu_reference_step_time(cfg, 2, 1)
@@ -352,11 +470,12 @@ def run_ours(args):
         sec1, _, _ = cpu_reference_step_time(cfg, 1, 0, threads=1)
         cpu['one_thread'] = {'value': ctoks / sec1, 'unit': UNIT, 'cores': 1, 'ms_per_step': sec1 * 1e3,
                              'sample': '1 full train step, no warm-up'}
+    launches_per_step = int(launches_graph)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'global_batch': 32 * world, 'per_gpu_batch': 32,
+        'config': {'workload': WORKLOAD, 'arithmetic': 'f32 (every dense product as a bf16x3 split on the tensor cores, ~5e-6 relative)', 'global_batch': 32 * world, 'per_gpu_batch': 32,
                    'parallelism': 'dp%d' % world, 'l2': 'flushed (256 MiB write) between timed steps',
                    'instances_per_sec': 32 * world / (ms_per_step * 1e-3),
                    'program_tokens_per_step': toks_all, 'cuda_graph': True},
@@ -371,6 +490,9 @@ def run_ours(args):
         'roofline': roofline,
         'cpu_baseline': cpu,
         'final_loss': loss,
+        'cross_rank_param_checksum_match': params_match,
+        'param_checksum': [int(x) for x in csum.tolist()],
+        'secondary': secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -384,6 +506,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the C1 / C4 / C5 secondary measurements')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

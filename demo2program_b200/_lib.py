@@ -68,6 +68,7 @@ SIGNATURES = {
     'd2p_greedy_ws_bytes': (_sz, [_i, _i, _i]),
     'd2p_lstm_decoder_greedy': (_i, [_fp, _i, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp, _fp,
                                      _fp, _fp, _fp, _fp, _sz, _fp]),
+    'd2p_greedy_near_ties': (_i, [_fp, _i, _i, _i, _fp, _f, _fp, _fp]),
     'd2p_luong_pool_attention_ws_bytes': (_sz, [_i, _i, _i, _i]),
     'd2p_luong_pool_attention': (_i, [_fp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _i, _fp, _sz, _fp]),
     'd2p_induction_decode_ws_bytes': (_sz, [_i, _i, _i, _i]),
@@ -114,6 +115,8 @@ SIGNATURES = {
     'd2p_lstm_set_persistent': (_i, [_i]),
     'd2p_conv_set_fused': (_i, [_i]),
     'd2p_device_error': (_i, [_fp]),
+    'd2p_device_error_async': (_i, [_fp, _fp]),
+    'd2p_debug_inject_device_error': (_i, [_i]),
     'd2p_debug_stamp': (_i, [_fp, _i, _fp]),
     'd2p_gemm_set_persistent': (_i, [_i]),
     'd2p_crc32c': (C.c_uint32, [_fp, _sz, C.c_uint32]),

@@ -46,15 +46,20 @@ sqnorm_partial(const float* __restrict__ g, size_t n, double* __restrict__ parti
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// state: [0] step (as double), [1] lr_t, [2] clip scale, [3] global norm, [4] extra sq-norm
+// state: [0] step (as double), [1] lr_t, [2] clip scale, [3] global norm, [4] extra sq-norm,
+// [5] skip flag: a persistent kernel's step barrier timed out (sticky error words e0 / e1), the
+// gradients are garbage - the update is skipped and the step counter does not advance
 __global__ void __launch_bounds__(AD_THREADS)
 adam_prepare(const double* __restrict__ partial, int nblk, double* __restrict__ state,
-             float lr, float b1, float b2, float clip, float grad_scale, int staircase_decay) {
+             float lr, float b1, float b2, float clip, float grad_scale, int staircase_decay,
+             const unsigned* __restrict__ e0, const unsigned* __restrict__ e1) {
     __shared__ double sh[AD_THREADS];
     double a = 0.0;
     for (int i = threadIdx.x; i < nblk; i += AD_THREADS) a += partial[i];
     double s = block_sum_d(a, sh);
     if (threadIdx.x != 0) return;
+    if ((e0 && *e0) || (e1 && *e1)) { state[5] = 1.0; return; }
+    state[5] = 0.0;
     s += state[4];
     double norm = sqrt(s) * (double)grad_scale;
     double step0 = state[0];
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(AD_THREADS)
 adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, size_t n, const double* __restrict__ state,
             float b1, float b2, float eps) {
+    if (state[5] != 0.0) return;   // failed step: leave parameters and both slots untouched
     const float lr_t = (float)state[1], gs = (float)state[2];
     const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
@@ -112,6 +118,7 @@ adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }  // namespace
 }  // namespace d2p
 
+namespace d2p { int device_error_addrs(unsigned** out); }
 using namespace d2p;
 
 extern "C" size_t d2p_adam_ws_bytes(void) { return (size_t)AD_BLOCKS * sizeof(double); }
@@ -127,10 +134,12 @@ extern "C" int d2p_clip_adam_step(float* params, const float* grads, float* m, f
     D2P_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                 "adam: buffers must be 16-byte aligned");
     const int nblk = AD_BLOCKS;
+    unsigned* errw[2];
+    D2P_TRY(device_error_addrs(errw));
     sqnorm_partial<<<nblk, AD_THREADS, 0, st>>>(grads, n, (double*)ws);
     D2P_CHECK_LAUNCH();
     adam_prepare<<<1, AD_THREADS, 0, st>>>((const double*)ws, nblk, state, lr, b1, b2, clip_norm, grad_scale,
-                                           staircase_decay_steps);
+                                           staircase_decay_steps, errw[0], errw[1]);
     D2P_CHECK_LAUNCH();
     adam_update<<<AD_BLOCKS, AD_THREADS, 0, st>>>(params, grads, m, v, n, state, b1, b2, eps);
     D2P_CHECK_LAUNCH();

@@ -831,6 +831,44 @@ int conv_fused_set_probe(long long* buf) {
     return 0;
 }
 }
+namespace d2p {
+int lstm_persist_error_addr(unsigned** out);
+// device addresses of the two sticky error words: [0] LSTM recurrence, [1] fused conv encoder
+int device_error_addrs(unsigned** out) {
+    static unsigned* cached[2] = {nullptr, nullptr};
+    if (!cached[0]) {
+        unsigned *a = nullptr, *b = nullptr;
+        D2P_TRY(lstm_persist_error_addr(&a));
+        D2P_CHECK_CUDA(cudaGetSymbolAddress((void**)&b, g_conv_sticky_error));
+        cached[0] = a; cached[1] = b;
+    }
+    out[0] = cached[0]; out[1] = cached[1];
+    return 0;
+}
+}
+// Asynchronous form for the training loop: copies the two sticky words (LSTM recurrence, fused conv
+// encoder) into dst[0..1] on the device, in stream order (capturable into a CUDA graph; nothing is
+// cleared) - the engine reads them back with every loss.
+extern "C" int d2p_device_error_async(unsigned* dst, void* stream) {
+    D2P_REQUIRE(dst != nullptr, "device_error_async: null argument");
+    unsigned* w[2];
+    D2P_TRY(d2p::device_error_addrs(w));
+    D2P_CHECK_CUDA(cudaMemcpyAsync(dst, w[0], sizeof(unsigned), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    D2P_CHECK_CUDA(cudaMemcpyAsync(dst + 1, w[1], sizeof(unsigned), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+// Fault injection for the tests of the error path: ORs `flags` (bit 0 LSTM recurrence, bit 1 fused
+// conv encoder) into the sticky words, as a timed-out step barrier would.
+extern "C" int d2p_debug_inject_device_error(int flags) {
+    unsigned* w[2];
+    D2P_TRY(d2p::device_error_addrs(w));
+    const unsigned one = 1;
+    if (flags & 1) D2P_CHECK_CUDA(cudaMemcpy(w[0], &one, sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (flags & 2) D2P_CHECK_CUDA(cudaMemcpy(w[1], &one, sizeof(unsigned), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // Synchronises the device and reports (and clears) whether a step barrier of a persistent /
 // cooperative kernel timed out since the last call: 0 = none, bit 0 = LSTM recurrence, bit 1 =
 // fused conv encoder.  Results produced by such a launch are invalid.

@@ -261,6 +261,36 @@ __global__ void luong_attn_mean_kernel(const float* __restrict__ part, int B, in
     *reinterpret_cast<float4*>(ctx + bj * ldc + u) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
 }
 
+
+// Arg-max margin guard of the tensor-core greedy path: counts the (step, row) positions that a
+// row actually executed (t < lengths[row]) whose top-2 logit gap is <= rel_tol * max(1, max|logit|),
+// i.e. where the ~5e-6 relative error of the bf16x3 products could flip the arg-max against an
+// fp32 evaluation.  The host re-runs the decode on the exact fp32 engine when the count is not 0.
+__global__ void near_tie_kernel(const float* __restrict__ logits, int Tdec, int R, int V,
+                                const int* __restrict__ lengths, float rel_tol, int* __restrict__ count) {
+    const int warps = blockDim.x / 32, lane = threadIdx.x % 32;
+    const long long total = (long long)Tdec * R;
+    for (long long idx = blockIdx.x * (long long)warps + threadIdx.x / 32; idx < total;
+         idx += (long long)gridDim.x * warps) {
+        const int t = (int)(idx / R), row = (int)(idx % R);
+        if (t >= lengths[row]) continue;
+        const float* x = logits + (size_t)idx * V;
+        float b1 = -INFINITY, b2 = -INFINITY, am = 0.f;
+        for (int v = lane; v < V; v += 32) {
+            const float xv = x[v];
+            am = fmaxf(am, fabsf(xv));
+            if (xv > b1) { b2 = b1; b1 = xv; } else if (xv > b2) b2 = xv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+            if (o1 > b1) { b2 = fmaxf(b1, o2); b1 = o1; } else b2 = fmaxf(b2, o1);
+        }
+        if (lane == 0 && V > 1 && b1 - b2 <= rel_tol * fmaxf(1.f, am)) atomicAdd(count, 1);
+    }
+}
+
 // x[r2,:] = table[id] with id = (t == 0 ? start_id : tokens[r2, t-1]); out of range -> 0
 __global__ void gather_step_kernel(const float* __restrict__ table, int vocab_rows, int E,
                                    const int* __restrict__ tokens, int R2, int L, int t, int start_id,
@@ -431,6 +461,19 @@ extern "C" int d2p_induction_decode(const float* keys, const float* memory_layer
             D2P_CHECK_LAUNCH();
         }
     }
+    return 0;
+}
+
+extern "C" int d2p_greedy_near_ties(const float* logits, int Tdec, int R, int V, const int* lengths,
+                                    float rel_tol, int* count, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    D2P_REQUIRE(logits && lengths && count && Tdec > 0 && R > 0 && V > 0, "greedy_near_ties: bad arguments");
+    D2P_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    const long long total = (long long)Tdec * R;
+    long long blocks = (total + 7) / 8;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    near_tie_kernel<<<(int)blocks, 256, 0, st>>>(logits, Tdec, R, V, lengths, rel_tol, count);
+    D2P_CHECK_LAUNCH();
     return 0;
 }
 

@@ -665,6 +665,12 @@ int lstm_persist_error(unsigned* out, bool clear) {
     return 0;
 }
 
+// device address of the sticky error word (read by the optimizer kernel and the async error copy)
+int lstm_persist_error_addr(unsigned** out) {
+    D2P_CHECK_CUDA(cudaGetSymbolAddress((void**)out, g_persist_sticky_error));
+    return 0;
+}
+
 int lstm_persist_set_probe(long long* buf) {
     D2P_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_tc_dbg, &buf, sizeof(buf)));
     return 0;

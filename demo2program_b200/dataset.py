@@ -321,6 +321,10 @@ def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None, workers=0, l
     through anonymous shared mappings) and still delivers them in the seeded order."""
     r = np.random.RandomState(seed)
     ids = list(dataset.ids)
+    if len(ids) < batch_size:
+        # (a generator: the error surfaces at the first next(), before any step is attempted)
+        raise ValueError('dataset split has %d examples, fewer than batch_size=%d: no full batch can '
+                         'be formed' % (len(ids), batch_size))
 
     def id_lists():
         e = 0

@@ -101,7 +101,7 @@ class Engine:
     def _tc_bind(self):
         """The arena registration is library-global: bind this engine's buffers
         before issuing work (also invalidates the packed-weight cache)."""
-        if self.use_tc:
+        if self.use_tc and not getattr(self, '_force_fp32', False):
             self.lib.d2p_tc_configure(ptr(self.tc_scratch), self.tc_scratch.numel(),
                                       ptr(self.tc_cache), self.tc_cache.numel(), 1)
             for s_, arena in zip(self._all_side, self.tc_side):
@@ -162,6 +162,10 @@ class Engine:
             'per': torch.zeros(R, T, Pd).pin_memory(),
         }
         self.h_loss = torch.zeros(4).pin_memory()
+        # sticky step-barrier time-out words (LSTM recurrence, fused conv encoder): refreshed at the end of
+        # every step on the device (d2p_device_error_async) and read back with the loss
+        self.err_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.h_err = torch.zeros(2, dtype=torch.int32).pin_memory()
         # ---- conv encoder ----
         d = ConvDesc()
         d.B, d.k, d.T, d.h, d.w, d.d = B, k, T, cfg.h, cfg.w, cfg.depth
@@ -741,6 +745,7 @@ class Engine:
             self.backward()
             if with_opt:
                 self.optimizer_step()
+            self._record_errors()
             return
         cur = torch.cuda.current_stream(self.dev)
         self.main_stream.wait_stream(cur)
@@ -749,7 +754,19 @@ class Engine:
             self.backward()
             if with_opt:
                 self.optimizer_step()
+            self._record_errors()
         cur.wait_stream(self.main_stream)
+
+    def _record_errors(self):
+        """Copy the sticky device-error words next to the loss (stream-ordered, graph-capturable)."""
+        self._call('d2p_device_error_async', ptr(self.err_dev), self._st())
+
+    def _raise_if_failed(self, words):
+        """words: the two error words read back with a loss.  Raises if a step barrier timed out; the
+        optimizer has skipped that step's update on the device (d2p_clip_adam_step), so parameters
+        and Adam slots are those of the last good step."""
+        if int(words[0]) or int(words[1]):
+            self.check_device()      # synchronises, clears the sticky words and raises
 
     def _capture(self, fn):
         """Warm up `fn` on a side stream (lazy module loading), then capture it."""
@@ -819,8 +836,9 @@ class Engine:
         self.stage_batch(batch)
         self.train_step_device(True)
         self.h_loss.copy_(self.loss, non_blocking=True)
+        self.h_err.copy_(self.err_dev, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
-        self.check_device()
+        self._raise_if_failed(self.h_err)
         return float(self.h_loss[0])
 
     def _input_pairs(self):
@@ -850,6 +868,7 @@ class Engine:
                 'free': [torch.cuda.Event() for _ in range(2)],
                 'done': [torch.cuda.Event() for _ in range(2)],
                 'loss': [torch.zeros(4).pin_memory() for _ in range(2)],
+                'err': [torch.zeros(2, dtype=torch.int32).pin_memory() for _ in range(2)],
             }
         pf = self._pf
         keys = ['s_h', 'demo_len', 'program_len', 'program_tokens'] + \
@@ -882,10 +901,12 @@ class Engine:
             pf['free'][slot].record(main)
             self.train_step_device(True)
             pf['loss'][slot].copy_(self.loss, non_blocking=True)
+            pf['err'][slot].copy_(self.err_dev, non_blocking=True)
             pf['done'][slot].record(main)
-            # read back step i-1's loss while step i runs
+            # read back step i-1's loss (and its device-error words) while step i runs
             if i >= 1:
                 pf['done'][slot ^ 1].synchronize()
+                self._raise_if_failed(pf['err'][slot ^ 1])
                 yield float(pf['loss'][slot ^ 1][0])
             try:
                 nxt = next(it)
@@ -896,7 +917,7 @@ class Engine:
             i += 1
         last = (i - 1) & 1
         pf['done'][last].synchronize()
-        self.check_device()
+        self._raise_if_failed(pf['err'][last])
         yield float(pf['loss'][last][0])
 
     # ------------------------------------------------------------------ outputs
@@ -910,33 +931,68 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ greedy decode
-    def _greedy(self, scope, vocab, end_id, max_len, rows, h0, c0, exact=True, nsl=1):
+    # arg-max margin below which a tensor-core (bf16x3, ~5e-6 relative) greedy decode is repeated
+    # on the exact fp32 engine: 40x the product error bound, relative to max(1, max|logit|)
+    TIE_TOL = 2e-4
+
+    def _near_ties(self, logits, lengths):
+        """Executed positions of a greedy decode whose top-2 logit gap is within TIE_TOL
+        (d2p_greedy_near_ties).  Synchronises the stream (one int comes back)."""
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        Tn, rows, vocab = logits.shape
+        self._call('d2p_greedy_near_ties', ptr(logits), Tn, rows, vocab, ptr(lengths), self.TIE_TOL,
+                   ptr(cnt), self._st())
+        return int(cnt.item())
+
+    def _greedy(self, scope, vocab, end_id, max_len, rows, h0, c0, exact=None, nsl=1):
         """GreedyEmbeddingHelper decode with the decoder under `scope` (reference
-        models/model_full.py:424-435).  exact=True runs every contraction on the
-        fp32 SIMT engine so that arg-max ties resolve as in fp32 arithmetic."""
+        models/model_full.py:424-435).  exact=True runs every contraction on the fp32 SIMT
+        engine; exact=False on the tensor-core engine; exact=None (default, what the facade
+        ships): tensor cores, and if any executed arg-max has a top-2 margin within TIE_TOL the
+        decode is repeated on the fp32 engine, so the token ids are those of fp32 arithmetic."""
         H = self.H
         logits = torch.zeros(max_len, rows, vocab, dtype=torch.float32, device=self.dev)
         tokens = torch.zeros(max_len, rows, dtype=torch.int32, device=self.dev)
         lengths = torch.zeros(rows, dtype=torch.int32, device=self.dev)
         wsb = self.lib.d2p_greedy_ws_bytes(rows, H, H)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
-        if exact:
-            self.lib.d2p_tc_configure(None, 0, None, 0, 0)
-        else:
-            self._tc_bind()
         d = scope + '/dynamic_decoder/'
-        try:
-            self._call('d2p_lstm_decoder_greedy',
-                       ptr(self.P(scope + '/Token_Embedding/embedding_map')), vocab + 1, H,
-                       ptr(self.P(d + 'basic_lstm_cell/kernel')), ptr(self.P(d + 'basic_lstm_cell/bias')),
-                       ptr(self.P(d + 'output_projection/kernel')), rows, H, vocab, vocab, end_id,
-                       max_len, nsl, ptr(h0), ptr(c0), ptr(logits), ptr(tokens), ptr(lengths), ptr(ws), wsb,
-                       self._st())
-        finally:
-            self._tc_bind()
+
+        def run(on_fp32):
+            if on_fp32 or not self.use_tc:
+                self.lib.d2p_tc_configure(None, 0, None, 0, 0)
+            else:
+                self._tc_bind()
+            try:
+                self._call('d2p_lstm_decoder_greedy',
+                           ptr(self.P(scope + '/Token_Embedding/embedding_map')), vocab + 1, H,
+                           ptr(self.P(d + 'basic_lstm_cell/kernel')), ptr(self.P(d + 'basic_lstm_cell/bias')),
+                           ptr(self.P(d + 'output_projection/kernel')), rows, H, vocab, vocab, end_id,
+                           max_len, nsl, ptr(h0), ptr(c0), ptr(logits), ptr(tokens), ptr(lengths), ptr(ws), wsb,
+                           self._st())
+            finally:
+                self._tc_bind()
+        self.greedy_path = 'fp32' if (exact or not self.use_tc) else 'tensor-core'
+        run(bool(exact))
+        if exact is None and self.use_tc:
+            self.greedy_near_ties = self._near_ties(logits, lengths)
+            if self.greedy_near_ties:
+                # the whole chain again in fp32 arithmetic: the forward pass that produced (h0, c0)
+                # (BatchNorm moving statistics and losses are put back) and the decode
+                self.greedy_path = 'fp32 (re-evaluated: %d near-tie arg-maxes)' % self.greedy_near_ties
+                state, loss = self.state.clone(), self.loss.clone()
+                self._force_fp32 = True
+                try:
+                    self.forward()
+                    run(True)
+                finally:
+                    self._force_fp32 = False
+                    self._tc_bind()
+                self.state.copy_(state)
+                self.loss.copy_(loss)
         return logits, tokens, lengths
 
-    def greedy_program(self, exact=True):
+    def greedy_program(self, exact=None):
         """After forward(): (greedy_pred_program [B,V,L], greedy_pred_program_len [B,1],
         tokens [B,L]) - the reference's greedy program decoder outputs."""
         cfg = self.cfg
@@ -947,7 +1003,7 @@ class Engine:
         self._call('d2p_logits_to_bvl', ptr(logits), L, B, V, ptr(out), self._st())
         return out, lengths.view(B, 1), tokens.t().contiguous()
 
-    def greedy_actions(self, exact=True):
+    def greedy_actions(self, exact=None):
         """`full` only: greedy action decoders of all k demos, batched as R = B*k rows.
         Returns (logits [B,k,T,A], lengths [B,k])."""
         cfg = self.cfg

@@ -175,12 +175,33 @@ class InductionEngine:
                    ptr(self.runlen), ptr(self.w), ptr(self.rowloss), None, ptr(self.loss), 0, st)
         return self.logits.permute(1, 0, 2).reshape(self.B, tk, T, A).contiguous()
 
-    def greedy(self, exact=True):
-        """Greedy action decode of every unseen demo: (logits [B,test_k,T,A], lengths [B,test_k])."""
+    TIE_TOL = 2e-4     # see Engine.TIE_TOL
+
+    def greedy(self, exact=None):
+        """Greedy action decode of every unseen demo: (logits [B,test_k,T,A], lengths [B,test_k]).
+        exact=None (default): tensor-core engine, repeated on the exact fp32 engine if any executed
+        arg-max has a top-2 margin within TIE_TOL (d2p_greedy_near_ties), so the token ids are those
+        of fp32 arithmetic; True / False force the fp32 / tensor-core engine."""
         A, T, R2, tk = self.cfg.action_space, self.T, self.R2, self.tk
         toks = torch.zeros(T, R2, dtype=torch.int32, device=self.dev)
         lens = torch.zeros(R2, dtype=torch.int32, device=self.dev)
-        self._decode(None, toks, lens, exact)
+        on_fp32 = bool(exact) or not self.use_tc
+        self._decode(None, toks, lens, on_fp32)
+        self.greedy_path = 'fp32' if on_fp32 else 'tensor-core'
+        if exact is None and self.use_tc:
+            cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._call('d2p_greedy_near_ties', ptr(self.logits), T, R2, A, ptr(lens), self.TIE_TOL, ptr(cnt),
+                       self._st())
+            self.greedy_near_ties = int(cnt.item())
+            if self.greedy_near_ties:
+                # the whole chain again in fp32 arithmetic: encoder (BatchNorm moving statistics are
+                # put back so that a train-mode model does not advance them twice) and decoder
+                self.greedy_path = 'fp32 (re-evaluated: %d near-tie arg-maxes)' % self.greedy_near_ties
+                state = self.state.clone()
+                self.encode(exact=True)
+                self.state.copy_(state)
+                self._decode(None, toks, lens, True)
+        self.greedy_tokens = toks
         return (self.logits.permute(1, 0, 2).reshape(self.B, tk, T, A).contiguous(),
                 lens.view(self.B, tk))
 

@@ -148,6 +148,14 @@ int d2p_lstm_decoder_greedy(const float* table, int vocab_rows, int E, const flo
                             const float* h0, const float* c0, float* logits, int* tokens,
                             int* lengths, void* ws, size_t ws_bytes, void* stream);
 
+/* Arg-max margin guard for a greedy decode that ran on the tensor-core (bf16x3) engine: *count =
+ * number of executed positions (t < lengths[row]) of logits [Tdec, R, V] whose top-2 gap is
+ * <= rel_tol * max(1, max|logit|).  North_star asks for bit-exact greedy token ids: when the count
+ * is not zero the host repeats the decode on the exact fp32 engine (models/model_full.py:424-435
+ * argmax semantics, lowest index wins). */
+int d2p_greedy_near_ties(const float* logits, int Tdec, int R, int V, const int* lengths,
+                         float rel_tol, int* count, void* stream);
+
 /* ---- K6: pooled Luong attention + induction decoder --------------------------------
  * reference models/baselines/model_induction.py:25-53, 107-182, 638-709.
  * keys/values [T, R, H] time-major (R = B*k, keys = values * W_mem), mem_len [R];
@@ -308,6 +316,13 @@ int d2p_lstm_set_persistent(int mode);
  * recurrence, bit 1 = fused conv encoder); the outputs of such a launch are invalid.  The engine
  * checks it whenever it hands a loss to the caller. */
 int d2p_device_error(int* flags);
+/* Stream-ordered, non-clearing form for the training loop: dst[0] = LSTM recurrence word, dst[1] =
+ * fused conv encoder word (device memory; capturable into a CUDA graph).  d2p_clip_adam_step reads
+ * the same words and skips the update (parameters, slots and step counter untouched) when one is
+ * set, so a failed step never reaches the weights. */
+int d2p_device_error_async(unsigned* dst, void* stream);
+/* test hook: set the sticky words as a timed-out barrier would (bit 0 / bit 1 as above) */
+int d2p_debug_inject_device_error(int flags);
 /* developer tool: record SM-clock stamps of CTA (0,0,0) of the tensor-core kernels
  * into buf (>= 128 int64 on the device; the persistent recurrence kernels use
  * slots 64..127); NULL disables. */

@@ -1,0 +1,181 @@
+"""GPU parity at the BASELINE.json sizes, default engine (tensor cores + persistent recurrences +
+fused conv + token tables + CUDA graph) against the fp64 CPU oracle - not against other schedules
+of this library.
+
+ * C2: Karel `full`, k=10, B=32 (the benchmarked shape, R = 320 rows): loss, per-variable
+   gradients, then 3 optimizer steps.
+ * C4: ViZDoom `full` 80x80x3 on the default (tensor-core) engine at B=8, T=8.
+ * Sequence_Loss's token / sequence accuracies (reference models/model_full.py:660-683).
+
+Floating point: north_star asks for training loss within 1e-4 (fp32); gradients are compared per
+variable relative to the variable's largest entry."""
+import numpy as np
+import pytest
+import torch
+
+from demo2program_b200.config import karel_config, vizdoom_config
+from parity_util import oracle_and_engine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+GRAD_TOL = 3e-4       # bf16x3 tensor-core products vs fp64, relative to the variable's max |grad|
+
+
+def _grad_check(pm, g, go, tol=GRAD_TOL):
+    gmax = np.abs(go).max()
+    worst = ('', 0.0)
+    for e in pm:
+        a, b = g[e.offset:e.offset + e.size], go[e.offset:e.offset + e.size]
+        err = np.abs(a - b).max() / (np.abs(b).max() + 1e-5 * gmax / tol)
+        if err > worst[1]:
+            worst = (e.name, float(err))
+        assert np.abs(a - b).max() < tol * np.abs(b).max() + 1e-5 * gmax, (e.name, err)
+    return worst
+
+
+def test_c2_default_engine_matches_fp64_oracle():
+    """BASELINE configs[1] at its real size through the CUDA graph the bench replays."""
+    cfg = karel_config('full', batch_size=32, k=10)
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=True)
+    loss_o, grad_o, out = orc.model.loss_and_grad(batch)
+    eng.stage_batch(batch)
+    eng.train_step_device(False)          # captured forward + backward, no optimizer
+    eng.train_step_device(False)          # replay
+    torch.cuda.synchronize()
+    eng.check_device()
+    losses = eng.loss.cpu().numpy()
+    assert abs(float(losses[0]) - loss_o) < LOSS_TOL
+    assert abs(float(losses[1]) - float(out['program_loss'])) < LOSS_TOL
+    assert abs(float(losses[2]) - float(out['avg_action_loss'])) < LOSS_TOL
+    assert abs(float(losses[3]) - float(out['avg_per_loss'])) < LOSS_TOL
+    _grad_check(pm, eng.grads.cpu().numpy(), grad_o.numpy())
+    assert rel_err(eng.pred_program().cpu().numpy(), out['pred_program'].detach().numpy()) < 1e-4
+    assert rel_err(eng.dsum_h.cpu().numpy(), out['demo_h_summary'].detach().numpy()) < 1e-4
+    # three optimizer steps (clip + TF-Adam + BatchNorm moving statistics)
+    # the two forward passes above advanced the engine's BatchNorm moving statistics
+    eng.state.copy_(torch.from_numpy(sm.init_flat(0)))
+    for step in range(3):
+        lo, norm_o, _ = orc.train_step(batch)
+        le = eng.train_step(batch)
+        assert abs(le - lo) < LOSS_TOL, (step, le, lo)
+        assert abs(eng.global_norm() - norm_o) < 5e-4 * max(1.0, norm_o)
+    assert eng.step_count() == 3
+    assert rel_err(eng.state.cpu().numpy(), orc.model.state.numpy()) < 2e-3
+
+
+def test_c4_vizdoom_default_engine_matches_oracle():
+    """BASELINE configs[3] geometry on the default engine (tensor-core products everywhere,
+    persistent recurrences) at a well-conditioned size: BatchNorm over B*T*3*3 = 576 values in the
+    last conv layer and B*k*k = 72 rows in rn_pool."""
+    cfg = vizdoom_config('full', batch_size=8, k=3, max_demo_len=8, test_k=2, max_program_len=12)
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False)
+    loss_o, grad_o, out = orc.model.loss_and_grad(batch)
+    eng.stage_batch(batch)
+    eng.forward()
+    eng.backward()
+    torch.cuda.synchronize()
+    eng.check_device()
+    assert eng.F == 432
+    assert abs(float(eng.loss[0]) - loss_o) < LOSS_TOL
+    _grad_check(pm, eng.grads.cpu().numpy(), grad_o.numpy(), tol=1e-3)
+
+
+def test_c5_induction_tensor_core_path_matches_oracle():
+    """BASELINE configs[4] path (induction baseline, eval-mode BatchNorm) on the SHIPPED default
+    engine - tensor-core products, R = B*k = 640 encoder rows (> 512: the per-step recurrence
+    kernels and the persistent tile-queue GEMM the B=512 run uses): teacher-forced loss / logits and
+    greedy token ids + lengths against the fp64 oracle.  The greedy default (exact=None) decodes on
+    the tensor cores and re-evaluates in fp32 only if an executed arg-max is a near tie
+    (d2p_greedy_near_ties); the plain tensor-core decode (exact=False) is compared too."""
+    from oracle.models import OracleModel
+    from demo2program_b200.induction import InductionEngine
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('induction_baseline', batch_size=64, k=10)
+    pm, sm = build_manifests(cfg)
+    p0, s0 = pm.init_flat(5), sm.init_flat(5)
+    s0 = s0 + np.random.RandomState(1).uniform(0.0, 0.3, s0.shape).astype(np.float32)
+    batch = make_batch(cfg, seed=11)
+    om = OracleModel(cfg, p0, s0, is_train=False)
+    with torch.no_grad():
+        out = om.forward_induction(batch, greedy=True)
+    o_len = out['greedy_pred_action_len'].numpy()
+    o_tok = out['greedy_pred_action'].numpy().argmax(-1)            # [B, tk, T]
+    eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=False, use_tc=True)
+    eng.stage_batch(batch)
+    eng.encode()
+    pred = eng.forward_teacher()
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss[0]) - float(out['loss'])) < LOSS_TOL
+    assert rel_err(pred.cpu().numpy(), out['pred_action'].numpy()) < 1e-4
+    B, tk, T = cfg.batch_size, cfg.test_k, cfg.max_demo_len
+    for exact in (None, False):
+        g, gl = eng.greedy(exact=exact)
+        torch.cuda.synchronize()
+        assert np.array_equal(gl.cpu().numpy(), o_len), (exact, eng.greedy_path)
+        tok = eng.greedy_tokens.cpu().numpy().T.reshape(B, tk, T)    # [T, B*tk] -> [B, tk, T]
+        live = np.arange(T)[None, None, :] < o_len[..., None]
+        assert np.array_equal(tok[live], o_tok[live]), (exact, eng.greedy_path)
+        assert rel_err(g.cpu().numpy(), out['greedy_pred_action'].numpy()) < 1e-4
+    assert eng.greedy_path == 'tensor-core'
+
+
+def test_near_tie_guard_reruns_in_fp32():
+    """d2p_greedy_near_ties counts executed arg-maxes within the tolerance; a non-zero count makes
+    Engine.greedy_program (exact=None) repeat forward + decode on the fp32 engine, which then
+    equals the exact=True result bit for bit."""
+    from demo2program_b200 import _lib
+    lib = _lib.load()
+    logits = torch.tensor([[[0.0, 1.0, 3.0], [2.0, 2.00001, -1.0]],
+                           [[5.0, 5.0, 5.0], [0.0, 9.0, 1.0]]], device='cuda')     # [T=2, R=2, V=3]
+    cnt = torch.zeros(1, dtype=torch.int32, device='cuda')
+    for lens, want in (([2, 2], 2), ([1, 2], 1), ([1, 1], 1), ([2, 0], 1)):
+        ln = torch.tensor(lens, dtype=torch.int32, device='cuda')
+        assert lib.d2p_greedy_near_ties(logits.data_ptr(), 2, 2, 3, ln.data_ptr(), 1e-4, cnt.data_ptr(), None) == 0
+        assert int(cnt.item()) == want, lens
+    cfg = karel_config('synthesis_baseline', batch_size=8, k=2)
+    _, eng, batch, _, _ = oracle_and_engine(cfg, use_graph=False)
+    eng.stage_batch(batch)
+    eng._force_fp32 = True                  # reference: forward + decode both in fp32 arithmetic
+    eng.forward()
+    ref = eng.greedy_program(exact=True)
+    eng._force_fp32 = False
+    eng.TIE_TOL = 10.0                      # every arg-max counts as a near tie
+    eng.forward()
+    got = eng.greedy_program()
+    assert eng.greedy_near_ties > 0 and eng.greedy_path.startswith('fp32 (re-evaluated')
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+
+
+def test_failed_step_is_reported_with_its_loss_and_never_reaches_the_weights():
+    """A timed-out step barrier (injected through d2p_debug_inject_device_error) is raised with the
+    loss of the step it poisoned - in the synchronous train_step and in the pipelined train_steps -
+    and clip+Adam skips that step's update: parameters, slots and the step counter stay put."""
+    from demo2program_b200 import _lib
+    from demo2program_b200.synthetic import make_batch
+    lib = _lib.load()
+    cfg = karel_config('full', batch_size=4, k=3)
+    _, eng, batch, _, _ = oracle_and_engine(cfg, use_graph=True)
+    eng.train_step(batch)
+    snap = [t.clone() for t in (eng.params, eng.adam_m, eng.adam_v)]
+    assert lib.d2p_debug_inject_device_error(1) == 0
+    with pytest.raises(_lib.D2PError):
+        eng.train_step(batch)
+    for a, b in zip(snap, (eng.params, eng.adam_m, eng.adam_v)):
+        assert torch.equal(a, b)
+    assert eng.step_count() == 1
+    eng.train_step(batch)                      # the words were cleared: training continues
+    assert eng.step_count() == 2 and not torch.equal(snap[0], eng.params)
+    # pipelined loop: the error surfaces at the failed step, not at the end of the iterator
+    batches = [make_batch(cfg, seed=60 + i) for i in range(6)]
+    seen = 0
+    with pytest.raises(_lib.D2PError):
+        for i, loss in enumerate(eng.train_steps(iter(batches))):
+            seen += 1
+            if i == 1:
+                lib.d2p_debug_inject_device_error(2)
+    assert seen < len(batches)
+    flags = __import__('ctypes').c_int(0)
+    lib.d2p_device_error(__import__('ctypes').byref(flags))
