@@ -337,6 +337,7 @@ def ncu_traffic(kernel_substr):
 def run_ours(args):
     import torch
     from demo2program_b200.config import karel_config
+    from demo2program_b200.dp import shutdown as dp_shutdown
     from demo2program_b200.engine import Engine
     from demo2program_b200.synthetic import make_batch, program_tokens_in_batch
     rank, local, world = dist_env()
@@ -426,8 +427,8 @@ def run_ours(args):
     else:
         toks_all = float(toks)
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        eng.close()
+        dp_shutdown()
         return
     ms_per_step = dev_ms / args.steps
     value = toks_all / (ms_per_step * 1e-3)
@@ -496,7 +497,8 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        eng.close()
+        dp_shutdown()
 
 
 def main():

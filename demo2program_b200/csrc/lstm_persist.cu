@@ -410,6 +410,278 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compact forward recurrence: ONE column of 32 CTAs walks all row tiles of the sequence batch
+// (R <= 512 rows in up to 4 tiles) instead of one CTA per (column, row tile).  Row tiles are
+// independent recurrences, so a CTA time-multiplexes them: while tile j's cell math / publish /
+// copy-out runs on the epilogue warps, the producer lane is already streaming tile j+1's operand
+// and the MMA lane is issuing its products into tile j+1's own TMEM accumulator (NT x 128
+// columns).  The step-to-step dependency chain of one tile (barrier, bulk-copy latency, MMA,
+// MUFU, publish) hides behind the other tiles' streams, so 32 SMs sustain about the step rate
+// 96 SMs reach with one tile per CTA - and three such recurrences (the action, perception and
+// program decoders of models/model_full.py:440-595) fit on the GPU side by side.
+//   warps 0..15  epilogue: thread = (accumulator row, 4 hidden units); c and h of every tile in registers
+//   warp 16      producer lane: per (step, tile) waits for the tile's 32 publishers, streams the
+//                8 k-blocks of packed h_{t-1} through the ring
+//   warp 17      MMA lane: Ahi*[Bhi|Blo] (N=128) + Alo*Bhi (N=64) per k16 into the tile's accumulator
+constexpr int MT_MAX_TILES = 4;
+constexpr int MT_EPI_THREADS = 512;
+constexpr int MT_THREADS = MT_EPI_THREADS + 64;
+constexpr long long MT_MBAR_SPIN = 2000000000LL;
+
+struct FwdMtArgs {
+    FwdArgs f;
+    int nt;                        // row tiles
+    int g0[MT_MAX_TILES + 1];      // first 8-row group of tile j (g0[nt] = groups)
+};
+
+// mbarrier wait with a time-out: a protocol error sets the sticky word instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity, unsigned* err) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    int it = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++it & 255) == 0) {
+            if (ld_acquire(err) != 0u) return;
+            if (clock64() - t0 > MT_MBAR_SPIN) { atomicExch(err, 1u); atomicExch(&g_persist_sticky_error, 1u); return; }
+        }
+    }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// timeline probe of the compact kernels: CTA 0, step P_PROBE_STEP, tile j -> slots 64 + 16 j + k
+__device__ __forceinline__ void mstamp(int step, int j, int k) {
+    if (g_tc_dbg != nullptr && step == P_PROBE_STEP && blockIdx.x == 0) g_tc_dbg[64 + 16 * j + k] = clock64();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(MT_THREADS, 1) lstm_persist_fwd_mt_kernel(const FwdMtArgs am) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2 * MT_MAX_TILES + 1];
+    __shared__ uint32_t tmem_slot;
+    const FwdArgs& a = am.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * PBN, u0 = blockIdx.x * PUPT;
+    const int H = PH, G4 = 4 * PH, R = a.R, rot = blockIdx.x & (PNKB - 1);
+    unsigned* err = a.sync + 63;
+    constexpr uint32_t TCOLS = NT <= 2 ? 256u : 512u;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[PMAXSLOTS]);
+    const uint32_t accf0 = smem_u32(&bars[2 * PMAXSLOTS]), acce0 = smem_u32(&bars[2 * PMAXSLOTS + MT_MAX_TILES]);
+    const uint32_t wfull = smem_u32(&bars[2 * PMAXSLOTS + 2 * MT_MAX_TILES]);
+    // ring geometry: slots sized for the largest tile; the MMA reads a full 128-row image from a
+    // slot, so the last slot must start at least 32 KB before the end of the ring
+    int gmax = 0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) gmax = max(gmax, am.g0[j + 1] - am.g0[j]);
+    const uint32_t slot_bytes = (uint32_t)gmax * 2048u;
+    int nslots = (int)((P_RING_BYTES - (BM / 8) * 2048) / slot_bytes) + 1;
+    if (nslots > PMAXSLOTS) nslots = PMAXSLOTS;
+    const size_t a_kb_stride = (size_t)a.mgp_h * 2048;
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < 2 * PMAXSLOTS; ++s2) mbar_init(full0 + 8 * s2, 1);
+        for (int j = 0; j < MT_MAX_TILES; ++j) { mbar_init(accf0 + 8 * j, 1); mbar_init(acce0 + 8 * j, MT_EPI_THREADS / 32); }
+        mbar_init(wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_slot)), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {   // rows a partial tile never loads must hold finite values
+        uint4* ring = reinterpret_cast<uint4*>(smem + P_W_BYTES);
+        for (int i = tid; i < (int)(P_RING_BYTES / 16); i += MT_THREADS) ring[i] = make_uint4(0, 0, 0, 0);
+    }
+    proxy_fence();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp == MT_EPI_THREADS / 32) {
+        // ===================== producer lane =====================
+        if (lane == 0) {
+            mbar_expect_tx(wfull, (uint32_t)P_W_BYTES);
+            const uint8_t* wsrc = a.whpk + (size_t)(n0 / PBN) * PB_BYTES;
+            for (int kb = 0; kb < PNKB; ++kb)
+                bulk_copy(sbase + kb * PB_BYTES, wsrc + (size_t)kb * a.mgp_w * 2048, PB_BYTES, wfull);
+            int slot = 0;
+            uint32_t phase = 0;
+            bool wrapped = false;
+            for (int t = 0; t < a.T; ++t) {
+                const uint8_t* hsrc = (t & 1) ? a.hpk1 : a.hpk0;
+#pragma unroll 1
+                for (int j = 0; j < NT; ++j) {
+                    mstamp(t, j, 0);
+                    if (t > 0) grid_wait(a.sync + j, (unsigned)(PCOLS * t), err);
+                    mstamp(t, j, 1);
+                    proxy_fence();
+                    const uint32_t bytes = (uint32_t)(am.g0[j + 1] - am.g0[j]) * 2048u;
+                    const uint8_t* src = hsrc + (size_t)am.g0[j] * 2048;
+                    for (int kb = 0; kb < PNKB; ++kb) {
+                        if (wrapped) mbar_wait_bounded(empty0 + 8 * slot, phase ^ 1u, err);
+                        const uint32_t bar = full0 + 8 * slot;
+                        mbar_expect_tx(bar, bytes);
+                        bulk_copy(sbase + (uint32_t)P_W_BYTES + slot * slot_bytes,
+                                  src + (size_t)((kb + rot) & (PNKB - 1)) * a_kb_stride, bytes, bar);
+                        if (++slot == nslots) { slot = 0; phase ^= 1u; wrapped = true; }
+                    }
+                    mstamp(t, j, 2);
+                }
+            }
+        }
+    } else if (warp == MT_EPI_THREADS / 32 + 1) {
+        // ===================== MMA lane =====================
+        if (lane == 0) {
+            constexpr uint32_t LBO = 256, SBO = 2048, WLBO = 128, WSBO = 1024;
+            constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PBN >> 3) << 17) |
+                                         ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * PBN) >> 3) << 17) |
+                                          ((uint32_t)(BM >> 4) << 24);
+            const uint64_t a_base = make_desc(sbase + (uint32_t)P_W_BYTES, LBO, SBO);
+            const uint64_t w_base = make_desc(sbase, WLBO, WSBO);
+            const uint32_t a_slot = slot_bytes >> 4;
+            int slot = 0;
+            uint32_t phase = 0;
+            mbar_wait_bounded(wfull, 0, err);
+            for (int t = 0; t < a.T; ++t) {
+#pragma unroll 1
+                for (int j = 0; j < NT; ++j) {
+                    mstamp(t, j, 3);
+                    if (t > 0) mbar_wait_bounded(acce0 + 8 * j, (uint32_t)((t - 1) & 1), err);
+                    mstamp(t, j, 4);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t td = tmem_d + (uint32_t)(j * PTMEM);
+#pragma unroll 1
+                    for (int kb = 0; kb < PNKB; ++kb) {
+                        mbar_wait_bounded(full0 + 8 * slot, phase, err);
+                        if (kb == 0) mstamp(t, j, 5);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t ad = a_base + (uint64_t)(slot * a_slot);
+                        const uint64_t wd = w_base + (uint64_t)(((kb + rot) & (PNKB - 1)) * (PB_BYTES >> 4));
+                        if (kb == 0) umma_imm<false>(td, ad, wd, idesc128);
+                        else umma_imm<true>(td, ad, wd, idesc128);
+                        umma_imm<true>(td, ad + 8, wd, idesc64);
+#pragma unroll
+                        for (int kk = 1; kk < BK / 16; ++kk) {
+                            umma_imm<true>(td, ad + kk * 32, wd + kk * 16, idesc128);
+                            umma_imm<true>(td, ad + kk * 32 + 8, wd + kk * 16, idesc64);
+                        }
+                        umma_commit(empty0 + 8 * slot);
+                        if (kb == PNKB - 1) umma_commit(accf0 + 8 * j);
+                        if (++slot == nslots) { slot = 0; phase ^= 1u; }
+                    }
+                    mstamp(t, j, 6);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int row = (warp & 3) * 32 + lane, jq = (warp >> 2) * 4;
+        const uint32_t tacc = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)jq;
+        float c[NT][4], h[NT][4];
+        int mylen[NT], rr[NT];
+        bool valid[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int nr = min((am.g0[j + 1] - am.g0[j]) * 8, R - am.g0[j] * 8);
+            rr[j] = am.g0[j] * 8 + row;
+            valid[j] = row < nr;
+            mylen[j] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[j][e] = h[j][e] = 0.f;
+            if (valid[j]) {
+                const size_t su = (size_t)rr[j] * H + u0 + jq;
+                mylen[j] = a.len[rr[j]];
+                if (a.c0) ld4r(a.c0 + su, c[j]);
+                if (a.h0) ld4r(a.h0 + su, h[j]);
+            }
+        }
+        for (int t = 0; t < a.T; ++t) {
+            uint8_t* hnext = (t & 1) ? a.hpk0 : a.hpk1;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int r = valid[j] ? rr[j] : 0;
+                const bool live = valid[j] && t < mylen[j];
+                float* grow = a.gates + ((size_t)t * R + r) * G4 + u0 + jq;
+                float zi[4], zj[4], zf[4], zo[4];
+                if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
+                if (tid == 0) mstamp(t, j, 7);
+                if (lane == 0) mbar_wait_bounded(accf0 + 8 * j, (uint32_t)(t & 1), err);
+                __syncwarp();
+                if (tid == 0) mstamp(t, j, 8);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                {
+                    const uint32_t tj = tacc + (uint32_t)(j * PTMEM);
+                    float ai[4], aj[4], af[4], ao[4];
+                    float bi[4], bj[4], bf[4], bo[4];
+                    tmem_ld4(tj, ai); tmem_ld4(tj + PUPT, aj); tmem_ld4(tj + 2 * PUPT, af); tmem_ld4(tj + 3 * PUPT, ao);
+                    tmem_ld4(tj + PBN, bi); tmem_ld4(tj + PBN + PUPT, bj); tmem_ld4(tj + PBN + 2 * PUPT, bf);
+                    tmem_ld4(tj + PBN + 3 * PUPT, bo);
+                    tmem_ld_wait();
+                    // the accumulator of tile j may be overwritten by the next step's products
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce0 + 8 * j);
+                    if (live) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            zi[e] = sigmoid_p(zi[e] + (ai[e] + bi[e]));
+                            zj[e] = tanh_p(zj[e] + (aj[e] + bj[e]));
+                            zf[e] = sigmoid_p(zf[e] + (af[e] + bf[e]) + a.forget_bias);
+                            zo[e] = sigmoid_p(zo[e] + (ao[e] + bo[e]));
+                            c[j][e] = c[j][e] * zf[e] + zi[e] * zj[e];
+                            h[j][e] = tanh_p(c[j][e]) * zo[e];
+                        }
+                    }
+                }
+                // Everything this step leaves in global memory is stored BEFORE the publish: a gpu-scope
+                // fence waits for every store the SM has in flight, so output stores issued by the other
+                // warps while the publishing thread sits in its fence would stretch the fence (measured:
+                // 10 k cycles).  The tile's chain has slack here - the other tiles' streams hide it.
+                if (tid == 0) mstamp(t, j, 9);
+                if (valid[j]) {
+                    if (t + 1 < a.T) store_packed4(hnext, a.mgp_h, rr[j], u0 + jq, h[j]);
+                    const size_t gu = ((size_t)t * R + rr[j]) * H + u0 + jq;
+                    st4r(a.cells + gu, c[j]);
+                    if (live) {
+                        st4r(grow, zi); st4r(grow + H, zj); st4r(grow + 2 * H, zf); st4r(grow + 3 * H, zo);
+                        st4r(a.Y + gu, h[j]);
+                    } else {
+                        *reinterpret_cast<float4*>(a.Y + gu) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                epi_bar_sync();
+                if (tid == 0) mstamp(t, j, 10);
+                if (tid == 0 && t + 1 < a.T) { __threadfence(); proxy_fence(); red_relaxed(a.sync + j, 1u); }
+                if (tid == 0) mstamp(t, j, 11);
+                if (tid == 0) mstamp(t, j, 12);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            if (valid[j]) {
+                const size_t su = (size_t)rr[j] * H + u0 + jq;
+                st4r(a.hT + su, h[j]);
+                st4r(a.cT + su, c[j]);
+            }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCOLS));
+}
+
 struct BwdArgs {
     const uint8_t* wtpk; int mgp_w;     // Op_B[n = hidden unit, k = gate column] = Wh[n, k]
     uint8_t* dzpk; int mgp_z;           // packed dZ: one step [R, 4H], or (full != 0) all steps [T*R, 4H]
@@ -629,10 +901,10 @@ int g_persist_mode = 1;   // 0 = per-step launches, 1 = persistent kernels where
 
 template <class Args>
 int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args,
-                int cluster_x = 1) {
+                int cluster_x = 1, int threads = PTHREADS) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(PTHREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -680,10 +952,36 @@ bool lstm_persist_supported(int R, int H) {
     return g_persist_mode != 0 && tc_available() && H == PH && R >= 1 && cdiv(R, BM) * PCOLS <= kNumSMs;
 }
 
+// Compact grid (32 CTAs walking all row tiles): more than one row tile and at most MT_MAX_TILES.
+bool lstm_persist_compact_supported(int R, int H) {
+    return lstm_persist_supported(R, H) && R > BM && cdiv(cdiv(R, 8), BM / 8) <= MT_MAX_TILES;
+}
+
+namespace {
+// balanced split of the 8-row groups over the fewest 128-row tiles
+int mt_partition(int R, int* g0) {
+    const int G = cdiv(R, 8), nt = cdiv(G, BM / 8);
+    const int base = G / nt, rem = G % nt;
+    g0[0] = 0;
+    for (int j = 0; j < nt; ++j) g0[j + 1] = g0[j] + base + (j < rem ? 1 : 0);
+    return nt;
+}
+template <int NT>
+int launch_fwd_mt(cudaStream_t st, const FwdMtArgs& am) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_mt_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)P_SMEM));
+        attr_set = true;
+    }
+    return launch_coop<FwdMtArgs>(lstm_persist_fwd_mt_kernel<NT>, dim3(PCOLS, 1), P_SMEM, st, am, 1, MT_THREADS);
+}
+}  // namespace
+
 // Recurrence phase of lstm_seq_fwd: gates already hold X*Wx + b.
 int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
                      const float* Wh, float forget_bias, float* Y, float* hT, float* cT, float* gates,
-                     float* cells) {
+                     float* cells, bool compact) {
     const int G4 = 4 * H;
     size_t off = 0;
     // R <= 32: no padding to 128-row tiles, so a row tile's 8 k-blocks are contiguous (one bulk copy)
@@ -708,6 +1006,16 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
         D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)P_SMEM));
         attr_set = true;
+    }
+    if (compact && lstm_persist_compact_supported(R, H)) {
+        FwdMtArgs am;
+        am.f = a;
+        am.nt = mt_partition(R, am.g0);
+        switch (am.nt) {
+            case 2: return launch_fwd_mt<2>(st, am);
+            case 3: return launch_fwd_mt<3>(st, am);
+            case 4: return launch_fwd_mt<4>(st, am);
+        }
     }
     return launch_coop<FwdArgs>(lstm_persist_fwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a);
 }

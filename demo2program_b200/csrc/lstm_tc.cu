@@ -34,7 +34,7 @@ int lstm_skinny_bwd_step(cudaStream_t, const float*, const float*, int, int, flo
 // persistent weight-stationary recurrences (lstm_persist.cu)
 bool lstm_persist_supported(int R, int H);
 int lstm_persist_fwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float,
-                     float*, float*, float*, float*, float*);
+                     float*, float*, float*, float*, float*, bool compact);
 int lstm_persist_bwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float*,
                      const float*, const float*, const float*, const float*, float*, float*, float*, const void**,
                      size_t*);
@@ -279,7 +279,8 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     size_t off = 0;
     if (lstm_persist_supported(R, H) && aligned16(Wh) && aligned16(gates) && aligned16(hT) && aligned16(cT) &&
         (!h0 || aligned16(h0)) && (!c0 || aligned16(c0)))
-        return lstm_persist_fwd(st, T, R, H, len, h0, c0, Wh, forget_bias, Y, hT, cT, gates, cells);
+        return lstm_persist_fwd(st, T, R, H, len, h0, c0, Wh, forget_bias, Y, hT, cT, gates, cells,
+                                (phases & D2P_LSTM_COMPACT) != 0);
     if (lstm_skinny_supported(R, H) && aligned16(Wh) && aligned16(hT) && aligned16(gates)) {
         // every CTA reads all of h_{t-1}: ping-pong between hT and a scratch copy
         float* hb[2] = {hT, (float*)tc_scratch_alloc(st, &off, RH * sizeof(float))};

@@ -16,6 +16,7 @@ model_summarizer.py:363-397, model_synthesis.py:325-358):
   loss = program + mean_k action + mean_k per.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -23,7 +24,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, FcBn, check, ptr
 from .manifest import build_manifests
-from .dp import allreduce_flat_gradients
+from .dp import BucketedAllReduce, allreduce_flat_gradients
 
 
 def _al(n, a=64):
@@ -36,13 +37,17 @@ class Engine:
 
     def __init__(self, cfg, device='cuda:0', seed=0, is_train=True,
                  frames_dtype=np.uint8, flat_params=None, flat_state=None,
-                 world_size=1, use_graph=True, use_tc=True, concurrent=True, token_tables=True):
+                 world_size=1, use_graph=True, use_tc=True, concurrent=True, token_tables=True,
+                 compact_decoders=True, overlap_allreduce=None):
         self.lib = _lib.load()
         # token_tables: the teacher-forced token decoders feed embedding rows, so their input
         # products have at most V+1 distinct rows: gates = (E*Wx + b)[token] in the forward,
         # dWx = E^T*S and dE = S*Wx^T from the per-token sums S of dZ in the backward, instead of
         # [T*R]-row products (same arithmetic, different association; False = row-by-row products)
         self.token_tables = bool(token_tables)
+        # compact_decoders: the action / perception decoder recurrences of `full` run in compact form
+        # (32 CTAs each) side by side with the program decoder instead of one after the other
+        self.compact_decoders = bool(compact_decoders)
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
                                 'fallback)')
@@ -92,6 +97,16 @@ class Engine:
         self._tc_bind()
         self._graph = None
         self._graph_key = None
+        # data parallelism: the flat gradient buffer is summed over the ranks in two pieces on a
+        # communication stream under the backward pass (dp.BucketedAllReduce), inside the step's
+        # CUDA graph.  overlap_allreduce=False (or D2P_DP_OVERLAP=0): one all-reduce of the whole
+        # buffer between a forward+backward graph and a clip+Adam graph.
+        if overlap_allreduce is None:
+            overlap_allreduce = os.environ.get('D2P_DP_OVERLAP', '1') != '0'
+        self.dp = None
+        self._dp_active = False
+        if self.world > 1 and overlap_allreduce and self.concurrent:
+            self.dp = BucketedAllReduce(self.grads, self.pm, self.world, self.dev)
 
     @property
     def ws(self):
@@ -263,7 +278,12 @@ class Engine:
     def _call(self, name, *args):
         check(getattr(self.lib, name)(*args), name)
 
-    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3):
+    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3, compact=False):
+        """compact: D2P_LSTM_COMPACT - the recurrence runs on a 32-CTA grid whose CTAs walk all row
+        tiles, so that independent recurrences share the GPU (the library falls back to one CTA per
+        row tile when the shape has a single tile)."""
+        if compact:
+            phases |= 8
         self._call('d2p_lstm_seq_fwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
                    ptr(self.P(scope + 'kernel')), ptr(self.P(scope + 'bias')), 1.0,
                    ptr(b['y']), ptr(b['hT']), ptr(b['cT']), ptr(b['gates']), ptr(b['cells']),
@@ -412,6 +432,10 @@ class Engine:
         self._stamp('fwd start')
         call('d2p_len_to_int', ptr(self.d_demo_len_f), ptr(self.d_demo_len), R, S())
         call('d2p_len_to_int', ptr(self.d_prog_len_f), ptr(self.d_prog_len), B, S())
+        if self.model == 'full':
+            # instance normalisers / run lengths shared by the action and per decoders
+            call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(self.act['w']),
+                 ptr(self.act['runlen']), S())
         # The decoders' hoisted input products (teacher-forced embeddings x Wx) do not depend
         # on the encoder: issue them on the side streams now, under the encoder recurrence.
         p = self.prog
@@ -490,7 +514,61 @@ class Engine:
                            'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec)
             self._stamp('second-path lstm fwd done')
             fin = self.sec
+        else:
+            fin = self.enc
+        self.fin = fin
+        full = self.model == 'full'
+        if full:
+            A, Pd = cfg.action_space, cfg.per_dim
+            a, q = self.act, self.per
+            side_by_side = self.concurrent and self.compact_decoders
 
+            def act_fwd():
+                self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                               'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=2, compact=side_by_side)
+                Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
+                self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
+                call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
+                     ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
+                     ptr(self.loss[2:]), 0, S())
+                self._stamp('action decoder fwd done')
+
+            def per_fwd():
+                self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                               'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, phases=2, compact=side_by_side)
+                Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
+                self._gemm(0, 0, T * R, Pd, H, 1.0, q['y'], H, Wq, Pd, 0.0, q['logits'], Pd)
+                call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
+                     ptr(a['runlen']), ptr(a['w']), ptr(q['rowloss']), ptr(q['dlogits']),
+                     ptr(self.loss[3:]), 0, S())
+                self._stamp('per decoder fwd done')
+
+            # The action and perception decoders (forward AND backward) depend only on the second-path
+            # final states - not on the summary pools or the program decoder.  Their chain (two k*B-row
+            # recurrences forward, two backward) is as long as pools -> program decoder forward ->
+            # backward -> pools backward, so it forks HERE, on side stream 1, and is joined in the
+            # backward pass where the three initial-state gradients meet.  Forward: in compact form
+            # (32 CTAs each) the two recurrences run side by side (side streams 1 and 2) and leave 84
+            # SMs to the pools and the 32-CTA program decoder; otherwise they are chained (two 96-CTA
+            # cooperative grids cannot be resident together).
+            if self.concurrent:
+                main = torch.cuda.current_stream(self.dev)
+                ev_fin = torch.cuda.Event()
+                ev_fin.record(main)
+                s1, s2 = self.side_streams[:2]
+                s1.wait_event(ev_fin)
+                if side_by_side:
+                    s2.wait_event(ev_fin)
+                    with torch.cuda.stream(s1):
+                        act_fwd()
+                    with torch.cuda.stream(s2):     # per_in ran on side stream 2 (stream order)
+                        per_fwd()
+                else:
+                    with torch.cuda.stream(s1):
+                        act_fwd()
+                        s1.wait_stream(s2)          # the per decoder's hoisted input product
+                        per_fwd()
+        if self.model in ('full', 'summarizer'):
             def pool(s, out, saved):
                 def run():
                     call('d2p_rn_pool_fwd', ptr(fin[s + 'T']), B, k, H, C.byref(self.fc[(s, 'fc1')]),
@@ -500,15 +578,10 @@ class Engine:
                         call('d2p_group_sum', ptr(fin[s + 'T']), B, k, H, 1.0 / k, ptr(out), 1, S())
                 return run
             self._parallel([pool('h', self.dsum_h, self.rn_saved_h),
-                            pool('c', self.dsum_c, self.rn_saved_c)])
+                            pool('c', self.dsum_c, self.rn_saved_c)], streams=self.side_streams[2:])
             self._stamp('pools fwd done')
         else:
-            if cfg.demo_aggregation != 'avgpool':
-                raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
-            fin = self.enc
-            call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, S())
-            call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, S())
-        self.fin = fin
+            self._aggregate_fwd(fin)
 
         def prog_fwd():   # program decoder (teacher forcing)
             call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), S())
@@ -523,50 +596,37 @@ class Engine:
                  ptr(self.loss[1:]), 0, S())
             self._stamp('program decoder fwd done')
 
-        if self.model != 'full':
-            prog_fwd()
+        prog_fwd()
+        if not full:
             if self.concurrent:
                 torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[0])
             call('d2p_axpby', ptr(self.loss[1:]), 1.0, ptr(self.loss), 0.0, 1, S())
             return
-        A, Pd = cfg.action_space, cfg.per_dim
-        a, q = self.act, self.per
-        # instance normalisers / run lengths shared by the action and per decoders
-        call('d2p_seq_weights', ptr(self.d_demo_len), R, k, 1.0 / k, T, ptr(a['w']), ptr(a['runlen']), S())
-
-        def act_fwd():
-            self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=2)
-            Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
-            call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
-                 ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
-                 ptr(self.loss[2:]), 0, S())
-            self._stamp('action decoder fwd done')
-
-        def per_fwd():
-            self._lstm_fwd(q['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                           'Per_Decoder/dynamic_decoder/basic_lstm_cell/', q, phases=2)
-            Wq = self.P('Per_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(0, 0, T * R, Pd, H, 1.0, q['y'], H, Wq, Pd, 0.0, q['logits'], Pd)
-            call('d2p_sigmoid_ce', ptr(q['logits']), T, R, Pd, ptr(self.d_per), ptr(self.d_demo_len),
-                 ptr(a['runlen']), ptr(a['w']), ptr(q['rowloss']), ptr(q['dlogits']),
-                 ptr(self.loss[3:]), 0, S())
-            self._stamp('per decoder fwd done')
-
-        # The two k*B-row decoders are persistent kernels of 96 CTAs each: they cannot be
-        # resident together, and a half-placed second one would only hold the SMs the
-        # 32-CTA program decoder needs.  Chain them on one stream next to the program decoder.
-        def act_then_per():
+        if not self.concurrent:
             act_fwd()
-            if self.concurrent:   # the per decoder's hoisted input product ran on side stream 2
-                torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[1])
             per_fwd()
         self._fwd_open = bool(open_tail and self.concurrent)
-        self._parallel([prog_fwd, act_then_per], join=not self._fwd_open)
         self._stamp('fwd done')
         if not self._fwd_open:
+            self._join_act_per()
             self._total_loss()
+
+    def _join_act_per(self):
+        """Joins the action / per decoder branch (side streams 1 and 2) into the current stream."""
+        if self.concurrent:
+            main = torch.cuda.current_stream(self.dev)
+            main.wait_stream(self.side_streams[0])
+            main.wait_stream(self.side_streams[1])
+
+    def _aggregate_fwd(self, fin):
+        """synthesis_baseline: demo_aggregation over the k per-demonstration final states."""
+        cfg = self.cfg
+        B, k, H = self.B, self.k, self.H
+        call, S = self._call, self._st
+        if cfg.demo_aggregation != 'avgpool':
+            raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
+        call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, S())
+        call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, S())
 
     def _total_loss(self):
         """total = program + action + per"""
@@ -683,12 +743,22 @@ class Engine:
 
             def act_then_per_bwd():
                 act_bwd()
+                if self.concurrent:   # the per decoder's forward may still run on side stream 2
+                    torch.cuda.current_stream(self.dev).wait_stream(self.side_streams[1])
                 per_bwd()
-            self._parallel([prog_then_pools, act_then_per_bwd])
-            if getattr(self, '_fwd_open', False):   # the forward's action / per decoders are joined now
+            if getattr(self, '_fwd_open', False):
+                # the action / per branch forked in the forward pass (side stream 1) simply continues
+                # with its backward - it never waits for the program decoder; joined below
+                with torch.cuda.stream(self.side_streams[0]):
+                    act_then_per_bwd()
+                prog_then_pools()
+                self._join_act_per()
                 self._total_loss()
                 self._fwd_open = False
+            else:
+                self._parallel([prog_then_pools, act_then_per_bwd])
             self._stamp('decoders + pools bwd joined')
+            self._reduce_bucket(0)
             # dh2 = d(action init) + d(per init) + d(pools)
             call('d2p_add3', ptr(a['dh0']), ptr(q['dh0']), ptr(self.pool_dh), ptr(self.dh2), R * H, S())
             call('d2p_add3', ptr(a['dc0']), ptr(q['dc0']), ptr(self.pool_dc), ptr(self.dc2), R * H, S())
@@ -697,6 +767,7 @@ class Engine:
             if self.model == 'summarizer':
                 self._parallel([pool_bwd('h', p['dh0'], self.rn_saved_h, self.dh2),
                                 pool_bwd('c', p['dc0'], self.rn_saved_c, self.dc2)])
+            self._reduce_bucket(0)
         if self.model in ('full', 'summarizer'):
             sec = self.sec
             self._lstm_bwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
@@ -724,13 +795,26 @@ class Engine:
             for gs in self.grad_streams:
                 torch.cuda.current_stream(self.dev).wait_stream(gs)
         self._stamp('bwd done (weight-gradient stream joined)')
+        self._reduce_bucket(1)
+
+    def _reduce_bucket(self, b):
+        """Data parallelism: everything that writes gradient bucket b has been enqueued (on this
+        stream and the gradient streams) - sum it over the ranks on the communication stream."""
+        if self.dp is not None and self._dp_active:
+            self.dp.reduce(b, [torch.cuda.current_stream(self.dev)] + self.grad_streams)
+            if getattr(self, 'timeline', None) is not None:
+                with torch.cuda.stream(self.dp.comm):
+                    self._stamp('gradient bucket %d summed over the ranks' % b)
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
         """clip_by_global_norm(20) + Adam (reference trainer.py:102-109); the
         gradient is first averaged over ranks with ONE all-reduce of the flat
         buffer when world_size > 1."""
-        scale = allreduce_flat_gradients(self.grads, self.world)
+        if self.dp is not None and self.dp.reduced:     # the backward pass reduced the buckets
+            scale = self.dp.join(torch.cuda.current_stream(self.dev))
+        else:
+            scale = allreduce_flat_gradients(self.grads, self.world)
         decay = 10000 if self.cfg.lr_weight_decay else 0
         self._call('d2p_clip_adam_step', ptr(self.params), ptr(self.grads), ptr(self.adam_m),
                    ptr(self.adam_v), self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip,
@@ -740,6 +824,7 @@ class Engine:
 
     # ------------------------------------------------------------------ steps
     def _step_body(self, with_opt):
+        self._dp_active = bool(with_opt)      # gradient buckets are reduced only when an update follows
         if self.main_stream is None:
             self.forward()
             self.backward()
@@ -800,11 +885,13 @@ class Engine:
         if self._graph is None or self._graph_key != key:
             snap = [t.clone() for t in (self.params, self.state, self.adam_m, self.adam_v,
                                         self.adam_state)]
-            if self.world > 1:
+            if self.world > 1 and (self.dp is None or not with_opt):
                 g1, n1 = self._capture(lambda: self._step_body(False))
                 g2, n2 = self._capture(lambda: self._adam_only(1.0 / self.world))
                 self._graph, self.launches_per_step = (g1, g2), n1 + n2
             else:
+                # one graph for the whole step; with data parallelism the bucketed NCCL all-reduces
+                # are nodes of that graph (communication stream forked from / joined into the step)
                 g, n = self._capture(lambda: self._step_body(with_opt))
                 self._graph, self.launches_per_step = g, n
             for t, sv in zip((self.params, self.state, self.adam_m, self.adam_v, self.adam_state),
@@ -812,13 +899,20 @@ class Engine:
                 t.copy_(sv)
             torch.cuda.synchronize(self.dev)
             self._graph_key = key
-        if self.world > 1:
+        if isinstance(self._graph, tuple):
             self._graph[0].replay()
             if with_opt:
                 allreduce_flat_gradients(self.grads, self.world)
                 self._graph[1].replay()
         else:
             self._graph.replay()
+
+    def close(self):
+        """Drops the captured CUDA graphs (with data parallelism they hold NCCL nodes: release them
+        before torch.distributed.destroy_process_group, which otherwise may not return)."""
+        torch.cuda.synchronize(self.dev)
+        self._graph = None
+        self._graph_key = None
 
     def check_device(self):
         """Fail loudly if a step barrier of a persistent kernel timed out (d2p_device_error):

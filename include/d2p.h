@@ -94,6 +94,8 @@ enum { D2P_LSTM_INPUT = 1,      /* gates = X*Wx + b for all steps (independent o
        D2P_LSTM_RECUR = 2,      /* the recurrence over T steps */
        D2P_LSTM_BWD_RECUR = 1,  /* BPTT recurrence + dX, dh0, dc0 */
        D2P_LSTM_BWD_PARAMS = 2, /* dW, db from the dZ left in `gates` by the recurrence phase */
+       D2P_LSTM_COMPACT = 8,    /* (fwd and bwd recurrence) 32-CTA grid: every CTA walks all row tiles, so that
+                                 * independent recurrences (action / perception / program decoders) share the GPU */
        D2P_LSTM_BWD_NO_DWX = 4  /* with BWD_PARAMS: leave the input-weight rows dW[0:In] alone (X is not read).
                                  * For a teacher-forced token decoder (X = embedding rows, reference
                                  * models/model_full.py:440-471) the caller forms dWx = E^T * S and

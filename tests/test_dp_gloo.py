@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 from demo2program_b200.config import karel_config
 from demo2program_b200.manifest import build_manifests
 from demo2program_b200.synthetic import make_batch
-from demo2program_b200.dp import allreduce_flat_gradients, shard_seed
+from demo2program_b200.dp import BucketedAllReduce, allreduce_flat_gradients, gradient_buckets, shard_seed
 
 
 def _free_port():
@@ -36,6 +36,12 @@ def _worker(rank, world, port, q):
     local = grad.clone()
     scale = allreduce_flat_gradients(grad, world)       # in-place SUM, returns 1/world
     avg = grad * scale
+    # the same sum, bucket by bucket in completion order (what Engine issues under the backward pass)
+    piece = local.clone()
+    dp = BucketedAllReduce(piece, pm, world)
+    for b in range(len(dp.buckets)):
+        dp.reduce(b)
+    assert dp.join() == scale and torch.equal(piece, grad)
     q.put((rank, float(loss), local.numpy(), avg.numpy()))
     dist.destroy_process_group()
 
@@ -56,3 +62,21 @@ def test_two_rank_flat_gradient_allreduce():
 
 def test_shard_seeds_are_distinct():
     assert len({shard_seed(123, r) for r in range(8)}) == 8
+
+
+def test_gradient_buckets_partition_the_flat_buffer():
+    """Every element of the flat gradient buffer is in exactly one bucket range; the demonstration
+    and second-path encoders form the last bucket (completion order of the backward pass)."""
+    for model in ('full', 'summarizer', 'synthesis_baseline', 'induction_baseline'):
+        pm, _ = build_manifests(karel_config(model, batch_size=4, k=3))
+        buckets = gradient_buckets(pm)
+        cover = np.zeros(pm.total, np.int32)
+        for r in buckets:
+            for lo, hi in r:
+                cover[lo:hi] += 1
+        assert (cover == 1).all()
+        e = pm['Demo_Encoder/rnn/basic_lstm_cell/kernel']
+        assert any(lo <= e.offset < hi for lo, hi in buckets[-1])
+        if model in ('full', 'summarizer'):
+            e = pm['SecondPathEncoder/rnn/basic_lstm_cell/kernel']
+            assert any(lo <= e.offset < hi for lo, hi in buckets[1])

@@ -24,7 +24,7 @@ def test_two_rank_nccl_step_matches_averaged_gradient_oracle():
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
            os.path.join(ROOT, 'tools', 'dp_check.py')]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(lines[-1])
