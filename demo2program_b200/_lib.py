@@ -94,6 +94,8 @@ SIGNATURES = {
     'd2p_rn_pool_bwd_hold_floats': (_sz, [_i, _i, _i]),
     'd2p_group_sum': (_i, [_fp, _i, _i, _i, _f, _fp, _i, _fp]),
     'd2p_group_bcast': (_i, [_fp, _i, _i, _i, _f, _fp, _i, _fp]),
+    'd2p_group_max': (_i, [_fp, _i, _i, _i, _fp, _fp, _fp]),
+    'd2p_group_max_bwd': (_i, [_fp, _fp, _i, _i, _i, _fp, _fp]),
     'd2p_axpby': (_i, [_fp, _f, _fp, _f, _sz, _fp]),
     'd2p_add3': (_i, [_fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_logits_to_bvl': (_i, [_fp, _i, _i, _i, _fp, _fp]),

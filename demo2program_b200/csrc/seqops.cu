@@ -203,6 +203,33 @@ __global__ void group_bcast_kernel(const float* __restrict__ S, int B, int k, in
     out[idx] = (accumulate ? out[idx] : 0.f) + alpha * S[(size_t)b * H + u];
 }
 
+// out[b,u] = max_i F[b,i,u] (lowest i among equal maxima), arg[b,u] = that i
+__global__ void group_max_kernel(const float* __restrict__ F, int B, int k, int H, float* __restrict__ out,
+                                 int* __restrict__ arg) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    int b = idx / H, u = idx % H;
+    float m = F[(size_t)b * k * H + u];
+    int am = 0;
+    for (int i = 1; i < k; ++i) {
+        const float v = F[((size_t)b * k + i) * H + u];
+        if (v > m) { m = v; am = i; }
+    }
+    out[idx] = m;
+    arg[idx] = am;
+}
+
+// dF[b,i,u] = (i == arg[b,u]) ? dout[b,u] : 0
+__global__ void group_max_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, int B, int k,
+                                     int H, float* __restrict__ dF) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * k * H) return;
+    int u = (int)(idx % H);
+    int i = (int)((idx / H) % k), b = (int)(idx / ((size_t)k * H));
+    const size_t o = (size_t)b * H + u;
+    dF[idx] = arg[o] == i ? dout[o] : 0.f;
+}
+
 // y = alpha*x + beta*y
 __global__ void axpby_kernel(const float* __restrict__ x, float alpha, float* __restrict__ y,
                              float beta, size_t n) {
@@ -350,6 +377,21 @@ extern "C" int d2p_group_bcast(const float* S, int B, int k, int H, float alpha,
     D2P_REQUIRE(S && out, "group_bcast: null buffer");
     group_bcast_kernel<<<cdiv((long long)B * k * H, 256), 256, 0, (cudaStream_t)stream>>>(
         S, B, k, H, alpha, out, accumulate);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_group_max(const float* F, int B, int k, int H, float* out, int* arg, void* stream) {
+    D2P_REQUIRE(F && out && arg, "group_max: null buffer");
+    D2P_REQUIRE(B > 0 && k > 0 && H > 0, "group_max: empty shape");
+    group_max_kernel<<<cdiv((long long)B * H, 256), 256, 0, (cudaStream_t)stream>>>(F, B, k, H, out, arg);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int d2p_group_max_bwd(const float* dout, const int* arg, int B, int k, int H, float* dF, void* stream) {
+    D2P_REQUIRE(dout && arg && dF, "group_max_bwd: null buffer");
+    group_max_bwd_kernel<<<cdiv((long long)B * k * H, 256), 256, 0, (cudaStream_t)stream>>>(dout, arg, B, k, H, dF);
     D2P_CHECK_LAUNCH();
     return 0;
 }

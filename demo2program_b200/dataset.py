@@ -313,14 +313,15 @@ def _collate_job(job):
     return slot, meta, b
 
 
-def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None, workers=0, lookahead=4):
+def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None, workers=0, lookahead=4, rank=0, world=1):
     """Deterministic replacement of string_input_producer + shuffle_batch (reference
     karel_env/input_ops_karel.py:24-125 uses 16 loader threads and an unordered queue).  The
     per-example work is Python-bound (~0.6 ms), so `workers` > 0 assembles batches in forked
     loader PROCESSES (the memory-mapped HDF5 file is shared read-only; the large arrays come back
-    through anonymous shared mappings) and still delivers them in the seeded order."""
+    through anonymous shared mappings) and still delivers them in the seeded order.
+    rank / world: the ids are sharded ids[rank::world] before batching."""
     r = np.random.RandomState(seed)
-    ids = list(dataset.ids)
+    ids = list(dataset.ids)[rank::world]      # data parallelism: every rank owns a disjoint shard of the ids
     if len(ids) < batch_size:
         # (a generator: the error surfaces at the first next(), before any step is attempted)
         raise ValueError('dataset split has %d examples, fewer than batch_size=%d: no full batch can '

@@ -619,14 +619,41 @@ class Engine:
             main.wait_stream(self.side_streams[1])
 
     def _aggregate_fwd(self, fin):
-        """synthesis_baseline: demo_aggregation over the k per-demonstration final states."""
+        """synthesis_baseline: demo_aggregation over the k per-demonstration final states (reference
+        models/baselines/model_synthesis.py:336-358).  'concat' hands a [B, k*H] state to a
+        BasicLSTMCell of H units - the reference graph only builds for k == 1, where it is the
+        identity; the same restriction applies here."""
         cfg = self.cfg
         B, k, H = self.B, self.k, self.H
         call, S = self._call, self._st
-        if cfg.demo_aggregation != 'avgpool':
-            raise NotImplementedError('demo_aggregation=%s' % cfg.demo_aggregation)
-        call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, S())
-        call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, S())
+        agg = cfg.demo_aggregation
+        if agg == 'concat':
+            if k != 1:
+                raise ValueError("demo_aggregation='concat' gives the decoder a [B, k*H] initial state; the "
+                                 "reference's BasicLSTMCell(H) cannot take it either - use k == 1, avgpool or maxpool")
+            agg = 'avgpool'
+        if agg == 'avgpool':
+            call('d2p_group_sum', ptr(fin['hT']), B, k, H, 1.0 / k, ptr(self.dsum_h), 0, S())
+            call('d2p_group_sum', ptr(fin['cT']), B, k, H, 1.0 / k, ptr(self.dsum_c), 0, S())
+        elif agg == 'maxpool':
+            if not hasattr(self, 'agg_arg_h'):
+                self.agg_arg_h = torch.zeros(B, H, dtype=torch.int32, device=self.dev)
+                self.agg_arg_c = torch.zeros(B, H, dtype=torch.int32, device=self.dev)
+            call('d2p_group_max', ptr(fin['hT']), B, k, H, ptr(self.dsum_h), ptr(self.agg_arg_h), S())
+            call('d2p_group_max', ptr(fin['cT']), B, k, H, ptr(self.dsum_c), ptr(self.agg_arg_c), S())
+        else:
+            raise ValueError('Unknown demo aggregation type: %s' % agg)
+
+    def _aggregate_bwd(self, dh, dc):
+        """Gradient of _aggregate_fwd wrt the per-demonstration final states -> self.dh2 / self.dc2."""
+        B, k, H = self.B, self.k, self.H
+        call, S = self._call, self._st
+        if self.cfg.demo_aggregation == 'maxpool':
+            call('d2p_group_max_bwd', ptr(dh), ptr(self.agg_arg_h), B, k, H, ptr(self.dh2), S())
+            call('d2p_group_max_bwd', ptr(dc), ptr(self.agg_arg_c), B, k, H, ptr(self.dc2), S())
+        else:
+            call('d2p_group_bcast', ptr(dh), B, k, H, 1.0 / k, ptr(self.dh2), 0, S())
+            call('d2p_group_bcast', ptr(dc), B, k, H, 1.0 / k, ptr(self.dc2), 0, S())
 
     def _total_loss(self):
         """total = program + action + per"""
@@ -781,8 +808,7 @@ class Engine:
             call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0 / k, ptr(self.dc2), 0, S())
             dY1 = self.dy1
         else:
-            call('d2p_group_bcast', ptr(p['dh0']), B, k, H, 1.0 / k, ptr(self.dh2), 0, S())
-            call('d2p_group_bcast', ptr(p['dc0']), B, k, H, 1.0 / k, ptr(self.dc2), 0, S())
+            self._aggregate_bwd(p['dh0'], p['dc0'])
             dY1 = None
         self._lstm_bwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, dY1, self.dh2, self.dc2,

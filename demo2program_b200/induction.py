@@ -241,9 +241,23 @@ class InductionModel(object):
         self.loss = float(eng.loss[0])
         self.report_loss = {'avg_action_loss': self.loss}
         self.output = [np.asarray(feed['test_a_h']), pred.cpu().numpy()]
+        # report surface of models/baselines/model_induction.py:788-862
+        from .metrics import demo_sequence_stats
+        B, tk, T = eng.B, eng.tk, eng.T
+        t_tok = torch.as_tensor(np.asarray(feed['test_a_h_tokens'])).long().to(eng.dev).view(B, tk, T)
+        t_len = torch.as_tensor(np.asarray(feed['test_demo_len'])).long().to(eng.dev).view(B, tk)
+        st = demo_sequence_stats(pred, t_tok, t_len, t_len)
+        self.report_accuracy = {'avg_action_token_acc': st['token_acc'], 'avg_action_seq_acc': st['seq_acc'],
+                                'avg_action_seq_all_acc': st['seq_all_acc']}
+        self.report_hist = {}
         if greedy:
             g, gl = eng.greedy()
             self.greedy_pred_action, self.greedy_pred_action_len = g.cpu().numpy(), gl.cpu().numpy()
+            gst = demo_sequence_stats(g, t_tok, gl.long(), t_len)
+            self.report_loss['greedy_avg_action_loss'] = gst['loss']
+            self.report_accuracy.update({'greedy_avg_action_token_acc': gst['token_acc'],
+                                         'greedy_avg_action_seq_acc': gst['seq_acc'],
+                                         'greedy_avg_action_seq_all_acc': gst['seq_all_acc']})
         return self.loss
 
     def state_dict(self):

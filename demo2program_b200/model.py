@@ -19,6 +19,7 @@ import torch
 
 from .config import D2PConfig, MODEL_NAMES
 from .engine import Engine
+from .metrics import demo_sequence_stats, sequence_stats
 
 FEED_KEYS = ('id', 'program', 'program_tokens', 's_h', 'a_h', 'a_h_tokens', 'program_len',
              'demo_len', 'test_s_h', 'test_demo_len', 'per', 'test_per')
@@ -46,16 +47,8 @@ def config_from_namespace(ns):
 def _seq_stats(logits_bvl, gt_tokens, pred_len, gt_len):
     """token / sequence accuracy of Sequence_Loss (reference models/model_full.py:660-683).
     logits [B,V,L]; gt_tokens [B,L]; lengths [B]."""
-    B, V, L = logits_bvl.shape
-    pred = logits_bvl.argmax(1)
-    ar = torch.arange(L, device=pred.device)[None]
-    gt_mask = (ar < gt_len[:, None]).float()
-    max_mask = (ar < torch.maximum(pred_len, gt_len)[:, None]).float()
-    min_mask = (ar < torch.minimum(pred_len, gt_len)[:, None]).float()
-    eq = (pred == gt_tokens).float()
-    token_acc = float((eq * min_mask).sum() / max_mask.sum().clamp(min=1))
-    seq_eq = ((pred.float() * gt_mask) == (gt_tokens.float() * gt_mask)).all(1) & (pred_len == gt_len)
-    return token_acc, float(seq_eq.float().mean()), pred, seq_eq
+    st = sequence_stats(logits_bvl, gt_tokens, pred_len, gt_len)
+    return st['token_acc'], st['seq_acc'], st['pred_tokens'], st['is_same_seq']
 
 
 def _acc_hist(num_correct, k):
@@ -93,6 +86,13 @@ class Model(object):
         self.loss = self.engine.train_step(feed)
         return self.loss
 
+    def run_train_steps(self, feeds):
+        """Training loop over an iterable of feed dicts through the engine's pipelined input path
+        (Engine.train_steps): yields every step's loss, one step behind the device."""
+        for loss in self.engine.train_steps(feeds):
+            self.loss = loss
+            yield loss
+
     def _common_outputs(self, feed, greedy):
         eng, cfg = self.engine, self.config
         dev = eng.dev
@@ -110,15 +110,36 @@ class Model(object):
                                 'program_syntax_acc': float('nan'),
                                 'pred_exact_program_accuracy': float('nan')}
         if cfg.model == 'full':
+            # teacher-forced action decoders (models/model_full.py:1014-1036): statistics per
+            # demonstration, averaged over the k demonstrations
+            B, k, T, A = eng.B, eng.k, eng.T, cfg.action_space
+            a_tok = torch.as_tensor(np.asarray(feed['a_h_tokens'])).long().to(dev).view(B, k, T)
+            a_len = torch.as_tensor(np.asarray(feed['demo_len'])).long().to(dev).view(B, k)
+            pa = eng.act['logits'].view(T, B, k, A).permute(1, 2, 0, 3)
+            ast = demo_sequence_stats(pa, a_tok, a_len, a_len)
+            self.pred_action = pa.contiguous().cpu().numpy()
             self.report_loss['avg_action_loss'] = float(losses[2])
+            self.report_accuracy['avg_action_token_acc'] = ast['token_acc']
+            self.report_accuracy['avg_action_seq_acc'] = ast['seq_acc']
         if greedy:
             gp, glen, _ = eng.greedy_program()
-            gt, gs, gtok, gsame = _seq_stats(gp, gt_tok, glen[:, 0].long(), gt_len)
+            gst = sequence_stats(gp, gt_tok, glen[:, 0].long(), gt_len)
+            gtok, gsame = gst['pred_tokens'], gst['is_same_seq']
             self.greedy_pred_program = gp.cpu().numpy()
             self.greedy_pred_program_len = glen.cpu().numpy()
-            self.report_accuracy.update({'greedy_program_token_acc': gt, 'greedy_program_seq_acc': gs,
+            self.report_loss['greedy_program_loss'] = gst['loss']
+            self.report_accuracy.update({'greedy_program_token_acc': gst['token_acc'],
+                                         'greedy_program_seq_acc': gst['seq_acc'],
                                          'greedy_program_syntax_acc': float('nan'),
                                          'greedy_exact_program_accuracy': float('nan')})
+            if cfg.model == 'full':     # models/model_full.py:1038-1058
+                ga, galen = eng.greedy_actions()
+                gast = demo_sequence_stats(ga, a_tok, galen.long(), a_len)
+                self.greedy_pred_action = ga.cpu().numpy()
+                self.greedy_pred_action_len = galen.cpu().numpy()
+                self.report_loss['greedy_avg_action_loss'] = gast['loss']
+                self.report_accuracy['greedy_avg_action_token_acc'] = gast['token_acc']
+                self.report_accuracy['greedy_avg_action_seq_acc'] = gast['seq_acc']
         self.report_hist = {}
         self.output = [self.ground_truth_program, self.pred_program]
         if cfg.dataset_type == 'karel':

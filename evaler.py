@@ -2,8 +2,10 @@
 """Evaluation driver with the reference's CLI (reference evaler.py:362-495):
 restores a checkpoint, runs `max_steps` batches with is_train=False (BatchNorm on
 moving statistics, evaler.py:61), aggregates report_loss / report_accuracy and
-prints / writes the final report (evaler.py:292-359).  Program dumps
-(`--pred_program`) write predicted and ground-truth token strings."""
+prints / writes the final report incl. the execution-accuracy histograms (evaler.py:292-359).
+`--pred_program` writes out_<checkpoint>_<split>.{txt,hdf5,log} and `--result_data` the per-example
+result file, like evaler.py:151-208 (HDF5 through hdf5_lite.write_hdf5).  `--id_list` and
+`--unseen_test` are accepted and unused, exactly as in the reference (it never reads them)."""
 import argparse
 import glob
 import logging
@@ -53,34 +55,113 @@ class Evaler(object):
             log.warning("No checkpoint given: evaluating the initial parameters")
 
     def eval_run(self):
-        max_steps = self.config.max_steps
-        loss_all, acc_all, time_all = [], [], 0.0
-        vocab = None
-        if self.config.pred_program and self.output_dir:
+        """reference evaler.py:96-248: per-batch report, optional dumps (`--pred_program`: text /
+        HDF5 / log files named out_<checkpoint>_<split>.*; `--result_data`: one HDF5 group per
+        example with the ground-truth and greedy programs and the demonstrations), final averages of
+        losses, accuracies and execution histograms."""
+        cfg = self.config
+        max_steps = cfg.max_steps
+        if max_steps <= 0:
+            raise ValueError('nothing to evaluate: max_steps = len(split) // batch_size = 0 '
+                             '(%d examples, batch_size %d)' % (len(self.dataset), self.batch_size))
+        model_is_program = cfg.model != 'induction_baseline'
+        vocab = text_file = log_file = None
+        pred_tree, result_tree = {}, {}
+        if cfg.pred_program and model_is_program:
+            if not self.output_dir:
+                raise ValueError('--pred_program needs --output_dir')
+            if getattr(cfg, 'dataset_type', 'karel') != 'karel':
+                raise ValueError('--pred_program: only the Karel vocabulary is available offline')
             from demo2program_b200.vocab import karel_vocab
             vocab = karel_vocab()
             os.makedirs(self.output_dir, exist_ok=True)
+            base_name = os.path.join(self.output_dir, 'out_{}_{}'.format(
+                os.path.basename(self.checkpoint) if self.checkpoint else 'init',
+                getattr(cfg, 'dataset_split', 'test')))
+            log.info("Output Dir: %s", self.output_dir)
+            text_file = open('{}.txt'.format(base_name), 'w')
+            log_file = open('{}.log'.format(base_name), 'w')
+        final_msg = ''
+        loss_all, acc_all, hist_all, time_all = [], [], {}, []
+        loss = acc = {}
         for s in range(max_steps):
             step_time, loss, acc, hist, feed = self.run_single_step(self.batch)
-            loss_all.append(loss); acc_all.append(acc); time_all += step_time
-            if not self.config.quiet:
-                self.log_step_message(s, loss, acc, hist, step_time)
-            if vocab is not None and self.model.greedy_pred_program is not None:
-                with open(os.path.join(self.output_dir, 'out_%d.txt' % s), 'w') as f:
-                    pred = self.model.greedy_pred_program.argmax(1)
-                    for b in range(pred.shape[0]):
-                        n = int(self.model.greedy_pred_program_len[b, 0])
-                        g = int(self.model.program_len[b, 0])
-                        f.write('[pred] %s\n[gt]   %s\n' % (
-                            vocab.intseq2str(pred[b, :n]),
-                            vocab.intseq2str(np.asarray(feed['program_tokens'])[b, :g])))
-        lk, ak = sorted(loss_all[0]), sorted(acc_all[0])
-        avg_loss = [float(np.mean([l[k] for l in loss_all])) for k in lk]
-        avg_acc = [float(np.nanmean([a[k] for a in acc_all])) if not all(
-            np.isnan(a[k]) for a in acc_all) else float('nan') for k in ak]
-        self.log_final_message(avg_loss, lk, avg_acc, ak, {}, [], time_all,
-                               write_summary=self.config.write_summary,
-                               summary_file=self.config.summary_file)
+            m = self.model
+            step_msg = ''
+            if not cfg.quiet:
+                step_msg = self.log_step_message(s, loss, acc, hist, step_time)
+            ids = [i.decode() if isinstance(i, bytes) else str(i) for i in np.asarray(feed['id']).reshape(-1)]
+            if cfg.result_data and model_is_program:
+                for i, pid in enumerate(ids):
+                    if pid in result_tree:
+                        print('Duplicates: {}'.format(pid))
+                        continue
+                    result_tree[pid] = {
+                        'program': np.asarray(m.ground_truth_program[i]),
+                        'pred_program': np.asarray(m.greedy_pred_program[i]),
+                        'pred_program_len': np.int64(m.greedy_pred_program_len[i][0]),
+                        # the reference re-reads the stored demonstrations (unpadded, all demos of
+                        # the program); the batch holds the same frames padded to max_demo_len
+                        's_h': self._stored(pid, 's_h', feed['s_h'][i]),
+                        'test_s_h': self._stored(pid, 'test_s_h', feed['test_s_h'][i])}
+            if vocab is not None:
+                log_file.write('{}\n'.format(step_msg))
+                correctness = ['wrong', 'correct']
+                gt_tokens = np.asarray(feed['program_tokens'])
+                for i, pid in enumerate(ids):
+                    n, g = int(m.program_len[i, 0]), int(m.greedy_pred_program_len[i, 0])
+                    pred_str = vocab.intseq2str(m.pred_program[i, :, :n].argmax(0))
+                    greedy_str = vocab.intseq2str(m.greedy_pred_program[i, :, :g].argmax(0))
+                    have = len(m.program_is_correct_syntax) > 0
+                    psyn = int(m.program_is_correct_syntax[i]) if have else 0
+                    gsyn = int(m.greedy_program_is_correct_syntax[i]) if have else 0
+                    if pid not in pred_tree:
+                        grp = {'program_prediction': pred_str, 'program_syntax': correctness[psyn],
+                               'greedy_prediction': greedy_str, 'greedy_syntax': correctness[gsyn]}
+                        if have:
+                            grp.update({
+                                'program_num_execution_correct': np.int64(m.program_num_execution_correct[i]),
+                                'program_is_correct_execution': np.asarray(m.program_is_correct_execution[i]),
+                                'greedy_num_execution_correct': np.int64(m.greedy_num_execution_correct[i]),
+                                'greedy_is_correct_execution': np.asarray(m.greedy_is_correct_execution[i])})
+                        pred_tree[pid] = grp
+                    text_file.write('[id: {}]\ngt: {}\npred{}: {}\ngreedy{}: {}\n'.format(
+                        pid, vocab.intseq2str(gt_tokens[i, :n]), '(error)' if psyn == 0 else '', pred_str,
+                        '(error)' if gsyn == 0 else '', greedy_str))
+            loss_all.append(loss); acc_all.append(acc); time_all.append(step_time)
+            for hk, hv in hist.items():
+                hist_all.setdefault(hk, []).append(np.asarray(hv))
+        if not cfg.no_loss:
+            lk, ak = sorted(loss), sorted(acc)
+            avg_loss = [float(np.mean([l[k] for l in loss_all])) for k in lk]
+            avg_acc = [float(np.nanmean([a[k] for a in acc_all])) if not all(
+                np.isnan(a[k]) for a in acc_all) else float('nan') for k in ak]
+            hist_avg = {hk: np.average(np.stack(hv), axis=0) for hk, hv in hist_all.items()}
+            final_msg = self.log_final_message(avg_loss, lk, avg_acc, ak, hist_avg, sorted(hist_avg),
+                                               float(np.sum(time_all)), write_summary=cfg.write_summary,
+                                               summary_file=cfg.summary_file)
+        from demo2program_b200.hdf5_lite import write_hdf5
+        if cfg.result_data and model_is_program:
+            write_hdf5(cfg.result_data_path, result_tree)
+            log.info("Wrote evaluation results of %d programs: %s", len(result_tree), cfg.result_data_path)
+        if vocab is not None:
+            write_hdf5('{}.hdf5'.format(base_name), pred_tree)
+            log_file.write('{}\n'.format(final_msg))
+            log_file.write("Model class: {}\n".format(cfg.model))
+            log_file.write("Checkpoint: {}\n".format(self.checkpoint))
+            log_file.write("Dataset: {}\n".format(cfg.dataset_path))
+            log_file.close()
+            text_file.close()
+        log.warning('Completed Evaluation.')
+
+    def _stored(self, pid, key, fallback):
+        """The example's demonstrations as stored in the dataset file (reference evaler.py:160-161
+        copies data_file[id][key]); synthetic datasets have no file - the padded batch entry."""
+        f = getattr(self.dataset, 'file', None) or getattr(self.dataset, 'data', None)
+        try:
+            return np.asarray(f[pid][key]) if f is not None else np.asarray(fallback)
+        except Exception:
+            return np.asarray(fallback)
 
     def run_single_step(self, batch):
         _start_time = time.time()
@@ -94,20 +175,26 @@ class Evaler(object):
             step_time = 0.001
         loss_str = "".join("{}:{loss: .3f} ".format(k, loss=loss[k]) for k in sorted(loss))
         acc_str = "".join("{}:{acc: .3f} ".format(k, acc=acc[k]) for k in sorted(acc))
-        msg = ("[{split_mode:5s} step {step:5d}] {loss_str}{acc_str}"
+        hist_str = ""
+        for k in sorted(hist):
+            hist_str += "{}: [".format(k) + "".join("{acc: .3f}, ".format(acc=h) for h in hist[k]) + "] "
+        msg = ("[{split_mode:5s} step {step:5d}] {loss_str}{acc_str}{hist_str}"
                "({sec_per_batch:.3f} sec/batch, {instance_per_sec:.3f} instances/sec)").format(
                    split_mode=(is_train and 'train' or 'val'), step=step, loss_str=loss_str,
-                   acc_str=acc_str, sec_per_batch=step_time,
+                   acc_str=acc_str, hist_str=hist_str, sec_per_batch=step_time,
                    instance_per_sec=self.batch_size / step_time)
         log.info(msg)
         return msg
 
     def log_final_message(self, loss, loss_key, acc, acc_key, hist, hist_key, time_,
                           write_summary=False, summary_file=None, is_train=False):
-        loss_str = "".join("{}:{loss: .3f} ".format(k, loss=v) for k, v in zip(loss_key, loss))
-        acc_str = "".join("{}:{acc: .3f}\n".format(k, acc=v) for k, v in zip(acc_key, acc))
-        msg = ("[Final Avg Report] \n[Loss] {}\n[Acc]  {}\n[Hist] \n[Time] ({:.3f} sec)").format(
-            loss_str, acc_str[:-1], time_)
+        loss_str = "".join("{}:{loss: .3f} ".format(k, loss=v) for k, v in sorted(zip(loss_key, loss)))
+        acc_str = "".join("{}:{acc: .3f}\n".format(k, acc=v) for k, v in sorted(zip(acc_key, acc)))
+        hist_str = ""
+        for key in sorted(hist_key):
+            hist_str += "{}: [".format(key) + "".join("{acc: .3f}, ".format(acc=h) for h in hist[key]) + "]\n"
+        msg = ("[Final Avg Report] \n[Loss] {}\n[Acc]  {}\n[Hist] {}\n[Time] ({:.3f} sec)").format(
+            loss_str, acc_str[:-1], hist_str[:-1], time_)
         log.info(msg)
         log.info("Model class: %s", self.config.model)
         log.info("Checkpoint: %s", self.checkpoint)

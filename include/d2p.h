@@ -254,6 +254,12 @@ int d2p_group_sum(const float* F, int B, int k, int H, float alpha, float* out, 
                   void* stream);
 int d2p_group_bcast(const float* S, int B, int k, int H, float alpha, float* out, int accumulate,
                     void* stream);
+/* demo_aggregation == 'maxpool' of synthesis_baseline / induction_baseline (tf.layers.max_pooling1d over the k
+ * demonstrations, reference models/baselines/model_synthesis.py:344-356): out[b,u] = max_i F[b,i,u]; the winning
+ * demonstration index (lowest among equal maxima) is kept for the backward pass, which routes the whole
+ * gradient to it like MaxPoolGrad. */
+int d2p_group_max(const float* F, int B, int k, int H, float* out, int* arg, void* stream);
+int d2p_group_max_bwd(const float* dout, const int* arg, int B, int k, int H, float* dF, void* stream);
 int d2p_axpby(const float* x, float alpha, float* y, float beta, size_t n, void* stream);
 /* y = (a + b) + c: the sum of the three gradient contributions to the per-demonstration summary state
  * (action decoder, perception decoder, summary pools; reference models/model_full.py:918-1079 adds the three

@@ -44,6 +44,28 @@ def test_loss_and_gradients_match_oracle(model, B, k):
     assert rel_err(eng.dsum_h.cpu().numpy(), out['demo_h_summary'].detach().numpy()) < 1e-4
 
 
+def test_maxpool_aggregation_matches_oracle():
+    """synthesis_baseline with demo_aggregation=maxpool (reference
+    models/baselines/model_synthesis.py:344-356): forward and the MaxPoolGrad-style backward."""
+    cfg = karel_config('synthesis_baseline', batch_size=6, k=4, demo_aggregation='maxpool')
+    orc, eng, batch, pm, sm = oracle_and_engine(cfg, use_graph=False)
+    out = _check_step(orc, eng, batch, pm)
+    assert rel_err(eng.dsum_h.cpu().numpy(), out['demo_h_summary'].detach().numpy()) < 1e-4
+    assert rel_err(eng.dsum_c.cpu().numpy(), out['demo_c_summary'].detach().numpy()) < 1e-4
+    # concat: identity for k == 1, rejected otherwise (the reference graph does not build either)
+    cfg1 = karel_config('synthesis_baseline', batch_size=4, k=1, demo_aggregation='concat')
+    orc1, eng1, batch1, pm1, _ = oracle_and_engine(karel_config('synthesis_baseline', batch_size=4, k=1),
+                                                   use_graph=False)
+    from demo2program_b200.engine import Engine
+    e_cat = Engine(cfg1, flat_params=eng1.params.cpu().numpy(), flat_state=eng1.state.cpu().numpy(), use_graph=False)
+    _check_step(orc1, e_cat, batch1, pm1)
+    bad = Engine(karel_config('synthesis_baseline', batch_size=4, k=2, demo_aggregation='concat'), use_graph=False)
+    from demo2program_b200.synthetic import make_batch
+    bad.stage_batch(make_batch(bad.cfg, seed=1))
+    with pytest.raises(ValueError):
+        bad.forward()
+
+
 def test_engine_matches_committed_golden():
     """The CUDA path against tests/golden/oracle_golden.json (committed oracle outputs on seeded
     inputs; generator: tests/golden/make_oracle_golden.py) - no oracle code runs here."""
@@ -263,6 +285,50 @@ def test_model_facade_reports_karel_program_metrics():
     assert np.array_equal(num, m.greedy_num_execution_correct)
 
 
+def test_model_facade_report_surface_matches_reference_keys_and_oracle():
+    """Every report key of the reference's `full` model (models/model_full.py:1099-1132) is present;
+    the losses / action accuracies (teacher-forced and greedy) equal an oracle restatement of
+    Sequence_Loss applied to the ORACLE's own logits."""
+    from demo2program_b200.model import Model
+    from demo2program_b200.metrics import demo_sequence_stats, sequence_stats
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    from oracle.models import OracleModel
+    cfg = karel_config('full', batch_size=5, k=3)
+    pm, sm = build_manifests(cfg)
+    p0, s0 = pm.init_flat(3), sm.init_flat(3)
+    s0 = s0 + np.random.RandomState(2).uniform(0.0, 0.3, s0.shape).astype(np.float32)
+    m = Model(cfg, is_train=False, use_graph=False, flat_params=p0, flat_state=s0)
+    batch = make_batch(cfg, seed=9)
+    m.run_eval_step(m.get_feed_dict(batch), greedy=True)
+    assert set(m.report_loss) == {'program_loss', 'greedy_program_loss', 'avg_action_loss', 'greedy_avg_action_loss'}
+    assert set(m.report_accuracy) == {
+        'program_token_acc', 'program_seq_acc', 'program_syntax_acc', 'pred_exact_program_accuracy',
+        'greedy_exact_program_accuracy', 'greedy_program_token_acc', 'greedy_program_seq_acc',
+        'greedy_program_syntax_acc', 'avg_action_token_acc', 'avg_action_seq_acc',
+        'greedy_avg_action_token_acc', 'greedy_avg_action_seq_acc'}
+    om = OracleModel(cfg, p0, s0, is_train=False)
+    with torch.no_grad():
+        out = om.forward(batch, greedy=True)
+    t = lambda x: torch.as_tensor(np.asarray(x))
+    gt_tok, gt_len = t(batch['program_tokens']).long(), t(batch['program_len'])[:, 0].long()
+    a_tok, a_len = t(batch['a_h_tokens']).long(), t(batch['demo_len']).long()
+    want = {
+        'program_loss': float(out['program_loss']), 'avg_action_loss': float(out['avg_action_loss']),
+        'greedy_program_loss': sequence_stats(out['greedy_pred_program'].float(), gt_tok,
+                                              out['greedy_pred_program_len'][:, 0], gt_len)['loss'],
+    }
+    ga = demo_sequence_stats(out['greedy_pred_action'].float(), a_tok, out['greedy_pred_action_len'], a_len)
+    ta = demo_sequence_stats(out['pred_action'].float(), a_tok, a_len, a_len)
+    want['greedy_avg_action_loss'] = ga['loss']
+    for key, v in want.items():
+        assert abs(m.report_loss[key] - v) < LOSS_TOL, (key, m.report_loss[key], v)
+    assert abs(ta['loss'] - want['avg_action_loss']) < 1e-6      # metrics.py restates the oracle's CE
+    for key, v in (('avg_action_token_acc', ta['token_acc']), ('avg_action_seq_acc', ta['seq_acc']),
+                   ('greedy_avg_action_token_acc', ga['token_acc']), ('greedy_avg_action_seq_acc', ga['seq_acc'])):
+        assert abs(m.report_accuracy[key] - v) < 1e-6, key
+
+
 def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
     """trainer.py / evaler.py with the reference's flags on synthetic data."""
     import trainer, evaler, glob, os
@@ -287,6 +353,33 @@ def test_cli_trainer_and_evaler_smoke(tmp_path, monkeypatch):
                  '--summary_file', str(tmp_path / 'report_tf.txt')])
     strip = lambda t: [l for l in t.splitlines() if 'heckpoint' not in l and 'time' not in l.lower()]
     assert strip(open(tmp_path / 'report_tf.txt').read()) == strip(rep)
+    # the final report carries the four execution-accuracy histograms (reference evaler.py:324-359)
+    for key in ('program_execution_acc_hist', 'greedy_program_execution_acc_hist',
+                'test_program_execution_acc_hist', 'test_greedy_program_execution_acc_hist'):
+        assert key + ': [' in rep, key
+    # --pred_program / --result_data dumps (reference evaler.py:151-208)
+    out_dir = tmp_path / 'out'
+    evaler.main(['--model', 'synthesis_baseline', '--dataset_path', 'synthetic:64', '--num_k', '2',
+                 '--batch_size', '8', '--max_steps', '2', '--checkpoint', ck[0], '--pred_program',
+                 '--output_dir', str(out_dir), '--result_data', '--result_data_path', str(tmp_path / 'result.hdf5'),
+                 '--no_write_summary'])
+    base = glob.glob(str(out_dir / 'out_*_test.txt'))
+    assert len(base) == 1
+    txt = open(base[0]).read()
+    assert txt.count('[id: ') == 16 and 'gt: DEF run m(' in txt and 'greedy' in txt
+    assert 'Final Avg Report' in open(base[0][:-4] + '.log').read()
+    from demo2program_b200.hdf5_lite import File
+    with File(base[0][:-4] + '.hdf5') as f:
+        assert len(f.keys()) == 16
+        g = f[sorted(f.keys())[0]]
+        assert {'program_prediction', 'program_syntax', 'greedy_prediction', 'greedy_syntax',
+                'program_num_execution_correct', 'program_is_correct_execution',
+                'greedy_num_execution_correct', 'greedy_is_correct_execution'} <= set(g.keys())
+    with File(str(tmp_path / 'result.hdf5')) as f:
+        assert len(f.keys()) == 16
+        g = f[sorted(f.keys())[0]]
+        assert set(g.keys()) == {'program', 'pred_program', 'pred_program_len', 's_h', 'test_s_h'}
+        assert np.asarray(g['pred_program']).shape == np.asarray(g['program']).shape
 
 
 def test_tf_checkpoint_resume_is_bitwise(tmp_path):

@@ -6,9 +6,14 @@ same dataset-derived config fields (trainer.py:312-335), same log line
 (trainer.py:227-240), same train_dir naming (trainer.py:37-53); the TF graph +
 session is replaced by `demo2program_b200.model.Model` (libd2p on one B200, or one
 process per GPU under torchrun with a single NCCL all-reduce of the gradients).
+The train loop feeds `Engine.train_steps`, the pipelined public API `bench.py` times as `e2e`
+(batch i+1 is staged and copied while step i runs; losses come back one step later), in runs that
+end where a validation step or a checkpoint is due.
 Deviations (documented in DESIGN.md): `--dataset_path synthetic[:N]` selects seeded
-synthetic data; checkpoints are .npz files keyed by TF variable name; TensorBoard
-summaries and the host-interpreter metrics are not produced.
+synthetic data; checkpoints are written both as TF-1.x tensor bundles (model-<step>.index/.data,
+`checkpoint` state file) and as .npz keyed by TF variable name; TensorBoard summaries are not
+produced.  Under torchrun every rank trains its own shard of the example ids; rank 0 alone owns
+the train_dir, the log lines and the checkpoints.
 """
 import argparse
 import logging
@@ -37,12 +42,16 @@ class Trainer(object):
         self.train_dir = './train_dir/%s-%s-%s-%s-%s-%s' % (
             config.dataset_type, '_'.join(config.dataset_path.split('/')), config.model,
             config.prefix, hyper_parameter_str, time.strftime("%Y%m%d-%H%M%S"))
-        os.makedirs(self.train_dir, exist_ok=True)
-        log.info("Train Dir: %s", self.train_dir)
+        self.is_chief = config.rank == 0
+        if self.is_chief:       # one train_dir per job, not one per rank
+            os.makedirs(self.train_dir, exist_ok=True)
+            log.info("Train Dir: %s", self.train_dir)
         from demo2program_b200.dataset import batches
         self.batch_size = config.batch_size
+        # data parallelism: rank r draws its batches from ids[r::world] (no example twice per epoch)
         self.batch_train = batches(dataset, self.batch_size, shuffle=True, seed=config.rank,
-                                   workers=getattr(config, 'loader_workers', 0))
+                                   workers=getattr(config, 'loader_workers', 0),
+                                   rank=config.rank, world=config.world_size)
         self.batch_test = batches(dataset_test, self.batch_size, shuffle=False)
         Model = self.get_model_class(config.model)
         log.info("Using Model class: %s", Model)
@@ -64,20 +73,41 @@ class Trainer(object):
     def train(self, max_steps=1000000):
         log.info("Training Starts!")
         ckpt_save_step = 1000
-        for s in range(max_steps):
-            step, loss, step_time = self.run_single_step(self.batch_train, step=s, is_train=True)
-            if s % self.log_step == 0:
-                self.log_step_message(step, loss, step_time)
+        s = 0
+        while s < max_steps:
+            # a run of pipelined steps ends with the step after which a validation step or a
+            # checkpoint is due (reference trainer.py:126-183 does both right after step s)
+            due = lambda t: t % self.test_sample_step == 0 or t % ckpt_save_step == 0
+            stop = s
+            while not due(stop) and stop + 1 < max_steps:
+                stop += 1
+            for s, (step, loss, step_time) in zip(range(s, stop + 1), self.run_steps(self.batch_train, stop + 1 - s)):
+                if s % self.log_step == 0 and self.is_chief:
+                    self.log_step_message(step, loss, step_time)
+            s = stop
             if s % self.test_sample_step == 0:
                 step, test_loss, test_time = self.run_test(self.batch_test)
-                self.log_step_message(step, test_loss, test_time, is_train=False)
-            if s % ckpt_save_step == 0 and self.config.rank == 0:
+                if self.is_chief:
+                    self.log_step_message(step, test_loss, test_time, is_train=False)
+            if s % ckpt_save_step == 0 and self.is_chief:
+                step = self.model.engine.step_count()
                 log.info("Saved checkpoint at %d", s)
                 np.savez(os.path.join(self.train_dir, 'model-%d.npz' % step), **self.model.state_dict())
                 # and in the reference's own format (saver.save(..., 'model', global_step), trainer.py:182):
                 # model-<step>.index / .data-00000-of-00001 + the `checkpoint` state file
                 from demo2program_b200 import tf_checkpoint
                 tf_checkpoint.save_model(os.path.join(self.train_dir, 'model-%d' % step), self.model)
+            s += 1
+
+    def run_steps(self, batch, n):
+        """n train steps through the pipelined input path; yields (global step, loss, seconds)."""
+        feeds = (self.model.get_feed_dict(next(batch), is_training=True) for _ in range(n))
+        t0 = time.time()
+        step0 = self.model.engine.step_count()
+        for i, loss in enumerate(self.model.run_train_steps(feeds)):
+            t1 = time.time()
+            yield step0 + i + 1, loss, t1 - t0
+            t0 = t1
 
     def run_single_step(self, batch, step=None, is_train=True):
         _start_time = time.time()
