@@ -58,6 +58,10 @@ SIGNATURES = {
                               _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                               _sz, _i, _fp]),
     'd2p_embed_shifted': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp]),
+    'd2p_step_lens': (_i, [_fp, _i, _i, _fp, _fp]),
+    'd2p_embed_shifted_step': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _i, _fp, _fp]),
+    'd2p_sched_sample_step': (_i, [_fp, _i, _i, _fp, _i, _i, _fp, _i, _f, C.c_uint, _i, _fp, _fp, _fp]),
+    'd2p_sched_hash': (C.c_uint, [C.c_uint] * 6),
     'd2p_embed_shifted_bwd_ws_bytes': (_sz, [_i, _i, _i, _i]),
     'd2p_embed_shifted_bwd': (_i, [_fp, _i, _i, _fp, _i, _i, _i, _fp, _fp, _sz, _fp]),
     'd2p_seq_weights': (_i, [_fp, _i, _i, _f, _i, _fp, _fp, _fp]),
@@ -75,6 +79,12 @@ SIGNATURES = {
     'd2p_induction_decode': (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp,
                                   _fp, _fp, _i, _fp, _fp, _fp, _fp, _sz, _fp]),
     'd2p_concat_cols': (_i, [_fp, _i, _fp, _i, _ll, _fp, _fp]),
+    'd2p_luong_pool_attention_train_ws_bytes': (_sz, [_i, _i, _i, _i]),
+    'd2p_luong_pool_attention_train_fwd': (_i, [_fp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _i, _fp, _fp, _sz,
+                                                _fp]),
+    'd2p_luong_pool_attention_train_bwd': (_i, [_fp, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _fp, _i,
+                                                _fp, _fp, _fp, _sz, _fp]),
+    'd2p_split_cols': (_i, [_fp, _i, _i, _i, _ll, _fp, _fp]),
     'd2p_karel_check_syntax': (_i, [_fp, _i]),
     'd2p_karel_execute': (_i, [_fp, _i, _fp, _i, _i, _i, _i, _fp, _fp]),
     'd2p_karel_programs_equal': (_i, [_fp, _i, _fp, _i]),

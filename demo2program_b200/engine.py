@@ -48,6 +48,14 @@ class Engine:
         # compact_decoders: the action / perception decoder recurrences of `full` run in compact form
         # (32 CTAs each) side by side with the program decoder instead of one after the other
         self.compact_decoders = bool(compact_decoders)
+        # scheduled sampling (reference models/model_full.py:59-67, 414-423): the program / action decoders
+        # run step by step and feed, with the scheduled probability, a token sampled from their own
+        # output instead of the ground truth.  sched_p_override >= 0 replaces the schedule (tests).
+        self.sched = bool(cfg.scheduled_sampling) and bool(is_train)
+        self.sched_seed = int(seed) & 0xFFFFFFFF
+        self.sched_p_override = -1.0
+        if self.sched:
+            self.token_tables = True
         if not torch.cuda.is_available():
             raise _lib.D2PError('demo2program_b200 needs a CUDA device (no CPU '
                                 'fallback)')
@@ -251,6 +259,10 @@ class Engine:
         self.prog.update(tab=z(V + 2, 4 * H), tsum=z(V + 1, 4 * H))
         if cfg.model == 'full':
             self.act.update(tab=z(A + 2, 4 * H), tsum=z(A + 1, 4 * H))
+        if self.sched:
+            for b_, Rn, Ln in ([(self.prog, B, L)] + ([(self.act, R, T)] if cfg.model == 'full' else [])):
+                b_.update(fed=zi(Rn, Ln), sampled=zi(Rn, Ln), steplen=zi(Ln, Rn),
+                          hpp=[z(Rn, H), z(Rn, H)], cpp=[z(Rn, H), z(Rn, H)])
         ws = max(ws, lib.d2p_adam_ws_bytes(),
                  lib.d2p_embed_shifted_bwd_ws_bytes(V + 1, 4 * H, B, L),
                  lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, 4 * H, R, T))
@@ -352,8 +364,32 @@ class Engine:
         E, W, bias = self.P(emb_name), self.P(scope + 'kernel'), self.P(scope + 'bias')
         self._gemm(0, 0, rows, 4 * H, H, 1.0, E, H, W, 4 * H, 0.0, b['tab'], 4 * H, bias=bias)
         self._call('d2p_axpby', ptr(bias), 1.0, ptr(b['tab'][rows]), 0.0, 4 * H, self._st())
+        if self.sched:      # the gate rows are gathered step by step from the tokens actually fed
+            return
         self._call('d2p_embed_shifted', ptr(b['tab']), rows + 1, 4 * H, ptr(tokens), Rn, Tn, rows,
                    ptr(b['gates']), self._st())
+
+    def _sched_decoder_fwd(self, b, rows, gt_tokens, Rn, Tn, h0, c0, scope, Wp, vocab, decoder_id):
+        """Scheduled-sampling forward of a token decoder (seq2seq.ScheduledEmbeddingTrainingHelper,
+        reference models/model_full.py:414-423): per step the hoisted gate row of the token fed
+        (tab[token], <s> at t = 0), one recurrence step, the output projection, then the draw of
+        the token fed to the next step (d2p_sched_sample_step).  Leaves y / gates / cells / logits
+        of all steps exactly as the teacher-forced path does, and the fed tokens in b['fed'] - the
+        backward pass is the teacher-forced one over those."""
+        H, call, S = self.H, self._call, self._st
+        W, bias = self.P(scope + 'kernel'), self.P(scope + 'bias')
+        call('d2p_step_lens', ptr(b['runlen']), Rn, Tn, ptr(b['steplen']), S())
+        for t in range(Tn):
+            call('d2p_embed_shifted_step', ptr(b['tab']), rows + 1, 4 * H, ptr(b['fed']), Rn, Tn, t, rows,
+                 ptr(b['gates'][t]), S())
+            h_prev, c_prev = (h0, c0) if t == 0 else (b['hpp'][t & 1], b['cpp'][t & 1])
+            call('d2p_lstm_seq_fwd', ptr(b['X']), 1, Rn, H, H, ptr(b['steplen'][t]), ptr(h_prev), ptr(c_prev),
+                 ptr(W), ptr(bias), 1.0, ptr(b['y'][t]), ptr(b['hpp'][(t + 1) & 1]), ptr(b['cpp'][(t + 1) & 1]),
+                 ptr(b['gates'][t]), ptr(b['cells'][t]), 2, S())
+            self._gemm(0, 0, Rn, vocab, H, 1.0, b['y'][t], H, Wp, vocab, 0.0, b['logits'][t], vocab)
+            call('d2p_sched_sample_step', ptr(b['logits'][t]), Rn, vocab, ptr(gt_tokens), Tn, t,
+                 ptr(self.adam_state), int(self.cfg.scheduled_sampling_decay_steps), float(self.sched_p_override),
+                 self.sched_seed, decoder_id, ptr(b['fed']), ptr(b['sampled']), S())
 
     def _token_grads(self, emb_name, scope, rows, tokens, Rn, Tn, b):
         """Backward of _token_gates from the dZ left in b['gates']: S[v] = sum of the dZ rows that
@@ -524,10 +560,15 @@ class Engine:
             side_by_side = self.concurrent and self.compact_decoders
 
             def act_fwd():
-                self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
-                               'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=2, compact=side_by_side)
                 Wa = self.P('Action_Decoder/dynamic_decoder/output_projection/kernel')
-                self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
+                if self.sched:
+                    self._sched_decoder_fwd(a, A + 1, self.d_act_tok, R, T, fin['hT'], fin['cT'],
+                                            'Action_Decoder/dynamic_decoder/basic_lstm_cell/', Wa, A, 2)
+                else:
+                    self._lstm_fwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
+                                   'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, phases=2,
+                                   compact=side_by_side)
+                    self._gemm(0, 0, T * R, A, H, 1.0, a['y'], H, Wa, A, 0.0, a['logits'], A)
                 call('d2p_softmax_ce', ptr(a['logits']), T, R, A, ptr(self.d_act_tok), ptr(self.d_demo_len),
                      ptr(a['runlen']), ptr(a['w']), ptr(a['rowloss']), ptr(a['dlogits']),
                      ptr(self.loss[2:]), 0, S())
@@ -587,10 +628,14 @@ class Engine:
             call('d2p_seq_weights', ptr(self.d_prog_len), B, 1, 1.0, L, ptr(p['w']), ptr(p['runlen']), S())
             if self._ev_prog_in is not None:
                 torch.cuda.current_stream(self.dev).wait_event(self._ev_prog_in)
-            self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
-                           'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, phases=2)
             Wp = self.P('Program_Decoder/dynamic_decoder/output_projection/kernel')
-            self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
+            if self.sched:
+                self._sched_decoder_fwd(p, V + 1, self.d_prog_tok, B, L, self.dsum_h, self.dsum_c,
+                                        'Program_Decoder/dynamic_decoder/basic_lstm_cell/', Wp, V, 1)
+            else:
+                self._lstm_fwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
+                               'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, phases=2)
+                self._gemm(0, 0, L * B, V, H, 1.0, p['y'], H, Wp, V, 0.0, p['logits'], V)
             call('d2p_softmax_ce', ptr(p['logits']), L, B, V, ptr(self.d_prog_tok), ptr(self.d_prog_len),
                  ptr(p['runlen']), ptr(p['w']), ptr(p['rowloss']), ptr(p['dlogits']),
                  ptr(self.loss[1:]), 0, S())
@@ -689,7 +734,7 @@ class Engine:
                                None, token_fn=lambda: self._token_grads(
                                    'Program_Decoder/Token_Embedding/embedding_map',
                                    'Program_Decoder/dynamic_decoder/basic_lstm_cell/', V + 1,
-                                   self.d_prog_tok, B, L, p))
+                                   p['fed'] if self.sched else self.d_prog_tok, B, L, p))
             else:
                 self._lstm_bwd(p['X'], L, B, H, p['runlen'], self.dsum_h, self.dsum_c,
                                'Program_Decoder/dynamic_decoder/basic_lstm_cell/', p, p['dy'], None, None,
@@ -732,7 +777,7 @@ class Engine:
                                    None, token_fn=lambda: self._token_grads(
                                        'Action_Decoder/Token_Embedding/embedding_map',
                                        'Action_Decoder/dynamic_decoder/basic_lstm_cell/', A + 1,
-                                       self.d_act_tok, R, T, a))
+                                       a['fed'] if self.sched else self.d_act_tok, R, T, a))
                 else:
                     self._lstm_bwd(a['X'], T, R, H, a['runlen'], fin['hT'], fin['cT'],
                                    'Action_Decoder/dynamic_decoder/basic_lstm_cell/', a, a['dy'], None, None,

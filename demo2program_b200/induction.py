@@ -2,9 +2,13 @@
 (CNN features ++ perception vector -> LSTM), avg aggregate, k-way pooled Luong
 attention decoder predicting the action sequences of the `test_k` unseen demos.
 
-Inference path only (BASELINE.json configs[4]: greedy decode, batch 512): the
-teacher-forced forward pass with its loss, and the greedy decoder.  Training this
-baseline (attention backward) is not part of the benchmarked path.
+Inference (BASELINE.json configs[4]: greedy decode, batch 512): the teacher-forced forward pass
+with its loss and the greedy decoder run in one fused device loop (d2p_induction_decode).
+Training (reference trainer.py:102-109 over model_induction.py:788-819): `train_step` unrolls the
+teacher-forced decoder step by step through the same C-ABI cell (d2p_lstm_seq_fwd/_bwd with T = 1,
+input [embedding ; attention_{t-1}]), the training forms of the pooled attention
+(d2p_luong_pool_attention_train_fwd/_bwd, csrc/attn_train.cu) and the shared clip + Adam step;
+it is not a benchmarked configuration.
 """
 import ctypes as C
 
@@ -175,6 +179,175 @@ class InductionEngine:
                    ptr(self.runlen), ptr(self.w), ptr(self.rowloss), None, ptr(self.loss), 0, st)
         return self.logits.permute(1, 0, 2).reshape(self.B, tk, T, A).contiguous()
 
+    # ------------------------------------------------------------------ training
+    def G(self, name):
+        e = self.pm[name]
+        return self.grads[e.offset:e.offset + e.size]
+
+    def _alloc_train(self):
+        if hasattr(self, 'grads'):
+            return
+        cfg, lib, dev = self.cfg, self.lib, self.dev
+        B, k, tk, T, H, R, R2, F = self.B, self.k, self.tk, self.T, self.H, self.R, self.R2, self.F
+        A, Pd = cfg.action_space, cfg.per_dim
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.grads, self.adam_m, self.adam_v = z(self.pm.total), z(self.pm.total), z(self.pm.total)
+        self.adam_state = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.lr, self.clip = cfg.learning_rate, 20.0
+        for li in range(self.conv_desc.n_layers):
+            sc = 'Demo_Encoder/State_Encoder/conv%d' % (li + 1)
+            l, bn = self.conv_desc.layers[li], sc + '/bn_act/BatchNorm/'
+            l.dw, l.db = ptr(self.G(sc + '/Conv/weights')), ptr(self.G(sc + '/Conv/biases'))
+            l.dgamma, l.dbeta = ptr(self.G(bn + 'gamma')), ptr(self.G(bn + 'beta'))
+        self.tr = dict(
+            emb=z(T, R2, H), xa=z(T, R2, 2 * H), hs=z(T, R2, H), cs=z(T, R2, H), gates=z(T, R2, 4 * H),
+            ctx=z(R2, H), hc=z(T, R2, 2 * H), att=z(T, R2, H), alpha=z(T, B * k * tk * T),
+            dlogits=z(T, R2, A), datt=z(T, R2, H), dhc=z(R2, 2 * H), dh=z(R2, H), dxa=z(R2, 2 * H), tmp=z(R2, H),
+            dh0=z(R2, H), dc0=[z(R2, H), z(R2, H)], demb=z(T, R2, H), h0=z(R2, H), c0=z(R2, H), zero=z(R2, H),
+            hT=z(R2, H), cT=z(R2, H), ones=torch.ones(R2, dtype=torch.int32, device=dev),
+            dkeys=z(T, R, H), dvalues=z(T, R, H), dX=z(T, R, F + Pd), dfeat=z(T, R, F),
+            dhT=z(R, H), dcT=z(R, H), dsum_h=z(B, H), dsum_c=z(B, H), edh0=z(R, H), edc0=z(R, H))
+        ws = max(self.ws_bytes, lib.d2p_lstm_seq_bwd_ws_bytes(T, R, H), lib.d2p_lstm_seq_bwd_ws_bytes(1, R2, H),
+                 lib.d2p_adam_ws_bytes(), lib.d2p_embed_shifted_bwd_ws_bytes(A + 1, H, R2, T),
+                 lib.d2p_luong_pool_attention_train_ws_bytes(B, k, tk, H))
+        if ws > self.ws_bytes:
+            self.ws_bytes = (ws + 255) // 256 * 256
+            self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+        if self.use_tc:     # operand arena for the backward products ([T*R, 4H] dZ operands, K = T*R sums)
+            big = lib.d2p_gemm_tc_ws_bytes(T * max(R, R2), 4 * H, 4 * H) + (16 << 20)
+            if big > self.tc_scratch.numel():
+                self.tc_scratch = torch.zeros(big, dtype=torch.uint8, device=dev)
+
+    def forward_train(self):
+        """Encoder + teacher-forced attention decoder, keeping what the backward pass needs.
+        loss = mean over test_k of the masked cross-entropies (model_induction.py:788-819)."""
+        self._alloc_train()
+        cfg, st, call, tr = self.cfg, self._st(), self._call, self.tr
+        B, k, tk, T, H, R, R2 = self.B, self.k, self.tk, self.T, self.H, self.R, self.R2
+        A = cfg.action_space
+        if self.fold_memory_layer:
+            raise NotImplementedError('training needs the keys tensor (fold_memory_layer=False)')
+        self.encode()
+        w = 'Manipulation/dynamic_decoder/pooling_attention_wrapper/'
+        K, bias = self.P(w + 'basic_lstm_cell/kernel'), self.P(w + 'basic_lstm_cell/bias')
+        Wa = self.P(w + 'attention_layer/kernel')
+        proj = self.P('Manipulation/dynamic_decoder/output_projection/kernel')
+        table = self.P('Manipulation/Token_Embedding/embedding_map')
+        # teacher-forced inputs: <s> (id A+1, out of the table's range -> zero row), then the gt tokens
+        call('d2p_embed_shifted', ptr(table), A + 1, H, ptr(self.d_ttok), R2, T, A + 1, ptr(tr['emb']), st)
+        call('d2p_seq_weights', ptr(self.d_tlen), R2, tk, 1.0 / tk, T, ptr(self.w), ptr(self.runlen), st)
+        # the reference's swapped initial state (model_induction.py:674-676): cell c := h summary, h := c summary
+        call('d2p_group_bcast', ptr(self.c_sum), B, tk, H, 1.0, ptr(tr['h0']), 0, st)
+        call('d2p_group_bcast', ptr(self.h_sum), B, tk, H, 1.0, ptr(tr['c0']), 0, st)
+        for t in range(T):
+            att_prev = tr['att'][t - 1] if t else tr['zero']
+            h_prev, c_prev = (tr['hs'][t - 1], tr['cs'][t - 1]) if t else (tr['h0'], tr['c0'])
+            call('d2p_concat_cols', ptr(tr['emb'][t]), H, ptr(att_prev), H, R2, ptr(tr['xa'][t]), st)
+            call('d2p_lstm_seq_fwd', ptr(tr['xa'][t]), 1, R2, 2 * H, H, ptr(tr['ones']), ptr(h_prev), ptr(c_prev),
+                 ptr(K), ptr(bias), 1.0, ptr(tr['hs'][t]), ptr(tr['hT']), ptr(tr['cT']), ptr(tr['gates'][t]),
+                 ptr(tr['cs'][t]), 3, st)
+            call('d2p_luong_pool_attention_train_fwd', ptr(tr['hs'][t]), H, ptr(self.keys), ptr(self.Y),
+                 ptr(self.d_demo_len), B, k, tk, T, H, ptr(tr['ctx']), H, ptr(tr['alpha'][t]), ptr(self.ws),
+                 self.ws_bytes, st)
+            call('d2p_concat_cols', ptr(tr['hs'][t]), H, ptr(tr['ctx']), H, R2, ptr(tr['hc'][t]), st)
+            call('d2p_gemm', 0, 0, R2, H, 2 * H, 1.0, ptr(tr['hc'][t]), 2 * H, ptr(Wa), H, 0.0, ptr(tr['att'][t]), H,
+                 None, st)
+        call('d2p_gemm', 0, 0, T * R2, A, H, 1.0, ptr(tr['att']), H, ptr(proj), A, 0.0, ptr(self.logits), A, None, st)
+        call('d2p_softmax_ce', ptr(self.logits), T, R2, A, ptr(self.d_ttok), ptr(self.d_tlen), ptr(self.runlen),
+             ptr(self.w), ptr(self.rowloss), ptr(tr['dlogits']), ptr(self.loss), 0, st)
+
+    def backward_train(self):
+        """Back-propagation through the attention decoder (BPTT over the T decoder steps), the memory
+        layer, the demonstration encoder and the frame encoder into self.grads."""
+        cfg, st, call, tr = self.cfg, self._st(), self._call, self.tr
+        B, k, tk, T, H, R, R2, F = self.B, self.k, self.tk, self.T, self.H, self.R, self.R2, self.F
+        A, Pd = cfg.action_space, cfg.per_dim
+        w = 'Manipulation/dynamic_decoder/pooling_attention_wrapper/'
+        Kn, bn = w + 'basic_lstm_cell/kernel', w + 'basic_lstm_cell/bias'
+        Wan, projn = w + 'attention_layer/kernel', 'Manipulation/dynamic_decoder/output_projection/kernel'
+        self.grads.zero_()
+        tr['dkeys'].zero_()
+        tr['dvalues'].zero_()
+        # output projection: logits = att * proj
+        call('d2p_gemm', 1, 0, H, A, T * R2, 1.0, ptr(tr['att']), H, ptr(tr['dlogits']), A, 0.0, ptr(self.G(projn)), A,
+             None, st)
+        call('d2p_gemm', 0, 1, T * R2, H, A, 1.0, ptr(tr['dlogits']), A, ptr(self.P(projn)), A, 0.0, ptr(tr['datt']), H,
+             None, st)
+        for t in reversed(range(T)):
+            last = t == T - 1
+            h_prev, c_prev = (tr['hs'][t - 1], tr['cs'][t - 1]) if t else (tr['h0'], tr['c0'])
+            if not last:    # attention_t also feeds the cell input of step t+1
+                call('d2p_split_cols', ptr(tr['dxa']), 2 * H, H, H, R2, ptr(tr['tmp']), st)
+                call('d2p_axpby', ptr(tr['tmp']), 1.0, ptr(tr['datt'][t]), 1.0, R2 * H, st)
+            # attention layer [h ; ctx] * W_a
+            call('d2p_gemm', 0, 1, R2, 2 * H, H, 1.0, ptr(tr['datt'][t]), H, ptr(self.P(Wan)), H, 0.0, ptr(tr['dhc']),
+                 2 * H, None, st)
+            call('d2p_split_cols', ptr(tr['dhc']), 2 * H, 0, H, R2, ptr(tr['dh']), st)
+            if not last:
+                call('d2p_axpby', ptr(tr['dh0']), 1.0, ptr(tr['dh']), 1.0, R2 * H, st)
+            dctx = tr['dhc'].view(-1)[H:]          # columns H..2H of dhc, row stride 2H
+            call('d2p_luong_pool_attention_train_bwd', ptr(tr['hs'][t]), H, ptr(self.keys), ptr(self.Y),
+                 ptr(self.d_demo_len), ptr(tr['alpha'][t]), ptr(dctx), 2 * H, B, k, tk, T, H, ptr(tr['dh']), H,
+                 ptr(tr['dkeys']), ptr(tr['dvalues']), ptr(self.ws), self.ws_bytes, st)
+            dc_in = None if last else tr['dc0'][(t + 1) & 1]
+            call('d2p_lstm_seq_bwd', ptr(tr['xa'][t]), 1, R2, 2 * H, H, ptr(tr['ones']), ptr(h_prev), ptr(c_prev),
+                 ptr(self.P(Kn)), ptr(tr['hs'][t]), ptr(tr['gates'][t]), ptr(tr['cs'][t]), ptr(tr['dh']), None,
+                 ptr(dc_in), ptr(tr['dxa']), ptr(self.G(Kn)), ptr(self.G(bn)), ptr(tr['dh0']), ptr(tr['dc0'][t & 1]),
+                 ptr(self.ws), self.ws_bytes, 3, st)
+            call('d2p_split_cols', ptr(tr['dxa']), 2 * H, 0, H, R2, ptr(tr['demb'][t]), st)
+        call('d2p_gemm', 1, 0, 2 * H, H, T * R2, 1.0, ptr(tr['hc']), 2 * H, ptr(tr['datt']), H, 0.0, ptr(self.G(Wan)), H,
+             None, st)
+        call('d2p_embed_shifted_bwd', ptr(tr['demb']), A + 1, H, ptr(self.d_ttok), R2, T, A + 1,
+             ptr(self.G('Manipulation/Token_Embedding/embedding_map')), ptr(self.ws), self.ws_bytes, st)
+        # initial state (swapped): d c_summary from dh0, d h_summary from dc0; summaries = mean over k
+        call('d2p_group_sum', ptr(tr['dh0']), B, tk, H, 1.0, ptr(tr['dsum_c']), 0, st)
+        call('d2p_group_sum', ptr(tr['dc0'][0]), B, tk, H, 1.0, ptr(tr['dsum_h']), 0, st)
+        call('d2p_group_bcast', ptr(tr['dsum_h']), B, k, H, 1.0 / k, ptr(tr['dhT']), 0, st)
+        call('d2p_group_bcast', ptr(tr['dsum_c']), B, k, H, 1.0 / k, ptr(tr['dcT']), 0, st)
+        # memory layer keys = values * W_mem
+        Wm = 'AttnMechanism/memory_layer/kernel'
+        call('d2p_gemm', 1, 0, H, H, T * R, 1.0, ptr(self.Y), H, ptr(tr['dkeys']), H, 0.0, ptr(self.G(Wm)), H, None, st)
+        call('d2p_gemm', 0, 1, T * R, H, H, 1.0, ptr(tr['dkeys']), H, ptr(self.P(Wm)), H, 1.0, ptr(tr['dvalues']), H,
+             None, st)
+        # demonstration encoder (values = its outputs) and the frame encoder
+        sc = 'Demo_Encoder/rnn/basic_lstm_cell/'
+        call('d2p_lstm_seq_bwd', ptr(self.X), T, R, F + Pd, H, ptr(self.d_demo_len), None, None,
+             ptr(self.P(sc + 'kernel')), ptr(self.Y), ptr(self.gates), ptr(self.cells), ptr(tr['dvalues']),
+             ptr(tr['dhT']), ptr(tr['dcT']), ptr(tr['dX']), ptr(self.G(sc + 'kernel')), ptr(self.G(sc + 'bias')),
+             ptr(tr['edh0']), ptr(tr['edc0']), ptr(self.ws), self.ws_bytes, 3, st)
+        call('d2p_split_cols', ptr(tr['dX']), F + Pd, 0, F, T * R, ptr(tr['dfeat']), st)
+        call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(tr['dfeat']),
+             ptr(self.conv_saved), int(self.is_train), ptr(self.ws), self.ws_bytes, st)
+
+    def optimizer_step(self, world=1):
+        """clip_by_global_norm(20) + Adam, shared with the other models (reference trainer.py:102-109)."""
+        from .dp import allreduce_flat_gradients
+        scale = allreduce_flat_gradients(self.grads, world)
+        decay = 10000 if self.cfg.lr_weight_decay else 0
+        self._call('d2p_clip_adam_step', ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
+                   self.pm.total, self.lr, 0.9, 0.999, 1e-8, self.clip, scale, decay, ptr(self.adam_state),
+                   ptr(self.ws), self.ws_bytes, self._st())
+        self.lib.d2p_tc_new_step()
+
+    def train_step(self, batch, world=1):
+        """Public API: host batch in, loss out."""
+        self.stage_batch(batch)
+        self.forward_train()
+        self.backward_train()
+        self.optimizer_step(world)
+        loss = float(self.loss[0].item())
+        flags = C.c_int(0)
+        check(self.lib.d2p_device_error(C.byref(flags)), 'd2p_device_error')
+        if flags.value:
+            raise _lib.D2PError('a persistent-kernel step barrier timed out (flags=%d)' % flags.value)
+        return loss
+
+    def step_count(self):
+        return int(self.adam_state[0].item()) if hasattr(self, 'adam_state') else 0
+
+    def global_norm(self):
+        return float(self.adam_state[3].item())
+
     TIE_TOL = 2e-4     # see Engine.TIE_TOL
 
     def greedy(self, exact=None):
@@ -207,9 +380,10 @@ class InductionEngine:
 
 
 class InductionModel(object):
-    """Reference-facing facade for `--model induction_baseline` (evaluation only)."""
+    """Reference-facing facade for `--model induction_baseline`."""
 
-    def __init__(self, config, debug_information=False, is_train=True, global_step=None, **kw):
+    def __init__(self, config, debug_information=False, is_train=True, global_step=None, world_size=1, **kw):
+        self.world = int(world_size)
         from .config import D2PConfig
         from .model import config_from_namespace
         self.config = config if isinstance(config, D2PConfig) else config_from_namespace(config)
@@ -229,8 +403,12 @@ class InductionModel(object):
         return batch_chunk
 
     def run_train_step(self, feed):
-        raise NotImplementedError('training the induction baseline is outside the B200 hot path '
-                                  '(inference / greedy decode only)')
+        self.loss = self.engine.train_step(feed, world=self.world)
+        return self.loss
+
+    def run_train_steps(self, feeds):
+        for feed in feeds:
+            yield self.run_train_step(feed)
 
     def run_eval_step(self, feed, greedy=True):
         eng = self.engine

@@ -121,6 +121,23 @@ int d2p_lstm_seq_bwd(const float* X, int T, int R, int In, int H, const int* len
  * :620-657 (Sequence_Loss). tokens [R,L] int32; X [L,R,E]. */
 int d2p_embed_shifted(const float* table, int vocab_rows, int E, const int* tokens, int R, int L,
                       int start_id, float* X, void* stream);
+/* ---- scheduled sampling (reference models/model_full.py:59-67, 414-423; trainer.py:278-281) ----
+ * seq2seq.ScheduledEmbeddingTrainingHelper: after decoder step t a row feeds, with probability
+ * p = 1 - polynomial_decay(1.0 -> 0.1 over decay_steps)(global step), a token drawn from
+ * Categorical(logits_t) to step t+1 instead of the ground-truth token.  The decoder therefore runs
+ * step by step: d2p_embed_shifted_step (input row of step t from the tokens fed so far), one
+ * d2p_lstm_seq_fwd step with the 0/1 lengths of d2p_step_lens, the projection, then
+ * d2p_sched_sample_step, which writes fed_tokens[r, t] (and sampled[r, t] = 1 where it drew).
+ * The reference's draws are unseeded; here they are d2p_sched_hash(seed, global step, decoder, t, row,
+ * 0 | 1) / 2^32 (Bernoulli | inverse-CDF categorical), reproducible and restated by the oracle.
+ * adam_state[0] is the device-resident global step; p_override >= 0 replaces the schedule (tests). */
+int d2p_step_lens(const int* runlen, int R, int L, int* out /*[L,R]: t < runlen[r]*/, void* stream);
+int d2p_embed_shifted_step(const float* table, int vocab_rows, int E, const int* tokens, int R, int L, int t,
+                           int start_id, float* out, void* stream);
+int d2p_sched_sample_step(const float* logits, int R, int V, const int* gt_tokens, int L, int t,
+                          const double* adam_state, int decay_steps, float p_override, unsigned seed,
+                          int decoder, int* fed_tokens, int* sampled, void* stream);
+unsigned d2p_sched_hash(unsigned seed, unsigned step, unsigned decoder, unsigned t, unsigned r, unsigned which);
 size_t d2p_embed_shifted_bwd_ws_bytes(int vocab_rows, int E, int R, int L);
 int d2p_embed_shifted_bwd(const float* dX, int vocab_rows, int E, const int* tokens, int R, int L,
                           int start_id, float* dTable, void* ws, size_t ws_bytes, void* stream);
@@ -183,6 +200,23 @@ int d2p_induction_decode(const float* keys, const float* memory_layer, const flo
                          void* stream);
 /* out[row] = [A[row, :F1] ; B[row, :F2]]  (conv features ++ perception vector,
  * model_induction.py:399-424) */
+/* Training forms of the pooled Luong attention (the induction baseline is trained by the reference's
+ * trainer.py:102-109 through tf.gradients of models/baselines/model_induction.py:25-53, 107-182):
+ * _train_fwd also returns the attention weights alpha [B,k,tk,T] (zero past the memory length);
+ * _train_bwd takes dctx (gradient of the MEAN context, rows b*tk+j, stride ldd) and ACCUMULATES into
+ * dq (stride lddq), dkeys and dvalues [T, B*k, H]: one decoder step per call, every memory row owned by
+ * one CTA, fixed summation order. */
+size_t d2p_luong_pool_attention_train_ws_bytes(int B, int k, int tk, int H);
+int d2p_luong_pool_attention_train_fwd(const float* q, int ldq, const float* keys, const float* values,
+                                       const int* mem_len, int B, int k, int tk, int T, int H, float* ctx,
+                                       int ldc, float* alpha, void* ws, size_t ws_bytes, void* stream);
+int d2p_luong_pool_attention_train_bwd(const float* q, int ldq, const float* keys, const float* values,
+                                       const int* mem_len, const float* alpha, const float* dctx, int ldd,
+                                       int B, int k, int tk, int T, int H, float* dq, int lddq, float* dkeys,
+                                       float* dvalues, void* ws, size_t ws_bytes, void* stream);
+/* dst[row, :F1] = src[row, c0 : c0+F1] (rows of width F): the conv-feature part of the gradient of the
+ * [features ; perception] encoder input (model_induction.py:399-474; the perception vector is data) */
+int d2p_split_cols(const float* src, int F, int c0, int F1, long long rows, float* dst, void* stream);
 int d2p_concat_cols(const float* A, int F1, const float* Bm, int F2, long long rows, float* out,
                     void* stream);
 

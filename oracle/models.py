@@ -106,6 +106,20 @@ class OracleModel:
             self.p(d + 'basic_lstm_cell/bias'),
             self.p(d + 'output_projection/kernel'), max_len)
 
+    def token_decoder_scheduled(self, scope, h0, c0, gt_tokens, seq_len, max_len, vocab, sched, decoder, rows,
+                                replay=None):
+        """LSTM_Decoder with unroll_type='scheduled_sampling' (reference models/model_full.py:414-423)."""
+        table = self.p(scope + '/Token_Embedding/embedding_map')
+        d = scope + '/dynamic_decoder/'
+        p = sched.get('p_override', -1.0)
+        if p < 0:
+            p = T.scheduled_sampling_prob(sched['step'], self.cfg.scheduled_sampling_decay_steps)
+        return T.decode_scheduled(
+            lambda ids: T.embedding_lookup_gpu(table, ids), vocab + 1, gt_tokens, seq_len, c0, h0,
+            self.p(d + 'basic_lstm_cell/kernel'), self.p(d + 'basic_lstm_cell/bias'),
+            self.p(d + 'output_projection/kernel'), max_len, p, sched['seed'], sched['step'], decoder, rows,
+            replay=replay)
+
     def token_decoder_greedy(self, scope, h0, c0, max_len, vocab, end_id):
         table = self.p(scope + '/Token_Embedding/embedding_map')
         d = scope + '/dynamic_decoder/'
@@ -116,7 +130,10 @@ class OracleModel:
             self.p(d + 'output_projection/kernel'), max_len)
 
     # -- whole graphs -----------------------------------------------------------
-    def forward(self, batch, greedy=False):
+    def forward(self, batch, greedy=False, sched=None):
+        """sched (scheduled sampling): dict(step, seed[, p_override][, replay_program [B,L],
+        replay_action [B,k,T]]); the tokens fed / draws taken come back in out['fed_*'],
+        out['took_*'] and out['sched_mismatches']."""
         cfg, dt = self.cfg, self.dtype
         self.new_state = self.state.clone()   # moving stats advance once per forward
         s_h = torch.as_tensor(np.asarray(batch['s_h'])).to(dt)
@@ -159,8 +176,16 @@ class OracleModel:
         out['demo_h_summary'], out['demo_c_summary'] = h_sum, c_sum
 
         V, L = cfg.dim_program_token, cfg.max_program_len
-        logits = self.token_decoder('Program_Decoder', h_sum, c_sum, ptoks,
-                                    program_len, L, V)
+        if sched is not None:
+            out['sched_mismatches'] = []
+            logits, fed, took, mm = self.token_decoder_scheduled(
+                'Program_Decoder', h_sum, c_sum, ptoks, program_len, L, V, sched, 1,
+                np.arange(ptoks.shape[0]), replay=sched.get('replay_program'))
+            out['fed_program'], out['took_program'] = fed, took
+            out['sched_mismatches'] += mm
+        else:
+            logits = self.token_decoder('Program_Decoder', h_sum, c_sum, ptoks,
+                                        program_len, L, V)
         out['pred_program'] = logits.transpose(1, 2)           # [B,V,L]
         program_loss = T.softmax_ce_loss(logits, program.transpose(1, 2),
                                          program_len)
@@ -181,8 +206,17 @@ class OracleModel:
             act_loss, per_loss = 0, 0
             pa, pp, ga, galen = [], [], [], []
             for i in range(k):
-                lg = self.token_decoder('Action_Decoder', demo_h[i], demo_c[i],
-                                        a_tok[:, i], demo_len[:, i], Tm, A)
+                if sched is not None:
+                    rp = sched.get('replay_action')
+                    lg, fed, took, mm = self.token_decoder_scheduled(
+                        'Action_Decoder', demo_h[i], demo_c[i], a_tok[:, i], demo_len[:, i], Tm, A, sched, 2,
+                        np.arange(a_tok.shape[0]) * k + i, replay=None if rp is None else rp[:, i])
+                    out.setdefault('fed_action', []).append(fed)
+                    out.setdefault('took_action', []).append(took)
+                    out['sched_mismatches'] += mm
+                else:
+                    lg = self.token_decoder('Action_Decoder', demo_h[i], demo_c[i],
+                                            a_tok[:, i], demo_len[:, i], Tm, A)
                 pa.append(lg)
                 act_loss = act_loss + T.softmax_ce_loss(lg, a_h[:, i],
                                                         demo_len[:, i])
@@ -292,11 +326,14 @@ class OracleModel:
             out['greedy_pred_action_len'] = torch.stack(g_lens, 1)
         return out
 
-    def loss_and_grad(self, batch):
+    def loss_and_grad(self, batch, sched=None):
         """Returns (loss float, flat grad tensor, outputs)."""
         if self.flat.grad is not None:
             self.flat.grad = None
-        out = self.forward(batch)
+        if self.cfg.model == 'induction_baseline':
+            out = self.forward_induction(batch)
+        else:
+            out = self.forward(batch, sched=sched)
         out['loss'].backward()
         return float(out['loss'].detach()), self.flat.grad.detach().clone(), out
 

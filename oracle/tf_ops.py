@@ -164,6 +164,83 @@ def decode_greedy(embed_fn, start_id, end_id, c0, h0, kernel, bias, proj,
     return logits, lengths, tokens
 
 
+# ---- scheduled sampling (reference models/model_full.py:59-67, 414-423) -----------------------
+def _mix32(x):
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7feb352d) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846ca68b) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def sched_hash(seed, step, decoder, t, r, which):
+    """The counter-based draw of csrc/sched_sample.cu (d2p_sched_hash), restated."""
+    h = _mix32(seed + 0x9E3779B9)
+    h = _mix32(h ^ step)
+    h = _mix32(h + decoder)
+    h = _mix32(h ^ t)
+    h = _mix32(h + r)
+    h = _mix32(h ^ which)
+    return h
+
+
+def scheduled_sampling_prob(step, decay_steps):
+    """1 - tf.train.polynomial_decay(1.0, step, decay_steps, end_learning_rate=0.1, power=1.0):
+    the probability of feeding a sampled token (ScheduledEmbeddingTrainingHelper's
+    sampling_probability = 1 - sample_prob)."""
+    frac = min(float(step), float(decay_steps)) / float(decay_steps)
+    return 1.0 - ((1.0 - 0.1) * (1.0 - frac) + 0.1)
+
+
+def decode_scheduled(embed_fn, start_id, gt_tokens, seq_len, c0, h0, kernel, bias, proj, max_len,
+                     p, seed, step, decoder, rows, replay=None, tol=1e-4):
+    """dynamic_decode(BasicDecoder(cell, ScheduledEmbeddingTrainingHelper(...))): like
+    decode_training, but after step t row r feeds, if p > u1, a token drawn from
+    Categorical(logits_t[r]) (inverse CDF at u2) to step t+1, else the ground-truth token.
+    u1 / u2 = sched_hash(seed, step, decoder, t, rows[r], 0 / 1) / 2^32.
+    replay [R, max_len] (the tokens another implementation fed): followed whenever this
+    restatement's own draw differs; differences further than `tol` (of the total mass) from a CDF
+    boundary are returned as mismatches.  Returns (logits, fed tokens, took mask, mismatches)."""
+    import numpy as np
+    R = c0.shape[0]
+    n_iter = max(int(min(int(seq_len.max()), max_len)), 1)
+    c, h = c0, h0
+    ids = torch.full((R,), start_id, dtype=torch.long)
+    fed = gt_tokens.clone().long()
+    took = torch.zeros_like(fed)
+    outs, mismatches = [], []
+    for t in range(n_iter):
+        c, h = lstm_cell(embed_fn(ids), c, h, kernel, bias)
+        logit = h @ proj
+        outs.append(logit)
+        lg = logit.detach().double().numpy()
+        for r in range(R):
+            u1 = sched_hash(seed, step, decoder, t, int(rows[r]), 0) / 4294967296.0
+            if not p > u1:
+                continue
+            took[r, t] = 1
+            e = np.exp(lg[r] - lg[r].max())
+            cdf = np.cumsum(e)
+            u2 = float(np.float32(sched_hash(seed, step, decoder, t, int(rows[r]), 1) / 4294967296.0))
+            target = u2 * cdf[-1]
+            own = int(np.argmax(cdf > target)) if (cdf > target).any() else len(e) - 1
+            tok = own
+            if replay is not None and int(replay[r, t]) != own:
+                tok = int(replay[r, t])
+                lo, hi = min(own, tok), max(own, tok)
+                # the draw sits within tol of every CDF boundary between the two answers
+                if not all(abs(cdf[v] - target) <= tol * cdf[-1] for v in range(lo, hi)):
+                    mismatches.append((decoder, t, r, own, tok))
+            fed[r, t] = tok
+        ids = fed[:, t]
+    logits = torch.stack(outs, 1)
+    if n_iter < max_len:
+        logits = torch.cat([logits, logits.new_zeros(R, max_len - n_iter, logits.shape[2])], 1)
+    return logits, fed, took, mismatches
+
+
 def sequence_mask(lengths, max_len, dtype):
     return (torch.arange(max_len, device=lengths.device)[None, :] <
             lengths[:, None]).to(dtype)

@@ -649,3 +649,61 @@ def test_token_table_decoders_match_row_products(model, B, k, use_graph):
     for e in pm:
         a, b = g0[e.offset:e.offset + e.size], g1[e.offset:e.offset + e.size]
         assert np.abs(a - b).max() < 2e-5 * np.abs(a).max() + 1e-7 * gmax, e.name
+
+
+@pytest.mark.parametrize('use_tc', [False, True])
+def test_induction_training_step_matches_oracle(use_tc):
+    """Training the induction baseline (reference trainer.py:102-109 over
+    models/baselines/model_induction.py:788-819): loss and every gradient of the attention decoder,
+    the memory layer, the demonstration encoder and the frame encoder against the fp64 oracle's
+    autograd, then 3 optimizer steps."""
+    from oracle.models import OracleTrainer
+    from demo2program_b200.induction import InductionEngine
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    cfg = karel_config('induction_baseline', batch_size=4, k=3)
+    pm, sm = build_manifests(cfg)
+    p0, s0 = pm.init_flat(2), sm.init_flat(2)
+    rs = np.random.RandomState(19)
+    for e in pm:
+        if e.name.endswith('/beta') or e.name.endswith('biases') or e.name.endswith('/bias'):
+            p0[e.offset:e.offset + e.size] = rs.uniform(-0.1, 0.1, e.size)
+        if e.name.endswith('/gamma'):
+            p0[e.offset:e.offset + e.size] = rs.uniform(0.8, 1.2, e.size)
+    batch = make_batch(cfg, seed=3)
+    orc = OracleTrainer(cfg, p0, s0, dtype=torch.float64)
+    loss_o, grad_o, out = orc.model.loss_and_grad(batch)
+    eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=True, use_tc=use_tc)
+    eng.stage_batch(batch)
+    eng.forward_train()
+    eng.backward_train()
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss[0]) - loss_o) < LOSS_TOL
+    pred = eng.logits.permute(1, 0, 2).reshape(cfg.batch_size, cfg.test_k, cfg.max_demo_len, cfg.action_space)
+    assert rel_err(pred.cpu().numpy(), out['pred_action'].detach().numpy()) < 1e-4
+    g, go = eng.grads.cpu().numpy(), grad_o.numpy()
+    gmax = np.abs(go).max()
+    tol = 1e-3 if use_tc else GRAD_TOL
+    bad = []
+    for e in pm:
+        a, b = g[e.offset:e.offset + e.size], go[e.offset:e.offset + e.size]
+        if not np.abs(a - b).max() < tol * np.abs(b).max() + 1e-5 * gmax:
+            bad.append((e.name, float(np.abs(a - b).max()), float(np.abs(b).max())))
+    assert not bad, bad
+    eng = InductionEngine(cfg, flat_params=p0, flat_state=s0, is_train=True, use_tc=use_tc)
+    orc = OracleTrainer(cfg, p0, s0, dtype=torch.float64)
+    for step in range(3):
+        lo, norm_o, _ = orc.train_step(batch)
+        le = eng.train_step(batch)
+        assert abs(le - lo) < LOSS_TOL, (step, le, lo)
+        assert abs(eng.global_norm() - norm_o) < 5e-4 * max(1.0, norm_o)
+    assert eng.step_count() == 3
+
+
+def test_trainer_cli_trains_the_induction_baseline(tmp_path, monkeypatch):
+    """`trainer.py --model induction_baseline` runs (it raised at the first step)."""
+    import trainer, glob
+    monkeypatch.chdir(tmp_path)
+    trainer.main(['--model', 'induction_baseline', '--dataset_path', 'synthetic:32', '--num_k', '2',
+                  '--batch_size', '4', '--max_steps', '3', '--log_step', '1', '--test_sample_step', '2'])
+    assert glob.glob(str(tmp_path / 'train_dir' / '*' / 'model-*.npz'))

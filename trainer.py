@@ -204,9 +204,10 @@ def main(argv=None):
                         help='(addition) stop after this many steps')
     add_model_flags(parser)
     config = parser.parse_args(argv)
-    if config.scheduled_sampling:
-        raise ValueError('scheduled sampling is unseeded/non-deterministic in the reference and is '
-                         'out of scope of the B200 path')
+    if config.scheduled_sampling and config.model == 'induction_baseline':
+        raise ValueError('--scheduled_sampling: the step-by-step sampling decoder is built for the program / '
+                         'action token decoders (full, summarizer, synthesis_baseline), not for the attention '
+                         'decoder of induction_baseline')
     # one process per GPU (torchrun); single process otherwise
     config.rank = int(os.environ.get('RANK', '0'))
     config.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
