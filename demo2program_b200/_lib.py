@@ -126,6 +126,7 @@ SIGNATURES = {
     'd2p_debug_set_probe': (_i, [_fp]),
     'd2p_lstm_set_persistent': (_i, [_i]),
     'd2p_conv_set_fused': (_i, [_i]),
+    'd2p_conv_set_tc': (_i, [_i]),
     'd2p_device_error': (_i, [_fp]),
     'd2p_device_error_async': (_i, [_fp, _fp]),
     'd2p_debug_inject_device_error': (_i, [_i]),

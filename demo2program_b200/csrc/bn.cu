@@ -405,6 +405,59 @@ int bn_forward_stats(cudaStream_t st, const float* X, long long rows, int C, int
     return 0;
 }
 
+// one warp per (channel, slice): statistics from the partials; the moving averages follow in bn_moving_update
+__global__ void bn_fwd_finalize_par(const float2* __restrict__ partial, int nchunk, int C, int nsl, double count,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                    float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ var_out) {
+    const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32, sl = blockIdx.y;
+    if (c >= C) return;
+    double s = 0.0, s2 = 0.0;
+    for (int j = lane; j < nchunk; j += 32) {
+        const float2 p = partial[((size_t)sl * nchunk + j) * C + c];
+        s += p.x; s2 += p.y;
+    }
+    s = warp_sum_d(s); s2 = warp_sum_d(s2);
+    const double mu = s / count;
+    double var = s2 / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    if (lane == 0) {
+        const float muf = (float)mu, rs = (float)(1.0 / sqrt(var + (double)eps)), g = gamma[c];
+        mean_out[sl * C + c] = muf; rstd_out[sl * C + c] = rs;
+        scale[sl * C + c] = g * rs; shift[sl * C + c] = beta[c] - muf * g * rs;
+        var_out[sl * C + c] = (float)var;
+    }
+}
+// slices in order, as the reference updates the moving statistics once per reuse call (i = 0..k-1)
+__global__ void bn_moving_update(const float* __restrict__ mean, const float* __restrict__ var, int C, int nsl,
+                                 float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mm = moving_mean[c], mv = moving_var[c];
+    for (int sl = 0; sl < nsl; ++sl) {
+        mm -= (mm - mean[sl * C + c]) * (1.f - decay);
+        mv -= (mv - var[sl * C + c]) * (1.f - decay);
+    }
+    moving_mean[c] = mm; moving_var[c] = mv;
+}
+
+// Train-mode statistics from (sum, sum of squares) partials produced elsewhere (the tensor-core
+// convolution's epilogue): partial[(sl*nchunk + chunk)*C + c], `count` rows per slice.
+int bn_forward_finalize(cudaStream_t st, const float2* partial, int nchunk, long long count, int C, int nsl,
+                        const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                        float* stats) {
+    float* mean = stats; float* rstd = stats + (size_t)nsl * C;
+    float* scale = rstd + (size_t)nsl * C; float* shift = scale + (size_t)nsl * C;
+    float* var = (float*)(partial + (size_t)nsl * nchunk * C);   // [nsl, C] behind the partials
+    bn_fwd_finalize_par<<<dim3(cdiv(C, 8), nsl), 256, 0, st>>>(partial, nchunk, C, nsl, (double)count, gamma, beta,
+                                                                1e-3f, mean, rstd, scale, shift, var);
+    D2P_CHECK_LAUNCH();
+    bn_moving_update<<<cdiv(C, 128), 128, 0, st>>>(mean, var, C, nsl, 0.9f, moving_mean, moving_var);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
 int bn_apply(cudaStream_t st, const float* X, float* Y, long long rows, int C, int seg, int nsl,
              const float* stats, int permT, int permR) {
     const float* scale = stats + 2 * (size_t)nsl * C;

@@ -15,9 +15,12 @@
 // TF SAME geometry: pad_before = pad_total / 2, so every
 // Karel layer and ViZDoom L1-L4 pad (0 top/left, 1 bottom/right).
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace d2p {
 
+int bn_forward_finalize(cudaStream_t, const float2*, int, long long, int, int, const float*, const float*, float*,
+                        float*, float*);
 int bn_forward_stats(cudaStream_t, const float*, long long, int, int, int, const float*,
                      const float*, float*, float*, int, float*, void*, size_t);
 int bn_apply(cudaStream_t, const float*, float*, long long, int, int, int, const float*, int, int);
@@ -43,9 +46,7 @@ namespace {
 constexpr int PX = 32;          // output pixels per tile
 constexpr int MAXC = 48;        // max channels of any layer on the path
 
-struct Geo {
-    int N, IH, IW, CIN, OH, OW, COUT, PT, PL, T, k;
-};
+typedef ConvGeo Geo;
 
 template <typename IN_T>
 __device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (float)in[idx]; }
@@ -181,14 +182,15 @@ static size_t stat_floats(const Geo& g) { return (size_t)4 * g.k * g.COUT; }
 // scratch carve-up shared by fwd/bwd: dZ | dY | dy_tmp | coef | partials
 struct Plan {
     Geo geo[D2P_MAX_CONV_LAYERS];
-    size_t off_dz, off_dy, off_tmp, off_coef, off_part, part_bytes, total;
+    size_t off_dz, off_dy, off_tmp, off_coef, off_part, part_bytes, off_tc, tc_bytes, total;
 };
 
 static void make_plan(const d2p_conv_desc* d, Plan* p) {
-    size_t max_act = 0, max_in = 0, max_kc = 0, max_part = 0;
+    size_t max_act = 0, max_in = 0, max_kc = 0, max_part = 0, max_tc = 0;
     for (int l = 0; l < d->n_layers; ++l) {
         Geo& g = p->geo[l];
         fill_geo(d, l, &g);
+        if (l > 0 && conv_tc_supported(g) && conv_tc_ws_bytes(g) > max_tc) max_tc = conv_tc_ws_bytes(g);
         size_t a = act_floats(g);
         size_t i = (size_t)g.N * g.IH * g.IW * g.CIN;
         if (a > max_act) max_act = a;
@@ -215,7 +217,9 @@ static void make_plan(const d2p_conv_desc* d, Plan* p) {
     p->off_coef = p->off_tmp + al(max_act * sizeof(float));
     p->off_part = p->off_coef + al(2 * max_kc * sizeof(float));
     p->part_bytes = al(max_part);
-    p->total = p->off_part + p->part_bytes;
+    p->off_tc = p->off_part + p->part_bytes;
+    p->tc_bytes = al(max_tc);
+    p->total = p->off_tc + p->tc_bytes;
 }
 
 namespace {
@@ -294,13 +298,25 @@ extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, 
         const float* sc = prev_stats ? prev_stats + 2 * (size_t)g.k * g.CIN : nullptr;
         const float* sh = prev_stats ? prev_stats + 3 * (size_t)g.k * g.CIN : nullptr;
         (void)blocks;
-        if (l == 0 && d->frames_dtype == D2P_U8)
+        bool stats_done = false;
+        if (l > 0 && (conv_tc_mode() & 1) && conv_tc_supported(g)) {
+            // tensor-core implicit GEMM; the BatchNorm (sum, sum of squares) partials come from its epilogue
+            int nchunk = 0; float2* partial = nullptr;
+            D2P_TRY(conv_tc_fwd(st, g, prev, sc, sh, L.w, L.b, act, training, &nchunk, &partial, wsb + p.off_tc,
+                                p.tc_bytes));
+            if (training) {
+                D2P_TRY(bn_forward_finalize(st, partial, nchunk, npix / g.k, g.COUT, g.k, L.gamma, L.beta,
+                                            L.moving_mean, L.moving_var, stats));
+                stats_done = true;
+            }
+        } else if (l == 0 && d->frames_dtype == D2P_U8)
             D2P_TRY(launch_conv_fwd<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, L.w, L.b, act));
         else
             D2P_TRY(launch_conv_fwd<float>(st, g, l == 0 ? (const float*)frames : prev, sc, sh, L.w, L.b, act));
-        D2P_TRY(bn_forward_stats(st, act, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma, L.beta,
-                                 L.moving_mean, L.moving_var, training, stats, wsb + p.off_part,
-                                 p.part_bytes));
+        if (!stats_done)
+            D2P_TRY(bn_forward_stats(st, act, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma, L.beta,
+                                     L.moving_mean, L.moving_var, training, stats, wsb + p.off_part,
+                                     p.part_bytes));
         prev = act; prev_stats = stats;
         if (l == d->n_layers - 1) {
             // feature = BN(a_L) flattened HWC, written time-major [T, R, F]
@@ -359,18 +375,24 @@ extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, 
         int ppb; int nblk = dw_blocks(npix, &ppb);
         const float* sc = l > 0 ? stats[l - 1] + 2 * (size_t)g.k * g.CIN : nullptr;
         const float* sh = l > 0 ? stats[l - 1] + 3 * (size_t)g.k * g.CIN : nullptr;
-        if (l == 0 && d->frames_dtype == D2P_U8)
-            D2P_TRY(launch_conv_dw<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, nblk, (float*)part));
-        else
-            D2P_TRY(launch_conv_dw<float>(st, g, l == 0 ? (const float*)frames : acts[l - 1], sc, sh, dZ, ppb, nblk, (float*)part));
-        int nw = 9 * g.CIN * g.COUT;
-        conv_dw_reduce<<<cdiv(nw, 256), 256, 0, st>>>((const float*)part, nblk, nw, L.dw);
-        D2P_CHECK_LAUNCH();
+        const bool tc_ok = l > 0 && conv_tc_supported(g);
+        if (tc_ok && (conv_tc_mode() & 4)) {
+            D2P_TRY(conv_tc_dw(st, g, acts[l - 1], sc, sh, dZ, L.dw, wsb + p.off_tc, p.tc_bytes));
+        } else {
+            if (l == 0 && d->frames_dtype == D2P_U8)
+                D2P_TRY(launch_conv_dw<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, nblk, (float*)part));
+            else
+                D2P_TRY(launch_conv_dw<float>(st, g, l == 0 ? (const float*)frames : acts[l - 1], sc, sh, dZ, ppb, nblk, (float*)part));
+            int nw = 9 * g.CIN * g.COUT;
+            conv_dw_reduce<<<cdiv(nw, 256), 256, 0, st>>>((const float*)part, nblk, nw, L.dw);
+            D2P_CHECK_LAUNCH();
+        }
         if (l > 0) {
             D2P_REQUIRE(g.CIN % 4 == 0, "conv bwd: CIN %% 4");
-            long long nin = (long long)g.N * g.IH * g.IW;
-            (void)nin;
-            D2P_TRY(launch_conv_dx(st, g, dZ, L.w, dY));
+            if (tc_ok && (conv_tc_mode() & 2))
+                D2P_TRY(conv_tc_dx(st, g, dZ, L.w, dY, wsb + p.off_tc, p.tc_bytes));
+            else
+                D2P_TRY(launch_conv_dx(st, g, dZ, L.w, dY));
         }
     }
     return 0;

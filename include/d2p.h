@@ -83,6 +83,12 @@ int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float
  * (conv -> lrelu -> BatchNorm x3, activations in shared memory, per-slice statistics exchanged
  * among the CTAs of a slice); 0: one kernel sequence per layer (always used for ViZDoom). */
 int d2p_conv_set_fused(int mode);
+/* Per-layer path, layers with 16/32/48 input channels (ViZDoom conv2-5, Karel conv2-3; replaces the
+ * same slim.conv2d call, models/ops.py:27-33, and its gradients): bit 0 = forward, bit 1 = input
+ * gradient, bit 2 = weight gradient run as tcgen05 implicit-GEMM kernels (bf16x3 split, no im2col
+ * buffer) whenever the tensor-core arena is configured (d2p_tc_configure).  Default 7; returns the
+ * previous mode.  0 keeps the fp32 CUDA-core kernels (the A/B reference of the parity tests). */
+int d2p_conv_set_tc(int mode);
 
 /* ---- K2/K3: LSTM over a sequence -------------------------------------------
  * reference models/model_full.py:244-258 (Demo_Encoder), :265-277

@@ -30,6 +30,10 @@ class OracleModel:
         self.flat.requires_grad_(True)
         self.state = torch.tensor(np.asarray(flat_state), dtype=dtype)
         self.new_state = self.state.clone()
+        # test hook: conv_slope_hook(layer, pre_activation, lrelu_value) -> tensor with the same values whose
+        # backward uses a slope pattern chosen by the caller (lrelu is not differentiable at 0: a path whose
+        # forward rounds differently picks the other one-sided slope for activations within rounding of 0)
+        self.conv_slope_hook = None
 
     # -- parameter access ---------------------------------------------------
     def p(self, name):
@@ -68,7 +72,10 @@ class OracleModel:
             sc = 'Demo_Encoder/State_Encoder/conv%d' % (li + 1)
             x = T.conv2d_3x3_s2_same(x, self.p(sc + '/Conv/weights'),
                                      self.p(sc + '/Conv/biases'))
-            x = self._bn(T.lrelu(x), sc + '/bn_act')
+            a = T.lrelu(x)
+            if self.conv_slope_hook is not None:
+                a = self.conv_slope_hook(li, x, a)
+            x = self._bn(a, sc + '/bn_act')
         return x.reshape(x.shape[0], -1)
 
     def demo_encoder(self, s_h_i, len_i, per_i=None):

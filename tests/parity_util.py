@@ -38,3 +38,45 @@ def per_var_errors(pm, flat_a, flat_b):
         b = flat_b[e.offset:e.offset + e.size]
         out[e.name] = rel_err(a, b)
     return out
+
+
+class ConvSlopeHook:
+    """OracleModel.conv_slope_hook that makes the oracle's backward pass use the lrelu slopes the ENGINE
+    used (read from its saved conv activations).  lrelu has a kink at 0: a forward pass that rounds
+    differently (bf16x3 tensor-core products: ~5e-6 of the largest activation) lands a handful of
+    activations on the other side of 0 and so picks the other one-sided derivative (1 vs 0.2) - a
+    legitimate sub-gradient, but a discrete 0.8x change of that element's contribution which a
+    max-abs gradient criterion sees.  The hook keeps the oracle's forward VALUES, counts the sign
+    disagreements (`mismatch`, with the largest |a| at which one occurs relative to the layer's max in
+    `worst_rel`) and applies the engine's slope pattern in backward, so the gradient comparison that
+    follows is tight again; the test asserts separately that disagreements are rare and only at |a| ~ 0."""
+
+    def __init__(self, eng, cfg):
+        import numpy as np
+        d = eng.conv_desc
+        saved = eng.conv_saved.cpu().numpy()
+        B, k, Tm = cfg.batch_size, cfg.k, cfg.max_demo_len
+        self.acts, off, ih, iw = [], 0, cfg.h, cfg.w
+        for l in range(d.n_layers):
+            oh, ow, c = (ih + 1) // 2, (iw + 1) // 2, d.layers[l].cout
+            na = B * k * Tm * oh * ow * c
+            self.acts.append(saved[off:off + na].reshape(B, k, Tm, oh, ow, c))
+            off += na + 4 * k * c
+            ih, iw = oh, ow
+        self.calls = [0] * d.n_layers
+        self.k = k
+        self.mismatch, self.total, self.worst_rel = 0, 0, 0.0
+
+    def __call__(self, li, x, a):
+        i = self.calls[li] % self.k
+        self.calls[li] += 1
+        ae = torch.from_numpy(np.ascontiguousarray(self.acts[li][:, i])).reshape(a.shape).to(a.dtype)
+        slope = torch.where(ae > 0, torch.ones_like(a), torch.where(ae < 0, torch.full_like(a, 0.2),
+                                                                     torch.full_like(a, 0.6)))
+        ad = a.detach()
+        bad = (torch.sign(ad) != torch.sign(ae))
+        self.mismatch += int(bad.sum())
+        self.total += ad.numel()
+        if bad.any():
+            self.worst_rel = max(self.worst_rel, float(ad[bad].abs().max() / ad.abs().max()))
+        return x * slope + (ad - (x * slope).detach())

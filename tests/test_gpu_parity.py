@@ -563,6 +563,58 @@ def test_fused_conv_encoder_matches_layered(B, k, dtype, train):
     assert rel_err(b['grads'], a['grads']) < 1e-4
 
 
+def _run_conv_tc(cfg, batch, mode):
+    from demo2program_b200 import _lib
+    from demo2program_b200.engine import Engine
+    lib = _lib.load()
+    lib.d2p_conv_set_tc(mode)
+    lib.d2p_conv_set_fused(0)
+    try:
+        eng = Engine(cfg, use_graph=False)
+        eng.stage_batch(batch)
+        eng.forward()
+        eng.backward()
+        torch.cuda.synchronize()
+        eng.check_device()
+        return {'loss': float(eng.loss[0]), 'feat': eng.feat.cpu().numpy().copy(),
+                'saved': eng.conv_saved.cpu().numpy().copy(), 'state': eng.state.cpu().numpy().copy(),
+                'grads': eng.grads.cpu().numpy().copy()}
+    finally:
+        lib.d2p_conv_set_tc(7)
+        lib.d2p_conv_set_fused(1)
+
+
+@pytest.mark.parametrize('which', ['vizdoom', 'karel'])
+def test_tensor_core_conv_matches_cuda_core(which):
+    """csrc/conv_tc.cu (tcgen05 implicit GEMM: forward with the BatchNorm partial sums in its epilogue,
+    input gradient per parity class incl. the (1,1)-padded 5 -> 3 layer, weight gradient with MN-major
+    operands) against the fp32 CUDA-core kernels, one d2p_conv_set_tc bit at a time.  Forward:
+    activations, statistics, features and moving statistics to bf16x3 accuracy.  The gradient kernels
+    are switched on with the forward left on the CUDA cores, so both runs see identical activations
+    (no lrelu-slope ambiguity) and every gradient must agree to 3e-5 of its variable's largest entry."""
+    from demo2program_b200.config import vizdoom_config
+    from demo2program_b200.manifest import build_manifests
+    from demo2program_b200.synthetic import make_batch
+    if which == 'vizdoom':
+        cfg = vizdoom_config('full', batch_size=8, k=3, max_demo_len=8, test_k=2, max_program_len=8)
+    else:
+        cfg = karel_config('full', batch_size=8, k=3)      # per-layer path: conv2 (16->32) and conv3 (32->48)
+    batch = make_batch(cfg, seed=3)
+    ref = _run_conv_tc(cfg, batch, 0)
+    fwd = _run_conv_tc(cfg, batch, 1)
+    assert abs(fwd['loss'] - ref['loss']) < 1e-5
+    assert rel_err(fwd['feat'], ref['feat']) < 5e-5
+    assert rel_err(fwd['saved'], ref['saved']) < 2e-5
+    assert rel_err(fwd['state'], ref['state']) < 2e-5
+    pm, _ = build_manifests(cfg)
+    for mode in (2, 4, 6):
+        out = _run_conv_tc(cfg, batch, mode)
+        assert out['loss'] == ref['loss'] and np.array_equal(out['saved'], ref['saved'])
+        for e in pm:
+            a, b = out['grads'][e.offset:e.offset + e.size], ref['grads'][e.offset:e.offset + e.size]
+            assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max() + 1e-7 * np.abs(ref['grads']).max(), (mode, e.name)
+
+
 @pytest.mark.parametrize('model,B,k', [('full', 32, 10), ('full', 4, 3), ('synthesis_baseline', 8, 2)])
 def test_persistent_recurrence_matches_per_step(model, B, k):
     """lstm_persist.cu (one cooperative kernel per sequence) against one launch per step."""
