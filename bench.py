@@ -353,7 +353,8 @@ def run_ours(args):
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group('nccl', device_id=torch.device(dev))
+            from demo2program_b200.dp import init_nccl
+            init_nccl(dev)
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()

@@ -43,6 +43,8 @@ int conv_fused_bwd(cudaStream_t st, const d2p_conv_desc* d, const void* frames, 
 
 namespace {
 
+int g_conv_rgb = 1;             // d2p_conv_set_tc bit 4 clear: the direct RGB-layer forward kernel
+
 constexpr int PX = 32;          // output pixels per tile
 constexpr int MAXC = 48;        // max channels of any layer on the path
 
@@ -52,6 +54,91 @@ template <typename IN_T>
 __device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (float)in[idx]; }
 
 #include "conv_v2.cuh"
+// RGB input layer (CIN = 3, COUT = 16, u8 frames), forward: one thread per output pixel, the 27 x 16 weights as
+// broadcast float4 reads from shared memory, a = lrelu(conv + bias) written as one 64-byte row, and the
+// BatchNorm (sum, sum of squares) of the block's pixels reduced in a fixed order into
+// partial[(slice*nchunk + chunk)*16 + c] (a block never straddles a demonstration, i.e. a slice).
+constexpr int RGB_THREADS = 256, RGB_PPT = 4;
+__global__ void __launch_bounds__(RGB_THREADS)
+conv_rgb_fwd_kernel(Geo g, const uint8_t* __restrict__ in, const float* __restrict__ W,
+                    const float* __restrict__ bias, float* __restrict__ out, float2* __restrict__ partial,
+                    int cpd, int nchunk) {
+    __shared__ float4 ws[27 * 4];
+    __shared__ float4 bs[4];
+    __shared__ float red[RGB_THREADS / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 27 * 4; i += RGB_THREADS) ws[i] = reinterpret_cast<const float4*>(W)[i];
+    if (tid < 4) bs[tid] = reinterpret_cast<const float4*>(bias)[tid];
+    __syncthreads();
+    const int r = blockIdx.x / cpd, j = blockIdx.x - r * cpd;
+    const int HW = g.OH * g.OW, P = g.T * HW;
+    const int q0 = j * (RGB_THREADS * RGB_PPT);
+    float s1[16], s2[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    for (int it = 0; it < RGB_PPT; ++it) {
+        const int q = q0 + it * RGB_THREADS + tid;
+        if (q >= P) break;
+        const int t = q / HW, rem = q - t * HW, oy = rem / g.OW, ox = rem - oy * g.OW;
+        const uint8_t* fin = in + (size_t)(r * g.T + t) * g.IH * g.IW * 3;
+        float acc[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            acc[4 * c4] = bs[c4].x; acc[4 * c4 + 1] = bs[c4].y; acc[4 * c4 + 2] = bs[c4].z; acc[4 * c4 + 3] = bs[c4].w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy + ky - g.PT;
+            if (iy < 0 || iy >= g.IH) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox + kx - g.PL;
+                if (ix < 0 || ix >= g.IW) continue;
+                const uint8_t* px = fin + ((size_t)iy * g.IW + ix) * 3;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = (float)__ldg(px + ci);
+                    const float4* w = ws + ((ky * 3 + kx) * 3 + ci) * 4;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 ww = w[c4];
+                        acc[4 * c4] = fmaf(v, ww.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)r * P + q) * 16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { acc[c] = lrelu_f(acc[c]); s1[c] += acc[c]; s2[c] = fmaf(acc[c], acc[c], s2[c]); }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) o[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+    }
+    if (partial == nullptr) return;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        s1[c] = warp_sum(s1[c]); s2[c] = warp_sum(s2[c]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { red[warp][c] = s1[c]; red[warp][16 + c] = s2[c]; }
+    }
+    __syncthreads();
+    if (tid < 16) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < RGB_THREADS / 32; ++w) { a += red[w][tid]; b += red[w][16 + tid]; }
+        const int chunk = (r / g.k) * cpd + j, sl = r % g.k;
+        partial[((size_t)sl * nchunk + chunk) * 16 + tid] = make_float2(a, b);
+    }
+}
+inline int rgb_cpd(const Geo& g) { return cdiv((long long)g.T * g.OH * g.OW, RGB_THREADS * RGB_PPT); }
+inline bool rgb_fwd_supported(const d2p_conv_desc* d, const Geo& g) {
+    return d->frames_dtype == D2P_U8 && g.CIN == 3 && g.COUT == 16 && g.N % g.T == 0 && (g.N / g.T) % g.k == 0;
+}
+inline size_t rgb_fwd_ws_bytes(const Geo& g) {
+    return ((size_t)g.k * (g.N / g.T / g.k) * rgb_cpd(g) * 16 * 2 + (size_t)g.k * 16) * sizeof(float);
+}
+
 // dW[tap, o] += sum_blk partial[blk, tap, o]
 __global__ void conv_dw_reduce(const float* __restrict__ partial, int nblk, int n,
                                float* __restrict__ dW) {
@@ -191,6 +278,9 @@ static void make_plan(const d2p_conv_desc* d, Plan* p) {
         Geo& g = p->geo[l];
         fill_geo(d, l, &g);
         if (l > 0 && conv_tc_supported(g) && conv_tc_ws_bytes(g) > max_tc) max_tc = conv_tc_ws_bytes(g);
+        if (l == 0 && rgb_fwd_supported(d, g) && rgb_fwd_ws_bytes(g) > max_tc) max_tc = rgb_fwd_ws_bytes(g);
+        if (l == 0 && d->frames_dtype == D2P_U8 && conv_tc_dw3_supported(g) && conv_tc_dw3_ws_bytes(g) > max_tc)
+            max_tc = conv_tc_dw3_ws_bytes(g);
         size_t a = act_floats(g);
         size_t i = (size_t)g.N * g.IH * g.IW * g.CIN;
         if (a > max_act) max_act = a;
@@ -255,6 +345,8 @@ int unpermute_frames(cudaStream_t st, const float* X, float* Y, int N, int F, in
 
 using namespace d2p;
 
+namespace d2p { void conv_set_rgb(int on) { g_conv_rgb = on; } }
+
 extern "C" size_t d2p_conv_encoder_saved_floats(const d2p_conv_desc* d) {
     if (check_desc(d)) return 0;
     size_t n = 0;
@@ -304,6 +396,18 @@ extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, 
             int nchunk = 0; float2* partial = nullptr;
             D2P_TRY(conv_tc_fwd(st, g, prev, sc, sh, L.w, L.b, act, training, &nchunk, &partial, wsb + p.off_tc,
                                 p.tc_bytes));
+            if (training) {
+                D2P_TRY(bn_forward_finalize(st, partial, nchunk, npix / g.k, g.COUT, g.k, L.gamma, L.beta,
+                                            L.moving_mean, L.moving_var, stats));
+                stats_done = true;
+            }
+        } else if (l == 0 && g_conv_rgb && rgb_fwd_supported(d, g)) {
+            // RGB input layer: direct kernel with the BatchNorm partial sums fused
+            const int cpd = rgb_cpd(g), nchunk = (g.N / g.T / g.k) * cpd;
+            float2* partial = training ? (float2*)(wsb + p.off_tc) : nullptr;
+            conv_rgb_fwd_kernel<<<(g.N / g.T) * cpd, RGB_THREADS, 0, st>>>(g, (const uint8_t*)frames, L.w, L.b, act,
+                                                                         partial, cpd, nchunk);
+            D2P_CHECK_LAUNCH();
             if (training) {
                 D2P_TRY(bn_forward_finalize(st, partial, nchunk, npix / g.k, g.COUT, g.k, L.gamma, L.beta,
                                             L.moving_mean, L.moving_var, stats));
@@ -378,6 +482,8 @@ extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, 
         const bool tc_ok = l > 0 && conv_tc_supported(g);
         if (tc_ok && (conv_tc_mode() & 4)) {
             D2P_TRY(conv_tc_dw(st, g, acts[l - 1], sc, sh, dZ, L.dw, wsb + p.off_tc, p.tc_bytes));
+        } else if (l == 0 && d->frames_dtype == D2P_U8 && (conv_tc_mode() & 4) && conv_tc_dw3_supported(g)) {
+            D2P_TRY(conv_tc_dw3(st, g, (const uint8_t*)frames, dZ, L.dw, wsb + p.off_tc, p.tc_bytes));
         } else {
             if (l == 0 && d->frames_dtype == D2P_U8)
                 D2P_TRY(launch_conv_dw<uint8_t>(st, g, (const uint8_t*)frames, nullptr, nullptr, dZ, ppb, nblk, (float*)part));

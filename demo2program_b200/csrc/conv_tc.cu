@@ -29,6 +29,7 @@
 namespace d2p {
 
 bool tc_available();
+void conv_set_rgb(int on);
 
 namespace {
 using namespace tc;
@@ -629,6 +630,191 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight gradient of the RGB input layer (CIN = 3, u8 frames): dW[27, COUT] = sum_pixels patch[27] x dZ[COUT]
+// ------------------------------------------------------------------------------------------------
+// Same structure as conv_tc_dw_kernel with M = 27 patch elements (4 mn-groups of one 128-row accumulator; the
+// other 12 groups of the descriptor read whatever follows in the stage and produce rows nobody reads).  The
+// frame bytes 0..255 are exact in bf16, so A has no lo part and one tcgen05.mma `A x [dZhi|dZlo]` per k16 step
+// is the full fp32-equivalent product.  Stage = 32 pixels; thread (pixel, s) of a producer group gathers the
+// eight patch bytes 8s..8s+7 of its pixel and the s-th 16-byte chunk of its dZ row.
+struct Dw3Params {
+    const uint8_t* in;       // [N, IH, IW, 3]
+    const float* dz;         // [N, OH, OW, COUT]
+    float* partial;          // [grid, 27, COUT]
+    int IH, IW, OH, OW, PT, PL;
+    long long npix;
+    int pix_per_cta, stages;
+};
+template <int COUT>
+struct Dw3Cfg {
+    static constexpr int PXS = 32, KG = 4, KS = 2;
+    static constexpr uint32_t LBO_A = 4 * 128;                     // 4 mn-groups (32 patch rows) per k-group
+    static constexpr uint32_t A_BYTES = KG * LBO_A;
+    static constexpr uint32_t LBO_B = 2 * (COUT / 8) * 128;
+    static constexpr uint32_t B_BYTES = KG * LBO_B;
+    static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
+    static constexpr uint32_t TCOLS = 2 * COUT <= 32 ? 32 : 64;
+    static_assert(COUT == 16, "four 16-byte dZ chunks per pixel, one per producer sub-lane");
+    static_assert((16 - 4) * 128 <= (int)B_BYTES, "the accumulator tile's over-read stays inside the stage");
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
+    using C = Dw3Cfg<COUT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    uint8_t* ring = smem;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]),
+                   accum = smem_u32(&bars[2 * kMaxStages]);
+    if (tid == 0) {
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_slot)), "r"(C::TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // the whole ring starts as zeros: rows 27..31 of A stay zero forever, stale bits never reach a valid row
+    for (int i = tid; i < (int)(S * C::STAGE / 16); i += kThreadsTc)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    proxy_fence_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const long long pix0 = (long long)blockIdx.x * p.pix_per_cta;
+    long long pix_end = pix0 + p.pix_per_cta;
+    if (pix_end > p.npix) pix_end = p.npix;
+    const int nst = (int)((pix_end - pix0 + C::PXS - 1) / C::PXS);
+
+    if (warp >= 5) {
+        const int ptid = tid - (kEpi + 32);
+        const int grp = ptid >> 7, gt = ptid & 127;
+        const int pl = gt & 31, sub = gt >> 5;          // a warp = the 32 pixels of the stage, sub-lane = warp in group
+        const int kg = pl >> 3, p8 = pl & 7;
+        long long pix = pix0 + (long long)grp * C::PXS + pl;
+        int ox = (int)(pix % p.OW), oy = (int)((pix / p.OW) % p.OH);
+        int n = (int)(pix / ((long long)p.OW * p.OH));
+        const uint32_t ring_u = smem_u32(ring);
+        const uint32_t a_off = (uint32_t)kg * C::LBO_A + (uint32_t)sub * 128u + (uint32_t)p8 * 16u;
+        const uint32_t b_off = C::A_BYTES + (uint32_t)kg * C::LBO_B + (uint32_t)(sub >> 1) * 128u +
+                               (uint32_t)p8 * 16u + (uint32_t)(sub & 1) * 8u;
+        // U stages per iteration: all of their byte loads are issued before the first conversion
+        constexpr int U = 3;
+        int stage = (grp * U) % S, round = (grp * U) / S;
+        pix = pix0 + (long long)grp * U * C::PXS + pl;
+        ox = (int)(pix % p.OW); oy = (int)((pix / p.OW) % p.OH);
+        n = (int)(pix / ((long long)p.OW * p.OH));
+        for (int s0 = grp * U; s0 < nst; s0 += kGroups * U) {
+            float x[U][8];
+            float4 z[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool valid = pix < pix_end;     // (a stage past nst has no valid pixel either)
+                const uint8_t* fin = p.in + (size_t)n * p.IH * p.IW * 3;
+                const int iy0 = 2 * oy - p.PT, ix0 = 2 * ox - p.PL;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int el = sub * 8 + e;             // patch element (ky, kx, ci) = (el / 9, (el % 9) / 3, el % 3)
+                    const int iy = iy0 + el / 9, ix = ix0 + (el % 9) / 3;
+                    const bool ok = valid && el < 27 && iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW;
+                    x[u][e] = ok ? (float)__ldg(fin + ((size_t)iy * p.IW + ix) * 3 + el % 3) : 0.f;
+                }
+                z[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) z[u] = __ldg(reinterpret_cast<const float4*>(p.dz + (size_t)pix * COUT) + sub);
+                pix += C::PXS;
+                ox += C::PXS;
+                while (ox >= p.OW) { ox -= p.OW; ++oy; }
+                while (oy >= p.OH) { oy -= p.OH; ++n; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (s0 + u < nst) {
+                    if (round > 0) {
+                        if (lane == 0) mbar_wait(empty0 + 8 * stage, (round - 1) & 1);
+                        __syncwarp();
+                    }
+                    const uint32_t sbase = ring_u + (uint32_t)stage * C::STAGE;
+                    uint4 hi;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(x[u][1]), "f"(x[u][0]));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(x[u][3]), "f"(x[u][2]));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.z) : "f"(x[u][5]), "f"(x[u][4]));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.w) : "f"(x[u][7]), "f"(x[u][6]));
+                    st_shared16(sbase + a_off, hi);
+                    uint2 zh, zl;
+                    split2p(z[u].x, z[u].y, zh.x, zl.x);
+                    split2p(z[u].z, z[u].w, zh.y, zl.y);
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sbase + b_off), "r"(zh.x), "r"(zh.y) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sbase + b_off + (COUT / 8) * 128u), "r"(zl.x),
+                                 "r"(zl.y) : "memory");
+                    proxy_fence_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full0 + 8 * stage);
+                    if (++stage == S) { stage = 0; ++round; }
+                }
+            }
+            stage += (kGroups - 1) * U;
+            while (stage >= S) { stage -= S; ++round; }
+            pix += (long long)(kGroups - 1) * U * C::PXS;
+            ox += (kGroups - 1) * U * C::PXS;
+            while (ox >= p.OW) { ox -= p.OW; ++oy; }
+            while (oy >= p.OH) { oy -= p.OH; ++n; }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                       ((uint32_t)(kRows >> 4) << 24) | ((uint32_t)((2 * COUT) >> 3) << 17);
+            const uint32_t ring_u = smem_u32(ring);
+            int stage = 0, phase = 0;
+            for (int s = 0; s < nst; ++s) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = ring_u + (uint32_t)stage * C::STAGE, sb = sa + C::A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < C::KS; ++ks) {
+                    const uint64_t a = make_desc(sa + ks * 2 * C::LBO_A, C::LBO_A, 128);
+                    const uint64_t b = make_desc(sb + ks * 2 * C::LBO_B, C::LBO_B, 128);
+                    umma_bf16(tmem_base, a, b, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * stage);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(accum);
+        }
+    } else {
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        float* part = p.partial + (size_t)blockIdx.x * 27 * COUT;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t a[16], b[16];
+        tmem_ld16(taddr, a);
+        tmem_ld16(taddr + COUT, b);
+        tmem_ld_wait();
+        if (tid < 27) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(part + (size_t)tid * COUT + j) = make_float4(
+                    __uint_as_float(a[j]) + __uint_as_float(b[j]), __uint_as_float(a[j + 1]) + __uint_as_float(b[j + 1]),
+                    __uint_as_float(a[j + 2]) + __uint_as_float(b[j + 2]), __uint_as_float(a[j + 3]) + __uint_as_float(b[j + 3]));
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TCOLS));
+    }
+}
+
 // dW[i] += sum_blk partial[blk, i]   (fixed order, double accumulation)
 __global__ void conv_tc_dw_reduce(const float* __restrict__ partial, int nblk, int n, float* __restrict__ dW) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -804,11 +990,41 @@ int conv_tc_dw(cudaStream_t st, const ConvGeo& g, const float* in, const float* 
     return 0;
 }
 
+size_t conv_tc_dw3_ws_bytes(const ConvGeo& g) { return al((size_t)kNumSMs * 27 * g.COUT * sizeof(float)); }
+bool conv_tc_dw3_supported(const ConvGeo& g) {
+    return g.CIN == 3 && g.COUT == 16 && (long long)g.N * g.IH * g.IW * 3 < (1LL << 31);
+}
+// RGB input layer (u8 frames): dW += im2col(frames)^T dZ
+int conv_tc_dw3(cudaStream_t st, const ConvGeo& g, const uint8_t* in, const float* dZ, float* dW, void* ws,
+                size_t ws_bytes) {
+    D2P_REQUIRE(ws_bytes >= conv_tc_dw3_ws_bytes(g) && conv_tc_dw3_supported(g), "conv tc dw3: workspace / shape");
+    using C = Dw3Cfg<16>;
+    Dw3Params p{};
+    p.in = in; p.dz = dZ; p.partial = (float*)ws;
+    p.IH = g.IH; p.IW = g.IW; p.OH = g.OH; p.OW = g.OW; p.PT = g.PT; p.PL = g.PL;
+    p.npix = (long long)g.N * g.OH * g.OW;
+    p.stages = kMaxStages;
+    const long long nchunks = (p.npix + C::PXS - 1) / C::PXS;
+    long long grid = nchunks < kNumSMs ? nchunks : kNumSMs;
+    const long long per = (nchunks + grid - 1) / grid * C::PXS;
+    grid = (p.npix + per - 1) / per;
+    p.pix_per_cta = (int)per;
+    const size_t smem = (size_t)p.stages * C::STAGE;
+    D2P_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_dw3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_dw3_kernel<16><<<(int)grid, kThreadsTc, smem, st>>>(p);
+    D2P_CHECK_LAUNCH();
+    const int nw = 27 * g.COUT;
+    conv_tc_dw_reduce<<<cdiv(nw, 256), 256, 0, st>>>(p.partial, (int)grid, nw, dW);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace d2p
 
 extern "C" int d2p_conv_set_tc(int mode) {
     const int old = d2p::g_conv_tc_mode | (d2p::g_conv_tc_swap << 8);
     d2p::g_conv_tc_mode = mode & 7;
+    d2p::conv_set_rgb((mode & 16) ? 0 : 1);
     d2p::g_conv_tc_swap = (mode >> 8) & 1;
     return old;
 }

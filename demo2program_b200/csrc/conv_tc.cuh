@@ -27,4 +27,10 @@ int conv_tc_dx(cudaStream_t st, const ConvGeo& g, const float* dZ, const float* 
 int conv_tc_dw(cudaStream_t st, const ConvGeo& g, const float* in, const float* scale, const float* shift,
                const float* dZ, float* dW, void* ws, size_t ws_bytes);
 
+// RGB input layer with u8 frames (CIN = 3, COUT = 16): dW += im2col(frames)^T dZ on the tensor cores
+bool conv_tc_dw3_supported(const ConvGeo& g);
+size_t conv_tc_dw3_ws_bytes(const ConvGeo& g);
+int conv_tc_dw3(cudaStream_t st, const ConvGeo& g, const uint8_t* in, const float* dZ, float* dW, void* ws,
+                size_t ws_bytes);
+
 }  // namespace d2p

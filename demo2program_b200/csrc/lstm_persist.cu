@@ -255,6 +255,7 @@ struct FwdArgs {
     const float* h0; const float* c0; float* hT; float* cT;
     const int* len; int R, T; float forget_bias;
     unsigned* sync;                     // [row tiles] arrival counters, sync[63] = error word
+    int rt;                             // rows per row tile (multiple of 8, <= 128): row tile mt = rows [mt*rt, mt*rt + rt)
 };
 
 __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const FwdArgs a) {
@@ -262,12 +263,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
     __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.y, m0 = mt * BM, n0 = blockIdx.x * PBN, u0 = blockIdx.x * PUPT;
+    const int mt = blockIdx.y, m0 = mt * a.rt, n0 = blockIdx.x * PBN, u0 = blockIdx.x * PUPT;
     const int H = PH, G4 = 4 * PH, R = a.R, rot = blockIdx.x & (PNKB - 1);
     unsigned* ctr = a.sync + mt;
     unsigned* err = a.sync + 63;
     int rows = R - m0;
-    if (rows > BM) rows = BM;
+    if (rows > a.rt) rows = a.rt;
     PersistBars pb;
     const size_t a_kb_stride = (size_t)a.mgp_h * 2048;
     const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a_kb_stride,
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
     // This thread's item: accumulator row (= its TMEM lane) 32 (warp % 4) + lane, hidden units
     // u0 + 4 (warp / 4) .. + 4.  The cell state c and the carried h stay in registers.
     const int row = (warp & 3) * 32 + lane, jq = (warp >> 2) * 4, r = m0 + row;
-    const bool valid = r < R;
+    const bool valid = row < rows;      // (rows past the tile belong to the next row tile's CTAs)
     const size_t su = (size_t)(valid ? r : 0) * H + u0 + jq;
     const uint32_t tacc = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)jq;
     float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
 
     // copy-out item of this thread (coalesced: 4 lanes per row, 64 B per row and array)
     const int crow = tid >> 2, cpart = (tid & 3) * 4, cr = m0 + crow;
-    const bool cvalid = cr < R;
+    const bool cvalid = crow < rows;
     const int clen = cvalid ? a.len[cr] : 0;
     float* stg = reinterpret_cast<float*>(smem + P_W_BYTES);
 
@@ -690,6 +691,7 @@ struct BwdArgs {
     const float* cells; const float* c0; const float* dY;
     const float* dhT; const float* dcT; float* dh0; float* dc0;
     const int* len; int R, T, has_h0;
+    int rt;                             // rows per row tile (see FwdArgs)
     float* dbpart;                      // [row tiles][4H] column sums of dZ over this tile's rows and all steps
     unsigned* sync;                     // [row tiles] dZ_t published counters, [63] error word
 };
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     __shared__ __align__(8) uint64_t bars[2 * PMAXSLOTS + 2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.y, m0 = mt * BM;
+    const int mt = blockIdx.y, m0 = mt * a.rt;
     const int q = blockIdx.x, nt = q >> 2, ks = q & 3;     // 64-unit output tile, K-chunk (= gate)
     const int kb0 = ks * PNKB, rot = nt & (PNKB - 1);
     const int H = PH, G4 = 4 * PH, R = a.R;
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
     unsigned* ctrP = a.sync + mt;
     unsigned* err = a.sync + 63;
     int rows = R - m0;
-    if (rows > BM) rows = BM;
+    if (rows > a.rt) rows = a.rt;
     PersistBars pb;
     const size_t a_kb_stride = (size_t)a.mgp_z * 2048;
     const uint32_t tmem_d = persist_setup(smem, bars, &tmem_slot, pb, rows, a_kb_stride,
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
 
     // phase-P item of this thread: (row, 4 hidden units) of units [16 q, 16 q + 16)
     const int row = tid >> 2, up = (tid & 3) * 4, u = q * PUPT + up, r = m0 + row;
-    const bool valid = r < R;
+    const bool valid = row < rows;
     const size_t su = (size_t)(valid ? r : 0) * H + u;
     // my 16 B of each partial tile: row `row`, tile columns 16 ks + up .. + 4
     const uint32_t my_part = stage_u32 + (uint32_t)((row * PGROW + ks * PUPT + up) * sizeof(float));
@@ -948,6 +950,16 @@ int lstm_persist_set_probe(long long* buf) {
     return 0;
 }
 
+// rows per row tile: 128, or - for a recurrence that has the GPU to itself (D2P_LSTM_WIDE) - the rows split
+// evenly over as many row tiles as co-resident CTAs allow (4 x 32): R = 320 -> 4 tiles of 80 rows, so the
+// per-step operand stream of a CTA is 160 KB instead of 256 KB
+static int persist_row_tile(int R, bool wide) {
+    if (!wide || R <= BM) return BM;
+    const int nt = kNumSMs / PCOLS, groups = cdiv(R, 8);
+    const int rt = 8 * cdiv(groups, nt);
+    return rt < BM ? rt : BM;
+}
+
 bool lstm_persist_supported(int R, int H) {
     return g_persist_mode != 0 && tc_available() && H == PH && R >= 1 && cdiv(R, BM) * PCOLS <= kNumSMs;
 }
@@ -981,7 +993,7 @@ int launch_fwd_mt(cudaStream_t st, const FwdMtArgs& am) {
 // Recurrence phase of lstm_seq_fwd: gates already hold X*Wx + b.
 int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
                      const float* Wh, float forget_bias, float* Y, float* hT, float* cT, float* gates,
-                     float* cells, bool compact) {
+                     float* cells, bool compact, bool wide) {
     const int G4 = 4 * H;
     size_t off = 0;
     // R <= 32: no padding to 128-row tiles, so a row tile's 8 k-blocks are contiguous (one bulk copy)
@@ -1001,6 +1013,7 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
     a.whpk = (const uint8_t*)whpk; a.mgp_w = mgp_of(G4); a.mgp_h = mgp_h;
     a.gates = gates; a.cells = cells; a.Y = Y; a.h0 = h0; a.c0 = c0; a.hT = hT; a.cT = cT;
     a.len = len; a.R = R; a.T = T; a.forget_bias = forget_bias;
+    a.rt = persist_row_tile(R, wide && !compact);
     static bool attr_set = false;
     if (!attr_set) {
         D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1017,7 +1030,7 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
             case 4: return launch_fwd_mt<4>(st, am);
         }
     }
-    return launch_coop<FwdArgs>(lstm_persist_fwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a);
+    return launch_coop<FwdArgs>(lstm_persist_fwd_kernel, dim3(PCOLS, cdiv(R, a.rt)), P_SMEM, st, a);
 }
 
 // Recurrence phase of lstm_seq_bwd (without dX): gates -> dZ, dh0, dc0.
@@ -1034,7 +1047,8 @@ __global__ void add_db_partials(const float* __restrict__ part, int nt, int n, f
 // The kernel also accumulates the bias gradient (column sums of dZ): db += sum over row tiles.
 int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const float* h0, const float* c0,
                      const float* Wh, float* gates, const float* cells, const float* dY, const float* dhT,
-                     const float* dcT, float* dh0, float* dc0, float* db, const void** dz_full, size_t* off_out) {
+                     const float* dcT, float* dh0, float* dc0, float* db, const void** dz_full, size_t* off_out,
+                     bool wide) {
     const int G4 = 4 * H;
     size_t off = 0;
     // R > 32 and whole 8-row groups per step: the kernel writes dZ_t straight into the packed
@@ -1044,10 +1058,12 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     const int mgp_z = full ? mgp_of(T * R) : (R <= 32 ? cdiv(R, 8) : mgp_of(R));
     const size_t zbytes = (size_t)kgp_of(G4) * mgp_z * 256;
     BwdArgs a;
+    a.rt = persist_row_tile(R, wide);
+    const int ntiles = cdiv(R, a.rt);
     a.full = full ? 1 : 0;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
     a.sync = (unsigned*)tc_scratch_alloc(st, &off, 256);
-    a.dbpart = (float*)tc_scratch_alloc(st, &off, (size_t)cdiv(R, BM) * G4 * sizeof(float));
+    a.dbpart = (float*)tc_scratch_alloc(st, &off, (size_t)ntiles * G4 * sizeof(float));
     D2P_REQUIRE(a.dzpk && a.sync && a.dbpart, "lstm persist bwd: tensor-core scratch arena too small");
     const void* wtpk;
     D2P_TRY(get_packed(st, Wh, H, G4, G4, true, true, &off, &wtpk, 1000, 0));
@@ -1062,8 +1078,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
                                             (int)P_SMEM));
         attr_set = true;
     }
-    D2P_TRY(launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, cdiv(R, BM)), P_SMEM, st, a, 4));
-    add_db_partials<<<cdiv(G4, 256), 256, 0, st>>>(a.dbpart, cdiv(R, BM), G4, db);
+    D2P_TRY(launch_coop<BwdArgs>(lstm_persist_bwd_kernel, dim3(PCOLS, ntiles), P_SMEM, st, a, 4));
+    add_db_partials<<<cdiv(G4, 256), 256, 0, st>>>(a.dbpart, ntiles, G4, db);
     D2P_CHECK_LAUNCH();
     if (dz_full) *dz_full = full ? a.dzpk : nullptr;
     if (off_out) *off_out = off;

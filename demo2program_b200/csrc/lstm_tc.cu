@@ -34,10 +34,10 @@ int lstm_skinny_bwd_step(cudaStream_t, const float*, const float*, int, int, flo
 // persistent weight-stationary recurrences (lstm_persist.cu)
 bool lstm_persist_supported(int R, int H);
 int lstm_persist_fwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float,
-                     float*, float*, float*, float*, float*, bool compact);
+                     float*, float*, float*, float*, float*, bool compact, bool wide);
 int lstm_persist_bwd(cudaStream_t, int, int, int, const int*, const float*, const float*, const float*, float*,
                      const float*, const float*, const float*, const float*, float*, float*, float*, const void**,
-                     size_t*);
+                     size_t*, bool wide);
 
 namespace {
 
@@ -280,7 +280,7 @@ int lstm_seq_fwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
     if (lstm_persist_supported(R, H) && aligned16(Wh) && aligned16(gates) && aligned16(hT) && aligned16(cT) &&
         (!h0 || aligned16(h0)) && (!c0 || aligned16(c0)))
         return lstm_persist_fwd(st, T, R, H, len, h0, c0, Wh, forget_bias, Y, hT, cT, gates, cells,
-                                (phases & D2P_LSTM_COMPACT) != 0);
+                                (phases & D2P_LSTM_COMPACT) != 0, (phases & D2P_LSTM_WIDE) != 0);
     if (lstm_skinny_supported(R, H) && aligned16(Wh) && aligned16(hT) && aligned16(gates)) {
         // every CTA reads all of h_{t-1}: ping-pong between hT and a scratch copy
         float* hb[2] = {hT, (float*)tc_scratch_alloc(st, &off, RH * sizeof(float))};
@@ -348,7 +348,7 @@ int lstm_seq_bwd_tc(cudaStream_t st, const float* X, int T, int R, int In, int H
         const void* dzfull = nullptr;
         size_t off = 0;
         D2P_TRY(lstm_persist_bwd(st, T, R, H, len, h0, c0, Wh, gates, cells, dY, dhT, dcT, dh0, dc0, db,
-                                 dX ? &dzfull : nullptr, &off));
+                                 dX ? &dzfull : nullptr, &off, (phases & D2P_LSTM_WIDE) != 0));
         if (dX && dzfull && tc_eligible(T * R, In, G4)) {   // dX = dZ * Wx^T from the operand the kernel packed
             const void* wxpk;
             D2P_TRY(get_packed(st, Wx, In, G4, G4, true, true, &off, &wxpk));

@@ -16,6 +16,28 @@ import torch
 import torch.distributed as dist
 
 
+def init_nccl(device=None):
+    """init_process_group('nccl') for one process per GPU.  The communicator is limited to
+    D2P_NCCL_MAX_CTAS CTAs (default 8): the gradient all-reduce runs UNDER the backward pass, whose
+    persistent recurrence kernels are cooperative launches that need 96-128 free SMs at once - a
+    collective spread over 16-32 SMs delays them by more than it gains in bus bandwidth (the 32 MB
+    bucket has ~1 ms of backward pass to hide under).  0 keeps NCCL's default."""
+    import os
+    kw = {}
+    if device is not None:
+        kw['device_id'] = torch.device(device)
+    max_ctas = int(os.environ.get('D2P_NCCL_MAX_CTAS', '8'))
+    if max_ctas > 0:
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = max_ctas
+            opts.config.min_ctas = min(max_ctas, 4)
+            kw['pg_options'] = opts
+        except (AttributeError, RuntimeError):      # a torch build without the NCCL config fields
+            pass
+    dist.init_process_group('nccl', **kw)
+
+
 def shard_seed(base_seed, rank):
     """Every rank draws its own shard of synthetic examples."""
     return int(base_seed) + 1009 * int(rank)

@@ -48,6 +48,13 @@ class Engine:
         # compact_decoders: the action / perception decoder recurrences of `full` run in compact form
         # (32 CTAs each) side by side with the program decoder instead of one after the other
         self.compact_decoders = bool(compact_decoders)
+        # D2P_LSTM_WIDE for the encoder / second-path recurrences: D2P_WIDE_LSTM = 1 (default) forward only,
+        # 2 forward and backward, 0 never.  Measured at C2 (profiles/r02p_*): 4 x 80-row tiles shorten each
+        # of these recurrences by 5-17 us, but in the backward pass the 128 CTAs leave only 20 SMs to the
+        # deferred weight-gradient products, whose tail then ends 80 us later - a net loss there.
+        self.wide_lstm = os.environ.get('D2P_WIDE_LSTM', '1') != '0'
+        self.wide_lstm_bwd = os.environ.get('D2P_WIDE_LSTM', '1') == '2'
+        self._bwd_wide = False
         # scheduled sampling (reference models/model_full.py:59-67, 414-423): the program / action decoders
         # run step by step and feed, with the scheduled probability, a token sampled from their own
         # output instead of the ground truth.  sched_p_override >= 0 replaces the schedule (tests).
@@ -290,31 +297,37 @@ class Engine:
     def _call(self, name, *args):
         check(getattr(self.lib, name)(*args), name)
 
-    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3, compact=False):
+    def _lstm_fwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, phases=3, compact=False, wide=False):
         """compact: D2P_LSTM_COMPACT - the recurrence runs on a 32-CTA grid whose CTAs walk all row
         tiles, so that independent recurrences share the GPU (the library falls back to one CTA per
-        row tile when the shape has a single tile)."""
+        row tile when the shape has a single tile).  wide: D2P_LSTM_WIDE - the recurrence runs alone
+        (encoder / second-path LSTMs): rows split evenly over 4 x 32 CTAs."""
         if compact:
             phases |= 8
+        if wide and self.wide_lstm:
+            phases |= 16
         self._call('d2p_lstm_seq_fwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
                    ptr(self.P(scope + 'kernel')), ptr(self.P(scope + 'bias')), 1.0,
                    ptr(b['y']), ptr(b['hT']), ptr(b['cT']), ptr(b['gates']), ptr(b['cells']),
                    phases, self._st())
 
     def _lstm_bwd_call(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, phases):
+        if self._bwd_wide and self.wide_lstm_bwd:
+            phases |= 16
         self._call('d2p_lstm_seq_bwd', ptr(X), Tn, Rn, In, self.H, ptr(lens), ptr(h0), ptr(c0),
                    ptr(self.P(scope + 'kernel')), ptr(b['y']), ptr(b['gates']), ptr(b['cells']),
                    ptr(dY), ptr(dhT), ptr(dcT), ptr(dX), ptr(self.G(scope + 'kernel')),
                    ptr(self.G(scope + 'bias')), ptr(b['dh0']), ptr(b['dc0']), ptr(self.ws),
                    self.ws_bytes, phases, self._st())
 
-    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, token_fn=None):
+    def _lstm_bwd(self, X, Tn, Rn, In, lens, h0, c0, scope, b, dY, dhT, dcT, dX, token_fn=None, wide=False):
         """BPTT recurrence (+ dX) on the current stream; the parameter-gradient products
         (dWx, dWh, db: large, throughput-bound) are handed to the gradient stream so they
         overlap with the latency-bound recurrences that follow.  token_fn (token decoders with
         token_tables): no dX, no [T*R]-row dWx product - token_fn() forms dWx and dE from the
         per-token sums of dZ, behind the dWh product on the same gradient stream."""
         nodwx = 4 if token_fn is not None else 0      # D2P_LSTM_BWD_NO_DWX
+        self._bwd_wide = bool(wide)
         if token_fn is not None:
             dX = None
         if not self.concurrent:
@@ -539,7 +552,7 @@ class Engine:
                 act_in()
                 per_in()
         self._lstm_fwd(self.feat, T, R, F, self.d_demo_len, None, None,
-                       'Demo_Encoder/rnn/basic_lstm_cell/', self.enc)
+                       'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, wide=True)
         self._stamp('encoder lstm fwd done')
         if self.model in ('full', 'summarizer'):
             call('d2p_group_sum', ptr(self.enc['hT']), B, k, H, 1.0 / k, ptr(self.sum1_h), 0, S())
@@ -547,7 +560,7 @@ class Engine:
             call('d2p_group_bcast', ptr(self.sum1_h), B, k, H, 1.0, ptr(self.init2_h), 0, S())
             call('d2p_group_bcast', ptr(self.sum1_c), B, k, H, 1.0, ptr(self.init2_c), 0, S())
             self._lstm_fwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
-                           'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec)
+                           'SecondPathEncoder/rnn/basic_lstm_cell/', self.sec, wide=True)
             self._stamp('second-path lstm fwd done')
             fin = self.sec
         else:
@@ -844,7 +857,7 @@ class Engine:
             sec = self.sec
             self._lstm_bwd(self.enc['y'], T, R, H, self.d_demo_len, self.init2_h, self.init2_c,
                            'SecondPathEncoder/rnn/basic_lstm_cell/', sec, None, self.dh2, self.dc2,
-                           self.dy1)
+                           self.dy1, wide=True)
             self._stamp('second-path lstm bwd done')
             # init state = mean_i of first-pass finals, broadcast over i
             call('d2p_group_sum', ptr(sec['dh0']), B, k, H, 1.0, ptr(self.sum1_h), 0, S())
@@ -857,7 +870,7 @@ class Engine:
             dY1 = None
         self._lstm_bwd(self.feat, T, R, F, self.d_demo_len, None, None,
                        'Demo_Encoder/rnn/basic_lstm_cell/', self.enc, dY1, self.dh2, self.dc2,
-                       self.dfeat)
+                       self.dfeat, wide=True)
         self._stamp('encoder lstm bwd done')
         call('d2p_conv_encoder_bwd', C.byref(self.conv_desc), ptr(self.d_frames), ptr(self.dfeat),
              ptr(self.conv_saved), tr, ptr(self.ws), self.ws_bytes, S())

@@ -102,6 +102,10 @@ enum { D2P_LSTM_INPUT = 1,      /* gates = X*Wx + b for all steps (independent o
        D2P_LSTM_BWD_PARAMS = 2, /* dW, db from the dZ left in `gates` by the recurrence phase */
        D2P_LSTM_COMPACT = 8,    /* (fwd and bwd recurrence) 32-CTA grid: every CTA walks all row tiles, so that
                                  * independent recurrences (action / perception / program decoders) share the GPU */
+       D2P_LSTM_WIDE = 16,      /* (fwd and bwd recurrence, more than 128 rows) this recurrence has the GPU to itself:
+                                 * its rows are split evenly over 4 row tiles x 32 column CTAs (R = 320: 4 x 80 rows,
+                                 * 128 CTAs) instead of 128-row tiles (96 CTAs), which shortens the per-step operand
+                                 * stream of every CTA; not for recurrences that run beside another persistent kernel */
        D2P_LSTM_BWD_NO_DWX = 4  /* with BWD_PARAMS: leave the input-weight rows dW[0:In] alone (X is not read).
                                  * For a teacher-forced token decoder (X = embedding rows, reference
                                  * models/model_full.py:440-471) the caller forms dWx = E^T * S and

@@ -591,7 +591,9 @@ def test_tensor_core_conv_matches_cuda_core(which):
     operands) against the fp32 CUDA-core kernels, one d2p_conv_set_tc bit at a time.  Forward:
     activations, statistics, features and moving statistics to bf16x3 accuracy.  The gradient kernels
     are switched on with the forward left on the CUDA cores, so both runs see identical activations
-    (no lrelu-slope ambiguity) and every gradient must agree to 3e-5 of its variable's largest entry."""
+    (no lrelu-slope ambiguity) and every gradient must agree to 3e-5 of its variable's largest entry.
+    On ViZDoom the RGB input layer is covered too: its direct forward kernel with fused statistics
+    (bit 4 switches it off) and its tensor-core weight gradient (u8 frames are exact in bf16)."""
     from demo2program_b200.config import vizdoom_config
     from demo2program_b200.manifest import build_manifests
     from demo2program_b200.synthetic import make_batch
@@ -600,14 +602,15 @@ def test_tensor_core_conv_matches_cuda_core(which):
     else:
         cfg = karel_config('full', batch_size=8, k=3)      # per-layer path: conv2 (16->32) and conv3 (32->48)
     batch = make_batch(cfg, seed=3)
-    ref = _run_conv_tc(cfg, batch, 0)
-    fwd = _run_conv_tc(cfg, batch, 1)
-    assert abs(fwd['loss'] - ref['loss']) < 1e-5
-    assert rel_err(fwd['feat'], ref['feat']) < 5e-5
-    assert rel_err(fwd['saved'], ref['saved']) < 2e-5
-    assert rel_err(fwd['state'], ref['state']) < 2e-5
+    ref = _run_conv_tc(cfg, batch, 16)      # bit 4: also without the direct RGB-layer forward kernel
+    for mode in (0, 1 | 16):                # the RGB-layer forward (fp32, fused statistics); the tcgen05 forward
+        fwd = _run_conv_tc(cfg, batch, mode)
+        assert abs(fwd['loss'] - ref['loss']) < 1e-5
+        assert rel_err(fwd['feat'], ref['feat']) < 5e-5
+        assert rel_err(fwd['saved'], ref['saved']) < 2e-5
+        assert rel_err(fwd['state'], ref['state']) < 2e-5
     pm, _ = build_manifests(cfg)
-    for mode in (2, 4, 6):
+    for mode in (2 | 16, 4 | 16, 6 | 16):   # bit 2 includes the RGB layer's weight gradient (conv_tc_dw3_kernel)
         out = _run_conv_tc(cfg, batch, mode)
         assert out['loss'] == ref['loss'] and np.array_equal(out['saved'], ref['saved'])
         for e in pm:

@@ -39,10 +39,10 @@ def run(cfg, batch, mode):
 
 def compare(cfg, tag):
     batch = make_batch(cfg, seed=3)
-    eng, ref = run(cfg, batch, 0)
+    eng, ref = run(cfg, batch, 16)      # every convolution on the fp32 CUDA-core per-layer kernels
     names = [e for e in eng.pm if 'conv' in e.name.lower() or 'State_Encoder' in e.name]
     print('== %s: conv variables %s' % (tag, [e.name.split('/')[-2] + '/' + e.name.split('/')[-1] for e in names][:6]))
-    for mode, label in ((1, 'fwd'), (2, 'dx'), (4, 'dw'), (7, 'all')):
+    for mode, label in ((0, 'rgb fwd'), (1 | 16, 'fwd'), (2 | 16, 'dx'), (4 | 16, 'dw'), (7, 'all')):
         try:
             _, out = run(cfg, batch, mode)
         except Exception as ex:   # noqa: BLE001
@@ -53,7 +53,7 @@ def compare(cfg, tag):
         print('mode %-20s loss %.6f (ref %.6f)  feat %.2e  saved %.2e  all grads %.2e  worst conv grad %.2e %s' % (
             label, out['loss'], ref['loss'], rel(out['feat'], ref['feat']), rel(out['saved'], ref['saved']),
             rel(out['grads'], ref['grads']), worst[0], worst[1]))
-        if mode in (1, 9):
+        if mode in (17, 0):
             # per-layer activations / statistics inside `saved`
             d = eng.conv_desc
             off, ih, iw = 0, cfg.h, cfg.w
@@ -76,14 +76,14 @@ def compare(cfg, tag):
             for e in names:
                 a, b = out['grads'][e.offset:e.offset + e.size], ref['grads'][e.offset:e.offset + e.size]
                 print('      %-62s err %.2e  max|g| %.2e  (model max %.2e)' % (e.name, np.abs(a - b).max(), np.abs(b).max(), gmax))
-        if mode in (4, 4 | 256):
+        if mode in (20,):
             for e in names:
                 if e.name.endswith('weights'):
                     print('      %-60s %.2e' % (e.name, rel(out['grads'][e.offset:e.offset + e.size],
                                                                ref['grads'][e.offset:e.offset + e.size])))
 
 
-def timing(cfg, tag, modes=(0, 7)):
+def timing(cfg, tag, modes=(16, 7)):
     """conv encoder forward / backward alone (CUDA events, warm), tensor-core kernels vs CUDA-core kernels"""
     import ctypes as C
     from demo2program_b200._lib import ptr, check

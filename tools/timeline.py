@@ -17,7 +17,8 @@ world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('R
 torch.cuda.set_device(local)
 if world > 1:
     import torch.distributed as dist
-    dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
+    from demo2program_b200.dp import init_nccl
+    init_nccl('cuda:%d' % local)
     dist.all_reduce(torch.zeros(1, device='cuda'))
 eng = Engine(cfg, device='cuda:%d' % local, world_size=world, use_graph=True)
 eng.timeline = torch.zeros(64, dtype=torch.int64, device=eng.dev)

@@ -216,7 +216,8 @@ def main(argv=None):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(config.local_rank)
-        dist.init_process_group('nccl')
+        from demo2program_b200.dp import init_nccl
+        init_nccl('cuda:%d' % config.local_rank)
     from demo2program_b200 import dataset
     if config.dataset_type not in ('karel', 'vizdoom'):
         raise ValueError(config.dataset_type)
