@@ -524,6 +524,7 @@ def _run_variant(cfg, batch, fused, persistent, frames_dtype=np.uint8, is_train=
     from demo2program_b200.engine import Engine
     lib = _lib.load()
     lib.d2p_conv_set_fused(fused)
+    lib.d2p_conv_set_tc(0)          # the per-layer reference of these tests is the fp32 CUDA-core path
     lib.d2p_lstm_set_persistent(persistent)
     try:
         eng = Engine(cfg, use_graph=False, frames_dtype=frames_dtype, is_train=is_train)
@@ -537,6 +538,7 @@ def _run_variant(cfg, batch, fused, persistent, frames_dtype=np.uint8, is_train=
                 'grads': eng.grads.cpu().numpy().copy()}
     finally:
         lib.d2p_conv_set_fused(1)
+        lib.d2p_conv_set_tc(7)
         lib.d2p_lstm_set_persistent(1)
 
 
