@@ -17,16 +17,16 @@ import torch.distributed as dist
 
 
 def init_nccl(device=None):
-    """init_process_group('nccl') for one process per GPU.  The communicator is limited to
-    D2P_NCCL_MAX_CTAS CTAs (default 8): the gradient all-reduce runs UNDER the backward pass, whose
-    persistent recurrence kernels are cooperative launches that need 96-128 free SMs at once - a
-    collective spread over 16-32 SMs delays them by more than it gains in bus bandwidth (the 32 MB
-    bucket has ~1 ms of backward pass to hide under).  0 keeps NCCL's default."""
+    """init_process_group('nccl') for one process per GPU.  D2P_NCCL_MAX_CTAS > 0 limits the
+    communicator to that many CTAs (the gradient all-reduce runs UNDER the backward pass and shares the
+    SMs with its cooperative recurrence kernels).  Default 0 = NCCL's own choice: measured at N=2
+    (profiles/r02r_*), 8 CTAs make the hidden 32 MB bucket no cheaper for the backward pass and the
+    exposed last bucket 43 us slower (3.009 vs 2.986 ms/step)."""
     import os
     kw = {}
     if device is not None:
         kw['device_id'] = torch.device(device)
-    max_ctas = int(os.environ.get('D2P_NCCL_MAX_CTAS', '8'))
+    max_ctas = int(os.environ.get('D2P_NCCL_MAX_CTAS', '0'))
     if max_ctas > 0:
         try:
             opts = dist.ProcessGroupNCCL.Options()
