@@ -86,8 +86,10 @@ int d2p_conv_set_fused(int mode);
 /* Per-layer path, layers with 16/32/48 input channels (ViZDoom conv2-5, Karel conv2-3; replaces the
  * same slim.conv2d call, models/ops.py:27-33, and its gradients): bit 0 = forward, bit 1 = input
  * gradient, bit 2 = weight gradient run as tcgen05 implicit-GEMM kernels (bf16x3 split, no im2col
- * buffer) whenever the tensor-core arena is configured (d2p_tc_configure).  Default 7; returns the
- * previous mode.  0 keeps the fp32 CUDA-core kernels (the A/B reference of the parity tests). */
+ * buffer) whenever the tensor-core arena is configured (d2p_tc_configure); bit 2 also runs the weight
+ * gradient of the u8 RGB input layer (CIN = 3) on the tensor cores.  Bit 4 SET switches the direct
+ * RGB-layer forward kernel (fused BatchNorm partial sums) off.  Default 7; returns the previous
+ * mode.  16 = the fp32 CUDA-core per-layer kernels everywhere (the A/B reference of the parity tests). */
 int d2p_conv_set_tc(int mode);
 
 /* ---- K2/K3: LSTM over a sequence -------------------------------------------
