@@ -78,9 +78,15 @@ __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target, 
 
 // timeline probe (developer tool): stamps of CTA (0,0) during step index P_PROBE_STEP
 constexpr int P_PROBE_STEP = 5;
+// The stamps go to shared memory and are flushed once at the end of the kernel: a global load / store per
+// stamp queues behind whatever the SM's memory pipe is draining and distorts the very thing it measures.
+__shared__ long long g_pstamps[32];
 __device__ __forceinline__ void pstamp(int step, int slot) {
-    if (g_tc_dbg != nullptr && step == P_PROBE_STEP && blockIdx.x == 0 && blockIdx.y == 0)
-        g_tc_dbg[64 + slot] = clock64();   // slots 0..63 belong to the per-step kernels' probe
+    if (step == P_PROBE_STEP && blockIdx.x == 0 && blockIdx.y == 0) g_pstamps[slot & 31] = clock64();
+}
+__device__ __forceinline__ void pstamp_flush() {   // after a CTA barrier, slots 0..63 belong to the per-step kernels' probe
+    if (threadIdx.x < 32 && g_tc_dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
+        g_tc_dbg[64 + threadIdx.x] = g_pstamps[threadIdx.x];
 }
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -275,13 +281,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
                                           a.whpk + (size_t)(n0 / PBN) * PB_BYTES, (size_t)a.mgp_w * 2048);
     const uint32_t sbase = smem_u32(smem);
     RingPos rp{0, 0, 0};   // used by the producer lane and (separately) by the MMA lane
-    // Early first block: the per-step outputs are staged in the low P_STAGE_BYTES of the ring; when
-    // the LAST ring slot lies above them, every step starts its slot sequence there, and the
-    // producer fetches the first k-block of step t+1 while step t's copy-out is still draining
-    // (the step barrier and one bulk-copy latency disappear behind the copy-out).
-    const bool early = !pb.single && pb.nslots < PNKB &&
-                       (uint32_t)(pb.nslots - 1) * pb.a_bytes >= (uint32_t)P_STAGE_BYTES;
-    bool early_issued = false;   // (producer lane) k-block 0 of the coming step is already in flight
+    // Head of a step's operand stream: the first `nhead` k-blocks of step t+1 are issued at the END of step t,
+    // right after the staged outputs have been read back into registers (the whole ring is free then) and
+    // BEFORE the copy-out stores are issued.  The order matters: the producer lane's barrier polls
+    // (ld.acquire) share the SM's memory pipe with those 57 KB of stores and used to sit behind them for
+    // ~4 k cycles per step (tools/probe_persist.py).
+    const int nhead = pb.single ? PNKB : (pb.nslots < PNKB ? pb.nslots : PNKB);
+    int issued = 0;              // (producer lane) k-blocks of the coming step already in flight
 
     // This thread's item: accumulator row (= its TMEM lane) 32 (warp % 4) + lane, hidden units
     // u0 + 4 (warp / 4) .. + 4.  The cell state c and the carried h stay in registers.
@@ -302,30 +308,50 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
     const bool cvalid = crow < rows;
     const int clen = cvalid ? a.len[cr] : 0;
     float* stg = reinterpret_cast<float*>(smem + P_W_BYTES);
+    // copy-out registers (staged outputs of the step just finished)
+    float4 o_c = make_float4(0.f, 0.f, 0.f, 0.f), o_y = o_c, o_g[4] = {o_c, o_c, o_c, o_c};
+    auto copy_out = [&](int ts) {
+        if (cvalid) {
+            const size_t gu = ((size_t)ts * R + cr) * H + u0 + cpart;
+            *reinterpret_cast<float4*>(a.cells + gu) = o_c;
+            if (ts < clen) {
+                float* gout = a.gates + ((size_t)ts * R + cr) * G4 + u0 + cpart;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(gout + g * H) = o_g[g];
+            }
+            // ts >= len: output row is zero, (c, h) are carried through (dynamic_rnn, A.5)
+            *reinterpret_cast<float4*>(a.Y + gu) = o_y;
+        }
+    };
 
     for (int t = 0; t < a.T; ++t) {
         const float* grow = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u0 + jq;
         const bool live = valid && t < mylen;
-        // hoisted x*Wx + b part of this thread's pre-activations: in flight during the main loop
         float zi[4], zj[4], zf[4], zo[4];
-        if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
-        if (tid == 0) pstamp(t, 0);
+        // (the two role lanes issue their own loads after their latency-critical work)
+        if (tid == 0) { pstamp(t, 0); pstamp(t - 1, 11); }
         if (warp == 0 && lane == 0) {
-            if (t > 0 && !early_issued) grid_wait(ctr, (unsigned)(PCOLS * t), err);
-            pstamp(t, 1);
-            proxy_fence();   // also orders the previous step's generic staging accesses before the bulk writes
-            if (early && !early_issued) rp.slot = pb.nslots - 1;
-            persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot,
-                            early_issued ? 1 : 0);
+            if (issued == 0) {
+                if (t > 0) grid_wait(ctr, (unsigned)(PCOLS * t), err);
+                pstamp(t, 1);
+                proxy_fence();   // also orders the previous step's generic staging accesses before the bulk writes
+            }
+            if (!(pb.single && issued > 0))
+                persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot,
+                                issued);
             pstamp(t, 2);
+            if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
         } else if (warp == 1 && lane == 0) {
-            if (early) rp.slot = pb.nslots - 1;
             persist_mma(pb, rp, sbase, tmem_d, rot, t == 0);
             pstamp(t, 3);
+            if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
             // only this lane polls the accumulator barrier; everybody else parks on the hardware
             // CTA barrier below (hundreds of threads spinning on try_wait steal shared-memory
             // bandwidth from the tensor core's operand reads)
             mbar_wait(pb.accum, t & 1);
+        } else {
+            // hoisted x*Wx + b part of this thread's pre-activations: in flight during the main loop
+            if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
         }
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -370,43 +396,42 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
             st4r(stage_ptr(stg, 5, row, jq), h);
         }
         __syncthreads();
+        // staged outputs -> registers (4 lanes per row, 64 B per row and array), so that the ring is free again
+        o_y = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cvalid) {
-            const size_t gu = ((size_t)t * R + cr) * H + u0 + cpart;
-            *reinterpret_cast<float4*>(a.cells + gu) = *reinterpret_cast<const float4*>(stage_ptr(stg, 4, crow, cpart));
+            o_c = *reinterpret_cast<const float4*>(stage_ptr(stg, 4, crow, cpart));
             if (t < clen) {
-                float* gout = a.gates + ((size_t)t * R + cr) * G4 + u0 + cpart;
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<float4*>(gout + g * H) =
-                        *reinterpret_cast<const float4*>(stage_ptr(stg, g, crow, cpart));
-                *reinterpret_cast<float4*>(a.Y + gu) = *reinterpret_cast<const float4*>(stage_ptr(stg, 5, crow, cpart));
-            } else {
-                // t >= len: output row is zero, (c, h) are carried through (dynamic_rnn, A.5)
-                *reinterpret_cast<float4*>(a.Y + gu) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int g = 0; g < 4; ++g) o_g[g] = *reinterpret_cast<const float4*>(stage_ptr(stg, g, crow, cpart));
+                o_y = *reinterpret_cast<const float4*>(stage_ptr(stg, 5, crow, cpart));
             }
         }
-        if (tid == 64) pstamp(t, 9);
+        __syncthreads();
         if (tid == 0) {
-            early_issued = false;
-            if (early && t + 1 < a.T) {
-                // k-block 0 of step t+1 into the slot above the staging area (all MMAs of step t
-                // have retired: its empty barrier is already complete)
+            issued = 0;
+            if (t + 1 < a.T) {
+                // head of step t+1's operand stream (all MMAs of step t have retired: every slot is free)
                 grid_wait(ctr, (unsigned)(PCOLS * (t + 1)), err);
                 proxy_fence();
-                rp.slot = pb.nslots - 1;
                 persist_produce(pb, rp, sbase, (((t + 1) & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048,
-                                a_kb_stride, rot, 0, 1);
-                early_issued = true;
+                                a_kb_stride, rot, 0, nhead);
+                issued = nhead;
                 pstamp(t, 10);
             }
         }
-        __syncthreads();   // staging drained before the next step's bulk copies land in the lower slots
+        // (measured, profiles/r02u_*: holding the other warps' stores back behind one more CTA barrier, or
+        // deferring the two role warps' stores to after their next role work, is no faster than this)
+        copy_out(t);
+        if (tid == 64) pstamp(t, 9);
+        if (tid == PTHREADS - 1) pstamp(t, 13);
+        if (tid == 0) pstamp(t, 12);
     }
     if (valid) {
         st4r(a.hT + su, h);
         st4r(a.cT + su, c);
     }
     __syncthreads();
+    pstamp_flush();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
 }
@@ -765,26 +790,34 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         if (a.dhT) ld4r(a.dhT + su, dhc);
         if (a.dcT) ld4r(a.dcT + su, dcc);
     }
+    // Saved activations / incoming gradient of a step, fetched one step ahead (during the previous step's
+    // phase G, when the epilogue threads are idle): the loads used to sit at the top of the step, ~2 k
+    // cycles of exposed latency in front of phase P.
+    float gi[4], gj[4], gf[4], go[4], cc[4], cp[4], dy[4];
+    float ngi[4], ngj[4], ngf[4], ngo[4], ncc[4], ncp[4], ndy[4];
+    auto fetch = [&](int ts, float* xi, float* xj, float* xf, float* xo, float* xcc, float* xcp, float* xdy) {
+        if (valid && ts >= 0 && ts < mylen) {
+            const float* gs = a.gates + ((size_t)ts * R + r) * G4 + u;
+            ld4r(gs, xi); ld4r(gs + H, xj); ld4r(gs + 2 * H, xf); ld4r(gs + 3 * H, xo);
+            ld4r(a.cells + (size_t)ts * RH + su, xcc);
+            if (ts > 0) ld4r(a.cells + (size_t)(ts - 1) * RH + su, xcp);
+            else if (a.c0) ld4r(a.c0 + su, xcp);
+            else { xcp[0] = xcp[1] = xcp[2] = xcp[3] = 0.f; }
+            if (a.dY) ld4r(a.dY + (size_t)ts * RH + su, xdy);
+            else { xdy[0] = xdy[1] = xdy[2] = xdy[3] = 0.f; }
+        }
+    };
+    fetch(a.T - 1, gi, gj, gf, go, cc, cp, dy);
     cluster_sync_all();      // every CTA of the cluster is resident and set up before any remote access
     int ground = 0;          // GEMM rounds completed so far
     bool have_partials = false;
     for (int t = a.T - 1; t >= 0; --t) {
         const int step = a.T - 1 - t;
         const int zrow0 = a.full ? t * R : 0;      // first packed row of this step's dZ
-        if (tid == 0) pstamp(step, 16);
+        if (tid == 0) { pstamp(step, 16); pstamp(step - 1, 16 + 9); }
         // ---- phase P: dZ_t for this CTA's 16 hidden units ----
         float* g = a.gates + ((size_t)t * R + (valid ? r : 0)) * G4 + u;
-        float gi[4], gj[4], gf[4], go[4], cc[4], cp[4], dy[4];
         const bool live = valid && t < mylen;
-        if (live) {
-            ld4r(g, gi); ld4r(g + H, gj); ld4r(g + 2 * H, gf); ld4r(g + 3 * H, go);
-            ld4r(a.cells + (size_t)t * RH + su, cc);
-            if (t > 0) ld4r(a.cells + (size_t)(t - 1) * RH + su, cp);
-            else if (a.c0) ld4r(a.c0 + su, cp);
-            else { cp[0] = cp[1] = cp[2] = cp[3] = 0.f; }
-            if (a.dY) ld4r(a.dY + (size_t)t * RH + su, dy);
-            else { dy[0] = dy[1] = dy[2] = dy[3] = 0.f; }
-        }
         if (have_partials && valid) {
             const float4 p0 = ld_dsmem4(my_part, 0u), p1 = ld_dsmem4(my_part, 1u);
             const float4 p2 = ld_dsmem4(my_part, 2u), p3 = ld_dsmem4(my_part, 3u);
@@ -829,18 +862,32 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             if (tid == 0) { __threadfence(); proxy_fence(); red_relaxed(ctrP, 1u); pstamp(step, 20); }
             __syncthreads();
         }
-        if (valid) { st4r(g, di); st4r(g + H, dj); st4r(g + 2 * H, df); st4r(g + 3 * H, dq); }
-        if (!do_gemm) { have_partials = false; break; }
+        if (!do_gemm) {
+            if (valid) { st4r(g, di); st4r(g + H, dj); st4r(g + 2 * H, df); st4r(g + 3 * H, dq); }
+            have_partials = false;
+            break;
+        }
         // ---- phase G: partial[ks] = dZ_t[:, gate ks] * Wh[n-tile, gate ks]^T ----
+        // The fp32 dZ stores (32 KB per CTA, for the dW products after the kernel) are issued only once the
+        // head of the operand stream is out: the producer lane's barrier polls share the SM's memory pipe
+        // with them and sat behind them for ~1.5 k cycles per step (tools/probe_persist.py).
+        const uint8_t* zsrc = a.dzpk + ((size_t)kb0 * a.mgp_z + (zrow0 + m0) / 8) * 2048;
+        const int nhead = pb.single ? PNKB : (pb.nslots < PNKB ? pb.nslots : PNKB);
         if (warp == 0 && lane == 0) {
             grid_wait(ctrP, (unsigned)(PCOLS * (ground + 1)), err);
             pstamp(step, 21);
             proxy_fence();
-            persist_produce(pb, rp, sbase, a.dzpk + ((size_t)kb0 * a.mgp_z + (zrow0 + m0) / 8) * 2048, a_kb_stride, rot);
+            persist_produce(pb, rp, sbase, zsrc, a_kb_stride, rot, 0, nhead);
+        }
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            if (!pb.single) persist_produce(pb, rp, sbase, zsrc, a_kb_stride, rot, nhead, PNKB);
         } else if (warp == 1 && lane == 0) {
             persist_mma(pb, rp, sbase, tmem_d, rot, ground == 0);
-            mbar_wait(pb.accum, ground & 1);
         }
+        fetch(t - 1, ngi, ngj, ngf, ngo, ncc, ncp, ndy);     // next step's inputs
+        if (valid) { st4r(g, di); st4r(g + H, dj); st4r(g + 2 * H, df); st4r(g + 3 * H, dq); }
+        if (warp == 1 && lane == 0) mbar_wait(pb.accum, ground & 1);
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) pstamp(step, 22);
@@ -866,6 +913,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         if (tid == 0) pstamp(step, 24);
         ++ground;
         have_partials = true;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            cc[e] = ncc[e];
+            gi[e] = ngi[e]; gj[e] = ngj[e]; gf[e] = ngf[e]; go[e] = ngo[e]; cp[e] = ncp[e]; dy[e] = ndy[e];
+        }
     }
     if (have_partials && valid) {   // dh0 = carry + last partial sums
 #pragma unroll
@@ -895,6 +947,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             a.dbpart[(size_t)mt * G4 + (tid >> 4) * H + q * PUPT + (tid & 15)] = s;
         }
     }
+    __syncthreads();
+    pstamp_flush();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)PTMEM));
 }

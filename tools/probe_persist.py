@@ -15,9 +15,9 @@ cache = torch.zeros(128 << 20, dtype=torch.uint8, device=dev)
 lib.d2p_tc_configure(ptr(scratch), scratch.numel(), ptr(cache), cache.numel(), 1)
 lib.d2p_lstm_set_persistent(1)
 FW = ['top', 'grid barrier passed', 'last bulk copy issued', 'last MMA issued', None, 'accum ready',
-      'cell math done', 'packed h stores issued', 'arrive issued', 'copy-out stores issued']
+      'cell math done', 'packed h stores issued', 'arrive issued', 'copy-out stores issued', 'early k-block issued', 'next step top', 'end-of-step CTA barrier passed', 'last warp: copy-out stores issued']
 BW = ['top', None, 'cluster partials summed (DSMEM)', 'packed dZ stores issued', 'publish (arrive) issued',
-      'row-tile barrier passed', 'accum ready', 'partial tile parked in ring', 'cluster barrier passed']
+      'row-tile barrier passed', 'accum ready', 'partial tile parked in ring', 'cluster barrier passed', 'next step top']
 
 for (T, R) in [(20, 320), (50, 32)]:
     In = 512
@@ -45,10 +45,13 @@ for (T, R) in [(20, 320), (50, 32)]:
         fwd(); bwd()
     torch.cuda.synchronize()
     lib.d2p_debug_set_probe(ptr(probe))
-    fwd(); bwd()
+    fwd()
+    torch.cuda.synchronize()
+    pf = probe.cpu().tolist()[64:]
+    bwd()
     torch.cuda.synchronize()
     lib.d2p_debug_set_probe(None)
-    p = probe.cpu().tolist()[64:]
+    p = pf[:16] + probe.cpu().tolist()[64 + 16:]
     print('== T=%d R=%d forward step 5, CTA(0,0), SM cycles from loop top' % (T, R))
     for i, n in enumerate(FW):
         if n:
