@@ -53,13 +53,35 @@ class CheckpointError(IOError):
 
 
 # ----------------------------------------------------------------------------- checksums
+_CRC_TABLE = None
+
+
+def _crc32c_numpy(buf, crc=0):
+    """CRC-32C (Castagnoli, reflected 0x82F63B78) without libd2p.so: table-driven, one byte at a time
+    (slow - checkpoints can still be read on a host where the CUDA library cannot be loaded)."""
+    global _CRC_TABLE
+    if _CRC_TABLE is None:
+        t = np.arange(256, dtype=np.uint64)
+        for _ in range(8):
+            t = np.where(t & 1, (t >> np.uint64(1)) ^ np.uint64(0x82F63B78), t >> np.uint64(1))
+        _CRC_TABLE = [int(x) for x in t]
+    c = (crc ^ 0xffffffff) & 0xffffffff
+    tab = _CRC_TABLE
+    for b in buf.tobytes():
+        c = tab[(c ^ b) & 0xff] ^ (c >> 8)
+    return c ^ 0xffffffff
+
+
 def crc32c(data, crc=0):
-    from . import _lib
-    lib = _lib.load()
     buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else \
         np.ascontiguousarray(data).view(np.uint8).reshape(-1)
     if buf.size == 0:
         return crc
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:       # no libd2p.so / no CUDA driver on this host: pure-Python fallback
+        return _crc32c_numpy(buf, crc)
     return int(lib.d2p_crc32c(buf.ctypes.data, buf.size, crc))
 
 
@@ -477,8 +499,10 @@ def is_tf_checkpoint(path):
 OPT_SCOPE = 'optimizer_pixel_loss'      # optimize_loss(name=...) at reference trainer.py:108
 
 
-def with_optimizer_slots(state, adam_m, adam_v, step, beta1=0.9, beta2=0.999, trainable=None):
-    """Adds what the reference's full Saver also stores: Adam slots, beta powers, global_step.
+def with_optimizer_slots(state, adam_m, adam_v, step, beta1=0.9, beta2=0.999, trainable=None, learning_rate=1e-3):
+    """Adds what the reference's full Saver also stores: Adam slots, beta powers, the
+    `optimizer_pixel_loss/learning_rate` variable that `optimize_loss` creates for a float learning rate
+    (trainer.py:102-109; a full-graph `saver.restore` would raise NotFound without it), global_step.
 
     state: name -> array (model.state_dict()); adam_m / adam_v: name -> array for the trainable
     variables.  TF keeps beta^t as variables that start at beta and are multiplied after every
@@ -489,6 +513,7 @@ def with_optimizer_slots(state, adam_m, adam_v, step, beta1=0.9, beta2=0.999, tr
         out['%s/%s/Adam_1' % (OPT_SCOPE, name)] = adam_v[name]
     out[OPT_SCOPE + '/beta1_power'] = np.float32(beta1 ** (step + 1))
     out[OPT_SCOPE + '/beta2_power'] = np.float32(beta2 ** (step + 1))
+    out[OPT_SCOPE + '/learning_rate'] = np.float32(learning_rate)
     out['global_step'] = np.int64(step)
     return out
 
@@ -500,6 +525,8 @@ def split_optimizer_slots(variables):
     for name, a in variables.items():
         if name.startswith(pre):
             inner = name[len(pre):]
+            if inner == 'learning_rate':
+                continue
             if inner.endswith('/Adam_1'):
                 v[inner[:-7]] = a
             elif inner.endswith('/Adam'):
@@ -525,7 +552,7 @@ def save_model(prefix, model, include_optimizer=True):
     if include_optimizer and hasattr(eng, 'adam_m'):
         m = _by_name(eng.pm, eng.adam_m.cpu().numpy())
         v = _by_name(eng.pm, eng.adam_v.cpu().numpy())
-        variables = with_optimizer_slots(state, m, v, step)
+        variables = with_optimizer_slots(state, m, v, step, learning_rate=float(getattr(eng, 'lr', 1e-3)))
     else:
         variables = dict(state)
         variables['global_step'] = np.int64(step)

@@ -152,7 +152,8 @@ def test_optimizer_slot_names_follow_tf_slot_naming():
     out = tfc.with_optimizer_slots(state, m, v, step=3)
     assert set(out) == {'a/kernel', 'a/BatchNorm/moving_mean', 'optimizer_pixel_loss/a/kernel/Adam',
                         'optimizer_pixel_loss/a/kernel/Adam_1', 'optimizer_pixel_loss/beta1_power',
-                        'optimizer_pixel_loss/beta2_power', 'global_step'}
+                        'optimizer_pixel_loss/beta2_power', 'optimizer_pixel_loss/learning_rate',
+                        'global_step'}
     assert out['global_step'].dtype == np.int64
     assert np.isclose(out['optimizer_pixel_loss/beta1_power'], 0.9 ** 4)
     st, m2, v2, step = tfc.split_optimizer_slots(out)
@@ -173,7 +174,7 @@ def test_full_model_variable_set_round_trips_by_name(tmp_path):
     prefix = str(tmp_path / 'model-7')
     tfc.save_checkpoint(prefix, tfc.with_optimizer_slots(state, m, v, 7))
     names = [n for n, _, _ in tfc.list_variables(prefix)]
-    assert len(names) == 3 * len(pm.entries) + len(sm.entries) + 3
+    assert len(names) == 3 * len(pm.entries) + len(sm.entries) + 4      # + beta powers, learning_rate, global_step
     st, m2, v2, step = tfc.split_optimizer_slots(tfc.load_checkpoint(prefix))
     assert step == 7
     for e in pm:
