@@ -57,6 +57,16 @@ __device__ __forceinline__ void red_relaxed(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Reader side of a step hand-off.  The WRITERS make their generic stores of the packed operand visible to the
+// async proxy (fence.proxy.async before the release, above); the reader only has to order its own CTA's generic
+// accesses to the ring (the staged outputs) before the bulk copies that overwrite it - a shared-memory-only
+// proxy fence.  The all-state-space form waits for every global store the SM has in flight (measured: 3.8 k
+// cycles behind the 57 KB of copy-out stores, 0.4 k without them; tools/probe_persist.py).  D2P_PERSIST_FENCE=1
+// (d2p_lstm_set_persistent bit 2) restores the full fence.
+__device__ __forceinline__ void proxy_fence_reader(int full) {
+    if (full) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // Sticky device-side error word: a step barrier that timed out anywhere since the last query
 // (d2p_device_error); the per-launch word in the arena is recycled by later kernels.
@@ -82,11 +92,15 @@ constexpr int P_PROBE_STEP = 5;
 // stamp queues behind whatever the SM's memory pipe is draining and distorts the very thing it measures.
 __shared__ long long g_pstamps[32];
 __device__ __forceinline__ void pstamp(int step, int slot) {
-    if (step == P_PROBE_STEP && blockIdx.x == 0 && blockIdx.y == 0) g_pstamps[slot & 31] = clock64();
+    if (step == P_PROBE_STEP) g_pstamps[slot & 31] = clock64();
 }
-__device__ __forceinline__ void pstamp_flush() {   // after a CTA barrier, slots 0..63 belong to the per-step kernels' probe
-    if (threadIdx.x < 32 && g_tc_dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
-        g_tc_dbg[64 + threadIdx.x] = g_pstamps[threadIdx.x];
+// after a CTA barrier: CTA (0,0) -> slots 64..95 (0..63 belong to the per-step kernels' probe); every CTA ->
+// 32 slots at 256 + 32 * (blockIdx.y * gridDim.x + blockIdx.x) (SM clocks: only differences within a CTA compare)
+__device__ __forceinline__ void pstamp_flush() {
+    if (threadIdx.x < 32 && g_tc_dbg != nullptr) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) g_tc_dbg[64 + threadIdx.x] = g_pstamps[threadIdx.x];
+        g_tc_dbg[256 + 32 * (blockIdx.y * gridDim.x + blockIdx.x) + threadIdx.x] = g_pstamps[threadIdx.x];
+    }
 }
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -262,6 +276,7 @@ struct FwdArgs {
     const int* len; int R, T; float forget_bias;
     unsigned* sync;                     // [row tiles] arrival counters, sync[63] = error word
     int rt;                             // rows per row tile (multiple of 8, <= 128): row tile mt = rows [mt*rt, mt*rt + rt)
+    int full_fence;                     // reader-side proxy fence over all state spaces (see proxy_fence_reader)
 };
 
 __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const FwdArgs a) {
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
             if (issued == 0) {
                 if (t > 0) grid_wait(ctr, (unsigned)(PCOLS * t), err);
                 pstamp(t, 1);
-                proxy_fence();   // also orders the previous step's generic staging accesses before the bulk writes
+                proxy_fence_reader(a.full_fence);   // orders the previous step's generic staging accesses before the bulk writes
             }
             if (!(pb.single && issued > 0))
                 persist_produce(pb, rp, sbase, ((t & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048, a_kb_stride, rot,
@@ -396,6 +411,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
             st4r(stage_ptr(stg, 5, row, jq), h);
         }
         __syncthreads();
+        if (tid == 0) pstamp(t, 14);
         // staged outputs -> registers (4 lanes per row, 64 B per row and array), so that the ring is free again
         o_y = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cvalid) {
@@ -409,10 +425,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         __syncthreads();
         if (tid == 0) {
             issued = 0;
+            pstamp(t, 15);
             if (t + 1 < a.T) {
                 // head of step t+1's operand stream (all MMAs of step t have retired: every slot is free)
                 grid_wait(ctr, (unsigned)(PCOLS * (t + 1)), err);
-                proxy_fence();
+                pstamp(t, 17);
+                proxy_fence_reader(a.full_fence);
                 persist_produce(pb, rp, sbase, (((t + 1) & 1) ? a.hpk1 : a.hpk0) + (size_t)(m0 / 8) * 2048,
                                 a_kb_stride, rot, 0, nhead);
                 issued = nhead;
@@ -551,7 +569,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) lstm_persist_fwd_mt_kernel(cons
                     mstamp(t, j, 0);
                     if (t > 0) grid_wait(a.sync + j, (unsigned)(PCOLS * t), err);
                     mstamp(t, j, 1);
-                    proxy_fence();
+                    proxy_fence_reader(a.full_fence);
                     const uint32_t bytes = (uint32_t)(am.g0[j + 1] - am.g0[j]) * 2048u;
                     const uint8_t* src = hsrc + (size_t)am.g0[j] * 2048;
                     for (int kb = 0; kb < PNKB; ++kb) {
@@ -717,6 +735,7 @@ struct BwdArgs {
     const float* dhT; const float* dcT; float* dh0; float* dc0;
     const int* len; int R, T, has_h0;
     int rt;                             // rows per row tile (see FwdArgs)
+    int full_fence;
     float* dbpart;                      // [row tiles][4H] column sums of dZ over this tile's rows and all steps
     unsigned* sync;                     // [row tiles] dZ_t published counters, [63] error word
 };
@@ -876,7 +895,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         if (warp == 0 && lane == 0) {
             grid_wait(ctrP, (unsigned)(PCOLS * (ground + 1)), err);
             pstamp(step, 21);
-            proxy_fence();
+            proxy_fence_reader(a.full_fence);
             persist_produce(pb, rp, sbase, zsrc, a_kb_stride, rot, 0, nhead);
         }
         __syncthreads();
@@ -954,6 +973,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
 }
 
 int g_persist_mode = 1;   // 0 = per-step launches, 1 = persistent kernels where supported
+int g_persist_full_fence = 0;   // reader-side proxy fence over all state spaces (A/B switch)
 
 template <class Args>
 int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args,
@@ -1068,6 +1088,7 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
     a.gates = gates; a.cells = cells; a.Y = Y; a.h0 = h0; a.c0 = c0; a.hT = hT; a.cT = cT;
     a.len = len; a.R = R; a.T = T; a.forget_bias = forget_bias;
     a.rt = persist_row_tile(R, wide && !compact);
+    a.full_fence = g_persist_full_fence;
     static bool attr_set = false;
     if (!attr_set) {
         D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1113,6 +1134,7 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     const size_t zbytes = (size_t)kgp_of(G4) * mgp_z * 256;
     BwdArgs a;
     a.rt = persist_row_tile(R, wide);
+    a.full_fence = g_persist_full_fence;
     const int ntiles = cdiv(R, a.rt);
     a.full = full ? 1 : 0;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
@@ -1144,6 +1166,8 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
 
 // 0: one launch per recurrent step; 1 (default): persistent kernels where supported.
 extern "C" int d2p_lstm_set_persistent(int mode) {
+    d2p::g_persist_full_fence = (mode >> 2) & 1;
+    mode &= 3;
     d2p::g_persist_mode = mode;
     return 0;
 }

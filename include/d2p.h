@@ -363,7 +363,10 @@ int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes);
  * 1 (default) = ONE persistent cooperative kernel per sequence where supported
  * (H = 512, <= 512 rows, tensor-core arena configured): recurrent weight resident in
  * shared memory, cell state in registers, steps separated by a release/acquire barrier
- * among the CTAs of a row tile; 0 = one launch per time step. */
+ * among the CTAs of a row tile; 0 = one launch per time step; 2 = persistent kernels launched
+ * without the cooperative attribute (profiling under ncu).  Bit 2 (value 4, added to the mode): the
+ * producer lane's reader-side proxy fence covers all state spaces instead of shared memory only
+ * (A/B switch; see proxy_fence_reader in csrc/lstm_persist.cu). */
 int d2p_lstm_set_persistent(int mode);
 /* Synchronises the device and reports (then clears) whether a step barrier of one of the persistent
  * cooperative kernels ran into its ~2 s spin limit since the last call (0 = none, bit 0 = LSTM

@@ -30,7 +30,7 @@ for (T, R) in [(20, 320), (50, 32)]:
     dY, dX, dW, db, dh0, dc0 = torch.randn(T, R, H, device=dev), z(T, R, In), z(In + H, 4 * H), z(4 * H), z(R, H), z(R, H)
     wsb = lib.d2p_lstm_seq_bwd_ws_bytes(T, R, H)
     ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
-    probe = torch.zeros(128, dtype=torch.int64, device=dev)
+    probe = torch.zeros(256 + 32 * 160, dtype=torch.int64, device=dev)
 
     def fwd():
         check(lib.d2p_lstm_seq_fwd(ptr(X), T, R, In, H, ptr(ln), None, None, ptr(W), ptr(b), 1.0, ptr(Y), ptr(hT),
@@ -48,9 +48,22 @@ for (T, R) in [(20, 320), (50, 32)]:
     fwd()
     torch.cuda.synchronize()
     pf = probe.cpu().tolist()[64:]
+    allf = probe.cpu().numpy()[256:].reshape(-1, 32).copy()
     bwd()
     torch.cuda.synchronize()
+    allb = probe.cpu().numpy()[256:].reshape(-1, 32).copy()
     lib.d2p_debug_set_probe(None)
+    ncta = 32 * ((R + 127) // 128)
+    import numpy as np
+    def col(a, k): return (a[:ncta, k] - a[:ncta, 0]).astype(np.int64)
+    print('== all %d CTAs, forward step 5 (cycles after the CTA\'s own loop top): min / median / max' % ncta)
+    for k, n in ((2, 'last bulk copy issued'), (3, 'last MMA issued'), (5, 'accum ready'), (8, 'arrive issued'), (14, 'outputs staged'), (15, 'staging consumed'), (17, 'row-tile barrier passed'), (10, 'next head issued'), (11, 'next step top')):
+        c = col(allf, k)
+        print('   %-24s %7d %7d %7d   slowest CTA (x,y) = (%d,%d)' % (n, c.min(), np.median(c), c.max(), int(c.argmax()) % 32, int(c.argmax()) // 32))
+    print('== all CTAs, backward step 5')
+    for k, n in ((20, 'publish issued'), (21, 'row-tile barrier passed'), (22, 'accum ready'), (24, 'cluster barrier passed'), (25, 'next step top')):
+        c = (allb[:ncta, k] - allb[:ncta, 16]).astype(np.int64)
+        print('   %-24s %7d %7d %7d   slowest CTA (x,y) = (%d,%d)' % (n, c.min(), np.median(c), c.max(), int(c.argmax()) % 32, int(c.argmax()) // 32))
     p = pf[:16] + probe.cpu().tolist()[64 + 16:]
     print('== T=%d R=%d forward step 5, CTA(0,0), SM cycles from loop top' % (T, R))
     for i, n in enumerate(FW):
