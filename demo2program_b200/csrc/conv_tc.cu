@@ -44,6 +44,7 @@ constexpr size_t kSmemLimit = 227 * 1024 - 1024;   // dynamic shared memory we a
 
 int g_conv_tc_mode = 7;
 int g_conv_tc_swap = 0;   // developer switch: exchange LBO / SBO of the MN-major descriptors
+int g_conv_tc_quad = 1;   // d2p_conv_set_tc bit 5 SET: input gradient per parity class instead of the quad form
 
 __device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -91,6 +92,9 @@ struct GatherParams {
     int SH, SW, OH, OW;
     int smul, dmul;
     int act;                 // epilogue: + bias, lrelu
+    int quad;                // > 0: NOUT = 4*quad columns are the four parity classes (py, px) x `quad` channels of the
+                             // 2x2 destination block at (2y, 2x): the input gradient as ONE stride-1 product
+    int nw;                  // weight images (9 taps, or 4 in quad mode)
     int nclass, ntiles, nchunk, stages;
     TapClass cls[4];
 };
@@ -101,10 +105,10 @@ struct GatherCfg {
     static constexpr int D = G == 2 ? 2 : 1;           // (tile, tap) items per producer batch
     static constexpr uint32_t STAGE = CSRC * 512;      // one tap: 128 rows x CSRC x (hi, lo)
     static constexpr uint32_t WTAP = CSRC * NOUT * 4;  // one tap of weights: NOUT x CSRC x (hi, lo)
-    static constexpr uint32_t WBYTES = 9 * WTAP;
     static constexpr int OST = NOUT + 4;               // staging row pitch in floats (conflict-free float4 rows)
     static constexpr uint32_t OST_BYTES = kRows * OST * 4;
-    static constexpr uint32_t TCOLS = NOUT <= 16 ? 64 : (NOUT <= 32 ? 128 : 256);   // 2 buffers x 2*NOUT columns
+    static constexpr uint32_t TCOLS = NOUT <= 16 ? 64 : (NOUT <= 32 ? 128 : (NOUT <= 64 ? 256 : 512));   // 2 buffers x 2*NOUT columns
+    static_assert(4 * NOUT <= 512, "TMEM columns");
     static constexpr uint32_t B_LBO = NOUT * 32;       // bytes between k-groups of the weight image
 };
 
@@ -147,10 +151,11 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.stages;
     uint8_t* wsm = smem;
-    uint8_t* ring = wsm + C::WBYTES;
+    uint8_t* ring = wsm + (size_t)p.nw * C::WTAP;
     float* ost = reinterpret_cast<float*>(ring + (size_t)S * C::STAGE);
     long long* rowdst = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(ost) + C::OST_BYTES);
-    float* aff = reinterpret_cast<float*>(rowdst + kRows);     // [2][k*CSRC] scale | shift
+    int* rowflag = reinterpret_cast<int*>(rowdst + kRows);     // quad mode: bit 0 / 1 = row 2y+1 / column 2x+1 exists
+    float* aff = reinterpret_cast<float*>(rowflag + kRows);    // [2][k*CSRC] scale | shift
     const int kc = p.k * CSRC;
 
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]),
@@ -270,8 +275,8 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
     } else if (warp == 4) {
         if (lane == 0) {
             // ======================= MMA issuer =======================
-            mbar_expect_tx(wbar, C::WBYTES);
-            for (int t = 0; t < 9; ++t)
+            mbar_expect_tx(wbar, (uint32_t)p.nw * C::WTAP);
+            for (int t = 0; t < p.nw; ++t)
                 bulk_copy(smem_u32(wsm) + t * C::WTAP, p.wimg + (size_t)t * C::WTAP, C::WTAP, wbar);
             mbar_wait(wbar, 0);
             // f32 accumulator, bf16 x bf16, K-major A and B, M = 128
@@ -340,13 +345,28 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
             rowdst[etid] = rc.valid ? ((rc.frame * p.OH + (p.dmul * rc.y + cl.doff_y)) * p.OW +
                                        (p.dmul * rc.x + cl.doff_x))
                                     : -1;
+            rowflag[etid] = ((2 * rc.y + 1 < p.OH) ? 1 : 0) | ((2 * rc.x + 1 < p.OW) ? 2 : 0);
             epi_bar();
-            for (int idx = etid; idx < kRows * (NOUT / 4); idx += kEpi) {
-                const int row = idx / (NOUT / 4), c4 = idx - row * (NOUT / 4);
-                const long long d = rowdst[row];
-                if (d >= 0)
-                    *reinterpret_cast<float4*>(p.out + (size_t)d * NOUT + c4 * 4) =
-                        *reinterpret_cast<const float4*>(ost + row * C::OST + c4 * 4);
+            if (p.quad == 0) {
+                for (int idx = etid; idx < kRows * (NOUT / 4); idx += kEpi) {
+                    const int row = idx / (NOUT / 4), c4 = idx - row * (NOUT / 4);
+                    const long long d = rowdst[row];
+                    if (d >= 0)
+                        *reinterpret_cast<float4*>(p.out + (size_t)d * NOUT + c4 * 4) =
+                            *reinterpret_cast<const float4*>(ost + row * C::OST + c4 * 4);
+                }
+            } else {
+                // column block cls = (py, px) of a row goes to pixel (2y + py, 2x + px), `quad` channels each
+                const int QC = p.quad, q4 = QC / 4;
+                for (int idx = etid; idx < kRows * (NOUT / 4); idx += kEpi) {
+                    const int row = idx / (NOUT / 4), c4 = idx - row * (NOUT / 4);
+                    const int cls = c4 / q4, cc = (c4 - cls * q4) * 4, py = cls >> 1, px = cls & 1;
+                    const long long d = rowdst[row];
+                    const int fl = rowflag[row];
+                    if (d >= 0 && (!py || (fl & 1)) && (!px || (fl & 2)))
+                        *reinterpret_cast<float4*>(p.out + (size_t)(d + py * p.OW + px) * QC + cc) =
+                            *reinterpret_cast<const float4*>(ost + row * C::OST + c4 * 4);
+                }
             }
             float s = 0.f, s2 = 0.f;
             const int c = etid % NOUT, half = etid / NOUT;
@@ -395,6 +415,27 @@ __global__ void conv_tc_pack_w(const float* __restrict__ W, int CIN, int COUT, u
             *reinterpret_cast<bf16*>(img_x + base) = h;
             *reinterpret_cast<bf16*>(img_x + base + (size_t)(CIN / 8) * 128) = l;
         }
+    }
+}
+
+// Weight images of the quad input-gradient form: tap (iy, ix) in {0,1}^2 <-> source offset (dys[iy], dxs[ix]) on the
+// dZ grid, k = co, n = (py*2 + px)*CIN + ci with W[ky, kx, ci, co] for ky = py + PT - 2*dy, kx = px + PL - 2*dx
+// (zero when that tap does not reach the class); same core-matrix layout as conv_tc_pack_w.
+__global__ void conv_tc_pack_wq(const float* __restrict__ W, int CIN, int COUT, int PT, int PL,
+                                uint8_t* __restrict__ img) {
+    const int NOUT = 4 * CIN, total = 4 * COUT * NOUT;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx % NOUT, o = (idx / NOUT) % COUT, ti = idx / (NOUT * COUT);
+        const int cls = n / CIN, c = n - cls * CIN, py = cls >> 1, px = cls & 1;
+        const int dy = (ti >> 1) ? (PT ? 1 : -1) : 0, dx = (ti & 1) ? (PL ? 1 : -1) : 0;
+        const int ky = py + PT - 2 * dy, kx = px + PL - 2 * dx;
+        float w = 0.f;
+        if (ky >= 0 && ky < 3 && kx >= 0 && kx < 3) w = W[((size_t)(ky * 3 + kx) * CIN + c) * COUT + o];
+        const bf16 h = __float2bfloat16_rn(w);
+        const bf16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        const size_t base = ((size_t)(ti * (COUT / 8) + o / 8) * (2 * (NOUT / 8)) + n / 8) * 128 + (n % 8) * 16 + (o % 8) * 2;
+        *reinterpret_cast<bf16*>(img + base) = h;
+        *reinterpret_cast<bf16*>(img + base + (size_t)(NOUT / 8) * 128) = l;
     }
 }
 
@@ -825,7 +866,7 @@ __global__ void conv_tc_dw_reduce(const float* __restrict__ partial, int nblk, i
 }
 
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-inline size_t img_bytes(const ConvGeo& g) { return (size_t)9 * g.CIN * g.COUT * 4; }
+inline size_t img_bytes(const ConvGeo& g) { return (size_t)16 * g.CIN * g.COUT * 4; }   // 9 taps, or 4 quad taps x 4 classes
 inline int fwd_tpd(const ConvGeo& g) { return cdiv((long long)g.T * g.OH * g.OW, kRows); }
 inline int fwd_nchunk(const ConvGeo& g) { return (g.N / g.T / g.k) * fwd_tpd(g); }
 inline size_t stat_bytes(const ConvGeo& g) { return ((size_t)g.k * fwd_nchunk(g) * g.COUT * 2 + (size_t)g.k * g.COUT) * sizeof(float); }
@@ -833,7 +874,8 @@ inline size_t stat_bytes(const ConvGeo& g) { return ((size_t)g.k * fwd_nchunk(g)
 template <int CSRC, int NOUT>
 int launch_gather(cudaStream_t st, GatherParams& p) {
     using C = GatherCfg<CSRC, NOUT>;
-    const size_t fixed = C::WBYTES + C::OST_BYTES + kRows * sizeof(long long) + (size_t)2 * p.k * CSRC * sizeof(float);
+    const size_t fixed = (size_t)p.nw * C::WTAP + C::OST_BYTES + kRows * (sizeof(long long) + sizeof(int)) +
+                         (size_t)2 * p.k * CSRC * sizeof(float);
     D2P_REQUIRE(fixed + 2 * C::STAGE <= kSmemLimit, "conv tc: shared memory (k=%d)", p.k);
     int S = (int)((kSmemLimit - fixed) / C::STAGE);
     if (S > kMaxStages) S = kMaxStages;
@@ -856,6 +898,7 @@ int dispatch_gather(cudaStream_t st, int CSRC, int NOUT, GatherParams& p) {
     D2P_GATHER(16, 16); D2P_GATHER(16, 32); D2P_GATHER(16, 48);
     D2P_GATHER(32, 16); D2P_GATHER(32, 32); D2P_GATHER(32, 48);
     D2P_GATHER(48, 16); D2P_GATHER(48, 32); D2P_GATHER(48, 48);
+    D2P_GATHER(32, 64); D2P_GATHER(48, 128);       // quad input gradients of 16- and 32-channel inputs
 #undef D2P_GATHER
     return fail(D2P_ERR_ARG, "conv tc: unsupported channel counts %d -> %d", CSRC, NOUT);
 }
@@ -919,6 +962,7 @@ int conv_tc_fwd(cudaStream_t st, const ConvGeo& g, const float* in, const float*
     p.R = g.N / g.T; p.T = g.T; p.k = g.k;
     p.SH = g.IH; p.SW = g.IW; p.OH = g.OH; p.OW = g.OW;
     p.smul = 2; p.dmul = 1; p.act = 1;
+    p.nw = 9;
     p.nclass = 1;
     TapClass& c = p.cls[0];
     c.tile_begin = 0; c.tpd = fwd_tpd(g); c.DH = g.OH; c.DW = g.OW; c.doff_y = c.doff_x = 0; c.ntaps = 9;
@@ -942,6 +986,31 @@ int conv_tc_dx(cudaStream_t st, const ConvGeo& g, const float* dZ, const float* 
     p.R = g.N / g.T; p.T = g.T; p.k = g.k;
     p.SH = g.OH; p.SW = g.OW; p.OH = g.IH; p.OW = g.IW;
     p.smul = 1; p.dmul = 2; p.act = 0;
+    p.nw = 9;
+    // bit 0 = 16-channel inputs, bit 1 = 32-channel inputs.  Default: 16-channel inputs only (conv2's input gradient, the
+    // largest one).  The <48,128> instance (32-channel inputs: 2 ring stages, all 512 TMEM columns) is correct with one
+    // tile per CTA but NOT with several (wrong results / hangs in tools/quad_debug.py) - unresolved, so it stays off.
+    int quad_mask = 1;
+    if (const char* e = getenv("D2P_CONV_QUAD_MASK")) quad_mask = atoi(e);
+    if (g_conv_tc_quad && ((g.COUT == 32 && g.CIN == 16 && (quad_mask & 1)) || (g.COUT == 48 && g.CIN == 32 && (quad_mask & 2)))) {
+        // one stride-1 product over the dZ grid with 2x2 taps produces all four parity classes of a 2x2 input
+        // block at once: every dZ pixel is gathered 4 times instead of 9, and there are 4x fewer tiles
+        const int total = 4 * g.COUT * 4 * g.CIN;
+        conv_tc_pack_wq<<<cdiv(total, 256), 256, 0, st>>>(W, g.CIN, g.COUT, g.PT, g.PL, wsb + al(img_bytes(g)));
+        D2P_CHECK_LAUNCH();
+        p.quad = g.CIN; p.nw = 4;
+        p.nclass = 1;
+        TapClass& c = p.cls[0];
+        c.tile_begin = 0; c.DH = (g.IH + 1) / 2; c.DW = (g.IW + 1) / 2; c.doff_y = c.doff_x = 0; c.ntaps = 4;
+        c.tpd = cdiv((long long)g.T * c.DH * c.DW, kRows);
+        for (int ti = 0; ti < 4; ++ti) {
+            c.offy[ti] = (signed char)((ti >> 1) ? (g.PT ? 1 : -1) : 0);
+            c.offx[ti] = (signed char)((ti & 1) ? (g.PL ? 1 : -1) : 0);
+            c.wtap[ti] = (signed char)ti;
+        }
+        p.ntiles = p.R * c.tpd; p.nchunk = 0;
+        return dispatch_gather(st, g.COUT, 4 * g.CIN, p);
+    }
     int nc = 0, tiles = 0;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
@@ -1025,6 +1094,7 @@ extern "C" int d2p_conv_set_tc(int mode) {
     const int old = d2p::g_conv_tc_mode | (d2p::g_conv_tc_swap << 8);
     d2p::g_conv_tc_mode = mode & 7;
     d2p::conv_set_rgb((mode & 16) ? 0 : 1);
+    d2p::g_conv_tc_quad = (mode & 32) ? 0 : 1;
     d2p::g_conv_tc_swap = (mode >> 8) & 1;
     return old;
 }

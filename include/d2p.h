@@ -88,7 +88,9 @@ int d2p_conv_set_fused(int mode);
  * gradient, bit 2 = weight gradient run as tcgen05 implicit-GEMM kernels (bf16x3 split, no im2col
  * buffer) whenever the tensor-core arena is configured (d2p_tc_configure); bit 2 also runs the weight
  * gradient of the u8 RGB input layer (CIN = 3) on the tensor cores.  Bit 4 SET switches the direct
- * RGB-layer forward kernel (fused BatchNorm partial sums) off.  Default 7; returns the previous
+ * RGB-layer forward kernel (fused BatchNorm partial sums) off; bit 5 SET computes the input gradient of
+ * 16- / 32-channel inputs per parity class instead of the quad form (one 2x2-tap stride-1 product over
+ * the dZ grid that yields the four classes of a 2x2 input block at once).  Default 7; returns the previous
  * mode.  16 = the fp32 CUDA-core per-layer kernels everywhere (the A/B reference of the parity tests). */
 int d2p_conv_set_tc(int mode);
 

@@ -612,7 +612,9 @@ def test_tensor_core_conv_matches_cuda_core(which):
         assert rel_err(fwd['saved'], ref['saved']) < 2e-5
         assert rel_err(fwd['state'], ref['state']) < 2e-5
     pm, _ = build_manifests(cfg)
-    for mode in (2 | 16, 4 | 16, 6 | 16):   # bit 2 includes the RGB layer's weight gradient (conv_tc_dw3_kernel)
+    # bit 2 includes the RGB layer's weight gradient (conv_tc_dw3_kernel); bit 5 set: the input gradient of the
+    # 16- / 32-channel inputs per parity class instead of the quad (2x2-tap, four classes at once) form
+    for mode in (2 | 16, 2 | 16 | 32, 4 | 16, 6 | 16):
         out = _run_conv_tc(cfg, batch, mode)
         assert out['loss'] == ref['loss'] and np.array_equal(out['saved'], ref['saved'])
         for e in pm:

@@ -42,7 +42,7 @@ def compare(cfg, tag):
     eng, ref = run(cfg, batch, 16)      # every convolution on the fp32 CUDA-core per-layer kernels
     names = [e for e in eng.pm if 'conv' in e.name.lower() or 'State_Encoder' in e.name]
     print('== %s: conv variables %s' % (tag, [e.name.split('/')[-2] + '/' + e.name.split('/')[-1] for e in names][:6]))
-    for mode, label in ((0, 'rgb fwd'), (1 | 16, 'fwd'), (2 | 16, 'dx'), (4 | 16, 'dw'), (7, 'all')):
+    for mode, label in ((0, 'rgb fwd'), (1 | 16, 'fwd'), (2 | 16, 'dx (quad form)'), (2 | 16 | 32, 'dx (per class)'), (4 | 16, 'dw'), (7, 'all')):
         try:
             _, out = run(cfg, batch, mode)
         except Exception as ex:   # noqa: BLE001
