@@ -96,6 +96,7 @@ struct GatherParams {
                              // 2x2 destination block at (2y, 2x): the input gradient as ONE stride-1 product
     int nw;                  // weight images (9 taps, or 4 in quad mode)
     int nclass, ntiles, nchunk, stages;
+    int ngroups;             // active producer groups: <= kGroups and ngroups * D <= stages (see the producers)
     TapClass cls[4];
 };
 
@@ -182,9 +183,11 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
 
     if (warp >= 5) {
         // ======================= producers: gather -> bf16 hi/lo core matrices =======================
-        // kGroups groups of four warps, one thread per row.  The flat sequence of (tile, tap) items is cut into
-        // batches of D items; a group owns every kGroups-th batch, issues all of its loads, then converts - so
-        // the other groups' loads are in flight while one converts and stores.
+        // Up to kGroups groups of four warps, one thread per row.  The flat sequence of (tile, tap) items is cut into
+        // batches of D items; a group owns every ngroups-th batch, issues all of its loads, then converts - so
+        // the other groups' loads are in flight while one converts and stores.  ngroups * D <= S (ring depth):
+        // a group must not get a whole ring round ahead of the group that fills the same slot one round earlier,
+        // or its parity wait on the slot's empty barrier aliases (it would see the phase before last as complete).
         const int ptid = tid - (kEpi + 32);
         const int prow = ptid & (kRows - 1), grp = ptid >> 7;
         const uint32_t ring_u = smem_u32(ring);
@@ -202,6 +205,8 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
         const float4* src4 = reinterpret_cast<const float4*>(p.src);
         const uint32_t row_off = (uint32_t)(prow >> 3) * 128u + (uint32_t)(prow & 7) * 16u;
         int stage = (grp * C::D) % S, round = (grp * C::D) / S;     // ring position of this group's next item
+        const int NG = p.ngroups;
+        if (grp >= NG) tile = p.ntiles;                            // this group is not used (shallow ring)
         while (tile < p.ntiles) {
             float4 v[C::D][C::G][2];
             bool act[C::D], ok[C::D];
@@ -267,9 +272,9 @@ conv_tc_gather_kernel(const __grid_constant__ GatherParams p) {
                     if (++stage == S) { stage = 0; ++round; }
                 }
             }
-            stage += (kGroups - 1) * C::D;                       // the other groups' batches
+            stage += (NG - 1) * C::D;                            // the other groups' batches
             while (stage >= S) { stage -= S; ++round; }
-            for (int d = 0; d < (kGroups - 1) * C::D; ++d)
+            for (int d = 0; d < (NG - 1) * C::D; ++d)
                 if (tile < p.ntiles) advance();
         }
     } else if (warp == 4) {
@@ -451,6 +456,7 @@ struct DwParams {
     int T, k, IH, IW, OH, OW, PT, PL;
     long long npix;
     int pix_per_cta, stages, swap_ls;
+    int ngroups;             // active producer groups (<= kGroups, <= stages)
 };
 
 template <int CIN, int COUT>
@@ -528,7 +534,8 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
         const uint32_t a_off = (uint32_t)kg * C::LBO_A + (uint32_t)p8 * 16u;
         const uint32_t b_off = 2 * C::A_HALF + (uint32_t)kg * C::LBO_B + (uint32_t)sub * 128u + (uint32_t)p8 * 16u;
         int stage = grp % S, round = grp / S;
-        for (int s = grp; s < nst; s += kGroups) {
+        const int NG = p.ngroups;
+        for (int s = grp < NG ? grp : nst; s < nst; s += NG) {
             const bool valid = pix < pix_end;
             const int sl = (n / p.T) % p.k;
             const float4* fin = in4 + (size_t)n * p.IH * p.IW * (CIN / 4);
@@ -597,10 +604,10 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
             proxy_fence_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * stage);
-            stage += kGroups;
+            stage += NG;
             while (stage >= S) { stage -= S; ++round; }
-            pix += kGroups * C::PXS;
-            ox += kGroups * C::PXS;
+            pix += NG * C::PXS;
+            ox += NG * C::PXS;
             while (ox >= p.OW) { ox -= p.OW; ++oy; }
             while (oy >= p.OH) { oy -= p.OH; ++n; }
         }
@@ -750,7 +757,9 @@ conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
         const uint32_t b_off = C::A_BYTES + (uint32_t)kg * C::LBO_B + (uint32_t)(sub >> 1) * 128u +
                                (uint32_t)p8 * 16u + (uint32_t)(sub & 1) * 8u;
         // U stages per iteration: all of their byte loads are issued before the first conversion
-        constexpr int U = 3;
+        // (kGroups * U <= ring depth, see the producers of conv_tc_gather_kernel)
+        constexpr int U = 2;
+        static_assert(kGroups * U <= kMaxStages, "a producer group must stay within one ring round of the others");
         int stage = (grp * U) % S, round = (grp * U) / S;
         pix = pix0 + (long long)grp * U * C::PXS + pl;
         ox = (int)(pix % p.OW); oy = (int)((pix / p.OW) % p.OH);
@@ -879,7 +888,13 @@ int launch_gather(cudaStream_t st, GatherParams& p) {
     D2P_REQUIRE(fixed + 2 * C::STAGE <= kSmemLimit, "conv tc: shared memory (k=%d)", p.k);
     int S = (int)((kSmemLimit - fixed) / C::STAGE);
     if (S > kMaxStages) S = kMaxStages;
+    if (const char* e = getenv("D2P_CONV_TC_STAGES")) {   // developer switch: ring depth of the gather kernel
+        const int v = atoi(e);
+        if (v >= 2 && v < S) S = v;
+    }
     p.stages = S;
+    p.ngroups = S / C::D < kGroups ? S / C::D : kGroups;
+    D2P_REQUIRE(p.ngroups >= 1, "conv tc: ring too shallow");
     const size_t smem = fixed + (size_t)S * C::STAGE;
     D2P_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_gather_kernel<CSRC, NOUT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -911,6 +926,7 @@ int launch_dw(cudaStream_t st, DwParams& p, int* grid_out) {
     if (S > kMaxStages) S = kMaxStages;
     D2P_REQUIRE(S >= 2, "conv tc dw: shared memory");
     p.stages = S;
+    p.ngroups = S < kGroups ? S : kGroups;
     const long long nchunks = (p.npix + C::PXS - 1) / C::PXS;
     long long grid = nchunks < kNumSMs ? nchunks : kNumSMs;
     const long long per = (nchunks + grid - 1) / grid * C::PXS;
@@ -987,10 +1003,8 @@ int conv_tc_dx(cudaStream_t st, const ConvGeo& g, const float* dZ, const float* 
     p.SH = g.OH; p.SW = g.OW; p.OH = g.IH; p.OW = g.IW;
     p.smul = 1; p.dmul = 2; p.act = 0;
     p.nw = 9;
-    // bit 0 = 16-channel inputs, bit 1 = 32-channel inputs.  Default: 16-channel inputs only (conv2's input gradient, the
-    // largest one).  The <48,128> instance (32-channel inputs: 2 ring stages, all 512 TMEM columns) is correct with one
-    // tile per CTA but NOT with several (wrong results / hangs in tools/quad_debug.py) - unresolved, so it stays off.
-    int quad_mask = 1;
+    // developer switch: bit 0 = 16-channel inputs, bit 1 = 32-channel inputs
+    int quad_mask = 3;
     if (const char* e = getenv("D2P_CONV_QUAD_MASK")) quad_mask = atoi(e);
     if (g_conv_tc_quad && ((g.COUT == 32 && g.CIN == 16 && (quad_mask & 1)) || (g.COUT == 48 && g.CIN == 32 && (quad_mask & 2)))) {
         // one stride-1 product over the dZ grid with 2x2 taps produces all four parity classes of a 2x2 input
