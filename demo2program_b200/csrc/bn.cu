@@ -312,6 +312,49 @@ __global__ void bn_bwd_apply_v4(const float4* __restrict__ A, const float4* __re
     }
 }
 
+// bn_bwd_apply_v4<true> that also leaves the column sums of the dZ it writes (the bias gradient of the layer in
+// front of this BatchNorm) as per-block partials: thread (rl, ct) owns channel quad ct and every RL-th row of
+// the block's chunk, so its four running sums belong to fixed channels; combined over rl in a fixed order.
+// smem: float red[RL][CT][4]
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_db_v4(const float4* __restrict__ A, const float4* __restrict__ DY, float4* __restrict__ DZ,
+                   long long rows, int C4, int seg, int nsl, int rows_per_chunk,
+                   const float4* __restrict__ gamma, const float4* __restrict__ mean,
+                   const float4* __restrict__ rstd, const float4* __restrict__ k1,
+                   const float4* __restrict__ k2, float2* __restrict__ partial) {
+    extern __shared__ float red4[];
+    const int CT = C4, RL = kThreads / CT;
+    const int rl = threadIdx.x / CT, ct = threadIdx.x % CT;
+    const long long q0 = (long long)blockIdx.x * rows_per_chunk;
+    long long q1 = q0 + rows_per_chunk;
+    if (q1 > rows) q1 = rows;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rl < RL) {
+        const float4 g = gamma[ct];
+        for (long long row = q0 + rl; row < q1; row += RL) {
+            const size_t idx = (size_t)row * C4 + ct;
+            const float4 a = A[idx], dy = DY[idx];
+            const int p = (int)((row / seg) % nsl) * C4 + ct;
+            const float4 rs = rstd[p], mu = mean[p], c1 = k1[p], c2 = k2[p];
+            float4 o;
+            o.x = g.x * rs.x * (dy.x - c1.x - (a.x - mu.x) * rs.x * c2.x) * lrelu_grad_from_out(a.x);
+            o.y = g.y * rs.y * (dy.y - c1.y - (a.y - mu.y) * rs.y * c2.y) * lrelu_grad_from_out(a.y);
+            o.z = g.z * rs.z * (dy.z - c1.z - (a.z - mu.z) * rs.z * c2.z) * lrelu_grad_from_out(a.z);
+            o.w = g.w * rs.w * (dy.w - c1.w - (a.w - mu.w) * rs.w * c2.w) * lrelu_grad_from_out(a.w);
+            DZ[idx] = o;
+            s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
+        }
+        float* d = red4 + ((size_t)rl * CT + ct) * 4;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < CT * 4; w += kThreads) {
+        float acc = 0.f;
+        for (int r = 0; r < RL; ++r) acc += red4[((size_t)r * CT + w / 4) * 4 + (w & 3)];
+        partial[(size_t)blockIdx.x * (CT * 4) + w] = make_float2(acc, 0.f);
+    }
+}
+
 __global__ void colsum_finalize(const float2* __restrict__ partial, int nchunk, int C,
                                 float* __restrict__ out, float beta) {
     const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -519,6 +562,43 @@ int bn_backward(cudaStream_t st, const float* A, const float* DY, float* DZ, lon
     else
         bn_bwd_apply_kernel<false><<<ew_blocks(rows * C), 256, 0, st>>>(
             A, dy_lin, DZ, rows, C, seg, nsl, gamma, mean, rstd, k1, k2, 0, 0);
+    D2P_CHECK_LAUNCH();
+    return 0;
+}
+
+int colsum(cudaStream_t st, const float* X, long long rows, int C, float* out, float beta, void* ws,
+           size_t ws_bytes);
+
+// bn_backward(act = 1) followed by db += column sums of DZ, with the sums taken inside the apply pass (one read
+// of DZ less: 655 MB for the first ViZDoom layer at C4).  Falls back to the two calls when the layout does not
+// allow the 16-byte kernel.
+int bn_backward_db(cudaStream_t st, const float* A, const float* DY, float* DZ, long long rows, int C, int seg,
+                   int nsl, const float* gamma, const float* stats, float* dgamma, float* dbeta, float* db,
+                   int training, float* coef, void* ws, size_t ws_bytes) {
+    const float* mean = stats; const float* rstd = stats + (size_t)nsl * C;
+    float* k1 = coef; float* k2 = coef + (size_t)nsl * C;
+    int rpc_db;
+    const int nchunk_db = pick_chunks(rows, 1, &rpc_db);
+    const bool v4 = C % 4 == 0 && C / 4 <= kThreads && al16(A) && al16(DY) && al16(DZ) && al16(gamma) && al16(mean) &&
+                    al16(rstd) && al16(k1) && al16(k2) && ws_bytes >= (size_t)nchunk_db * C * sizeof(float2);
+    if (!v4) {
+        D2P_TRY(bn_backward(st, A, DY, DZ, rows, C, seg, nsl, gamma, stats, dgamma, dbeta, training, 1, coef, ws,
+                            ws_bytes, 0, 0, nullptr));
+        return colsum(st, DZ, rows, C, db, 1.0f, ws, ws_bytes);
+    }
+    int rpc;
+    const int nchunk = pick_chunks(rows / nsl, nsl, &rpc);
+    D2P_REQUIRE(ws_bytes >= (size_t)nsl * nchunk * C * sizeof(float2), "bn: workspace too small");
+    D2P_TRY(launch_colstats<1>(st, A, DY, mean, rstd, rows / nsl, C, seg, nsl, nchunk, rpc, (float2*)ws));
+    bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk, C, nsl, (double)(rows / nsl), dgamma, dbeta,
+                                                 k1, k2, training);
+    D2P_CHECK_LAUNCH();
+    const int C4 = C / 4, RL = kThreads / C4;
+    bn_bwd_apply_db_v4<<<nchunk_db, kThreads, (size_t)RL * C4 * 4 * sizeof(float), st>>>(
+        (const float4*)A, (const float4*)DY, (float4*)DZ, rows, C4, seg, nsl, rpc_db, (const float4*)gamma,
+        (const float4*)mean, (const float4*)rstd, (const float4*)k1, (const float4*)k2, (float2*)ws);
+    D2P_CHECK_LAUNCH();
+    colsum_finalize<<<cdiv(C, 8), 256, 0, st>>>((const float2*)ws, nchunk_db, C, db, 1.0f);
     D2P_CHECK_LAUNCH();
     return 0;
 }

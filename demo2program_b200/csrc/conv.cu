@@ -28,6 +28,8 @@ int bn_backward(cudaStream_t, const float*, const float*, float*, long long, int
                 const float*, const float*, float*, float*, int, int, float*, void*, size_t, int,
                 int, float*);
 int colsum(cudaStream_t, const float*, long long, int, float*, float, void*, size_t);
+int bn_backward_db(cudaStream_t, const float*, const float*, float*, long long, int, int, int, const float*,
+                   const float*, float*, float*, float*, int, float*, void*, size_t);
 size_t bn_ws_bytes(long long rows, int C, int nsl);
 int permute_frames(cudaStream_t, const float*, float*, int, int, int, int);
 int unpermute_frames(cudaStream_t, const float*, float*, int, int, int, int);
@@ -472,10 +474,8 @@ extern "C" int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, 
             D2P_TRY(unpermute_frames(st, dfeat, dy_tmp, g.N, g.OH * g.OW * g.COUT, g.T, d->B * d->k));
             dy_lin = dy_tmp;
         }
-        D2P_TRY(bn_backward(st, acts[l], dy_lin, dZ, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma,
-                            stats[l], L.dgamma, L.dbeta, training, 1, coef, part, p.part_bytes, 0, 0,
-                            nullptr));
-        D2P_TRY(colsum(st, dZ, npix, g.COUT, L.db, 1.0f, part, p.part_bytes));
+        D2P_TRY(bn_backward_db(st, acts[l], dy_lin, dZ, npix, g.COUT, g.T * g.OH * g.OW, g.k, L.gamma,
+                               stats[l], L.dgamma, L.dbeta, L.db, training, coef, part, p.part_bytes));
         int ppb; int nblk = dw_blocks(npix, &ppb);
         const float* sc = l > 0 ? stats[l - 1] + 2 * (size_t)g.k * g.CIN : nullptr;
         const float* sh = l > 0 ? stats[l - 1] + 3 * (size_t)g.k * g.CIN : nullptr;
