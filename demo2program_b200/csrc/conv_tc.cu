@@ -519,11 +519,12 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
     if (pix_end > p.npix) pix_end = p.npix;
     const int nst = (int)((pix_end - pix0 + C::PXS - 1) / C::PXS);
 
-    if (warp >= 5) {
+    if (warp != 4) {
         // ======================= producers =======================
-        // kGroups groups of four warps; a group owns every kGroups-th stage (the others' loads fly while it converts)
-        const int ptid = tid - (kEpi + 32);
-        const int grp = ptid >> 7, gt = ptid & 127;
+        // kGroups + 1 groups of four warps (the epilogue warps have nothing to do until the last stage has been
+        // multiplied, so they produce too, as group kGroups); a group owns every ngroups-th stage (the others'
+        // loads fly while it converts)
+        const int grp = warp >= 5 ? (tid - (kEpi + 32)) >> 7 : kGroups, gt = warp >= 5 ? (tid - (kEpi + 32)) & 127 : tid;
         const int pl = gt % C::PXS, sub = gt / C::PXS;
         const int kg = pl >> 3, p8 = pl & 7;
         const float4* in4 = reinterpret_cast<const float4*>(p.in);
@@ -611,7 +612,8 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
             while (ox >= p.OW) { ox -= p.OW; ++oy; }
             while (oy >= p.OH) { oy -= p.OH; ++n; }
         }
-    } else if (warp == 4) {
+    }
+    if (warp == 4) {
         if (lane == 0) {
             // ======================= MMA issuer: MN-major A (im2col^T) and B (dZ^T) =======================
             constexpr uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
@@ -643,7 +645,7 @@ conv_tc_dw_kernel(const __grid_constant__ DwParams p) {
             }
             umma_commit(accum);
         }
-    } else {
+    } else if (warp < 4) {
         // ======================= epilogue: this CTA's partial dW tile =======================
         mbar_wait(accum, 0);
         tc_fence_after();
@@ -744,9 +746,9 @@ conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
     if (pix_end > p.npix) pix_end = p.npix;
     const int nst = (int)((pix_end - pix0 + C::PXS - 1) / C::PXS);
 
-    if (warp >= 5) {
-        const int ptid = tid - (kEpi + 32);
-        const int grp = ptid >> 7, gt = ptid & 127;
+    constexpr int NG3 = kGroups + 1;   // the epilogue warps produce too (group kGroups) until the last stage
+    if (warp != 4) {
+        const int grp = warp >= 5 ? (tid - (kEpi + 32)) >> 7 : kGroups, gt = warp >= 5 ? (tid - (kEpi + 32)) & 127 : tid;
         const int pl = gt & 31, sub = gt >> 5;          // a warp = the 32 pixels of the stage, sub-lane = warp in group
         const int kg = pl >> 3, p8 = pl & 7;
         long long pix = pix0 + (long long)grp * C::PXS + pl;
@@ -759,12 +761,12 @@ conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
         // U stages per iteration: all of their byte loads are issued before the first conversion
         // (kGroups * U <= ring depth, see the producers of conv_tc_gather_kernel)
         constexpr int U = 2;
-        static_assert(kGroups * U <= kMaxStages, "a producer group must stay within one ring round of the others");
+        static_assert(NG3 * U <= kMaxStages, "a producer group must stay within one ring round of the others");
         int stage = (grp * U) % S, round = (grp * U) / S;
         pix = pix0 + (long long)grp * U * C::PXS + pl;
         ox = (int)(pix % p.OW); oy = (int)((pix / p.OW) % p.OH);
         n = (int)(pix / ((long long)p.OW * p.OH));
-        for (int s0 = grp * U; s0 < nst; s0 += kGroups * U) {
+        for (int s0 = grp * U; s0 < nst; s0 += NG3 * U) {
             float x[U][8];
             float4 z[U];
 #pragma unroll
@@ -812,14 +814,15 @@ conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
                     if (++stage == S) { stage = 0; ++round; }
                 }
             }
-            stage += (kGroups - 1) * U;
+            stage += (NG3 - 1) * U;
             while (stage >= S) { stage -= S; ++round; }
-            pix += (long long)(kGroups - 1) * U * C::PXS;
-            ox += (kGroups - 1) * U * C::PXS;
+            pix += (long long)(NG3 - 1) * U * C::PXS;
+            ox += (NG3 - 1) * U * C::PXS;
             while (ox >= p.OW) { ox -= p.OW; ++oy; }
             while (oy >= p.OH) { oy -= p.OH; ++n; }
         }
-    } else if (warp == 4) {
+    }
+    if (warp == 4) {
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(kRows >> 4) << 24) | ((uint32_t)((2 * COUT) >> 3) << 17);
@@ -840,7 +843,7 @@ conv_tc_dw3_kernel(const __grid_constant__ Dw3Params p) {
             }
             umma_commit(accum);
         }
-    } else {
+    } else if (warp < 4) {
         mbar_wait(accum, 0);
         tc_fence_after();
         float* part = p.partial + (size_t)blockIdx.x * 27 * COUT;
@@ -926,7 +929,7 @@ int launch_dw(cudaStream_t st, DwParams& p, int* grid_out) {
     if (S > kMaxStages) S = kMaxStages;
     D2P_REQUIRE(S >= 2, "conv tc dw: shared memory");
     p.stages = S;
-    p.ngroups = S < kGroups ? S : kGroups;
+    p.ngroups = S < kGroups + 1 ? S : kGroups + 1;
     const long long nchunks = (p.npix + C::PXS - 1) / C::PXS;
     long long grid = nchunks < kNumSMs ? nchunks : kNumSMs;
     const long long per = (nchunks + grid - 1) / grid * C::PXS;
