@@ -622,6 +622,27 @@ def test_tensor_core_conv_matches_cuda_core(which):
             assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max() + 1e-7 * np.abs(ref['grads']).max(), (mode, e.name)
 
 
+@pytest.mark.parametrize('stages', ['2', '3'])
+def test_tensor_core_conv_shallow_ring_is_bit_identical(stages):
+    """Regression test of the operand-ring protocol of csrc/conv_tc.cu: with a ring shallower than
+    (producer groups x batch) a group used to lap the group filling the same slot one round earlier and
+    its parity wait on the slot's empty barrier aliased (wrong tiles at 3 stages, hangs at 2).  The
+    launchers now cap the active groups; the ring depth changes no arithmetic, so forward activations and
+    all gradients must be BIT-identical to the default depth (several tiles per CTA at this size)."""
+    from demo2program_b200.config import vizdoom_config
+    from demo2program_b200.synthetic import make_batch
+    cfg = vizdoom_config('full', batch_size=8, k=3, max_demo_len=8, test_k=2, max_program_len=8)
+    batch = make_batch(cfg, seed=3)
+    ref = _run_conv_tc(cfg, batch, 7)
+    os.environ['D2P_CONV_TC_STAGES'] = stages
+    try:
+        out = _run_conv_tc(cfg, batch, 7)
+    finally:
+        del os.environ['D2P_CONV_TC_STAGES']
+    assert np.array_equal(out['saved'], ref['saved'])
+    assert np.array_equal(out['grads'], ref['grads'])
+
+
 @pytest.mark.parametrize('model,B,k', [('full', 32, 10), ('full', 4, 3), ('synthesis_baseline', 8, 2)])
 def test_persistent_recurrence_matches_per_step(model, B, k):
     """lstm_persist.cu (one cooperative kernel per sequence) against one launch per step."""
