@@ -26,7 +26,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n }"
                  ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-template <int N>
+template <int N, int M = 128>
 __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int distinct, long long* cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int dist
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = tmem_base;
     if (threadIdx.x == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         const uint32_t sa = smem_u32(smem), sb = sa + 64 * 1024;
         uint32_t lbo, sbo, layout, kstep;
         if (mode == 0) { lbo = 256; sbo = 2048; layout = 0; kstep = 512; }
@@ -135,20 +135,20 @@ void run_loop(int n_kb, int commit_every, int nwait, long long* d) {
     printf("persist loop: %d k-blocks (%d MMAs), commit every %d, %d threads polling: %.0f cycles = %.1f cyc/mma\n", n_kb,
            n_kb * 8, commit_every, nwait, (double)tot / 96, (double)tot / 96 / (n_kb * 8));
 }
-template <int N>
+template <int N, int M = 128>
 void run(int mode, int n_mma, int grid, long long* d) {
     const int smem = 192 * 1024;
-    cudaFuncSetAttribute(rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rate_kernel<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     long long h[2 * 148];
     for (int rep = 0; rep < 2; ++rep) {
-        rate_kernel<N><<<grid, 128, smem>>>(mode, n_mma, 1, d);
+        rate_kernel<N, M><<<grid, 128, smem>>>(mode, n_mma, 1, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return; }
     }
     cudaMemcpy(h, d, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
     long long issue = 0, done = 0;
     for (int i = 0; i < grid; ++i) { issue += h[2 * i]; done += h[2 * i + 1]; }
-    printf("N=%3d mode=%d grid=%3d n=%4d: issue %.1f cyc/mma, complete %.1f cyc/mma (floor %d)\n", N, mode, grid, n_mma,
+    printf("M=%3d N=%3d mode=%d grid=%3d n=%4d: issue %.1f cyc/mma, complete %.1f cyc/mma (floor %d)\n", M, N, mode, grid, n_mma,
            (double)issue / grid / n_mma, (double)done / grid / n_mma, 128 * N / 256);
 }
 int main() {
@@ -158,6 +158,9 @@ int main() {
     run_loop(80, 0, 0, d);
     for (int ce = 2; ce <= 64; ce *= 2) run_loop(80, ce, 0, d);
     run_loop(8, 8, 512, d);
+    run<64, 64>(0, 960, 148, d);       // M = 64 tiles (half the rows): is the 64-cycle floor per instruction?
+    run<128, 64>(0, 960, 148, d);
+    run<256, 64>(0, 960, 148, d);
     for (int mode = 0; mode < 4; mode += 3) {
         run<64>(mode, 96, 1, d);
         run<64>(mode, 960, 148, d);
