@@ -47,7 +47,7 @@ class Engine:
         self.token_tables = bool(token_tables)
         # compact_decoders: the action / perception decoder recurrences of `full` run in compact form
         # (32 CTAs each) side by side with the program decoder instead of one after the other
-        self.compact_decoders = bool(compact_decoders)
+        self.compact_decoders = bool(compact_decoders) and os.environ.get('D2P_COMPACT_DECODERS', '1') != '0'
         # D2P_LSTM_WIDE for the encoder / second-path recurrences: D2P_WIDE_LSTM = 1 (default) forward only,
         # 2 forward and backward, 0 never.  Measured at C2 (profiles/r02p_*): 4 x 80-row tiles shorten each
         # of these recurrences by 5-17 us, but in the backward pass the 128 CTAs leave only 20 SMs to the
