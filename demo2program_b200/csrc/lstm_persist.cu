@@ -133,6 +133,30 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* x) {
     x[0] = __uint_as_float(v0); x[1] = __uint_as_float(v1); x[2] = __uint_as_float(v2); x[3] = __uint_as_float(v3);
 }
 
+// "Stacked" operand of a 32-row recurrence (program decoder, B = 32): per 64-wide k-block 8 KB,
+//     [m-group' 0..7][k-group 0..7][8 rows x 16 B],   m-group' g < 4: bf16 HI of rows 8g..8g+7,  g >= 4: LO of rows 8(g-4)..
+// so that ONE M = 128 tcgen05.mma per k16 against [Bhi | Blo] (N = 128) yields rows 0-31 = Ahi*[Bhi|Blo] and rows
+// 32-63 = Alo*[Bhi|Blo]: all four bf16 partial products in 32 instead of 64 MMAs per step (a tile of 32 valid rows
+// costs the same ~68 cycles as a full one, M = 64 included - tools/micro/mma_rate.cu).  LBO 128, SBO 1024.
+constexpr int P_STACK_ROWS = 32;
+__device__ __forceinline__ void store_stacked4(uint8_t* base, int r, int k0, const float* x) {
+    uint32_t h[2], l[2];
+    split2(x[0], x[1], h[0], l[0]);
+    split2(x[2], x[3], h[1], l[1]);
+    uint8_t* p = base + (size_t)(k0 >> 6) * 8192 + (size_t)(((r >> 3) * 8 + ((k0 >> 3) & 7)) * 128) + (r & 7) * 16 +
+                 (k0 & 7) * 2;
+    *reinterpret_cast<uint2*>(p) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(p + 4096) = make_uint2(l[0], l[1]);
+}
+__global__ void pack_stacked32_kernel(const float* __restrict__ X /*[32, K]*/, int K, uint8_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (row, 4 consecutive k)
+    if (idx >= P_STACK_ROWS * (K / 4)) return;
+    const int r = idx / (K / 4), k0 = (idx - r * (K / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(X + (size_t)r * K + k0);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    store_stacked4(out, r, k0, x);
+}
+
 // barriers: full[PMAXSLOTS], empty[PMAXSLOTS], accum, wfull
 struct PersistBars {
     uint32_t full0, empty0, accum, wfull;
@@ -228,7 +252,7 @@ __device__ __forceinline__ void umma_imm(uint32_t tmem_d, uint64_t adesc, uint64
 // tcgen05.mma adds to the MMA time), so the descriptors are formed by adding constants to the
 // low word of two base descriptors instead of being rebuilt per MMA.
 __device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, uint32_t sbase, uint32_t tmem_d,
-                                            int rot, bool first_round) {
+                                            int rot, bool first_round, bool stacked = false) {
     // streamed operand: standard packed core matrices (hi/lo interleaved, LBO 256, SBO 2048);
     // resident slab: [hi|lo][group][k-group] (LBO 128, SBO 1024) - 16 uniform row groups, so
     // Ahi * [Bhi | Blo] is ONE N = 128 MMA into columns [0,64) | [64,128), then Alo * Bhi (N = 64)
@@ -242,6 +266,24 @@ __device__ __forceinline__ void persist_mma(const PersistBars& pb, RingPos& rp, 
     const uint64_t w_base = make_desc(sbase, WLBO, WSBO);
     const uint32_t a_slot = pb.a_bytes >> 4;
     if (first_round) mbar_wait(pb.wfull, 0);
+    if (stacked) {
+        // single-request operand in the stacked layout: one N = 128 MMA per k16 (see store_stacked4)
+        const uint64_t s_base = make_desc(sbase + (uint32_t)P_W_BYTES, 128, 1024);
+        mbar_wait(pb.full0, rp.par & 1u);
+        rp.par ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int kb = 0; kb < PNKB; ++kb) {
+            const uint64_t ad = s_base + (uint64_t)(kb * (8192 >> 4));
+            const uint64_t wd = w_base + (uint64_t)(kb * (PB_BYTES >> 4));
+            if (kb == 0) umma_imm<false>(tmem_d, ad, wd, idesc128);
+            else umma_imm<true>(tmem_d, ad, wd, idesc128);
+#pragma unroll
+            for (int kk = 1; kk < BK / 16; ++kk) umma_imm<true>(tmem_d, ad + kk * 16, wd + kk * 16, idesc128);
+        }
+        umma_commit(pb.accum);
+        return;
+    }
 #pragma unroll 1
     if (pb.single) rot = 0;
     for (int kb = 0; kb < PNKB; ++kb) {
@@ -277,6 +319,7 @@ struct FwdArgs {
     unsigned* sync;                     // [row tiles] arrival counters, sync[63] = error word
     int rt;                             // rows per row tile (multiple of 8, <= 128): row tile mt = rows [mt*rt, mt*rt + rt)
     int full_fence;                     // reader-side proxy fence over all state spaces (see proxy_fence_reader)
+    int stacked;                        // R == 32: operand in the stacked hi/lo layout (store_stacked4)
 };
 
 __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const FwdArgs a) {
@@ -357,7 +400,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
             pstamp(t, 2);
             if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
         } else if (warp == 1 && lane == 0) {
-            persist_mma(pb, rp, sbase, tmem_d, rot, t == 0);
+            persist_mma(pb, rp, sbase, tmem_d, rot, t == 0, a.stacked != 0);
             pstamp(t, 3);
             if (live) { ld4r(grow, zi); ld4r(grow + H, zj); ld4r(grow + 2 * H, zf); ld4r(grow + 3 * H, zo); }
             // only this lane polls the accumulator barrier; everybody else parks on the hardware
@@ -377,6 +420,25 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         tmem_ld4(tacc + PBN, bi); tmem_ld4(tacc + PBN + PUPT, bj); tmem_ld4(tacc + PBN + 2 * PUPT, bf);
         tmem_ld4(tacc + PBN + 3 * PUPT, bo);
         tmem_ld_wait();
+        if (a.stacked) {
+            // accumulator rows 32-63 (TMEM lanes of the warps with warp % 4 == 1) hold h_lo * [Wh_hi | Wh_lo] of
+            // rows 0-31: hand them to the owners of those rows through the ring (above the operand, idle now)
+            float* xch = reinterpret_cast<float*>(smem + P_W_BYTES + 64 * 1024) + ((warp >> 2) * 32 + lane) * 16;
+            if ((warp & 3) == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xch[e] = ai[e] + bi[e]; xch[4 + e] = aj[e] + bj[e];
+                    xch[8 + e] = af[e] + bf[e]; xch[12 + e] = ao[e] + bo[e];
+                }
+            }
+            __syncthreads();
+            if ((warp & 3) == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ai[e] += xch[e]; aj[e] += xch[4 + e]; af[e] += xch[8 + e]; ao[e] += xch[12 + e];
+                }
+            }
+        }
         if (live) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -391,7 +453,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_fwd_kernel(const Fwd
         if (tid == 64) pstamp(t, 6);
         // publish h_t (or the carried h) as next step's packed operand FIRST; everything the
         // backward pass needs is written out after the arrive, off the step-to-step critical path
-        if (t + 1 < a.T && valid) store_packed4((t & 1) ? a.hpk0 : a.hpk1, a.mgp_h, r, u0 + jq, h);
+        if (t + 1 < a.T && valid) {
+            if (a.stacked) store_stacked4((t & 1) ? a.hpk0 : a.hpk1, r, u0 + jq, h);
+            else store_packed4((t & 1) ? a.hpk0 : a.hpk1, a.mgp_h, r, u0 + jq, h);
+        }
         if (tid == 64) pstamp(t, 7);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();   // all MMAs of this step retired (ring idle), accumulator read, h_t stores issued
@@ -736,6 +801,7 @@ struct BwdArgs {
     const int* len; int R, T, has_h0;
     int rt;                             // rows per row tile (see FwdArgs)
     int full_fence;
+    int stacked;                        // R == 32: packed dZ in the stacked hi/lo layout
     float* dbpart;                      // [row tiles][4H] column sums of dZ over this tile's rows and all steps
     unsigned* sync;                     // [row tiles] dZ_t published counters, [63] error word
 };
@@ -845,6 +911,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             dhc[0] += p1.x; dhc[1] += p1.y; dhc[2] += p1.z; dhc[3] += p1.w;
             dhc[0] += p2.x; dhc[1] += p2.y; dhc[2] += p2.z; dhc[3] += p2.w;
             dhc[0] += p3.x; dhc[1] += p3.y; dhc[2] += p3.z; dhc[3] += p3.w;
+            if (a.stacked) {    // rows 32-63 of the parked tiles: the dZ_lo part of the same rows
+#pragma unroll
+                for (int sc = 0; sc < 4; ++sc) {
+                    const float4 pl = ld_dsmem4(my_part + (uint32_t)(P_STACK_ROWS * PGROW * sizeof(float)), (uint32_t)sc);
+                    dhc[0] += pl.x; dhc[1] += pl.y; dhc[2] += pl.z; dhc[3] += pl.w;
+                }
+            }
         }
         if (tid == 64) pstamp(step, 18);
         float di[4], dj[4], df[4], dq[4];
@@ -868,10 +941,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         }
         const bool do_gemm = t > 0 || a.has_h0;
         if (valid && (do_gemm || a.full)) {
-            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, u, di);
-            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, H + u, dj);
-            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 2 * H + u, df);
-            store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 3 * H + u, dq);
+            if (a.stacked) {
+                store_stacked4(a.dzpk, r, u, di); store_stacked4(a.dzpk, r, H + u, dj);
+                store_stacked4(a.dzpk, r, 2 * H + u, df); store_stacked4(a.dzpk, r, 3 * H + u, dq);
+            } else {
+                store_packed4(a.dzpk, a.mgp_z, zrow0 + r, u, di);
+                store_packed4(a.dzpk, a.mgp_z, zrow0 + r, H + u, dj);
+                store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 2 * H + u, df);
+                store_packed4(a.dzpk, a.mgp_z, zrow0 + r, 3 * H + u, dq);
+            }
         }
         if (do_gemm) {
             // packed operand first, then publish; the fp32 dZ (for the dW products after the
@@ -902,7 +980,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
         if (warp == 0 && lane == 0) {
             if (!pb.single) persist_produce(pb, rp, sbase, zsrc, a_kb_stride, rot, nhead, PNKB);
         } else if (warp == 1 && lane == 0) {
-            persist_mma(pb, rp, sbase, tmem_d, rot, ground == 0);
+            persist_mma(pb, rp, sbase, tmem_d, rot, ground == 0, a.stacked != 0);
         }
         fetch(t - 1, ngi, ngj, ngf, ngo, ncc, ncp, ndy);     // next step's inputs
         if (valid) { st4r(g, di); st4r(g + H, dj); st4r(g + 2 * H, df); st4r(g + 3 * H, dq); }
@@ -944,6 +1022,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
             const float4 p = ld_dsmem4(my_part, (uint32_t)sc);
             dhc[0] += p.x; dhc[1] += p.y; dhc[2] += p.z; dhc[3] += p.w;
         }
+        if (a.stacked) {
+#pragma unroll
+            for (int sc = 0; sc < 4; ++sc) {
+                const float4 p = ld_dsmem4(my_part + (uint32_t)(P_STACK_ROWS * PGROW * sizeof(float)), (uint32_t)sc);
+                dhc[0] += p.x; dhc[1] += p.y; dhc[2] += p.z; dhc[3] += p.w;
+            }
+        }
     }
     if (valid) {
         st4r(a.dh0 + su, dhc);
@@ -974,6 +1059,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) lstm_persist_bwd_kernel(const Bwd
 
 int g_persist_mode = 1;   // 0 = per-step launches, 1 = persistent kernels where supported
 int g_persist_full_fence = 0;   // reader-side proxy fence over all state spaces (A/B switch)
+int g_persist_stacked = 1;      // 32-row recurrences use the stacked hi/lo operand (d2p_lstm_set_persistent bit 3 clears it)
 
 template <class Args>
 int launch_coop(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args,
@@ -1080,7 +1166,11 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
     D2P_REQUIRE(a.hpk0 && a.hpk1 && a.sync, "lstm persist fwd: tensor-core scratch arena too small");
     const void* whpk;
     D2P_TRY(get_packed(st, Wh, G4, H, G4, false, true, &off, &whpk, 1000 + PBN, H));
-    if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, a.hpk0, 0, 0, mgp_h));
+    const bool stacked = R == P_STACK_ROWS && g_persist_stacked;
+    if (h0 && stacked) {
+        pack_stacked32_kernel<<<cdiv(P_STACK_ROWS * (H / 4), 256), 256, 0, st>>>(h0, H, a.hpk0);
+        D2P_CHECK_LAUNCH();
+    } else if (h0) D2P_TRY(pack_bf16(st, h0, R, H, H, true, a.hpk0, 0, 0, mgp_h));
     else D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk0, 0, hbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.hpk1, 0, hbytes, st));
     D2P_CHECK_CUDA(cudaMemsetAsync(a.sync, 0, 256, st));
@@ -1089,6 +1179,7 @@ int lstm_persist_fwd(cudaStream_t st, int T, int R, int H, const int* len, const
     a.len = len; a.R = R; a.T = T; a.forget_bias = forget_bias;
     a.rt = persist_row_tile(R, wide && !compact);
     a.full_fence = g_persist_full_fence;
+    a.stacked = (R == P_STACK_ROWS && g_persist_stacked) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
         D2P_CHECK_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1135,6 +1226,7 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
     BwdArgs a;
     a.rt = persist_row_tile(R, wide);
     a.full_fence = g_persist_full_fence;
+    a.stacked = (R == P_STACK_ROWS && g_persist_stacked) ? 1 : 0;
     const int ntiles = cdiv(R, a.rt);
     a.full = full ? 1 : 0;
     a.dzpk = (uint8_t*)tc_scratch_alloc(st, &off, zbytes);
@@ -1167,6 +1259,7 @@ int lstm_persist_bwd(cudaStream_t st, int T, int R, int H, const int* len, const
 // 0: one launch per recurrent step; 1 (default): persistent kernels where supported.
 extern "C" int d2p_lstm_set_persistent(int mode) {
     d2p::g_persist_full_fence = (mode >> 2) & 1;
+    d2p::g_persist_stacked = ((mode >> 3) & 1) ? 0 : 1;
     mode &= 3;
     d2p::g_persist_mode = mode;
     return 0;

@@ -368,7 +368,9 @@ int d2p_tc_bind_stream(void* stream, void* scratch, size_t scratch_bytes);
  * among the CTAs of a row tile; 0 = one launch per time step; 2 = persistent kernels launched
  * without the cooperative attribute (profiling under ncu).  Bit 2 (value 4, added to the mode): the
  * producer lane's reader-side proxy fence covers all state spaces instead of shared memory only
- * (A/B switch; see proxy_fence_reader in csrc/lstm_persist.cu). */
+ * (A/B switch; see proxy_fence_reader in csrc/lstm_persist.cu).  Bit 3 (value 8): 32-row recurrences
+ * (program decoder at B = 32) keep the interleaved hi/lo operand and two MMAs per k16 instead of the
+ * stacked operand (rows 0-31 = bf16 hi, rows 32-63 = lo of the same rows: one MMA per k16). */
 int d2p_lstm_set_persistent(int mode);
 /* Synchronises the device and reports (then clears) whether a step barrier of one of the persistent
  * cooperative kernels ran into its ~2 s spin limit since the last call (0 = none, bit 0 = LSTM
