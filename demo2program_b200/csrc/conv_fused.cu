@@ -17,6 +17,7 @@
 // Eval mode (moving statistics) needs no exchange at all and streams any number of frames
 // per CTA in chunks of 64.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace d2p {
 namespace {
@@ -25,7 +26,9 @@ constexpr int KF_THREADS = 512;
 constexpr int KF_MAXF = 64;                       // frames per chunk held in shared memory
 constexpr int KF_W1 = 9 * 16 * 16, KF_W2 = 9 * 16 * 32, KF_W3 = 4 * 32 * 48;
 constexpr int KF_RED = 32 * 48 * 2;
-constexpr size_t KF_SMEM = (size_t)(KF_W1 + KF_W2 + KF_W3 + KF_MAXF * (256 + 128 + 48) + KF_RED + 512) * sizeof(float);
+// weights as bf16 mma.sync B fragments: [k16 step][8-channel tile][hi|mid|lo][lane] x (b0, b1)
+constexpr int KF_WF1 = 9 * 2 * 3 * 32 * 2, KF_WF2 = 9 * 4 * 3 * 32 * 2, KF_WF3 = 8 * 6 * 3 * 32 * 2;
+constexpr size_t KF_SMEM = (size_t)(KF_WF1 + KF_WF2 + KF_WF3 + KF_MAXF * (256 + 128 + 48) + KF_RED + 512) * sizeof(float);
 constexpr long long KF_SPIN_CYCLES = 4000000000LL;
 constexpr float KF_EPS = 1e-3f, KF_DECAY = 0.9f;
 
@@ -69,32 +72,53 @@ __device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, un
     }
 }
 
-__device__ __forceinline__ void kf_load16(const void* frames, int u8, size_t pix, float* x) {
-    if (u8) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(frames) + pix * 16));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) x[q * 4 + b] = (float)((w[q] >> (8 * b)) & 0xffu);
-    } else {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + pix * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = __ldg(p + q);
-            x[q * 4] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
-        }
+// ---- warp-level tensor-core pieces of the forward kernel ----
+// The three layers are tiny GEMMs (K = 144 / 144 / 128) whose FFMA form is bound by shared-memory operand
+// wavefronts (a broadcast 16-byte weight load still occupies the pipe for four phases): measured 32 k + 33 k +
+// 16 k cycles of a 110 k-cycle kernel.  mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with EXACT operand splits
+// keeps the result at fp32 accuracy: an fp32 value is the exact sum of three bf16 terms (8 + 8 + 8 significant
+// bits), u8 frame bytes are exact in one; of the nine partial products the six of weight >= 2^-16 are issued
+// (the dropped ones are below 2^-24 relative), smallest first.
+__device__ __forceinline__ void kf_mma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x0, x1) -> packed bf16 pairs (element 0 in the low half): x = h + m + l exactly
+__device__ __forceinline__ void kf_split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
+    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+    const float s0 = r0 - __bfloat162float(m0), s1 = r1 - __bfloat162float(m1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(s0), l1 = __float2bfloat16_rn(s1);
+    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    m = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+// two adjacent frame bytes -> packed bf16 pair (exact)
+__device__ __forceinline__ uint32_t kf_u8x2_bf16(const uint8_t* p) {
+    const uint32_t v = *reinterpret_cast<const unsigned short*>(p);
+    return __byte_perm(__float_as_uint((float)(v & 0xffu)), __float_as_uint((float)(v >> 8)), 0x7632);
+}
+// B fragments of one layer: W(ks, kk, n) = weight of k-step ks, row kk (0..15) of the step, output channel n
+template <int KS, int NT, class WF>
+__device__ __forceinline__ void kf_build_frags(uint2* dst, WF W) {
+    for (int e = threadIdx.x; e < KS * NT * 32; e += KF_THREADS) {
+        const int lane = e & 31, t = e >> 5, nt = t % NT, ks = t / NT;
+        const int n = nt * 8 + (lane >> 2), k0 = (lane & 3) * 2;
+        uint32_t h0, m0, l0, h1, m1, l1;
+        kf_split3(W(ks, k0, n), W(ks, k0 + 1, n), h0, m0, l0);
+        kf_split3(W(ks, k0 + 8, n), W(ks, k0 + 9, n), h1, m1, l1);
+        uint2* o = dst + (size_t)t * 96 + lane;
+        o[0] = make_uint2(h0, h1); o[32] = make_uint2(m0, m1); o[64] = make_uint2(l0, l1);
     }
 }
-
-// acc[0..16) += x * w[0..16)
-__device__ __forceinline__ void kf_fma16(float x, const float* __restrict__ w, float* acc) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
-        acc[q * 4] = fmaf(x, ww.x, acc[q * 4]);         acc[q * 4 + 1] = fmaf(x, ww.y, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(x, ww.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x, ww.w, acc[q * 4 + 3]);
-    }
+// acc (16 x 8 tile) += A (fp32 split in three) * W (split in three), the six leading partial products
+__device__ __forceinline__ void kf_mma6(float* acc, const uint32_t* ah, const uint32_t* am, const uint32_t* al,
+                                        const uint2* wf) {
+    const uint2 bh = wf[0], bm = wf[32], bl = wf[64];
+    kf_mma(acc, al, bh.x, bh.y); kf_mma(acc, ah, bl.x, bl.y); kf_mma(acc, am, bm.x, bm.y);
+    kf_mma(acc, am, bh.x, bh.y); kf_mma(acc, ah, bm.x, bm.y); kf_mma(acc, ah, bh.x, bh.y);
 }
 
 // Per-channel (sum, sum of squares) of A[rows][C] over this CTA's rows -> red[0..C) (float2),
@@ -119,6 +143,28 @@ __device__ __forceinline__ void kf_col_stats(const float* __restrict__ A, int ro
     }
 }
 
+// The gs per-CTA partials of one slice -> shared memory with all threads' loads in flight at once (a
+// thread-per-channel loop over gs dependent-latency L2 reads cost ~5 k cycles per exchange); false if
+// they do not fit `red`, then the caller reads them from L2 in the same (fixed) order.
+template <int C>
+__device__ __forceinline__ bool kf_gather_partials(const float2* base, int gs, float* red) {
+    if (gs * C * 2 > KF_RED) return false;
+    float2* rp = reinterpret_cast<float2*>(red);
+    for (int i = threadIdx.x; i < gs * C; i += KF_THREADS) rp[i] = __ldcg(base + (size_t)(i / C) * 48 + i % C);
+    __syncthreads();
+    return true;
+}
+
+// dst[0..n) <- src[0..n) (shared <- global), 16-byte loads when the source is aligned
+__device__ __forceinline__ void kf_stage(float* dst, const float* __restrict__ src, int n) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int i = threadIdx.x; i < n / 4; i += KF_THREADS)
+            *reinterpret_cast<float4*>(dst + i * 4) = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += KF_THREADS) dst[i] = src[i];
+    }
+}
+
 // Statistics exchange + finalize of layer `l` (C channels): scale/shift of this CTA's slice
 // into sc/sh (shared memory).
 template <int C>
@@ -139,12 +185,18 @@ __device__ __forceinline__ void kf_bn_finalize(const KfArgs& a, int l, int slice
             kf_wait(ctr, (unsigned)a.gs, a.sync + 63);
         }
         __syncthreads();
+        const float2* pbase = a.partials + (size_t)(l * a.k + slice) * a.gs * 48;
+        const bool staged = kf_gather_partials<C>(pbase, a.gs, red);
         if (tid < C) {
             double s = 0.0, s2 = 0.0;
-            const float2* p = a.partials + (size_t)(l * a.k + slice) * a.gs * 48 + tid;
-            for (int jj = 0; jj < a.gs; ++jj) {
-                const float2 v = __ldcg(p + (size_t)jj * 48);
-                s += v.x; s2 += v.y;
+            if (staged) {
+                const float2* rp = reinterpret_cast<const float2*>(red);
+                for (int jj = 0; jj < a.gs; ++jj) { const float2 v = rp[jj * C + tid]; s += v.x; s2 += v.y; }
+            } else {
+                for (int jj = 0; jj < a.gs; ++jj) {
+                    const float2 v = __ldcg(pbase + (size_t)jj * 48 + tid);
+                    s += v.x; s2 += v.y;
+                }
             }
             const double count = (double)a.B * a.T * pixels;
             const double mu = s / count;
@@ -174,10 +226,10 @@ __device__ __forceinline__ void kf_bn_finalize(const KfArgs& a, int l, int slice
 
 __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float* W1s = sm;
-    float* W2s = W1s + KF_W1;
-    float* W3s = W2s + KF_W2;
-    float* A1 = W3s + KF_W3;
+    uint2* WF1 = reinterpret_cast<uint2*>(sm);
+    uint2* WF2 = WF1 + KF_WF1 / 2;
+    uint2* WF3 = WF2 + KF_WF2 / 2;
+    float* A1 = reinterpret_cast<float*>(WF3 + KF_WF3 / 2);
     float* A2 = A1 + KF_MAXF * 256;
     float* A3 = A2 + KF_MAXF * 128;
     float* red = A3 + KF_MAXF * 48;
@@ -190,92 +242,161 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
     const int g0 = (int)((long long)j * a.B * a.T / a.gs), g1 = (int)((long long)(j + 1) * a.B * a.T / a.gs);
     const int nfr = g1 - g0;
     const int R = a.B * a.k;
+    cstamp(16);
 
-    for (int i = tid; i < KF_W1; i += KF_THREADS) W1s[i] = a.L[0].w[i];
-    for (int i = tid; i < KF_W2; i += KF_THREADS) W2s[i] = a.L[1].w[i];
-    for (int i = tid; i < KF_W3; i += KF_THREADS) {
-        // taps (kh, kw) in {0,1}^2 of the 3x3 kernel: the only ones inside the 2x2 input
-        const int tap = i / (32 * 48), rem = i % (32 * 48);
-        W3s[i] = a.L[2].w[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem];
+    {
+        const float* w1 = a.L[0].w; const float* w2 = a.L[1].w; const float* w3 = a.L[2].w;
+        kf_build_frags<9, 2>(WF1, [=](int ks, int kk, int n) { return __ldg(w1 + (ks * 16 + kk) * 16 + n); });
+        kf_build_frags<9, 4>(WF2, [=](int ks, int kk, int n) { return __ldg(w2 + (ks * 16 + kk) * 32 + n); });
+        // k = tap * 32 + ci over the taps (kh, kw) in {0,1}^2 of the 3x3 kernel: the only ones inside the 2x2 input
+        kf_build_frags<8, 6>(WF3, [=](int ks, int kk, int n) {
+            const int tap = ks >> 1, ci = (ks & 1) * 16 + kk;
+            return __ldg(w3 + (((tap >> 1) * 3 + (tap & 1)) * 32 + ci) * 48 + n);
+        });
     }
+    const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, fc2 = (lane & 3) * 2;
     if (tid < 16) b1s[tid] = a.L[0].b[tid];
     if (tid < 32) b2s[tid] = a.L[1].b[tid];
     if (tid < 48) b3s[tid] = a.L[2].b[tid];
     __syncthreads();
+    cstamp(17);
 
     for (int f0 = 0; f0 < nfr; f0 += KF_MAXF) {
         const int fc = nfr - f0 < KF_MAXF ? nfr - f0 : KF_MAXF;
         // ---- conv1 (8x8x16 -> 4x4x16) + bias + lrelu ----
-        for (int it = tid; it < fc * 16; it += KF_THREADS) {
-            const int f = it >> 4, px = it & 15, oh = px >> 2, ow = px & 3;
-            const int fl = g0 + f0 + f;
-            const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
-            float acc[16];
+        if (a.frames_u8) {
+            // a warp owns whole frames: the frame's 1 KB is staged into its own A1 slot, one m16 tile = its 16 output
+            // pixels, one k16 step per tap (16 channels), the output overwrites the slot
+            for (int idx = tid; idx < fc * 64; idx += KF_THREADS) {
+                const int fl = g0 + f0 + (idx >> 6);
+                const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
+                reinterpret_cast<uint4*>(A1)[idx] =
+                    __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.frames) + n * 1024) + (idx & 63));
+            }
+            __syncthreads();
+            for (int f = warp; f < fc; f += KF_THREADS / 32) {
+                const uint8_t* fr = reinterpret_cast<const uint8_t*>(A1 + (size_t)f * 256);
+                float acc[2][4];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = b1s[c];
+                for (int nt = 0; nt < 2; ++nt) {
+                    acc[nt][0] = acc[nt][2] = b1s[nt * 8 + fc2]; acc[nt][1] = acc[nt][3] = b1s[nt * 8 + fc2 + 1];
+                }
+                const int oh = fg >> 2, ow = fg & 3;           // rows fg and fg + 8 of the tile: pixels (oh, ow), (oh + 2, ow)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int ih = 2 * oh + kh;
-                if (ih >= 8) continue;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap % 3;
+                    const int ih = 2 * oh + kh, iw = 2 * ow + kw;
+                    const bool v0 = iw < 8, v1 = iw < 8 && ih + 4 < 8;
+                    const uint8_t* p0 = fr + (ih * 8 + iw) * 16 + fc2;
+                    uint32_t af[4];
+                    af[0] = v0 ? kf_u8x2_bf16(p0) : 0u;       af[2] = v0 ? kf_u8x2_bf16(p0 + 8) : 0u;
+                    af[1] = v1 ? kf_u8x2_bf16(p0 + 512) : 0u; af[3] = v1 ? kf_u8x2_bf16(p0 + 520) : 0u;
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int iw = 2 * ow + kw;
-                    if (iw >= 8) continue;
-                    float x[16];
-                    kf_load16(a.frames, a.frames_u8, n * 64 + ih * 8 + iw, x);
-                    const float* w = W1s + (kh * 3 + kw) * 256;
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const uint2* wf = WF1 + (size_t)(tap * 2 + nt) * 96 + lane;
+                        const uint2 bh = wf[0], bm = wf[32], bl = wf[64];
+                        kf_mma(acc[nt], af, bl.x, bl.y); kf_mma(acc[nt], af, bm.x, bm.y); kf_mma(acc[nt], af, bh.x, bh.y);
+                    }
+                }
+                __syncwarp();
+                float* o = A1 + (size_t)f * 256;
 #pragma unroll
-                    for (int ci = 0; ci < 16; ++ci) kf_fma16(x[ci], w + ci * 16, acc);
+                for (int nt = 0; nt < 2; ++nt) {
+                    *reinterpret_cast<float2*>(o + fg * 16 + nt * 8 + fc2) = make_float2(lrelu_f(acc[nt][0]), lrelu_f(acc[nt][1]));
+                    *reinterpret_cast<float2*>(o + (fg + 8) * 16 + nt * 8 + fc2) = make_float2(lrelu_f(acc[nt][2]), lrelu_f(acc[nt][3]));
                 }
             }
-            float* o = A1 + (size_t)f * 256 + px * 16;
+        } else {
+            // fp32 frames (as the reference feeds them): fragments straight from global memory, split in three like any
+            // fp32 operand (for values that are exact in bf16 - the dataset's 0/1 planes - the extra terms are zero and
+            // the result is bit-identical to the u8 path)
+            for (int f = warp; f < fc; f += KF_THREADS / 32) {
+                const int fl = g0 + f0 + f;
+                const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
+                const float* fr = static_cast<const float*>(a.frames) + n * 1024;
+                float acc[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
-                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+                for (int nt = 0; nt < 2; ++nt) {
+                    acc[nt][0] = acc[nt][2] = b1s[nt * 8 + fc2]; acc[nt][1] = acc[nt][3] = b1s[nt * 8 + fc2 + 1];
+                }
+                const int oh = fg >> 2, ow = fg & 3;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap % 3;
+                    const int ih = 2 * oh + kh, iw = 2 * ow + kw;
+                    const bool v0 = iw < 8, v1 = iw < 8 && ih + 4 < 8;
+                    const float2* p0 = reinterpret_cast<const float2*>(fr + (ih * 8 + iw) * 16 + fc2);
+                    const float2 z = make_float2(0.f, 0.f);
+                    const float2 x0 = v0 ? __ldg(p0) : z, x2 = v0 ? __ldg(p0 + 4) : z;
+                    const float2 x1 = v1 ? __ldg(p0 + 256) : z, x3 = v1 ? __ldg(p0 + 260) : z;
+                    uint32_t ah[4], am[4], al[4];
+                    kf_split3(x0.x, x0.y, ah[0], am[0], al[0]); kf_split3(x1.x, x1.y, ah[1], am[1], al[1]);
+                    kf_split3(x2.x, x2.y, ah[2], am[2], al[2]); kf_split3(x3.x, x3.y, ah[3], am[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) kf_mma6(acc[nt], ah, am, al, WF1 + (size_t)(tap * 2 + nt) * 96 + lane);
+                }
+                float* o = A1 + (size_t)f * 256;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    *reinterpret_cast<float2*>(o + fg * 16 + nt * 8 + fc2) = make_float2(lrelu_f(acc[nt][0]), lrelu_f(acc[nt][1]));
+                    *reinterpret_cast<float2*>(o + (fg + 8) * 16 + nt * 8 + fc2) = make_float2(lrelu_f(acc[nt][2]), lrelu_f(acc[nt][3]));
+                }
+            }
         }
         __syncthreads();
+        cstamp(18);
         for (int idx = tid; idx < fc * 64; idx += KF_THREADS) {   // saved a1, 1 KB per frame
             const int f = idx >> 6, fl = g0 + f0 + f;
             const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
             *reinterpret_cast<float4*>(a.L[0].act + n * 256 + (idx & 63) * 4) =
                 *reinterpret_cast<const float4*>(A1 + (size_t)idx * 4);
         }
+        cstamp(19);
         kf_bn_finalize<16>(a, 0, slice, j, A1, fc * 16, 16, red, sc, sh);
+        cstamp(20);
         for (int idx = tid; idx < fc * 256; idx += KF_THREADS) A1[idx] = fmaf(A1[idx], sc[idx & 15], sh[idx & 15]);
         __syncthreads();
-        // ---- conv2 (4x4x16 -> 2x2x32): item = (16 output channels, frame, pixel) ----
-        for (int it = tid; it < fc * 8; it += KF_THREADS) {
-            const int half = it / (fc * 4), rem = it - half * fc * 4;
-            const int f = rem >> 2, px = rem & 3, oh = px >> 1, ow = px & 1;
-            float acc[16];
+        // ---- conv2 (4x4x16 -> 2x2x32): m16 tile = 4 frames x 4 output pixels, one k16 step per tap ----
+        for (int mt = warp; mt < (fc + 3) >> 2; mt += KF_THREADS / 32) {
+            const int f_lo = mt * 4 + (fg >> 2), f_hi = f_lo + 2;         // rows fg and fg + 8
+            const int r_lo = f_lo < fc ? f_lo : fc - 1, r_hi = f_hi < fc ? f_hi : fc - 1;
+            const int px = fg & 3, oh = px >> 1, ow = px & 1;
+            float acc[4][4];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = b2s[half * 16 + c];
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int ih = 2 * oh + kh;
-                if (ih >= 4) continue;
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int iw = 2 * ow + kw;
-                    if (iw >= 4) continue;
-                    const float* xin = A1 + (size_t)f * 256 + (ih * 4 + iw) * 16;
-                    const float* w = W2s + (kh * 3 + kw) * 512 + half * 16;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 xv = *reinterpret_cast<const float4*>(xin + c4 * 4);
-                        kf_fma16(xv.x, w + (c4 * 4) * 32, acc);     kf_fma16(xv.y, w + (c4 * 4 + 1) * 32, acc);
-                        kf_fma16(xv.z, w + (c4 * 4 + 2) * 32, acc); kf_fma16(xv.w, w + (c4 * 4 + 3) * 32, acc);
-                    }
-                }
+            for (int nt = 0; nt < 4; ++nt) {
+                acc[nt][0] = acc[nt][2] = b2s[nt * 8 + fc2]; acc[nt][1] = acc[nt][3] = b2s[nt * 8 + fc2 + 1];
             }
-            float* o = A2 + (size_t)f * 128 + px * 32 + half * 16;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
-                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+            for (int tap = 0; tap < 9; ++tap) {
+                const int kh = tap / 3, kw = tap % 3;
+                const int ih = 2 * oh + kh, iw = 2 * ow + kw;
+                uint32_t ah[4], am[4], al[4];
+                if (ih < 4 && iw < 4) {
+                    const float* x_lo = A1 + (size_t)r_lo * 256 + (ih * 4 + iw) * 16 + fc2;
+                    const float* x_hi = A1 + (size_t)r_hi * 256 + (ih * 4 + iw) * 16 + fc2;
+                    const float2 x0 = *reinterpret_cast<const float2*>(x_lo), x2 = *reinterpret_cast<const float2*>(x_lo + 8);
+                    const float2 x1 = *reinterpret_cast<const float2*>(x_hi), x3 = *reinterpret_cast<const float2*>(x_hi + 8);
+                    kf_split3(x0.x, x0.y, ah[0], am[0], al[0]); kf_split3(x1.x, x1.y, ah[1], am[1], al[1]);
+                    kf_split3(x2.x, x2.y, ah[2], am[2], al[2]); kf_split3(x3.x, x3.y, ah[3], am[3], al[3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ah[q] = am[q] = al[q] = 0u;
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) kf_mma6(acc[nt], ah, am, al, WF2 + (size_t)(tap * 4 + nt) * 96 + lane);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (f_lo < fc)
+                    *reinterpret_cast<float2*>(A2 + (size_t)f_lo * 128 + px * 32 + nt * 8 + fc2) =
+                        make_float2(lrelu_f(acc[nt][0]), lrelu_f(acc[nt][1]));
+                if (f_hi < fc)
+                    *reinterpret_cast<float2*>(A2 + (size_t)f_hi * 128 + px * 32 + nt * 8 + fc2) =
+                        make_float2(lrelu_f(acc[nt][2]), lrelu_f(acc[nt][3]));
+            }
         }
         __syncthreads();
+        cstamp(21);
         for (int idx = tid; idx < fc * 32; idx += KF_THREADS) {   // saved a2, 512 B per frame
             const int f = idx >> 5, fl = g0 + f0 + f;
             const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
@@ -283,32 +404,44 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
                 *reinterpret_cast<const float4*>(A2 + (size_t)idx * 4);
         }
         kf_bn_finalize<32>(a, 1, slice, j, A2, fc * 4, 4, red, sc, sh);
+        cstamp(22);
         for (int idx = tid; idx < fc * 128; idx += KF_THREADS) A2[idx] = fmaf(A2[idx], sc[idx & 31], sh[idx & 31]);
         __syncthreads();
-        // ---- conv3 (2x2x32 -> 1x1x48): item = (16 output channels, frame) ----
-        for (int it = tid; it < fc * 3; it += KF_THREADS) {
-            const int g3 = it / fc, f = it - g3 * fc;
-            float acc[16];
+        // ---- conv3 (2x2x32 -> 1x1x48): m16 tile = 16 frames, K = 4 taps x 32 channels = the frame's 128 inputs in
+        // order, a warp takes one tile and two of the six 8-channel tiles ----
+        for (int u = warp; u < ((fc + 15) >> 4) * 3; u += KF_THREADS / 32) {
+            const int mt = u / 3, ng = u - mt * 3;
+            const int f_lo = mt * 16 + fg, f_hi = f_lo + 8;
+            const int r_lo = f_lo < fc ? f_lo : fc - 1, r_hi = f_hi < fc ? f_hi : fc - 1;
+            float acc[2][4];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = b3s[g3 * 16 + c];
-#pragma unroll
-            for (int tap = 0; tap < 4; ++tap) {
-                const float* xin = A2 + (size_t)f * 128 + tap * 32;
-                const float* w = W3s + tap * 32 * 48 + g3 * 16;
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xin + c4 * 4);
-                    kf_fma16(xv.x, w + (c4 * 4) * 48, acc);     kf_fma16(xv.y, w + (c4 * 4 + 1) * 48, acc);
-                    kf_fma16(xv.z, w + (c4 * 4 + 2) * 48, acc); kf_fma16(xv.w, w + (c4 * 4 + 3) * 48, acc);
-                }
+            for (int q = 0; q < 2; ++q) {
+                const int n = (ng * 2 + q) * 8 + fc2;
+                acc[q][0] = acc[q][2] = b3s[n]; acc[q][1] = acc[q][3] = b3s[n + 1];
             }
-            float* o = A3 + (size_t)f * 48 + g3 * 16;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(o + q * 4) = make_float4(lrelu_f(acc[q * 4]), lrelu_f(acc[q * 4 + 1]),
-                                                                    lrelu_f(acc[q * 4 + 2]), lrelu_f(acc[q * 4 + 3]));
+            for (int ks = 0; ks < 8; ++ks) {
+                const float* x_lo = A2 + (size_t)r_lo * 128 + ks * 16 + fc2;
+                const float* x_hi = A2 + (size_t)r_hi * 128 + ks * 16 + fc2;
+                const float2 x0 = *reinterpret_cast<const float2*>(x_lo), x2 = *reinterpret_cast<const float2*>(x_lo + 8);
+                const float2 x1 = *reinterpret_cast<const float2*>(x_hi), x3 = *reinterpret_cast<const float2*>(x_hi + 8);
+                uint32_t ah[4], am[4], al[4];
+                kf_split3(x0.x, x0.y, ah[0], am[0], al[0]); kf_split3(x1.x, x1.y, ah[1], am[1], al[1]);
+                kf_split3(x2.x, x2.y, ah[2], am[2], al[2]); kf_split3(x3.x, x3.y, ah[3], am[3], al[3]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) kf_mma6(acc[q], ah, am, al, WF3 + (size_t)(ks * 6 + ng * 2 + q) * 96 + lane);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int n = (ng * 2 + q) * 8 + fc2;
+                if (f_lo < fc)
+                    *reinterpret_cast<float2*>(A3 + (size_t)f_lo * 48 + n) = make_float2(lrelu_f(acc[q][0]), lrelu_f(acc[q][1]));
+                if (f_hi < fc)
+                    *reinterpret_cast<float2*>(A3 + (size_t)f_hi * 48 + n) = make_float2(lrelu_f(acc[q][2]), lrelu_f(acc[q][3]));
+            }
         }
         __syncthreads();
+        cstamp(23);
         for (int idx = tid; idx < fc * 12; idx += KF_THREADS) {   // saved a3, 192 B per frame
             const int f = idx / 12, fl = g0 + f0 + f;
             const size_t n = ((size_t)(fl / a.T) * a.k + slice) * a.T + fl % a.T;
@@ -316,6 +449,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
                 *reinterpret_cast<const float4*>(A3 + (size_t)idx * 4);
         }
         kf_bn_finalize<48>(a, 2, slice, j, A3, fc, 1, red, sc, sh);
+        cstamp(24);
         // ---- feature = BN(a3), time-major [T, R, 48] ----
         for (int idx = tid; idx < fc * 48; idx += KF_THREADS) {
             const int f = idx / 48, c = idx - f * 48, fl = g0 + f0 + f;
@@ -323,6 +457,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
             a.feat[((size_t)t * R + r) * 48 + c] = fmaf(A3[idx], sc[c], sh[c]);
         }
         __syncthreads();
+        cstamp(25);
     }
     if (!a.training) return;
     // ---- moving statistics: the last CTA to finish applies the k per-slice updates in slice
@@ -431,10 +566,16 @@ __device__ __forceinline__ void kb_bn_bwd(const KbArgs& a, int l, int slice, int
         kf_wait(ctr, (unsigned)a.gs, a.sync + 63);
     }
     __syncthreads();
+    const float2* pbase = a.partials + (size_t)(l * a.k + slice) * a.gs * 48;
+    const bool staged = kf_gather_partials<C>(pbase, a.gs, red);
     if (tid < C) {
         double s = 0.0, s2 = 0.0;
-        const float2* p = a.partials + (size_t)(l * a.k + slice) * a.gs * 48 + tid;
-        for (int jj = 0; jj < a.gs; ++jj) { const float2 q = __ldcg(p + (size_t)jj * 48); s += q.x; s2 += q.y; }
+        if (staged) {
+            const float2* rp = reinterpret_cast<const float2*>(red);
+            for (int jj = 0; jj < a.gs; ++jj) { const float2 q = rp[jj * C + tid]; s += q.x; s2 += q.y; }
+        } else {
+            for (int jj = 0; jj < a.gs; ++jj) { const float2 q = __ldcg(pbase + (size_t)jj * 48 + tid); s += q.x; s2 += q.y; }
+        }
         const double count = (double)a.B * a.T * pixels;
         v[3 * C + tid] = (float)(s / count);
         v[4 * C + tid] = (float)(s2 / count);

@@ -648,7 +648,10 @@ def test_persistent_recurrence_matches_per_step(model, B, k):
     """lstm_persist.cu (one cooperative kernel per sequence) against one launch per step."""
     from demo2program_b200.synthetic import make_batch
     cfg = karel_config(model, batch_size=B, k=k)
-    batch = make_batch(cfg, seed=9)
+    # seed 1, not 9: with seed 9 at (full, 4, 3) one pre-activation of the relation-network fc1 lies within
+    # rounding of the lrelu kink, the two recurrences (1e-7 apart) pick different one-sided slopes and that
+    # bias gradient differs by 1.8e-3 (tools/variant_sens.py: 2-4e-6 on every other seed)
+    batch = make_batch(cfg, seed=1)
     a = _run_variant(cfg, batch, 1, 0)
     b = _run_variant(cfg, batch, 1, 1)
     assert abs(float(b['loss'][0] - a['loss'][0])) < 2e-5

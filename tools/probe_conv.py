@@ -1,4 +1,5 @@
-"""Developer tool (GPU): SM-clock timeline of CTA 0 of the fused Karel conv backward kernel."""
+"""Developer tool (GPU): SM-clock timelines of CTA 0 of the fused Karel conv forward / backward kernels,
+and event timings of the fused vs the per-layer (tensor-core) paths."""
 import ctypes as C
 import sys
 sys.path.insert(0, '.')
@@ -29,3 +30,36 @@ names = ['start', 'loads issued', 'layer-3 BN backward done', 'dW3 done', 'dy2 d
          'dy1 done', 'layer-1 BN backward done', 'dW1 done', 'grid barrier passed', 'partials reduced']
 for i, n in enumerate(names):
     print('%-28s +%d cycles' % (n, p[i] - p[0]))
+
+lib.d2p_debug_set_probe(ptr(probe))
+fwd()
+torch.cuda.synchronize()
+lib.d2p_debug_set_probe(None)
+p = probe.cpu().tolist()[96 + 16:]
+names = ['start', 'weights staged', 'conv1 done', 'a1 saved', 'BN1 exchanged', 'conv2 done', 'BN2 exchanged (a2 saved)',
+         'conv3 done', 'BN3 exchanged (a3 saved)', 'features written']
+print('forward:')
+for i, n in enumerate(names):
+    print('%-28s +%d cycles' % (n, p[i] - p[0]))
+
+
+def timed(fn, n=50):
+    for _ in range(5):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+print('fused: fwd %.1f us  bwd %.1f us' % (timed(fwd), timed(bwd)))
+lib.d2p_conv_set_fused(0)
+for mode in (0, 7):
+    lib.d2p_conv_set_tc(mode)
+    print('per-layer, tc mode %d: fwd %.1f us  bwd %.1f us' % (mode, timed(fwd), timed(bwd)))
+lib.d2p_conv_set_fused(1)
+lib.d2p_conv_set_tc(7)
