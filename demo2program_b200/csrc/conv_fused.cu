@@ -84,21 +84,22 @@ __device__ __forceinline__ void kf_mma(float* d, const uint32_t* a, uint32_t b0,
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// (x0, x1) -> packed bf16 pairs (element 0 in the low half): x = h + m + l exactly
+// (x0, x1) -> packed bf16 pairs (element 0 in the low half): x = h + m + l exactly.  The packed conversion
+// (cvt.rn.bf16x2.f32 = F2FP, full rate) matters: the scalar F2F form runs on the conversion pipe at 16 lanes per
+// clock and bound the backward products (444 of them per pass).
 __device__ __forceinline__ void kf_split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
-    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
-    const float s0 = r0 - __bfloat162float(m0), s1 = r1 - __bfloat162float(m1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(s0), l1 = __float2bfloat16_rn(s1);
-    h = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    m = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
-    l = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
+    const float s0 = r0 - __uint_as_float(m << 16), s1 = r1 - __uint_as_float(m & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(s1), "f"(s0));
 }
+// byte -> float without the conversion pipe (I2F issues at 16 lanes per clock): 2^23 + b is exact, subtract 2^23
+__device__ __forceinline__ float kf_u8_f32(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
 // two adjacent frame bytes -> packed bf16 pair (exact)
 __device__ __forceinline__ uint32_t kf_u8x2_bf16(const uint8_t* p) {
     const uint32_t v = *reinterpret_cast<const unsigned short*>(p);
-    return __byte_perm(__float_as_uint((float)(v & 0xffu)), __float_as_uint((float)(v >> 8)), 0x7632);
+    return __byte_perm(__float_as_uint(kf_u8_f32(v & 0xffu)), __float_as_uint(kf_u8_f32(v >> 8)), 0x7632);
 }
 // B fragments of one layer: W(ks, kk, n) = weight of k-step ks, row kk (0..15) of the step, output channel n
 template <int KS, int NT, class WF>
@@ -113,12 +114,24 @@ __device__ __forceinline__ void kf_build_frags(uint2* dst, WF W) {
         o[0] = make_uint2(h0, h1); o[32] = make_uint2(m0, m1); o[64] = make_uint2(l0, l1);
     }
 }
-// acc (16 x 8 tile) += A (fp32 split in three) * W (split in three), the six leading partial products
-__device__ __forceinline__ void kf_mma6(float* acc, const uint32_t* ah, const uint32_t* am, const uint32_t* al,
-                                        const uint2* wf) {
-    const uint2 bh = wf[0], bm = wf[32], bl = wf[64];
+// acc (16 x 8 tile) += A (fp32 split in three) * B (split in three), the six leading partial products
+__device__ __forceinline__ void kf_mma6r(float* acc, const uint32_t* ah, const uint32_t* am, const uint32_t* al,
+                                         uint2 bh, uint2 bm, uint2 bl) {
     kf_mma(acc, al, bh.x, bh.y); kf_mma(acc, ah, bl.x, bl.y); kf_mma(acc, am, bm.x, bm.y);
     kf_mma(acc, am, bh.x, bh.y); kf_mma(acc, ah, bm.x, bm.y); kf_mma(acc, ah, bh.x, bh.y);
+}
+__device__ __forceinline__ void kf_mma6(float* acc, const uint32_t* ah, const uint32_t* am, const uint32_t* al,
+                                        const uint2* wf) {
+    kf_mma6r(acc, ah, am, al, wf[0], wf[32], wf[64]);
+}
+// B fragment (k = 2c, 2c+1 | 2c+8, 2c+9 of one column) from four fp32 values
+__device__ __forceinline__ void kf_bfrag(float v0, float v1, float v8, float v9, uint2& bh, uint2& bm, uint2& bl) {
+    kf_split3(v0, v1, bh.x, bm.x, bl.x);
+    kf_split3(v8, v9, bh.y, bm.y, bl.y);
+}
+// values that are exact in bf16 (frame bytes): the pair of upper halves
+__device__ __forceinline__ uint32_t kf_pack_exact(float x0, float x1) {
+    return __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
 }
 
 // Per-channel (sum, sum of squares) of A[rows][C] over this CTA's rows -> red[0..C) (float2),
@@ -498,9 +511,7 @@ constexpr int KB_MAXF = 60;
 constexpr int KB_A1 = KB_MAXF * 256, KB_A2 = KB_MAXF * 128, KB_A3 = KB_MAXF * 48;
 // float offsets: A1 | D1 (A3, D3 alias its head) | A2 | D2 (u8 frames alias A2+D2) | W | red | misc
 constexpr int KB_OFF_A1 = 0, KB_OFF_D1 = KB_A1, KB_OFF_A2 = 2 * KB_A1, KB_OFF_D2 = KB_OFF_A2 + KB_A2;
-// weights are staged with padded rows (W3: 52 floats per (tap, ci) row, W2: 36) so that lanes that walk
-// consecutive rows with 16-byte loads fall into different banks
-constexpr int KB_W3S = 52, KB_W2S = 36, KB_WBUF = 128 * KB_W3S;
+constexpr int KB_WBUF = 9 * 2 * 2 * 3 * 32 * 2;   // W2^T as B fragments: [tap][k16 step][8-channel tile][hi|mid|lo][lane] x (b0, b1)
 constexpr int KB_OFF_W = KB_OFF_D2 + KB_A2, KB_OFF_RED = KB_OFF_W + KB_WBUF, KB_OFF_MISC = KB_OFF_RED + KF_RED;
 constexpr size_t KB_SMEM = (size_t)(KB_OFF_MISC + 1024) * sizeof(float);
 // per-CTA partial gradients: dW1 | dW2 | dW3 (4 live taps) | db1 | db2 | db3
@@ -613,6 +624,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     const int nfr = g1 - g0;
     const int R = a.B * a.k;
     float* mypart = a.part + (size_t)blockIdx.x * KB_PART;
+    const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, fc2 = (lane & 3) * 2;
     auto frame_n = [&](int f) { return ((size_t)((g0 + f) / a.T) * a.k + slice) * a.T + (g0 + f) % a.T; };
 
     cstamp(0);
@@ -631,10 +643,6 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         *reinterpret_cast<float4*>(D3 + (size_t)idx * 4) =
             *reinterpret_cast<const float4*>(a.dfeat + ((size_t)t * R + r) * 48 + q * 4);
     }
-    for (int i = tid; i < KF_W3; i += KF_THREADS) {
-        const int tap = i / (32 * 48), rem = i % (32 * 48);
-        Ws[(i / 48) * KB_W3S + i % 48] = a.L[2].w[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem];
-    }
     if (tid < 32) {   // BatchNorm of layer 2 as applied to conv3's input
         scin[tid] = a.L[1].stats[2 * a.k * 32 + slice * 32 + tid];
         shin[tid] = a.L[1].stats[3 * a.k * 32 + slice * 32 + tid];
@@ -645,105 +653,161 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     // ================= layer 3 =================
     kb_bn_bwd<48>(a, 2, slice, j, A3, D3, nfr, 1, red, misc, mypart + KB_P_B3);
     cstamp(2);
-    // dW3[tap][ci][co] = sum_f x2n[f][tap][ci] * dz3[f][co]; item = ((tap, ci), 4 output channels):
-    // one scalar + one 16-byte shared-memory load per 4 FMAs
-    for (int it = tid; it < 128 * 12; it += KF_THREADS) {
-        const int pr = it / 12, c4 = (it - pr * 12) * 4, ci = pr & 31;     // pr = tap*32 + ci
-        const float sc = scin[ci], sh = shin[ci];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int f = 0; f < nfr; ++f) {
-            const float x = fmaf(A2[(size_t)f * 128 + pr], sc, sh);
-            const float4 d = *reinterpret_cast<const float4*>(D3 + (size_t)f * 48 + c4);
-            acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y); acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
+    // The five products below are tiny GEMMs on mma.sync.m16n8k16 with exact three-way bf16 splits of both fp32
+    // operands (see the forward kernel; the FFMA forms were bound by shared-memory wavefronts and register spills:
+    // 14 k / 13 k / 25 k / 32 k / 58 k cycles of 210 k).
+    // dW3[(tap, ci)][co] = sum_f x2n[f][(tap, ci)] * dz3[f][co]: M = 128, N = 48, K = frames (zero padded);
+    // warp = (16-row tile, three of the six 8-channel tiles)
+    {
+        const int m_lo = (warp >> 1) * 16 + fg, m_hi = m_lo + 8, nh = (warp & 1) * 3;
+        const float sc_lo = scin[m_lo & 31], sh_lo = shin[m_lo & 31], sc_hi = scin[m_hi & 31], sh_hi = shin[m_hi & 31];
+        float acc[3][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+        for (int fk = fc2; fk - fc2 < nfr; fk += 16) {     // frames fk, fk + 1, fk + 8, fk + 9 are this lane's k
+            auto xa = [&](int f, int m, float sc, float sh) { return f < nfr ? fmaf(A2[(size_t)f * 128 + m], sc, sh) : 0.f; };
+            uint32_t ah[4], am[4], al[4];
+            kf_split3(xa(fk, m_lo, sc_lo, sh_lo), xa(fk + 1, m_lo, sc_lo, sh_lo), ah[0], am[0], al[0]);
+            kf_split3(xa(fk, m_hi, sc_hi, sh_hi), xa(fk + 1, m_hi, sc_hi, sh_hi), ah[1], am[1], al[1]);
+            kf_split3(xa(fk + 8, m_lo, sc_lo, sh_lo), xa(fk + 9, m_lo, sc_lo, sh_lo), ah[2], am[2], al[2]);
+            kf_split3(xa(fk + 8, m_hi, sc_hi, sh_hi), xa(fk + 9, m_hi, sc_hi, sh_hi), ah[3], am[3], al[3]);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int n = (nh + q) * 8 + fg;
+                auto dz = [&](int f) { return f < nfr ? D3[(size_t)f * 48 + n] : 0.f; };
+                uint2 bh, bm, bl;
+                kf_bfrag(dz(fk), dz(fk + 1), dz(fk + 8), dz(fk + 9), bh, bm, bl);
+                kf_mma6r(acc[q], ah, am, al, bh, bm, bl);
+            }
         }
-        *reinterpret_cast<float4*>(mypart + KB_P_W3 + pr * 48 + c4) = acc;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float* o = mypart + KB_P_W3 + (nh + q) * 8 + fc2;
+            *reinterpret_cast<float2*>(o + m_lo * 48) = make_float2(acc[q][0], acc[q][1]);
+            *reinterpret_cast<float2*>(o + m_hi * 48) = make_float2(acc[q][2], acc[q][3]);
+        }
     }
     cstamp(3);
-    // dy2[f][tap][ci] = sum_co dz3[f][co] * W3[tap][ci][co]
-    for (int idx = tid; idx < nfr * 128; idx += KF_THREADS) {
-        const int f = idx >> 7, pr = idx & 127;
-        const float* w = Ws + pr * KB_W3S;
-        const float* dz = D3 + (size_t)f * 48;
-        float acc = 0.f;
+    // dy2[f][(tap, ci)] = sum_co dz3[f][co] * W3[tap][ci][co]: M = frames, N = 128, K = 48; warp = 8-column tile,
+    // its W3^T fragments straight from global memory into registers
+    {
+        const int n = warp * 8 + fg, tap = n >> 5;
+        const float* wrow = a.L[2].w + (size_t)(((tap >> 1) * 3 + (tap & 1)) * 32 + (n & 31)) * 48 + fc2;
+        uint2 bh[3], bm[3], bl[3];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
-            const float4 dd = *reinterpret_cast<const float4*>(dz + q * 4);
-            acc = fmaf(ww.x, dd.x, acc); acc = fmaf(ww.y, dd.y, acc); acc = fmaf(ww.z, dd.z, acc); acc = fmaf(ww.w, dd.w, acc);
+        for (int ks = 0; ks < 3; ++ks)
+            kf_bfrag(__ldg(wrow + ks * 16), __ldg(wrow + ks * 16 + 1), __ldg(wrow + ks * 16 + 8), __ldg(wrow + ks * 16 + 9),
+                     bh[ks], bm[ks], bl[ks]);
+        for (int f0 = 0; f0 < nfr; f0 += 16) {
+            const int f_lo = f0 + fg, f_hi = f_lo + 8;
+            const float* x_lo = D3 + (size_t)(f_lo < nfr ? f_lo : nfr - 1) * 48 + fc2;
+            const float* x_hi = D3 + (size_t)(f_hi < nfr ? f_hi : nfr - 1) * 48 + fc2;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const float2 x0 = *reinterpret_cast<const float2*>(x_lo + ks * 16), x2 = *reinterpret_cast<const float2*>(x_lo + ks * 16 + 8);
+                const float2 x1 = *reinterpret_cast<const float2*>(x_hi + ks * 16), x3 = *reinterpret_cast<const float2*>(x_hi + ks * 16 + 8);
+                uint32_t ah[4], am[4], al[4];
+                kf_split3(x0.x, x0.y, ah[0], am[0], al[0]); kf_split3(x1.x, x1.y, ah[1], am[1], al[1]);
+                kf_split3(x2.x, x2.y, ah[2], am[2], al[2]); kf_split3(x3.x, x3.y, ah[3], am[3], al[3]);
+                kf_mma6r(acc, ah, am, al, bh[ks], bm[ks], bl[ks]);
+            }
+            if (f_lo < nfr) *reinterpret_cast<float2*>(D2 + (size_t)f_lo * 128 + warp * 8 + fc2) = make_float2(acc[0], acc[1]);
+            if (f_hi < nfr) *reinterpret_cast<float2*>(D2 + (size_t)f_hi * 128 + warp * 8 + fc2) = make_float2(acc[2], acc[3]);
         }
-        D2[idx] = acc;
     }
     __syncthreads();
     cstamp(4);
     // ================= layer 2 =================
-    for (int i = tid; i < KF_W2; i += KF_THREADS) Ws[(i >> 5) * KB_W2S + (i & 31)] = a.L[1].w[i];
+    {   // W2^T as B fragments for dy1: k = output channel, n = input channel, one pair of k16 steps per tap
+        const float* w2 = a.L[1].w;
+        kf_build_frags<18, 2>(reinterpret_cast<uint2*>(Ws), [=](int ksx, int kk, int n) {
+            return __ldg(w2 + ((ksx >> 1) * 16 + n) * 32 + (ksx & 1) * 16 + kk);
+        });
+    }
     if (tid < 16) {
         scin[tid] = a.L[0].stats[2 * a.k * 16 + slice * 16 + tid];
         shin[tid] = a.L[0].stats[3 * a.k * 16 + slice * 16 + tid];
     }
     kb_bn_bwd<32>(a, 1, slice, j, A2, D2, nfr * 4, 4, red, misc, mypart + KB_P_B2);
     cstamp(5);
-    // dW2[tap][ci][co] = sum_{f, opx valid} x1n[f][ipx][ci] * dz2[f][opx][co]; item = ((tap, ci), 4 co)
-    for (int it = tid; it < 144 * 8; it += KF_THREADS) {
-        const int pr = it >> 3, c4 = (it & 7) * 4;             // pr = tap*16 + ci
-        const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
-        const float sc = scin[ci], sh = shin[ci];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int oh = 0; oh < 2; ++oh) {
-            const int ih = 2 * oh + kh;
-            if (ih >= 4) continue;
-            for (int ow = 0; ow < 2; ++ow) {
-                const int iw = 2 * ow + kw;
-                if (iw >= 4) continue;
-                const float* xa = A1 + (ih * 4 + iw) * 16 + ci;
-                const float* dz = D2 + (oh * 2 + ow) * 32 + c4;
-                for (int f = 0; f < nfr; ++f) {
-                    const float x = fmaf(xa[(size_t)f * 256], sc, sh);
-                    const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)f * 128);
-                    acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y); acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
-                }
+    // dW2[tap][ci][co] = sum_{f, opx valid} x1n[f][ipx][ci] * dz2[f][opx][co]: per tap M = 16 ci, N = 32 co,
+    // K = (frame, output pixel), a k16 step = 4 frames x 4 pixels; warp = tap
+    if (warp < 9) {
+        const int kh = warp / 3, kw = warp % 3, c = lane & 3;
+        const int oh = c & 1;                                   // this lane's k: pixels (oh, 0), (oh, 1) of frames c/2, c/2 + 2
+        const int ih = 2 * oh + kh;
+        const bool v0 = ih < 4, v1 = ih < 4 && kw < 2;          // iw = kw (ow = 0), 2 + kw (ow = 1)
+        const float* xa0 = A1 + (ih * 4 + kw) * 16;
+        const float sc_lo = scin[fg], sh_lo = shin[fg], sc_hi = scin[fg + 8], sh_hi = shin[fg + 8];
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        for (int fA = c >> 1; fA - (c >> 1) < nfr; fA += 4) {
+            const int fB = fA + 2;
+            const bool a_ok = fA < nfr, b_ok = fB < nfr;
+            const float* pA = xa0 + (size_t)fA * 256; const float* pB = xa0 + (size_t)fB * 256;
+            uint32_t ah[4], am[4], al[4];
+            kf_split3(a_ok && v0 ? fmaf(pA[fg], sc_lo, sh_lo) : 0.f, a_ok && v1 ? fmaf(pA[32 + fg], sc_lo, sh_lo) : 0.f, ah[0], am[0], al[0]);
+            kf_split3(a_ok && v0 ? fmaf(pA[fg + 8], sc_hi, sh_hi) : 0.f, a_ok && v1 ? fmaf(pA[40 + fg], sc_hi, sh_hi) : 0.f, ah[1], am[1], al[1]);
+            kf_split3(b_ok && v0 ? fmaf(pB[fg], sc_lo, sh_lo) : 0.f, b_ok && v1 ? fmaf(pB[32 + fg], sc_lo, sh_lo) : 0.f, ah[2], am[2], al[2]);
+            kf_split3(b_ok && v0 ? fmaf(pB[fg + 8], sc_hi, sh_hi) : 0.f, b_ok && v1 ? fmaf(pB[40 + fg], sc_hi, sh_hi) : 0.f, ah[3], am[3], al[3]);
+            const float* dA = D2 + (size_t)fA * 128 + oh * 64 + fg; const float* dB = D2 + (size_t)fB * 128 + oh * 64 + fg;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint2 bh, bm, bl;
+                kf_bfrag(a_ok ? dA[nt * 8] : 0.f, a_ok ? dA[32 + nt * 8] : 0.f, b_ok ? dB[nt * 8] : 0.f, b_ok ? dB[32 + nt * 8] : 0.f, bh, bm, bl);
+                kf_mma6r(acc[nt], ah, am, al, bh, bm, bl);
             }
         }
-        *reinterpret_cast<float4*>(mypart + KB_P_W2 + pr * 32 + c4) = acc;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* o = mypart + KB_P_W2 + (warp * 16) * 32 + nt * 8 + fc2;
+            *reinterpret_cast<float2*>(o + fg * 32) = make_float2(acc[nt][0], acc[nt][1]);
+            *reinterpret_cast<float2*>(o + (fg + 8) * 32) = make_float2(acc[nt][2], acc[nt][3]);
+        }
     }
     cstamp(6);
     __syncthreads();   // A3 / D3 (aliasing D1) are dead from here
-    // dy1[f][ipx][ci] = sum_{(opx, tap): ipx = 2 opx + tap} sum_co dz2[f][opx][co] * W2[tap][ci][co]
-    // item = (frame, input channel): the 16 input pixels accumulate in registers; per (output pixel,
-    // tap) pair one broadcast 16-byte load of dz2 and one conflict-free 16-byte load of the weight row
-    for (int it = tid; it < nfr * 16; it += KF_THREADS) {
-        const int f = it >> 4, ci = it & 15;
-        float acc[16];
+    // dy1[f][ipx][ci] = sum_{(opx, tap): ipx = 2 opx + tap} sum_co dz2[f][opx][co] * W2[tap][ci][co]: per tap
+    // M = (frame, output pixel), N = 16 ci, K = 32 co; a warp owns 4-frame tiles: dz2 fragments once, nine taps,
+    // each tap's tile is added into dy1 at the input pixel it reaches (a row reaches one pixel per tap; the
+    // rows of a tile that reach the same pixel do so in different taps, hence the warp barrier between taps)
+    for (int idx = tid; idx < nfr * 64; idx += KF_THREADS) reinterpret_cast<float4*>(D1)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int mt = warp; mt < (nfr + 3) >> 2; mt += KF_THREADS / 32) {
+        const int f_lo = mt * 4 + (fg >> 2), f_hi = f_lo + 2, opx = fg & 3, oh = opx >> 1, ow = opx & 1;
+        const float* x_lo = D2 + (size_t)(f_lo < nfr ? f_lo : nfr - 1) * 128 + opx * 32 + fc2;
+        const float* x_hi = D2 + (size_t)(f_hi < nfr ? f_hi : nfr - 1) * 128 + opx * 32 + fc2;
+        uint32_t ah[2][4], am[2][4], al[2][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int opx = 0; opx < 4; ++opx) {
-            const float* dz = D2 + (size_t)f * 128 + opx * 32;
-            float4 dd[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dd[q] = *reinterpret_cast<const float4*>(dz + q * 4);
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int ih = 2 * (opx >> 1) + kh;
-                if (ih >= 4) continue;
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int iw = 2 * (opx & 1) + kw;
-                    if (iw >= 4) continue;
-                    const float* w = Ws + ((kh * 3 + kw) * 16 + ci) * KB_W2S;
-                    float s4 = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 ww = *reinterpret_cast<const float4*>(w + q * 4);
-                        s4 = fmaf(ww.x, dd[q].x, s4); s4 = fmaf(ww.y, dd[q].y, s4);
-                        s4 = fmaf(ww.z, dd[q].z, s4); s4 = fmaf(ww.w, dd[q].w, s4);
-                    }
-                    acc[ih * 4 + iw] += s4;
-                }
-            }
+        for (int ks = 0; ks < 2; ++ks) {
+            const float2 x0 = *reinterpret_cast<const float2*>(x_lo + ks * 16), x2 = *reinterpret_cast<const float2*>(x_lo + ks * 16 + 8);
+            const float2 x1 = *reinterpret_cast<const float2*>(x_hi + ks * 16), x3 = *reinterpret_cast<const float2*>(x_hi + ks * 16 + 8);
+            kf_split3(x0.x, x0.y, ah[ks][0], am[ks][0], al[ks][0]); kf_split3(x1.x, x1.y, ah[ks][1], am[ks][1], al[ks][1]);
+            kf_split3(x2.x, x2.y, ah[ks][2], am[ks][2], al[ks][2]); kf_split3(x3.x, x3.y, ah[ks][3], am[ks][3], al[ks][3]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) D1[(size_t)f * 256 + i * 16 + ci] = acc[i];
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ih = 2 * oh + tap / 3, iw = 2 * ow + tap % 3;
+            const bool ok = ih < 4 && iw < 4;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    kf_mma6(acc, ah[ks], am[ks], al[ks], reinterpret_cast<const uint2*>(Ws) + (size_t)((tap * 2 + ks) * 2 + nt) * 96 + lane);
+                if (ok && f_lo < nfr) {
+                    float2* p = reinterpret_cast<float2*>(D1 + (size_t)f_lo * 256 + (ih * 4 + iw) * 16 + nt * 8 + fc2);
+                    float2 v = *p; v.x += acc[0]; v.y += acc[1]; *p = v;
+                }
+                if (ok && f_hi < nfr) {
+                    float2* p = reinterpret_cast<float2*>(D1 + (size_t)f_hi * 256 + (ih * 4 + iw) * 16 + nt * 8 + fc2);
+                    float2 v = *p; v.x += acc[2]; v.y += acc[3]; *p = v;
+                }
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
     cstamp(7);
@@ -755,49 +819,84 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
             *reinterpret_cast<uint4*>(FR + (size_t)idx * 16) = __ldg(reinterpret_cast<const uint4*>(
                 static_cast<const uint8_t*>(a.frames) + frame_n(idx >> 6) * 1024 + (idx & 63) * 16));
     __syncthreads();
-    // dW1[tap][ci][co] = sum_{f, opx valid} x0[f][ipx][ci] * dz1[f][opx][co]; item = ((tap, ci), 4 co);
-    // Karel frames are one-hot planes: most x are zero and skip the gradient load
+    // dW1[tap][ci][co] = sum_{f, opx} x0[f][ipx][ci] * dz1[f][opx][co]: per tap M = 16 ci, N = 16 co, K = (frame,
+    // 16 output pixels), a k16 step = one frame.  warp = (one of 8 frame groups, taps 0-4 | 5-8): the dz1 fragments
+    // of a frame are split once for the warp's taps; the 8 partial sets meet in shared memory in a fixed order.
+    // Frame bytes are exact in one bf16 term (three products); fp32 frames take the general six (the same
+    // non-zero products in the same order when the values are 0/1 planes: bit-identical).
     {
-        const float* ff = static_cast<const float*>(a.frames);   // fp32 frames (as the reference feeds): from L2
-        for (int it = tid; it < 144 * 4; it += KF_THREADS) {
-            const int pr = it >> 2, c4 = (it & 3) * 4;
-            const int tap = pr >> 4, ci = pr & 15, kh = tap / 3, kw = tap % 3;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int oh = 0; oh < 4; ++oh) {
-                const int ih = 2 * oh + kh;
-                if (ih >= 8) continue;
-                for (int ow = 0; ow < 4; ++ow) {
-                    const int iw = 2 * ow + kw;
-                    if (iw >= 8) continue;
-                    const int xo = (ih * 8 + iw) * 16 + ci;
-                    const float* dz = D1 + (oh * 4 + ow) * 16 + c4;
-                    int f = 0;
+        const int kq = warp >> 1, t0 = (warp & 1) * 5, ntap = (warp & 1) ? 4 : 5, c = lane & 3;
+        const int oh = c >> 1, ow = (c & 1) * 2;               // this lane's k: pixels (oh, ow), (oh, ow + 1), (oh + 2, ..)
+        const float* ff = static_cast<const float*>(a.frames);
+        float acc[5][2][4];
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) acc[t][nt][0] = acc[t][nt][1] = acc[t][nt][2] = acc[t][nt][3] = 0.f;
+        for (int f = kq; f < nfr; f += 8) {
+            uint2 bh[2], bm[2], bl[2];
+            const float* dz = D1 + (size_t)f * 256 + (oh * 4 + ow) * 16 + fg;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                kf_bfrag(dz[nt * 8], dz[16 + nt * 8], dz[128 + nt * 8], dz[144 + nt * 8], bh[nt], bm[nt], bl[nt]);
+            const size_t fbase = a.frames_u8 ? (size_t)f * 1024 : frame_n(f) * 1024;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                if (t < ntap) {
+                    const int tap = t0 + t, kh = tap / 3, kw = tap - kh * 3;
+                    const int ih = 2 * oh + kh, iw = 2 * ow + kw;      // second pixel: iw + 2; k + 8: ih + 4
+                    const bool w0 = iw < 8, w1 = iw + 2 < 8, h1 = ih + 4 < 8;
+                    const size_t o = fbase + (ih * 8 + iw) * 16 + fg;
+                    float x[8];       // (pixel 0 | pixel 1) x (ci = fg | fg + 8) for k, then the same for k + 8
                     if (a.frames_u8) {
-                        for (; f + 4 <= nfr; f += 4) {     // four independent loads in flight
-                            float x[4];
+                        const uint8_t* q = FR + o;
+                        x[0] = w0 ? kf_u8_f32(q[0]) : 0.f;        x[1] = w1 ? kf_u8_f32(q[32]) : 0.f;
+                        x[2] = w0 ? kf_u8_f32(q[8]) : 0.f;        x[3] = w1 ? kf_u8_f32(q[40]) : 0.f;
+                        x[4] = w0 && h1 ? kf_u8_f32(q[512]) : 0.f; x[5] = w1 && h1 ? kf_u8_f32(q[544]) : 0.f;
+                        x[6] = w0 && h1 ? kf_u8_f32(q[520]) : 0.f; x[7] = w1 && h1 ? kf_u8_f32(q[552]) : 0.f;
+                        uint32_t af[4];
+                        af[0] = kf_pack_exact(x[0], x[1]); af[1] = kf_pack_exact(x[2], x[3]);
+                        af[2] = kf_pack_exact(x[4], x[5]); af[3] = kf_pack_exact(x[6], x[7]);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) x[u] = (float)FR[(size_t)(f + u) * 1024 + xo];
+                        for (int nt = 0; nt < 2; ++nt) {
+                            kf_mma(acc[t][nt], af, bl[nt].x, bl[nt].y); kf_mma(acc[t][nt], af, bm[nt].x, bm[nt].y);
+                            kf_mma(acc[t][nt], af, bh[nt].x, bh[nt].y);
+                        }
+                    } else {
+                        const float* q = ff + o;
+                        x[0] = w0 ? __ldg(q) : 0.f;              x[1] = w1 ? __ldg(q + 32) : 0.f;
+                        x[2] = w0 ? __ldg(q + 8) : 0.f;          x[3] = w1 ? __ldg(q + 40) : 0.f;
+                        x[4] = w0 && h1 ? __ldg(q + 512) : 0.f;  x[5] = w1 && h1 ? __ldg(q + 544) : 0.f;
+                        x[6] = w0 && h1 ? __ldg(q + 520) : 0.f;  x[7] = w1 && h1 ? __ldg(q + 552) : 0.f;
+                        uint32_t ah[4], am[4], al[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (x[u] != 0.f) {
-                                    const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)(f + u) * 256);
-                                    acc.x = fmaf(x[u], d.x, acc.x); acc.y = fmaf(x[u], d.y, acc.y);
-                                    acc.z = fmaf(x[u], d.z, acc.z); acc.w = fmaf(x[u], d.w, acc.w);
-                                }
-                        }
-                    }
-                    for (; f < nfr; ++f) {
-                        const float x = a.frames_u8 ? (float)FR[(size_t)f * 1024 + xo] : __ldg(ff + frame_n(f) * 1024 + xo);
-                        if (x != 0.f) {
-                            const float4 d = *reinterpret_cast<const float4*>(dz + (size_t)f * 256);
-                            acc.x = fmaf(x, d.x, acc.x); acc.y = fmaf(x, d.y, acc.y);
-                            acc.z = fmaf(x, d.z, acc.z); acc.w = fmaf(x, d.w, acc.w);
-                        }
+                        for (int r = 0; r < 4; ++r) kf_split3(x[2 * r], x[2 * r + 1], ah[r], am[r], al[r]);
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) kf_mma6r(acc[t][nt], ah, am, al, bh[nt], bm[nt], bl[nt]);
                     }
                 }
             }
-            *reinterpret_cast<float4*>(mypart + KB_P_W1 + pr * 16 + c4) = acc;
         }
+        float* set = kq < 6 ? A1 + kq * KF_W1 : Ws + (kq - 6) * KF_W1;     // A1 is dead, Ws + red are free
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < ntap)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float* o = set + ((t0 + t) * 16) * 16 + nt * 8 + fc2;
+                    *reinterpret_cast<float2*>(o + fg * 16) = make_float2(acc[t][nt][0], acc[t][nt][1]);
+                    *reinterpret_cast<float2*>(o + (fg + 8) * 16) = make_float2(acc[t][nt][2], acc[t][nt][3]);
+                }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < KF_W1 / 4; idx += KF_THREADS) {
+        float4 sum = reinterpret_cast<const float4*>(A1)[idx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            const float4 v = reinterpret_cast<const float4*>(q < 6 ? A1 + q * KF_W1 : Ws + (q - 6) * KF_W1)[idx];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        *reinterpret_cast<float4*>(mypart + KB_P_W1 + idx * 4) = sum;
     }
     cstamp(9);
     // ================= grid-wide fixed-order reduction of the partial gradients =================
@@ -810,10 +909,27 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     }
     __syncthreads();
     cstamp(10);
-    for (int idx = blockIdx.x * KF_THREADS + tid; idx < KB_PART + 96; idx += gridDim.x * KF_THREADS)
-    if (idx < KB_PART) {
-        double s = 0.0;
-        for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(a.part + (size_t)c * KB_PART + idx);
+    // every CTA sums an equal share of the outputs; four adjacent lanes take a quarter of the per-CTA partials
+    // each (in CTA order) and meet in a fixed order: (q0 + q1) + (q2 + q3)
+    const int per = (KB_PART + 96 + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int it = tid; it < ((per * 4 + 31) & ~31); it += KF_THREADS) {
+        const int ol = it >> 2, q = it & 3, idx = blockIdx.x * per + ol;
+        const bool live = ol < per && idx < KB_PART + 96;
+        double s = 0.0, s2 = 0.0;
+        if (live && idx < KB_PART) {
+            const unsigned c0 = gridDim.x * q / 4, c1 = gridDim.x * (q + 1) / 4;
+            for (unsigned c = c0; c < c1; ++c) s += __ldcg(a.part + (size_t)c * KB_PART + idx);
+        } else if (live) {   // dgamma / dbeta: slice totals in slice order
+            const int c96 = idx - KB_PART;
+            const int l = c96 < 16 ? 0 : (c96 < 48 ? 1 : 2), c = c96 - (l == 0 ? 0 : (l == 1 ? 16 : 48));
+            for (int sl = a.k * q / 4; sl < a.k * (q + 1) / 4; ++sl) {
+                const float2 t2 = __ldcg(a.totals + (l * a.k + sl) * 48 + c);
+                s += t2.x; s2 += t2.y;
+            }
+        }
+        s += __shfl_down_sync(0xffffffffu, s, 1); s2 += __shfl_down_sync(0xffffffffu, s2, 1);
+        s += __shfl_down_sync(0xffffffffu, s, 2); s2 += __shfl_down_sync(0xffffffffu, s2, 2);
+        if (!live || q != 0) continue;
         const float v = (float)s;
         if (idx < KB_P_W2) a.L[0].dw[idx] += v;
         else if (idx < KB_P_W3) a.L[1].dw[idx - KB_P_W2] += v;
@@ -822,17 +938,13 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
             a.L[2].dw[((tap >> 1) * 3 + (tap & 1)) * 32 * 48 + rem] += v;
         } else if (idx < KB_P_B2) a.L[0].db[idx - KB_P_B1] += v;
         else if (idx < KB_P_B3) a.L[1].db[idx - KB_P_B2] += v;
-        else a.L[2].db[idx - KB_P_B3] += v;
-    } else {   // dgamma / dbeta: slice totals in slice order
-        const int c96 = idx - KB_PART;
-        const int l = c96 < 16 ? 0 : (c96 < 48 ? 1 : 2), c = c96 - (l == 0 ? 0 : (l == 1 ? 16 : 48));
-        double tg = 0.0, tb = 0.0;
-        for (int sl = 0; sl < a.k; ++sl) {
-            const float2 t2 = __ldcg(a.totals + (l * a.k + sl) * 48 + c);
-            tb += t2.x; tg += t2.y;
+        else if (idx < KB_PART) a.L[2].db[idx - KB_P_B3] += v;
+        else {
+            const int c96 = idx - KB_PART;
+            const int l = c96 < 16 ? 0 : (c96 < 48 ? 1 : 2), c = c96 - (l == 0 ? 0 : (l == 1 ? 16 : 48));
+            a.L[l].dbeta[c] += v;
+            a.L[l].dgamma[c] += (float)s2;
         }
-        a.L[l].dgamma[c] += (float)tg;
-        a.L[l].dbeta[c] += (float)tb;
     }
     cstamp(11);
 }
