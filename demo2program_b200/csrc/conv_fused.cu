@@ -102,14 +102,26 @@ __device__ __forceinline__ uint32_t kf_u8x2_bf16(const uint8_t* p) {
     return __byte_perm(__float_as_uint(kf_u8_f32(v & 0xffu)), __float_as_uint(kf_u8_f32(v >> 8)), 0x7632);
 }
 // B fragments of one layer: W(ks, kk, n) = weight of k-step ks, row kk (0..15) of the step, output channel n
-template <int KS, int NT, class WF>
+// two-term split (x = h + l + O(2^-17 x)), same signature: the middle term is zero
+__device__ __forceinline__ void kb_split2(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+    m = 0u;
+}
+template <int KS, int NT, bool EXACT = true, class WF>
 __device__ __forceinline__ void kf_build_frags(uint2* dst, WF W) {
     for (int e = threadIdx.x; e < KS * NT * 32; e += KF_THREADS) {
         const int lane = e & 31, t = e >> 5, nt = t % NT, ks = t / NT;
         const int n = nt * 8 + (lane >> 2), k0 = (lane & 3) * 2;
         uint32_t h0, m0, l0, h1, m1, l1;
-        kf_split3(W(ks, k0, n), W(ks, k0 + 1, n), h0, m0, l0);
-        kf_split3(W(ks, k0 + 8, n), W(ks, k0 + 9, n), h1, m1, l1);
+        if (EXACT) {
+            kf_split3(W(ks, k0, n), W(ks, k0 + 1, n), h0, m0, l0);
+            kf_split3(W(ks, k0 + 8, n), W(ks, k0 + 9, n), h1, m1, l1);
+        } else {
+            kb_split2(W(ks, k0, n), W(ks, k0 + 1, n), h0, m0, l0);
+            kb_split2(W(ks, k0 + 8, n), W(ks, k0 + 9, n), h1, m1, l1);
+        }
         uint2* o = dst + (size_t)t * 96 + lane;
         o[0] = make_uint2(h0, h1); o[32] = make_uint2(m0, m1); o[64] = make_uint2(l0, l1);
     }
@@ -191,6 +203,7 @@ __device__ __forceinline__ void kf_bn_finalize(const KfArgs& a, int l, int slice
         float2* mine = a.partials + ((size_t)(l * a.k + slice) * a.gs + j) * 48;
         kf_col_stats<C>(A, rows, red, mine);
         __syncthreads();
+        cstamp(27);
         unsigned* ctr = a.sync + l * a.k + slice;
         if (tid == 0) {
             __threadfence();
@@ -198,6 +211,7 @@ __device__ __forceinline__ void kf_bn_finalize(const KfArgs& a, int l, int slice
             kf_wait(ctr, (unsigned)a.gs, a.sync + 63);
         }
         __syncthreads();
+        cstamp(28);
         const float2* pbase = a.partials + (size_t)(l * a.k + slice) * a.gs * 48;
         const bool staged = kf_gather_partials<C>(pbase, a.gs, red);
         if (tid < C) {
@@ -287,6 +301,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_fwd_fused(const KfAr
                     __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.frames) + n * 1024) + (idx & 63));
             }
             __syncthreads();
+            cstamp(26);
             for (int f = warp; f < fc; f += KF_THREADS / 32) {
                 const uint8_t* fr = reinterpret_cast<const uint8_t*>(A1 + (size_t)f * 256);
                 float acc[2][4];
@@ -608,6 +623,22 @@ __device__ __forceinline__ void kb_bn_bwd(const KbArgs& a, int l, int slice, int
     __syncthreads();
 }
 
+// The backward products use two-term splits and the three leading partial products (bf16x3: ~5e-6 relative, the
+// accuracy of every other product of the engine); nothing downstream of them has a kink, unlike the forward
+// activations, and the legacy HMMA issue rate is what bounds these loops.
+__device__ __forceinline__ void kb_mma3r(float* acc, const uint32_t* ah, const uint32_t*, const uint32_t* al,
+                                         uint2 bh, uint2, uint2 bl) {
+    kf_mma(acc, al, bh.x, bh.y); kf_mma(acc, ah, bl.x, bl.y); kf_mma(acc, ah, bh.x, bh.y);
+}
+__device__ __forceinline__ void kb_mma3(float* acc, const uint32_t* ah, const uint32_t* am, const uint32_t* al,
+                                        const uint2* wf) {
+    kb_mma3r(acc, ah, am, al, wf[0], wf[32], wf[64]);
+}
+__device__ __forceinline__ void kb_bfrag(float v0, float v1, float v8, float v9, uint2& bh, uint2& bm, uint2& bl) {
+    kb_split2(v0, v1, bh.x, bm.x, bl.x);
+    kb_split2(v8, v9, bh.y, bm.y, bl.y);
+}
+
 __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbArgs a) {
     extern __shared__ __align__(16) float sm[];
     float* A1 = sm + KB_OFF_A1; float* D1 = sm + KB_OFF_D1;
@@ -653,8 +684,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     // ================= layer 3 =================
     kb_bn_bwd<48>(a, 2, slice, j, A3, D3, nfr, 1, red, misc, mypart + KB_P_B3);
     cstamp(2);
-    // The five products below are tiny GEMMs on mma.sync.m16n8k16 with exact three-way bf16 splits of both fp32
-    // operands (see the forward kernel; the FFMA forms were bound by shared-memory wavefronts and register spills:
+    // The five products below are tiny GEMMs on mma.sync.m16n8k16 with bf16 hi/lo splits of both fp32 operands
+    // (see the forward kernel; the FFMA forms were bound by shared-memory wavefronts and register spills:
     // 14 k / 13 k / 25 k / 32 k / 58 k cycles of 210 k).
     // dW3[(tap, ci)][co] = sum_f x2n[f][(tap, ci)] * dz3[f][co]: M = 128, N = 48, K = frames (zero padded);
     // warp = (16-row tile, three of the six 8-channel tiles)
@@ -667,17 +698,17 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         for (int fk = fc2; fk - fc2 < nfr; fk += 16) {     // frames fk, fk + 1, fk + 8, fk + 9 are this lane's k
             auto xa = [&](int f, int m, float sc, float sh) { return f < nfr ? fmaf(A2[(size_t)f * 128 + m], sc, sh) : 0.f; };
             uint32_t ah[4], am[4], al[4];
-            kf_split3(xa(fk, m_lo, sc_lo, sh_lo), xa(fk + 1, m_lo, sc_lo, sh_lo), ah[0], am[0], al[0]);
-            kf_split3(xa(fk, m_hi, sc_hi, sh_hi), xa(fk + 1, m_hi, sc_hi, sh_hi), ah[1], am[1], al[1]);
-            kf_split3(xa(fk + 8, m_lo, sc_lo, sh_lo), xa(fk + 9, m_lo, sc_lo, sh_lo), ah[2], am[2], al[2]);
-            kf_split3(xa(fk + 8, m_hi, sc_hi, sh_hi), xa(fk + 9, m_hi, sc_hi, sh_hi), ah[3], am[3], al[3]);
+            kb_split2(xa(fk, m_lo, sc_lo, sh_lo), xa(fk + 1, m_lo, sc_lo, sh_lo), ah[0], am[0], al[0]);
+            kb_split2(xa(fk, m_hi, sc_hi, sh_hi), xa(fk + 1, m_hi, sc_hi, sh_hi), ah[1], am[1], al[1]);
+            kb_split2(xa(fk + 8, m_lo, sc_lo, sh_lo), xa(fk + 9, m_lo, sc_lo, sh_lo), ah[2], am[2], al[2]);
+            kb_split2(xa(fk + 8, m_hi, sc_hi, sh_hi), xa(fk + 9, m_hi, sc_hi, sh_hi), ah[3], am[3], al[3]);
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int n = (nh + q) * 8 + fg;
                 auto dz = [&](int f) { return f < nfr ? D3[(size_t)f * 48 + n] : 0.f; };
                 uint2 bh, bm, bl;
-                kf_bfrag(dz(fk), dz(fk + 1), dz(fk + 8), dz(fk + 9), bh, bm, bl);
-                kf_mma6r(acc[q], ah, am, al, bh, bm, bl);
+                kb_bfrag(dz(fk), dz(fk + 1), dz(fk + 8), dz(fk + 9), bh, bm, bl);
+                kb_mma3r(acc[q], ah, am, al, bh, bm, bl);
             }
         }
 #pragma unroll
@@ -696,7 +727,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         uint2 bh[3], bm[3], bl[3];
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks)
-            kf_bfrag(__ldg(wrow + ks * 16), __ldg(wrow + ks * 16 + 1), __ldg(wrow + ks * 16 + 8), __ldg(wrow + ks * 16 + 9),
+            kb_bfrag(__ldg(wrow + ks * 16), __ldg(wrow + ks * 16 + 1), __ldg(wrow + ks * 16 + 8), __ldg(wrow + ks * 16 + 9),
                      bh[ks], bm[ks], bl[ks]);
         for (int f0 = 0; f0 < nfr; f0 += 16) {
             const int f_lo = f0 + fg, f_hi = f_lo + 8;
@@ -708,9 +739,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                 const float2 x0 = *reinterpret_cast<const float2*>(x_lo + ks * 16), x2 = *reinterpret_cast<const float2*>(x_lo + ks * 16 + 8);
                 const float2 x1 = *reinterpret_cast<const float2*>(x_hi + ks * 16), x3 = *reinterpret_cast<const float2*>(x_hi + ks * 16 + 8);
                 uint32_t ah[4], am[4], al[4];
-                kf_split3(x0.x, x0.y, ah[0], am[0], al[0]); kf_split3(x1.x, x1.y, ah[1], am[1], al[1]);
-                kf_split3(x2.x, x2.y, ah[2], am[2], al[2]); kf_split3(x3.x, x3.y, ah[3], am[3], al[3]);
-                kf_mma6r(acc, ah, am, al, bh[ks], bm[ks], bl[ks]);
+                kb_split2(x0.x, x0.y, ah[0], am[0], al[0]); kb_split2(x1.x, x1.y, ah[1], am[1], al[1]);
+                kb_split2(x2.x, x2.y, ah[2], am[2], al[2]); kb_split2(x3.x, x3.y, ah[3], am[3], al[3]);
+                kb_mma3r(acc, ah, am, al, bh[ks], bm[ks], bl[ks]);
             }
             if (f_lo < nfr) *reinterpret_cast<float2*>(D2 + (size_t)f_lo * 128 + warp * 8 + fc2) = make_float2(acc[0], acc[1]);
             if (f_hi < nfr) *reinterpret_cast<float2*>(D2 + (size_t)f_hi * 128 + warp * 8 + fc2) = make_float2(acc[2], acc[3]);
@@ -721,7 +752,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
     // ================= layer 2 =================
     {   // W2^T as B fragments for dy1: k = output channel, n = input channel, one pair of k16 steps per tap
         const float* w2 = a.L[1].w;
-        kf_build_frags<18, 2>(reinterpret_cast<uint2*>(Ws), [=](int ksx, int kk, int n) {
+        kf_build_frags<18, 2, false>(reinterpret_cast<uint2*>(Ws), [=](int ksx, int kk, int n) {
             return __ldg(w2 + ((ksx >> 1) * 16 + n) * 32 + (ksx & 1) * 16 + kk);
         });
     }
@@ -748,16 +779,16 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
             const bool a_ok = fA < nfr, b_ok = fB < nfr;
             const float* pA = xa0 + (size_t)fA * 256; const float* pB = xa0 + (size_t)fB * 256;
             uint32_t ah[4], am[4], al[4];
-            kf_split3(a_ok && v0 ? fmaf(pA[fg], sc_lo, sh_lo) : 0.f, a_ok && v1 ? fmaf(pA[32 + fg], sc_lo, sh_lo) : 0.f, ah[0], am[0], al[0]);
-            kf_split3(a_ok && v0 ? fmaf(pA[fg + 8], sc_hi, sh_hi) : 0.f, a_ok && v1 ? fmaf(pA[40 + fg], sc_hi, sh_hi) : 0.f, ah[1], am[1], al[1]);
-            kf_split3(b_ok && v0 ? fmaf(pB[fg], sc_lo, sh_lo) : 0.f, b_ok && v1 ? fmaf(pB[32 + fg], sc_lo, sh_lo) : 0.f, ah[2], am[2], al[2]);
-            kf_split3(b_ok && v0 ? fmaf(pB[fg + 8], sc_hi, sh_hi) : 0.f, b_ok && v1 ? fmaf(pB[40 + fg], sc_hi, sh_hi) : 0.f, ah[3], am[3], al[3]);
+            kb_split2(a_ok && v0 ? fmaf(pA[fg], sc_lo, sh_lo) : 0.f, a_ok && v1 ? fmaf(pA[32 + fg], sc_lo, sh_lo) : 0.f, ah[0], am[0], al[0]);
+            kb_split2(a_ok && v0 ? fmaf(pA[fg + 8], sc_hi, sh_hi) : 0.f, a_ok && v1 ? fmaf(pA[40 + fg], sc_hi, sh_hi) : 0.f, ah[1], am[1], al[1]);
+            kb_split2(b_ok && v0 ? fmaf(pB[fg], sc_lo, sh_lo) : 0.f, b_ok && v1 ? fmaf(pB[32 + fg], sc_lo, sh_lo) : 0.f, ah[2], am[2], al[2]);
+            kb_split2(b_ok && v0 ? fmaf(pB[fg + 8], sc_hi, sh_hi) : 0.f, b_ok && v1 ? fmaf(pB[40 + fg], sc_hi, sh_hi) : 0.f, ah[3], am[3], al[3]);
             const float* dA = D2 + (size_t)fA * 128 + oh * 64 + fg; const float* dB = D2 + (size_t)fB * 128 + oh * 64 + fg;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 uint2 bh, bm, bl;
-                kf_bfrag(a_ok ? dA[nt * 8] : 0.f, a_ok ? dA[32 + nt * 8] : 0.f, b_ok ? dB[nt * 8] : 0.f, b_ok ? dB[32 + nt * 8] : 0.f, bh, bm, bl);
-                kf_mma6r(acc[nt], ah, am, al, bh, bm, bl);
+                kb_bfrag(a_ok ? dA[nt * 8] : 0.f, a_ok ? dA[32 + nt * 8] : 0.f, b_ok ? dB[nt * 8] : 0.f, b_ok ? dB[32 + nt * 8] : 0.f, bh, bm, bl);
+                kb_mma3r(acc[nt], ah, am, al, bh, bm, bl);
             }
         }
 #pragma unroll
@@ -784,8 +815,8 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
         for (int ks = 0; ks < 2; ++ks) {
             const float2 x0 = *reinterpret_cast<const float2*>(x_lo + ks * 16), x2 = *reinterpret_cast<const float2*>(x_lo + ks * 16 + 8);
             const float2 x1 = *reinterpret_cast<const float2*>(x_hi + ks * 16), x3 = *reinterpret_cast<const float2*>(x_hi + ks * 16 + 8);
-            kf_split3(x0.x, x0.y, ah[ks][0], am[ks][0], al[ks][0]); kf_split3(x1.x, x1.y, ah[ks][1], am[ks][1], al[ks][1]);
-            kf_split3(x2.x, x2.y, ah[ks][2], am[ks][2], al[ks][2]); kf_split3(x3.x, x3.y, ah[ks][3], am[ks][3], al[ks][3]);
+            kb_split2(x0.x, x0.y, ah[ks][0], am[ks][0], al[ks][0]); kb_split2(x1.x, x1.y, ah[ks][1], am[ks][1], al[ks][1]);
+            kb_split2(x2.x, x2.y, ah[ks][2], am[ks][2], al[ks][2]); kb_split2(x3.x, x3.y, ah[ks][3], am[ks][3], al[ks][3]);
         }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -796,7 +827,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
-                    kf_mma6(acc, ah[ks], am[ks], al[ks], reinterpret_cast<const uint2*>(Ws) + (size_t)((tap * 2 + ks) * 2 + nt) * 96 + lane);
+                    kb_mma3(acc, ah[ks], am[ks], al[ks], reinterpret_cast<const uint2*>(Ws) + (size_t)((tap * 2 + ks) * 2 + nt) * 96 + lane);
                 if (ok && f_lo < nfr) {
                     float2* p = reinterpret_cast<float2*>(D1 + (size_t)f_lo * 256 + (ih * 4 + iw) * 16 + nt * 8 + fc2);
                     float2 v = *p; v.x += acc[0]; v.y += acc[1]; *p = v;
@@ -819,10 +850,11 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
             *reinterpret_cast<uint4*>(FR + (size_t)idx * 16) = __ldg(reinterpret_cast<const uint4*>(
                 static_cast<const uint8_t*>(a.frames) + frame_n(idx >> 6) * 1024 + (idx & 63) * 16));
     __syncthreads();
+    cstamp(12);
     // dW1[tap][ci][co] = sum_{f, opx} x0[f][ipx][ci] * dz1[f][opx][co]: per tap M = 16 ci, N = 16 co, K = (frame,
     // 16 output pixels), a k16 step = one frame.  warp = (one of 8 frame groups, taps 0-4 | 5-8): the dz1 fragments
     // of a frame are split once for the warp's taps; the 8 partial sets meet in shared memory in a fixed order.
-    // Frame bytes are exact in one bf16 term (three products); fp32 frames take the general six (the same
+    // Frame bytes are exact in one bf16 term (two products); fp32 frames take the general three (the same
     // non-zero products in the same order when the values are 0/1 planes: bit-identical).
     {
         const int kq = warp >> 1, t0 = (warp & 1) * 5, ntap = (warp & 1) ? 4 : 5, c = lane & 3;
@@ -838,7 +870,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
             const float* dz = D1 + (size_t)f * 256 + (oh * 4 + ow) * 16 + fg;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
-                kf_bfrag(dz[nt * 8], dz[16 + nt * 8], dz[128 + nt * 8], dz[144 + nt * 8], bh[nt], bm[nt], bl[nt]);
+                kb_bfrag(dz[nt * 8], dz[16 + nt * 8], dz[128 + nt * 8], dz[144 + nt * 8], bh[nt], bm[nt], bl[nt]);
             const size_t fbase = a.frames_u8 ? (size_t)f * 1024 : frame_n(f) * 1024;
 #pragma unroll
             for (int t = 0; t < 5; ++t) {
@@ -859,8 +891,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                         af[2] = kf_pack_exact(x[4], x[5]); af[3] = kf_pack_exact(x[6], x[7]);
 #pragma unroll
                         for (int nt = 0; nt < 2; ++nt) {
-                            kf_mma(acc[t][nt], af, bl[nt].x, bl[nt].y); kf_mma(acc[t][nt], af, bm[nt].x, bm[nt].y);
-                            kf_mma(acc[t][nt], af, bh[nt].x, bh[nt].y);
+                            kf_mma(acc[t][nt], af, bl[nt].x, bl[nt].y); kf_mma(acc[t][nt], af, bh[nt].x, bh[nt].y);
                         }
                     } else {
                         const float* q = ff + o;
@@ -870,9 +901,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                         x[6] = w0 && h1 ? __ldg(q + 520) : 0.f;  x[7] = w1 && h1 ? __ldg(q + 552) : 0.f;
                         uint32_t ah[4], am[4], al[4];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) kf_split3(x[2 * r], x[2 * r + 1], ah[r], am[r], al[r]);
+                        for (int r = 0; r < 4; ++r) kb_split2(x[2 * r], x[2 * r + 1], ah[r], am[r], al[r]);
 #pragma unroll
-                        for (int nt = 0; nt < 2; ++nt) kf_mma6r(acc[t][nt], ah, am, al, bh[nt], bm[nt], bl[nt]);
+                        for (int nt = 0; nt < 2; ++nt) kb_mma3r(acc[t][nt], ah, am, al, bh[nt], bm[nt], bl[nt]);
                     }
                 }
             }
@@ -889,6 +920,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) karel_conv_bwd_fused(const KbAr
                 }
     }
     __syncthreads();
+    cstamp(13);
     for (int idx = tid; idx < KF_W1 / 4; idx += KF_THREADS) {
         float4 sum = reinterpret_cast<const float4*>(A1)[idx];
 #pragma unroll

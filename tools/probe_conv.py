@@ -30,6 +30,7 @@ names = ['start', 'loads issued', 'layer-3 BN backward done', 'dW3 done', 'dy2 d
          'dy1 done', 'layer-1 BN backward done', 'dW1 done', 'grid barrier passed', 'partials reduced']
 for i, n in enumerate(names):
     print('%-28s +%d cycles' % (n, p[i] - p[0]))
+print('  (frames staged for dW1 +%d, dW1 products done +%d)' % (p[12] - p[0], p[13] - p[0]))
 
 lib.d2p_debug_set_probe(ptr(probe))
 fwd()
@@ -56,6 +57,9 @@ def timed(fn, n=50):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+q = probe.cpu().tolist()[96:]
+print('  (conv1 frames staged +%d; layer-3 exchange: statistics ready +%d, slice barrier passed +%d)' % (
+    q[26] - q[16], q[27] - q[16], q[28] - q[16]))
 print('fused: fwd %.1f us  bwd %.1f us' % (timed(fwd), timed(bwd)))
 lib.d2p_conv_set_fused(0)
 for mode in (0, 7):
