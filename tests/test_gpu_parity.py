@@ -545,7 +545,8 @@ def _run_variant(cfg, batch, fused, persistent, frames_dtype=np.uint8, is_train=
 @pytest.mark.parametrize('B,k,dtype,train', [(32, 10, np.uint8, True),     # C2: 140 CTAs, 2-3 demos each
                                              (4, 3, np.float32, True),     # fp32 frames as the reference feeds
                                              (5, 2, np.uint8, False),      # eval: moving statistics, no exchange
-                                             (40, 3, np.uint8, False)])    # eval, several 64-frame chunks per CTA
+                                             (40, 3, np.uint8, False),     # eval, several 64-frame chunks per CTA
+                                             (40, 1, np.uint8, True)])     # one slice over 40 CTAs: exchange partials read from L2
 def test_fused_conv_encoder_matches_layered(B, k, dtype, train):
     """The single-kernel Karel encoder forward (conv_fused.cu) against the per-layer kernels:
     features, saved activations / statistics, BatchNorm moving statistics, and the gradients the
