@@ -57,21 +57,22 @@ __device__ __forceinline__ float load_in(const IN_T* in, size_t idx) { return (f
 
 #include "conv_v2.cuh"
 // RGB input layer (CIN = 3, COUT = 16, u8 frames), forward: one thread per output pixel, the 27 x 16 weights as
-// broadcast float4 reads from shared memory, a = lrelu(conv + bias) written as one 64-byte row, and the
+// CONSTANT-BANK operands of the FMAs (copied device-to-device into c_rgb_w in front of the launch: `ncu --set full`
+// showed the former broadcast float4 reads from shared memory filling 92 % of the L1 data pipe - a broadcast LDS.128
+// still costs four wavefronts - while the FMA pipe sat at 32 %; profiles/r03s_ncu_full_c4_rgb_bn.txt),
+// a = lrelu(conv + bias) written as one 64-byte row, and the
 // BatchNorm (sum, sum of squares) of the block's pixels reduced in a fixed order into
 // partial[(slice*nchunk + chunk)*16 + c] (a block never straddles a demonstration, i.e. a slice).
 constexpr int RGB_THREADS = 256, RGB_PPT = 4;
+__constant__ float c_rgb_w[27 * 16];
+__constant__ float c_rgb_b[16];
 __global__ void __launch_bounds__(RGB_THREADS)
 conv_rgb_fwd_kernel(Geo g, const uint8_t* __restrict__ in, const float* __restrict__ W,
                     const float* __restrict__ bias, float* __restrict__ out, float2* __restrict__ partial,
                     int cpd, int nchunk) {
-    __shared__ float4 ws[27 * 4];
-    __shared__ float4 bs[4];
     __shared__ float red[RGB_THREADS / 32][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 27 * 4; i += RGB_THREADS) ws[i] = reinterpret_cast<const float4*>(W)[i];
-    if (tid < 4) bs[tid] = reinterpret_cast<const float4*>(bias)[tid];
-    __syncthreads();
+    (void)W; (void)bias;          // staged into c_rgb_w / c_rgb_b by the launcher
     const int r = blockIdx.x / cpd, j = blockIdx.x - r * cpd;
     const int HW = g.OH * g.OW, P = g.T * HW;
     const int q0 = j * (RGB_THREADS * RGB_PPT);
@@ -85,9 +86,7 @@ conv_rgb_fwd_kernel(Geo g, const uint8_t* __restrict__ in, const float* __restri
         const uint8_t* fin = in + (size_t)(r * g.T + t) * g.IH * g.IW * 3;
         float acc[16];
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            acc[4 * c4] = bs[c4].x; acc[4 * c4 + 1] = bs[c4].y; acc[4 * c4 + 2] = bs[c4].z; acc[4 * c4 + 3] = bs[c4].w;
-        }
+        for (int c = 0; c < 16; ++c) acc[c] = c_rgb_b[c];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = 2 * oy + ky - g.PT;
@@ -100,13 +99,8 @@ conv_rgb_fwd_kernel(Geo g, const uint8_t* __restrict__ in, const float* __restri
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     const float v = (float)__ldg(px + ci);
-                    const float4* w = ws + ((ky * 3 + kx) * 3 + ci) * 4;
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 ww = w[c4];
-                        acc[4 * c4] = fmaf(v, ww.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
-                        acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
-                    }
+                    for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, c_rgb_w[((ky * 3 + kx) * 3 + ci) * 16 + c], acc[c]);
                 }
             }
         }
@@ -407,6 +401,8 @@ extern "C" int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, 
             // RGB input layer: direct kernel with the BatchNorm partial sums fused
             const int cpd = rgb_cpd(g), nchunk = (g.N / g.T / g.k) * cpd;
             float2* partial = training ? (float2*)(wsb + p.off_tc) : nullptr;
+            D2P_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_rgb_w, L.w, sizeof(float) * 27 * 16, 0, cudaMemcpyDeviceToDevice, st));
+            D2P_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_rgb_b, L.b, sizeof(float) * 16, 0, cudaMemcpyDeviceToDevice, st));
             conv_rgb_fwd_kernel<<<(g.N / g.T) * cpd, RGB_THREADS, 0, st>>>(g, (const uint8_t*)frames, L.w, L.b, act,
                                                                          partial, cpd, nchunk);
             D2P_CHECK_LAUNCH();
