@@ -74,7 +74,10 @@ typedef struct {
 size_t d2p_conv_encoder_saved_floats(const d2p_conv_desc* d);
 size_t d2p_conv_encoder_ws_bytes(const d2p_conv_desc* d);
 int d2p_conv_encoder_feature_dim(const d2p_conv_desc* d);
-/* feat: [T, R, F] time-major. training != 0: batch statistics + moving update. */
+/* feat: [T, R, F] time-major. training != 0: batch statistics + moving update.
+ * The RGB input layer of u8 frames (d = 3, first layer 16 channels: ViZDoom) stages its weights in ONE
+ * __constant__ symbol of the library in front of its kernel: calls for such descriptors must not overlap on
+ * different streams of the same process (one process per GPU, as everywhere here, is unaffected). */
 int d2p_conv_encoder_fwd(const d2p_conv_desc* d, const void* frames, float* feat, float* saved,
                          int training, void* ws, size_t ws_bytes, void* stream);
 int d2p_conv_encoder_bwd(const d2p_conv_desc* d, const void* frames, const float* dfeat,
