@@ -45,3 +45,19 @@ def test_our_arm_needs_a_gpu():
         pytest.skip('a CUDA device is present')
     r = _run(['--steps', '1', '--warmup', '0'])
     assert r.returncode != 0 and r.stdout.strip() == ''
+
+
+def test_roofline_traffic_comes_from_the_committed_capture(tmp_path):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel,
+    taken from the committed `ncu --set full` summary through profiles/ncu_traffic.json (tools/ncu_traffic.py)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench
+    import ncu_traffic
+    traffic, source = bench.ncu_traffic('lstm_persist_fwd')
+    assert source and os.path.exists(os.path.join(ROOT, source))
+    parsed = ncu_traffic.parse(os.path.join(ROOT, source))
+    rec = [v for k, v in parsed.items() if 'lstm_persist_fwd' in k][0]
+    assert traffic == rec['dram_bytes_per_launch'] == rec['dram_read'] + rec['dram_write']
+    assert 1e6 < traffic < 1e9          # tens of MB per launch: weights once + gates / cells / Y of 20 steps
+    assert bench.ncu_traffic('no_such_kernel') == (None, None)
