@@ -221,6 +221,14 @@ class Dataset(object):
             return arr[()] if self.shape == () else arr
         return arr[key]
 
+    def stored(self):
+        """The dataset in its STORED element type, without the bool / byte-order conversion copies of
+        [()] (an enum(bool) dataset comes back as its 0/1 bytes): a zero-copy view of the memory-mapped
+        file for contiguous and compact layouts.  For bulk consumers that convert while they copy."""
+        if self._dt.vlen_str:
+            return self._read()
+        return self._raw().reshape(self.shape)
+
     def __array__(self, dtype=None, copy=None):
         a = np.asarray(self._read())
         return a.astype(dtype) if dtype is not None else a

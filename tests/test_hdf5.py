@@ -204,6 +204,52 @@ def test_vizdoom_dataset_directory(tmp_path):
     b = ds.collate(tr, tr.ids[:2])
     assert b['s_h'].dtype == np.uint8 and b['init_pos'].shape == (2, num_k, 2, PL, 2)
     assert set(ds.VIZDOOM_EXTRA_KEYS) <= set(b)
+    _same_batches(b, ds.collate(tr, tr.ids[:2], fast=False))      # direct fill == get_data + stack + astype
+
+
+def _same_batches(x, y):
+    assert set(x) == set(y)
+    for key in x:
+        assert x[key].dtype == y[key].dtype and x[key].shape == y[key].shape, key
+        assert np.array_equal(x[key], y[key]), key
+
+
+def test_direct_fill_collate_equals_get_data_stack(tmp_path):
+    """collate()'s default path for the HDF5 datasets (_fast_collate: batch arrays filled straight from the
+    memory-mapped file, stored-array views cached per example) against the general path over the
+    golden-pinned get_data: same keys, shapes, dtypes and bytes - first touch and cached, every --num_k."""
+    from demo2program_b200 import dataset as ds
+    d = str(tmp_path / 'karel_fast')
+    ds.write_karel_dataset(d, 10, 3, 2, 5, test_k=3, seed=11)
+    for num_k in (5, 2, 7):            # 7 > stored demos: the prefix is everything stored
+        tr, te, _ = ds.create_default_splits(d, num_k=num_k)
+        for split in (tr, te):
+            for rep in range(2):       # second pass: cached views
+                for lst in (split.ids[:3], split.ids[1:2], list(reversed(split.ids))):
+                    _same_batches(ds.collate(split, lst), ds.collate(split, lst, fast=False))
+        assert tr._stored_views and len(tr._stored_views) <= len(tr.ids)
+
+
+def test_loader_processes_without_the_parent_copy(tmp_path):
+    """batches(..., workers=2, copy=False): the same batches in the same order when every batch is consumed
+    on receipt (what the trainer does), and a yielded batch stays intact while ONE more batch is requested
+    (its shared-memory slot is recycled only with the second further request)."""
+    from demo2program_b200 import dataset as ds
+    d = str(tmp_path / 'karel_nocopy')
+    ds.write_karel_dataset(d, 24, 2, 2, 3, test_k=2, seed=9)
+    tr, _, _ = ds.create_default_splits(d, num_k=3)
+    want = list(ds.batches(tr, 4, shuffle=True, seed=2, epochs=2))
+    got, prev = [], None
+    for b in ds.batches(tr, 4, shuffle=True, seed=2, epochs=2, workers=2, copy=False, lookahead=2):
+        snap = {k: np.array(v, copy=True) for k, v in b.items()}
+        if prev is not None:           # the previous batch's windows are still what they were
+            for k in prev[0]:
+                assert np.array_equal(prev[0][k], prev[1][k]), k
+        prev = (b, snap)
+        got.append(snap)
+    assert len(got) == len(want) == 12
+    for x, y in zip(got, want):
+        _same_batches(x, y)
 
 
 def test_karel_loader_matches_reference_loader_golden(tmp_path):

@@ -51,7 +51,8 @@ class Trainer(object):
         # data parallelism: rank r draws its batches from ids[r::world] (no example twice per epoch)
         self.batch_train = batches(dataset, self.batch_size, shuffle=True, seed=config.rank,
                                    workers=getattr(config, 'loader_workers', 0),
-                                   rank=config.rank, world=config.world_size)
+                                   rank=config.rank, world=config.world_size,
+                                   copy=False)      # every batch is staged into pinned memory on receipt
         self.batch_test = batches(dataset_test, self.batch_size, shuffle=False)
         Model = self.get_model_class(config.model)
         log.info("Using Model class: %s", Model)
