@@ -306,3 +306,37 @@ def test_action_one_hots_equal_the_reference_loop():
         assert np.array_equal(tok, np.argmax(ref, axis=2))
     with pytest.raises(IndexError):
         _action_one_hots(np.zeros((2, T), np.int64), T, A)
+
+
+def test_rank_shards_are_disjoint_and_cover_the_split(tmp_path):
+    """batches(rank=r, world=W): rank r draws from ids[r::W] - no example twice per epoch across the ranks,
+    every example in exactly one shard; a shard smaller than the batch size fails at the first next()."""
+    import pytest
+    from demo2program_b200 import dataset as ds
+    d = str(tmp_path / 'karel_shards')
+    ds.write_karel_dataset(d, 16, 2, 2, 3, test_k=2, seed=21)
+    tr, _, _ = ds.create_default_splits(d, num_k=3)
+    seen = []
+    for r in range(2):
+        mine = []
+        for b in ds.batches(tr, 4, shuffle=True, seed=r, epochs=1, rank=r, world=2):
+            mine += [x.decode() for x in b['id']]
+        assert len(mine) == 8 and len(set(mine)) == 8 and set(mine) == set(tr.ids[r::2])
+        seen += mine
+    assert sorted(seen) == sorted(tr.ids)
+    with pytest.raises(ValueError, match='fewer than batch_size'):
+        next(ds.batches(tr, 4, rank=0, world=8))        # 2 examples per shard
+
+
+def test_stored_views_are_zero_copy_windows_of_the_file(tmp_path):
+    """hdf5_lite.Dataset.stored(): enum(bool) datasets come back as their 0/1 bytes (int8, h5py's enum base type), integers in their stored
+    width, both as windows of the memory map (no copy) for contiguous layouts; [()] converts as before."""
+    d = tmp_path / 'v.h5'
+    frames = np.random.RandomState(0).rand(3, 4, 5) > 0.5
+    hdf5_lite.write_hdf5(str(d), {'g': {'b': frames, 'i': np.arange(6, dtype=np.int16).reshape(2, 3)}})
+    f = hdf5_lite.File(str(d))
+    sb, si = f['g']['b'].stored(), f['g']['i'].stored()
+    assert sb.dtype == np.int8 and sb.shape == frames.shape and np.array_equal(sb, frames.astype(np.int8))   # h5py's enum base
+    assert si.dtype == np.int16 and np.array_equal(si, np.arange(6).reshape(2, 3))
+    assert not sb.flags.owndata and not sb.flags.writeable and not si.flags.owndata
+    assert f['g']['b'][()].dtype == np.bool_ and np.array_equal(f['g']['b'][()], frames)
