@@ -417,6 +417,30 @@ def test_tf_checkpoint_resume_is_bitwise(tmp_path):
         tfc.load_model(prefix, c)
 
 
+def test_cli_trainer_with_loader_processes(tmp_path, monkeypatch, caplog):
+    """trainer.py --loader_workers 2: batches assembled in forked loader processes (forked after the CUDA
+    context exists; the children only run NumPy) and handed over without the parent copy - the logged
+    losses equal those of the inline loader, step for step."""
+    import logging
+    import re
+    import trainer
+    from demo2program_b200 import dataset as ds
+    monkeypatch.chdir(tmp_path)
+    d = str(tmp_path / 'karel_ds')
+    ds.write_karel_dataset(d, 24, 8, 8, 4, test_k=2, seed=13)
+    losses = {}
+    for w in (0, 2):
+        caplog.clear()
+        # the split shuffle draws from a module-level RandomState (reference dataset_karel.py:11): same start for both
+        monkeypatch.setattr(ds, 'rs', np.random.RandomState(123))
+        with caplog.at_level(logging.INFO):
+            trainer.main(['--model', 'summarizer', '--dataset_path', d, '--num_k', '3', '--batch_size', '4',
+                          '--max_steps', '5', '--log_step', '1', '--test_sample_step', '100',
+                          '--loader_workers', str(w), '--prefix', 'w%d' % w])
+        losses[w] = [float(m) for m in re.findall(r'\[train step\s+\d+\] Loss: ([0-9.]+)', caplog.text)]
+    assert len(losses[0]) >= 4 and losses[0] == losses[2], losses
+
+
 def test_cli_trainer_on_hdf5_dataset_directory(tmp_path, monkeypatch):
     """trainer.py --dataset_path <dir with data.hdf5 + id.txt> (the generator's schema), read by
     the package's HDF5 reader: the first logged loss equals the loss of the same examples fed
