@@ -274,6 +274,7 @@ KEYS = ('program', 'program_tokens', 's_h', 'test_s_h', 'a_h', 'a_h_tokens', 'te
 VIZDOOM_EXTRA_KEYS = ('init_pos', 'init_pos_len', 'test_init_pos', 'test_init_pos_len')
 
 
+_LOADER_TIMEOUT_S = 600         # a forked loader process that hangs fails the run instead of stalling it
 _VIEW_CACHE_MAX = 1 << 18      # examples whose stored-array views are kept per dataset object (~1 KB each)
 
 
@@ -488,7 +489,10 @@ def batches(dataset, batch_size, shuffle=True, seed=0, epochs=None, workers=0, l
     held = collections.deque()     # copy=False: slots of the last two yielded batches
 
     def finish(res):
-        slot, meta, b = res.get()
+        try:
+            slot, meta, b = res.get(timeout=_LOADER_TIMEOUT_S)
+        except mp.TimeoutError:
+            raise RuntimeError('a loader process did not deliver its batch within %d s' % _LOADER_TIMEOUT_S)
         buf = _WORKER_SLOTS[slot]
         for key, (off, shape, dt) in meta.items():
             n = int(np.prod(shape)) * np.dtype(dt).itemsize

@@ -417,6 +417,7 @@ def test_tf_checkpoint_resume_is_bitwise(tmp_path):
         tfc.load_model(prefix, c)
 
 
+@pytest.mark.timeout(180)
 def test_cli_trainer_with_loader_processes(tmp_path, monkeypatch, caplog):
     """trainer.py --loader_workers 2: batches assembled in forked loader processes (forked after the CUDA
     context exists; the children only run NumPy) and handed over without the parent copy - the logged
